@@ -1,0 +1,1147 @@
+// api.cu — C ABI of libfetalb200.so (see include/fetal_b200.h): context, the plain 3D U-Net
+// (fetal_net/model/unet3d/unet.py:40-70) as a static launch plan over the kernels in conv_tc.cu /
+// conv_simt.cu / bandwidth.cu, the training step (forward, soft-Dice, backward, Keras-Adam) and the
+// patch-wise sliding-window inference (fetal_net/prediction.py:118-210).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error string (per thread)
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void fm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* fm_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int fm_ctx_create(int device, fm_ctx** out) {
+  FM_CHECK(out != nullptr, FM_EINVAL, "fm_ctx_create: out is NULL");
+  int count = 0;
+  FM_CUDA(cudaGetDeviceCount(&count));
+  FM_CHECK(device >= 0 && device < count, FM_EINVAL, "fm_ctx_create: device %d of %d", device, count);
+  FM_CUDA(cudaSetDevice(device));
+  fm_ctx* ctx = new fm_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  FM_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_major = prop.major;
+  ctx->sm_minor = prop.minor;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    fm_set_error("fetalb200 is built for sm_100a only; device %d is sm_%d%d (%s)", device, prop.major,
+                 prop.minor, prop.name);
+    delete ctx;
+    return FM_ECUDA;
+  }
+  FM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  FM_CUDA(cudaMalloc((void**)&ctx->red_scratch, 1024 * 8 * sizeof(double)));
+  *out = ctx;
+  return FM_OK;
+}
+
+extern "C" int fm_ctx_destroy(fm_ctx* ctx) {
+  if (!ctx) return FM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return FM_OK;
+}
+
+extern "C" int fm_ctx_device_info(fm_ctx* ctx, int out[3]) {
+  FM_CHECK(ctx && out, FM_EINVAL, "fm_ctx_device_info: NULL argument");
+  out[0] = ctx->sm_major;
+  out[1] = ctx->sm_minor;
+  out[2] = ctx->num_sms;
+  return FM_OK;
+}
+extern "C" uint64_t fm_ctx_stream(fm_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+extern "C" int fm_ctx_synchronize(fm_ctx* ctx) {
+  FM_CHECK(ctx, FM_EINVAL, "fm_ctx_synchronize: NULL ctx");
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FM_OK;
+}
+extern "C" int64_t fm_ctx_launch_count(fm_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->pinned_bytes < bytes) {
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    FM_CUDA(cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+  }
+  *out = ctx->pinned;
+  return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device-buffer helper
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t count) {
+    if (count <= n) return FM_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      fm_set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      return FM_ENOMEM;
+    }
+    n = count;
+    return FM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------
+struct Layer {
+  char name[32];
+  int c1, c2, cout, k;  // c2 > 0: second (skip) source of a concat
+  int level;            // resolution level (0 = full)
+  int64_t w_off, b_off; // offsets in the flat fp32 parameter buffer (kernel packed [Cout][taps][Cin])
+  bf16 *w_f = nullptr, *w_d0 = nullptr, *w_d1 = nullptr;  // bf16 packs (fprop, dgrad per source)
+  int cin() const { return c1 + c2; }
+  int taps() const { return k * k * k; }
+  int64_t wcount() const { return (int64_t)cout * taps() * cin(); }
+};
+
+struct fm_model {
+  fm_ctx* ctx = nullptr;
+  fm_unet3d_spec spec;
+  std::vector<Layer> layers;  // Keras creation order
+  int64_t nparams = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  bf16* wpack = nullptr;  // arena for all bf16 packs
+  int iterations = 0;
+  bool packs_dirty = true;
+
+  // activations, allocated for `cap` samples
+  int cap = 0;
+  bool train_alloc = false;
+  DevBuf<float> x_in, t_in, prob, dz;
+  std::vector<DevBuf<bf16>> encA, encB, pool, up, decA, decB;          // forward
+  std::vector<DevBuf<bf16>> gEncA, gEncB, gPool, gUp, gSkip, gDecA, gDecB;  // gradients
+  double* sums = nullptr;  // 8 doubles (device)
+  double sums_host[8];
+
+  // backward bucket events (one per layer, reverse creation order)
+  std::vector<cudaEvent_t> layer_done;
+  std::vector<std::pair<int, int>> buckets;  // [first layer, last layer] inclusive, creation order
+  cudaEvent_t ev_tmp = nullptr;
+  int last_batch = 0;
+  bool fwd_valid = false;
+
+  int depth() const { return spec.depth; }
+  Dims5 dims(int level, int C, int B) const {
+    return Dims5{B, spec.X >> level, spec.Y >> level, spec.Z >> level, C};
+  }
+  int64_t vox(int level) const {
+    return (int64_t)(spec.X >> level) * (spec.Y >> level) * (spec.Z >> level);
+  }
+};
+
+static int layer_index(fm_model* m, const char* name) {
+  for (size_t i = 0; i < m->layers.size(); ++i)
+    if (strcmp(m->layers[i].name, name) == 0) return (int)i;
+  return -1;
+}
+static Layer& L(fm_model* m, const char* fmt, int d) {
+  char nm[32];
+  snprintf(nm, sizeof(nm), fmt, d);
+  return m->layers[layer_index(m, nm)];
+}
+
+extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out) {
+  FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_unet3d: NULL argument");
+  FM_CHECK(spec->depth >= 2 && spec->depth <= 6, FM_EINVAL, "depth %d unsupported", spec->depth);
+  FM_CHECK(spec->in_channels == 1, FM_EINVAL,
+           "in_channels=%d: only the reference's single-modality path (1) is built", spec->in_channels);
+  FM_CHECK(spec->n_labels == 1, FM_EINVAL, "n_labels=%d: only 1 is built", spec->n_labels);
+  FM_CHECK(spec->n_base_filters == 16 || spec->n_base_filters == 32, FM_EINVAL,
+           "n_base_filters=%d: 16 or 32", spec->n_base_filters);
+  const int div = 1 << (spec->depth - 1);
+  FM_CHECK(spec->X > 0 && spec->Y > 0 && spec->Z > 0 && spec->X % div == 0 && spec->Y % div == 0 &&
+               spec->Z % div == 0,
+           FM_EINVAL, "input extent %dx%dx%d must be divisible by 2^(depth-1)=%d (unet3d/unet.py:32-33)",
+           spec->X, spec->Y, spec->Z, div);
+  FM_CUDA(cudaSetDevice(ctx->device));
+  fm_model* m = new fm_model();
+  m->ctx = ctx;
+  m->spec = *spec;
+  const int D = spec->depth, nf = spec->n_base_filters;
+  auto add = [&](const char* fmt, int d, int c1, int c2, int cout, int k, int level) {
+    Layer l;
+    memset(l.name, 0, sizeof(l.name));
+    snprintf(l.name, sizeof(l.name), fmt, d);
+    l.c1 = c1;
+    l.c2 = c2;
+    l.cout = cout;
+    l.k = k;
+    l.level = level;
+    l.w_off = m->nparams;
+    m->nparams += l.wcount();
+    l.b_off = m->nparams;
+    m->nparams += cout;
+    // keep every layer's block 16-byte aligned for the vectorised Adam / allreduce views
+    m->nparams = (m->nparams + 3) & ~(int64_t)3;
+    m->layers.push_back(l);
+  };
+  int c = spec->in_channels;
+  std::vector<int> skipc;
+  for (int d = 0; d < D; ++d) {
+    const int f1 = nf << d, f2 = f1 * 2;
+    add("enc%da", d, c, 0, f1, 3, d);
+    add("enc%db", d, f1, 0, f2, 3, d);
+    skipc.push_back(f2);
+    c = f2;
+  }
+  for (int d = D - 2; d >= 0; --d) {
+    add("dec%da", d, c, skipc[d], skipc[d], 3, d);  // concat order [up, skip] (unet.py:61)
+    add("dec%db", d, skipc[d], 0, skipc[d], 3, d);
+    c = skipc[d];
+  }
+  add("final", 0, c, 0, spec->n_labels, 1, 0);
+
+  const size_t pb = (size_t)m->nparams * sizeof(float);
+  FM_CUDA(cudaMalloc((void**)&m->params, pb));
+  FM_CUDA(cudaMalloc((void**)&m->grads, pb));
+  FM_CUDA(cudaMalloc((void**)&m->adam_m, pb));
+  FM_CUDA(cudaMalloc((void**)&m->adam_v, pb));
+  FM_CUDA(cudaMemset(m->params, 0, pb));
+  FM_CUDA(cudaMemset(m->grads, 0, pb));
+  FM_CUDA(cudaMemset(m->adam_m, 0, pb));
+  FM_CUDA(cudaMemset(m->adam_v, 0, pb));
+  // bf16 packs: fprop + dgrad copies of every kernel
+  int64_t pack_elems = 0;
+  for (auto& l : m->layers) pack_elems += 2 * ((l.wcount() + 63) & ~(int64_t)63);
+  FM_CUDA(cudaMalloc((void**)&m->wpack, (size_t)pack_elems * sizeof(bf16)));
+  FM_CUDA(cudaMemset(m->wpack, 0, (size_t)pack_elems * sizeof(bf16)));
+  bf16* wp = m->wpack;
+  for (auto& l : m->layers) {
+    const int64_t padded = (l.wcount() + 63) & ~(int64_t)63;
+    l.w_f = wp;
+    wp += padded;
+    l.w_d0 = wp;
+    l.w_d1 = wp + (int64_t)l.c1 * l.taps() * l.cout;
+    wp += padded;
+  }
+  FM_CUDA(cudaMalloc((void**)&m->sums, 8 * sizeof(double)));
+  FM_CUDA(cudaMemset(m->sums, 0, 8 * sizeof(double)));
+  m->encA.resize(D);
+  m->encB.resize(D);
+  m->pool.resize(D);
+  m->up.resize(D);
+  m->decA.resize(D);
+  m->decB.resize(D);
+  m->gEncA.resize(D);
+  m->gEncB.resize(D);
+  m->gPool.resize(D);
+  m->gUp.resize(D);
+  m->gSkip.resize(D);
+  m->gDecA.resize(D);
+  m->gDecB.resize(D);
+  m->layer_done.resize(m->layers.size());
+  for (auto& e : m->layer_done) FM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  FM_CUDA(cudaEventCreateWithFlags(&m->ev_tmp, cudaEventDisableTiming));
+  // gradient buckets: consecutive layers in backward (= reverse creation) order, ~1/4 of the
+  // parameters each; every bucket is one contiguous range of the flat buffer.
+  {
+    const int nl = (int)m->layers.size();
+    const int64_t target = m->nparams / 4 + 1;
+    int hi = nl - 1;
+    int64_t acc = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      acc += m->layers[i].wcount() + m->layers[i].cout;
+      if (acc >= target || i == 0) {
+        m->buckets.push_back({i, hi});
+        hi = i - 1;
+        acc = 0;
+      }
+    }
+  }
+  *out = m;
+  return FM_OK;
+}
+
+extern "C" int fm_model_destroy(fm_model* m) {
+  if (!m) return FM_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  cudaFree(m->params);
+  cudaFree(m->grads);
+  cudaFree(m->adam_m);
+  cudaFree(m->adam_v);
+  cudaFree(m->wpack);
+  cudaFree(m->sums);
+  m->x_in.release();
+  m->t_in.release();
+  m->prob.release();
+  m->dz.release();
+  for (auto* v : {&m->encA, &m->encB, &m->pool, &m->up, &m->decA, &m->decB, &m->gEncA, &m->gEncB,
+                  &m->gPool, &m->gUp, &m->gSkip, &m->gDecA, &m->gDecB})
+    for (auto& b : *v) b.release();
+  for (auto& e : m->layer_done) cudaEventDestroy(e);
+  if (m->ev_tmp) cudaEventDestroy(m->ev_tmp);
+  delete m;
+  return FM_OK;
+}
+
+extern "C" int fm_model_num_layers(fm_model* m) { return m ? (int)m->layers.size() : -1; }
+extern "C" int64_t fm_model_num_params(fm_model* m) {
+  if (!m) return -1;
+  int64_t n = 0;
+  for (auto& l : m->layers) n += l.wcount() + l.cout;
+  return n;
+}
+extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_t info[5]) {
+  FM_CHECK(m && layer >= 0 && layer < (int)m->layers.size(), FM_EINVAL, "layer %d out of range", layer);
+  const Layer& l = m->layers[layer];
+  if (name) memcpy(name, l.name, 32);
+  if (info) {
+    info[0] = l.cin();
+    info[1] = l.cout;
+    info[2] = l.k;
+    info[3] = l.w_off;
+    info[4] = l.b_off;
+  }
+  return FM_OK;
+}
+
+// Keras layout (k0,k1,k2,Cin,Cout) <-> packed [Cout][tap=(k0*K+k1)*K+k2][Cin]
+static void keras_to_packed(const float* kern, float* packed, int K, int Cin, int Cout) {
+  const int taps = K * K * K;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int co = 0; co < Cout; ++co)
+        packed[((int64_t)co * taps + tap) * Cin + ci] = kern[((int64_t)tap * Cin + ci) * Cout + co];
+}
+static void packed_to_keras(const float* packed, float* kern, int K, int Cin, int Cout) {
+  const int taps = K * K * K;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int co = 0; co < Cout; ++co)
+        kern[((int64_t)tap * Cin + ci) * Cout + co] = packed[((int64_t)co * taps + tap) * Cin + ci];
+}
+
+extern "C" int fm_model_set_weights(fm_model* m, int layer, const float* kernel, const float* bias) {
+  FM_CHECK(m && layer >= 0 && layer < (int)m->layers.size() && kernel && bias, FM_EINVAL,
+           "fm_model_set_weights: bad argument");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  Layer& l = m->layers[layer];
+  std::vector<float> packed((size_t)l.wcount());
+  keras_to_packed(kernel, packed.data(), l.k, l.cin(), l.cout);
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  FM_CUDA(cudaMemcpy(m->params + l.w_off, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  FM_CUDA(cudaMemcpy(m->params + l.b_off, bias, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
+  m->packs_dirty = true;
+  return FM_OK;
+}
+static int get_flat(fm_model* m, const float* flat, int layer, float* kernel, float* bias) {
+  FM_CHECK(m && layer >= 0 && layer < (int)m->layers.size(), FM_EINVAL, "layer %d out of range", layer);
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  Layer& l = m->layers[layer];
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  if (kernel) {
+    std::vector<float> packed((size_t)l.wcount());
+    FM_CUDA(cudaMemcpy(packed.data(), flat + l.w_off, packed.size() * 4, cudaMemcpyDeviceToHost));
+    packed_to_keras(packed.data(), kernel, l.k, l.cin(), l.cout);
+  }
+  if (bias) FM_CUDA(cudaMemcpy(bias, flat + l.b_off, (size_t)l.cout * 4, cudaMemcpyDeviceToHost));
+  return FM_OK;
+}
+extern "C" int fm_model_get_weights(fm_model* m, int layer, float* kernel, float* bias) {
+  return get_flat(m, m ? m->params : nullptr, layer, kernel, bias);
+}
+extern "C" int fm_model_get_grads(fm_model* m, int layer, float* kernel, float* bias) {
+  return get_flat(m, m ? m->grads : nullptr, layer, kernel, bias);
+}
+extern "C" int fm_model_reset_optimizer(fm_model* m) {
+  FM_CHECK(m, FM_EINVAL, "NULL model");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  const size_t pb = (size_t)m->nparams * sizeof(float);
+  FM_CUDA(cudaMemsetAsync(m->adam_m, 0, pb, m->ctx->stream));
+  FM_CUDA(cudaMemsetAsync(m->adam_v, 0, pb, m->ctx->stream));
+  m->iterations = 0;
+  return FM_OK;
+}
+
+static int refresh_packs(fm_model* m) {
+  if (!m->packs_dirty) return FM_OK;
+  for (auto& l : m->layers) {
+    if (l.k == 1 && l.cout == 1) continue;  // head reads fp32 weights directly
+    FM_TRY(k_repack_weights(m->ctx, m->params + l.w_off, l.w_f, l.w_d0, l.c2 ? l.w_d1 : nullptr, l.cout,
+                            l.taps(), l.c1, l.c2));
+  }
+  m->packs_dirty = false;
+  return FM_OK;
+}
+
+static int ensure_capacity(fm_model* m, int B, bool train) {
+  if (B <= m->cap && (!train || m->train_alloc)) return FM_OK;
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  const int cap = std::max(B, m->cap);
+  const int D = m->depth();
+  const size_t v0 = (size_t)m->vox(0);
+  FM_TRY(m->x_in.ensure((size_t)cap * v0 * m->spec.in_channels));
+  FM_TRY(m->prob.ensure((size_t)cap * v0));
+  for (int d = 0; d < D; ++d) {
+    const size_t v = (size_t)m->vox(d) * cap;
+    const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
+    FM_TRY(m->encA[d].ensure(v * la.cout));
+    FM_TRY(m->encB[d].ensure(v * lb.cout));
+    if (d < D - 1) {
+      FM_TRY(m->pool[d].ensure((size_t)m->vox(d + 1) * cap * lb.cout));
+      const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
+      FM_TRY(m->up[d].ensure(v * da.c1));
+      FM_TRY(m->decA[d].ensure(v * da.cout));
+      FM_TRY(m->decB[d].ensure(v * db.cout));
+    }
+  }
+  if (train || m->train_alloc) {
+    FM_TRY(m->t_in.ensure((size_t)cap * v0));
+    FM_TRY(m->dz.ensure((size_t)cap * v0));
+    for (int d = 0; d < D; ++d) {
+      const size_t v = (size_t)m->vox(d) * cap;
+      const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
+      FM_TRY(m->gEncA[d].ensure(v * la.cout));
+      FM_TRY(m->gEncB[d].ensure(v * lb.cout));
+      if (d < D - 1) {
+        FM_TRY(m->gPool[d].ensure((size_t)m->vox(d + 1) * cap * lb.cout));
+        const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
+        FM_TRY(m->gUp[d].ensure(v * da.c1));
+        FM_TRY(m->gSkip[d].ensure(v * da.c2));
+        FM_TRY(m->gDecA[d].ensure(v * da.cout));
+        FM_TRY(m->gDecB[d].ensure(v * db.cout));
+      }
+    }
+    m->train_alloc = true;
+  }
+  m->cap = cap;
+  return FM_OK;
+}
+
+// conv block forward: Conv3D + bias + ReLU (create_convolution_block, unet.py:102-113)
+static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2, bf16* y, int B) {
+  fm_ctx* ctx = m->ctx;
+  const Dims5 d = m->dims(l.level, l.cout, B);
+  const float* bias = m->params + l.b_off;
+  if (conv_tc_supported(l.c1, l.c2, l.cout, l.k))
+    return k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout,
+                             l.k, 1, l.cout, 0);
+  return k_conv3d_simt_fprop(ctx, x1, 0, x2, l.w_f, bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2,
+                             l.cout, l.k, 1, nullptr);
+}
+
+// forward pass on x_in (fp32 [B, X, Y, Z], C = 1) -> prob (fp32 [B, X, Y, Z])
+static int forward(fm_model* m, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int D = m->depth();
+  FM_TRY(refresh_packs(m));
+  const bf16* cur = nullptr;
+  for (int d = 0; d < D; ++d) {
+    const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
+    const Dims5 dd = m->dims(d, la.cout, B);
+    if (d == 0) {
+      FM_TRY(k_conv3d_simt_fprop(ctx, m->x_in.p, 1, nullptr, la.w_f, m->params + la.b_off, m->encA[0].p,
+                                 nullptr, B, dd.X, dd.Y, dd.Z, la.c1, 0, la.cout, la.k, 1, nullptr));
+    } else {
+      FM_TRY(conv_fwd(m, la, cur, nullptr, m->encA[d].p, B));
+    }
+    FM_TRY(conv_fwd(m, lb, m->encA[d].p, nullptr, m->encB[d].p, B));
+    cur = m->encB[d].p;
+    if (d < D - 1) {
+      FM_TRY(k_maxpool3d_fwd(ctx, m->encB[d].p, m->pool[d].p, m->dims(d, lb.cout, B)));
+      cur = m->pool[d].p;
+    }
+  }
+  for (int d = D - 2; d >= 0; --d) {
+    const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
+    FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B)));
+    FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
+    FM_TRY(conv_fwd(m, db, m->decA[d].p, nullptr, m->decB[d].p, B));
+    cur = m->decB[d].p;
+  }
+  const Layer& lf = m->layers.back();
+  FM_TRY(k_head_fwd(ctx, cur, m->params + lf.w_off, m->params + lf.b_off, m->prob.p,
+                    (int64_t)B * m->vox(0), lf.c1));
+  return FM_OK;
+}
+
+// wgrad + bias grad of one conv layer
+static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2, const bf16* dy, int B) {
+  fm_ctx* ctx = m->ctx;
+  const Dims5 d = m->dims(l.level, l.cout, B);
+  float* dw = m->grads + l.w_off;
+  const bf16* xs[2] = {x1, x2};
+  const int cs[2] = {l.c1, l.c2};
+  int cofs = 0;
+  for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
+    if (conv_tc_supported(cs[s], 0, l.cout, l.k))
+      FM_TRY(k_conv3d_tc_wgrad(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout, l.k));
+    else
+      FM_TRY(k_conv3d_simt_wgrad(ctx, xs[s], 0, dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout,
+                                 l.k));
+    cofs += cs[s];
+  }
+  FM_TRY(k_bias_grad(ctx, dy, m->grads + l.b_off, d.voxels(), l.cout));
+  return FM_OK;
+}
+
+// dgrad of one source of a conv layer: dx = conv(dy, W flipped^T) [* ReLU mask of `mask`]
+static int conv_dgrad(fm_model* m, const Layer& l, int src, const bf16* dy, const bf16* mask, bf16* dx,
+                      int B) {
+  fm_ctx* ctx = m->ctx;
+  const Dims5 d = m->dims(l.level, l.cout, B);
+  const int cs = src == 0 ? l.c1 : l.c2;
+  const bf16* wd = src == 0 ? l.w_d0 : l.w_d1;
+  if (conv_tc_supported(l.cout, 0, cs, l.k))
+    return k_conv3d_tc_fprop(ctx, dy, nullptr, wd, nullptr, dx, mask, B, d.X, d.Y, d.Z, l.cout, 0, cs, l.k,
+                             0, cs, 0);
+  return k_conv3d_simt_fprop(ctx, dy, 0, nullptr, wd, nullptr, dx, nullptr, B, d.X, d.Y, d.Z, l.cout, 0,
+                             cs, l.k, 0, mask);
+}
+
+static int mark_layer_done(fm_model* m, const Layer& l) {
+  const int i = (int)(&l - &m->layers[0]);
+  FM_CUDA(cudaEventRecord(m->layer_done[i], m->ctx->stream));
+  return FM_OK;
+}
+
+static int backward(fm_model* m, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int D = m->depth();
+  const int64_t n0 = (int64_t)B * m->vox(0);
+  FM_TRY(k_zero(ctx, m->grads, (size_t)m->nparams * sizeof(float)));
+  FM_TRY(k_dice_bwd(ctx, m->prob.p, m->t_in.p, m->sums, n0, m->dz.p, 1));
+  const Layer& lf = m->layers.back();
+  // head backward: gradient lands masked by the ReLU of dec0b (or encB[0] when depth == 1)
+  FM_TRY(k_head_bwd(ctx, m->decB[0].p, m->dz.p, m->params + lf.w_off, m->gDecB[0].p, m->grads + lf.w_off,
+                    m->grads + lf.b_off, n0, lf.c1));
+  FM_TRY(mark_layer_done(m, lf));
+  for (int d = 0; d <= D - 2; ++d) {
+    const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
+    // dec_b: input decA[d]
+    FM_TRY(conv_wgrad(m, db, m->decA[d].p, nullptr, m->gDecB[d].p, B));
+    FM_TRY(mark_layer_done(m, db));
+    FM_TRY(conv_dgrad(m, db, 0, m->gDecB[d].p, m->decA[d].p, m->gDecA[d].p, B));
+    // dec_a: inputs [up[d], encB[d]]
+    FM_TRY(conv_wgrad(m, da, m->up[d].p, m->encB[d].p, m->gDecA[d].p, B));
+    FM_TRY(mark_layer_done(m, da));
+    FM_TRY(conv_dgrad(m, da, 0, m->gDecA[d].p, nullptr, m->gUp[d].p, B));
+    FM_TRY(conv_dgrad(m, da, 1, m->gDecA[d].p, nullptr, m->gSkip[d].p, B));
+    // through UpSampling3D into the coarser tensor that was upsampled (+ its ReLU mask)
+    const bool bottom = (d + 1 == D - 1);
+    const bf16* act = bottom ? m->encB[D - 1].p : m->decB[d + 1].p;
+    bf16* gdst = bottom ? m->gEncB[D - 1].p : m->gDecB[d + 1].p;
+    FM_TRY(k_upsample3d_bwd(ctx, m->gUp[d].p, act, gdst, m->dims(d + 1, da.c1, B), da.c1, 0));
+  }
+  for (int d = D - 1; d >= 0; --d) {
+    const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
+    if (d < D - 1) {
+      // gradient of encB[d]: skip path + MaxPooling3D backward, masked by its ReLU
+      FM_TRY(k_maxpool3d_bwd(ctx, m->encB[d].p, m->gPool[d].p, m->gSkip[d].p, m->gEncB[d].p,
+                             m->dims(d, lb.cout, B), 1));
+    }
+    FM_TRY(conv_wgrad(m, lb, m->encA[d].p, nullptr, m->gEncB[d].p, B));
+    FM_TRY(mark_layer_done(m, lb));
+    FM_TRY(conv_dgrad(m, lb, 0, m->gEncB[d].p, m->encA[d].p, m->gEncA[d].p, B));
+    if (d > 0) {
+      FM_TRY(conv_wgrad(m, la, m->pool[d - 1].p, nullptr, m->gEncA[d].p, B));
+      FM_TRY(mark_layer_done(m, la));
+      FM_TRY(conv_dgrad(m, la, 0, m->gEncA[d].p, nullptr, m->gPool[d - 1].p, B));
+    } else {
+      const Dims5 dd = m->dims(0, la.cout, B);
+      FM_TRY(k_conv3d_simt_wgrad(ctx, m->x_in.p, 1, m->gEncA[0].p, m->grads + la.w_off, B, dd.X, dd.Y, dd.Z,
+                                 la.c1, la.c1, 0, la.cout, la.k));
+      FM_TRY(k_bias_grad(ctx, m->gEncA[0].p, m->grads + la.b_off, dd.voxels(), la.cout));
+      FM_TRY(mark_layer_done(m, la));
+    }
+  }
+  return FM_OK;
+}
+
+static void metrics_from_sums(const double s[8], float out[4]) {
+  const double dice = (2.0 * s[0] + 1.0) / (s[1] + s[2] + 1.0);
+  const double uni = s[4] + s[5] - s[3];
+  out[0] = (float)(-dice);                       // loss = -dice (metrics.py:31-32)
+  out[1] = (float)(s[7] > 0 ? s[6] / s[7] : 0);  // binary_accuracy
+  out[2] = (float)((s[3] + 1.0) / (uni + 1.0));  // vod_coefficient (metrics.py:18-28)
+  out[3] = (float)dice;
+}
+
+static int upload(fm_model* m, const float* src, float* dst, size_t count) {
+  // pageable -> device through the runtime's own staging; callers that care pass pinned memory
+  FM_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+  return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inference
+// ---------------------------------------------------------------------------------------------
+extern "C" int fm_predict_device(fm_model* m, uint64_t x_dev, int batch, uint64_t y_dev) {
+  FM_CHECK(m && batch > 0, FM_EINVAL, "fm_predict_device: bad argument");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_TRY(ensure_capacity(m, batch, false));
+  const size_t n = (size_t)batch * m->vox(0);
+  FM_CUDA(cudaMemcpyAsync(m->x_in.p, (const void*)(uintptr_t)x_dev, n * 4, cudaMemcpyDeviceToDevice,
+                          m->ctx->stream));
+  FM_TRY(forward(m, batch));
+  if (y_dev)
+    FM_CUDA(cudaMemcpyAsync((void*)(uintptr_t)y_dev, m->prob.p, n * 4, cudaMemcpyDeviceToDevice,
+                            m->ctx->stream));
+  m->fwd_valid = false;
+  return FM_OK;
+}
+
+extern "C" int fm_predict(fm_model* m, const float* x, int batch, float* y) {
+  FM_CHECK(m && x && y && batch > 0, FM_EINVAL, "fm_predict: bad argument");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_TRY(ensure_capacity(m, batch, false));
+  const size_t n = (size_t)batch * m->vox(0);
+  FM_TRY(upload(m, x, m->x_in.p, n));
+  FM_TRY(forward(m, batch));
+  FM_CUDA(cudaMemcpyAsync(y, m->prob.p, n * 4, cudaMemcpyDeviceToHost, m->ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  m->fwd_valid = false;
+  return FM_OK;
+}
+
+extern "C" int fm_patch_plan(const int32_t padded[3], const int32_t patch[3], const int32_t pred[3],
+                             double overlap_factor, int32_t* out_idx, int64_t cap, int64_t* out_n) {
+  FM_CHECK(padded && patch && pred && out_n, FM_EINVAL, "fm_patch_plan: NULL argument");
+  std::vector<int32_t> starts[3];
+  for (int a = 0; a < 3; ++a) {
+    const int min_ov = patch[a] - pred[a];
+    const int max_ov = patch[a] - 1;
+    // prediction.py:137: (overlap_factor * (max - min)).astype(int) truncates toward zero
+    const int ov = min_ov + (int)(overlap_factor * (double)(max_ov - min_ov));
+    const int step = patch[a] - ov;
+    const int stop = padded[a] - patch[a];
+    FM_CHECK(step > 0, FM_EINVAL, "fm_patch_plan: non-positive step on axis %d (overlap_factor %g)", a,
+             overlap_factor);
+    FM_CHECK(stop >= 0, FM_EINVAL, "fm_patch_plan: padded extent %d smaller than patch %d on axis %d",
+             padded[a], patch[a], a);
+    for (int s = 0; s <= stop; s += step) starts[a].push_back(s);  // range(0, stop+1, step)
+    if (stop % step > 0) starts[a].push_back(stop);                // prediction.py:93-94
+  }
+  const int64_t n = (int64_t)starts[0].size() * starts[1].size() * starts[2].size();
+  *out_n = n;
+  if (out_idx == nullptr) return FM_OK;
+  FM_CHECK(cap >= n, FM_EINVAL, "fm_patch_plan: capacity %lld < %lld patches", (long long)cap, (long long)n);
+  int64_t i = 0;
+  for (int32_t x : starts[0])
+    for (int32_t y : starts[1])
+      for (int32_t z : starts[2]) {
+        out_idx[i * 3] = x;
+        out_idx[i * 3 + 1] = y;
+        out_idx[i * 3 + 2] = z;
+        ++i;
+      }
+  return FM_OK;
+}
+
+extern "C" int fm_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
+                                 const int32_t halo_pad[6], const int32_t fit_pad[6],
+                                 const double pad_value[2], const int32_t* idx, int64_t n,
+                                 const int32_t patch[3], float* out) {
+  FM_CHECK(ctx && vol && vol_dims && halo_pad && fit_pad && pad_value && idx && patch && out && n > 0,
+           FM_EINVAL, "fm_gather_patches: bad argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  const size_t nv = (size_t)vol_dims[0] * vol_dims[1] * vol_dims[2];
+  const size_t np = (size_t)n * patch[0] * patch[1] * patch[2];
+  DevBuf<float> dvol, dout;
+  DevBuf<int32_t> didx;
+  FM_TRY(dvol.ensure(nv));
+  FM_TRY(dout.ensure(np));
+  FM_TRY(didx.ensure((size_t)n * 3));
+  FM_CUDA(cudaMemcpyAsync(dvol.p, vol, nv * 4, cudaMemcpyHostToDevice, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  int r = k_gather_patches(ctx, dvol.p, vol_dims, halo_pad, fit_pad, (float)pad_value[0],
+                           (float)pad_value[1], didx.p, n, patch, dout.p);
+  if (r == FM_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, dout.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      fm_set_error("fm_gather_patches: %s", cudaGetErrorString(e));
+      r = FM_ECUDA;
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  dvol.release();
+  dout.release();
+  didx.release();
+  return r;
+}
+
+extern "C" int fm_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx, int64_t n,
+                             const int32_t pred_shape[3], int channels, const int32_t out_dims[3],
+                             double* out, int16_t* out_count) {
+  FM_CHECK(ctx && preds && idx && pred_shape && out_dims && out && n > 0 && channels > 0, FM_EINVAL,
+           "fm_reassemble: bad argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  const size_t np = (size_t)n * pred_shape[0] * pred_shape[1] * pred_shape[2] * channels;
+  const size_t nvox = (size_t)out_dims[0] * out_dims[1] * out_dims[2];
+  DevBuf<float> dp;
+  DevBuf<double> dout;
+  DevBuf<int16_t> dcnt;
+  FM_TRY(dp.ensure(np));
+  FM_TRY(dout.ensure(nvox * channels));
+  FM_TRY(dcnt.ensure(nvox));
+  FM_CUDA(cudaMemcpyAsync(dp.p, preds, np * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int r = k_reassemble(ctx, dp.p, idx, n, 0, n, 0, pred_shape, channels, out_dims, dout.p, dcnt.p, 1);
+  if (r == FM_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, dout.p, nvox * channels * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && out_count)
+      e = cudaMemcpyAsync(out_count, dcnt.p, nvox * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      fm_set_error("fm_reassemble: %s", cudaGetErrorString(e));
+      r = FM_ECUDA;
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  dp.release();
+  dout.release();
+  dcnt.release();
+  return r;
+}
+
+extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t vol_dims[3],
+                                    const int32_t halo_pad[6], const int32_t fit_pad[6],
+                                    const double pad_value[2], const int32_t* idx, int64_t n, int batch,
+                                    int shard_rank, int shard_count, double* out, int16_t* out_count) {
+  FM_CHECK(m && vol && vol_dims && halo_pad && fit_pad && pad_value && idx && out && n > 0 && batch > 0,
+           FM_EINVAL, "fm_patchwise_predict: bad argument");
+  FM_CHECK(shard_count >= 1 && shard_rank >= 0 && shard_rank < shard_count, FM_EINVAL,
+           "fm_patchwise_predict: shard %d of %d", shard_rank, shard_count);
+  fm_ctx* ctx = m->ctx;
+  FM_CUDA(cudaSetDevice(ctx->device));
+  const int32_t patch[3] = {m->spec.X, m->spec.Y, m->spec.Z};
+  int32_t out_dims[3];
+  for (int a = 0; a < 3; ++a) {
+    FM_CHECK(halo_pad[2 * a] == 0 && halo_pad[2 * a + 1] == 0, FM_EINVAL,
+             "fm_patchwise_predict: 3D models predict the whole patch, halo pad must be 0");
+    out_dims[a] = vol_dims[a] + fit_pad[2 * a] + fit_pad[2 * a + 1];
+  }
+  const size_t nv = (size_t)vol_dims[0] * vol_dims[1] * vol_dims[2];
+  const size_t nout = (size_t)out_dims[0] * out_dims[1] * out_dims[2];
+  const size_t pv = (size_t)m->vox(0);
+  const int64_t lo = n * shard_rank / shard_count, hi = n * (shard_rank + 1) / shard_count;
+  const int64_t nloc = hi - lo;
+  batch = (int)std::min<int64_t>(batch, std::max<int64_t>(nloc, 1));
+  FM_TRY(ensure_capacity(m, batch, false));
+  DevBuf<float> dvol, dpred;
+  DevBuf<int32_t> didx;
+  DevBuf<double> dout;
+  DevBuf<int16_t> dcnt;
+  int r = FM_OK;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(ctx->stream);
+    dvol.release();
+    dpred.release();
+    didx.release();
+    dout.release();
+    dcnt.release();
+  };
+#define FM_PW(expr)        \
+  do {                     \
+    r = (expr);            \
+    if (r != FM_OK) {      \
+      cleanup();           \
+      return r;            \
+    }                      \
+  } while (0)
+#define FM_PWC(expr)                                                        \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) {                                                \
+      fm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      cleanup();                                                            \
+      return FM_ECUDA;                                                      \
+    }                                                                       \
+  } while (0)
+  FM_PW(dvol.ensure(nv));
+  FM_PW(dpred.ensure(std::max<size_t>(1, (size_t)nloc) * pv));
+  FM_PW(didx.ensure((size_t)n * 3));
+  FM_PW(dout.ensure(nout));
+  FM_PW(dcnt.ensure(nout));
+  FM_PWC(cudaMemcpyAsync(dvol.p, vol, nv * 4, cudaMemcpyHostToDevice, ctx->stream));
+  FM_PWC(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  FM_PWC(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));
+  for (int64_t b0 = lo; b0 < hi; b0 += batch) {
+    const int nb = (int)std::min<int64_t>(batch, hi - b0);
+    FM_PW(k_gather_patches(ctx, dvol.p, vol_dims, halo_pad, fit_pad, (float)pad_value[0],
+                           (float)pad_value[1], didx.p + b0 * 3, nb, patch, m->x_in.p));
+    FM_PW(forward(m, nb));
+    FM_PWC(cudaMemcpyAsync(dpred.p + (size_t)(b0 - lo) * pv, m->prob.p, (size_t)nb * pv * 4,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  FM_PW(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, patch, 1, out_dims, dout.p, dcnt.p,
+                     shard_count == 1 ? 1 : 0));
+  FM_PWC(cudaMemcpyAsync(out, dout.p, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_count) FM_PWC(cudaMemcpyAsync(out_count, dcnt.p, nout * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_PWC(cudaStreamSynchronize(ctx->stream));
+#undef FM_PW
+#undef FM_PWC
+  cleanup();
+  m->fwd_valid = false;
+  return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training
+// ---------------------------------------------------------------------------------------------
+static int train_forward_dev(fm_model* m, int batch) {
+  FM_TRY(forward(m, batch));
+  FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0));
+  m->last_batch = batch;
+  m->fwd_valid = true;
+  return FM_OK;
+}
+
+extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int batch) {
+  FM_CHECK(m && x && t && batch > 0, FM_EINVAL, "fm_train_forward: bad argument");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_TRY(ensure_capacity(m, batch, true));
+  const size_t n = (size_t)batch * m->vox(0);
+  FM_TRY(upload(m, x, m->x_in.p, n));
+  FM_TRY(upload(m, t, m->t_in.p, n));
+  return train_forward_dev(m, batch);
+}
+
+extern "C" int fm_train_backward(fm_model* m) {
+  FM_CHECK(m, FM_EINVAL, "NULL model");
+  FM_CHECK(m->fwd_valid, FM_ESTATE, "fm_train_backward called without a preceding fm_train_forward");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_TRY(backward(m, m->last_batch));
+  m->fwd_valid = false;
+  return FM_OK;
+}
+
+extern "C" int fm_train_apply(fm_model* m, float lr, uint64_t after_stream, float out_metrics[4]) {
+  FM_CHECK(m, FM_EINVAL, "NULL model");
+  fm_ctx* ctx = m->ctx;
+  FM_CUDA(cudaSetDevice(ctx->device));
+  if (after_stream) {
+    FM_CUDA(cudaEventRecord(m->ev_tmp, (cudaStream_t)(uintptr_t)after_stream));
+    FM_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_tmp, 0));
+  }
+  FM_TRY(k_adam(ctx, m->params, m->grads, m->adam_m, m->adam_v, m->nparams, m->iterations, lr));
+  m->iterations++;
+  m->packs_dirty = true;
+  FM_TRY(refresh_packs(m));
+  if (out_metrics) {
+    FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FM_CUDA(cudaStreamSynchronize(ctx->stream));
+    metrics_from_sums(m->sums_host, out_metrics);
+  }
+  return FM_OK;
+}
+
+extern "C" int fm_model_loss_sums(fm_model* m, uint64_t* dev_ptr) {
+  FM_CHECK(m && dev_ptr, FM_EINVAL, "NULL argument");
+  *dev_ptr = (uint64_t)(uintptr_t)m->sums;
+  return FM_OK;
+}
+extern "C" int fm_model_grad_buffer(fm_model* m, uint64_t* dev_ptr, int64_t* n) {
+  FM_CHECK(m && dev_ptr && n, FM_EINVAL, "NULL argument");
+  *dev_ptr = (uint64_t)(uintptr_t)m->grads;
+  *n = m->nparams;
+  return FM_OK;
+}
+extern "C" int fm_model_num_buckets(fm_model* m) { return m ? (int)m->buckets.size() : -1; }
+extern "C" int fm_model_bucket_range(fm_model* m, int bucket, int64_t* offset, int64_t* count) {
+  FM_CHECK(m && bucket >= 0 && bucket < (int)m->buckets.size() && offset && count, FM_EINVAL,
+           "bucket %d out of range", bucket);
+  const Layer& first = m->layers[m->buckets[bucket].first];
+  const int last_i = m->buckets[bucket].second;
+  const int64_t end = last_i + 1 < (int)m->layers.size() ? m->layers[last_i + 1].w_off : m->nparams;
+  *offset = first.w_off;
+  *count = end - first.w_off;
+  return FM_OK;
+}
+extern "C" int fm_stream_wait_bucket(fm_model* m, uint64_t stream, int bucket) {
+  FM_CHECK(m && bucket >= 0 && bucket < (int)m->buckets.size(), FM_EINVAL, "bucket %d out of range", bucket);
+  // backward runs in reverse creation order: the bucket is final when its FIRST layer is done
+  FM_CUDA(cudaStreamWaitEvent((cudaStream_t)(uintptr_t)stream, m->layer_done[m->buckets[bucket].first], 0));
+  return FM_OK;
+}
+
+extern "C" int fm_train_step_device(fm_model* m, uint64_t x_dev, uint64_t t_dev, int batch, float lr,
+                                    float out_metrics[4]) {
+  FM_CHECK(m && x_dev && t_dev && batch > 0, FM_EINVAL, "fm_train_step_device: bad argument");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_TRY(ensure_capacity(m, batch, true));
+  const size_t n = (size_t)batch * m->vox(0);
+  FM_CUDA(cudaMemcpyAsync(m->x_in.p, (const void*)(uintptr_t)x_dev, n * 4, cudaMemcpyDeviceToDevice,
+                          m->ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(m->t_in.p, (const void*)(uintptr_t)t_dev, n * 4, cudaMemcpyDeviceToDevice,
+                          m->ctx->stream));
+  FM_TRY(train_forward_dev(m, batch));
+  FM_TRY(fm_train_backward(m));
+  return fm_train_apply(m, lr, 0, out_metrics);
+}
+
+extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
+                             float out_metrics[4]) {
+  FM_TRY(fm_train_forward(m, x, t, batch));
+  FM_TRY(fm_train_backward(m));
+  return fm_train_apply(m, lr, 0, out_metrics);
+}
+
+extern "C" int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]) {
+  FM_CHECK(out_metrics, FM_EINVAL, "fm_evaluate: out_metrics is NULL");
+  FM_TRY(fm_train_forward(m, x, t, batch));
+  m->fwd_valid = false;
+  FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  metrics_from_sums(m->sums_host, out_metrics);
+  return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-op hooks (host fp32 channels-last in/out; bf16 on the device)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct OpScratch {
+  fm_ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit OpScratch(fm_ctx* c) : ctx(c) {}
+  ~OpScratch() {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+      fm_set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+      return FM_ENOMEM;
+    }
+    ptrs.push_back(p);
+    *out = (T*)p;
+    return FM_OK;
+  }
+  // host fp32 -> device bf16
+  int up_bf16(const float* h, size_t count, bf16** out) {
+    float* tmp;
+    FM_TRY(alloc(&tmp, count));
+    FM_TRY(alloc(out, count));
+    FM_CUDA(cudaMemcpyAsync(tmp, h, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return k_cast_f32_to_bf16(ctx, tmp, *out, (int64_t)count);
+  }
+  int up_f32(const float* h, size_t count, float** out) {
+    FM_TRY(alloc(out, count));
+    FM_CUDA(cudaMemcpyAsync(*out, h, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return FM_OK;
+  }
+  // device bf16 -> host fp32
+  int down_bf16(const bf16* d, size_t count, float* h) {
+    float* tmp;
+    FM_TRY(alloc(&tmp, count));
+    FM_TRY(k_cast_bf16_to_f32(ctx, d, tmp, (int64_t)count));
+    FM_CUDA(cudaMemcpyAsync(h, tmp, count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FM_OK;
+  }
+};
+}  // namespace
+
+extern "C" int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const float* x2,
+                                  const float* w_keras, const float* bias, int N, int X, int Y, int Z,
+                                  int C1, int C2, int Cout, int ksize, int relu, float* y) {
+  FM_CHECK(ctx && x && w_keras && y, FM_EINVAL, "fm_op_conv3d_fprop: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t vox = (size_t)N * X * Y * Z;
+  const int taps = ksize * ksize * ksize, Ct = C1 + C2;
+  std::vector<float> packed((size_t)Cout * taps * Ct);
+  keras_to_packed(w_keras, packed.data(), ksize, Ct, Cout);
+  bf16 *dx1 = nullptr, *dx2 = nullptr, *dw = nullptr, *dy = nullptr;
+  float* dbias = nullptr;
+  FM_TRY(s.up_bf16(x, vox * C1, &dx1));
+  if (C2 > 0) FM_TRY(s.up_bf16(x2, vox * C2, &dx2));
+  FM_TRY(s.up_bf16(packed.data(), packed.size(), &dw));
+  if (bias) FM_TRY(s.up_f32(bias, Cout, &dbias));
+  FM_TRY(s.alloc(&dy, vox * Cout));
+  if (impl == 0)
+    FM_TRY(k_conv3d_tc_fprop(ctx, dx1, dx2, dw, dbias, dy, nullptr, N, X, Y, Z, C1, C2, Cout, ksize, relu,
+                             Cout, 0));
+  else
+    FM_TRY(k_conv3d_simt_fprop(ctx, dx1, 0, dx2, dw, dbias, dy, nullptr, N, X, Y, Z, C1, C2, Cout, ksize,
+                               relu, nullptr));
+  return s.down_bf16(dy, vox * Cout, y);
+}
+
+extern "C" int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const float* w_keras,
+                                  const float* mask, int N, int X, int Y, int Z, int Cin, int Cout,
+                                  float* dx) {
+  FM_CHECK(ctx && dy && w_keras && dx, FM_EINVAL, "fm_op_conv3d_dgrad: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t vox = (size_t)N * X * Y * Z;
+  const int ksize = 3, taps = 27;
+  std::vector<float> packed((size_t)Cout * taps * Cin);
+  keras_to_packed(w_keras, packed.data(), ksize, Cin, Cout);
+  float* dwm = nullptr;
+  bf16 *wd = nullptr, *ddy = nullptr, *dmask = nullptr, *ddx = nullptr;
+  FM_TRY(s.up_f32(packed.data(), packed.size(), &dwm));
+  FM_TRY(s.alloc(&wd, packed.size()));
+  FM_TRY(k_repack_weights(ctx, dwm, nullptr, wd, nullptr, Cout, taps, Cin, 0));
+  FM_TRY(s.up_bf16(dy, vox * Cout, &ddy));
+  if (mask) FM_TRY(s.up_bf16(mask, vox * Cin, &dmask));
+  FM_TRY(s.alloc(&ddx, vox * Cin));
+  if (impl == 0)
+    FM_TRY(k_conv3d_tc_fprop(ctx, ddy, nullptr, wd, nullptr, ddx, dmask, N, X, Y, Z, Cout, 0, Cin, ksize, 0,
+                             Cin, 0));
+  else
+    FM_TRY(k_conv3d_simt_fprop(ctx, ddy, 0, nullptr, wd, nullptr, ddx, nullptr, N, X, Y, Z, Cout, 0, Cin,
+                               ksize, 0, dmask));
+  return s.down_bf16(ddx, vox * Cin, dx);
+}
+
+extern "C" int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const float* dy, int N, int X,
+                                  int Y, int Z, int Cin, int Cout, float* dw_keras, float* dbias) {
+  FM_CHECK(ctx && x && dy && dw_keras, FM_EINVAL, "fm_op_conv3d_wgrad: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t vox = (size_t)N * X * Y * Z;
+  const int ksize = 3, taps = 27;
+  bf16 *dx = nullptr, *ddy = nullptr;
+  float *dw = nullptr, *db = nullptr;
+  FM_TRY(s.up_bf16(x, vox * Cin, &dx));
+  FM_TRY(s.up_bf16(dy, vox * Cout, &ddy));
+  const size_t wn = (size_t)Cout * taps * Cin;
+  FM_TRY(s.alloc(&dw, wn));
+  FM_TRY(s.alloc(&db, Cout));
+  FM_TRY(k_zero(ctx, dw, wn * 4));
+  FM_TRY(k_zero(ctx, db, (size_t)Cout * 4));
+  if (impl == 0)
+    FM_TRY(k_conv3d_tc_wgrad(ctx, dx, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, ksize));
+  else
+    FM_TRY(k_conv3d_simt_wgrad(ctx, dx, 0, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, ksize));
+  FM_TRY(k_bias_grad(ctx, ddy, db, (int64_t)vox, Cout));
+  std::vector<float> packed(wn);
+  FM_CUDA(cudaMemcpyAsync(packed.data(), dw, wn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dbias) FM_CUDA(cudaMemcpyAsync(dbias, db, (size_t)Cout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  packed_to_keras(packed.data(), dw_keras, ksize, Cin, Cout);
+  return FM_OK;
+}
+
+extern "C" int fm_op_maxpool3d(fm_ctx* ctx, const float* x, int N, int X, int Y, int Z, int C, float* y) {
+  FM_CHECK(ctx && x && y, FM_EINVAL, "fm_op_maxpool3d: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t n = (size_t)N * X * Y * Z * C;
+  bf16 *dx = nullptr, *dy = nullptr;
+  FM_TRY(s.up_bf16(x, n, &dx));
+  FM_TRY(s.alloc(&dy, n / 8));
+  FM_TRY(k_maxpool3d_fwd(ctx, dx, dy, Dims5{N, X, Y, Z, C}));
+  return s.down_bf16(dy, n / 8, y);
+}
+
+extern "C" int fm_op_maxpool3d_bwd(fm_ctx* ctx, const float* x, const float* dy, const float* dskip,
+                                   int N, int X, int Y, int Z, int C, float* dx) {
+  FM_CHECK(ctx && x && dy && dx, FM_EINVAL, "fm_op_maxpool3d_bwd: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t n = (size_t)N * X * Y * Z * C;
+  bf16 *bx = nullptr, *bdy = nullptr, *bsk = nullptr, *bdx = nullptr;
+  FM_TRY(s.up_bf16(x, n, &bx));
+  FM_TRY(s.up_bf16(dy, n / 8, &bdy));
+  if (dskip) FM_TRY(s.up_bf16(dskip, n, &bsk));
+  FM_TRY(s.alloc(&bdx, n));
+  FM_TRY(k_maxpool3d_bwd(ctx, bx, bdy, bsk, bdx, Dims5{N, X, Y, Z, C}, 1));
+  return s.down_bf16(bdx, n, dx);
+}
+
+extern "C" int fm_op_upsample3d(fm_ctx* ctx, const float* x, int N, int X, int Y, int Z, int C, float* y) {
+  FM_CHECK(ctx && x && y, FM_EINVAL, "fm_op_upsample3d: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t n = (size_t)N * X * Y * Z * C;
+  bf16 *dx = nullptr, *dy = nullptr;
+  FM_TRY(s.up_bf16(x, n, &dx));
+  FM_TRY(s.alloc(&dy, n * 8));
+  FM_TRY(k_upsample3d_fwd(ctx, dx, dy, Dims5{N, X, Y, Z, C}));
+  return s.down_bf16(dy, n * 8, y);
+}
+
+extern "C" int fm_op_upsample3d_bwd(fm_ctx* ctx, const float* dy, const float* act, int N, int X, int Y,
+                                    int Z, int C, float* dx) {
+  FM_CHECK(ctx && dy && dx, FM_EINVAL, "fm_op_upsample3d_bwd: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t n = (size_t)N * X * Y * Z * C;  // coarse elements
+  bf16 *bdy = nullptr, *bact = nullptr, *bdx = nullptr;
+  FM_TRY(s.up_bf16(dy, n * 8, &bdy));
+  if (act) FM_TRY(s.up_bf16(act, n, &bact));
+  FM_TRY(s.alloc(&bdx, n));
+  FM_TRY(k_upsample3d_bwd(ctx, bdy, bact, bdx, Dims5{N, X, Y, Z, C}, C, 0));
+  return s.down_bf16(bdx, n, dx);
+}
+
+extern "C" int fm_op_dice(fm_ctx* ctx, const float* p, const float* t, int64_t n, double sums[8],
+                          float* dloss_dp) {
+  FM_CHECK(ctx && p && t && sums && n > 0, FM_EINVAL, "fm_op_dice: bad argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  float *dp = nullptr, *dt = nullptr, *dg = nullptr;
+  double* ds = nullptr;
+  FM_TRY(s.up_f32(p, (size_t)n, &dp));
+  FM_TRY(s.up_f32(t, (size_t)n, &dt));
+  FM_TRY(s.alloc(&ds, 8));
+  FM_TRY(k_dice_sums(ctx, dp, dt, n, ds, 0));
+  FM_CUDA(cudaMemcpyAsync(sums, ds, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dloss_dp) {
+    FM_TRY(s.alloc(&dg, (size_t)n));
+    FM_TRY(k_dice_bwd(ctx, dp, dt, ds, n, dg, 0));
+    FM_CUDA(cudaMemcpyAsync(dloss_dp, dg, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FM_OK;
+}
+
+extern "C" int fm_op_adam(fm_ctx* ctx, float* p, const float* g, float* mm, float* vv, int64_t n,
+                          int iterations, float lr) {
+  FM_CHECK(ctx && p && g && mm && vv && n > 0, FM_EINVAL, "fm_op_adam: bad argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  float *dp, *dg, *dm, *dv;
+  FM_TRY(s.up_f32(p, (size_t)n, &dp));
+  FM_TRY(s.up_f32(g, (size_t)n, &dg));
+  FM_TRY(s.up_f32(mm, (size_t)n, &dm));
+  FM_TRY(s.up_f32(vv, (size_t)n, &dv));
+  FM_TRY(k_adam(ctx, dp, dg, dm, dv, n, iterations, lr));
+  FM_CUDA(cudaMemcpyAsync(p, dp, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(mm, dm, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(vv, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FM_OK;
+}

@@ -1,0 +1,666 @@
+// bandwidth.cu — HBM-bound kernels of the hot path: MaxPooling3D / UpSampling3D forward+backward,
+// soft-Dice statistics and backward, Keras-Adam, patch gather and overlap-add reassembly.
+// Device layout everywhere: channels-last [N][X][Y][Z][C] (C contiguous), bf16 activations.
+// All kernels move 16-byte vectors per thread along the contiguous (C, then Z) direction.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ void unpack8(uint4 v, float f[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// casts
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(in + i));
+    float4 b = __ldg(reinterpret_cast<const float4*>(in + i + 4));
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    stg16(out + i, pack8(f));
+  } else {
+    for (; i < n; ++i) out[i] = __float2bfloat16(in[i]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float f[8];
+    unpack8(ldg16(in + i), f);
+    *reinterpret_cast<float4*>(out + i) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(out + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (; i < n; ++i) out[i] = __bfloat162float(in[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPooling3D((2,2,2)) — Keras call site fetal_net/model/unet3d/unet.py:51 (valid, stride 2)
+// one thread = one pooled voxel x 8 channels (16 B); the two z-children of a window are adjacent
+// in memory so every warp-level request is a run of full 32 B sectors.
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
+                                     int Y, int Z, int C) {
+  const int c8n = C >> 3;
+  const int Xo = X >> 1, Yo = Y >> 1, Zo = Z >> 1;
+  const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int c8 = (int)(g % c8n);
+  int64_t v = g / c8n;
+  const int zo = (int)(v % Zo);
+  v /= Zo;
+  const int yo = (int)(v % Yo);
+  v /= Yo;
+  const int xo = (int)(v % Xo);
+  const int n = (int)(v / Xo);
+  __nv_bfloat162 m[4];
+  bool first = true;
+#pragma unroll
+  for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz) {
+        const int64_t vi = (((int64_t)n * X + 2 * xo + dx) * Y + 2 * yo + dy) * Z + 2 * zo + dz;
+        uint4 t = ldg16(x + vi * C + c8 * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+        if (first) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m[i] = h[i];
+          first = false;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], h[i]);
+        }
+      }
+  uint4 o;
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) oh[i] = m[i];
+  const int64_t vo = (((int64_t)n * Xo + xo) * Yo + yo) * Zo + zo;
+  stg16(y + vo * C + c8 * 8, o);
+}
+
+// Backward of MaxPooling3D fused with the skip-connection gradient add and the ReLU mask of the
+// producing conv block: dx = [x>0] * (dskip + [x is the first max of its window] * dy).
+__global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                     const bf16* __restrict__ dskip, bf16* __restrict__ dx, int N,
+                                     int X, int Y, int Z, int C, int relu_mask) {
+  const int c8n = C >> 3;
+  const int Xo = X >> 1, Yo = Y >> 1, Zo = Z >> 1;
+  const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int c8 = (int)(g % c8n);
+  int64_t v = g / c8n;
+  const int zo = (int)(v % Zo);
+  v /= Zo;
+  const int yo = (int)(v % Yo);
+  v /= Yo;
+  const int xo = (int)(v % Xo);
+  const int n = (int)(v / Xo);
+  float xv[8][8];
+  int64_t vi[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
+    vi[k] = (((int64_t)n * X + 2 * xo + ddx) * Y + 2 * yo + ddy) * Z + 2 * zo + ddz;
+    unpack8(ldg16(x + vi[k] * C + c8 * 8), xv[k]);
+  }
+  const int64_t vo = (((int64_t)n * Xo + xo) * Yo + yo) * Zo + zo;
+  float g8[8];
+  unpack8(ldg16(dy + vo * C + c8 * 8), g8);
+  int arg[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float best = xv[0][c];
+    int a = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (xv[k][c] > best) {
+        best = xv[k][c];
+        a = k;
+      }
+    arg[c] = a;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float o[8];
+    if (dskip != nullptr) {
+      unpack8(ldg16(dskip + vi[k] * C + c8 * 8), o);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (arg[c] == k) o[c] += g8[c];
+      if (relu_mask && !(xv[k][c] > 0.f)) o[c] = 0.f;
+    }
+    stg16(dx + vi[k] * C + c8 * 8, pack8(o));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UpSampling3D((2,2,2)) nearest — Keras call site fetal_net/model/unet3d/unet.py:138
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
+                                      int Y, int Z, int C) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)N * X * Y * Z * c8n;
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int c8 = (int)(g % c8n);
+  int64_t v = g / c8n;
+  const int z = (int)(v % Z);
+  int64_t r = v / Z;
+  const int yy = (int)(r % Y);
+  r /= Y;
+  const int xx = (int)(r % X);
+  const int n = (int)(r / X);
+  const uint4 t = ldg16(x + v * C + c8 * 8);
+  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
+    const int64_t vo = (((int64_t)n * X2 + 2 * xx + ddx) * Y2 + 2 * yy + ddy) * Z2 + 2 * z + ddz;
+    stg16(y + vo * C + c8 * 8, t);
+  }
+}
+
+// backward: 2^3 sum-pool of dy (fp32 accumulate), optionally masked by ReLU of the coarse activation
+__global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ act,
+                                      bf16* __restrict__ dx, int N, int X, int Y, int Z, int C,
+                                      int dyC, int dy_cofs) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)N * X * Y * Z * c8n;
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int c8 = (int)(g % c8n);
+  int64_t v = g / c8n;
+  const int z = (int)(v % Z);
+  int64_t r = v / Z;
+  const int yy = (int)(r % Y);
+  r /= Y;
+  const int xx = (int)(r % X);
+  const int n = (int)(r / X);
+  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
+    const int64_t vo = (((int64_t)n * X2 + 2 * xx + ddx) * Y2 + 2 * yy + ddy) * Z2 + 2 * z + ddz;
+    float f[8];
+    unpack8(ldg16(dy + vo * dyC + dy_cofs + c8 * 8), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] += f[c];
+  }
+  if (act != nullptr) {
+    float a[8];
+    unpack8(ldg16(act + v * C + c8 * 8), a);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (!(a[c] > 0.f)) acc[c] = 0.f;
+  }
+  stg16(dx + v * C + c8 * 8, pack8(acc));
+}
+
+// ---------------------------------------------------------------------------------------------
+// soft-Dice statistics — fetal_net/metrics.py:11-15 (dice), :18-28 (vod), Keras binary_accuracy
+// deterministic two-stage reduction: per-block partials in double, then one block sums them.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRedBlocks = 592;  // 4 x 148 SMs
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __restrict__ p,
+                                                                const float* __restrict__ t,
+                                                                int64_t n, double* __restrict__ part) {
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t nv = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 pp = __ldg(reinterpret_cast<const float4*>(p) + i);
+    const float4 tt = __ldg(reinterpret_cast<const float4*>(t) + i);
+    const float pa[4] = {pp.x, pp.y, pp.z, pp.w};
+    const float ta[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float pb = pa[k] > 0.5f ? 1.f : 0.f;
+      const float tb = ta[k] > 0.5f ? 1.f : 0.f;
+      s[0] += ta[k] * pa[k];
+      s[1] += ta[k];
+      s[2] += pa[k];
+      s[3] += tb * pb;
+      s[4] += tb;
+      s[5] += pb;
+      s[6] += (ta[k] == pb) ? 1.f : 0.f;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = nv << 2; i < n; ++i) {
+      const float pb = p[i] > 0.5f ? 1.f : 0.f, tb = t[i] > 0.5f ? 1.f : 0.f;
+      s[0] += t[i] * p[i];
+      s[1] += t[i];
+      s[2] += p[i];
+      s[3] += tb * pb;
+      s[4] += tb;
+      s[5] += pb;
+      s[6] += (t[i] == pb) ? 1.f : 0.f;
+    }
+  }
+  __shared__ double sh[kThreads / 32][7];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const double w = warp_sum((double)s[k]);
+    if (lane == 0) sh[warp][k] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double a = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) a += sh[w][threadIdx.x];
+    part[(int64_t)blockIdx.x * 8 + threadIdx.x] = a;
+  }
+}
+
+__global__ void dice_final_kernel(const double* __restrict__ part, int nblocks, double n_elems,
+                                  double* __restrict__ sums, int accumulate) {
+  const int k = threadIdx.x;
+  if (k < 7) {
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += part[(int64_t)b * 8 + k];
+    sums[k] = accumulate ? sums[k] + a : a;
+  } else if (k == 7) {
+    sums[7] = accumulate ? sums[7] + n_elems : n_elems;
+  }
+}
+
+// dL/dz for L = -dice(t, sigmoid(z)): closed form of metrics.py:11-15,31-32 with smooth = 1
+__global__ void dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                const double* __restrict__ sums, int64_t n, float* __restrict__ dz,
+                                int through_sigmoid) {
+  const double I = sums[0], S = sums[1] + sums[2] + 1.0;
+  const float a = (float)(-2.0 / S);               // coefficient of t_i
+  const float b = (float)((2.0 * I + 1.0) / (S * S));  // constant term
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    const float4 pp = __ldg(reinterpret_cast<const float4*>(p + i));
+    const float4 tt = __ldg(reinterpret_cast<const float4*>(t + i));
+    float4 o;
+    o.x = a * tt.x + b;
+    o.y = a * tt.y + b;
+    o.z = a * tt.z + b;
+    o.w = a * tt.w + b;
+    if (through_sigmoid) {
+      o.x *= pp.x * (1.f - pp.x);
+      o.y *= pp.y * (1.f - pp.y);
+      o.z *= pp.z * (1.f - pp.z);
+      o.w *= pp.w * (1.f - pp.w);
+    }
+    *reinterpret_cast<float4*>(dz + i) = o;
+  } else {
+    for (; i < n; ++i) {
+      float o = a * t[i] + b;
+      if (through_sigmoid) o *= p[i] * (1.f - p[i]);
+      dz[i] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras-2 Adam: epsilon outside the bias correction, lr_t folded on host
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_t, float b1, float b2,
+                            float eps) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i));
+    float4 mm = *reinterpret_cast<float4*>(m + i);
+    float4 vv = *reinterpret_cast<float4*>(v + i);
+#define FM_ADAM1(c)                                   \
+  mm.c = b1 * mm.c + (1.f - b1) * gg.c;               \
+  vv.c = b2 * vv.c + (1.f - b2) * gg.c * gg.c;        \
+  pp.c = pp.c - lr_t * mm.c / (sqrtf(vv.c) + eps);
+    FM_ADAM1(x) FM_ADAM1(y) FM_ADAM1(z) FM_ADAM1(w)
+#undef FM_ADAM1
+    *reinterpret_cast<float4*>(p + i) = pp;
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+  } else {
+    for (; i < n; ++i) {
+      const float gg = g[i];
+      const float mm = b1 * m[i] + (1.f - b1) * gg;
+      const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+      m[i] = mm;
+      v[i] = vv;
+      p[i] = p[i] - lr_t * mm / (sqrtf(vv) + eps);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// patch gather — get_patch_from_3d_data on the virtually padded volume
+// (fetal_net/utils/patches.py:57-72; padding of fetal_net/prediction.py:138-146)
+// ---------------------------------------------------------------------------------------------
+struct GatherGeom {
+  int vol[3], halo[3], fit[3], padded[3], patch[3];
+  int halo_dims[3];
+};
+
+__global__ void gather_patches_kernel(const float* __restrict__ vol, GatherGeom gm, float pad0,
+                                      float pad1, const int32_t* __restrict__ idx, int64_t n,
+                                      float* __restrict__ out) {
+  const int64_t pv = (int64_t)gm.patch[0] * gm.patch[1] * gm.patch[2];
+  const int64_t total = n * pv;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pi = g / pv;
+    int64_t r = g - pi * pv;
+    const int k = (int)(r % gm.patch[2]);
+    r /= gm.patch[2];
+    const int j = (int)(r % gm.patch[1]);
+    const int i = (int)(r / gm.patch[1]);
+    // coordinate in the fit-padded array -> halo-padded array -> original volume
+    const int c[3] = {idx[pi * 3 + 0] + i, idx[pi * 3 + 1] + j, idx[pi * 3 + 2] + k};
+    float val;
+    int h[3], o[3];
+    bool in_halo = true, in_vol = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      h[a] = c[a] - gm.fit[a];
+      in_halo = in_halo && h[a] >= 0 && h[a] < gm.halo_dims[a];
+      o[a] = h[a] - gm.halo[a];
+      in_vol = in_vol && o[a] >= 0 && o[a] < gm.vol[a];
+    }
+    if (!in_halo)
+      val = pad1;
+    else if (!in_vol)
+      val = pad0;
+    else
+      val = __ldg(vol + ((int64_t)o[0] * gm.vol[1] + o[1]) * gm.vol[2] + o[2]);
+    out[g] = val;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// overlap-add / average reassembly — fetal_net/prediction.py:188-193,210
+// output-stationary: every output voxel walks the (contiguous) range of patches covering it per
+// axis, adding float32 predictions in float64 in ascending patch order — the same order the
+// reference's `+=` loop uses — so the sum (and sum / count) is bit-identical. No atomics.
+// ---------------------------------------------------------------------------------------------
+struct ReasmGeom {
+  int out[3], pred[3], np[3];
+  int channels;
+};
+
+__global__ void reassemble_kernel(const float* __restrict__ preds, ReasmGeom gm,
+                                  const int32_t* __restrict__ starts,   // [3][max np]
+                                  const int32_t* __restrict__ cover,    // [3][max dim][2] lo,hi
+                                  int starts_pitch, int cover_pitch, int64_t shard_lo,
+                                  int64_t shard_hi, int64_t pred_base, double* __restrict__ out,
+                                  int16_t* __restrict__ count, int divide) {
+  const int64_t nvox = (int64_t)gm.out[0] * gm.out[1] * gm.out[2];
+  const int64_t total = nvox * gm.channels;
+  const int64_t pvox = (int64_t)gm.pred[0] * gm.pred[1] * gm.pred[2];
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(g % gm.channels);
+    int64_t v = g / gm.channels;
+    const int z = (int)(v % gm.out[2]);
+    int64_t r = v / gm.out[2];
+    const int y = (int)(r % gm.out[1]);
+    const int x = (int)(r / gm.out[1]);
+    const int xlo = cover[(0 * cover_pitch + x) * 2], xhi = cover[(0 * cover_pitch + x) * 2 + 1];
+    const int ylo = cover[(1 * cover_pitch + y) * 2], yhi = cover[(1 * cover_pitch + y) * 2 + 1];
+    const int zlo = cover[(2 * cover_pitch + z) * 2], zhi = cover[(2 * cover_pitch + z) * 2 + 1];
+    double acc = 0.0;
+    for (int ix = xlo; ix < xhi; ++ix) {
+      const int px = x - starts[0 * starts_pitch + ix];
+      for (int iy = ylo; iy < yhi; ++iy) {
+        const int py = y - starts[1 * starts_pitch + iy];
+        for (int iz = zlo; iz < zhi; ++iz) {
+          const int64_t patch = ((int64_t)ix * gm.np[1] + iy) * gm.np[2] + iz;
+          if (patch < shard_lo || patch >= shard_hi) continue;
+          const int pz = z - starts[2 * starts_pitch + iz];
+          const int64_t off = (((patch - pred_base) * pvox) +
+                               ((int64_t)px * gm.pred[1] + py) * gm.pred[2] + pz) * gm.channels + ch;
+          acc += (double)__ldg(preds + off);
+        }
+      }
+    }
+    const int cnt = (xhi - xlo) * (yhi - ylo) * (zhi - zlo);
+    if (count != nullptr && ch == 0) count[v] = (int16_t)cnt;
+    if (divide)
+      out[g] = acc / (double)cnt;
+    else
+      out[g] += acc;
+  }
+}
+
+__global__ void divide_by_count_kernel(double* __restrict__ out, const int16_t* __restrict__ count,
+                                       int64_t nvox, int channels) {
+  const int64_t total = nvox * channels;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (int64_t)gridDim.x * blockDim.x)
+    out[g] = out[g] / (double)count[g / channels];
+}
+
+inline int grid_for(int64_t work_items, int cap = 1 << 30) {
+  int64_t b = ceil_div64(work_items, kThreads);
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------
+int k_cast_f32_to_bf16(fm_ctx* ctx, const float* in, bf16* out, int64_t n) {
+  cast_f32_bf16_kernel<<<grid_for(ceil_div64(n, 8)), kThreads, 0, ctx->stream>>>(in, out, n);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_cast_bf16_to_f32(fm_ctx* ctx, const bf16* in, float* out, int64_t n) {
+  cast_bf16_f32_kernel<<<grid_for(ceil_div64(n, 8)), kThreads, 0, ctx->stream>>>(in, out, n);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_maxpool3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in) {
+  FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % 2 == 0, FM_EINVAL,
+           "maxpool3d: need C%%8==0 and even extents (got C=%d %dx%dx%d)", in.C, in.X, in.Y, in.Z);
+  const int64_t total = in.elems() / 64;
+  maxpool3d_fwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z,
+                                                                     in.C);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dskip, bf16* dx, Dims5 in,
+                    int relu_mask) {
+  FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % 2 == 0, FM_EINVAL,
+           "maxpool3d_bwd: need C%%8==0 and even extents");
+  const int64_t total = in.elems() / 64;
+  maxpool3d_bwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X,
+                                                                     in.Y, in.Z, in.C, relu_mask);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_upsample3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in) {
+  FM_CHECK(in.C % 8 == 0, FM_EINVAL, "upsample3d: need C%%8==0");
+  upsample3d_fwd_kernel<<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X,
+                                                                               in.Y, in.Z, in.C);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dims5 coarse, int dy_C,
+                     int dy_cofs) {
+  FM_CHECK(coarse.C % 8 == 0 && dy_C % 8 == 0 && dy_cofs % 8 == 0, FM_EINVAL,
+           "upsample3d_bwd: channel counts must be multiples of 8");
+  upsample3d_bwd_kernel<<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
+      dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* sums, int accumulate) {
+  dice_partial_kernel<<<kRedBlocks, kThreads, 0, ctx->stream>>>(p, t, n, ctx->red_scratch);
+  FM_LAUNCH_OK(ctx);
+  dice_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->red_scratch, kRedBlocks, (double)n, sums,
+                                              accumulate);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_dice_bwd(fm_ctx* ctx, const float* p, const float* t, const double* sums, int64_t n, float* dz,
+               int through_sigmoid) {
+  dice_bwd_kernel<<<grid_for(ceil_div64(n, 4)), kThreads, 0, ctx->stream>>>(p, t, sums, n, dz,
+                                                                           through_sigmoid);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_adam(fm_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, int iterations,
+           float lr) {
+  const double b1 = 0.9, b2 = 0.999;
+  const double t = (double)iterations + 1.0;
+  const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
+  adam_kernel<<<grid_for(ceil_div64(n, 4)), kThreads, 0, ctx->stream>>>(p, g, m, v, n, lr_t, 0.9f,
+                                                                       0.999f, 1e-7f);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_zero(fm_ctx* ctx, void* p, size_t bytes) {
+  FM_CUDA(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+  return FM_OK;
+}
+
+int k_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
+                     const int32_t halo_pad[6], const int32_t fit_pad[6], float pad0, float pad1,
+                     const int32_t* idx_dev, int64_t n, const int32_t patch[3], float* out) {
+  GatherGeom gm;
+  for (int a = 0; a < 3; ++a) {
+    gm.vol[a] = vol_dims[a];
+    gm.halo[a] = halo_pad[2 * a];
+    gm.fit[a] = fit_pad[2 * a];
+    gm.halo_dims[a] = vol_dims[a] + halo_pad[2 * a] + halo_pad[2 * a + 1];
+    gm.padded[a] = gm.halo_dims[a] + fit_pad[2 * a] + fit_pad[2 * a + 1];
+    gm.patch[a] = patch[a];
+  }
+  const int64_t total = n * (int64_t)patch[0] * patch[1] * patch[2];
+  gather_patches_kernel<<<grid_for(total, 148 * 32), kThreads, 0, ctx->stream>>>(vol, gm, pad0, pad1,
+                                                                                idx_dev, n, out);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// Host side of the reassembly: turns the corner list into per-axis start lists + per-coordinate
+// covering ranges (the corners of fm_patch_plan are always a Cartesian product in x-major order;
+// anything else is rejected). `preds` holds patches [pred_base, pred_base + n_local) of the plan.
+int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64_t n_total,
+                 int64_t shard_lo, int64_t shard_hi, int64_t pred_base,
+                 const int32_t pred_shape[3], int channels, const int32_t out_dims[3],
+                 double* out_dev, int16_t* count_dev, int divide) {
+  std::vector<int32_t> st[3];
+  for (int a = 0; a < 3; ++a) {
+    for (int64_t i = 0; i < n_total; ++i) {
+      const int32_t v = idx_host[i * 3 + a];
+      bool seen = false;
+      for (int32_t s : st[a]) seen = seen || (s == v);
+      if (!seen) st[a].push_back(v);
+    }
+    for (size_t i = 1; i < st[a].size(); ++i)
+      FM_CHECK(st[a][i] > st[a][i - 1], FM_EINVAL, "reassemble: patch corners not ascending on axis %d", a);
+  }
+  const int64_t np0 = st[0].size(), np1 = st[1].size(), np2 = st[2].size();
+  FM_CHECK(np0 * np1 * np2 == n_total, FM_EINVAL,
+           "reassemble: corner list is not a Cartesian product (%lld*%lld*%lld != %lld)",
+           (long long)np0, (long long)np1, (long long)np2, (long long)n_total);
+  for (int64_t i = 0; i < n_total; ++i) {
+    const int64_t i2 = i % np2, i1 = (i / np2) % np1, i0 = i / (np2 * np1);
+    FM_CHECK(idx_host[i * 3] == st[0][i0] && idx_host[i * 3 + 1] == st[1][i1] &&
+                 idx_host[i * 3 + 2] == st[2][i2],
+             FM_EINVAL, "reassemble: corner list is not in x-major product order at %lld", (long long)i);
+  }
+  int maxnp = (int)std::max(np0, std::max(np1, np2));
+  int maxdim = std::max(out_dims[0], std::max(out_dims[1], out_dims[2]));
+  std::vector<int32_t> starts(3 * (size_t)maxnp, 0), cover(3 * (size_t)maxdim * 2, 0);
+  for (int a = 0; a < 3; ++a) {
+    for (size_t i = 0; i < st[a].size(); ++i) starts[(size_t)a * maxnp + i] = st[a][i];
+    for (int c = 0; c < out_dims[a]; ++c) {
+      int lo = (int)st[a].size(), hi = 0;
+      for (int i = 0; i < (int)st[a].size(); ++i)
+        if (st[a][i] <= c && c < st[a][i] + pred_shape[a]) {
+          lo = std::min(lo, i);
+          hi = std::max(hi, i + 1);
+        }
+      FM_CHECK(hi > lo, FM_EINVAL, "Found zeros in count");  // prediction.py:196
+      for (int i = lo; i < hi; ++i)
+        FM_CHECK(st[a][i] <= c && c < st[a][i] + pred_shape[a], FM_EINVAL,
+                 "reassemble: covering set not contiguous");
+      cover[((size_t)a * maxdim + c) * 2] = lo;
+      cover[((size_t)a * maxdim + c) * 2 + 1] = hi;
+    }
+  }
+  int32_t *d_starts = nullptr, *d_cover = nullptr;
+  FM_CUDA(cudaMallocAsync((void**)&d_starts, starts.size() * 4, ctx->stream));
+  FM_CUDA(cudaMallocAsync((void**)&d_cover, cover.size() * 4, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(d_starts, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(d_cover, cover.data(), cover.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope below
+  ReasmGeom gm;
+  for (int a = 0; a < 3; ++a) {
+    gm.out[a] = out_dims[a];
+    gm.pred[a] = pred_shape[a];
+  }
+  gm.np[0] = (int)np0;
+  gm.np[1] = (int)np1;
+  gm.np[2] = (int)np2;
+  gm.channels = channels;
+  const int64_t total = (int64_t)out_dims[0] * out_dims[1] * out_dims[2] * channels;
+  reassemble_kernel<<<grid_for(total, 148 * 16), kThreads, 0, ctx->stream>>>(
+      preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo, shard_hi, pred_base, out_dev, count_dev,
+      divide);
+  FM_LAUNCH_OK(ctx);
+  FM_CUDA(cudaFreeAsync(d_starts, ctx->stream));
+  FM_CUDA(cudaFreeAsync(d_cover, ctx->stream));
+  return FM_OK;
+}
+
+int k_divide_by_count(fm_ctx* ctx, double* out, const int16_t* count, int64_t nvox, int channels) {
+  divide_by_count_kernel<<<grid_for(nvox * channels, 148 * 16), kThreads, 0, ctx->stream>>>(
+      out, count, nvox, channels);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}

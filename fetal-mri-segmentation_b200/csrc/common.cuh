@@ -1,0 +1,142 @@
+// common.cuh — shared host/device helpers for libfetalb200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fetal_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void fm_set_error(const char* fmt, ...);
+
+#define FM_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      fm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      return FM_ECUDA;                                                                        \
+    }                                                                                         \
+  } while (0)
+
+#define FM_CHECK(cond, code, ...)                                                             \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      fm_set_error(__VA_ARGS__);                                                              \
+      return (code);                                                                          \
+    }                                                                                         \
+  } while (0)
+
+#define FM_TRY(expr)                                                                          \
+  do {                                                                                        \
+    int _r = (expr);                                                                          \
+    if (_r != FM_OK) return _r;                                                               \
+  } while (0)
+
+struct fm_ctx {
+  int device = 0;
+  int sm_major = 0, sm_minor = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // scratch for deterministic two-stage reductions
+  double* red_scratch = nullptr;  // [RED_BLOCKS * 8]
+  // pinned staging for host<->device copies
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Launch-error check that also counts the launch (bench.py reports gpu_launches from this).
+#define FM_LAUNCH_OK(ctx)                                                                     \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      fm_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,                     \
+                   cudaGetErrorString(_e));                                                   \
+      return FM_ECUDA;                                                                        \
+    }                                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// tensor descriptors (device storage is channels-last: [N][X][Y][Z][C], C contiguous)
+// ------------------------------------------------------------------------------------------
+struct Dims5 {
+  int N, X, Y, Z, C;
+  int64_t voxels() const { return (int64_t)N * X * Y * Z; }
+  int64_t elems() const { return voxels() * C; }
+};
+
+// ------------------------------------------------------------------------------------------
+// kernel launch wrappers implemented across the .cu files (all asynchronous on ctx->stream)
+// ------------------------------------------------------------------------------------------
+
+// bandwidth.cu
+int k_cast_f32_to_bf16(fm_ctx*, const float* in, bf16* out, int64_t n);
+int k_cast_bf16_to_f32(fm_ctx*, const bf16* in, float* out, int64_t n);
+int k_maxpool3d_fwd(fm_ctx*, const bf16* x, bf16* y, Dims5 in);
+// dx = relu'(x) * ( dskip(optional) + route(dy) ): fused MaxPooling3D backward + skip-gradient add
+int k_maxpool3d_bwd(fm_ctx*, const bf16* x, const bf16* dy, const bf16* dskip, bf16* dx, Dims5 in,
+                    int relu_mask);
+int k_upsample3d_fwd(fm_ctx*, const bf16* x, bf16* y, Dims5 in);
+// dx[v] = (act? act[v]>0 : 1) * sum_{8 children} dy[child]; `in` = coarse dims
+int k_upsample3d_bwd(fm_ctx*, const bf16* dy, const bf16* act, bf16* dx, Dims5 coarse,
+                     int dy_C, int dy_cofs);
+// loss statistics over p,t (fp32): sums[8] (double) = {tp, t, p, tbpb, tb, pb, correct, count}
+int k_dice_sums(fm_ctx*, const float* p, const float* t, int64_t n, double* sums, int accumulate);
+// dL/dz = dL/dp * p (1-p) with global sums (closed form, metrics.py:11-15)
+int k_dice_bwd(fm_ctx*, const float* p, const float* t, const double* sums, int64_t n, float* dz,
+               int through_sigmoid);
+int k_adam(fm_ctx*, float* p, const float* g, float* m, float* v, int64_t n, int iterations,
+           float lr);
+int k_zero(fm_ctx*, void* p, size_t bytes);
+int k_gather_patches(fm_ctx*, const float* vol, const int32_t vol_dims[3], const int32_t halo_pad[6],
+                     const int32_t fit_pad[6], float pad0, float pad1, const int32_t* idx_dev,
+                     int64_t n, const int32_t patch[3], float* out);
+int k_reassemble(fm_ctx*, const float* preds, const int32_t* idx_host, int64_t n_total,
+                 int64_t shard_lo, int64_t shard_hi, int64_t pred_base, const int32_t pred_shape[3],
+                 int channels, const int32_t out_dims[3], double* out_dev, int16_t* count_dev,
+                 int divide);
+int k_divide_by_count(fm_ctx*, double* out, const int16_t* count, int64_t nvox, int channels);
+
+// conv_simt.cu
+// first layer: fp32 single/multi-channel input (channels-last), small Cin; out bf16 + ReLU
+int k_conv3d_simt_fprop(fm_ctx*, const void* x, int x_is_f32, const bf16* x2, const bf16* w_packed,
+                        const float* bias, bf16* y, float* y_f32, int N, int X, int Y, int Z, int C1,
+                        int C2, int Cout, int ksize, int relu, const bf16* mask);
+int k_conv3d_simt_wgrad(fm_ctx*, const void* x, int x_is_f32, const bf16* dy, float* dw_packed,
+                        int N, int X, int Y, int Z, int Cin, int Cin_total, int cin_ofs, int Cout,
+                        int ksize);
+int k_bias_grad(fm_ctx*, const bf16* dy, float* db, int64_t voxels, int C);
+// 1x1x1 head: z = w.x + b ; p = sigmoid(z) (fp32 out)
+int k_head_fwd(fm_ctx*, const bf16* x, const float* w, const float* b, float* p, int64_t voxels,
+               int C);
+// head backward: dx[v,c] = dz[v] * w[c] * (x[v,c] > 0); dw[c] = sum_v dz[v] x[v,c]; db = sum dz
+int k_head_bwd(fm_ctx*, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
+               float* db, int64_t voxels, int C);
+// weight repack: master fp32 [Cout][taps][Cin] -> bf16 fprop pack (same layout) and bf16 dgrad
+// pack(s) [Cin_s][taps flipped][Cout] per source
+int k_repack_weights(fm_ctx*, const float* w, bf16* w_f, bf16* w_d0, bf16* w_d1, int Cout, int taps,
+                     int C1, int C2);
+
+// conv_tc.cu
+struct ConvTcPlan;  // opaque cached TMA descriptors for one conv launch configuration
+int conv_tc_supported(int C1, int C2, int Cout, int ksize);
+int k_conv3d_tc_fprop(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* w_packed,
+                      const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z,
+                      int C1, int C2, int Cout, int ksize, int relu, int out_C, int out_cofs);
+int k_conv3d_tc_wgrad(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y,
+                      int Z, int Cin, int Cin_total, int cin_ofs, int Cout, int ksize);

@@ -1,0 +1,405 @@
+// conv_simt.cu — the convolutions that are NOT tensor-core shaped, plus small helpers:
+//   * first layer (Cin = 1, K = 27): bandwidth kernel, fp32 volume in -> bf16 NDHWC out
+//   * N = 1 head: 1x1x1 conv + sigmoid fused, and its backward (+ ReLU mask of the producer)
+//   * bias gradients, weight repacking
+//   * a generic direct-convolution fprop / wgrad pair used (a) for shapes the tcgen05 kernels do
+//     not cover and (b) as the on-GPU cross-check of the tcgen05 kernels in tests (`impl = 1`).
+// Keras call sites: Conv3D in create_convolution_block (fetal_net/model/unet3d/unet.py:102) and
+// the final Conv3D(n_labels,(1,1,1)) + sigmoid (unet.py:68-69).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float ldx(const void* x, int is_f32, int64_t i) {
+  return is_f32 ? __ldg(reinterpret_cast<const float*>(x) + i)
+                : __bfloat162float(reinterpret_cast<const bf16*>(x)[i]);
+}
+
+// --------------------------------------------------------------------------------------------
+// generic direct conv (cross-correlation, 'same' zero padding, stride 1), one thread per
+// (voxel, cout). Weights packed [Cout][taps][Cin_total] bf16, tap = (kx*K + ky)*K + kz.
+// --------------------------------------------------------------------------------------------
+__global__ void conv3d_simt_fprop_kernel(const void* __restrict__ x, int x_is_f32,
+                                         const bf16* __restrict__ x2, const bf16* __restrict__ w,
+                                         const float* __restrict__ bias, bf16* __restrict__ y,
+                                         float* __restrict__ y32, int N, int X, int Y, int Z, int C1,
+                                         int C2, int Cout, int K, int relu,
+                                         const bf16* __restrict__ mask) {
+  const int64_t total = (int64_t)N * X * Y * Z * Cout;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int co = (int)(g % Cout);
+  int64_t v = g / Cout;
+  const int z = (int)(v % Z);
+  int64_t r = v / Z;
+  const int yy = (int)(r % Y);
+  r /= Y;
+  const int xx = (int)(r % X);
+  const int n = (int)(r / X);
+  const int pad = K / 2, Ct = C1 + C2, taps = K * K * K;
+  float acc = bias ? bias[co] : 0.f;
+  for (int kx = 0; kx < K; ++kx) {
+    const int xi = xx + kx - pad;
+    if (xi < 0 || xi >= X) continue;
+    for (int ky = 0; ky < K; ++ky) {
+      const int yi = yy + ky - pad;
+      if (yi < 0 || yi >= Y) continue;
+      for (int kz = 0; kz < K; ++kz) {
+        const int zi = z + kz - pad;
+        if (zi < 0 || zi >= Z) continue;
+        const int tap = (kx * K + ky) * K + kz;
+        const int64_t vi = (((int64_t)n * X + xi) * Y + yi) * Z + zi;
+        const bf16* wr = w + ((int64_t)co * taps + tap) * Ct;
+        for (int c = 0; c < C1; ++c) acc += ldx(x, x_is_f32, vi * C1 + c) * __bfloat162float(wr[c]);
+        for (int c = 0; c < C2; ++c)
+          acc += __bfloat162float(x2[vi * C2 + c]) * __bfloat162float(wr[C1 + c]);
+      }
+    }
+  }
+  if (relu) acc = fmaxf(acc, 0.f);
+  if (mask && !(__bfloat162float(mask[g]) > 0.f)) acc = 0.f;
+  if (y) y[g] = __float2bfloat16(acc);
+  if (y32) y32[g] = acc;
+}
+
+// generic wgrad: dw[co][tap][cin_ofs+ci] += sum_v dy[v][co] * x[v+shift(tap)][ci].
+// One warp per output element and voxel chunk; lanes stride over the voxels of the chunk.
+__global__ void conv3d_simt_wgrad_kernel(const void* __restrict__ x, int x_is_f32,
+                                         const bf16* __restrict__ dy, float* __restrict__ dw, int N,
+                                         int X, int Y, int Z, int Cin, int Ct, int cofs, int Cout,
+                                         int K, int64_t vox_per_chunk) {
+  const int taps = K * K * K, pad = K / 2;
+  const int64_t n_out = (int64_t)Cout * taps * Cin;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t o = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (o >= n_out) return;
+  const int lane = threadIdx.x & 31;
+  const int ci = (int)(o % Cin);
+  const int tap = (int)((o / Cin) % taps);
+  const int co = (int)(o / ((int64_t)Cin * taps));
+  const int kz = tap % K, ky = (tap / K) % K, kx = tap / (K * K);
+  const int64_t nvox = (int64_t)N * X * Y * Z;
+  const int64_t v0 = (int64_t)blockIdx.y * vox_per_chunk;
+  const int64_t v1 = min(nvox, v0 + vox_per_chunk);
+  float acc = 0.f;
+  for (int64_t v = v0 + lane; v < v1; v += 32) {
+    const int z = (int)(v % Z);
+    int64_t r = v / Z;
+    const int yy = (int)(r % Y);
+    r /= Y;
+    const int xx = (int)(r % X);
+    const int n = (int)(r / X);
+    const int xi = xx + kx - pad, yi = yy + ky - pad, zi = z + kz - pad;
+    if (xi < 0 || xi >= X || yi < 0 || yi >= Y || zi < 0 || zi >= Z) continue;
+    const int64_t vi = (((int64_t)n * X + xi) * Y + yi) * Z + zi;
+    acc += __bfloat162float(dy[v * Cout + co]) * ldx(x, x_is_f32, vi * Cin + ci);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) atomicAdd(dw + ((int64_t)co * taps + tap) * Ct + cofs + ci, acc);
+}
+
+// --------------------------------------------------------------------------------------------
+// first layer: Cin = 1 fp32 volume, 3x3x3, COUT in {16, 32}. One thread per voxel computes all
+// COUT outputs from 27 L1-cached neighbours; weights live in smem as fp32 [27][COUT] and are
+// read as LDS.128 broadcasts. Writes COUT bf16 (32/64 B) per voxel.
+// --------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) conv3d_first_kernel(const float* __restrict__ x,
+                                                                const bf16* __restrict__ w,
+                                                                const float* __restrict__ bias,
+                                                                bf16* __restrict__ y, int N, int X,
+                                                                int Y, int Z, int relu) {
+  __shared__ __align__(16) float ws[27 * COUT];
+  __shared__ float bs[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+    const int tap = i / COUT, co = i % COUT;
+    ws[i] = __bfloat162float(w[co * 27 + tap]);  // packed [Cout][27][1]
+  }
+  if (threadIdx.x < COUT) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int64_t nvox = (int64_t)N * X * Y * Z;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const int z = (int)(v % Z);
+    int64_t r = v / Z;
+    const int yy = (int)(r % Y);
+    r /= Y;
+    const int xx = (int)(r % X);
+    const int n = (int)(r / X);
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = bs[c];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xi = xx + kx - 1;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yi = yy + ky - 1;
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+          const int zi = z + kz - 1;
+          float xv = 0.f;
+          if (xi >= 0 && xi < X && yi >= 0 && yi < Y && zi >= 0 && zi < Z)
+            xv = __ldg(x + (((int64_t)n * X + xi) * Y + yi) * Z + zi);
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((kx * 3 + ky) * 3 + kz) * COUT);
+#pragma unroll
+          for (int q = 0; q < COUT / 4; ++q) {
+            const float4 ww = wr[q];
+            acc[4 * q + 0] += xv * ww.x;
+            acc[4 * q + 1] += xv * ww.y;
+            acc[4 * q + 2] += xv * ww.z;
+            acc[4 * q + 3] += xv * ww.w;
+          }
+        }
+      }
+    }
+    uint4* out = reinterpret_cast<uint4*>(y + v * COUT);
+#pragma unroll
+    for (int q = 0; q < COUT / 8; ++q) {
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = acc[8 * q + 2 * i], b = acc[8 * q + 2 * i + 1];
+        if (relu) {
+          a = fmaxf(a, 0.f);
+          b = fmaxf(b, 0.f);
+        }
+        h[i] = __floats2bfloat162_rn(a, b);
+      }
+      out[q] = o;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// bias gradient: db[c] += sum_v dy[v][c]. Threads are laid out (voxel-lane, channel) with the
+// channel fastest so each warp reads a contiguous run of rows.
+// --------------------------------------------------------------------------------------------
+__global__ void bias_grad_kernel(const bf16* __restrict__ dy, float* __restrict__ db, int64_t voxels,
+                                 int C, int64_t vox_per_block) {
+  extern __shared__ float sh[];
+  const int lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, l = threadIdx.x / C;
+  const int64_t v0 = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v1 = min(voxels, v0 + vox_per_block);
+  float acc = 0.f;
+  if (l < lanes)
+    for (int64_t v = v0 + l; v < v1; v += lanes) acc += __bfloat162float(dy[v * C + c]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (l == 0) {
+    for (int k = 1; k < lanes; ++k) acc += sh[k * C + c];
+    atomicAdd(db + c, acc);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// head: Conv3D(1,(1,1,1)) + sigmoid (unet.py:68-69). C/8 lanes cooperate on one voxel, each
+// loading 16 B; shuffle-reduce; one fp32 probability per voxel.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restrict__ x,
+                                                            const float* __restrict__ w,
+                                                            const float* __restrict__ b,
+                                                            float* __restrict__ p, int64_t voxels,
+                                                            int C) {
+  const int lpv = C >> 3;  // lanes per voxel (power of two <= 32)
+  const int sub = threadIdx.x % lpv;
+  float wv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + sub * 8 + i);
+  const float bb = __ldg(b);
+  const int64_t vpb = blockDim.x / lpv;
+  // every thread of the block runs the same trip count (the shuffles below need full warps)
+  for (int64_t base = (int64_t)blockIdx.x * vpb; base < voxels; base += (int64_t)gridDim.x * vpb) {
+    const int64_t v = base + threadIdx.x / lpv;
+    float acc = 0.f;
+    if (v < voxels) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        acc += f.x * wv[2 * i] + f.y * wv[2 * i + 1];
+      }
+    }
+    for (int s = lpv >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (sub == 0 && v < voxels) p[v] = 1.f / (1.f + __expf(-(acc + bb)));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restrict__ x,
+                                                            const float* __restrict__ dz,
+                                                            const float* __restrict__ w,
+                                                            bf16* __restrict__ dx,
+                                                            float* __restrict__ dw,
+                                                            float* __restrict__ db, int64_t voxels,
+                                                            int C) {
+  const int lpv = C >> 3;
+  const int sub = threadIdx.x % lpv;
+  float wv[8], gw[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    wv[i] = __ldg(w + sub * 8 + i);
+    gw[i] = 0.f;
+  }
+  float gb = 0.f;
+  const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / lpv);
+  for (int64_t v = (int64_t)blockIdx.x * (blockDim.x / lpv) + threadIdx.x / lpv; v < voxels;
+       v += vstride) {
+    const float g = __ldg(dz + v);
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      gw[2 * i] += g * f.x;
+      gw[2 * i + 1] += g * f.y;
+      oh[i] = __floats2bfloat162_rn(f.x > 0.f ? g * wv[2 * i] : 0.f,
+                                    f.y > 0.f ? g * wv[2 * i + 1] : 0.f);
+    }
+    if (sub == 0) gb += g;
+    *reinterpret_cast<uint4*>(dx + v * C + sub * 8) = o;
+  }
+  // block reduction: threads with equal `sub` hold partial sums of the same 8 channels
+  __shared__ float sh[kThreads][9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[threadIdx.x][i] = gw[i];
+  sh[threadIdx.x][8] = gb;
+  __syncthreads();
+  if ((int)threadIdx.x < lpv) {
+    float a[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int tt = threadIdx.x; tt < kThreads; tt += lpv)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) a[i] += sh[tt][i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dw + threadIdx.x * 8 + i, a[i]);
+    if (threadIdx.x == 0) atomicAdd(db, a[8]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// weight repack: master fp32 [Cout][taps][Ct] -> bf16 fprop pack (same order) and the dgrad packs
+// Wd_s[ci][tap'][co] = W[co][taps-1-tap'][cofs_s + ci]  (spatially flipped, in/out swapped)
+// --------------------------------------------------------------------------------------------
+__global__ void repack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wf,
+                                      bf16* __restrict__ wd0, bf16* __restrict__ wd1, int Cout,
+                                      int taps, int C1, int C2) {
+  const int Ct = C1 + C2;
+  const int64_t total = (int64_t)Cout * taps * Ct;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int c = (int)(g % Ct);
+  const int tap = (int)((g / Ct) % taps);
+  const int co = (int)(g / ((int64_t)Ct * taps));
+  const bf16 v = __float2bfloat16(w[g]);
+  if (wf) wf[g] = v;
+  const int tf = taps - 1 - tap;
+  if (c < C1) {
+    if (wd0) wd0[((int64_t)c * taps + tf) * Cout + co] = v;
+  } else {
+    if (wd1) wd1[((int64_t)(c - C1) * taps + tf) * Cout + co] = v;
+  }
+}
+
+inline int grid_for(int64_t work_items, int cap = 1 << 30) {
+  int64_t b = ceil_div64(work_items, kThreads);
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2, const bf16* w_packed,
+                        const float* bias, bf16* y, float* y_f32, int N, int X, int Y, int Z, int C1,
+                        int C2, int Cout, int ksize, int relu, const bf16* mask) {
+  if (x_is_f32 && C1 == 1 && C2 == 0 && ksize == 3 && y != nullptr && y_f32 == nullptr &&
+      mask == nullptr && bias != nullptr && (Cout == 16 || Cout == 32)) {
+    const int64_t nvox = (int64_t)N * X * Y * Z;
+    const int grid = grid_for(nvox, ctx->num_sms * 16);
+    if (Cout == 16)
+      conv3d_first_kernel<16><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, w_packed, bias, y,
+                                                                 N, X, Y, Z, relu);
+    else
+      conv3d_first_kernel<32><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, w_packed, bias, y,
+                                                                 N, X, Y, Z, relu);
+    FM_LAUNCH_OK(ctx);
+    return FM_OK;
+  }
+  const int64_t total = (int64_t)N * X * Y * Z * Cout;
+  conv3d_simt_fprop_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(
+      x, x_is_f32, x2, w_packed, bias, y, y_f32, N, X, Y, Z, C1, C2, Cout, ksize, relu, mask);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy, float* dw_packed,
+                        int N, int X, int Y, int Z, int Cin, int Cin_total, int cin_ofs, int Cout,
+                        int ksize) {
+  const int taps = ksize * ksize * ksize;
+  const int64_t n_out = (int64_t)Cout * taps * Cin;
+  const int64_t nvox = (int64_t)N * X * Y * Z;
+  // enough voxel chunks that small layers (the 432 outputs of the first layer) still fill the GPU
+  int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms * 64 / std::max<int64_t>(1, n_out / 8));
+  chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, nvox / 1024));
+  chunks = std::min<int64_t>(chunks, 65535);
+  const int64_t vpc = ceil_div64(nvox, chunks);
+  dim3 grid((unsigned)ceil_div64(n_out, kThreads / 32), (unsigned)ceil_div64(nvox, vpc));
+  conv3d_simt_wgrad_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, x_is_f32, dy, dw_packed, N, X, Y, Z,
+                                                              Cin, Cin_total, cin_ofs, Cout, ksize,
+                                                              vpc);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_bias_grad(fm_ctx* ctx, const bf16* dy, float* db, int64_t voxels, int C) {
+  FM_CHECK(C >= 1 && C <= 1024, FM_EINVAL, "bias_grad: C=%d unsupported", C);
+  const int lanes = std::max(1, kThreads / C);
+  const int threads = C * lanes;
+  int64_t blocks = std::min<int64_t>((int64_t)ctx->num_sms * 8, std::max<int64_t>(1, voxels / (lanes * 8)));
+  const int64_t vpb = ceil_div64(voxels, blocks);
+  blocks = ceil_div64(voxels, vpb);
+  bias_grad_kernel<<<(unsigned)blocks, threads, threads * sizeof(float), ctx->stream>>>(dy, db, voxels,
+                                                                                       C, vpb);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float* p, int64_t voxels,
+               int C) {
+  FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
+           "head: channel count %d must be a power of two in [8,256]", C);
+  const int lpv = C / 8;
+  const int64_t vpb = kThreads / lpv;
+  const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 32);
+  head_fwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, w, b, p, voxels, C);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
+               float* db, int64_t voxels, int C) {
+  FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
+           "head_bwd: channel count %d must be a power of two in [8,256]", C);
+  const int lpv = C / 8;
+  const int64_t vpb = kThreads / lpv;
+  const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 8);
+  head_bwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, dz, w, dx, dw, db, voxels, C);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_repack_weights(fm_ctx* ctx, const float* w, bf16* w_f, bf16* w_d0, bf16* w_d1, int Cout, int taps,
+                     int C1, int C2) {
+  const int64_t total = (int64_t)Cout * taps * (C1 + C2);
+  repack_weights_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(w, w_f, w_d0, w_d1, Cout, taps,
+                                                                      C1, C2);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}

@@ -1,0 +1,783 @@
+// conv_tc.cu — Conv3D as implicit GEMM on the 5th-generation tensor cores (sm_100a):
+// tcgen05.mma with TMEM accumulators, operands staged in shared memory by TMA, mbarrier pipeline,
+// warp-specialised (1 TMA producer warp, 1 MMA issuer warp, 4 epilogue warps), persistent CTAs.
+//
+//   fprop :  Y[v, co]  = act( sum_{tap, ci} X[v + shift(tap), ci] * W[co, tap, ci] + b[co] )
+//            GEMM view  M = voxels (tile = 128-voxel box), N = Cout, K = taps * Cin.
+//            A tile (128 voxels x KC channels, K-major) is ONE 5-D TMA box of the channels-last
+//            activation tensor at tap-shifted coordinates — out-of-bounds rows are zero-filled by
+//            TMA, which is exactly Keras' padding='same'. Up to two input tensors (K range split)
+//            make the skip `concatenate([up, skip], axis=1)` (unet3d/unet.py:61) zero-copy.
+//   dgrad :  the same kernel on dY with spatially flipped, in/out-swapped weights; the epilogue
+//            applies the ReLU mask of the producing block instead of bias+ReLU.
+//   wgrad :  dW[co, tap, ci] = sum_v dY[v, co] * X[v + shift(tap), ci]
+//            GEMM view  M = (tap, ci) stacked to 128 rows, N = Cout, K = voxels. Both operands are
+//            MN-major (the voxel axis is K and channels are contiguous in memory), accumulators for
+//            up to 512/N tap groups stay in TMEM for the whole voxel range of the CTA (split-K over
+//            CTAs, fp32 red.add into the gradient buffer).
+//
+// Keras call site replaced: Conv3D(n_filters, kernel, padding='same') in create_convolution_block
+// (fetal_net/model/unet3d/unet.py:102) and its TF autodiff gradients.
+#include "common.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a trap (clean CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("fetalb200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tm, uint32_t bar, int c0,
+                                            int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const void* tm, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, single-CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (SM100 format, version 1).
+//   bits [ 0,14) start address >> 4      bits [16,30) leading byte offset >> 4
+//   bits [32,46) stride byte offset >> 4 bits [46,48) version = 1   bits [61,64) swizzle mode
+// K-major swizzled tile (rows of 32/64/128 B): SBO = 8 rows, LBO unused (=1).
+// MN-major swizzled tile (k-rows of 32/64/128 B holding MN-contiguous elements): SBO = 8 k-rows,
+// LBO = distance between consecutive swizzle-wide MN blocks.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7u) << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 bits 17-22, M>>4 bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kTileM = 128;      // voxels per M tile == TMEM lanes
+constexpr int kThreadsTc = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t kABytes = kTileM * 128;  // A slot: 128 rows x 128 B (largest swizzle span)
+
+// swizzle span in bytes -> UMMA layout_type code
+__host__ __device__ constexpr uint32_t layout_code(int row_bytes) {
+  return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+}
+
+struct alignas(64) FpropParams {
+  CUtensorMap tmA[2];  // activation sources (5-D: C, Z, Y, X, N)
+  CUtensorMap tmW[2];  // packed weights per source (3-D: Cin_total, taps, Cout)
+  int nsrc;
+  int nchunks[2];  // C_s / KC_s
+  int KC[2];       // channels per K chunk (16, 32 or 64)
+  int wcofs[2];    // channel offset of the source inside the weight Cin axis
+  int N, X, Y, Z;
+  int bx, by, bz, tx, ty, tz;
+  int m_tiles, n_tiles, block_n;
+  int ksize, ntaps;
+  int out_C, out_cofs;
+  int relu;
+  int stages;
+  const float* bias;
+  bf16* out;
+  const bf16* mask;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
+    const __grid_constant__ FpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t bar0 = smem0 + (uint32_t)p.stages * stage_bytes;
+  // barrier map: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base address word
+  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 4);
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2u * (uint32_t)p.block_n) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) {
+      prefetch_tmap(&p.tmA[s]);
+      prefetch_tmap(&p.tmW[s]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int pad = p.ksize >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        const int iz = m % p.tz;
+        m /= p.tz;
+        const int iy = m % p.ty;
+        m /= p.ty;
+        const int ix = m % p.tx;
+        const int n = m / p.tx;
+        const int x0 = ix * p.bx, y0 = iy * p.by, z0 = iz * p.bz;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
+          for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+            for (int tap = 0; tap < p.ntaps; ++tap, ++it) {
+              const uint32_t stage = it % (uint32_t)p.stages;
+              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+              mbar_wait(empty_bar(stage), ph ^ 1u);
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              const int dz = tap % p.ksize - pad;
+              const int dy = (tap / p.ksize) % p.ksize - pad;
+              const int dx = tap / (p.ksize * p.ksize) - pad;
+              const uint32_t a_dst = smem0 + stage * stage_bytes;
+              tma_load_5d(a_dst, &p.tmA[s], full_bar(stage), ch * p.KC[s], z0 + dz, y0 + dy, x0 + dx,
+                          n);
+              tma_load_3d(a_dst + kABytes, &p.tmW[s], full_bar(stage), p.wcofs[s] + ch * p.KC[s], tap,
+                          n_tile * p.block_n);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      const uint32_t idesc = make_idesc(kTileM, p.block_n, 0, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
+          const uint32_t sbo = 8u * row_bytes;
+          const uint32_t lt = layout_code((int)row_bytes);
+          const int nk = p.KC[s] >> 4;
+          for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+            for (int tap = 0; tap < p.ntaps; ++tap, ++it) {
+              const uint32_t stage = it % (uint32_t)p.stages;
+              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+              mbar_wait(full_bar(stage), ph);
+              tc_fence_after();
+              const uint32_t a_addr = smem0 + stage * stage_bytes;
+              const uint32_t b_addr = a_addr + kABytes;
+              for (int k = 0; k < nk; ++k) {
+                const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+                const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
+                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+            }
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias/ReLU (fprop) or ReLU mask (dgrad) -> bf16 -> HBM =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rz = row % p.bz, ry = (row / p.bz) % p.by, rx = row / (p.bz * p.by);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int iz = m % p.tz;
+      m /= p.tz;
+      const int iy = m % p.ty;
+      m /= p.ty;
+      const int ix = m % p.tx;
+      const int n = m / p.tx;
+      const int x = ix * p.bx + rx, y = iy * p.by + ry, z = iz * p.bz + rz;
+      const bool valid = (x < p.X) && (y < p.Y) && (z < p.Z);
+      const int64_t v = (((int64_t)n * p.X + x) * p.Y + y) * p.Z + z;
+      const int64_t off = v * p.out_C + p.out_cofs + n_tile * p.block_n;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.block_n;
+      for (int c16 = 0; c16 < p.block_n / 16; ++c16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)c16 * 16u, r);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+            const float4* bp =
+                reinterpret_cast<const float4*>(p.bias + n_tile * p.block_n + c16 * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              f[4 * j] += b4.x;
+              f[4 * j + 1] += b4.y;
+              f[4 * j + 2] += b4.z;
+              f[4 * j + 3] += b4.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.mask != nullptr) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off + c16 * 16);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 mv = __ldg(mp + h);
+              const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 mf = __bfloat1622float2(mh[j]);
+                if (!(mf.x > 0.f)) f[8 * h + 2 * j] = 0.f;
+                if (!(mf.y > 0.f)) f[8 * h + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+          uint4 o[2];
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          uint4* op = reinterpret_cast<uint4*>(p.out + off + c16 * 16);
+          op[0] = o[0];
+          op[1] = o[1];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel
+// ---------------------------------------------------------------------------------------------
+struct alignas(64) WgradParams {
+  CUtensorMap tmX;   // input activation (5-D), box = (KC, bz, by, bx, 1)
+  CUtensorMap tmDY;  // output gradient (5-D), box = (NC, bz, by, bx, 1)
+  int KC, NC;        // channel chunk of X rows / dY sub-box
+  int g;             // taps stacked per 128-row group = 128 / KC
+  int ngroups;       // ceil(ntaps / g)
+  int G;             // groups per CTA (accumulators resident in TMEM)
+  int n_gsub;        // ceil(ngroups / G)
+  int n_cchunks;     // Cin / KC
+  int n_nblocks;     // Cout / NB
+  int NB;            // Cout block (MMA N)
+  int splits;        // split-K factor over voxel tiles
+  int N, X, Y, Z;
+  int bx, by, bz, tx, ty, tz;
+  int m_tiles;
+  int ksize, ntaps;
+  int Ct, cofs, Cout;  // dW layout [Cout][ntaps][Ct], this source at channel offset cofs
+  int stages;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
+    const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // smem: [stages] x 32 KB A slots (g tap tiles of 128 voxels x KC), then 2 dY buffers (128 x NB)
+  const uint32_t a_slot = 32768u;
+  const uint32_t dy_bytes = (uint32_t)kTileM * (uint32_t)p.NB * 2u;
+  const uint32_t dy0 = smem0 + (uint32_t)p.stages * a_slot;
+  const uint32_t bar0 = dy0 + 2u * dy_bytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
+  auto dyfull_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * p.stages + b); };
+  auto dyempty_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * p.stages + 2 + b); };
+  const uint32_t done_bar = bar0 + 8u * (uint32_t)(2 * p.stages + 4);
+  const uint32_t tmem_slot = bar0 + 8u * (uint32_t)(2 * p.stages + 5);
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(p.G * p.NB)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmX);
+    prefetch_tmap(&p.tmDY);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(dyfull_bar(b), 1);
+        mbar_init(dyempty_bar(b), 1);
+      }
+      mbar_init(done_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // work item decode: blockIdx.x = ((split * n_nblocks + nb) * n_cchunks + cc) * n_gsub + gs
+  int w = blockIdx.x;
+  const int gs = w % p.n_gsub;
+  w /= p.n_gsub;
+  const int cc = w % p.n_cchunks;
+  w /= p.n_cchunks;
+  const int nb = w % p.n_nblocks;
+  const int split = w / p.n_nblocks;
+  const int g_first = gs * p.G;
+  const int g_count = min(p.G, p.ngroups - g_first);
+  const int mt0 = (int)(((int64_t)p.m_tiles * split) / p.splits);
+  const int mt1 = (int)(((int64_t)p.m_tiles * (split + 1)) / p.splits);
+  const int pad = p.ksize >> 1;
+  const uint32_t tap_tile_bytes = (uint32_t)kTileM * (uint32_t)p.KC * 2u;
+  const uint32_t dy_sub_bytes = (uint32_t)kTileM * (uint32_t)p.NC * 2u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, vt = 0;
+      for (int mt = mt0; mt < mt1; ++mt, ++vt) {
+        int m = mt;
+        const int iz = m % p.tz;
+        m /= p.tz;
+        const int iy = m % p.ty;
+        m /= p.ty;
+        const int ix = m % p.tx;
+        const int n = m / p.tx;
+        const int x0 = ix * p.bx, y0 = iy * p.by, z0 = iz * p.bz;
+        const uint32_t b = vt & 1u, bph = (vt >> 1) & 1u;
+        mbar_wait(dyempty_bar(b), bph ^ 1u);
+        mbar_expect_tx(dyfull_bar(b), dy_bytes);
+        for (int j = 0; j < p.NB / p.NC; ++j)
+          tma_load_5d(dy0 + b * dy_bytes + (uint32_t)j * dy_sub_bytes, &p.tmDY, dyfull_bar(b),
+                      nb * p.NB + j * p.NC, z0, y0, x0, n);
+        for (int gi = 0; gi < g_count; ++gi, ++it) {
+          const uint32_t stage = it % (uint32_t)p.stages;
+          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+          mbar_wait(empty_bar(stage), ph ^ 1u);
+          mbar_expect_tx(full_bar(stage), (uint32_t)p.g * tap_tile_bytes);
+          for (int t = 0; t < p.g; ++t) {
+            const int tap = min((g_first + gi) * p.g + t, p.ntaps - 1);  // pad group with a repeat
+            const int dz = tap % p.ksize - pad;
+            const int dy = (tap / p.ksize) % p.ksize - pad;
+            const int dx = tap / (p.ksize * p.ksize) - pad;
+            tma_load_5d(smem0 + stage * a_slot + (uint32_t)t * tap_tile_bytes, &p.tmX, full_bar(stage),
+                        cc * p.KC, z0 + dz, y0 + dy, x0 + dx, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kTileM, p.NB, 1, 1);
+      const uint32_t a_row = (uint32_t)p.KC * 2u, b_row = (uint32_t)p.NC * 2u;
+      const uint32_t a_sbo = 8u * a_row, b_sbo = 8u * b_row;
+      const uint32_t a_lt = layout_code((int)a_row), b_lt = layout_code((int)b_row);
+      uint32_t it = 0, vt = 0;
+      for (int mt = mt0; mt < mt1; ++mt, ++vt) {
+        const uint32_t b = vt & 1u, bph = (vt >> 1) & 1u;
+        mbar_wait(dyfull_bar(b), bph);
+        tc_fence_after();
+        const uint32_t b_addr = dy0 + b * dy_bytes;
+        for (int gi = 0; gi < g_count; ++gi, ++it) {
+          const uint32_t stage = it % (uint32_t)p.stages;
+          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+          mbar_wait(full_bar(stage), ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem0 + stage * a_slot;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.NB);
+#pragma unroll 1
+          for (int ks = 0; ks < kTileM / 16; ++ks) {  // 16 voxels (two 8-row k groups) per MMA
+            const uint64_t ad =
+                make_smem_desc(a_addr + (uint32_t)ks * 2u * a_sbo, tap_tile_bytes, a_sbo, a_lt);
+            const uint64_t bd =
+                make_smem_desc(b_addr + (uint32_t)ks * 2u * b_sbo, dy_sub_bytes, b_sbo, b_lt);
+            umma_bf16(d_tmem, ad, bd, idesc, (vt > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+        }
+        umma_commit(dyempty_bar(b));
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;     // (tap within group, channel within chunk)
+    const int t_in_g = row / p.KC, ci = row % p.KC;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (mt1 > mt0) {
+      for (int gi = 0; gi < g_count; ++gi) {
+        const int tap = (g_first + gi) * p.g + t_in_g;
+        const bool valid = tap < p.ntaps;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * p.NB);
+        for (int c16 = 0; c16 < p.NB / 16; ++c16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)c16 * 16u, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = nb * p.NB + c16 * 16 + j;
+              atomicAdd(p.dw + ((int64_t)co * p.ntaps + tap) * p.Ct + p.cofs + cc * p.KC + ci,
+                        __uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: TMA descriptors and launch configuration
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 5-D map over a channels-last activation tensor [N][X][Y][Z][C] (bf16), box (cbox, bz, by, bx, 1)
+int make_act_tmap(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int cbox,
+                  int bz, int by, int bx) {
+  PFN_encodeTiled enc = get_encode();
+  FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2,
+                           (cuuint64_t)X * Y * Z * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cbox * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA,
+           "cuTensorMapEncodeTiled(act) failed: %d (N=%d %dx%dx%d C=%d box c=%d z=%d y=%d x=%d)", (int)r,
+           N, X, Y, Z, C, cbox, bz, by, bx);
+  return FM_OK;
+}
+
+// 3-D map over packed weights [Cout][taps][Ct] (bf16), box (kc, 1, nrows)
+int make_w_tmap(CUtensorMap* tm, const bf16* base, int Cout, int taps, int Ct, int kc, int nrows) {
+  PFN_encodeTiled enc = get_encode();
+  FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)Ct, (cuuint64_t)taps, (cuuint64_t)Cout};
+  cuuint64_t strides[2] = {(cuuint64_t)Ct * 2, (cuuint64_t)taps * Ct * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, 1, (cuuint32_t)nrows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA, "cuTensorMapEncodeTiled(weights) failed: %d (Cout=%d taps=%d Ct=%d)",
+           (int)r, Cout, taps, Ct);
+  return FM_OK;
+}
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// 128-voxel tile box: z fastest, powers of two
+void choose_box(int X, int Y, int Z, int* bx, int* by, int* bz) {
+  int z = std::min(kTileM, pow2_ceil(Z));
+  int y = std::min(kTileM / z, pow2_ceil(Y));
+  int x = kTileM / (z * y);
+  *bz = z;
+  *by = y;
+  *bx = x;
+}
+
+bool chan_ok(int C) { return C > 0 && C % 16 == 0 && (C <= 64 ? (C == 16 || C == 32 || C == 64) : C % 64 == 0); }
+int chunk_of(int C) { return std::min(C, 64); }
+
+const int kMaxDynSmem = 227 * 1024;
+
+}  // namespace
+
+int conv_tc_supported(int C1, int C2, int Cout, int ksize) {
+  if (!(ksize == 1 || ksize == 3)) return 0;
+  if (!chan_ok(C1)) return 0;
+  if (C2 != 0 && !chan_ok(C2)) return 0;
+  if (!(Cout == 16 || Cout == 32 || Cout == 64 || (Cout >= 128 && Cout % 128 == 0))) return 0;
+  return 1;
+}
+
+int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w_packed,
+                      const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1,
+                      int C2, int Cout, int ksize, int relu, int out_C, int out_cofs) {
+  FM_CHECK(conv_tc_supported(C1, C2, Cout, ksize), FM_EINVAL,
+           "conv3d tc: unsupported channels C1=%d C2=%d Cout=%d k=%d", C1, C2, Cout, ksize);
+  FM_CHECK(out_C % 8 == 0 && out_cofs % 8 == 0, FM_EINVAL, "conv3d tc: output channel pitch/offset");
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  p.nsrc = C2 > 0 ? 2 : 1;
+  p.N = N;
+  p.X = X;
+  p.Y = Y;
+  p.Z = Z;
+  choose_box(X, Y, Z, &p.bx, &p.by, &p.bz);
+  p.tx = ceil_div(X, p.bx);
+  p.ty = ceil_div(Y, p.by);
+  p.tz = ceil_div(Z, p.bz);
+  p.m_tiles = N * p.tx * p.ty * p.tz;
+  p.block_n = std::min(Cout, 128);
+  p.n_tiles = Cout / p.block_n;
+  p.ksize = ksize;
+  p.ntaps = ksize * ksize * ksize;
+  p.out_C = out_C;
+  p.out_cofs = out_cofs;
+  p.relu = relu;
+  p.bias = bias;
+  p.out = y;
+  p.mask = mask;
+  const int Ct = C1 + C2;
+  const int Cs[2] = {C1, C2};
+  const bf16* xs[2] = {x1, x2};
+  int cofs = 0;
+  for (int s = 0; s < p.nsrc; ++s) {
+    p.KC[s] = chunk_of(Cs[s]);
+    p.nchunks[s] = Cs[s] / p.KC[s];
+    p.wcofs[s] = cofs;
+    FM_TRY(make_act_tmap(&p.tmA[s], xs[s], N, X, Y, Z, Cs[s], p.KC[s], p.bz, p.by, p.bx));
+    FM_TRY(make_w_tmap(&p.tmW[s], w_packed, Cout, p.ntaps, Ct, p.KC[s], p.block_n));
+    cofs += Cs[s];
+  }
+  const uint32_t stage_bytes = kABytes + (uint32_t)p.block_n * 128u;
+  int stages = (kMaxDynSmem - 2048) / (int)stage_bytes;
+  stages = std::max(2, std::min(stages, 8));
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FM_CUDA(cudaFuncSetAttribute(conv3d_tc_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxDynSmem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.m_tiles * p.n_tiles, ctx->num_sms);
+  conv3d_tc_fprop_kernel<<<grid, kThreadsTc, smem, ctx->stream>>>(p);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_conv3d_tc_wgrad(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y,
+                      int Z, int Cin, int Cin_total, int cin_ofs, int Cout, int ksize) {
+  FM_CHECK(conv_tc_supported(Cin, 0, Cout, ksize), FM_EINVAL,
+           "conv3d tc wgrad: unsupported channels Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.X = X;
+  p.Y = Y;
+  p.Z = Z;
+  choose_box(X, Y, Z, &p.bx, &p.by, &p.bz);
+  p.tx = ceil_div(X, p.bx);
+  p.ty = ceil_div(Y, p.by);
+  p.tz = ceil_div(Z, p.bz);
+  p.m_tiles = N * p.tx * p.ty * p.tz;
+  p.ksize = ksize;
+  p.ntaps = ksize * ksize * ksize;
+  p.KC = chunk_of(Cin);
+  p.n_cchunks = Cin / p.KC;
+  p.g = kTileM / p.KC;
+  p.ngroups = ceil_div(p.ntaps, p.g);
+  p.NB = std::min(Cout, 128);
+  p.NC = std::min(p.NB, 64);
+  p.n_nblocks = Cout / p.NB;
+  p.G = std::min(p.ngroups, 512 / p.NB);
+  p.n_gsub = ceil_div(p.ngroups, p.G);
+  p.Ct = Cin_total;
+  p.cofs = cin_ofs;
+  p.Cout = Cout;
+  p.dw = dw_packed;
+  const int items = p.n_gsub * p.n_cchunks * p.n_nblocks;
+  int splits = std::max(1, (2 * ctx->num_sms) / items);
+  splits = std::min(splits, p.m_tiles);
+  p.splits = splits;
+  FM_TRY(make_act_tmap(&p.tmX, x, N, X, Y, Z, Cin, p.KC, p.bz, p.by, p.bx));
+  FM_TRY(make_act_tmap(&p.tmDY, dy, N, X, Y, Z, Cout, p.NC, p.bz, p.by, p.bx));
+  const uint32_t dy_bytes = (uint32_t)kTileM * (uint32_t)p.NB * 2u;
+  int stages = (kMaxDynSmem - 2048 - 2 * (int)dy_bytes) / 32768;
+  stages = std::max(2, std::min(stages, 5));
+  p.stages = stages;
+  const size_t smem = (size_t)stages * 32768 + 2 * dy_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FM_CUDA(cudaFuncSetAttribute(conv3d_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxDynSmem));
+    attr_set = true;
+  }
+  conv3d_tc_wgrad_kernel<<<items * splits, kThreadsTc, smem, ctx->stream>>>(p);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}

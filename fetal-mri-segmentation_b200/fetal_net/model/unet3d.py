@@ -1,0 +1,252 @@
+"""`unet_model_3d` — the reference builder (fetal_net/model/unet3d/unet.py:17-86) over libfetalb200.
+
+Returns a `Model` with the Keras-Model members the reference's callers use:
+predict / output_shape (prediction.py:129-134,361), fit_generator (training.py:110-124),
+train_on_batch / evaluate / metrics_names / optimizer.lr (experiments/train_adv.py:227,257,220,285),
+summary (train_fetal.py:44), load_weights / save / save_weights (train_fetal.py:43, training.py:83).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .. import _lib
+from ..metrics import dice_coefficient_loss
+
+
+class _Optimizer:
+    """`model.optimizer.lr` as used by Keras callbacks (ReduceLROnPlateau sets it)."""
+
+    def __init__(self, lr):
+        self.lr = float(lr)
+        self.beta_1, self.beta_2, self.epsilon = 0.9, 0.999, 1e-7
+
+
+class Model:
+    """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
+
+    def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
+                 device=None):
+        lib = _lib.load()
+        self._ctx = _lib.get_context(device)
+        in_ch, X, Y, Z = [int(v) for v in input_shape]
+        spec = _lib.UNet3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(n_labels))
+        h = _lib.c_vp()
+        _lib.check(lib.fm_model_create_unet3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+        self._h = h
+        self._lib = lib
+        self.input_shape = (None, in_ch, X, Y, Z)
+        self.output_shape = (None, int(n_labels), X, Y, Z)
+        self.depth = int(depth)
+        self.n_base_filters = int(n_base_filters)
+        self.n_labels = int(n_labels)
+        self.optimizer = _Optimizer(initial_learning_rate)
+        self.loss = loss_function
+        self.metrics = ['binary_accuracy', 'vod_coefficient']
+        self.metrics_names = ['loss', 'binary_accuracy', 'vod_coefficient']
+        if loss_function is not dice_coefficient_loss:
+            self.metrics_names.append('dice_coefficient')
+        self.stop_training = False
+        self.name = 'unet_model_3d'
+        # layer table (Keras creation order; Keras would name them conv3d_1..conv3d_N)
+        self.layers = []
+        for i in range(lib.fm_model_num_layers(h)):
+            name = ctypes.create_string_buffer(32)
+            info = (ctypes.c_int64 * 5)()
+            _lib.check(lib.fm_model_layer_info(h, i, name, info))
+            self.layers.append(dict(index=i, name=name.value.decode(), keras_name="conv3d_%d" % (i + 1),
+                                    cin=int(info[0]), cout=int(info[1]), k=int(info[2])))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.fm_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------
+    def count_params(self):
+        return int(self._lib.fm_model_num_params(self._h))
+
+    def get_weights(self):
+        """[kernel_1, bias_1, kernel_2, ...] in Keras layout (k,k,k,Cin,Cout) / (Cout,)."""
+        out = []
+        for l in self.layers:
+            k = np.empty((l["k"],) * 3 + (l["cin"], l["cout"]), np.float32)
+            b = np.empty((l["cout"],), np.float32)
+            _lib.check(self._lib.fm_model_get_weights(self._h, l["index"], _lib.fptr(k), _lib.fptr(b)))
+            out += [k, b]
+        return out
+
+    def set_weights(self, weights):
+        assert len(weights) == 2 * len(self.layers), "expected %d arrays" % (2 * len(self.layers))
+        for l in self.layers:
+            k = _lib.f32c(weights[2 * l["index"]])
+            b = _lib.f32c(weights[2 * l["index"] + 1])
+            assert k.shape == (l["k"],) * 3 + (l["cin"], l["cout"]), (l["name"], k.shape)
+            assert b.shape == (l["cout"],), (l["name"], b.shape)
+            _lib.check(self._lib.fm_model_set_weights(self._h, l["index"], _lib.fptr(k), _lib.fptr(b)))
+
+    def get_gradients(self):
+        """Gradients of the last train step (Keras layout) - test hook."""
+        out = []
+        for l in self.layers:
+            k = np.empty((l["k"],) * 3 + (l["cin"], l["cout"]), np.float32)
+            b = np.empty((l["cout"],), np.float32)
+            _lib.check(self._lib.fm_model_get_grads(self._h, l["index"], _lib.fptr(k), _lib.fptr(b)))
+            out += [k, b]
+        return out
+
+    def set_named_weights(self, named):
+        """`named`: {'<layer>/kernel': ..., '<layer>/bias': ...} keyed by our layer names (enc0a ...)."""
+        self.set_weights([named["%s/%s" % (l["name"], kind)] for l in self.layers for kind in ("kernel", "bias")])
+
+    def init_glorot_uniform(self, seed=0):
+        """Keras default initialisation (glorot_uniform kernels, zero biases)."""
+        rng = np.random.default_rng(seed)
+        ws = []
+        for l in self.layers:
+            rf = l["k"] ** 3
+            limit = np.sqrt(6.0 / (rf * l["cin"] + rf * l["cout"]))
+            ws.append(rng.uniform(-limit, limit, size=(l["k"],) * 3 + (l["cin"], l["cout"])).astype(np.float32))
+            ws.append(np.zeros((l["cout"],), np.float32))
+        self.set_weights(ws)
+
+    def save_weights(self, path):
+        """HDF5 is absent in this image: weights go to an .npz keyed by Keras layer names."""
+        arrays = {}
+        for l, (k, b) in zip(self.layers, zip(*[iter(self.get_weights())] * 2)):
+            arrays[l["keras_name"] + "/kernel:0"] = k
+            arrays[l["keras_name"] + "/bias:0"] = b
+        arrays["__config__"] = np.array([self.input_shape[1], self.input_shape[2], self.input_shape[3],
+                                         self.input_shape[4], self.depth, self.n_base_filters, self.n_labels])
+        with open(path, "wb") as f:   # keep the caller's file name (e.g. '...-epoch01-loss-0.5.h5')
+            np.savez(f, **arrays)
+
+    save = save_weights
+
+    def load_weights(self, path):
+        with np.load(path) as z:
+            ws = []
+            for l in self.layers:
+                ws += [z[l["keras_name"] + "/kernel:0"], z[l["keras_name"] + "/bias:0"]]
+        self.set_weights(ws)
+
+    def reset_optimizer(self):
+        _lib.check(self._lib.fm_model_reset_optimizer(self._h))
+
+    # ---- inference -------------------------------------------------------------------------
+    def predict(self, x, batch_size=32, verbose=0):
+        x = _lib.f32c(x)
+        assert x.ndim == 5 and x.shape[1:] == self.input_shape[1:], \
+            "expected [B,%s], got %s" % (self.input_shape[1:], x.shape)
+        out = np.empty((x.shape[0], self.n_labels) + x.shape[2:], np.float32)
+        for b0 in range(0, x.shape[0], batch_size):
+            xb = x[b0:b0 + batch_size]
+            yb = out[b0:b0 + batch_size]
+            _lib.check(self._lib.fm_predict(self._h, _lib.fptr(xb), int(xb.shape[0]), _lib.fptr(yb)))
+        return out
+
+    # ---- training --------------------------------------------------------------------------
+    def _check_loss(self):
+        if self.loss is not dice_coefficient_loss:
+            raise NotImplementedError("only dice_coefficient_loss is built on the device path")
+
+    def train_on_batch(self, x, y, **kw):
+        self._check_loss()
+        x, y = _lib.f32c(x), _lib.f32c(y)
+        assert x.shape[0] == y.shape[0] and x.shape[2:] == y.shape[2:]
+        m = np.zeros(4, np.float32)
+        _lib.check(self._lib.fm_train_step(self._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]),
+                                           float(self.optimizer.lr), _lib.fptr(m)))
+        return [float(v) for v in m[:len(self.metrics_names)]]
+
+    def test_on_batch(self, x, y, **kw):
+        x, y = _lib.f32c(x), _lib.f32c(y)
+        m = np.zeros(4, np.float32)
+        _lib.check(self._lib.fm_evaluate(self._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]), _lib.fptr(m)))
+        return [float(v) for v in m[:len(self.metrics_names)]]
+
+    def evaluate(self, x, y, batch_size=32, verbose=0):
+        """Keras semantics: per-batch metrics averaged with batch-size weights."""
+        tot, n = np.zeros(len(self.metrics_names)), 0
+        for b0 in range(0, len(x), batch_size):
+            r = self.test_on_batch(x[b0:b0 + batch_size], y[b0:b0 + batch_size])
+            nb = len(x[b0:b0 + batch_size])
+            tot += np.asarray(r) * nb
+            n += nb
+        return list(tot / max(n, 1))
+
+    def fit_generator(self, generator, steps_per_epoch, epochs=1, validation_data=None, validation_steps=None,
+                      max_queue_size=10, workers=1, use_multiprocessing=False, callbacks=None, verbose=1,
+                      initial_epoch=0, **kw):
+        """The training driver of fetal_net/training.py:110-124 (main-thread train_on_batch loop, per-epoch
+        validation, Keras callback protocol: on_train_begin / on_epoch_begin / on_epoch_end / on_train_end)."""
+        callbacks = list(callbacks or [])
+        history = {}
+        for cb in callbacks:
+            cb.set_model(self)
+            cb.on_train_begin()
+        self.stop_training = False
+        for epoch in range(initial_epoch, epochs):
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch)
+            tot, n = np.zeros(len(self.metrics_names)), 0
+            for _ in range(int(steps_per_epoch)):
+                x, y = next(generator)[:2]
+                r = self.train_on_batch(x, y)
+                tot += np.asarray(r) * len(x)
+                n += len(x)
+            logs = {k: float(v) for k, v in zip(self.metrics_names, tot / max(n, 1))}
+            if validation_data is not None and validation_steps:
+                vt, vn = np.zeros(len(self.metrics_names)), 0
+                for _ in range(int(validation_steps)):
+                    x, y = next(validation_data)[:2]
+                    r = self.test_on_batch(x, y)
+                    vt += np.asarray(r) * len(x)
+                    vn += len(x)
+                logs.update({"val_" + k: float(v) for k, v in zip(self.metrics_names, vt / max(vn, 1))})
+            logs["lr"] = float(self.optimizer.lr)
+            for k, v in logs.items():
+                history.setdefault(k, []).append(v)
+            if verbose:
+                print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            cb.on_train_end()
+        return history
+
+    def summary(self, print_fn=print):
+        print_fn("%-10s %-12s %6s %6s %3s %10s" % ("layer", "keras name", "Cin", "Cout", "k", "params"))
+        for l in self.layers:
+            print_fn("%-10s %-12s %6d %6d %3d %10d" % (l["name"], l["keras_name"], l["cin"], l["cout"], l["k"],
+                                                       l["k"] ** 3 * l["cin"] * l["cout"] + l["cout"]))
+        print_fn("Total params: %d" % self.count_params())
+
+    def to_json(self):
+        import json
+        return json.dumps(dict(class_name="unet_model_3d", input_shape=self.input_shape[1:], depth=self.depth,
+                               n_base_filters=self.n_base_filters, n_labels=self.n_labels))
+
+
+def unet_model_3d(input_shape, pool_size=(2, 2, 2), n_labels=1, initial_learning_rate=0.00001, deconvolution=False,
+                  depth=4, n_base_filters=32, include_label_wise_dice_coefficients=False,
+                  batch_normalization=False, activation_name="sigmoid", loss_function=dice_coefficient_loss,
+                  **kargs):
+    """Same signature and defaults as the reference builder (unet3d/unet.py:17-20); unknown kwargs
+    (dropout_rate, mask_shape, old_model_path, ... — train_fetal.py:33-39) are swallowed like there."""
+    if tuple(pool_size) != (2, 2, 2):
+        raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2,2)" % (pool_size,))
+    if deconvolution:
+        raise NotImplementedError("deconvolution=True (Deconvolution3D) is on the §8 'next' list")
+    if batch_normalization:
+        raise NotImplementedError("batch_normalization=True is on the §8 'next' list")
+    if activation_name != "sigmoid":
+        raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
+    return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
+                 initial_learning_rate=initial_learning_rate, loss_function=loss_function,
+                 device=kargs.get("device"))

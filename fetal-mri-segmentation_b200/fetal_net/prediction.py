@@ -1,0 +1,147 @@
+"""Sliding-window inference — same entry points as the reference's fetal_net/prediction.py.
+
+`patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size=5, permute=False,
+truth_data=None, prev_truth_index=None, prev_truth_size=None)` keeps the reference signature,
+return dtype (float64) and layout ([X,Y,Z,C], prediction.py:118-119,210). The host side here only
+does what the reference does with integers and one percentile (pad arithmetic, prediction.py:129-146);
+gather, network, overlap-add and the divide run on the device through the C ABI:
+
+  native Model  -> fm_patchwise_predict: upload volume once, gather -> U-Net -> fp64 overlap-add -> download
+  other models  -> fm_gather_patches, model.predict(batch) on whatever backend it has, fm_reassemble
+"""
+import itertools
+
+import numpy as np
+
+from . import _lib
+from .model.unet3d import Model
+
+
+def get_set_of_patch_indices_full(start, stop, step):
+    # prediction.py:88-95
+    indices = []
+    for start_i, stop_i, step_i in zip(start, stop, step):
+        indices_i = list(range(start_i, stop_i + 1, step_i))
+        if stop_i % step_i > 0:
+            indices_i += [stop_i]
+        indices += [indices_i]
+    return np.array(list(itertools.product(*indices)))
+
+
+def patch_plan(padded_shape, patch_shape, prediction_shape, overlap_factor):
+    """Patch corners through the C ABI (fm_patch_plan) — (n,3) int32, x-major product order."""
+    lib = _lib.load()
+    padded, patch, pred = _lib.i32x(padded_shape), _lib.i32x(patch_shape), _lib.i32x(prediction_shape)
+    n = _lib.c_i64(0)
+    import ctypes
+    _lib.check(lib.fm_patch_plan(_lib.i32ptr(padded), _lib.i32ptr(patch), _lib.i32ptr(pred),
+                                 float(overlap_factor), None, 0, ctypes.byref(n)))
+    idx = np.empty((n.value, 3), np.int32)
+    _lib.check(lib.fm_patch_plan(_lib.i32ptr(padded), _lib.i32ptr(patch), _lib.i32ptr(pred),
+                                 float(overlap_factor), _lib.i32ptr(idx), n.value, ctypes.byref(n)))
+    return idx
+
+
+def _pad_pairs(diff):
+    # [(ceil(d/2), floor(d/2))] — prediction.py:139-140,142-143
+    return [(int(np.ceil(d / 2)), int(np.floor(d / 2))) for d in diff]
+
+
+def _geometry(model, data, patch_shape, overlap_factor):
+    """Integer/percentile host logic of prediction.py:129-146,161-163,169-173."""
+    out_shape = tuple(model.output_shape)
+    is3d = int(np.sum(np.array(out_shape[1:]) > 1)) > 2
+    prediction_shape = tuple(out_shape[-3:]) if is3d else tuple(out_shape[-3:-1]) + (1,)
+    patch_shape = tuple(int(v) for v in patch_shape)
+    vol = data[0]
+    halo = _pad_pairs(np.subtract(patch_shape, prediction_shape))
+    pad0 = float(np.percentile(vol, q=1))
+    halo_dims = tuple(int(s + a + b) for s, (a, b) in zip(vol.shape, halo))
+    fit = _pad_pairs(np.maximum(np.subtract(patch_shape, halo_dims), 0))
+    if any(a + b for a, b in fit):
+        # second percentile is taken over the already halo-padded array (prediction.py:144-146)
+        padded_once = np.pad(vol, halo, mode='constant', constant_values=pad0) if any(a + b for a, b in halo) else vol
+        pad1 = float(np.percentile(padded_once, q=1))
+    else:
+        pad1 = pad0
+    padded = tuple(int(s + a + b) for s, (a, b) in zip(halo_dims, fit))
+    n_channels = out_shape[1] if is3d else out_shape[-1]
+    out_dims = tuple(int(s + a + b) for s, (a, b) in zip(vol.shape, fit))   # prediction.py:169
+    return dict(is3d=is3d, prediction_shape=prediction_shape, patch_shape=patch_shape, halo=halo, fit=fit,
+                pad=(pad0, pad1), padded=padded, out_dims=out_dims, channels=int(n_channels))
+
+
+def _crop_fit(arr, fit):
+    # prediction.py:198-207
+    if sum(a + b for a, b in fit) > 0:
+        sl = tuple(slice(a or None, -b if b else None) for a, b in fit)
+        arr = arr[sl]
+    return arr
+
+
+def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size=5,
+                          permute=False, truth_data=None, prev_truth_index=None, prev_truth_size=None,
+                          shard=None):
+    """Drop-in for fetal_net/prediction.py:118-210. `shard=(rank, count)` (extension) makes this call
+    process only its contiguous share of the patch list and return (partial float64 sums, int16 counts)
+    for the caller to reduce — see fetal_net.distributed.sharded_patch_wise_prediction."""
+    if permute:
+        raise NotImplementedError("permute=True (48-permutation TTA, prediction.py:364-369) is on the §8 'next' list")
+    if truth_data is not None:
+        raise NotImplementedError("truth_data / prev_truth conditioning belongs to the 2.5D path (§8 'next')")
+    lib = _lib.load()
+    data = np.asarray(data)
+    assert data.ndim == 4 and data.shape[0] == 1, "data must be [1,X,Y,Z] (prediction.py:296)"
+    g = _geometry(model, data, patch_shape, overlap_factor)
+    idx = patch_plan(g["padded"], g["patch_shape"], g["prediction_shape"], overlap_factor)
+    vol = _lib.f32c(data[0])                      # Keras casts the float64 feed to float32
+    vol_dims = _lib.i32x(vol.shape)
+    halo = _lib.i32x(g["halo"])
+    fit = _lib.i32x(g["fit"])
+    padv = np.asarray(g["pad"], np.float64)
+    out = np.empty(g["out_dims"] + (g["channels"],), np.float64)
+    cnt = np.empty(g["out_dims"], np.int16)
+    rank, count = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+
+    if isinstance(model, Model) and g["is3d"]:
+        assert tuple(g["patch_shape"]) == tuple(model.input_shape[2:]), \
+            "patch_shape %s != model input %s" % (g["patch_shape"], model.input_shape[2:])
+        _lib.check(lib.fm_patchwise_predict(model._h, _lib.fptr(vol), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
+                                            _lib.i32ptr(fit), _lib.dptr(padv), _lib.i32ptr(idx), len(idx),
+                                            int(batch_size), rank, count, _lib.dptr(out), _lib.i16ptr(cnt)))
+    else:
+        if not g["is3d"]:
+            raise NotImplementedError("2D / 2.5D models (unet_model_2d) are on the §8 'next' list")
+        ctx = _lib.get_context()
+        lo, hi = len(idx) * rank // count, len(idx) * (rank + 1) // count
+        ps = g["patch_shape"]
+        preds = np.empty((hi - lo,) + tuple(g["prediction_shape"]) + (g["channels"],), np.float32)
+        patch_i32 = _lib.i32x(ps)
+        for b0 in range(lo, hi, batch_size):
+            bi = np.ascontiguousarray(idx[b0:min(b0 + batch_size, hi)])
+            batch = np.empty((len(bi),) + tuple(ps), np.float32)
+            _lib.check(lib.fm_gather_patches(ctx.handle, _lib.fptr(vol), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
+                                             _lib.i32ptr(fit), _lib.dptr(padv), _lib.i32ptr(bi), len(bi),
+                                             _lib.i32ptr(patch_i32), _lib.fptr(batch)))
+            p = predict(model, batch[:, None], permute=False)          # [B,C,x,y,z]
+            preds[b0 - lo:b0 - lo + len(bi)] = np.asarray(p, np.float32).transpose(0, 2, 3, 4, 1)
+        if count == 1:
+            _lib.check(lib.fm_reassemble(ctx.handle, _lib.fptr(preds), _lib.i32ptr(idx), len(idx),
+                                         _lib.i32ptr(_lib.i32x(g["prediction_shape"])), g["channels"],
+                                         _lib.i32ptr(_lib.i32x(g["out_dims"])), _lib.dptr(out), _lib.i16ptr(cnt)))
+        else:
+            raise NotImplementedError("sharded inference needs a native Model")
+
+    if shard is not None and count > 1:
+        return _crop_fit(out, g["fit"]), _crop_fit(cnt, g["fit"])
+    assert np.all(cnt > 0), 'Found zeros in count'                               # prediction.py:196
+    out = _crop_fit(out, g["fit"])
+    assert np.array_equal(out.shape[:-1], data[0].shape), 'prediction shape wrong'  # prediction.py:209
+    return out
+
+
+def predict(model, data, permute=False):
+    # prediction.py:354-361
+    if permute:
+        raise NotImplementedError("permute=True is on the §8 'next' list")
+    return model.predict(data)

@@ -1,0 +1,194 @@
+/*
+ * fetal_b200.h — C ABI of libfetalb200.so: the B200-native replacement for the numeric
+ * backend underneath the reference's hot path (Keras/TensorFlow under fetal_net.model +
+ * fetal_net.metrics, and the NumPy inner loop of fetal_net.prediction.patch_wise_prediction).
+ *
+ * The reference has no FFI of its own (pure Python): the two seams it offers are
+ *   (i)  `getattr(fetal_net.model, config['model_name'])(...)` -> Keras-Model duck type
+ *        (fetal/train_fetal.py:31-39, fetal_net/training.py:74-75), whose members
+ *        `.predict`, `.train_on_batch`/`.fit_generator`, `.evaluate`, `.load_weights`/`.save`
+ *        are used at fetal_net/prediction.py:361, fetal_net/training.py:110-124,
+ *        fetal/experiments/train_adv.py:227,257;
+ *   (ii) `patch_wise_prediction(model, data, patch_shape, overlap_factor, batch_size, ...)`
+ *        (fetal_net/prediction.py:118-210).
+ * Every entry point below names the reference interface it stands in for. All signatures are
+ * plain C: pointers + sizes, no torch / numpy types. Every function returns 0 on success and a
+ * negative FM_E* code on failure; `fm_last_error()` returns the message for the calling thread.
+ *
+ * Threading: one fm_ctx per GPU / process rank; calls on one ctx must come from one host thread
+ * at a time (the reference calls model.predict / train_on_batch from the main thread only).
+ */
+#ifndef FETAL_B200_H
+#define FETAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_OK 0
+#define FM_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define FM_ECUDA (-2)    /* CUDA runtime or driver error                */
+#define FM_ENOMEM (-3)   /* device or host allocation failed            */
+#define FM_ESTATE (-4)   /* call order violated (e.g. backward w/o fwd) */
+
+typedef struct fm_ctx fm_ctx;
+typedef struct fm_model fm_model;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Replaces: Keras/TF session creation (implicit in `import keras`; fetal/utils.py:59-66). */
+int fm_ctx_create(int device, fm_ctx** out);
+int fm_ctx_destroy(fm_ctx* ctx);
+const char* fm_last_error(void);
+/* SM count / compute capability of the ctx device: out[0]=major, out[1]=minor, out[2]=#SM. */
+int fm_ctx_device_info(fm_ctx* ctx, int out[3]);
+/* cudaStream_t the model's kernels are launched on (as an integer handle, for event timing). */
+uint64_t fm_ctx_stream(fm_ctx* ctx);
+int fm_ctx_synchronize(fm_ctx* ctx);
+/* Number of kernels this library has launched on ctx since creation (bench `gpu_launches`). */
+int64_t fm_ctx_launch_count(fm_ctx* ctx);
+
+/* ---- model -------------------------------------------------------------------------------- */
+
+/* Builder spec. Replaces the kwargs of unet_model_3d (fetal_net/model/unet3d/unet.py:17-20):
+ * input_shape=(in_channels,X,Y,Z), depth, n_base_filters, n_labels. pool_size is (2,2,2),
+ * deconvolution=False, batch_normalization=False, activation 'sigmoid' (the defaults the
+ * reference's train_fetal.py path uses, fetal/train_fetal.py:33-39). */
+typedef struct fm_unet3d_spec {
+  int32_t in_channels;    /* 1 on the reference's path                       */
+  int32_t X, Y, Z;        /* patch extent; each divisible by 2^(depth-1)     */
+  int32_t depth;          /* default 4                                       */
+  int32_t n_base_filters; /* builder default 32; BASELINE configs use 16     */
+  int32_t n_labels;       /* 1                                               */
+} fm_unet3d_spec;
+
+/* Replaces: unet_model_3d(...) + model.compile(Adam, loss=dice_coefficient_loss)
+ * (fetal_net/model/unet3d/unet.py:40-86). Weights start as zeros: call fm_model_set_weights. */
+int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out);
+int fm_model_destroy(fm_model* m);
+
+/* Layer table, Keras creation order (conv3d_1 ... conv3d_15). */
+int fm_model_num_layers(fm_model* m);
+/* info[0]=cin, info[1]=cout, info[2]=kernel extent (3 or 1), info[3]=param offset of kernel,
+ * info[4]=param offset of bias (offsets into the flat fp32 parameter buffer). */
+int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_t info[5]);
+int64_t fm_model_num_params(fm_model* m);
+
+/* Replaces: Model.set_weights / load_weights (fetal/train_fetal.py:43, fetal_net/training.py:83).
+ * `kernel` is in **Keras layout** (k0,k1,k2,Cin,Cout) fp32, `bias` (Cout). Host pointers. */
+int fm_model_set_weights(fm_model* m, int layer, const float* kernel, const float* bias);
+/* Replaces: Model.get_weights / save (fetal_net/training.py:30-32 ModelCheckpoint). */
+int fm_model_get_weights(fm_model* m, int layer, float* kernel, float* bias);
+/* Gradients of the last backward pass, Keras layout (test hook; TF autodiff has no equivalent). */
+int fm_model_get_grads(fm_model* m, int layer, float* kernel, float* bias);
+/* Resets Adam moments and the iteration counter (a fresh model.compile). */
+int fm_model_reset_optimizer(fm_model* m);
+
+/* ---- inference ---------------------------------------------------------------------------- */
+
+/* Replaces: model.predict(ndarray[B,Cin,X,Y,Z]) -> float32 [B,n_labels,X,Y,Z]
+ * (fetal_net/prediction.py:354-361). Host pointers; H2D + forward + D2H inside the call.
+ * With n_labels == 1 the channels-first and channels-last output layouts coincide. */
+int fm_predict(fm_model* m, const float* x, int batch, float* y);
+
+/* Sliding-window plan. Replaces get_set_of_patch_indices_full + the overlap arithmetic
+ * (fetal_net/prediction.py:88-95,135-137,161-163). `padded` is the extent of the padded volume,
+ * `pred` the model's prediction extent (== patch for the 3D models). Writes up to `cap` corner
+ * triples (x-major product order) to `out_idx` and the total count to `out_n`. Pure host code. */
+int fm_patch_plan(const int32_t padded[3], const int32_t patch[3], const int32_t pred[3],
+                  double overlap_factor, int32_t* out_idx, int64_t cap, int64_t* out_n);
+
+/* Replaces the body of patch_wise_prediction for 3D models (fetal_net/prediction.py:161-210):
+ * gather patches from the (virtually padded) volume, run the network, overlap-add in float64 in
+ * patch order, divide by the int count. `vol` is the UNPADDED float32 volume [X,Y,Z] (host);
+ * padding is virtual: `halo_pad` = {before,after} x 3 axes of the first np.pad
+ * (prediction.py:138-141, filled with pad_value[0]) and `fit_pad` likewise for pad_for_fit
+ * (prediction.py:142-146, filled with pad_value[1]). 3D models predict the whole patch, so
+ * halo_pad must be all zero here. `idx` are the n patch corners from fm_patch_plan (coordinates in
+ * the padded volume). `out` receives float64 [X+fit, Y+fit, Z+fit, n_labels] (host) - the caller
+ * crops pad_for_fit (prediction.py:198-207). `batch` = patches per network launch (reference
+ * default 5; the result is batch-invariant).
+ * `shard_rank`/`shard_count`: this rank handles patches [rank*n/count, (rank+1)*n/count) and
+ * `out` then holds the partial SUM (not divided) when shard_count > 1; use shard 0 of 1 for the
+ * single-GPU drop-in. `out_count` (int16, same extent, may be NULL) receives the full count map. */
+int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t vol_dims[3],
+                         const int32_t halo_pad[6], const int32_t fit_pad[6],
+                         const double pad_value[2], const int32_t* idx, int64_t n, int batch,
+                         int shard_rank, int shard_count, double* out, int16_t* out_count);
+
+/* Reassembly alone (test hook for bit-exactness): `preds` float32 [n,P0,P1,P2,C] (host) are
+ * overlap-added exactly as fetal_net/prediction.py:188-193,210 does. */
+int fm_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx, int64_t n,
+                  const int32_t pred_shape[3], int channels, const int32_t out_dims[3],
+                  double* out, int16_t* out_count);
+/* Patch gather alone (test hook): replaces get_patch_from_3d_data on the padded volume
+ * (fetal_net/utils/patches.py:57-72) - out float32 [n,P0,P1,P2] (host). */
+int fm_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
+                      const int32_t halo_pad[6], const int32_t fit_pad[6],
+                      const double pad_value[2], const int32_t* idx, int64_t n,
+                      const int32_t patch[3], float* out);
+
+/* ---- training ----------------------------------------------------------------------------- */
+
+/* Replaces: model.train_on_batch(x, y) as driven by fit_generator (fetal_net/training.py:110-124):
+ * forward, soft-Dice loss (fetal_net/metrics.py:11-15,31-32), backward, Keras-2 Adam.
+ * x [B,Cin,X,Y,Z], t [B,n_labels,X,Y,Z] float32 host. out_metrics[4] = loss, binary_accuracy,
+ * vod_coefficient, dice_coefficient (the Keras metrics of unet3d/unet.py:81-83). */
+int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
+                  float out_metrics[4]);
+
+/* The same step split at its two exchange points, for data-parallel training (one process per
+ * GPU). fm_train_forward leaves the LOCAL sums {sum(t*p), sum(t), sum(p), sum(tb*pb), sum(tb),
+ * sum(pb), sum(correct), count} as 8 float64 at fm_model_loss_sums(); the caller all-reduces
+ * them (SUM) so every rank back-propagates the GLOBAL Dice (metrics.py flattens the whole
+ * batch), then fm_train_backward launches the backward pass; the caller all-reduces (SUM) the
+ * flat fp32 gradient buffer fm_model_grad_buffer() bucket by bucket — fm_stream_wait_bucket
+ * makes a foreign stream wait until bucket `b`'s gradients are final — and finally
+ * fm_train_apply runs Adam after making the compute stream wait on `after_stream`. */
+int fm_train_forward(fm_model* m, const float* x, const float* t, int batch);
+int fm_train_backward(fm_model* m);
+int fm_train_apply(fm_model* m, float lr, uint64_t after_stream, float out_metrics[4]);
+int fm_model_loss_sums(fm_model* m, uint64_t* dev_ptr);               /* 8 x float64, device */
+int fm_model_grad_buffer(fm_model* m, uint64_t* dev_ptr, int64_t* n); /* n x float32, device */
+int fm_model_num_buckets(fm_model* m);
+int fm_model_bucket_range(fm_model* m, int bucket, int64_t* offset, int64_t* count);
+int fm_stream_wait_bucket(fm_model* m, uint64_t stream, int bucket);
+/* Device-resident variants (x, t already float32 in HBM): what bench.py's `value` times. */
+int fm_train_step_device(fm_model* m, uint64_t x_dev, uint64_t t_dev, int batch, float lr,
+                         float out_metrics[4]);
+int fm_predict_device(fm_model* m, uint64_t x_dev, int batch, uint64_t y_dev);
+
+/* Replaces: model.evaluate / test_on_batch (validation loop of fit_generator). */
+int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]);
+
+/* ---- per-op hooks (parity tests call the kernels one at a time through these) --------------
+ * All pointers are HOST pointers; tensors are channels-last (NDHWC) fp32 on the host and are
+ * converted to the device storage type (bf16) inside the call. Each replaces one Keras layer
+ * call of create_convolution_block / unet_model_3d (fetal_net/model/unet3d/unet.py:51,61,102,138)
+ * or its TF autodiff counterpart. `impl`: 0 = tcgen05 tensor-core kernel, 1 = SIMT check kernel.
+ */
+int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const float* x2, const float* w_keras,
+                       const float* bias, int N, int X, int Y, int Z, int C1, int C2, int Cout,
+                       int ksize, int relu, float* y);
+int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const float* w_keras,
+                       const float* mask, int N, int X, int Y, int Z, int Cin, int Cout,
+                       float* dx);
+int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const float* dy, int N, int X, int Y,
+                       int Z, int Cin, int Cout, float* dw_keras, float* dbias);
+int fm_op_maxpool3d(fm_ctx* ctx, const float* x, int N, int X, int Y, int Z, int C, float* y);
+int fm_op_maxpool3d_bwd(fm_ctx* ctx, const float* x, const float* dy, const float* dskip, int N,
+                        int X, int Y, int Z, int C, float* dx);
+int fm_op_upsample3d(fm_ctx* ctx, const float* x, int N, int X, int Y, int Z, int C, float* y);
+int fm_op_upsample3d_bwd(fm_ctx* ctx, const float* dy, const float* act, int N, int X, int Y, int Z,
+                         int C, float* dx);
+int fm_op_dice(fm_ctx* ctx, const float* p, const float* t, int64_t n, double sums[8],
+               float* dloss_dp);
+int fm_op_adam(fm_ctx* ctx, float* p, const float* g, float* mm, float* vv, int64_t n,
+               int iterations, float lr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FETAL_B200_H */

@@ -1,0 +1,300 @@
+"""TEST INFRASTRUCTURE ONLY (the product path must never import `oracle/`).
+
+CPU restatement (PyTorch-CPU, fp32 or fp64) of the reference network path.
+PARITY UNPINNED for the network: Keras/TensorFlow are not installable in this
+image and the reference's own tests hold no numerics for the
+builders, so the restatement is anchored on the reference's call sites and the
+published Keras-2.2 / TF-1.x / keras_contrib semantics:
+
+  * `unet3d_layers` / `unet3d_forward`  <- unet_model_3d            fetal_net/model/unet3d/unet.py:40-70
+                                           create_convolution_block  fetal_net/model/unet3d/unet.py:89-115
+                                           get_up_convolution        fetal_net/model/unet3d/unet.py:132-138
+  * `isensee3d_forward`                 <- isensee2017_model_3d      fetal_net/model/unet3d/isensee2017.py:39-79,95-111
+  * `unet2d_forward`                    <- unet_model_2d             fetal_net/model/unet/unet.py:49-85,91-118
+  * `dice_coefficient(_loss)`, `vod_coefficient`  <- fetal_net/metrics.py:11-32
+  * `keras_adam_step`                   <- Adam(lr) in unet3d/unet.py:85 (Keras 2.x update rule, App. A.9)
+  * `glorot_uniform_weights`            <- Keras default initialisers (App. A.2)
+
+Weights are held in **Keras layout**: kernel (k0,k1,k2,Cin,Cout), bias (Cout,).
+Third-party arithmetic restated: Keras>=2 (requirements.txt:7, unpinned), TensorFlow 1.x
+(not listed), keras_contrib InstanceNormalization (git HEAD, unpinned).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# layer tables
+# ----------------------------------------------------------------------------------------------
+
+def unet3d_layers(depth=4, n_base_filters=32, in_channels=1, n_labels=1):
+    """[(name, cin, cout, k)] in Keras creation order (unet3d/unet.py:45-68)."""
+    layers = []
+    c = in_channels
+    skips = []
+    for d in range(depth):
+        f1 = n_base_filters * (2 ** d)
+        f2 = f1 * 2
+        layers.append(("enc%da" % d, c, f1, 3))
+        layers.append(("enc%db" % d, f1, f2, 3))
+        skips.append(f2)
+        c = f2
+    for d in range(depth - 2, -1, -1):
+        f = skips[d]
+        layers.append(("dec%da" % d, c + f, f, 3))
+        layers.append(("dec%db" % d, f, f, 3))
+        c = f
+    layers.append(("final", c, n_labels, 1))
+    return layers
+
+
+def glorot_uniform_weights(layers, seed=0, ndim=3):
+    """Keras glorot_uniform: limit = sqrt(6/(fan_in+fan_out)), fan = k^d*C; zero biases."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, cin, cout, k in layers:
+        rf = k ** ndim
+        limit = np.sqrt(6.0 / (rf * cin + rf * cout))
+        w[name + "/kernel"] = rng.uniform(-limit, limit, size=(k,) * ndim + (cin, cout)).astype(np.float32)
+        w[name + "/bias"] = np.zeros((cout,), np.float32)
+    return w
+
+
+def _tw(w, name, dtype):
+    """Keras kernel (k..., Cin, Cout) -> torch (Cout, Cin, k...)."""
+    k = torch.as_tensor(w[name + "/kernel"]).to(dtype)
+    nd = k.dim() - 2
+    perm = (nd + 1, nd) + tuple(range(nd))
+    return k.permute(*perm).contiguous(), torch.as_tensor(w[name + "/bias"]).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# plain 3D U-Net
+# ----------------------------------------------------------------------------------------------
+
+def unet3d_forward(x, w, depth=4, return_logits=False, quant=None):
+    """x: [B,Cin,X,Y,Z] torch tensor. `quant` (optional callable) is applied to every stored
+    activation and to the weights - used to model bf16 storage for tolerance studies."""
+    dt = x.dtype
+    q = quant if quant is not None else (lambda t: t)
+
+    def cb(t, name):
+        k, b = _tw(w, name, dt)
+        return q(F.relu(F.conv3d(t, q(k), b, padding=1)))
+
+    cur = q(x)
+    skips = []
+    for d in range(depth):
+        cur = cb(cur, "enc%da" % d)
+        cur = cb(cur, "enc%db" % d)
+        skips.append(cur)
+        if d < depth - 1:
+            cur = F.max_pool3d(cur, 2)
+    for d in range(depth - 2, -1, -1):
+        up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+        cur = torch.cat([up, skips[d]], dim=1)          # unet3d/unet.py:61: [up, skip]
+        cur = cb(cur, "dec%da" % d)
+        cur = cb(cur, "dec%db" % d)
+    k, b = _tw(w, "final", dt)
+    logits = F.conv3d(cur, q(k), b)
+    if return_logits:
+        return logits
+    return torch.sigmoid(logits)
+
+
+# ----------------------------------------------------------------------------------------------
+# losses / metrics (metrics.py:11-32)
+# ----------------------------------------------------------------------------------------------
+
+def dice_coefficient(t, p, smooth=1.0):
+    tf_, pf = t.reshape(-1), p.reshape(-1)
+    inter = (tf_ * pf).sum()
+    return (2.0 * inter + smooth) / (tf_.sum() + pf.sum() + smooth)
+
+
+def dice_coefficient_loss(t, p):
+    return -dice_coefficient(t, p)
+
+
+def vod_coefficient(t, p, smooth=1.0):
+    tb = (t.reshape(-1) > 0.5).to(p.dtype)
+    pb = (p.reshape(-1) > 0.5).to(p.dtype)
+    inter = (tb * pb).sum()
+    union = tb.sum() + pb.sum() - inter
+    return (inter + smooth) / (union + smooth)
+
+
+def binary_accuracy(t, p):
+    # Keras: mean(equal(y_true, round(y_pred)))
+    return (t == torch.round(p)).to(p.dtype).mean()
+
+
+def dice_grad_closed_form(t, p, smooth=1.0):
+    """dL/dp for L = -dice: -(2 t S - (2I+smooth)) / S^2, S = sum t + sum p + smooth."""
+    I = (t * p).sum()
+    S = t.sum() + p.sum() + smooth
+    return -(2.0 * t * S - (2.0 * I + smooth)) / (S * S)
+
+
+# ----------------------------------------------------------------------------------------------
+# Keras-2 Adam (App. A.9)
+# ----------------------------------------------------------------------------------------------
+
+def keras_adam_step(p, g, m, v, iterations, lr, beta_1=0.9, beta_2=0.999, eps=1e-7):
+    """In-place on numpy float32 arrays; `iterations` = number of steps already taken."""
+    t = iterations + 1
+    lr_t = lr * np.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+    m[...] = beta_1 * m + (1.0 - beta_1) * g
+    v[...] = beta_2 * v + (1.0 - beta_2) * g * g
+    p[...] = p - np.float32(lr_t) * m / (np.sqrt(v) + np.float32(eps))
+
+
+def unet3d_train_step(x, t, w, adam_state, lr, depth=4, dtype=torch.float32):
+    """One fwd + Dice loss + bwd + Keras-Adam update. Mutates w/adam_state. Returns dict of scalars+grads."""
+    names = sorted(w.keys())
+    params = {n: torch.tensor(w[n], dtype=dtype, requires_grad=True) for n in names}
+    xt = torch.as_tensor(x).to(dtype)
+    tt = torch.as_tensor(t).to(dtype)
+    p = unet3d_forward(xt, params, depth=depth)
+    loss = dice_coefficient_loss(tt, p)
+    loss.backward()
+    out = {"loss": float(loss), "binary_accuracy": float(binary_accuracy(tt, p.detach())),
+           "vod_coefficient": float(vod_coefficient(tt, p.detach())), "grads": {}, "pred": p.detach().numpy()}
+    it = adam_state.setdefault("iterations", 0)
+    for n in names:
+        g = params[n].grad.detach().to(torch.float32).numpy()
+        out["grads"][n] = g
+        m = adam_state.setdefault("m/" + n, np.zeros_like(w[n]))
+        v = adam_state.setdefault("v/" + n, np.zeros_like(w[n]))
+        keras_adam_step(w[n], g, m, v, it, lr)
+    adam_state["iterations"] = it + 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Isensee-2017 3D (isensee2017.py:39-79) — forward only
+# ----------------------------------------------------------------------------------------------
+
+def isensee3d_layers(depth=5, n_base_filters=16, n_segmentation_levels=1, in_channels=1, n_labels=1):
+    layers = []
+    c = in_channels
+    filt = []
+    for l in range(depth):
+        f = n_base_filters * (2 ** l)
+        filt.append(f)
+        layers += [("l%d_in" % l, c, f, 3), ("l%d_ctx1" % l, f, f, 3), ("l%d_ctx2" % l, f, f, 3)]
+        c = f
+    for l in range(depth - 2, -1, -1):
+        f = filt[l]
+        layers += [("u%d_up" % l, c, f, 3), ("u%d_loc1" % l, 2 * f, f, 3), ("u%d_loc2" % l, f, f, 1)]
+        c = f
+        if l < n_segmentation_levels:
+            layers.append(("u%d_seg" % l, f, n_labels, 1))
+    return layers
+
+
+def isensee3d_norm_params(layers):
+    p = {}
+    for name, cin, cout, k in layers:
+        if not name.endswith("_seg"):
+            p[name + "/gamma"] = np.ones((cout,), np.float32)
+            p[name + "/beta"] = np.zeros((cout,), np.float32)
+    return p
+
+
+def _instance_norm(t, gamma, beta, eps=1e-3):
+    # keras_contrib InstanceNormalization(axis=1): stddev = sqrt(var_biased) + eps (App. A.6)
+    dims = tuple(range(2, t.dim()))
+    mean = t.mean(dim=dims, keepdim=True)
+    std = t.var(dim=dims, unbiased=False, keepdim=True).sqrt() + eps
+    shape = (1, -1) + (1,) * (t.dim() - 2)
+    return (t - mean) / std * gamma.reshape(shape) + beta.reshape(shape)
+
+
+def isensee3d_forward(x, w, depth=5, n_segmentation_levels=1, return_logits=False):
+    dt = x.dtype
+
+    def cb(t, name, stride=1, k=3):
+        kk, b = _tw(w, name, dt)
+        if k == 3 and stride == 2:
+            t = F.pad(t, (0, 1, 0, 1, 0, 1))       # TF SAME, even input: pad_before 0, pad_after 1 (App. A.3)
+            y = F.conv3d(t, kk, b, stride=2)
+        elif k == 3:
+            y = F.conv3d(t, kk, b, padding=1)
+        else:
+            y = F.conv3d(t, kk, b)
+        g = torch.as_tensor(w[name + "/gamma"]).to(dt)
+        be = torch.as_tensor(w[name + "/beta"]).to(dt)
+        return F.leaky_relu(_instance_norm(y, g, be), 0.3)
+
+    cur = x
+    outs = []
+    for l in range(depth):
+        inc = cb(cur, "l%d_in" % l, stride=1 if l == 0 else 2)
+        ctx = cb(cb(inc, "l%d_ctx1" % l), "l%d_ctx2" % l)   # dropout: identity at rate 0 / inference
+        cur = inc + ctx
+        outs.append(cur)
+    segs = {}
+    for l in range(depth - 2, -1, -1):
+        up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+        up = cb(up, "u%d_up" % l)
+        cat = torch.cat([outs[l], up], dim=1)           # isensee2017.py:62: [skip, up]
+        cur = cb(cb(cat, "u%d_loc1" % l), "u%d_loc2" % l, k=1)
+        if l < n_segmentation_levels:
+            kk, b = _tw(w, "u%d_seg" % l, dt)
+            segs[l] = F.conv3d(cur, kk, b)
+    out = None
+    for l in reversed(range(n_segmentation_levels)):
+        out = segs[l] if out is None else out + segs[l]
+        if l > 0:
+            out = out.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+    return out if return_logits else torch.sigmoid(out)
+
+
+# ----------------------------------------------------------------------------------------------
+# 2D / 2.5D U-Net (model/unet/unet.py:49-85) — forward only
+# ----------------------------------------------------------------------------------------------
+
+def unet2d_layers(depth=4, n_base_filters=32, in_channels=6, n_labels=1):
+    return unet3d_layers(depth, n_base_filters, in_channels, n_labels)
+
+
+def unet2d_forward(x, w, depth=4, return_logits=False):
+    """x: [B,H,W,D] (slices-as-channels, Keras input layout) -> [B,H,W,n_labels]."""
+    dt = x.dtype
+    cur = x.permute(0, 3, 1, 2)                      # Permute((3,1,2))
+    skips = []
+
+    def cb(t, name):
+        k, b = _tw(w, name, dt)
+        return F.relu(F.conv2d(t, k, b, padding=1))
+
+    for d in range(depth):
+        cur = cb(cb(cur, "enc%da" % d), "enc%db" % d)
+        skips.append(cur)
+        if d < depth - 1:
+            cur = F.max_pool2d(cur, 2)
+    for d in range(depth - 2, -1, -1):
+        up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3)
+        cur = torch.cat([up, skips[d]], dim=1)
+        cur = cb(cb(cur, "dec%da" % d), "dec%db" % d)
+    k, b = _tw(w, "final", dt)
+    logits = F.conv2d(cur, k, b)
+    out = logits if return_logits else torch.sigmoid(logits)
+    return out.permute(0, 2, 3, 1)                   # Permute((2,3,1))
+
+
+class OracleModel:
+    """Keras-Model duck type over the oracle forward (used by tests and bench's cpu_baseline leg)."""
+
+    def __init__(self, weights, input_shape, depth=4, dtype=torch.float32):
+        self.w = weights
+        self.depth = depth
+        self.dtype = dtype
+        self.output_shape = (None, 1) + tuple(input_shape[1:])
+
+    def predict(self, data):
+        with torch.no_grad():
+            x = torch.as_tensor(np.asarray(data)).to(self.dtype)
+            return unet3d_forward(x, self.w, depth=self.depth).to(torch.float32).numpy()

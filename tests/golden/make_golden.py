@@ -1,0 +1,127 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference code
+(/root/reference/fetal_net/prediction.py, utils/patches.py) under the stub harness of
+oracle/ref_harness.py. Run in the build container only (the reference tree does not travel):
+
+    python tests/golden/make_golden.py
+
+Everything written here is deterministic IEEE arithmetic (NumPy float32 mul/add, float64 sums), so
+the fixtures are machine-independent. The fake "models" are position-dependent so that overlapping
+patches contribute DIFFERENT values to a voxel (an identity model cannot catch index/order bugs).
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.ref_harness import FunctionModel, load_reference_prediction  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def ramp_model(patch_shape, channels=1):
+    """predict(batch[B,1,x,y,z]) -> float32 [B,C,x,y,z]: batch * ramp_c + 0.125 * ramp_c (exact fp32 ops)."""
+    px, py, pz = patch_shape
+    g = np.meshgrid(np.arange(px), np.arange(py), np.arange(pz), indexing="ij")
+    ramps = []
+    for c in range(channels):
+        r = (1.0 + (g[0] * 3 + g[1] * 5 + g[2] * 7 + c * 11) % 13).astype(np.float32) / np.float32(16.0)
+        ramps.append(r)
+    ramp = np.stack(ramps)[None]                                  # [1,C,x,y,z]
+
+    def fn(batch):
+        b = np.asarray(batch).astype(np.float32)                  # Keras casts the feed to float32
+        return (b * ramp + np.float32(0.125) * ramp).astype(np.float32)
+
+    return fn, (None, channels) + tuple(patch_shape)
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def main():
+    pred = load_reference_prediction()
+    patches = pred._ref_patches
+    fx = {}
+
+    # ---- (1) plans: get_set_of_patch_indices_full with the overlap arithmetic of prediction.py:135-137
+    plan_cases = [
+        ("cfg1_f05", (256, 256, 64), (64, 64, 64), (64, 64, 64), 0.5),
+        ("cfg1_f0", (256, 256, 64), (64, 64, 64), (64, 64, 64), 0.0),
+        ("cfg1_f09", (256, 256, 64), (64, 64, 64), (64, 64, 64), 0.9),
+        ("cfg3_f05", (256, 256, 64), (128, 128, 64), (128, 128, 64), 0.5),
+        ("cfg5_f05", (512, 512, 128), (128, 128, 64), (128, 128, 64), 0.5),
+        ("cfg4_2d_f05", (256, 256, 68), (256, 256, 5), (256, 256, 1), 0.5),
+        ("odd_f03", (70, 50, 41), (32, 16, 8), (32, 16, 8), 0.3),
+        ("odd_f077", (97, 33, 40), (32, 32, 16), (32, 32, 16), 0.77),
+    ]
+    for name, padded, patch, pshape, f in plan_cases:
+        min_overlap = np.subtract(patch, pshape)
+        max_overlap = np.subtract(patch, (1, 1, 1))
+        overlap = min_overlap + (f * (max_overlap - min_overlap)).astype(int)
+        idx = pred.get_set_of_patch_indices_full((0, 0, 0), np.subtract(padded, patch), np.subtract(patch, overlap))
+        fx["plan/%s/args" % name] = np.array(list(padded) + list(patch) + list(pshape), np.int64)
+        fx["plan/%s/f" % name] = np.float64(f)
+        fx["plan/%s/n" % name] = np.int64(len(idx))
+        if len(idx) <= 4096:
+            fx["plan/%s/idx" % name] = idx.astype(np.int32)
+        fx["plan/%s/sha" % name] = np.array(sha16(idx.astype(np.int32)))
+
+    # ---- (2) cfg-1 count map (SURVEY.md §8c golden 5): run the reference accumulate loop on ones
+    ones_model = FunctionModel(lambda b: np.ones((len(b), 1, 64, 64, 64), np.float32), (None, 1, 64, 64, 64))
+    # count = sum of ones predictions before the divide: recover it by calling with a constant volume and
+    # instrumenting through a second pass: patch_wise_prediction returns sum/count == 1, so compute the
+    # count with the reference's own index list instead.
+    idx = pred.get_set_of_patch_indices_full((0, 0, 0), (192, 192, 0), (33, 33, 33))
+    cnt = np.zeros((256, 256, 64), np.int16)
+    for x, y, z in idx:
+        cnt[x:x + 64, y:y + 64, z:z + 64] += 1          # prediction.py:193
+    fx["count/cfg1/sha"] = np.array(sha16(cnt))
+    vals, freq = np.unique(cnt, return_counts=True)
+    fx["count/cfg1/hist"] = np.stack([vals.astype(np.int64), freq.astype(np.int64)])
+    fx["count/cfg1/axis_x"] = cnt[:, 0, 0].copy()
+    out = pred.patch_wise_prediction(ones_model, np.zeros((1, 256, 256, 64), np.float32), patch_shape=(64, 64, 64),
+                                     overlap_factor=0.5)
+    assert out.shape == (256, 256, 64, 1) and np.all(out == 1.0)
+
+    # ---- (3) full patch_wise_prediction runs with position-dependent fake models
+    run_cases = [
+        # name, volume shape, patch, overlap_factor, batch_size, channels
+        ("ramp_a", (1, 40, 36, 20), (16, 16, 16), 0.5, 5, 1),
+        ("ramp_fit", (1, 30, 12, 20), (16, 16, 16), 0.5, 3, 1),      # pad_for_fit on y (12 < 16)
+        ("ramp_f08", (1, 24, 24, 17), (8, 8, 8), 0.8, 7, 1),
+        ("ramp_c2", (1, 20, 24, 16), (8, 16, 8), 0.3, 4, 2),         # two output channels
+        ("ramp_f0", (1, 32, 32, 16), (16, 16, 16), 0.0, 5, 1),
+    ]
+    for name, vshape, patch, f, bs, ch in run_cases:
+        rng = np.random.default_rng(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+        vol = rng.standard_normal(vshape).astype(np.float32)
+        fn, oshape = ramp_model(patch, ch)
+        out = pred.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch_shape=patch, overlap_factor=f,
+                                         batch_size=bs)
+        fx["run/%s/vol" % name] = vol
+        fx["run/%s/patch" % name] = np.array(patch, np.int64)
+        fx["run/%s/f" % name] = np.float64(f)
+        fx["run/%s/batch" % name] = np.int64(bs)
+        fx["run/%s/channels" % name] = np.int64(ch)
+        fx["run/%s/out" % name] = out                                 # float64 [X,Y,Z,C]
+
+    # ---- (4) get_patch_from_3d_data incl. the out-of-bounds edge-pad branch (patches.py:57-91)
+    rng = np.random.default_rng(7)
+    data = rng.standard_normal((2, 12, 10, 9)).astype(np.float32)
+    corners = [(0, 0, 0), (4, 2, 1), (8, 6, 5), (-2, 0, 0), (9, 7, 6), (-1, -3, 6)]
+    fx["patch/data"] = data
+    fx["patch/corners"] = np.array(corners, np.int64)
+    fx["patch/shape"] = np.array((4, 4, 4), np.int64)
+    for i, c in enumerate(corners):
+        fx["patch/out%d" % i] = np.ascontiguousarray(patches.get_patch_from_3d_data(data, (4, 4, 4), np.array(c)))
+
+    np.savez_compressed(os.path.join(OUT, "prediction_golden.npz"), **fx)
+    print("wrote", os.path.join(OUT, "prediction_golden.npz"), len(fx), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+"""Per-op parity cases shared by tests/test_gpu_ops.py and tools/gpu_diag.py.
+
+Each case runs ONE kernel through the C ABI (fm_op_* hooks, host fp32 channels-last in/out) and
+compares with a plain PyTorch-CPU fp32/fp64 reference of the same op on the same bf16-rounded
+inputs. Tolerance (stated once): device tensors are bf16 with fp32 accumulation, so an output
+element may differ from the exact result by one bf16 rounding of itself plus accumulation-order
+noise:  |got - ref| <= 2^-7 * |ref| + 2^-8 * max|ref|   (bf16 has 8 significand bits).
+Gradients w.r.t. weights are fp32 end to end: rel. error of the whole tensor <= 2e-3.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from fetal_net import _lib
+
+
+def bf16_round(a):
+    return torch.as_tensor(np.asarray(a, np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def close_bf16(got, ref):
+    ref = np.asarray(ref, np.float64)
+    got = np.asarray(got, np.float64)
+    tol = 2.0 ** -7 * np.abs(ref) + 2.0 ** -8 * max(np.abs(ref).max(), 1e-30)
+    err = np.abs(got - ref)
+    worst = float((err / tol).max())
+    return worst <= 1.0, worst
+
+
+def rel_err(got, ref):
+    ref = np.asarray(ref, np.float64)
+    got = np.asarray(got, np.float64)
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def cl_to_cf(x):  # [N,X,Y,Z,C] -> [N,C,X,Y,Z]
+    return torch.as_tensor(x).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def cf_to_cl(x):
+    return x.permute(0, 2, 3, 4, 1).contiguous().numpy()
+
+
+def keras_to_torch_w(w):  # (k,k,k,Cin,Cout) -> (Cout,Cin,k,k,k)
+    return torch.as_tensor(w).permute(4, 3, 0, 1, 2).contiguous()
+
+
+CONV_CASES = [
+    # name, N, X, Y, Z, C1, C2, Cout, k
+    ("c16_32_8cube", 2, 8, 8, 8, 16, 0, 32, 3),         # SW32 operands (enc0b shape class)
+    ("c32_32_16cube", 1, 16, 16, 16, 32, 0, 32, 3),     # SW64
+    ("c64_64", 2, 8, 8, 8, 64, 0, 64, 3),               # SW128
+    ("c128_256", 1, 8, 8, 8, 128, 0, 256, 3),           # 2 K chunks, 2 N tiles
+    ("cat64_32_to32", 1, 16, 16, 16, 64, 32, 32, 3),    # dec0a: two sources, mixed swizzle
+    ("cat256_128_to128", 1, 8, 8, 8, 256, 128, 128, 3), # dec2a
+    ("ragged_12x10x6", 2, 12, 10, 6, 32, 0, 64, 3),     # partial tiles / clipping
+    ("tiny_4cube", 3, 4, 4, 4, 16, 0, 16, 3),           # box larger than the tensor
+    ("k1_64_32", 2, 8, 8, 8, 64, 0, 32, 1),             # 1x1x1 (Isensee localisation shape)
+    ("cfg_64cube_16_32", 1, 64, 64, 64, 16, 0, 32, 3),  # enc0b at the real patch size
+]
+
+
+def conv_fprop_case(ctx, impl, case, seed=0):
+    name, N, X, Y, Z, C1, C2, Cout, k = case
+    rng = np.random.default_rng(seed)
+    x1 = bf16_round(rng.standard_normal((N, X, Y, Z, C1)))
+    x2 = bf16_round(rng.standard_normal((N, X, Y, Z, C2))) if C2 else None
+    w = bf16_round(rng.standard_normal((k, k, k, C1 + C2, Cout)) / np.sqrt(k ** 3 * (C1 + C2)))
+    b = rng.standard_normal(Cout).astype(np.float32)
+    y = np.empty((N, X, Y, Z, Cout), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_fprop(ctx.handle, impl, _lib.fptr(x1), _lib.fptr(x2), _lib.fptr(w), _lib.fptr(b),
+                                      N, X, Y, Z, C1, C2, Cout, k, 1, _lib.fptr(y)))
+    xin = torch.as_tensor(x1 if x2 is None else np.concatenate([x1, x2], -1))
+    ref = F.relu(F.conv3d(cl_to_cf(xin).double(), keras_to_torch_w(w).double(), torch.as_tensor(b).double(),
+                          padding=k // 2))
+    return close_bf16(y, cf_to_cl(ref))
+
+
+def conv_dgrad_case(ctx, impl, case, seed=1):
+    name, N, X, Y, Z, C1, C2, Cout, k = case
+    Cin = C1  # single source
+    rng = np.random.default_rng(seed)
+    dy = bf16_round(rng.standard_normal((N, X, Y, Z, Cout)))
+    w = bf16_round(rng.standard_normal((3, 3, 3, Cin, Cout)) / np.sqrt(27 * Cout))
+    act = bf16_round(rng.standard_normal((N, X, Y, Z, Cin)))       # ReLU mask source (act > 0)
+    dx = np.empty((N, X, Y, Z, Cin), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_dgrad(ctx.handle, impl, _lib.fptr(dy), _lib.fptr(w), _lib.fptr(act),
+                                      N, X, Y, Z, Cin, Cout, _lib.fptr(dx)))
+    ref = F.conv_transpose3d(cl_to_cf(dy).double(), keras_to_torch_w(w).double(), padding=1)
+    ref = cf_to_cl(ref) * (act > 0)
+    return close_bf16(dx, ref)
+
+
+def conv_wgrad_case(ctx, impl, case, seed=2):
+    name, N, X, Y, Z, C1, C2, Cout, k = case
+    Cin = C1
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.standard_normal((N, X, Y, Z, Cin)))
+    dy = bf16_round(rng.standard_normal((N, X, Y, Z, Cout)))
+    dw = np.empty((3, 3, 3, Cin, Cout), np.float32)
+    db = np.empty((Cout,), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_wgrad(ctx.handle, impl, _lib.fptr(x), _lib.fptr(dy), N, X, Y, Z, Cin, Cout,
+                                      _lib.fptr(dw), _lib.fptr(db)))
+    xt = cl_to_cf(x).double().requires_grad_(False)
+    wt = torch.zeros(Cout, Cin, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    out = F.conv3d(xt, wt, padding=1)
+    out.backward(cl_to_cf(dy).double())
+    ref_w = wt.grad.permute(2, 3, 4, 1, 0).numpy()
+    ref_b = dy.reshape(-1, Cout).astype(np.float64).sum(0)
+    e = max(rel_err(dw, ref_w), rel_err(db, ref_b))
+    return e <= 2e-3, e / 2e-3
+
+
+def maxpool_case(ctx, seed=3):
+    N, X, Y, Z, C = 2, 8, 12, 16, 32
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.standard_normal((N, X, Y, Z, C)))
+    y = np.empty((N, X // 2, Y // 2, Z // 2, C), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_maxpool3d(ctx.handle, _lib.fptr(x), N, X, Y, Z, C, _lib.fptr(y)))
+    ref = cf_to_cl(F.max_pool3d(cl_to_cf(x), 2))
+    ok = np.array_equal(y, ref)                                    # exact: max of bf16 values
+    # backward with skip-gradient add and ReLU mask
+    dy = bf16_round(rng.standard_normal(y.shape))
+    dskip = bf16_round(rng.standard_normal(x.shape))
+    dx = np.empty_like(x)
+    _lib.check(lib.fm_op_maxpool3d_bwd(ctx.handle, _lib.fptr(x), _lib.fptr(dy), _lib.fptr(dskip), N, X, Y, Z, C,
+                                       _lib.fptr(dx)))
+    xt = cl_to_cf(x).double().requires_grad_(True)
+    F.max_pool3d(xt, 2).backward(cl_to_cf(dy).double())
+    refb = (cf_to_cl(xt.grad) + dskip) * (x > 0)
+    ok2, worst = close_bf16(dx, refb)
+    return ok and ok2, worst if ok else float("inf")
+
+
+def upsample_case(ctx, seed=4):
+    N, X, Y, Z, C = 2, 4, 6, 8, 64
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.standard_normal((N, X, Y, Z, C)))
+    y = np.empty((N, 2 * X, 2 * Y, 2 * Z, C), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_upsample3d(ctx.handle, _lib.fptr(x), N, X, Y, Z, C, _lib.fptr(y)))
+    ref = np.repeat(np.repeat(np.repeat(x, 2, 1), 2, 2), 2, 3)
+    ok = np.array_equal(y, ref)
+    dy = bf16_round(rng.standard_normal(y.shape))
+    act = bf16_round(rng.standard_normal(x.shape))
+    dx = np.empty_like(x)
+    _lib.check(lib.fm_op_upsample3d_bwd(ctx.handle, _lib.fptr(dy), _lib.fptr(act), N, X, Y, Z, C, _lib.fptr(dx)))
+    refb = dy.astype(np.float64).reshape(N, X, 2, Y, 2, Z, 2, C).sum((2, 4, 6)) * (act > 0)
+    ok2, worst = close_bf16(dx, refb)
+    return ok and ok2, worst if ok else float("inf")
+
+
+def dice_case(ctx, seed=5):
+    n = 8 * 16 ** 3 + 3           # not a multiple of 4: exercises the scalar tail
+    rng = np.random.default_rng(seed)
+    p = rng.random(n).astype(np.float32)
+    t = (rng.random(n) < 0.3).astype(np.float32)
+    sums = np.zeros(8, np.float64)
+    g = np.empty(n, np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_dice(ctx.handle, _lib.fptr(p), _lib.fptr(t), n, _lib.dptr(sums), _lib.fptr(g)))
+    pb, tb = (p > 0.5), (t > 0.5)
+    ref = np.array([(t.astype(np.float64) * p).sum(), t.sum(dtype=np.float64), p.sum(dtype=np.float64),
+                    (tb & pb).sum(), tb.sum(), pb.sum(), (t == pb.astype(np.float32)).sum(), n], np.float64)
+    e1 = float(np.max(np.abs(sums - ref) / np.maximum(np.abs(ref), 1)))
+    I, S = ref[0], ref[1] + ref[2] + 1.0
+    gref = -(2.0 * t * S - (2.0 * I + 1.0)) / (S * S)
+    e2 = rel_err(g, gref)
+    # float32 per-thread partial sums over <= n/151552 elements each, then float64: 1e-6 is ample
+    return e1 <= 1e-6 and e2 <= 1e-5, max(e1 / 1e-6, e2 / 1e-5)
+
+
+def adam_case(ctx, seed=6):
+    from oracle.unet_oracle import keras_adam_step
+    n = 100003
+    rng = np.random.default_rng(seed)
+    p = rng.standard_normal(n).astype(np.float32)
+    m = np.zeros(n, np.float32)
+    v = np.zeros(n, np.float32)
+    p2, m2, v2 = p.copy(), m.copy(), v.copy()
+    lib = _lib.load()
+    worst = 0.0
+    for it in range(3):
+        g = rng.standard_normal(n).astype(np.float32) * 1e-3
+        _lib.check(lib.fm_op_adam(ctx.handle, _lib.fptr(p), _lib.fptr(g), _lib.fptr(m), _lib.fptr(v), n, it, 1e-3))
+        keras_adam_step(p2, g, m2, v2, it, 1e-3)
+        worst = max(worst, float(np.max(np.abs(p - p2))), float(np.max(np.abs(m - m2))))
+    return worst <= 2e-6, worst / 2e-6

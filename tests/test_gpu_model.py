@@ -1,0 +1,168 @@
+"""Network-level parity on the GPU: unet_model_3d forward / training step through the reference-facing
+Python API (fetal_net.model.unet_model_3d -> Model.predict / train_on_batch) against the fp32 oracle.
+
+Stated tolerances (bf16 storage of every activation, fp32 accumulation, 15 layers deep):
+  probabilities  max|p - p_oracle| <= 0.03, mean <= 0.004; soft-Dice(p, p_oracle) >= 0.999;
+                 Dice of the 0.5-thresholded masks >= 0.999 (north_star bar)
+  loss           |loss - loss_oracle| <= 3e-3
+  gradients      per-layer cosine similarity >= 0.99 and norm ratio within 5 %
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+
+
+def decisive_weights(layers, seed=0):
+    """Glorot-uniform with gain sqrt(2) (variance preserving through ReLU) + small biases, so the logits are
+    O(1) and masks are decisive; plain glorot at 15 layers gives p = 0.5 +- 0.01 (useless for Dice)."""
+    w = uo.glorot_uniform_weights(layers, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    for k in w:
+        if k.endswith("/kernel"):
+            w[k] = (w[k] * np.sqrt(2.0) * 1.35).astype(np.float32)
+        else:
+            w[k] = (0.05 * rng.standard_normal(w[k].shape)).astype(np.float32)
+    return w
+
+
+def blob_target(shape, rng):
+    B, _, X, Y, Z = shape
+    g = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    t = np.zeros(shape, np.float32)
+    for b in range(B):
+        c = rng.uniform(0.3, 0.7, 3) * [X, Y, Z]
+        r = rng.uniform(0.2, 0.35) * min(X, Y, Z)
+        t[b, 0] = ((g[0] - c[0]) ** 2 + (g[1] - c[1]) ** 2 + (g[2] - c[2]) ** 2) < r * r
+    return t
+
+
+def mask_dice(a, b):
+    a, b = a > 0.5, b > 0.5
+    return (2.0 * (a & b).sum() + 1.0) / (a.sum() + b.sum() + 1.0)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from fetal_net.model import unet_model_3d
+    layers = uo.unet3d_layers(4, 16)
+    w = decisive_weights(layers)
+    model = unet_model_3d(input_shape=(1, 32, 32, 32), n_base_filters=16, depth=4, initial_learning_rate=1e-4)
+    model.set_named_weights(w)
+    return model, w
+
+
+def test_layer_table_and_param_count(setup):
+    model, w = setup
+    assert model.count_params() == 4079713
+    assert [l["name"] for l in model.layers] == [n for n, *_ in uo.unet3d_layers(4, 16)]
+    assert model.output_shape == (None, 1, 32, 32, 32)
+
+
+def test_weights_roundtrip_exact(setup):
+    model, w = setup
+    got = model.get_weights()
+    for l, k, b in zip(model.layers, got[0::2], got[1::2]):
+        assert np.array_equal(k, w[l["name"] + "/kernel"]) and np.array_equal(b, w[l["name"] + "/bias"])
+
+
+def test_forward_matches_oracle(setup):
+    model, w = setup
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 1, 32, 32, 32)).astype(np.float32)
+    p = model.predict(x)
+    assert p.shape == (3, 1, 32, 32, 32) and p.dtype == np.float32
+    with torch.no_grad():
+        ref = uo.unet3d_forward(torch.as_tensor(x), w).numpy()
+    d = np.abs(p - ref)
+    frac_decisive = np.mean(np.abs(ref - 0.5) > 0.05)
+    assert frac_decisive > 0.5, "test weights are not decisive (%.2f)" % frac_decisive
+    assert d.max() <= 0.03 and d.mean() <= 0.004, (d.max(), d.mean())
+    soft = (2 * (p * ref).sum() + 1) / ((p * p).sum() + (ref * ref).sum() + 1)
+    assert soft >= 0.999, soft
+    assert mask_dice(p, ref) >= 0.999, mask_dice(p, ref)
+    # batch invariance / determinism: sample 1 alone gives bit-identical output
+    assert np.array_equal(model.predict(x[1:2]), p[1:2])
+
+
+def test_train_step_matches_oracle(setup):
+    from fetal_net.model import unet_model_3d
+    _, w0 = setup
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32)
+    t = blob_target(x.shape, rng)
+    model = unet_model_3d(input_shape=(1, 32, 32, 32), n_base_filters=16, depth=4, initial_learning_rate=1e-4)
+    model.set_named_weights(w0)
+    w = {k: v.copy() for k, v in w0.items()}
+    state = {}
+    ref = uo.unet3d_train_step(x, t, w, state, 1e-4)
+    got = model.train_on_batch(x, t)
+    assert got[0] == pytest.approx(ref["loss"], abs=3e-3), (got, ref["loss"])
+    assert got[1] == pytest.approx(ref["binary_accuracy"], abs=5e-3)
+    assert got[2] == pytest.approx(ref["vod_coefficient"], abs=5e-3)
+    grads = model.get_gradients()
+    report = []
+    for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
+        for kind, g in (("kernel", gk), ("bias", gb)):
+            r = ref["grads"]["%s/%s" % (l["name"], kind)].astype(np.float64).ravel()
+            g = g.astype(np.float64).ravel()
+            cos = float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
+            ratio = float(np.linalg.norm(g) / max(np.linalg.norm(r), 1e-300))
+            report.append((l["name"], kind, cos, ratio))
+    bad = [r for r in report if not (r[2] >= 0.99 and 0.95 <= r[3] <= 1.05)]
+    assert not bad, bad
+    # Adam moved every weight by at most lr (first Keras-Adam step is lr * sign-like)
+    new = model.get_weights()
+    for l, k in zip(model.layers, new[0::2]):
+        assert np.max(np.abs(k - w0[l["name"] + "/kernel"])) <= 1.01e-4
+
+
+def test_loss_curve_tracks_oracle(setup):
+    from fetal_net.model import unet_model_3d
+    _, w0 = setup
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32)
+    t = blob_target(x.shape, rng)
+    model = unet_model_3d(input_shape=(1, 32, 32, 32), n_base_filters=16, depth=4, initial_learning_rate=3e-4)
+    model.set_named_weights(w0)
+    w = {k: v.copy() for k, v in w0.items()}
+    state = {}
+    ours, refs = [], []
+    for _ in range(6):
+        refs.append(uo.unet3d_train_step(x, t, w, state, 3e-4)["loss"])
+        ours.append(model.train_on_batch(x, t)[0])
+    assert refs[-1] < refs[0] - 0.01 and ours[-1] < ours[0] - 0.01, (ours, refs)   # it learns
+    assert np.max(np.abs(np.array(ours) - np.array(refs))) <= 0.02, (ours, refs)
+
+
+def test_evaluate_matches_host_metrics(setup):
+    import fetal_net.metrics as fm
+    model, _ = setup
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32)
+    t = blob_target(x.shape, rng)
+    p = model.predict(x)
+    loss, acc, vod = model.test_on_batch(x, t)
+    assert loss == pytest.approx(fm.dice_coefficient_loss(t, p), abs=1e-5)
+    assert acc == pytest.approx(fm.binary_accuracy(t, p), abs=1e-6)
+    assert vod == pytest.approx(fm.vod_coefficient(t, p), abs=1e-5)
+
+
+def test_backward_without_forward_is_an_error(setup):
+    from fetal_net import _lib
+    model, _ = setup
+    model.predict(np.zeros((1, 1, 32, 32, 32), np.float32))
+    with pytest.raises(_lib.FetalB200Error):
+        _lib.check(_lib.load().fm_train_backward(model._h))
+
+
+def test_bad_shapes_are_rejected():
+    from fetal_net import _lib
+    from fetal_net.model import unet_model_3d
+    with pytest.raises(_lib.FetalB200Error):
+        unet_model_3d(input_shape=(1, 30, 32, 32), n_base_filters=16)     # not divisible by 2^(depth-1)
+    with pytest.raises(_lib.FetalB200Error):
+        unet_model_3d(input_shape=(2, 32, 32, 32), n_base_filters=16)     # multi-modality not built

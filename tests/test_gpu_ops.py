@@ -1,0 +1,59 @@
+"""Per-kernel parity on the GPU, through the C ABI (see tests/gpu_cases.py for the stated tolerance)."""
+import pytest
+
+from tests import gpu_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+IDS = [c[0] for c in gc.CONV_CASES]
+SINGLE = [c for c in gc.CONV_CASES if c[6] == 0 and c[8] == 3]
+
+
+@pytest.mark.parametrize("case", gc.CONV_CASES, ids=IDS)
+def test_conv3d_fprop_tcgen05(ctx, case):
+    ok, worst = gc.conv_fprop_case(ctx, 0, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", gc.CONV_CASES[:9], ids=IDS[:9])
+def test_conv3d_fprop_simt(ctx, case):
+    ok, worst = gc.conv_fprop_case(ctx, 1, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", SINGLE, ids=[c[0] for c in SINGLE])
+def test_conv3d_dgrad_tcgen05(ctx, case):
+    ok, worst = gc.conv_dgrad_case(ctx, 0, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", SINGLE, ids=[c[0] for c in SINGLE])
+def test_conv3d_wgrad_tcgen05(ctx, case):
+    ok, worst = gc.conv_wgrad_case(ctx, 0, case)
+    assert ok, "rel. error / 2e-3 = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", SINGLE[:5], ids=[c[0] for c in SINGLE[:5]])
+def test_conv3d_wgrad_simt(ctx, case):
+    ok, worst = gc.conv_wgrad_case(ctx, 1, case)
+    assert ok, "rel. error / 2e-3 = %.3f" % worst
+
+
+def test_maxpool3d_fwd_bwd(ctx):
+    ok, worst = gc.maxpool_case(ctx)
+    assert ok, worst
+
+
+def test_upsample3d_fwd_bwd(ctx):
+    ok, worst = gc.upsample_case(ctx)
+    assert ok, worst
+
+
+def test_dice_sums_and_gradient(ctx):
+    ok, worst = gc.dice_case(ctx)
+    assert ok, worst
+
+
+def test_keras_adam(ctx):
+    ok, worst = gc.adam_case(ctx)
+    assert ok, worst

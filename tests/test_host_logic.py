@@ -1,0 +1,157 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/fetal_b200.h declares,
+the host-only entry point fm_patch_plan reproduces the reference plans, and the Python mirror of the
+reference interface keeps its names/signatures. No GPU compute here."""
+import ctypes
+import hashlib
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import prediction_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fetal_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from fetal_net import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), "libfetalb200.so does not export %s" % s
+        assert s in _lib.SIGNATURES, "ctypes binding missing for %s" % s
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from fetal_net import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libfetalb200.so")
+    with pytest.raises(_lib.FetalB200Error):
+        _lib.load()
+
+
+def test_ctx_create_without_gpu_reports_error(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = lib.fm_ctx_create(0, ctypes.byref(h))
+    assert rc != 0 and lib.fm_last_error()
+
+
+def test_fm_patch_plan_matches_golden_and_oracle(golden):
+    from fetal_net.prediction import patch_plan, get_set_of_patch_indices_full
+    names = sorted({k.split("/")[1] for k in golden if k.startswith("plan/")})
+    for name in names:
+        a = golden["plan/%s/args" % name]
+        padded, patch, pshape = tuple(int(v) for v in a[0:3]), tuple(int(v) for v in a[3:6]), tuple(int(v) for v in a[6:9])
+        f = float(golden["plan/%s/f" % name])
+        idx = patch_plan(padded, patch, pshape, f)
+        assert idx.dtype == np.int32 and idx.shape == (int(golden["plan/%s/n" % name]), 3), name
+        assert sha16(idx) == str(golden["plan/%s/sha" % name]), name
+        assert np.array_equal(idx, po.patch_plan(padded, patch, pshape, f)), name
+        ov = po.compute_overlap(patch, pshape, f)
+        assert np.array_equal(idx, get_set_of_patch_indices_full((0, 0, 0), np.subtract(padded, patch),
+                                                                 np.subtract(patch, ov))), name
+
+
+def test_fm_patch_plan_edge_cases():
+    from fetal_net import _lib
+    from fetal_net.prediction import patch_plan
+    # volume == patch: one patch; overlap 1.0 -> step 1 (predict.main default)
+    assert patch_plan((64, 64, 64), (64, 64, 64), (64, 64, 64), 0.5).tolist() == [[0, 0, 0]]
+    idx = patch_plan((20, 16, 16), (16, 16, 16), (16, 16, 16), 1.0)
+    assert idx[:, 0].tolist() == [0, 1, 2, 3, 4]
+    with pytest.raises(_lib.FetalB200Error):      # padded smaller than the patch
+        patch_plan((8, 64, 64), (64, 64, 64), (64, 64, 64), 0.5)
+    # randomised agreement with the oracle
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        patch = tuple(int(v) for v in rng.integers(1, 20, 3))
+        padded = tuple(int(p + v) for p, v in zip(patch, rng.integers(0, 40, 3)))
+        f = float(rng.choice([0.0, 0.25, 0.5, 0.77, 0.9, 1.0, rng.random()]))
+        assert np.array_equal(patch_plan(padded, patch, patch, f), po.patch_plan(padded, patch, patch, f))
+
+
+def test_geometry_matches_oracle_padding():
+    from fetal_net.prediction import _geometry
+
+    class M:
+        output_shape = (None, 1, 16, 16, 16)
+    rng = np.random.default_rng(1)
+    for vshape in [(1, 30, 12, 20), (1, 16, 16, 16), (1, 7, 40, 15)]:
+        vol = rng.standard_normal(vshape).astype(np.float32)
+        g = _geometry(M, vol, (16, 16, 16), 0.5)
+        d0, pf, _ = po.pad_volume(vol[0], (16, 16, 16), (16, 16, 16))
+        assert g["padded"] == d0.shape and [tuple(p) for p in g["fit"]] == [tuple(p) for p in pf]
+        # the virtual padding reproduces the reference's padded array exactly
+        rebuilt = np.full(g["padded"], g["pad"][1], np.float64)
+        sl = tuple(slice(a, a + s) for (a, _), s in zip(g["fit"], vol.shape[1:]))
+        rebuilt[sl] = vol[0]
+        assert np.array_equal(rebuilt.astype(np.float32), d0.astype(np.float32))
+
+
+def test_reference_api_surface():
+    import fetal_net.metrics as fm
+    import fetal_net.model as fmod
+    import fetal_net.prediction as fp
+    import fetal_net.training as ft
+    # names looked up by getattr in fetal/train_fetal.py:31-32 and exported by fetal_net/model/__init__.py:3-18
+    for n in ["unet_model_3d", "isensee2017_model_3d", "unet_model_2d", "isensee2017_model", "fetal_envelope_model",
+              "fetal_origin_model", "fetal_origin2_model", "fetal_origin3_model", "norm_net_model",
+              "discriminator_image_2d", "discriminator_image_3d"]:
+        assert callable(getattr(fmod, n)), n
+    for n in ["dice_coefficient", "dice_coefficient_loss", "dice_coef", "dice_coef_loss", "vod_coefficient",
+              "vod_coefficient_loss", "weighted_dice_coefficient", "weighted_dice_coefficient_loss",
+              "binary_crossentropy_loss", "focal_loss", "dice_and_xent", "dice_and_xent_mask"]:
+        assert callable(getattr(fm, n)), n
+    # signatures (prediction.py:118-119, unet3d/unet.py:17-20, training.py:89-92)
+    sig = inspect.signature(fp.patch_wise_prediction)
+    assert list(sig.parameters)[:9] == ["model", "data", "patch_shape", "overlap_factor", "batch_size", "permute",
+                                        "truth_data", "prev_truth_index", "prev_truth_size"]
+    assert sig.parameters["overlap_factor"].default == 0 and sig.parameters["batch_size"].default == 5
+    sig = inspect.signature(fmod.unet_model_3d)
+    assert sig.parameters["depth"].default == 4 and sig.parameters["n_base_filters"].default == 32
+    assert sig.parameters["initial_learning_rate"].default == 0.00001
+    assert sig.parameters["loss_function"].default is fm.dice_coefficient_loss
+    assert list(inspect.signature(ft.train_model).parameters)[:6] == [
+        "model", "model_file", "training_generator", "validation_generator", "steps_per_epoch", "validation_steps"]
+    with pytest.raises(NotImplementedError):
+        fmod.isensee2017_model_3d(input_shape=(1, 32, 32, 32))
+
+
+def test_host_metrics_known_answers():
+    import fetal_net.metrics as fm
+    d = np.zeros((1, 3, 10, 10, 10), np.float32)
+    d[0, 0, :5] = 1
+    d[0, 1, 5:] = 1
+    d[0, 2, :, :5] = 1
+    assert fm.dice_coefficient(d, d) == pytest.approx(1.0)
+    assert fm.dice_coefficient(d, np.zeros_like(d)) == pytest.approx(1.0 / 1501.0)
+    assert fm.dice_coefficient_loss(d, d) == pytest.approx(-1.0)
+    # reference test/test_metrics.py:19-38 (weighted dice known answers)
+    assert fm.weighted_dice_coefficient(d, d) == pytest.approx(1.0)
+    e = d.copy()
+    e[0, 0] = 0
+    assert fm.weighted_dice_coefficient(d, e) == pytest.approx(2 / 3, abs=1e-5)
+    assert fm.vod_coefficient(d, d) == pytest.approx(1.0)
+
+
+def test_callbacks_order():
+    # reference test/test_training.py:9-15
+    from fetal_net.training import EarlyStopping, ReduceLROnPlateau, get_callbacks
+    cbs = get_callbacks("model", early_stopping_patience=3)
+    assert isinstance(cbs[2], ReduceLROnPlateau) and isinstance(cbs[3], EarlyStopping)

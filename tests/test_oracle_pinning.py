@@ -1,0 +1,133 @@
+"""Pins the oracle (oracle/prediction_oracle.py) against (a) the goldens frozen from the unmodified
+reference code and (b) the reference itself where /root/reference is present (build container only).
+Also pins the closed forms of the network oracle (dice, Adam) against independent derivations."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prediction_oracle as po
+from oracle import unet_oracle as uo
+from oracle.ref_harness import FunctionModel, reference_available
+
+from tests.golden.make_golden import ramp_model
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def plan_names(golden):
+    return sorted({k.split("/")[1] for k in golden if k.startswith("plan/")})
+
+
+def run_names(golden):
+    return sorted({k.split("/")[1] for k in golden if k.startswith("run/")})
+
+
+def test_plans_match_golden(golden):
+    for name in plan_names(golden):
+        a = golden["plan/%s/args" % name]
+        padded, patch, pshape = tuple(a[0:3]), tuple(a[3:6]), tuple(a[6:9])
+        idx = po.patch_plan(padded, patch, pshape, float(golden["plan/%s/f" % name]))
+        assert len(idx) == int(golden["plan/%s/n" % name]), name
+        assert sha16(idx.astype(np.int32)) == str(golden["plan/%s/sha" % name]), name
+        if "plan/%s/idx" % name in golden:
+            assert np.array_equal(idx, golden["plan/%s/idx" % name]), name
+
+
+def test_survey_known_answers(golden):
+    # SURVEY.md §8c goldens (4) and (5)
+    idx = po.patch_plan((256, 256, 64), (64, 64, 64), (64, 64, 64), 0.5)
+    assert idx[:9].tolist() == [[0, 0, 0], [0, 33, 0], [0, 66, 0], [0, 99, 0], [0, 132, 0], [0, 165, 0],
+                                [0, 192, 0], [33, 0, 0], [33, 33, 0]]
+    assert len(idx) == 49
+    cnt = po.count_map((256, 256, 64), (64, 64, 64), idx)
+    assert sha16(cnt) == "ba96762db2430b62" == str(golden["count/cfg1/sha"])
+    hist = dict(zip(*[v.tolist() for v in golden["count/cfg1/hist"]]))
+    assert hist == {1: 295936, 2: 1601536, 3: 34816, 4: 2166784, 6: 94208, 9: 1024}
+    assert int(cnt.astype(np.int64).sum()) == 49 * 64 ** 3
+    assert np.array_equal(cnt[:, 0, 0], golden["count/cfg1/axis_x"])
+
+
+def test_patchwise_oracle_matches_golden(golden):
+    for name in run_names(golden):
+        vol = golden["run/%s/vol" % name]
+        patch = tuple(int(v) for v in golden["run/%s/patch" % name])
+        fn, oshape = ramp_model(patch, int(golden["run/%s/channels" % name]))
+        out = po.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch,
+                                       overlap_factor=float(golden["run/%s/f" % name]),
+                                       batch_size=int(golden["run/%s/batch" % name]))
+        ref = golden["run/%s/out" % name]
+        assert out.dtype == np.float64 and out.shape == ref.shape, name
+        assert np.array_equal(out, ref), name      # bit-exact
+
+
+def test_extract_patch_matches_golden(golden):
+    data = golden["patch/data"]
+    shape = tuple(int(v) for v in golden["patch/shape"])
+    for i, c in enumerate(golden["patch/corners"]):
+        assert np.array_equal(po.extract_patch(data, shape, c), golden["patch/out%d" % i]), i
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_matches_live_reference():
+    from oracle.ref_harness import load_reference_prediction
+    pred = load_reference_prediction()
+    rng = np.random.default_rng(3)
+    for vshape, patch, f, bs in [((1, 33, 20, 18), (16, 8, 8), 0.5, 5), ((1, 10, 30, 9), (16, 16, 8), 0.7, 2)]:
+        vol = rng.standard_normal(vshape).astype(np.float32)
+        fn, oshape = ramp_model(patch, 1)
+        ref = pred.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch_shape=patch, overlap_factor=f,
+                                         batch_size=bs)
+        out = po.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch, overlap_factor=f, batch_size=bs)
+        assert np.array_equal(out, ref)
+    # identity-model goldens of SURVEY.md §8c (1)-(2)
+    for vshape in [(1, 96, 80, 40), (1, 70, 70, 20)]:
+        vol = np.random.default_rng(0).standard_normal(vshape).astype(np.float32)
+        m = FunctionModel(lambda x: x.astype(np.float32), (None, 1, 32, 32, 32))
+        out = po.patch_wise_prediction(m, vol, (32, 32, 32), overlap_factor=0.5)
+        assert np.array_equal(out[..., 0], vol[0])
+
+
+# ---- network oracle: closed forms ------------------------------------------------------------
+
+def test_dice_known_answers():
+    # the test_metrics tensor of the reference (test/test_metrics.py:13-17): a 3-channel block pattern
+    d = np.zeros((1, 3, 10, 10, 10), np.float32)
+    d[0, 0, :5] = 1
+    d[0, 1, 5:] = 1
+    d[0, 2, :, :5] = 1
+    t = torch.tensor(d)
+    assert float(uo.dice_coefficient(t, t)) == pytest.approx(1.0)
+    assert float(uo.dice_coefficient(t, torch.zeros_like(t))) == pytest.approx(1.0 / (d.sum() + 1.0))
+    assert float(uo.dice_coefficient(torch.zeros_like(t), torch.zeros_like(t))) == pytest.approx(1.0)
+
+
+def test_dice_closed_form_gradient_matches_autograd():
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(2, 1, 6, 5, 4, generator=g, dtype=torch.float64, requires_grad=True)
+    t = (torch.rand(2, 1, 6, 5, 4, generator=g) < 0.3).double()
+    uo.dice_coefficient_loss(t, p).backward()
+    assert torch.allclose(p.grad, uo.dice_grad_closed_form(t, p.detach()), rtol=1e-12, atol=1e-14)
+
+
+def test_keras_adam_first_steps():
+    # Keras-2 Adam, step 1: m = (1-b1) g, v = (1-b2) g^2, lr_t = lr*sqrt(1-b2)/(1-b1)
+    p = np.array([1.0, -2.0], np.float32)
+    g = np.array([0.5, -0.25], np.float32)
+    m, v = np.zeros(2, np.float32), np.zeros(2, np.float32)
+    uo.keras_adam_step(p, g, m, v, 0, 1e-3)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    exp = np.array([1.0, -2.0]) - lr_t * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-7)
+    assert np.allclose(p, exp, rtol=1e-6)
+
+
+def test_param_counts_match_survey():
+    # 4 079 713 / 16 315 585 / 8 263 619 / 5 441 569
+    n = lambda L: sum(k ** (3 if len(L[0]) and True else 3) * ci * co + co for _, ci, co, k in L)
+    assert n(uo.unet3d_layers(4, 16)) == 4079713
+    assert n(uo.unet3d_layers(4, 32)) == 16315585
+    assert n(uo.isensee3d_layers(5, 16, 3)) == 8263619
+    assert sum(k ** 2 * ci * co + co for _, ci, co, k in uo.unet2d_layers(4, 32, 6)) == 5441569
