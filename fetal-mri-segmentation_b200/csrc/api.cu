@@ -55,6 +55,10 @@ extern "C" int fm_ctx_destroy(fm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->red_scratch) cudaFree(ctx->red_scratch);
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -75,6 +79,47 @@ extern "C" int fm_ctx_synchronize(fm_ctx* ctx) {
   return FM_OK;
 }
 extern "C" int64_t fm_ctx_launch_count(fm_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int fm_prof_begin(fm_ctx* ctx, const char* name, double flops, double bytes) {
+  ProfRec r;
+  r.name = name;
+  r.flops = flops;
+  r.bytes = bytes;
+  FM_CUDA(cudaEventCreate(&r.e0));
+  FM_CUDA(cudaEventCreate(&r.e1));
+  FM_CUDA(cudaEventRecord(r.e0, ctx->stream));
+  ctx->prof.push_back(r);
+  return FM_OK;
+}
+int fm_prof_end(fm_ctx* ctx) {
+  if (ctx->prof.empty()) return FM_OK;
+  FM_CUDA(cudaEventRecord(ctx->prof.back().e1, ctx->stream));
+  return FM_OK;
+}
+extern "C" int fm_ctx_profile_enable(fm_ctx* ctx, int on) {
+  FM_CHECK(ctx, FM_EINVAL, "NULL ctx");
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  ctx->profile = on != 0;
+  return FM_OK;
+}
+extern "C" int fm_ctx_profile_count(fm_ctx* ctx) { return ctx ? (int)ctx->prof.size() : -1; }
+extern "C" int fm_ctx_profile_get(fm_ctx* ctx, int i, char name[48], double out[3]) {
+  FM_CHECK(ctx && i >= 0 && i < (int)ctx->prof.size() && name && out, FM_EINVAL, "profile record %d", i);
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  FM_CUDA(cudaEventElapsedTime(&ms, ctx->prof[i].e0, ctx->prof[i].e1));
+  memset(name, 0, 48);
+  strncpy(name, ctx->prof[i].name, 47);
+  out[0] = ms;
+  out[1] = ctx->prof[i].flops;
+  out[2] = ctx->prof[i].bytes;
+  return FM_OK;
+}
 
 int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out) {
   if (ctx->pinned_bytes < bytes) {

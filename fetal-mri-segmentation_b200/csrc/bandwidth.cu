@@ -504,6 +504,7 @@ int k_maxpool3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in) {
   FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % 2 == 0, FM_EINVAL,
            "maxpool3d: need C%%8==0 and even extents (got C=%d %dx%dx%d)", in.C, in.X, in.Y, in.Z);
   const int64_t total = in.elems() / 64;
+  ProfScope prof(ctx, "maxpool3d_fwd", 0.0, (double)in.elems() * 2.0 * 1.125);
   maxpool3d_fwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z,
                                                                      in.C);
   FM_LAUNCH_OK(ctx);
@@ -514,6 +515,7 @@ int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dski
   FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % 2 == 0, FM_EINVAL,
            "maxpool3d_bwd: need C%%8==0 and even extents");
   const int64_t total = in.elems() / 64;
+  ProfScope prof(ctx, "maxpool3d_bwd", 0.0, (double)in.elems() * 2.0 * (dskip ? 3.125 : 2.125));
   maxpool3d_bwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X,
                                                                      in.Y, in.Z, in.C, relu_mask);
   FM_LAUNCH_OK(ctx);
@@ -521,6 +523,7 @@ int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dski
 }
 int k_upsample3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in) {
   FM_CHECK(in.C % 8 == 0, FM_EINVAL, "upsample3d: need C%%8==0");
+  ProfScope prof(ctx, "upsample3d_fwd", 0.0, (double)in.elems() * 2.0 * 9.0);
   upsample3d_fwd_kernel<<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X,
                                                                                in.Y, in.Z, in.C);
   FM_LAUNCH_OK(ctx);
@@ -530,6 +533,7 @@ int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dim
                      int dy_cofs) {
   FM_CHECK(coarse.C % 8 == 0 && dy_C % 8 == 0 && dy_cofs % 8 == 0, FM_EINVAL,
            "upsample3d_bwd: channel counts must be multiples of 8");
+  ProfScope prof(ctx, "upsample3d_bwd", 0.0, (double)coarse.elems() * 2.0 * (act ? 10.0 : 9.0));
   upsample3d_bwd_kernel<<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
       dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
   FM_LAUNCH_OK(ctx);
@@ -537,6 +541,7 @@ int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dim
 }
 
 int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* sums, int accumulate) {
+  ProfScope prof(ctx, "dice_sums", 0.0, (double)n * 8.0);
   dice_partial_kernel<<<kRedBlocks, kThreads, 0, ctx->stream>>>(p, t, n, ctx->red_scratch);
   FM_LAUNCH_OK(ctx);
   dice_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->red_scratch, kRedBlocks, (double)n, sums,
@@ -546,6 +551,7 @@ int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* 
 }
 int k_dice_bwd(fm_ctx* ctx, const float* p, const float* t, const double* sums, int64_t n, float* dz,
                int through_sigmoid) {
+  ProfScope prof(ctx, "dice_bwd", 0.0, (double)n * 12.0);
   dice_bwd_kernel<<<grid_for(ceil_div64(n, 4)), kThreads, 0, ctx->stream>>>(p, t, sums, n, dz,
                                                                            through_sigmoid);
   FM_LAUNCH_OK(ctx);
@@ -556,6 +562,7 @@ int k_adam(fm_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n,
   const double b1 = 0.9, b2 = 0.999;
   const double t = (double)iterations + 1.0;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
+  ProfScope prof(ctx, "adam", 0.0, (double)n * 28.0);
   adam_kernel<<<grid_for(ceil_div64(n, 4)), kThreads, 0, ctx->stream>>>(p, g, m, v, n, lr_t, 0.9f,
                                                                        0.999f, 1e-7f);
   FM_LAUNCH_OK(ctx);
@@ -579,6 +586,7 @@ int k_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
     gm.patch[a] = patch[a];
   }
   const int64_t total = n * (int64_t)patch[0] * patch[1] * patch[2];
+  ProfScope prof(ctx, "gather_patches", 0.0, (double)total * 8.0);
   gather_patches_kernel<<<grid_for(total, 148 * 32), kThreads, 0, ctx->stream>>>(vol, gm, pad0, pad1,
                                                                                 idx_dev, n, out);
   FM_LAUNCH_OK(ctx);
@@ -649,6 +657,7 @@ int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64
   gm.np[2] = (int)np2;
   gm.channels = channels;
   const int64_t total = (int64_t)out_dims[0] * out_dims[1] * out_dims[2] * channels;
+  ProfScope prof(ctx, "reassemble", 0.0, (double)(shard_hi - shard_lo) * pred_shape[0] * pred_shape[1] * pred_shape[2] * channels * 4.0 + (double)total * 8.0);
   reassemble_kernel<<<grid_for(total, 148 * 16), kThreads, 0, ctx->stream>>>(
       preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo, shard_hi, pred_base, out_dev, count_dev,
       divide);

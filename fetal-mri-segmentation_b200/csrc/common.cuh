@@ -42,8 +42,17 @@ void fm_set_error(const char* fmt, ...);
     if (_r != FM_OK) return _r;                                                               \
   } while (0)
 
+struct ProfRec {
+  const char* name;
+  double flops, bytes;
+  cudaEvent_t e0, e1;
+};
+
 struct fm_ctx {
   int device = 0;
+  // optional per-launch timing (fm_ctx_profile_*): CUDA events around every kernel launch
+  bool profile = false;
+  std::vector<ProfRec> prof;
   int sm_major = 0, sm_minor = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
@@ -58,6 +67,19 @@ int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Per-launch profiling hooks: `flops` / `bytes` are the ALGORITHMIC figures of the launch.
+int fm_prof_begin(fm_ctx* ctx, const char* name, double flops, double bytes);
+int fm_prof_end(fm_ctx* ctx);
+struct ProfScope {
+  fm_ctx* ctx;
+  ProfScope(fm_ctx* c, const char* name, double flops, double bytes) : ctx(c) {
+    if (ctx->profile) fm_prof_begin(ctx, name, flops, bytes);
+  }
+  ~ProfScope() {
+    if (ctx->profile) fm_prof_end(ctx);
+  }
+};
 
 // Launch-error check that also counts the launch (bench.py reports gpu_launches from this).
 #define FM_LAUNCH_OK(ctx)                                                                     \

@@ -323,6 +323,7 @@ int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2
       mask == nullptr && bias != nullptr && (Cout == 16 || Cout == 32)) {
     const int64_t nvox = (int64_t)N * X * Y * Z;
     const int grid = grid_for(nvox, ctx->num_sms * 16);
+    ProfScope prof(ctx, "conv3d_first", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
     if (Cout == 16)
       conv3d_first_kernel<16><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, w_packed, bias, y,
                                                                  N, X, Y, Z, relu);
@@ -333,6 +334,7 @@ int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2
     return FM_OK;
   }
   const int64_t total = (int64_t)N * X * Y * Z * Cout;
+  ProfScope prof(ctx, "conv3d_simt_fprop", 2.0 * ksize * ksize * ksize * (C1 + C2) * (double)total, 0.0);
   conv3d_simt_fprop_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(
       x, x_is_f32, x2, w_packed, bias, y, y_f32, N, X, Y, Z, C1, C2, Cout, ksize, relu, mask);
   FM_LAUNCH_OK(ctx);
@@ -351,6 +353,7 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
   chunks = std::min<int64_t>(chunks, 65535);
   const int64_t vpc = ceil_div64(nvox, chunks);
   dim3 grid((unsigned)ceil_div64(n_out, kThreads / 32), (unsigned)ceil_div64(nvox, vpc));
+  ProfScope prof(ctx, "conv3d_simt_wgrad", 2.0 * (double)n_out * (double)nvox, 0.0);
   conv3d_simt_wgrad_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, x_is_f32, dy, dw_packed, N, X, Y, Z,
                                                               Cin, Cin_total, cin_ofs, Cout, ksize,
                                                               vpc);
@@ -365,6 +368,7 @@ int k_bias_grad(fm_ctx* ctx, const bf16* dy, float* db, int64_t voxels, int C) {
   int64_t blocks = std::min<int64_t>((int64_t)ctx->num_sms * 8, std::max<int64_t>(1, voxels / (lanes * 8)));
   const int64_t vpb = ceil_div64(voxels, blocks);
   blocks = ceil_div64(voxels, vpb);
+  ProfScope prof(ctx, "bias_grad", 0.0, (double)voxels * C * 2.0);
   bias_grad_kernel<<<(unsigned)blocks, threads, threads * sizeof(float), ctx->stream>>>(dy, db, voxels,
                                                                                        C, vpb);
   FM_LAUNCH_OK(ctx);
@@ -378,6 +382,7 @@ int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float
   const int lpv = C / 8;
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 32);
+  ProfScope prof(ctx, "head_fwd", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 4.0));
   head_fwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, w, b, p, voxels, C);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
@@ -390,6 +395,7 @@ int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16
   const int lpv = C / 8;
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 8);
+  ProfScope prof(ctx, "head_bwd", 4.0 * C * (double)voxels, (double)voxels * (C * 4.0 + 4.0));
   head_bwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, dz, w, dx, dw, db, voxels, C);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
@@ -398,6 +404,7 @@ int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16
 int k_repack_weights(fm_ctx* ctx, const float* w, bf16* w_f, bf16* w_d0, bf16* w_d1, int Cout, int taps,
                      int C1, int C2) {
   const int64_t total = (int64_t)Cout * taps * (C1 + C2);
+  ProfScope prof(ctx, "repack_weights", 0.0, (double)total * 8.0);
   repack_weights_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(w, w_f, w_d0, w_d1, Cout, taps,
                                                                       C1, C2);
   FM_LAUNCH_OK(ctx);

@@ -725,6 +725,9 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
     attr_set = true;
   }
   const int grid = std::min(p.m_tiles * p.n_tiles, ctx->num_sms);
+  const double vox = (double)N * X * Y * Z;
+  ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_tc_dgrad" : "conv3d_tc_fprop",
+                 2.0 * p.ntaps * Ct * Cout * vox, vox * (Ct + Cout) * 2.0);
   conv3d_tc_fprop_kernel<<<grid, kThreadsTc, smem, ctx->stream>>>(p);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
@@ -777,6 +780,8 @@ int k_conv3d_tc_wgrad(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_pack
                                  kMaxDynSmem));
     attr_set = true;
   }
+  const double vox = (double)N * X * Y * Z;
+  ProfScope prof(ctx, "conv3d_tc_wgrad", 2.0 * p.ntaps * Cin * Cout * vox, vox * (Cin + Cout) * 2.0);
   conv3d_tc_wgrad_kernel<<<items * splits, kThreadsTc, smem, ctx->stream>>>(p);
   FM_LAUNCH_OK(ctx);
   return FM_OK;

@@ -39,6 +39,9 @@ SIGNATURES = {
     "fm_ctx_stream": (c_u64, [c_vp]),
     "fm_ctx_synchronize": (c_int, [c_vp]),
     "fm_ctx_launch_count": (c_i64, [c_vp]),
+    "fm_ctx_profile_enable": (c_int, [c_vp, c_int]),
+    "fm_ctx_profile_count": (c_int, [c_vp]),
+    "fm_ctx_profile_get": (c_int, [c_vp, c_int, ctypes.c_char_p, c_dp]),
     "fm_model_create_unet3d": (c_int, [c_vp, ctypes.POINTER(UNet3DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_destroy": (c_int, [c_vp]),
     "fm_model_num_layers": (c_int, [c_vp]),
@@ -155,6 +158,20 @@ class Context:
 
     def launch_count(self):
         return int(load().fm_ctx_launch_count(self.handle))
+
+    def profile(self, on):
+        check(load().fm_ctx_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_records(self):
+        """[(kernel name, ms, algorithmic flops, algorithmic bytes)] since profile(True)."""
+        lib = load()
+        out = []
+        for i in range(lib.fm_ctx_profile_count(self.handle)):
+            name = ctypes.create_string_buffer(48)
+            v = (c_d * 3)()
+            check(lib.fm_ctx_profile_get(self.handle, i, name, v))
+            out.append((name.value.decode(), float(v[0]), float(v[1]), float(v[2])))
+        return out
 
     def device_info(self):
         out = (c_int * 3)()

@@ -50,6 +50,13 @@ int fm_ctx_synchronize(fm_ctx* ctx);
 /* Number of kernels this library has launched on ctx since creation (bench `gpu_launches`). */
 int64_t fm_ctx_launch_count(fm_ctx* ctx);
 
+/* Per-launch timing (bench.py's roofline leg): when enabled, every kernel launch on ctx is
+ * bracketed by CUDA events; record i gives name, out[0]=ms, out[1]=algorithmic FLOPs,
+ * out[2]=algorithmic bytes of that launch. Enabling/disabling clears the records. */
+int fm_ctx_profile_enable(fm_ctx* ctx, int on);
+int fm_ctx_profile_count(fm_ctx* ctx);
+int fm_ctx_profile_get(fm_ctx* ctx, int i, char name[48], double out[3]);
+
 /* ---- model -------------------------------------------------------------------------------- */
 
 /* Builder spec. Replaces the kwargs of unet_model_3d (fetal_net/model/unet3d/unet.py:17-20):
