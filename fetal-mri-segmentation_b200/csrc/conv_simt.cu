@@ -175,6 +175,80 @@ __global__ void __launch_bounds__(kThreads) conv3d_first_kernel(const float* __r
   }
 }
 
+
+// --------------------------------------------------------------------------------------------
+// first-layer wgrad (Cin = 1): dW[co][tap] = sum_v dY[v][co] * x[v + shift(tap)].
+// A warp owns one (kx, 16-channel slice) class and 32 consecutive voxels per trip; every lane keeps
+// the 9 (ky,kz) x 16 (co) partial sums of its class in registers, the warp butterfly-reduces them once
+// at the end and issues 144 fp32 red.add per warp. dY rows are read as full 32 B sectors.
+// --------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(32 * 3 * (COUT / 16) * 2) conv3d_first_wgrad_kernel(
+    const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int N, int X,
+    int Y, int Z) {
+  constexpr int NCLS = 3 * (COUT / 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = warp % NCLS, vgrp = warp / NCLS;  // 2 voxel groups per block
+  const int kx = cls % 3, chalf = cls / 3;
+  const int64_t nvox = (int64_t)N * X * Y * Z;
+  float acc[9][16];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[t][c] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * 2 * 32;
+  for (int64_t v = ((int64_t)blockIdx.x * 2 + vgrp) * 32 + lane; v < nvox; v += stride) {
+    const int z = (int)(v % Z);
+    int64_t r = v / Z;
+    const int yy = (int)(r % Y);
+    r /= Y;
+    const int xx = (int)(r % X);
+    const int n = (int)(r / X);
+    const int xi = xx + kx - 1;
+    if (xi < 0 || xi >= X) continue;
+    float g[16];
+    {
+      const uint4* gp = reinterpret_cast<const uint4*>(dy + v * COUT + chalf * 16);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 t4 = __ldg(gp + h);
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(hh[j]);
+          g[8 * h + 2 * j] = f.x;
+          g[8 * h + 2 * j + 1] = f.y;
+        }
+      }
+    }
+    const float* xb = x + ((int64_t)n * X + xi) * Y * Z;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yi = yy + ky - 1;
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+        const int zi = z + kz - 1;
+        float xv = 0.f;
+        if (yi >= 0 && yi < Y && zi >= 0 && zi < Z) xv = __ldg(xb + (int64_t)yi * Z + zi);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[ky * 3 + kz][c] += xv * g[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float a = acc[t][c];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      if (lane == ((t * 16 + c) & 31)) {
+        const int co = chalf * 16 + c;
+        atomicAdd(dw + co * 27 + kx * 9 + t, a);  // packed [Cout][27][1]
+      }
+    }
+}
+
 // --------------------------------------------------------------------------------------------
 // bias gradient: db[c] += sum_v dy[v][c]. Threads are laid out (voxel-lane, channel) with the
 // channel fastest so each warp reads a contiguous run of rows.
@@ -347,6 +421,16 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
   const int taps = ksize * ksize * ksize;
   const int64_t n_out = (int64_t)Cout * taps * Cin;
   const int64_t nvox = (int64_t)N * X * Y * Z;
+  if (x_is_f32 && Cin == 1 && Cin_total == 1 && cin_ofs == 0 && ksize == 3 && (Cout == 16 || Cout == 32)) {
+    ProfScope prof(ctx, "conv3d_first_wgrad", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
+    const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 64), (int64_t)ctx->num_sms * 4);
+    if (Cout == 16)
+      conv3d_first_wgrad_kernel<16><<<grid, 32 * 3 * 1 * 2, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+    else
+      conv3d_first_wgrad_kernel<32><<<grid, 32 * 3 * 2 * 2, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+    FM_LAUNCH_OK(ctx);
+    return FM_OK;
+  }
   // enough voxel chunks that small layers (the 432 outputs of the first layer) still fill the GPU
   int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms * 64 / std::max<int64_t>(1, n_out / 8));
   chunks = std::min<int64_t>(chunks, std::max<int64_t>(1, nvox / 1024));
