@@ -169,6 +169,9 @@ struct Layer {
   int level;            // resolution level (0 = full)
   int64_t w_off, b_off; // offsets in the flat fp32 parameter buffer (kernel packed [Cout][taps][Cin])
   bf16 *w_f = nullptr, *w_d0 = nullptr, *w_d1 = nullptr;  // bf16 packs (fprop, dgrad per source)
+  // plane-marching kernel (conv_march.cu): packs per source for fprop / dgrad, null when not applicable
+  bf16 *w_mf[2] = {nullptr, nullptr}, *w_md[2] = {nullptr, nullptr};
+  bool march_f = false, march_d[2] = {false, false};
   int cin() const { return c1 + c2; }
   int taps() const { return k * k * k; }
   int64_t wcount() const { return (int64_t)cout * taps() * cin(); }
@@ -218,6 +221,12 @@ static Layer& L(fm_model* m, const char* fmt, int d) {
   char nm[32];
   snprintf(nm, sizeof(nm), fmt, d);
   return m->layers[layer_index(m, nm)];
+}
+
+// FETAL_B200_NO_MARCH=1 forces the per-tap kernel everywhere (A/B measurements, debugging)
+static bool use_march() {
+  const char* e = getenv("FETAL_B200_NO_MARCH");
+  return !(e && e[0] == '1');
 }
 
 extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out) {
@@ -294,6 +303,21 @@ extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, f
     l.w_d1 = wp + (int64_t)l.c1 * l.taps() * l.cout;
     wp += padded;
   }
+  for (auto& l : m->layers) {
+    if (l.k != 3 || l.c1 < 16) continue;
+    const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
+    const int cs[2] = {l.c1, l.c2};
+    if (use_march() && conv_march_supported(X, Y, Z, l.c1, l.c2, l.cout, l.k)) {
+      l.march_f = true;
+      for (int s = 0; s < (l.c2 ? 2 : 1); ++s)
+        FM_CUDA(cudaMalloc((void**)&l.w_mf[s], (size_t)conv_march_pack_elems(cs[s], l.cout) * sizeof(bf16)));
+    }
+    for (int s = 0; s < (l.c2 ? 2 : 1); ++s)
+      if (use_march() && conv_march_supported(X, Y, Z, l.cout, 0, cs[s], l.k)) {
+        l.march_d[s] = true;
+        FM_CUDA(cudaMalloc((void**)&l.w_md[s], (size_t)conv_march_pack_elems(l.cout, cs[s]) * sizeof(bf16)));
+      }
+  }
   FM_CUDA(cudaMalloc((void**)&m->sums, 8 * sizeof(double)));
   FM_CUDA(cudaMemset(m->sums, 0, 8 * sizeof(double)));
   m->encA.resize(D);
@@ -342,6 +366,11 @@ extern "C" int fm_model_destroy(fm_model* m) {
   cudaFree(m->adam_v);
   cudaFree(m->wpack);
   cudaFree(m->sums);
+  for (auto& l : m->layers)
+    for (int s = 0; s < 2; ++s) {
+      if (l.w_mf[s]) cudaFree(l.w_mf[s]);
+      if (l.w_md[s]) cudaFree(l.w_md[s]);
+    }
   m->x_in.release();
   m->t_in.release();
   m->prob.release();
@@ -440,6 +469,14 @@ static int refresh_packs(fm_model* m) {
     if (l.k == 1 && l.cout == 1) continue;  // head reads fp32 weights directly
     FM_TRY(k_repack_weights(m->ctx, m->params + l.w_off, l.w_f, l.w_d0, l.c2 ? l.w_d1 : nullptr, l.cout,
                             l.taps(), l.c1, l.c2));
+    const int cs[2] = {l.c1, l.c2};
+    int kofs = 0;
+    for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
+      if (l.march_f) FM_TRY(k_repack_march(m->ctx, l.w_f, l.w_mf[s], l.cout, l.cin(), kofs, cs[s]));
+      if (l.march_d[s])
+        FM_TRY(k_repack_march(m->ctx, s == 0 ? l.w_d0 : l.w_d1, l.w_md[s], cs[s], l.cout, 0, l.cout));
+      kofs += cs[s];
+    }
   }
   m->packs_dirty = false;
   return FM_OK;
@@ -494,6 +531,9 @@ static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2,
   fm_ctx* ctx = m->ctx;
   const Dims5 d = m->dims(l.level, l.cout, B);
   const float* bias = m->params + l.b_off;
+  if (l.march_f)
+    return k_conv3d_march(ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2,
+                          l.cout, 1, l.cout, 0);
   if (conv_tc_supported(l.c1, l.c2, l.cout, l.k))
     return k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout,
                              l.k, 1, l.cout, 0);
@@ -563,6 +603,9 @@ static int conv_dgrad(fm_model* m, const Layer& l, int src, const bf16* dy, cons
   const Dims5 d = m->dims(l.level, l.cout, B);
   const int cs = src == 0 ? l.c1 : l.c2;
   const bf16* wd = src == 0 ? l.w_d0 : l.w_d1;
+  if (l.march_d[src])
+    return k_conv3d_march(ctx, dy, nullptr, l.w_md[src], nullptr, nullptr, dx, mask, B, d.X, d.Y, d.Z, l.cout,
+                          0, cs, 0, cs, 0);
   if (conv_tc_supported(l.cout, 0, cs, l.k))
     return k_conv3d_tc_fprop(ctx, dy, nullptr, wd, nullptr, dx, mask, B, d.X, d.Y, d.Z, l.cout, 0, cs, l.k,
                              0, cs, 0);
@@ -1034,7 +1077,17 @@ extern "C" int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const f
   FM_TRY(s.up_bf16(packed.data(), packed.size(), &dw));
   if (bias) FM_TRY(s.up_f32(bias, Cout, &dbias));
   FM_TRY(s.alloc(&dy, vox * Cout));
-  if (impl == 0)
+  if (impl == 2) {
+    FM_CHECK(conv_march_supported(X, Y, Z, C1, C2, Cout, ksize), FM_EINVAL, "march kernel does not cover this shape");
+    bf16 *wm1 = nullptr, *wm2 = nullptr;
+    FM_TRY(s.alloc(&wm1, (size_t)conv_march_pack_elems(C1, Cout)));
+    FM_TRY(k_repack_march(ctx, dw, wm1, Cout, Ct, 0, C1));
+    if (C2 > 0) {
+      FM_TRY(s.alloc(&wm2, (size_t)conv_march_pack_elems(C2, Cout)));
+      FM_TRY(k_repack_march(ctx, dw, wm2, Cout, Ct, C1, C2));
+    }
+    FM_TRY(k_conv3d_march(ctx, dx1, dx2, wm1, wm2, dbias, dy, nullptr, N, X, Y, Z, C1, C2, Cout, relu, Cout, 0));
+  } else if (impl == 0)
     FM_TRY(k_conv3d_tc_fprop(ctx, dx1, dx2, dw, dbias, dy, nullptr, N, X, Y, Z, C1, C2, Cout, ksize, relu,
                              Cout, 0));
   else
@@ -1061,7 +1114,13 @@ extern "C" int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const 
   FM_TRY(s.up_bf16(dy, vox * Cout, &ddy));
   if (mask) FM_TRY(s.up_bf16(mask, vox * Cin, &dmask));
   FM_TRY(s.alloc(&ddx, vox * Cin));
-  if (impl == 0)
+  if (impl == 2) {
+    FM_CHECK(conv_march_supported(X, Y, Z, Cout, 0, Cin, ksize), FM_EINVAL, "march kernel does not cover this shape");
+    bf16* wm = nullptr;
+    FM_TRY(s.alloc(&wm, (size_t)conv_march_pack_elems(Cout, Cin)));
+    FM_TRY(k_repack_march(ctx, wd, wm, Cin, Cout, 0, Cout));
+    FM_TRY(k_conv3d_march(ctx, ddy, nullptr, wm, nullptr, nullptr, ddx, dmask, N, X, Y, Z, Cout, 0, Cin, 0, Cin, 0));
+  } else if (impl == 0)
     FM_TRY(k_conv3d_tc_fprop(ctx, ddy, nullptr, wd, nullptr, ddx, dmask, N, X, Y, Z, Cout, 0, Cin, ksize, 0,
                              Cin, 0));
   else

@@ -150,16 +150,18 @@ def keras_adam_step(p, g, m, v, iterations, lr, beta_1=0.9, beta_2=0.999, eps=1e
     p[...] = p - np.float32(lr_t) * m / (np.sqrt(v) + np.float32(eps))
 
 
-def unet3d_train_step(x, t, w, adam_state, lr, depth=4, dtype=torch.float32):
-    """One fwd + Dice loss + bwd + Keras-Adam update. Mutates w/adam_state. Returns dict of scalars+grads."""
+def unet3d_train_step(x, t, w, adam_state, lr, depth=4, dtype=torch.float32, quant=None):
+    """One fwd + Dice loss + bwd + Keras-Adam update. Mutates w/adam_state. Returns dict of scalars+grads.
+    `quant` (e.g. a bf16 round trip) is applied to stored activations/weights in the forward pass; autograd
+    treats it as identity, so ReLU masks and max-pool routing are decided on the quantised values."""
     names = sorted(w.keys())
     params = {n: torch.tensor(w[n], dtype=dtype, requires_grad=True) for n in names}
     xt = torch.as_tensor(x).to(dtype)
     tt = torch.as_tensor(t).to(dtype)
-    p = unet3d_forward(xt, params, depth=depth)
+    p = unet3d_forward(xt, params, depth=depth, quant=quant)
     loss = dice_coefficient_loss(tt, p)
     loss.backward()
-    out = {"loss": float(loss), "binary_accuracy": float(binary_accuracy(tt, p.detach())),
+    out = {"loss": float(loss.detach()), "binary_accuracy": float(binary_accuracy(tt, p.detach())),
            "vod_coefficient": float(vod_coefficient(tt, p.detach())), "grads": {}, "pred": p.detach().numpy()}
     it = adam_state.setdefault("iterations", 0)
     for n in names:

@@ -61,6 +61,18 @@ CONV_CASES = [
     ("cfg_64cube_16_32", 1, 64, 64, 64, 16, 0, 32, 3),  # enc0b at the real patch size
 ]
 
+# shapes the plane-marching kernel covers (Y % 16 == 0, Z % 8 == 0, filter bank resident in smem)
+MARCH_CASES = [
+    ("m32_32_16cube", 1, 16, 16, 16, 32, 0, 32, 3),
+    ("m16_32_32cube", 2, 32, 32, 32, 16, 0, 32, 3),     # SW32 slabs, ring wrap (X > 16 blocks)
+    ("m32_64_16x32x16", 1, 16, 32, 16, 32, 0, 64, 3),   # N = 64 (ring of 8 blocks)
+    ("m_oddx_10x16x8", 3, 10, 16, 8, 32, 0, 32, 3),     # X not a multiple of the x-chunk
+    ("m_cat64_32_32cube", 2, 32, 32, 32, 64, 32, 32, 3),  # dec0a: two sources, mixed swizzle
+    ("m64_16_32cube", 1, 32, 32, 32, 64, 0, 16, 3),     # N = 16 blocks
+    ("m_x2", 2, 2, 16, 8, 16, 0, 16, 3),                # only two planes
+    ("m_cfg_64cube_32_32", 1, 64, 64, 64, 32, 0, 32, 3),  # dec0b at the real patch size
+]
+
 
 def conv_fprop_case(ctx, impl, case, seed=0):
     name, N, X, Y, Z, C1, C2, Cout, k = case

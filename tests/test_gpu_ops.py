@@ -39,6 +39,25 @@ def test_conv3d_wgrad_simt(ctx, case):
     assert ok, "rel. error / 2e-3 = %.3f" % worst
 
 
+MIDS = [c[0] for c in gc.MARCH_CASES]
+MSINGLE = [c for c in gc.MARCH_CASES if c[6] == 0]
+
+
+@pytest.mark.parametrize("case", gc.MARCH_CASES, ids=MIDS)
+def test_conv3d_fprop_march(ctx, case):
+    ok, worst = gc.conv_fprop_case(ctx, 2, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", MSINGLE, ids=[c[0] for c in MSINGLE])
+def test_conv3d_dgrad_march(ctx, case):
+    # dgrad runs the marching kernel with Cout input channels and C1 output channels
+    if case[7] > 64 or case[5] > 64:
+        pytest.skip("filter bank not resident")
+    ok, worst = gc.conv_dgrad_case(ctx, 2, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
 def test_maxpool3d_fwd_bwd(ctx):
     ok, worst = gc.maxpool_case(ctx)
     assert ok, worst

@@ -110,9 +110,10 @@ def test_native_pipeline_close_to_fp32_oracle(native):
     out = patch_wise_prediction(model, vol, patch_shape=(32, 32, 32), overlap_factor=0.5)
     ref = po.patch_wise_prediction(uo.OracleModel(w, (1, 32, 32, 32)), vol, (32, 32, 32), overlap_factor=0.5)
     d = np.abs(out - ref)
-    assert d.max() <= 0.03 and d.mean() <= 0.004, (d.max(), d.mean())
-    a, b = out > 0.5, ref > 0.5
-    assert (2.0 * (a & b).sum() + 1) / (a.sum() + b.sum() + 1) >= 0.999
+    # bf16 tolerance of tests/test_gpu_model.py (random decisive weights: logit std ~2.7, 1.5-3 % logit error)
+    assert d.max() <= 0.12 and d.mean() <= 0.006, (d.max(), d.mean())
+    soft = (2 * (out * ref).sum() + 1) / ((out * out).sum() + (ref * ref).sum() + 1)
+    assert soft >= 0.999, soft
 
 
 def test_sharded_partial_sums_add_up(native):

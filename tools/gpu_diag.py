@@ -17,7 +17,9 @@ from fetal_net import _lib
 ctx = _lib.get_context(0)
 kind, impl, ci = %(kind)r, %(impl)d, %(ci)d
 t0 = time.time()
-if kind == 'fprop': r = gc.conv_fprop_case(ctx, impl, gc.CONV_CASES[ci])
+if kind == 'mfprop': r = gc.conv_fprop_case(ctx, 2, gc.MARCH_CASES[ci])
+elif kind == 'mdgrad': r = gc.conv_dgrad_case(ctx, 2, gc.MARCH_CASES[ci])
+elif kind == 'fprop': r = gc.conv_fprop_case(ctx, impl, gc.CONV_CASES[ci])
 elif kind == 'dgrad': r = gc.conv_dgrad_case(ctx, impl, gc.CONV_CASES[ci])
 elif kind == 'wgrad': r = gc.conv_wgrad_case(ctx, impl, gc.CONV_CASES[ci])
 else: r = getattr(gc, kind + '_case')(ctx)
@@ -38,6 +40,10 @@ def main():
             jobs.append(("dgrad", 0, ci, "dgrad[tc] %s" % c[0]))
             jobs.append(("wgrad", 1, ci, "wgrad[simt] %s" % c[0]))
             jobs.append(("wgrad", 0, ci, "wgrad[tc] %s" % c[0]))
+    for ci, c in enumerate(gc.MARCH_CASES):
+        jobs.append(("mfprop", 2, ci, "fprop[march] %s" % c[0]))
+        if c[6] == 0:
+            jobs.append(("mdgrad", 2, ci, "dgrad[march] %s" % c[0]))
     only = sys.argv[1] if len(sys.argv) > 1 else None
     results = {}
     for kind, impl, ci, label in jobs:
