@@ -51,20 +51,6 @@ struct alignas(64) MarchParams {
   const bf16* mask;
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-struct Seg {
-  uint32_t col;   // TMEM column of the first block
-  uint32_t brow;  // first B row (multiple of Cn)
-  uint32_t nblk;
-  uint32_t fresh;
-};
-
 __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid_constant__ MarchParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -122,113 +108,125 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
     xb = min(p.X, xa + p.xchunk);
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== producer: resident weights once, then one slab per (plane, dz, source, chunk) =====
-      mbar_expect_tx(wfull_bar, p.w_bytes);
-      for (int s = 0; s < p.nsrc; ++s) {
-        const uint32_t tile = 3u * (uint32_t)p.Cn * (uint32_t)p.KC[s] * 2u;
-        for (int t = 0; t < p.nchunks[s] * 9; ++t)
-          tma_load_2d(w_base + p.wofs[s] + (uint32_t)t * tile, &p.tmW[s], wfull_bar, 0, t * 3 * p.Cn);
-      }
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, iy, iz, xa, xb;
-        decode(item, n, iy, iz, xa, xb);
-        const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
-        for (int xi = x_first; xi <= x_last; ++xi)
-          for (int dz = 0; dz < 3; ++dz)
-            for (int s = 0; s < p.nsrc; ++s)
-              for (int ch = 0; ch < p.nchunks[s]; ++ch, ++it) {
-                const uint32_t stage = it % (uint32_t)p.stages;
-                const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-                mbar_wait(empty_bar(stage), ph ^ 1u);
-                mbar_expect_tx(full_bar(stage), (uint32_t)kSlabRows * (uint32_t)p.KC[s] * 2u);
-                tma_load_5d(a_base + stage * kSlot, &p.tmA[s], full_bar(stage), ch * p.KC[s],
-                            iz * kBZ + dz - 1, iy * kBY - 1, xi, n);
-              }
-      }
+  // make the values the producer / MMA warps compute on provably warp-uniform
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+
+  if (warp_u == 0) {
+    // ===== producer warp (all lanes converged, one elected lane issues): resident weights once, then one
+    //       slab per (plane, dz, source, chunk) =====
+    mbar_expect_tx_elect(wfull_bar, p.w_bytes);
+    for (int s = 0; s < p.nsrc; ++s) {
+      const uint32_t tile = 3u * (uint32_t)p.Cn * (uint32_t)p.KC[s] * 2u;
+      for (int t = 0; t < p.nchunks[s] * 9; ++t)
+        tma_load_2d_elect(w_base + p.wofs[s] + (uint32_t)t * tile, &p.tmW[s], wfull_bar, 0, t * 3 * p.Cn);
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      uint32_t idesc[4];
-      for (int b = 1; b <= 3; ++b) idesc[b] = make_idesc(128, b * p.Cn, 0, 0);
-      mbar_wait(wfull_bar, 0);
-      tc_fence_after();
-      uint32_t it = 0, ocount = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, iy, iz, xa, xb;
-        decode(item, n, iy, iz, xa, xb);
-        const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
-        for (int xi = x_first; xi <= x_last; ++xi) {
-          const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes fed by plane xi
-          const int j_lo = lo - (xi - 1);
-          // a block is fresh when xi is the first input plane contributing to it
-          Seg first[3], rest[2];
-          int nfirst = 0, nrest = 0;
-          for (int xo = lo; xo <= hi; ++xo) {
-            const uint32_t seq = ocount + (uint32_t)(xo - xa);
-            const uint32_t rb = seq % (uint32_t)p.R;
-            const uint32_t fresh = (xi == x_first || xo == xi + 1) ? 1u : 0u;
-            if (fresh) {
-              mbar_wait(tempty_bar(rb), ((seq / (uint32_t)p.R) & 1u) ^ 1u);  // epilogue drained it
-            }
-            const uint32_t col = rb * (uint32_t)p.Cn;
-            const uint32_t brow = (uint32_t)(j_lo + (xo - lo)) * (uint32_t)p.Cn;
-            if (nfirst > 0 && first[nfirst - 1].fresh == fresh &&
-                first[nfirst - 1].col + first[nfirst - 1].nblk * (uint32_t)p.Cn == col) {
-              first[nfirst - 1].nblk++;
-            } else {
-              first[nfirst++] = Seg{col, brow, 1u, fresh};
-            }
-            if (nrest > 0 && rest[nrest - 1].col + rest[nrest - 1].nblk * (uint32_t)p.Cn == col) {
-              rest[nrest - 1].nblk++;
-            } else {
-              rest[nrest++] = Seg{col, brow, 1u, 0u};
+    uint32_t stage = 0, ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, iy, iz, xa, xb;
+      decode(item, n, iy, iz, xa, xb);
+      const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+      const int yc = iy * kBY - 1, zc = iz * kBZ - 1;
+      for (int xi = x_first; xi <= x_last; ++xi)
+        for (int dz = 0; dz < 3; ++dz)
+          for (int s = 0; s < p.nsrc; ++s) {
+            const uint32_t bytes = (uint32_t)kSlabRows * (uint32_t)p.KC[s] * 2u;
+            for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+              mbar_wait(empty_bar(stage), ph ^ 1u);
+              mbar_expect_tx_elect(full_bar(stage), bytes);
+              tma_load_5d_elect(a_base + stage * kSlot, &p.tmA[s], full_bar(stage), ch * p.KC[s], zc + dz, yc, xi, n);
+              if (++stage == (uint32_t)p.stages) {
+                stage = 0;
+                ph ^= 1u;
+              }
             }
           }
-          tc_fence_after();
-          bool first_mma = true;
-          for (int dz = 0; dz < 3; ++dz)
-            for (int s = 0; s < p.nsrc; ++s) {
-              const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
-              const uint32_t sbo = 8u * row_bytes;
-              const uint32_t lt = layout_code((int)row_bytes);
-              const uint32_t btile = 3u * (uint32_t)p.Cn * row_bytes;
-              const int nk = p.KC[s] >> 4;
-              for (int ch = 0; ch < p.nchunks[s]; ++ch, ++it) {
-                const uint32_t stage = it % (uint32_t)p.stages;
-                const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-                mbar_wait(full_bar(stage), ph);
-                tc_fence_after();
-                const uint32_t a_addr = a_base + stage * kSlot;
-                for (int dy = 0; dy < 3; ++dy) {
-                  const uint32_t b_addr = w_base + p.wofs[s] + (uint32_t)((ch * 3 + dz) * 3 + dy) * btile;
-                  for (int k = 0; k < nk; ++k) {
-                    const uint32_t a_k = a_addr + (uint32_t)dy * sbo + (uint32_t)k * 32u;
-                    const uint64_t ad = make_smem_desc(a_k, 16u, sbo, lt);
-                    const Seg* sg = first_mma ? first : rest;
-                    const int ns = first_mma ? nfirst : nrest;
-                    for (int q = 0; q < ns; ++q) {
-                      const uint64_t bd =
-                          make_smem_desc(b_addr + sg[q].brow * row_bytes + (uint32_t)k * 32u, 16u, sbo, lt);
-                      umma_bf16(tmem_base + sg[q].col, ad, bd, idesc[sg[q].nblk],
-                                (first_mma && sg[q].fresh) ? 0u : 1u);
+    }
+  } else if (warp_u == 1) {
+    // ===== MMA warp: converged loops on uniform values, tcgen05.mma / commit predicated on one lane =====
+    const uint32_t Cn = (uint32_t)p.Cn;
+    const uint32_t ring_mask = (uint32_t)p.R - 1u;  // R is a power of two
+    const uint32_t ring_shift = 31u - (uint32_t)__clz(p.R);
+    const uint32_t idesc1 = make_idesc(128, (int)Cn, 0, 0);
+    const uint32_t idesc2 = make_idesc(128, 2 * (int)Cn, 0, 0);
+    const uint32_t idesc3 = make_idesc(128, 3 * (int)Cn, 0, 0);
+    mbar_wait(wfull_bar, 0);
+    tc_fence_after();
+    uint32_t stage = 0, ph = 0, ocount = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, iy, iz, xa, xb;
+      decode(item, n, iy, iz, xa, xb);
+      const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+      for (int xi = x_first; xi <= x_last; ++xi) {
+        const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes fed by plane xi
+        const uint32_t j_lo = (uint32_t)(lo - (xi - 1));
+        const uint32_t nblk = (uint32_t)(hi - lo + 1);
+        const uint32_t seq_lo = ocount + (uint32_t)(lo - xa);
+        const uint32_t rb_lo = seq_lo & ring_mask;
+        // blocks first touched by this plane must have been drained by the epilogue
+        const bool all_fresh = (xi == x_first);
+        for (uint32_t j = 0; j < nblk; ++j) {
+          const bool fresh = all_fresh || (lo + (int)j == xi + 1);
+          if (fresh) {
+            const uint32_t seq = seq_lo + j;
+            mbar_wait(tempty_bar(seq & ring_mask), ((seq >> ring_shift) & 1u) ^ 1u);
+          }
+        }
+        tc_fence_after();
+        // steady-state segments: the <= 3 consecutive ring blocks, split only where the ring wraps
+        const uint32_t nA = min(nblk, (uint32_t)p.R - rb_lo), nB = nblk - nA;
+        const uint32_t colA = tmem_base + rb_lo * Cn, colB = tmem_base;
+        const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
+        const uint32_t idB = nB == 1 ? idesc1 : idesc2;
+        bool first_mma = true;
+        for (int dz = 0; dz < 3; ++dz)
+          for (int s = 0; s < p.nsrc; ++s) {
+            const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
+            const uint32_t sbo = 8u * row_bytes;
+            const uint32_t hi32 = desc_hi(sbo, layout_code((int)row_bytes));
+            const uint32_t btile16 = (3u * Cn * row_bytes) >> 4;  // B tile stride, 16-byte units
+            const uint32_t blk16 = (Cn * row_bytes) >> 4;         // one N block of B rows
+            const uint32_t dy16 = sbo >> 4;                       // one y row = 8 slab rows
+            const int nk = p.KC[s] >> 4;
+            const uint32_t b_lo0 = desc_lo(w_base + p.wofs[s], 16u) + (uint32_t)(dz * 3) * btile16 + j_lo * blk16;
+            for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+              mbar_wait(full_bar(stage), ph);
+              tc_fence_after();
+              uint32_t a_lo = desc_lo(a_base + stage * kSlot, 16u);
+              uint32_t b_lo = b_lo0 + (uint32_t)(ch * 9) * btile16;
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                for (int k = 0; k < nk; ++k) {
+                  const uint32_t ak = a_lo + 2u * (uint32_t)k, bk = b_lo + 2u * (uint32_t)k;
+                  if (first_mma) {
+                    // first K step of the plane: block by block, fresh blocks overwrite
+                    for (uint32_t j = 0; j < nblk; ++j) {
+                      const uint32_t seq = seq_lo + j;
+                      const bool fresh = all_fresh || (lo + (int)j == xi + 1);
+                      umma_bf16_lh_elect(tmem_base + (seq & ring_mask) * Cn, ak, hi32, bk + j * blk16, hi32, idesc1,
+                                         fresh ? 0u : 1u);
                     }
                     first_mma = false;
+                  } else {
+                    umma_bf16_lh_elect(colA, ak, hi32, bk, hi32, idA, 1u);
+                    if (nB) umma_bf16_lh_elect(colB, ak, hi32, bk + nA * blk16, hi32, idB, 1u);
                   }
                 }
-                umma_commit(empty_bar(stage));
+                a_lo += dy16;
+                b_lo += btile16;
+              }
+              umma_commit_elect(empty_bar(stage));
+              if (++stage == (uint32_t)p.stages) {
+                stage = 0;
+                ph ^= 1u;
               }
             }
-          // completed output planes
-          if (xi - 1 >= xa) umma_commit(tfull_bar((ocount + (uint32_t)(xi - 1 - xa)) % (uint32_t)p.R));
-          if (xi == x_last && xi <= xb - 1)
-            umma_commit(tfull_bar((ocount + (uint32_t)(xi - xa)) % (uint32_t)p.R));
-        }
-        ocount += (uint32_t)(xb - xa);
+          }
+        // completed output planes
+        if (xi - 1 >= xa) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - 1 - xa)) & ring_mask));
+        if (xi == x_last && xi <= xb - 1) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - xa)) & ring_mask));
       }
+      ocount += (uint32_t)(xb - xa);
     }
   } else {
     // ===== epilogue =====
@@ -242,8 +240,8 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
       const int y = iy * kBY + yl, z = iz * kBZ + zl;
       for (int xo = xa; xo < xb; ++xo) {
         const uint32_t seq = ocount + (uint32_t)(xo - xa);
-        const uint32_t rb = seq % (uint32_t)p.R;
-        mbar_wait(tfull_bar(rb), (seq / (uint32_t)p.R) & 1u);
+        const uint32_t rb = seq & ((uint32_t)p.R - 1u);
+        mbar_wait(tfull_bar(rb), (seq >> (31u - (uint32_t)__clz(p.R))) & 1u);
         tc_fence_after();
         const int64_t v = (((int64_t)n * p.X + xo) * p.Y + y) * p.Z + z;
         const int64_t off = v * p.out_C + p.out_cofs;
