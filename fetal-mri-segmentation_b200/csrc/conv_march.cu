@@ -26,7 +26,7 @@ using namespace tcp;
 
 namespace {
 
-constexpr int kThreadsM = 192;
+constexpr int kThreadsM = 256;  // warp 0 TMA, warps 1-3 MMA issue (one per dz slab copy), warps 4-7 epilogue
 constexpr int kBY = 16, kBZ = 8, kSlabRows = (kBY + 2) * kBZ;  // 144 rows per slab
 constexpr uint32_t kSlot = kSlabRows * 128;                    // 18432 B (1024-aligned)
 constexpr int kMaxRing = 16;
@@ -46,6 +46,7 @@ struct alignas(64) MarchParams {
   int out_C, out_cofs, relu;
   uint32_t w_bytes;   // bytes the weight TMA loads deliver (mbarrier expect_tx)
   uint32_t w_region;  // shared-memory bytes reserved for them (1024-aligned per source)
+  int debug;          // FETAL_B200_DEBUG ablation bits: 1 skip slab TMA, 2 skip MMAs, 4 skip epilogue body
   const float* bias;
   bf16* out;
   const bf16* mask;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
         mbar_init(empty_bar(s), 1);
       }
       for (int b = 0; b < p.R; ++b) {
-        mbar_init(tfull_bar(b), 1);
+        mbar_init(tfull_bar(b), 3);     // one tcgen05.commit per MMA warp
         mbar_init(tempty_bar(b), 128);
       }
       mbar_init(wfull_bar, 1);
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
     xb = min(p.X, xa + p.xchunk);
   };
 
+  const int dbg = p.debug;
   // make the values the producer / MMA warps compute on provably warp-uniform
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -121,29 +123,43 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
       for (int t = 0; t < p.nchunks[s] * 9; ++t)
         tma_load_2d_elect(w_base + p.wofs[s] + (uint32_t)t * tile, &p.tmW[s], wfull_bar, 0, t * 3 * p.Cn);
     }
-    uint32_t stage = 0, ph = 0;
+    // every dz slab copy has its own ring of S3 = stages/3 slots, consumed strictly in order by "its" MMA
+    // warp (a consumer that skipped slots of a shared ring could not tell mbarrier phases apart)
+    const uint32_t S3 = (uint32_t)p.stages / 3u;
+    uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int n, iy, iz, xa, xb;
       decode(item, n, iy, iz, xa, xb);
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       const int yc = iy * kBY - 1, zc = iz * kBZ - 1;
-      for (int xi = x_first; xi <= x_last; ++xi)
+      for (int xi = x_first; xi <= x_last; ++xi) {
+#pragma unroll
         for (int dz = 0; dz < 3; ++dz)
           for (int s = 0; s < p.nsrc; ++s) {
             const uint32_t bytes = (uint32_t)kSlabRows * (uint32_t)p.KC[s] * 2u;
             for (int ch = 0; ch < p.nchunks[s]; ++ch) {
-              mbar_wait(empty_bar(stage), ph ^ 1u);
-              mbar_expect_tx_elect(full_bar(stage), bytes);
-              tma_load_5d_elect(a_base + stage * kSlot, &p.tmA[s], full_bar(stage), ch * p.KC[s], zc + dz, yc, xi, n);
-              if (++stage == (uint32_t)p.stages) {
-                stage = 0;
-                ph ^= 1u;
+              const uint32_t stage = (uint32_t)dz * S3 + sidx[dz];
+              mbar_wait(empty_bar(stage), sph[dz] ^ 1u);
+              if (dbg & 1) {
+                mbar_expect_tx_elect(full_bar(stage), 0);
+              } else {
+                mbar_expect_tx_elect(full_bar(stage), bytes);
+                tma_load_5d_elect(a_base + stage * kSlot, &p.tmA[s], full_bar(stage), ch * p.KC[s], zc + dz, yc, xi, n);
+              }
+              if (++sidx[dz] == S3) {
+                sidx[dz] = 0;
+                sph[dz] ^= 1u;
               }
             }
           }
+      }
     }
-  } else if (warp_u == 1) {
-    // ===== MMA warp: converged loops on uniform values, tcgen05.mma / commit predicated on one lane =====
+  } else if (warp_u <= 3) {
+    // ===== MMA warps 1..3: warp w owns the slab copy dz = w - 1 of every input plane. A single lane cannot
+    // issue one 48-cycle MMA every 48 cycles (each issue is ~15 dependent uniform-datapath instructions),
+    // so the issue stream is split three ways. All MMAs accumulate (the epilogue hands accumulator blocks
+    // back zeroed), which makes the result independent of the interleaving of the three issue streams. =====
+    const int dz = warp_u - 1;
     const uint32_t Cn = (uint32_t)p.Cn;
     const uint32_t ring_mask = (uint32_t)p.R - 1u;  // R is a power of two
     const uint32_t ring_shift = 31u - (uint32_t)__clz(p.R);
@@ -152,7 +168,9 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
     const uint32_t idesc3 = make_idesc(128, 3 * (int)Cn, 0, 0);
     mbar_wait(wfull_bar, 0);
     tc_fence_after();
-    uint32_t stage = 0, ph = 0, ocount = 0;
+    // this warp's private ring of S3 slots
+    const uint32_t S3 = (uint32_t)p.stages / 3u, slot0 = (uint32_t)dz * S3;
+    uint32_t sidx = 0, ph = 0, ocount = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int n, iy, iz, xa, xb;
       decode(item, n, iy, iz, xa, xb);
@@ -163,66 +181,52 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
         const uint32_t nblk = (uint32_t)(hi - lo + 1);
         const uint32_t seq_lo = ocount + (uint32_t)(lo - xa);
         const uint32_t rb_lo = seq_lo & ring_mask;
-        // blocks first touched by this plane must have been drained by the epilogue
-        const bool all_fresh = (xi == x_first);
+        // blocks first touched by this plane must have been drained (and zeroed) by the epilogue
         for (uint32_t j = 0; j < nblk; ++j) {
-          const bool fresh = all_fresh || (lo + (int)j == xi + 1);
-          if (fresh) {
+          if (xi == x_first || lo + (int)j == xi + 1) {
             const uint32_t seq = seq_lo + j;
-            mbar_wait(tempty_bar(seq & ring_mask), ((seq >> ring_shift) & 1u) ^ 1u);
+            mbar_wait(tempty_bar(seq & ring_mask), (seq >> ring_shift) & 1u);
           }
         }
         tc_fence_after();
-        // steady-state segments: the <= 3 consecutive ring blocks, split only where the ring wraps
+        // the <= 3 consecutive ring blocks, split only where the ring wraps
         const uint32_t nA = min(nblk, (uint32_t)p.R - rb_lo), nB = nblk - nA;
         const uint32_t colA = tmem_base + rb_lo * Cn, colB = tmem_base;
         const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
         const uint32_t idB = nB == 1 ? idesc1 : idesc2;
-        bool first_mma = true;
-        for (int dz = 0; dz < 3; ++dz)
-          for (int s = 0; s < p.nsrc; ++s) {
-            const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
-            const uint32_t sbo = 8u * row_bytes;
-            const uint32_t hi32 = desc_hi(sbo, layout_code((int)row_bytes));
-            const uint32_t btile16 = (3u * Cn * row_bytes) >> 4;  // B tile stride, 16-byte units
-            const uint32_t blk16 = (Cn * row_bytes) >> 4;         // one N block of B rows
-            const uint32_t dy16 = sbo >> 4;                       // one y row = 8 slab rows
-            const int nk = p.KC[s] >> 4;
-            const uint32_t b_lo0 = desc_lo(w_base + p.wofs[s], 16u) + (uint32_t)(dz * 3) * btile16 + j_lo * blk16;
-            for (int ch = 0; ch < p.nchunks[s]; ++ch) {
-              mbar_wait(full_bar(stage), ph);
-              tc_fence_after();
-              uint32_t a_lo = desc_lo(a_base + stage * kSlot, 16u);
-              uint32_t b_lo = b_lo0 + (uint32_t)(ch * 9) * btile16;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
+          const uint32_t sbo = 8u * row_bytes;
+          const uint32_t hi32 = desc_hi(sbo, layout_code((int)row_bytes));
+          const uint32_t btile16 = (3u * Cn * row_bytes) >> 4;  // B tile stride, 16-byte units
+          const uint32_t blk16 = (Cn * row_bytes) >> 4;         // one N block of B rows
+          const uint32_t dy16 = sbo >> 4;                       // one y row = 8 slab rows
+          const int nk = p.KC[s] >> 4;
+          const uint32_t b_lo0 = desc_lo(w_base + p.wofs[s], 16u) + (uint32_t)(dz * 3) * btile16 + j_lo * blk16;
+          for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+            const uint32_t stage = slot0 + sidx;
+            mbar_wait(full_bar(stage), ph);
+            tc_fence_after();
+            uint32_t a_lo = desc_lo(a_base + stage * kSlot, 16u);
+            uint32_t b_lo = b_lo0 + (uint32_t)(ch * 9) * btile16;
 #pragma unroll
-              for (int dy = 0; dy < 3; ++dy) {
-                for (int k = 0; k < nk; ++k) {
-                  const uint32_t ak = a_lo + 2u * (uint32_t)k, bk = b_lo + 2u * (uint32_t)k;
-                  if (first_mma) {
-                    // first K step of the plane: block by block, fresh blocks overwrite
-                    for (uint32_t j = 0; j < nblk; ++j) {
-                      const uint32_t seq = seq_lo + j;
-                      const bool fresh = all_fresh || (lo + (int)j == xi + 1);
-                      umma_bf16_lh_elect(tmem_base + (seq & ring_mask) * Cn, ak, hi32, bk + j * blk16, hi32, idesc1,
-                                         fresh ? 0u : 1u);
-                    }
-                    first_mma = false;
-                  } else {
-                    umma_bf16_lh_elect(colA, ak, hi32, bk, hi32, idA, 1u);
-                    if (nB) umma_bf16_lh_elect(colB, ak, hi32, bk + nA * blk16, hi32, idB, 1u);
-                  }
-                }
-                a_lo += dy16;
-                b_lo += btile16;
+            for (int dy = 0; dy < 3; ++dy) {
+              for (int k = 0; k < nk; ++k) {
+                const uint32_t ak = a_lo + 2u * (uint32_t)k, bk = b_lo + 2u * (uint32_t)k;
+                umma_bf16_lh_elect(colA, ak, hi32, bk, hi32, idA, 1u);
+                if (nB) umma_bf16_lh_elect(colB, ak, hi32, bk + nA * blk16, hi32, idB, 1u);
               }
-              umma_commit_elect(empty_bar(stage));
-              if (++stage == (uint32_t)p.stages) {
-                stage = 0;
-                ph ^= 1u;
-              }
+              a_lo += dy16;
+              b_lo += btile16;
+            }
+            umma_commit_elect(empty_bar(stage));
+            if (++sidx == S3) {
+              sidx = 0;
+              ph ^= 1u;
             }
           }
-        // completed output planes
+        }
+        // output planes completed by this input plane (each MMA warp contributes one arrival)
         if (xi - 1 >= xa) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - 1 - xa)) & ring_mask));
         if (xi == x_last && xi <= xb - 1) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - xa)) & ring_mask));
       }
@@ -234,6 +238,14 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
     const int row = q * 32 + lane;
     const int yl = row >> 3, zl = row & 7;
     uint32_t ocount = 0;
+    // hand every accumulator block to the MMA warps zeroed (TMEM is not initialised by the allocation)
+    for (int b = 0; b < p.R; ++b) {
+      for (int c16 = 0; c16 < p.Cn / 16; ++c16)
+        tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.Cn + c16 * 16));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(tempty_bar(b));
+    }
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int n, iy, iz, xa, xb;
       decode(item, n, iy, iz, xa, xb);
@@ -246,10 +258,11 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
         const int64_t v = (((int64_t)n * p.X + xo) * p.Y + y) * p.Z + z;
         const int64_t off = v * p.out_C + p.out_cofs;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + rb * (uint32_t)p.Cn;
-        for (int c16 = 0; c16 < p.Cn / 16; ++c16) {
+        for (int c16 = 0; c16 < ((dbg & 4) ? 0 : p.Cn / 16); ++c16) {
           uint32_t r[16];
           tmem_ld16(taddr + (uint32_t)c16 * 16u, r);
           tmem_ld_wait();
+          tmem_st16_zero(taddr + (uint32_t)c16 * 16u);
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]);
@@ -290,6 +303,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
           op[0] = o[0];
           op[1] = o[1];
         }
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(tempty_bar(rb));
       }
@@ -455,11 +469,16 @@ int k_conv3d_march(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1,
       FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA, "cuTensorMapEncodeTiled(march weights) failed: %d", (int)r);
     }
   }
+  {
+    const char* e = getenv("FETAL_B200_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+  }
   p.w_bytes = wbytes;
   p.w_region = wofs;
   const uint32_t w_region = wofs;
   int stages = (kMaxDynSmemM - 2048 - (int)w_region) / (int)kSlot;
-  stages = std::max(3, std::min(stages, 8));
+  stages = std::min(stages, 9) / 3 * 3;  // three private rings (one per dz slab copy / MMA warp)
+  FM_CHECK(stages >= 3, FM_EINVAL, "conv3d march: filter bank leaves no room for the slab rings");
   p.stages = stages;
   const size_t smem = (size_t)w_region + (size_t)stages * kSlot + 1024 + 512;
   FM_CHECK(smem <= (size_t)kMaxDynSmemM, FM_EINVAL, "conv3d march: %zu B of shared memory needed", smem);

@@ -102,77 +102,76 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int pad = p.ksize >> 1;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        int m = tile / p.n_tiles;
-        const int iz = m % p.tz;
-        m /= p.tz;
-        const int iy = m % p.ty;
-        m /= p.ty;
-        const int ix = m % p.tx;
-        const int n = m / p.tx;
-        const int x0 = ix * p.bx, y0 = iy * p.by, z0 = iz * p.bz;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
-          for (int ch = 0; ch < p.nchunks[s]; ++ch) {
-            for (int tap = 0; tap < p.ntaps; ++tap, ++it) {
-              const uint32_t stage = it % (uint32_t)p.stages;
-              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-              mbar_wait(empty_bar(stage), ph ^ 1u);
-              mbar_expect_tx(full_bar(stage), tx_bytes);
-              const int dz = tap % p.ksize - pad;
-              const int dy = (tap / p.ksize) % p.ksize - pad;
-              const int dx = tap / (p.ksize * p.ksize) - pad;
-              const uint32_t a_dst = smem0 + stage * stage_bytes;
-              tma_load_5d(a_dst, &p.tmA[s], full_bar(stage), ch * p.KC[s], z0 + dz, y0 + dy, x0 + dx,
-                          n);
-              tma_load_3d(a_dst + kABytes, &p.tmW[s], full_bar(stage), p.wcofs[s] + ch * p.KC[s], tap,
-                          n_tile * p.block_n);
-            }
-          }
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+
+  if (warp_u == 0) {
+    // ===== TMA producer warp (converged; one elected lane issues) =====
+    uint32_t stage = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int iz = m % p.tz;
+      m /= p.tz;
+      const int iy = m % p.ty;
+      m /= p.ty;
+      const int ix = m % p.tx;
+      const int n = m / p.tx;
+      const int x0 = ix * p.bx - pad, y0 = iy * p.by - pad, z0 = iz * p.bz - pad;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
+        for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+          int tap = 0;
+          for (int kx = 0; kx < p.ksize; ++kx)
+            for (int ky = 0; ky < p.ksize; ++ky)
+              for (int kz = 0; kz < p.ksize; ++kz, ++tap) {
+                mbar_wait(empty_bar(stage), ph ^ 1u);
+                mbar_expect_tx_elect(full_bar(stage), tx_bytes);
+                const uint32_t a_dst = smem0 + stage * stage_bytes;
+                tma_load_5d_elect(a_dst, &p.tmA[s], full_bar(stage), ch * p.KC[s], z0 + kz, y0 + ky, x0 + kx, n);
+                tma_load_3d_elect(a_dst + kABytes, &p.tmW[s], full_bar(stage), p.wcofs[s] + ch * p.KC[s], tap,
+                                  n_tile * p.block_n);
+                if (++stage == (uint32_t)p.stages) {
+                  stage = 0;
+                  ph ^= 1u;
+                }
+              }
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (one thread) =====
-      const uint32_t idesc = make_idesc(kTileM, p.block_n, 0, 0);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
-          const uint32_t sbo = 8u * row_bytes;
-          const uint32_t lt = layout_code((int)row_bytes);
-          const int nk = p.KC[s] >> 4;
-          for (int ch = 0; ch < p.nchunks[s]; ++ch) {
-            for (int tap = 0; tap < p.ntaps; ++tap, ++it) {
-              const uint32_t stage = it % (uint32_t)p.stages;
-              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-              mbar_wait(full_bar(stage), ph);
-              tc_fence_after();
-              const uint32_t a_addr = smem0 + stage * stage_bytes;
-              const uint32_t b_addr = a_addr + kABytes;
-              for (int k = 0; k < nk; ++k) {
-                const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-                const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 32u, 16u, sbo, lt);
-                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-            }
+  } else if (warp_u == 1) {
+    // ===== MMA warp (converged; tcgen05.mma / commit predicated on one elected lane) =====
+    const uint32_t idesc = make_idesc(kTileM, p.block_n, 0, 0);
+    uint32_t stage = 0, ph = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.block_n;
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
+        const uint32_t hi32 = desc_hi(8u * row_bytes, layout_code((int)row_bytes));
+        const int nk = p.KC[s] >> 4;
+        const int nst = p.nchunks[s] * p.ntaps;
+        for (int i = 0; i < nst; ++i) {
+          mbar_wait(full_bar(stage), ph);
+          tc_fence_after();
+          const uint32_t a_lo = desc_lo(smem0 + stage * stage_bytes, 16u);
+          const uint32_t b_lo = a_lo + (kABytes >> 4);
+          for (int k = 0; k < nk; ++k) {
+            umma_bf16_lh_elect(d_tmem, a_lo + 2u * (uint32_t)k, hi32, b_lo + 2u * (uint32_t)k, hi32, idesc,
+                               accumulate);
+            accumulate = 1;
+          }
+          umma_commit_elect(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == (uint32_t)p.stages) {
+            stage = 0;
+            ph ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
       }
+      umma_commit_elect(tfull_bar(acc));  // accumulator complete -> epilogue
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bias/ReLU (fprop) or ReLU mask (dgrad) -> bf16 -> HBM =====
@@ -344,73 +343,78 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
   const uint32_t tap_tile_bytes = (uint32_t)kTileM * (uint32_t)p.KC * 2u;
   const uint32_t dy_sub_bytes = (uint32_t)kTileM * (uint32_t)p.NC * 2u;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0, vt = 0;
-      for (int mt = mt0; mt < mt1; ++mt, ++vt) {
-        int m = mt;
-        const int iz = m % p.tz;
-        m /= p.tz;
-        const int iy = m % p.ty;
-        m /= p.ty;
-        const int ix = m % p.tx;
-        const int n = m / p.tx;
-        const int x0 = ix * p.bx, y0 = iy * p.by, z0 = iz * p.bz;
-        const uint32_t b = vt & 1u, bph = (vt >> 1) & 1u;
-        mbar_wait(dyempty_bar(b), bph ^ 1u);
-        mbar_expect_tx(dyfull_bar(b), dy_bytes);
-        for (int j = 0; j < p.NB / p.NC; ++j)
-          tma_load_5d(dy0 + b * dy_bytes + (uint32_t)j * dy_sub_bytes, &p.tmDY, dyfull_bar(b),
-                      nb * p.NB + j * p.NC, z0, y0, x0, n);
-        for (int gi = 0; gi < g_count; ++gi, ++it) {
-          const uint32_t stage = it % (uint32_t)p.stages;
-          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-          mbar_wait(empty_bar(stage), ph ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)p.g * tap_tile_bytes);
-          for (int t = 0; t < p.g; ++t) {
-            const int tap = min((g_first + gi) * p.g + t, p.ntaps - 1);  // pad group with a repeat
-            const int dz = tap % p.ksize - pad;
-            const int dy = (tap / p.ksize) % p.ksize - pad;
-            const int dx = tap / (p.ksize * p.ksize) - pad;
-            tma_load_5d(smem0 + stage * a_slot + (uint32_t)t * tap_tile_bytes, &p.tmX, full_bar(stage),
-                        cc * p.KC, z0 + dz, y0 + dy, x0 + dx, n);
-          }
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+
+  if (warp_u == 0) {
+    // ===== TMA producer warp =====
+    uint32_t stage = 0, ph = 0, vt = 0;
+    for (int mt = mt0; mt < mt1; ++mt, ++vt) {
+      int m = mt;
+      const int iz = m % p.tz;
+      m /= p.tz;
+      const int iy = m % p.ty;
+      m /= p.ty;
+      const int ix = m % p.tx;
+      const int n = m / p.tx;
+      const int x0 = ix * p.bx, y0 = iy * p.by, z0 = iz * p.bz;
+      const uint32_t b = vt & 1u, bph = (vt >> 1) & 1u;
+      mbar_wait(dyempty_bar(b), bph ^ 1u);
+      mbar_expect_tx_elect(dyfull_bar(b), dy_bytes);
+      for (int j = 0; j < p.NB / p.NC; ++j)
+        tma_load_5d_elect(dy0 + b * dy_bytes + (uint32_t)j * dy_sub_bytes, &p.tmDY, dyfull_bar(b),
+                          nb * p.NB + j * p.NC, z0, y0, x0, n);
+      for (int gi = 0; gi < g_count; ++gi) {
+        mbar_wait(empty_bar(stage), ph ^ 1u);
+        mbar_expect_tx_elect(full_bar(stage), (uint32_t)p.g * tap_tile_bytes);
+        for (int t = 0; t < p.g; ++t) {
+          const int tap = min((g_first + gi) * p.g + t, p.ntaps - 1);  // pad group with a repeat
+          const int dz = tap % p.ksize - pad;
+          const int dy = (tap / p.ksize) % p.ksize - pad;
+          const int dx = tap / (p.ksize * p.ksize) - pad;
+          tma_load_5d_elect(smem0 + stage * a_slot + (uint32_t)t * tap_tile_bytes, &p.tmX, full_bar(stage),
+                            cc * p.KC, z0 + dz, y0 + dy, x0 + dx, n);
+        }
+        if (++stage == (uint32_t)p.stages) {
+          stage = 0;
+          ph ^= 1u;
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kTileM, p.NB, 1, 1);
-      const uint32_t a_row = (uint32_t)p.KC * 2u, b_row = (uint32_t)p.NC * 2u;
-      const uint32_t a_sbo = 8u * a_row, b_sbo = 8u * b_row;
-      const uint32_t a_lt = layout_code((int)a_row), b_lt = layout_code((int)b_row);
-      uint32_t it = 0, vt = 0;
-      for (int mt = mt0; mt < mt1; ++mt, ++vt) {
-        const uint32_t b = vt & 1u, bph = (vt >> 1) & 1u;
-        mbar_wait(dyfull_bar(b), bph);
+  } else if (warp_u == 1) {
+    // ===== MMA warp =====
+    const uint32_t idesc = make_idesc(kTileM, p.NB, 1, 1);
+    const uint32_t a_row = (uint32_t)p.KC * 2u, b_row = (uint32_t)p.NC * 2u;
+    const uint32_t a_sbo = 8u * a_row, b_sbo = 8u * b_row;
+    const uint32_t a_hi = desc_hi(a_sbo, layout_code((int)a_row)), b_hi = desc_hi(b_sbo, layout_code((int)b_row));
+    const uint32_t a_step = (2u * a_sbo) >> 4, b_step = (2u * b_sbo) >> 4;  // 16 voxels per MMA
+    uint32_t stage = 0, ph = 0, vt = 0;
+    for (int mt = mt0; mt < mt1; ++mt, ++vt) {
+      const uint32_t b = vt & 1u, bph = (vt >> 1) & 1u;
+      mbar_wait(dyfull_bar(b), bph);
+      tc_fence_after();
+      const uint32_t b_lo0 = desc_lo(dy0 + b * dy_bytes, dy_sub_bytes);
+      for (int gi = 0; gi < g_count; ++gi) {
+        mbar_wait(full_bar(stage), ph);
         tc_fence_after();
-        const uint32_t b_addr = dy0 + b * dy_bytes;
-        for (int gi = 0; gi < g_count; ++gi, ++it) {
-          const uint32_t stage = it % (uint32_t)p.stages;
-          const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-          mbar_wait(full_bar(stage), ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem0 + stage * a_slot;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.NB);
-#pragma unroll 1
-          for (int ks = 0; ks < kTileM / 16; ++ks) {  // 16 voxels (two 8-row k groups) per MMA
-            const uint64_t ad =
-                make_smem_desc(a_addr + (uint32_t)ks * 2u * a_sbo, tap_tile_bytes, a_sbo, a_lt);
-            const uint64_t bd =
-                make_smem_desc(b_addr + (uint32_t)ks * 2u * b_sbo, dy_sub_bytes, b_sbo, b_lt);
-            umma_bf16(d_tmem, ad, bd, idesc, (vt > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));
+        uint32_t a_lo = desc_lo(smem0 + stage * a_slot, tap_tile_bytes);
+        uint32_t b_lo = b_lo0;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.NB);
+#pragma unroll
+        for (int ks = 0; ks < kTileM / 16; ++ks) {
+          umma_bf16_lh_elect(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, (vt > 0 || ks > 0) ? 1u : 0u);
+          a_lo += a_step;
+          b_lo += b_step;
         }
-        umma_commit(dyempty_bar(b));
+        umma_commit_elect(empty_bar(stage));
+        if (++stage == (uint32_t)p.stages) {
+          stage = 0;
+          ph ^= 1u;
+        }
       }
-      umma_commit(done_bar);
+      umma_commit_elect(dyempty_bar(b));
     }
+    umma_commit_elect(done_bar);
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;     // (tap within group, channel within chunk)

@@ -25,10 +25,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // Bounded wait: a pipeline bug must surface as a trap (clean CUDA error), never as a hung GPU.
+// try_wait suspends the thread for a hardware-bounded interval per probe; 2^22 failed probes is seconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
+  uint32_t done, spins = 0;
+  do {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -38,13 +38,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("fetalb200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
+    if (!done && ++spins > (1u << 22)) __trap();
+  } while (!done);
 }
 __device__ __forceinline__ void prefetch_tmap(const void* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -207,6 +202,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
         "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// zero 16 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
