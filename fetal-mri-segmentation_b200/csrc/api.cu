@@ -585,7 +585,9 @@ static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x
   const int cs[2] = {l.c1, l.c2};
   int cofs = 0;
   for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
-    if (conv_tc_supported(cs[s], 0, l.cout, l.k))
+    if (use_march() && conv_wgrad_march_supported(d.X, d.Y, d.Z, cs[s], l.cout, l.k))
+      FM_TRY(k_conv3d_wgrad_march(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout));
+    else if (conv_tc_supported(cs[s], 0, l.cout, l.k))
       FM_TRY(k_conv3d_tc_wgrad(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout, l.k));
     else
       FM_TRY(k_conv3d_simt_wgrad(ctx, xs[s], 0, dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout,
@@ -1145,7 +1147,9 @@ extern "C" int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const f
   FM_TRY(s.alloc(&db, Cout));
   FM_TRY(k_zero(ctx, dw, wn * 4));
   FM_TRY(k_zero(ctx, db, (size_t)Cout * 4));
-  if (impl == 0)
+  if (impl == 2)
+    FM_TRY(k_conv3d_wgrad_march(ctx, dx, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout));
+  else if (impl == 0)
     FM_TRY(k_conv3d_tc_wgrad(ctx, dx, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, ksize));
   else
     FM_TRY(k_conv3d_simt_wgrad(ctx, dx, 0, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, ksize));

@@ -41,7 +41,8 @@ struct alignas(64) MarchParams {
   int N, X, Y, Z;
   int ny, nz, nxc, xchunk, items;
   int Cn;  // output channels (MMA N of one accumulator block)
-  int R;   // accumulator ring blocks
+  int R;   // accumulator ring blocks per set
+  int nissue;  // MMA-issuing warps (1 or 3) == accumulator sets (one per issuing warp, summed by the epilogue)
   int stages;
   int out_C, out_cofs, relu;
   uint32_t w_bytes;   // bytes the weight TMA loads deliver (mbarrier expect_tx)
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
   const uint32_t tmem_slot = wfull_bar + 8u;
 
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(p.R * p.Cn)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(p.R * p.Cn * p.nissue)) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
         mbar_init(empty_bar(s), 1);
       }
       for (int b = 0; b < p.R; ++b) {
-        mbar_init(tfull_bar(b), 3);     // one tcgen05.commit per MMA warp
+        mbar_init(tfull_bar(b), (uint32_t)p.nissue);  // one tcgen05.commit per MMA-issuing warp
         mbar_init(tempty_bar(b), 128);
       }
       mbar_init(wfull_bar, 1);
@@ -155,82 +156,105 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
       }
     }
   } else if (warp_u <= 3) {
-    // ===== MMA warps 1..3: warp w owns the slab copy dz = w - 1 of every input plane. A single lane cannot
-    // issue one 48-cycle MMA every 48 cycles (each issue is ~15 dependent uniform-datapath instructions),
-    // so the issue stream is split three ways. All MMAs accumulate (the epilogue hands accumulator blocks
-    // back zeroed), which makes the result independent of the interleaving of the three issue streams. =====
-    const int dz = warp_u - 1;
-    const uint32_t Cn = (uint32_t)p.Cn;
-    const uint32_t ring_mask = (uint32_t)p.R - 1u;  // R is a power of two
-    const uint32_t ring_shift = 31u - (uint32_t)__clz(p.R);
-    const uint32_t idesc1 = make_idesc(128, (int)Cn, 0, 0);
-    const uint32_t idesc2 = make_idesc(128, 2 * (int)Cn, 0, 0);
-    const uint32_t idesc3 = make_idesc(128, 3 * (int)Cn, 0, 0);
-    mbar_wait(wfull_bar, 0);
-    tc_fence_after();
-    // this warp's private ring of S3 slots
-    const uint32_t S3 = (uint32_t)p.stages / 3u, slot0 = (uint32_t)dz * S3;
-    uint32_t sidx = 0, ph = 0, ocount = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      int n, iy, iz, xa, xb;
-      decode(item, n, iy, iz, xa, xb);
-      const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
-      for (int xi = x_first; xi <= x_last; ++xi) {
-        const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes fed by plane xi
-        const uint32_t j_lo = (uint32_t)(lo - (xi - 1));
-        const uint32_t nblk = (uint32_t)(hi - lo + 1);
-        const uint32_t seq_lo = ocount + (uint32_t)(lo - xa);
-        const uint32_t rb_lo = seq_lo & ring_mask;
-        // blocks first touched by this plane must have been drained (and zeroed) by the epilogue
-        for (uint32_t j = 0; j < nblk; ++j) {
-          if (xi == x_first || lo + (int)j == xi + 1) {
-            const uint32_t seq = seq_lo + j;
-            mbar_wait(tempty_bar(seq & ring_mask), (seq >> ring_shift) & 1u);
+    // ===== MMA warps. A single lane cannot issue one 48-cycle (N = 96) MMA every 48 cycles - each issue is
+    // ~15 dependent uniform-datapath instructions - so for Cout <= 32 the issue stream is split three ways:
+    // warp w owns the slab copy dz = w - 1 of every input plane and accumulates into its OWN set of TMEM
+    // accumulator blocks; the epilogue adds the three sets in a fixed order, which keeps the result
+    // bit-reproducible (a shared accumulator would depend on how the three streams interleave).
+    // For Cout = 64 (96-cycle MMAs) one issuing warp keeps up and walks dz = 0,1,2 itself. =====
+    const int mw = warp_u - 1;
+    if (mw < p.nissue) {
+      const int dz_lo = (p.nissue == 3) ? mw : 0, dz_hi = (p.nissue == 3) ? mw + 1 : 3;
+      const uint32_t Cn = (uint32_t)p.Cn;
+      const uint32_t ring_mask = (uint32_t)p.R - 1u;  // R is a power of two
+      const uint32_t ring_shift = 31u - (uint32_t)__clz(p.R);
+      const uint32_t idesc1 = make_idesc(128, (int)Cn, 0, 0);
+      const uint32_t idesc2 = make_idesc(128, 2 * (int)Cn, 0, 0);
+      const uint32_t idesc3 = make_idesc(128, 3 * (int)Cn, 0, 0);
+      const uint32_t set_base = tmem_base + (uint32_t)((p.nissue == 3) ? mw : 0) * (uint32_t)p.R * Cn;
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      const uint32_t S3 = (uint32_t)p.stages / 3u;
+      uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
+      uint32_t ocount = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int n, iy, iz, xa, xb;
+        decode(item, n, iy, iz, xa, xb);
+        const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+        for (int xi = x_first; xi <= x_last; ++xi) {
+          const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes fed by plane xi
+          const uint32_t j_lo = (uint32_t)(lo - (xi - 1));
+          const uint32_t nblk = (uint32_t)(hi - lo + 1);
+          const uint32_t seq_lo = ocount + (uint32_t)(lo - xa);
+          const uint32_t rb_lo = seq_lo & ring_mask;
+          const bool all_fresh = (xi == x_first);
+          // blocks first touched by this plane must have been drained by the epilogue
+          for (uint32_t j = 0; j < nblk; ++j) {
+            if (all_fresh || lo + (int)j == xi + 1) {
+              const uint32_t seq = seq_lo + j;
+              mbar_wait(tempty_bar(seq & ring_mask), ((seq >> ring_shift) & 1u) ^ 1u);
+            }
           }
-        }
-        tc_fence_after();
-        // the <= 3 consecutive ring blocks, split only where the ring wraps
-        const uint32_t nA = min(nblk, (uint32_t)p.R - rb_lo), nB = nblk - nA;
-        const uint32_t colA = tmem_base + rb_lo * Cn, colB = tmem_base;
-        const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
-        const uint32_t idB = nB == 1 ? idesc1 : idesc2;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
-          const uint32_t sbo = 8u * row_bytes;
-          const uint32_t hi32 = desc_hi(sbo, layout_code((int)row_bytes));
-          const uint32_t btile16 = (3u * Cn * row_bytes) >> 4;  // B tile stride, 16-byte units
-          const uint32_t blk16 = (Cn * row_bytes) >> 4;         // one N block of B rows
-          const uint32_t dy16 = sbo >> 4;                       // one y row = 8 slab rows
-          const int nk = p.KC[s] >> 4;
-          const uint32_t b_lo0 = desc_lo(w_base + p.wofs[s], 16u) + (uint32_t)(dz * 3) * btile16 + j_lo * blk16;
-          for (int ch = 0; ch < p.nchunks[s]; ++ch) {
-            const uint32_t stage = slot0 + sidx;
-            mbar_wait(full_bar(stage), ph);
-            tc_fence_after();
-            uint32_t a_lo = desc_lo(a_base + stage * kSlot, 16u);
-            uint32_t b_lo = b_lo0 + (uint32_t)(ch * 9) * btile16;
+          tc_fence_after();
+          // steady state: the <= 3 consecutive ring blocks, split only where the ring wraps
+          const uint32_t nA = min(nblk, (uint32_t)p.R - rb_lo), nB = nblk - nA;
+          const uint32_t colA = set_base + rb_lo * Cn, colB = set_base;
+          const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
+          const uint32_t idB = nB == 1 ? idesc1 : idesc2;
+          bool first_mma = true;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              for (int k = 0; k < nk; ++k) {
-                const uint32_t ak = a_lo + 2u * (uint32_t)k, bk = b_lo + 2u * (uint32_t)k;
-                umma_bf16_lh_elect(colA, ak, hi32, bk, hi32, idA, 1u);
-                if (nB) umma_bf16_lh_elect(colB, ak, hi32, bk + nA * blk16, hi32, idB, 1u);
+          for (int dz = 0; dz < 3; ++dz) {
+            if (dz < dz_lo || dz >= dz_hi) continue;
+            for (int s = 0; s < p.nsrc; ++s) {
+              const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
+              const uint32_t sbo = 8u * row_bytes;
+              const uint32_t hi32 = desc_hi(sbo, layout_code((int)row_bytes));
+              const uint32_t btile16 = (3u * Cn * row_bytes) >> 4;  // B tile stride, 16-byte units
+              const uint32_t blk16 = (Cn * row_bytes) >> 4;         // one N block of B rows
+              const uint32_t dy16 = sbo >> 4;                       // one y row = 8 slab rows
+              const int nk = p.KC[s] >> 4;
+              const uint32_t b_lo0 = desc_lo(w_base + p.wofs[s], 16u) + (uint32_t)(dz * 3) * btile16 + j_lo * blk16;
+              for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+                const uint32_t stage = (uint32_t)dz * S3 + sidx[dz];
+                mbar_wait(full_bar(stage), sph[dz]);
+                tc_fence_after();
+                uint32_t a_lo = desc_lo(a_base + stage * kSlot, 16u);
+                uint32_t b_lo = b_lo0 + (uint32_t)(ch * 9) * btile16;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                  for (int k = 0; k < nk; ++k) {
+                    const uint32_t ak = a_lo + 2u * (uint32_t)k, bk = b_lo + 2u * (uint32_t)k;
+                    if (first_mma) {
+                      // first K step of this warp in the plane: block by block, fresh blocks overwrite
+                      for (uint32_t j = 0; j < nblk; ++j) {
+                        const uint32_t seq = seq_lo + j;
+                        const bool fresh = all_fresh || (lo + (int)j == xi + 1);
+                        umma_bf16_lh_elect(set_base + (seq & ring_mask) * Cn, ak, hi32, bk + j * blk16, hi32, idesc1,
+                                           fresh ? 0u : 1u);
+                      }
+                      first_mma = false;
+                    } else {
+                      umma_bf16_lh_elect(colA, ak, hi32, bk, hi32, idA, 1u);
+                      if (nB) umma_bf16_lh_elect(colB, ak, hi32, bk + nA * blk16, hi32, idB, 1u);
+                    }
+                  }
+                  a_lo += dy16;
+                  b_lo += btile16;
+                }
+                umma_commit_elect(empty_bar(stage));
+                if (++sidx[dz] == S3) {
+                  sidx[dz] = 0;
+                  sph[dz] ^= 1u;
+                }
               }
-              a_lo += dy16;
-              b_lo += btile16;
-            }
-            umma_commit_elect(empty_bar(stage));
-            if (++sidx == S3) {
-              sidx = 0;
-              ph ^= 1u;
             }
           }
+          // output planes completed by this input plane (each issuing warp contributes one arrival)
+          if (xi - 1 >= xa) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - 1 - xa)) & ring_mask));
+          if (xi == x_last && xi <= xb - 1) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - xa)) & ring_mask));
         }
-        // output planes completed by this input plane (each MMA warp contributes one arrival)
-        if (xi - 1 >= xa) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - 1 - xa)) & ring_mask));
-        if (xi == x_last && xi <= xb - 1) umma_commit_elect(tfull_bar((ocount + (uint32_t)(xi - xa)) & ring_mask));
+        ocount += (uint32_t)(xb - xa);
       }
-      ocount += (uint32_t)(xb - xa);
     }
   } else {
     // ===== epilogue =====
@@ -238,14 +262,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
     const int row = q * 32 + lane;
     const int yl = row >> 3, zl = row & 7;
     uint32_t ocount = 0;
-    // hand every accumulator block to the MMA warps zeroed (TMEM is not initialised by the allocation)
-    for (int b = 0; b < p.R; ++b) {
-      for (int c16 = 0; c16 < p.Cn / 16; ++c16)
-        tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * p.Cn + c16 * 16));
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(tempty_bar(b));
-    }
+    const uint32_t set_stride = (uint32_t)p.R * (uint32_t)p.Cn;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       int n, iy, iz, xa, xb;
       decode(item, n, iy, iz, xa, xb);
@@ -259,13 +276,24 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
         const int64_t off = v * p.out_C + p.out_cofs;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + rb * (uint32_t)p.Cn;
         for (int c16 = 0; c16 < ((dbg & 4) ? 0 : p.Cn / 16); ++c16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)c16 * 16u, r);
-          tmem_ld_wait();
-          tmem_st16_zero(taddr + (uint32_t)c16 * 16u);
           float f[16];
+          if (p.nissue == 3) {
+            // three issue streams -> three partial sums: issue all TMEM loads, wait once, add in fixed order
+            uint32_t r0[16], r1[16], r2[16];
+            tmem_ld16(taddr + (uint32_t)c16 * 16u, r0);
+            tmem_ld16(taddr + set_stride + (uint32_t)c16 * 16u, r1);
+            tmem_ld16(taddr + 2u * set_stride + (uint32_t)c16 * 16u, r2);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j)
+              f[j] = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) + __uint_as_float(r2[j]);
+          } else {
+            uint32_t r0[16];
+            tmem_ld16(taddr + (uint32_t)c16 * 16u, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r0[j]);
+          }
           if (p.bias != nullptr) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + c16 * 16);
 #pragma unroll
@@ -303,7 +331,6 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
           op[0] = o[0];
           op[1] = o[1];
         }
-        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(tempty_bar(rb));
       }
@@ -408,7 +435,13 @@ int k_conv3d_march(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1,
   p.ny = Y / kBY;
   p.nz = Z / kBZ;
   p.Cn = Cout;
-  p.R = std::min(kMaxRing, 512 / Cout);
+  p.nissue = Cout <= 32 ? 3 : 1;
+  {
+    int r = 512 / (Cout * p.nissue);  // blocks per accumulator set, rounded down to a power of two
+    int r2 = 1;
+    while (r2 * 2 <= r) r2 *= 2;
+    p.R = std::min(kMaxRing, r2);
+  }
   p.out_C = out_C;
   p.out_cofs = out_cofs;
   p.relu = relu;

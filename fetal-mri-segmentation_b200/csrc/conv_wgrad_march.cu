@@ -1,0 +1,326 @@
+// conv_wgrad_march.cu — plane-marching weight gradient of Conv3D 3x3x3 on tcgen05:
+//
+//     dW[kx,ky,kz][ci][co] = sum_v  X[v + (kx-1, ky-1, kz-1)][ci] * dY[v][co]
+//
+// GEMM view per CTA: M = (ky, ci) stacked to 128 rows, N = (kx, co) stacked to 96 columns, K = voxels.
+// Both operands are MN-major (channels are contiguous in memory, voxels are the K axis).
+//   * A CTA owns a 16 (y) x 8 (z) column of the volume and marches along x, exactly like the forward
+//     marching kernel (conv_march.cu): per input plane it loads three z-shifted, y-haloed slabs of X
+//     (19 x 8 rows x 32 channels) and one dY tile per output plane (128 rows x 32 channels).
+//   * the three ky taps are the M-blocks of ONE UMMA A operand: block j starts 8 slab rows (= one swizzle
+//     atom) after block j-1, which is expressed by the descriptor's leading-byte-offset == stride-byte-offset.
+//     (M = 128 holds four 32-channel blocks; the fourth reads one more halo row and is discarded.)
+//   * the three kx taps are the N-blocks of the B operand: the dY tiles of output planes xi-1, xi, xi+1 sit
+//     in consecutive slots of a ring, leading-byte-offset = slot size.
+//   * kz selects the slab copy; each copy has its own MMA-issuing warp and its own TMEM accumulator, which
+//     stays resident for the CTA's whole lifetime (persistent CTA over many columns) and is flushed with
+//     fp32 red.add once at the end.
+// One CTA handles one (32 input channels x 32 output channels) pair; pairs are spread over the grid.
+// TF autodiff gradient of Conv3D in create_convolution_block (fetal_net/model/unet3d/unet.py:102).
+#include <algorithm>
+
+#include "tc_ptx.cuh"
+
+using namespace tcp;
+
+namespace {
+
+constexpr int kThreadsW = 256;  // warp 0 TMA, warps 1-3 MMA issue (kz = 0,1,2), warps 4-7 epilogue
+constexpr int kBY = 16, kBZ = 8;
+constexpr int kCC = 32;                                   // channels per operand block (64 B rows, SWIZZLE_64B)
+constexpr uint32_t kRow = kCC * 2;                        // 64 B
+constexpr uint32_t kSbo = 8 * kRow;                       // 512 B: one y row of 8 voxels = one swizzle atom
+constexpr uint32_t kXSlabRows = (kBY + 3) * kBZ;          // 19 y rows: 16 + halo + the discarded 4th block
+constexpr uint32_t kXSlot = 10240;                        // 9728 B rounded up to 1 KB
+constexpr uint32_t kDyTile = kBY * kBZ * kRow;            // 8192 B
+constexpr int kDyRing = 8;
+constexpr int kNcols = 96;                                // (kx, co) columns per accumulator
+
+struct alignas(64) WgMarchParams {
+  CUtensorMap tmX;   // box (32, 8, 19, 1, 1)
+  CUtensorMap tmDY;  // box (32, 8, 16, 1, 1)
+  int N, X, Y, Z;
+  int ny, nz, nxc, xchunk, items;
+  int n_ci, n_co;      // 32-channel chunks of Cin (this source) and Cout
+  int ctas_per_pair;   // grid = n_ci * n_co * ctas_per_pair
+  int S3;              // X slab slots per kz ring
+  int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
+  float* dw;
+};
+
+__global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const __grid_constant__ WgMarchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t x_base = smem0;                                        // 3 * S3 slab slots
+  const uint32_t dy_base = x_base + 3u * (uint32_t)p.S3 * kXSlot;        // kDyRing tiles
+  const uint32_t bar0 = dy_base + (uint32_t)kDyRing * kDyTile;
+  const int nx = 3 * p.S3;
+  auto xfull_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto xempty_bar = [&](uint32_t s) { return bar0 + 8u * ((uint32_t)nx + s); };
+  auto dyfull_bar = [&](uint32_t s) { return bar0 + 8u * ((uint32_t)(2 * nx) + s); };
+  auto dyempty_bar = [&](uint32_t s) { return bar0 + 8u * ((uint32_t)(2 * nx + kDyRing) + s); };
+  const uint32_t zero_bar = bar0 + 8u * (uint32_t)(2 * nx + 2 * kDyRing);
+  const uint32_t done_bar = zero_bar + 8u;
+  const uint32_t tmem_slot = done_bar + 8u;
+  constexpr uint32_t tmem_cols = 512;  // 3 accumulators x 96 columns, power of two
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmX);
+    prefetch_tmap(&p.tmDY);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < nx; ++s) {
+        mbar_init(xfull_bar(s), 1);
+        mbar_init(xempty_bar(s), 1);
+      }
+      for (int s = 0; s < kDyRing; ++s) {
+        mbar_init(dyfull_bar(s), 1);
+        mbar_init(dyempty_bar(s), 3);
+      }
+      mbar_init(zero_bar, 128);
+      mbar_init(done_bar, 3);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+
+  // this CTA's (ci chunk, co chunk) pair and its share of the columns
+  const int pair = blockIdx.x / p.ctas_per_pair;
+  const int rank = blockIdx.x % p.ctas_per_pair;
+  const int cic = pair % p.n_ci, coc = pair / p.n_ci;
+
+  auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) {
+    const int jx = item % p.nxc;
+    int t = item / p.nxc;
+    iz = t % p.nz;
+    t /= p.nz;
+    iy = t % p.ny;
+    n = t / p.ny;
+    xa = jx * p.xchunk;
+    xb = min(p.X, xa + p.xchunk);
+  };
+
+  if (warp_u == 0) {
+    // ===== TMA producer =====
+    uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
+    uint32_t dcount = 0;  // dY tiles issued so far (ring position)
+    for (int item = rank; item < p.items; item += p.ctas_per_pair) {
+      int n, iy, iz, xa, xb;
+      decode(item, n, iy, iz, xa, xb);
+      const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+      int next_dy = xa;  // next output plane whose dY tile has to be loaded
+      for (int xi = x_first; xi <= x_last; ++xi) {
+        const int need = min(xi + 1, xb - 1);  // dY tiles up to this output plane feed input plane xi
+        for (; next_dy <= need; ++next_dy, ++dcount) {
+          const uint32_t slot = dcount & (uint32_t)(kDyRing - 1);
+          mbar_wait(dyempty_bar(slot), ((dcount >> 3) & 1u) ^ 1u);
+          mbar_expect_tx_elect(dyfull_bar(slot), kDyTile);
+          tma_load_5d_elect(dy_base + slot * kDyTile, &p.tmDY, dyfull_bar(slot), coc * kCC, iz * kBZ, iy * kBY, next_dy, n);
+        }
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+          const uint32_t stage = (uint32_t)dz * (uint32_t)p.S3 + sidx[dz];
+          mbar_wait(xempty_bar(stage), sph[dz] ^ 1u);
+          mbar_expect_tx_elect(xfull_bar(stage), kXSlabRows * kRow);
+          tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * kCC, iz * kBZ + dz - 1, iy * kBY - 1,
+                            xi, n);
+          if (++sidx[dz] == (uint32_t)p.S3) {
+            sidx[dz] = 0;
+            sph[dz] ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_u <= 3) {
+    // ===== MMA warps: warp w issues the kz = w - 1 slab copy into its own accumulator =====
+    const int dz = warp_u - 1;
+    const uint32_t d_acc = tmem_base + (uint32_t)(dz * kNcols);
+    const uint32_t idesc1 = make_idesc(128, kCC, 1, 1), idesc2 = make_idesc(128, 2 * kCC, 1, 1),
+                   idesc3 = make_idesc(128, 3 * kCC, 1, 1);
+    const uint32_t hi32 = desc_hi(kSbo, layout_code((int)kRow));
+    const uint32_t kstep = (2u * kSbo) >> 4;  // 16 voxels (two 8-row groups) per MMA, in 16-byte units
+    mbar_wait(zero_bar, 0);                   // accumulators zeroed by the epilogue warps
+    tc_fence_after();
+    uint32_t sidx = 0, sph = 0, dcount = 0, dwaited = 0;
+    const uint32_t slot0 = (uint32_t)dz * (uint32_t)p.S3;
+    for (int item = rank; item < p.items; item += p.ctas_per_pair) {
+      int n, iy, iz, xa, xb;
+      decode(item, n, iy, iz, xa, xb);
+      const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+      for (int xi = x_first; xi <= x_last; ++xi) {
+        const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes paired with input plane xi
+        const uint32_t j_lo = (uint32_t)(lo - (xi - 1));           // N block j <-> xo = xi - 1 + j <-> kx = 2 - j
+        const uint32_t nblk = (uint32_t)(hi - lo + 1);
+        const uint32_t seq_lo = dcount + (uint32_t)(lo - xa);      // ring sequence number of dY(lo)
+        // wait (once per tile and warp) for the dY tiles up to output plane hi
+        const uint32_t seq_need = dcount + (uint32_t)(hi - xa);
+        for (; dwaited <= seq_need; ++dwaited)
+          mbar_wait(dyfull_bar(dwaited & (uint32_t)(kDyRing - 1)), (dwaited >> 3) & 1u);
+        const uint32_t stage = slot0 + sidx;
+        mbar_wait(xfull_bar(stage), sph);
+        tc_fence_after();
+        const uint32_t rs = seq_lo & (uint32_t)(kDyRing - 1);
+        const uint32_t nA = min(nblk, (uint32_t)kDyRing - rs), nB = nblk - nA;
+        const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
+        const uint32_t idB = nB == 1 ? idesc1 : idesc2;
+        uint32_t a_lo = desc_lo(x_base + stage * kXSlot, kSbo);           // M blocks (ky) one atom apart
+        uint32_t bA = desc_lo(dy_base + rs * kDyTile, kDyTile);           // N blocks (kx) one ring slot apart
+        uint32_t bB = desc_lo(dy_base, kDyTile);
+        const uint32_t dA = d_acc + j_lo * kCC, dB = dA + nA * kCC;
+#pragma unroll
+        for (int ks = 0; ks < (kBY * kBZ) / 16; ++ks) {
+          umma_bf16_lh_elect(dA, a_lo, hi32, bA, hi32, idA, 1u);
+          if (nB) umma_bf16_lh_elect(dB, a_lo, hi32, bB, hi32, idB, 1u);
+          a_lo += kstep;
+          bA += kstep;
+          bB += kstep;
+        }
+        umma_commit_elect(xempty_bar(stage));
+        if (++sidx == (uint32_t)p.S3) {
+          sidx = 0;
+          sph ^= 1u;
+        }
+        // dY tiles this warp is done with: output plane xi-1 always, and the rest at the end of the item
+        if (xi - 1 >= xa) umma_commit_elect(dyempty_bar((dcount + (uint32_t)(xi - 1 - xa)) & (uint32_t)(kDyRing - 1)));
+        if (xi == x_last && xi <= xb - 1)
+          umma_commit_elect(dyempty_bar((dcount + (uint32_t)(xi - xa)) & (uint32_t)(kDyRing - 1)));
+      }
+      dcount += (uint32_t)(xb - xa);
+    }
+    umma_commit_elect(done_bar);
+  } else {
+    // ===== epilogue warps: zero the accumulators, and flush them once at the end =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // (ky, ci) = (row / 32, row % 32); ky == 3 is the discarded block
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c16 = 0; c16 < 3 * kNcols / 16; ++c16) tmem_st16_zero(lane_base + (uint32_t)c16 * 16u);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(zero_bar);
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int ky = row >> 5, ci = row & 31;
+    for (int dz = 0; dz < 3; ++dz) {
+      for (int c16 = 0; c16 < kNcols / 16; ++c16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + (uint32_t)(dz * kNcols + c16 * 16), r);
+        tmem_ld_wait();
+        if (ky < 3) {
+          const int kx = 2 - (c16 >> 1);                 // 32 columns per kx block
+          const int tap = (kx * 3 + ky) * 3 + dz;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = coc * kCC + (c16 & 1) * 16 + j;
+            atomicAdd(p.dw + ((int64_t)co * 27 + tap) * p.Ct + p.cofs + cic * kCC + ci, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_w() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int by) {
+  PFN_encodeTiled enc = get_encode_w();
+  FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2,
+                           (cuuint64_t)X * Y * Z * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kCC, (cuuint32_t)kBZ, (cuuint32_t)by, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA, "cuTensorMapEncodeTiled(wgrad march) failed: %d", (int)r);
+  return FM_OK;
+}
+
+const int kMaxDynSmemW = 227 * 1024;
+
+}  // namespace
+
+int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize) {
+  if (ksize != 3) return 0;
+  if (Y % kBY != 0 || Z % kBZ != 0 || X < 2) return 0;
+  if (Cin % kCC != 0 || Cout % kCC != 0) return 0;
+  return 1;
+}
+
+int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
+                         int Cin, int Cin_total, int cin_ofs, int Cout) {
+  FM_CHECK(conv_wgrad_march_supported(X, Y, Z, Cin, Cout, 3), FM_EINVAL,
+           "conv3d wgrad march: unsupported shape %dx%dx%d Cin=%d Cout=%d", X, Y, Z, Cin, Cout);
+  WgMarchParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N;
+  p.X = X;
+  p.Y = Y;
+  p.Z = Z;
+  p.ny = Y / kBY;
+  p.nz = Z / kBZ;
+  p.n_ci = Cin / kCC;
+  p.n_co = Cout / kCC;
+  p.Ct = Cin_total;
+  p.cofs = cin_ofs;
+  p.dw = dw_packed;
+  const int pairs = p.n_ci * p.n_co;
+  const int cols = N * p.ny * p.nz;
+  p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, cols * std::max(1, X / 4)));
+  // x-chunking so that every CTA of a pair gets work: items >= ctas_per_pair, chunks of >= 4 planes
+  {
+    int nxc = 1;
+    while (cols * nxc < p.ctas_per_pair * 2 && ceil_div(X, nxc * 2) >= 4) nxc *= 2;
+    p.xchunk = ceil_div(X, nxc);
+    p.nxc = ceil_div(X, p.xchunk);
+    p.items = cols * p.nxc;
+    p.ctas_per_pair = std::min(p.ctas_per_pair, p.items);
+  }
+  FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 3));
+  FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY));
+  p.S3 = 4;
+  const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)kDyRing * kDyTile + 1024 + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FM_CUDA(cudaFuncSetAttribute(conv3d_wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxDynSmemW));
+    attr_set = true;
+  }
+  const double vox = (double)N * X * Y * Z;
+  ProfScope prof(ctx, "conv3d_wgrad_march", 2.0 * 27 * Cin * Cout * vox, vox * (Cin + Cout) * 2.0);
+  conv3d_wgrad_march_kernel<<<pairs * p.ctas_per_pair, kThreadsW, smem, ctx->stream>>>(p);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}

@@ -74,6 +74,17 @@ MARCH_CASES = [
 ]
 
 
+# shapes for the marching wgrad kernel (Cin, Cout multiples of 32)
+WGRAD_MARCH_CASES = [
+    ("w32_32_16cube", 1, 16, 16, 16, 32, 0, 32, 3),
+    ("w32_32_32cube", 2, 32, 32, 32, 32, 0, 32, 3),      # dY ring wrap (X > 8)
+    ("w64_32_16x32x16", 1, 16, 32, 16, 64, 0, 32, 3),    # two ci chunks
+    ("w32_64_oddx", 3, 10, 16, 8, 32, 0, 64, 3),         # two co chunks, X not multiple of chunk
+    ("w128_64_x2", 2, 2, 16, 16, 128, 0, 64, 3),         # 8 pairs, two planes
+    ("w_cfg_64cube_32_32", 1, 64, 64, 64, 32, 0, 32, 3),
+]
+
+
 def conv_fprop_case(ctx, impl, case, seed=0):
     name, N, X, Y, Z, C1, C2, Cout, k = case
     rng = np.random.default_rng(seed)

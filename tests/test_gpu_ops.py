@@ -58,6 +58,12 @@ def test_conv3d_dgrad_march(ctx, case):
     assert ok, "worst error / tolerance = %.3f" % worst
 
 
+@pytest.mark.parametrize("case", gc.WGRAD_MARCH_CASES, ids=[c[0] for c in gc.WGRAD_MARCH_CASES])
+def test_conv3d_wgrad_march(ctx, case):
+    ok, worst = gc.conv_wgrad_case(ctx, 2, case)
+    assert ok, "rel. error / 2e-3 = %.3f" % worst
+
+
 def test_maxpool3d_fwd_bwd(ctx):
     ok, worst = gc.maxpool_case(ctx)
     assert ok, worst

@@ -49,9 +49,9 @@ def main():
                         dx = np.empty((vox, C1), np.float32)
                         _lib.check(lib.fm_op_conv3d_dgrad(ctx.handle, impl, _lib.fptr(y), _lib.fptr(w), None,
                                                           B, S, S, S, C1, Co, _lib.fptr(dx)))
-                    elif what == "wgrad" and C2 == 0 and impl == 0:
+                    elif what == "wgrad" and C2 == 0:
                         dw = np.empty_like(w)
-                        _lib.check(lib.fm_op_conv3d_wgrad(ctx.handle, 0, _lib.fptr(x1), _lib.fptr(y), B, S, S, S, C1, Co,
+                        _lib.check(lib.fm_op_conv3d_wgrad(ctx.handle, impl, _lib.fptr(x1), _lib.fptr(y), B, S, S, S, C1, Co,
                                                           _lib.fptr(dw), None))
                 recs = [r for r in ctx.profile_records() if r[0].startswith("conv3d")]
                 if recs:

@@ -19,6 +19,7 @@ kind, impl, ci = %(kind)r, %(impl)d, %(ci)d
 t0 = time.time()
 if kind == 'mfprop': r = gc.conv_fprop_case(ctx, 2, gc.MARCH_CASES[ci])
 elif kind == 'mdgrad': r = gc.conv_dgrad_case(ctx, 2, gc.MARCH_CASES[ci])
+elif kind == 'mwgrad': r = gc.conv_wgrad_case(ctx, 2, gc.WGRAD_MARCH_CASES[ci])
 elif kind == 'fprop': r = gc.conv_fprop_case(ctx, impl, gc.CONV_CASES[ci])
 elif kind == 'dgrad': r = gc.conv_dgrad_case(ctx, impl, gc.CONV_CASES[ci])
 elif kind == 'wgrad': r = gc.conv_wgrad_case(ctx, impl, gc.CONV_CASES[ci])
@@ -44,6 +45,8 @@ def main():
         jobs.append(("mfprop", 2, ci, "fprop[march] %s" % c[0]))
         if c[6] == 0:
             jobs.append(("mdgrad", 2, ci, "dgrad[march] %s" % c[0]))
+    for ci, c in enumerate(gc.WGRAD_MARCH_CASES):
+        jobs.append(("mwgrad", 2, ci, "wgrad[march] %s" % c[0]))
     only = sys.argv[1] if len(sys.argv) > 1 else None
     results = {}
     for kind, impl, ci, label in jobs:
