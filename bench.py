@@ -272,10 +272,21 @@ def run_b200(args):
                      for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
         top = max(agg.items(), key=lambda kv: kv[1][1])
         name, (cnt, kms, fl, by) = top
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/)
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            key = {"conv3d_wgrad_march": "wgrad/conv3d_wgrad_march_kernel", "conv3d_march_fprop": "fprop/conv3d_march_kernel",
+                   "conv3d_march_dgrad": "dgrad/conv3d_march_kernel"}.get(name)
+            if key in tj:
+                traffic = tj[key]
+                traffic_note = "ncu capture of the dec0b-sized launch (32->32 @ 8x64^3; algorithmic bytes 268.4e6)"
         if fl > 0:
             ach = fl / kms / 1e9        # TFLOP/s: algorithmic flops per launch / avg launch duration
             roof = dict(kernel=name, bound="tensor", achieved=ach, peak=pk["tf_sustained"], unit="TFLOP/s",
-                        frac=ach / pk["tf_sustained"], traffic=None, peak_source=pk["src"] + " (sustained)",
+                        frac=ach / pk["tf_sustained"], traffic=traffic, traffic_note=traffic_note,
+                        peak_source=pk["src"] + " (sustained)",
                         launches_per_step=cnt // nprof, avg_launch_ms=kms / cnt,
                         algorithmic_flops_per_launch=fl / cnt, share_of_step=kms / total_ms)
         else:

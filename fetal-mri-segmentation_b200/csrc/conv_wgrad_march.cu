@@ -44,6 +44,7 @@ struct alignas(64) WgMarchParams {
   int n_ci, n_co;      // 32-channel chunks of Cin (this source) and Cout
   int ctas_per_pair;   // grid = n_ci * n_co * ctas_per_pair
   int S3;              // X slab slots per kz ring
+  int kcx;             // input channels per CTA / per M block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cin = 16)
   int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
   float* dw;
 };
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
 
   if (warp_u == 0) {
     // ===== TMA producer =====
+    const uint32_t x_bytes = (uint32_t)(kBY + 128 / p.kcx - 1) * kBZ * (uint32_t)p.kcx * 2u;  // slab box bytes
     uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
     uint32_t dcount = 0;  // dY tiles issued so far (ring position)
     for (int item = rank; item < p.items; item += p.ctas_per_pair) {
@@ -132,9 +134,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         for (int dz = 0; dz < 3; ++dz) {
           const uint32_t stage = (uint32_t)dz * (uint32_t)p.S3 + sidx[dz];
           mbar_wait(xempty_bar(stage), sph[dz] ^ 1u);
-          mbar_expect_tx_elect(xfull_bar(stage), kXSlabRows * kRow);
-          tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * kCC, iz * kBZ + dz - 1, iy * kBY - 1,
-                            xi, n);
+          mbar_expect_tx_elect(xfull_bar(stage), x_bytes);
+          tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ + dz - 1,
+                            iy * kBY - 1, xi, n);
           if (++sidx[dz] == (uint32_t)p.S3) {
             sidx[dz] = 0;
             sph[dz] ^= 1u;
@@ -148,8 +150,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     const uint32_t d_acc = tmem_base + (uint32_t)(dz * kNcols);
     const uint32_t idesc1 = make_idesc(128, kCC, 1, 1), idesc2 = make_idesc(128, 2 * kCC, 1, 1),
                    idesc3 = make_idesc(128, 3 * kCC, 1, 1);
-    const uint32_t hi32 = desc_hi(kSbo, layout_code((int)kRow));
+    const uint32_t hi32 = desc_hi(kSbo, layout_code((int)kRow));            // dY operand: 64-byte rows
     const uint32_t kstep = (2u * kSbo) >> 4;  // 16 voxels (two 8-row groups) per MMA, in 16-byte units
+    const uint32_t a_row = (uint32_t)p.kcx * 2u, a_sbo = 8u * a_row;         // X operand: 64- or 32-byte rows
+    const uint32_t a_hi32 = desc_hi(a_sbo, layout_code((int)a_row));
+    const uint32_t a_kstep = (2u * a_sbo) >> 4;
     mbar_wait(zero_bar, 0);                   // accumulators zeroed by the epilogue warps
     tc_fence_after();
     uint32_t sidx = 0, sph = 0, dcount = 0, dwaited = 0;
@@ -174,15 +179,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         const uint32_t nA = min(nblk, (uint32_t)kDyRing - rs), nB = nblk - nA;
         const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
         const uint32_t idB = nB == 1 ? idesc1 : idesc2;
-        uint32_t a_lo = desc_lo(x_base + stage * kXSlot, kSbo);           // M blocks (ky) one atom apart
+        uint32_t a_lo = desc_lo(x_base + stage * kXSlot, a_sbo);          // M blocks (ky) one atom apart
         uint32_t bA = desc_lo(dy_base + rs * kDyTile, kDyTile);           // N blocks (kx) one ring slot apart
         uint32_t bB = desc_lo(dy_base, kDyTile);
         const uint32_t dA = d_acc + j_lo * kCC, dB = dA + nA * kCC;
 #pragma unroll
         for (int ks = 0; ks < (kBY * kBZ) / 16; ++ks) {
-          umma_bf16_lh_elect(dA, a_lo, hi32, bA, hi32, idA, 1u);
-          if (nB) umma_bf16_lh_elect(dB, a_lo, hi32, bB, hi32, idB, 1u);
-          a_lo += kstep;
+          umma_bf16_lh_elect(dA, a_lo, a_hi32, bA, hi32, idA, 1u);
+          if (nB) umma_bf16_lh_elect(dB, a_lo, a_hi32, bB, hi32, idB, 1u);
+          a_lo += a_kstep;
           bA += kstep;
           bB += kstep;
         }
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     mbar_arrive(zero_bar);
     mbar_wait(done_bar, 0);
     tc_fence_after();
-    const int ky = row >> 5, ci = row & 31;
+    const int ky = row / p.kcx, ci = row % p.kcx;
     for (int dz = 0; dz < 3; ++dz) {
       for (int c16 = 0; c16 < kNcols / 16; ++c16) {
         uint32_t r[16];
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int co = coc * kCC + (c16 & 1) * 16 + j;
-            atomicAdd(p.dw + ((int64_t)co * 27 + tap) * p.Ct + p.cofs + cic * kCC + ci, __uint_as_float(r[j]));
+            atomicAdd(p.dw + ((int64_t)co * 27 + tap) * p.Ct + p.cofs + cic * p.kcx + ci, __uint_as_float(r[j]));
           }
         }
       }
@@ -253,17 +258,17 @@ PFN_encodeTiled get_encode_w() {
   return fn;
 }
 
-int make_map(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int by) {
+int make_map(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int by, int cbox) {
   PFN_encodeTiled enc = get_encode_w();
   FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2,
                            (cuuint64_t)X * Y * Z * C * 2};
-  cuuint32_t box[5] = {(cuuint32_t)kCC, (cuuint32_t)kBZ, (cuuint32_t)by, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)kBZ, (cuuint32_t)by, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA, "cuTensorMapEncodeTiled(wgrad march) failed: %d", (int)r);
   return FM_OK;
 }
@@ -275,7 +280,7 @@ const int kMaxDynSmemW = 227 * 1024;
 int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize) {
   if (ksize != 3) return 0;
   if (Y % kBY != 0 || Z % kBZ != 0 || X < 2) return 0;
-  if (Cin % kCC != 0 || Cout % kCC != 0) return 0;
+  if (!(Cin % kCC == 0 || Cin == 16) || Cout % kCC != 0) return 0;
   return 1;
 }
 
@@ -291,7 +296,8 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   p.Z = Z;
   p.ny = Y / kBY;
   p.nz = Z / kBZ;
-  p.n_ci = Cin / kCC;
+  p.kcx = (Cin % kCC == 0) ? kCC : 16;
+  p.n_ci = Cin / p.kcx;
   p.n_co = Cout / kCC;
   p.Ct = Cin_total;
   p.cofs = cin_ofs;
@@ -308,8 +314,8 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
     p.items = cols * p.nxc;
     p.ctas_per_pair = std::min(p.ctas_per_pair, p.items);
   }
-  FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 3));
-  FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY));
+  FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));  // halo + discarded M blocks
+  FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, kCC));
   p.S3 = 4;
   const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)kDyRing * kDyTile + 1024 + 512;
   static bool attr_set = false;

@@ -82,6 +82,7 @@ WGRAD_MARCH_CASES = [
     ("w32_64_oddx", 3, 10, 16, 8, 32, 0, 64, 3),         # two co chunks, X not multiple of chunk
     ("w128_64_x2", 2, 2, 16, 16, 128, 0, 64, 3),         # 8 pairs, two planes
     ("w_cfg_64cube_32_32", 1, 64, 64, 64, 32, 0, 32, 3),
+    ("w16_32_32cube", 2, 32, 32, 32, 16, 0, 32, 3),      # enc0b: Cin = 16 (SWIZZLE_32B X operand, 8 M blocks)
 ]
 
 
