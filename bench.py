@@ -334,6 +334,19 @@ def run_infer(args):
         out = patch_wise_prediction(model, vol, PATCH, overlap_factor=OVERLAP, batch_size=49)
     sec = (time.perf_counter() - t0) / args.steps
     nvox = int(np.prod(VOLUME))
+    ctx.profile(True)
+    t1 = time.perf_counter()
+    out = patch_wise_prediction(model, vol, PATCH, overlap_factor=OVERLAP, batch_size=49)
+    prof_wall = time.perf_counter() - t1
+    agg = {}
+    for name, kms, fl, by in ctx.profile_records():
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += kms
+    ctx.profile(False)
+    breakdown = {k: dict(launches=a[0], ms=a[1]) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+    breakdown["_sum_kernels_ms"] = sum(a[1] for a in agg.values())
+    breakdown["_wall_ms_profiled_call"] = prof_wall * 1e3
     line = dict(metric="U-Net infer voxels/sec", value=nvox / sec, unit=UNIT, n_gpus=1, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic",
@@ -342,7 +355,7 @@ def run_infer(args):
                 e2e=dict(value=nvox / sec, unit=UNIT, h2d_bytes_per_step=int(vol.nbytes),
                          d2h_bytes_per_step=int(out.nbytes + nvox * 2)),
                 gpu_launches=int((ctx.launch_count() - l0) // args.steps),
-                conv_tflops=49 * FWD_GF_PER_PATCH / (sec * 1e3), out_mean=float(out.mean()))
+                conv_tflops=49 * FWD_GF_PER_PATCH / (sec * 1e3), out_mean=float(out.mean()), kernel_breakdown=breakdown)
     print(json.dumps(line))
 
 

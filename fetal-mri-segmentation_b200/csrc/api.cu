@@ -196,6 +196,12 @@ struct fm_model {
   double* sums = nullptr;  // 8 doubles (device)
   double sums_host[8];
 
+  // sliding-window workspace (grow-only): volume, corners, per-patch probabilities, fp64 sums, counts
+  DevBuf<float> pw_vol, pw_pred;
+  DevBuf<int32_t> pw_idx;
+  DevBuf<double> pw_out;
+  DevBuf<int16_t> pw_cnt;
+
   // backward bucket events (one per layer, reverse creation order)
   std::vector<cudaEvent_t> layer_done;
   std::vector<std::pair<int, int>> buckets;  // [first layer, last layer] inclusive, creation order
@@ -371,6 +377,11 @@ extern "C" int fm_model_destroy(fm_model* m) {
       if (l.w_mf[s]) cudaFree(l.w_mf[s]);
       if (l.w_md[s]) cudaFree(l.w_md[s]);
     }
+  m->pw_vol.release();
+  m->pw_pred.release();
+  m->pw_idx.release();
+  m->pw_out.release();
+  m->pw_cnt.release();
   m->x_in.release();
   m->t_in.release();
   m->prob.release();
@@ -844,60 +855,40 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
   const int64_t nloc = hi - lo;
   batch = (int)std::min<int64_t>(batch, std::max<int64_t>(nloc, 1));
   FM_TRY(ensure_capacity(m, batch, false));
-  DevBuf<float> dvol, dpred;
-  DevBuf<int32_t> didx;
-  DevBuf<double> dout;
-  DevBuf<int16_t> dcnt;
-  int r = FM_OK;
-  auto cleanup = [&]() {
-    cudaStreamSynchronize(ctx->stream);
-    dvol.release();
-    dpred.release();
-    didx.release();
-    dout.release();
-    dcnt.release();
-  };
-#define FM_PW(expr)        \
-  do {                     \
-    r = (expr);            \
-    if (r != FM_OK) {      \
-      cleanup();           \
-      return r;            \
-    }                      \
-  } while (0)
-#define FM_PWC(expr)                                                        \
-  do {                                                                      \
-    cudaError_t _e = (expr);                                                \
-    if (_e != cudaSuccess) {                                                \
-      fm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
-      cleanup();                                                            \
-      return FM_ECUDA;                                                      \
-    }                                                                       \
-  } while (0)
-  FM_PW(dvol.ensure(nv));
-  FM_PW(dpred.ensure(std::max<size_t>(1, (size_t)nloc) * pv));
-  FM_PW(didx.ensure((size_t)n * 3));
-  FM_PW(dout.ensure(nout));
-  FM_PW(dcnt.ensure(nout));
-  FM_PWC(cudaMemcpyAsync(dvol.p, vol, nv * 4, cudaMemcpyHostToDevice, ctx->stream));
-  FM_PWC(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-  FM_PWC(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));
+  DevBuf<float>&dvol = m->pw_vol, &dpred = m->pw_pred;
+  DevBuf<int32_t>& didx = m->pw_idx;
+  DevBuf<double>& dout = m->pw_out;
+  DevBuf<int16_t>& dcnt = m->pw_cnt;
+  FM_TRY(dvol.ensure(nv));
+  FM_TRY(dpred.ensure(std::max<size_t>(1, (size_t)nloc) * pv));
+  FM_TRY(didx.ensure((size_t)n * 3));
+  FM_TRY(dout.ensure(nout));
+  FM_TRY(dcnt.ensure(nout));
+  // host <-> device through the context's pinned staging buffer (pageable cudaMemcpy runs at a fraction of PCIe)
+  void* pin = nullptr;
+  const size_t out_bytes = nout * sizeof(double), cnt_bytes = out_count ? nout * sizeof(int16_t) : 0;
+  FM_TRY(fm_ctx_pinned(ctx, std::max(nv * sizeof(float), out_bytes + cnt_bytes), &pin));
+  memcpy(pin, vol, nv * sizeof(float));
+  FM_CUDA(cudaMemcpyAsync(dvol.p, pin, nv * 4, cudaMemcpyHostToDevice, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  FM_CUDA(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));
   for (int64_t b0 = lo; b0 < hi; b0 += batch) {
     const int nb = (int)std::min<int64_t>(batch, hi - b0);
-    FM_PW(k_gather_patches(ctx, dvol.p, vol_dims, halo_pad, fit_pad, (float)pad_value[0],
-                           (float)pad_value[1], didx.p + b0 * 3, nb, patch, m->x_in.p));
-    FM_PW(forward(m, nb));
-    FM_PWC(cudaMemcpyAsync(dpred.p + (size_t)(b0 - lo) * pv, m->prob.p, (size_t)nb * pv * 4,
-                           cudaMemcpyDeviceToDevice, ctx->stream));
+    FM_TRY(k_gather_patches(ctx, dvol.p, vol_dims, halo_pad, fit_pad, (float)pad_value[0], (float)pad_value[1],
+                            didx.p + b0 * 3, nb, patch, m->x_in.p));
+    FM_TRY(forward(m, nb));
+    FM_CUDA(cudaMemcpyAsync(dpred.p + (size_t)(b0 - lo) * pv, m->prob.p, (size_t)nb * pv * 4,
+                            cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  FM_PW(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, patch, 1, out_dims, dout.p, dcnt.p,
-                     shard_count == 1 ? 1 : 0));
-  FM_PWC(cudaMemcpyAsync(out, dout.p, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_count) FM_PWC(cudaMemcpyAsync(out_count, dcnt.p, nout * 2, cudaMemcpyDeviceToHost, ctx->stream));
-  FM_PWC(cudaStreamSynchronize(ctx->stream));
-#undef FM_PW
-#undef FM_PWC
-  cleanup();
+  FM_TRY(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, patch, 1, out_dims, dout.p, dcnt.p,
+                      shard_count == 1 ? 1 : 0));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the H2D staging buffer is reused for the way back
+  FM_CUDA(cudaMemcpyAsync(pin, dout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_count)
+    FM_CUDA(cudaMemcpyAsync((char*)pin + out_bytes, dcnt.p, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, pin, out_bytes);
+  if (out_count) memcpy(out_count, (char*)pin + out_bytes, cnt_bytes);
   m->fwd_valid = false;
   return FM_OK;
 }

@@ -55,9 +55,11 @@ def _geometry(model, data, patch_shape, overlap_factor):
     patch_shape = tuple(int(v) for v in patch_shape)
     vol = data[0]
     halo = _pad_pairs(np.subtract(patch_shape, prediction_shape))
-    pad0 = float(np.percentile(vol, q=1))
     halo_dims = tuple(int(s + a + b) for s, (a, b) in zip(vol.shape, halo))
     fit = _pad_pairs(np.maximum(np.subtract(patch_shape, halo_dims), 0))
+    # the 1st-percentile pad value (prediction.py:141,146) is only needed where something is padded
+    needs_pad = any(a + b for a, b in halo) or any(a + b for a, b in fit)
+    pad0 = float(np.percentile(vol, q=1)) if needs_pad else 0.0
     if any(a + b for a, b in fit):
         # second percentile is taken over the already halo-padded array (prediction.py:144-146)
         padded_once = np.pad(vol, halo, mode='constant', constant_values=pad0) if any(a + b for a, b in halo) else vol
@@ -100,8 +102,10 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
     fit = _lib.i32x(g["fit"])
     padv = np.asarray(g["pad"], np.float64)
     out = np.empty(g["out_dims"] + (g["channels"],), np.float64)
-    cnt = np.empty(g["out_dims"], np.int16)
     rank, count = (0, 1) if shard is None else (int(shard[0]), int(shard[1]))
+    # counts are analytic: the library rejects an uncovered voxel itself ('Found zeros in count'), so the
+    # int16 map only travels back when the caller has to divide after a cross-rank reduce
+    cnt = np.empty(g["out_dims"], np.int16) if count > 1 else None
 
     if isinstance(model, Model) and g["is3d"]:
         assert tuple(g["patch_shape"]) == tuple(model.input_shape[2:]), \
@@ -128,13 +132,13 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
         if count == 1:
             _lib.check(lib.fm_reassemble(ctx.handle, _lib.fptr(preds), _lib.i32ptr(idx), len(idx),
                                          _lib.i32ptr(_lib.i32x(g["prediction_shape"])), g["channels"],
-                                         _lib.i32ptr(_lib.i32x(g["out_dims"])), _lib.dptr(out), _lib.i16ptr(cnt)))
+                                         _lib.i32ptr(_lib.i32x(g["out_dims"])), _lib.dptr(out), None))
         else:
             raise NotImplementedError("sharded inference needs a native Model")
 
     if shard is not None and count > 1:
         return _crop_fit(out, g["fit"]), _crop_fit(cnt, g["fit"])
-    assert np.all(cnt > 0), 'Found zeros in count'                               # prediction.py:196
+    # prediction.py:196 'Found zeros in count' is raised by the library (fm_reassemble) for an uncovered voxel
     out = _crop_fit(out, g["fit"])
     assert np.array_equal(out.shape[:-1], data[0].shape), 'prediction shape wrong'  # prediction.py:209
     return out
