@@ -172,8 +172,10 @@ struct Layer {
   // plane-marching kernel (conv_march.cu): packs per source for fprop / dgrad, null when not applicable
   bf16 *w_mf[2] = {nullptr, nullptr}, *w_md[2] = {nullptr, nullptr};
   bool march_f = false, march_d[2] = {false, false};
+  int cin_real = 0;     // true input channels when c1 is zero-padded to 16 (first layer of the 2.5D U-Net)
   int cin() const { return c1 + c2; }
-  int taps() const { return k * k * k; }
+  int taps() const { return kext_taps(k); }
+  int cin_keras() const { return cin_real ? cin_real : cin(); }
   int64_t wcount() const { return (int64_t)cout * taps() * cin(); }
 };
 
@@ -190,6 +192,10 @@ struct fm_model {
   // activations, allocated for `cap` samples
   int cap = 0;
   bool train_alloc = false;
+  int kcode = 3;  // 3: Conv3D 3x3x3 (unet_model_3d); 31: Conv2D 3x3 on a Z = 1 volume (unet_model_2d)
+  int pz = 2;     // pooling factor along z
+  int cin_real = 1;
+  DevBuf<bf16> x_pad;  // 2D model: input cast to bf16 and zero-padded to 16 channels
   DevBuf<float> x_in, t_in, prob, dz;
   std::vector<DevBuf<bf16>> encA, encB, pool, up, decA, decB;          // forward
   std::vector<DevBuf<bf16>> gEncA, gEncB, gPool, gUp, gSkip, gDecA, gDecB;  // gradients
@@ -211,10 +217,10 @@ struct fm_model {
 
   int depth() const { return spec.depth; }
   Dims5 dims(int level, int C, int B) const {
-    return Dims5{B, spec.X >> level, spec.Y >> level, spec.Z >> level, C};
+    return Dims5{B, spec.X >> level, spec.Y >> level, pz == 2 ? spec.Z >> level : spec.Z, C};
   }
   int64_t vox(int level) const {
-    return (int64_t)(spec.X >> level) * (spec.Y >> level) * (spec.Z >> level);
+    return (int64_t)(spec.X >> level) * (spec.Y >> level) * (pz == 2 ? spec.Z >> level : spec.Z);
   }
 };
 
@@ -235,23 +241,50 @@ static bool use_march() {
   return !(e && e[0] == '1');
 }
 
+static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_model** out);
+
 extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out) {
   FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_unet3d: NULL argument");
-  FM_CHECK(spec->depth >= 2 && spec->depth <= 6, FM_EINVAL, "depth %d unsupported", spec->depth);
   FM_CHECK(spec->in_channels == 1, FM_EINVAL,
            "in_channels=%d: only the reference's single-modality path (1) is built", spec->in_channels);
-  FM_CHECK(spec->n_labels == 1, FM_EINVAL, "n_labels=%d: only 1 is built", spec->n_labels);
-  FM_CHECK(spec->n_base_filters == 16 || spec->n_base_filters == 32, FM_EINVAL,
-           "n_base_filters=%d: 16 or 32", spec->n_base_filters);
-  const int div = 1 << (spec->depth - 1);
+  const int div = 1 << (spec->depth > 0 ? spec->depth - 1 : 0);
   FM_CHECK(spec->X > 0 && spec->Y > 0 && spec->Z > 0 && spec->X % div == 0 && spec->Y % div == 0 &&
                spec->Z % div == 0,
            FM_EINVAL, "input extent %dx%dx%d must be divisible by 2^(depth-1)=%d (unet3d/unet.py:32-33)",
            spec->X, spec->Y, spec->Z, div);
+  return build_unet(ctx, spec, 3, out);
+}
+
+extern "C" int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec2, fm_model** out) {
+  FM_CHECK(ctx && spec2 && out, FM_EINVAL, "fm_model_create_unet2d: NULL argument");
+  FM_CHECK(spec2->in_channels >= 1 && spec2->in_channels <= 16, FM_EINVAL,
+           "in_channels=%d: the slices-as-channels input supports 1..16 channels", spec2->in_channels);
+  const int div = 1 << (spec2->depth > 0 ? spec2->depth - 1 : 0);
+  FM_CHECK(spec2->H > 0 && spec2->W > 0 && spec2->H % div == 0 && spec2->W % div == 0, FM_EINVAL,
+           "input extent %dx%d must be divisible by 2^(depth-1)=%d", spec2->H, spec2->W, div);
+  fm_unet3d_spec s;
+  s.in_channels = spec2->in_channels;
+  s.X = spec2->H;
+  s.Y = spec2->W;
+  s.Z = 1;
+  s.depth = spec2->depth;
+  s.n_base_filters = spec2->n_base_filters;
+  s.n_labels = spec2->n_labels;
+  return build_unet(ctx, &s, 31, out);
+}
+
+static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_model** out) {
+  FM_CHECK(spec->depth >= 2 && spec->depth <= 6, FM_EINVAL, "depth %d unsupported", spec->depth);
+  FM_CHECK(spec->n_labels == 1, FM_EINVAL, "n_labels=%d: only 1 is built", spec->n_labels);
+  FM_CHECK(spec->n_base_filters == 16 || spec->n_base_filters == 32, FM_EINVAL,
+           "n_base_filters=%d: 16 or 32", spec->n_base_filters);
   FM_CUDA(cudaSetDevice(ctx->device));
   fm_model* m = new fm_model();
   m->ctx = ctx;
   m->spec = *spec;
+  m->kcode = kcode;
+  m->pz = kcode == 31 ? 1 : 2;
+  m->cin_real = spec->in_channels;
   const int D = spec->depth, nf = spec->n_base_filters;
   auto add = [&](const char* fmt, int d, int c1, int c2, int cout, int k, int level) {
     Layer l;
@@ -270,21 +303,23 @@ extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, f
     m->nparams = (m->nparams + 3) & ~(int64_t)3;
     m->layers.push_back(l);
   };
-  int c = spec->in_channels;
+  // the 2D model feeds its first conv from a 16-channel zero-padded copy of the input (tensor-core K granule)
+  int c = kcode == 31 ? 16 : spec->in_channels;
   std::vector<int> skipc;
   for (int d = 0; d < D; ++d) {
     const int f1 = nf << d, f2 = f1 * 2;
-    add("enc%da", d, c, 0, f1, 3, d);
-    add("enc%db", d, f1, 0, f2, 3, d);
+    add("enc%da", d, c, 0, f1, kcode, d);
+    add("enc%db", d, f1, 0, f2, kcode, d);
     skipc.push_back(f2);
     c = f2;
   }
   for (int d = D - 2; d >= 0; --d) {
-    add("dec%da", d, c, skipc[d], skipc[d], 3, d);  // concat order [up, skip] (unet.py:61)
-    add("dec%db", d, skipc[d], 0, skipc[d], 3, d);
+    add("dec%da", d, c, skipc[d], skipc[d], kcode, d);  // concat order [up, skip] (unet.py:61)
+    add("dec%db", d, skipc[d], 0, skipc[d], kcode, d);
     c = skipc[d];
   }
   add("final", 0, c, 0, spec->n_labels, 1, 0);
+  if (kcode == 31) m->layers[0].cin_real = spec->in_channels;
 
   const size_t pb = (size_t)m->nparams * sizeof(float);
   FM_CUDA(cudaMalloc((void**)&m->params, pb));
@@ -311,7 +346,7 @@ extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, f
   }
   for (auto& l : m->layers) {
     if (l.k != 3 || l.c1 < 16) continue;
-    const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
+    const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = m->pz == 2 ? spec->Z >> l.level : spec->Z;
     const int cs[2] = {l.c1, l.c2};
     if (use_march() && conv_march_supported(X, Y, Z, l.c1, l.c2, l.cout, l.k)) {
       l.march_f = true;
@@ -383,6 +418,7 @@ extern "C" int fm_model_destroy(fm_model* m) {
   m->pw_out.release();
   m->pw_cnt.release();
   m->x_in.release();
+  m->x_pad.release();
   m->t_in.release();
   m->prob.release();
   m->dz.release();
@@ -399,7 +435,7 @@ extern "C" int fm_model_num_layers(fm_model* m) { return m ? (int)m->layers.size
 extern "C" int64_t fm_model_num_params(fm_model* m) {
   if (!m) return -1;
   int64_t n = 0;
-  for (auto& l : m->layers) n += l.wcount() + l.cout;
+  for (auto& l : m->layers) n += (int64_t)l.cout * l.taps() * l.cin_keras() + l.cout;
   return n;
 }
 extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_t info[5]) {
@@ -407,9 +443,9 @@ extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_
   const Layer& l = m->layers[layer];
   if (name) memcpy(name, l.name, 32);
   if (info) {
-    info[0] = l.cin();
+    info[0] = l.cin_keras();
     info[1] = l.cout;
-    info[2] = l.k;
+    info[2] = kext_xy(l.k) * 10 + kext_z(l.k);  // 33: 3x3x3, 31: 3x3(x1), 11: 1x1x1
     info[3] = l.w_off;
     info[4] = l.b_off;
   }
@@ -417,19 +453,22 @@ extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_
 }
 
 // Keras layout (k0,k1,k2,Cin,Cout) <-> packed [Cout][tap=(k0*K+k1)*K+k2][Cin]
-static void keras_to_packed(const float* kern, float* packed, int K, int Cin, int Cout) {
-  const int taps = K * K * K;
+// `Cin` = channels of the Keras kernel, `Cpad` >= Cin = channels of the packed kernel (extra channels zero)
+static void keras_to_packed(const float* kern, float* packed, int K, int Cin, int Cout, int Cpad = 0) {
+  const int taps = kext_taps(K);
+  if (Cpad < Cin) Cpad = Cin;
   for (int tap = 0; tap < taps; ++tap)
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int co = 0; co < Cout; ++co)
-        packed[((int64_t)co * taps + tap) * Cin + ci] = kern[((int64_t)tap * Cin + ci) * Cout + co];
+    for (int co = 0; co < Cout; ++co)
+      for (int ci = 0; ci < Cpad; ++ci)
+        packed[((int64_t)co * taps + tap) * Cpad + ci] = ci < Cin ? kern[((int64_t)tap * Cin + ci) * Cout + co] : 0.f;
 }
-static void packed_to_keras(const float* packed, float* kern, int K, int Cin, int Cout) {
-  const int taps = K * K * K;
+static void packed_to_keras(const float* packed, float* kern, int K, int Cin, int Cout, int Cpad = 0) {
+  const int taps = kext_taps(K);
+  if (Cpad < Cin) Cpad = Cin;
   for (int tap = 0; tap < taps; ++tap)
     for (int ci = 0; ci < Cin; ++ci)
       for (int co = 0; co < Cout; ++co)
-        kern[((int64_t)tap * Cin + ci) * Cout + co] = packed[((int64_t)co * taps + tap) * Cin + ci];
+        kern[((int64_t)tap * Cin + ci) * Cout + co] = packed[((int64_t)co * taps + tap) * Cpad + ci];
 }
 
 extern "C" int fm_model_set_weights(fm_model* m, int layer, const float* kernel, const float* bias) {
@@ -438,7 +477,7 @@ extern "C" int fm_model_set_weights(fm_model* m, int layer, const float* kernel,
   FM_CUDA(cudaSetDevice(m->ctx->device));
   Layer& l = m->layers[layer];
   std::vector<float> packed((size_t)l.wcount());
-  keras_to_packed(kernel, packed.data(), l.k, l.cin(), l.cout);
+  keras_to_packed(kernel, packed.data(), l.k, l.cin_keras(), l.cout, l.cin());
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
   FM_CUDA(cudaMemcpy(m->params + l.w_off, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
   FM_CUDA(cudaMemcpy(m->params + l.b_off, bias, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
@@ -453,7 +492,7 @@ static int get_flat(fm_model* m, const float* flat, int layer, float* kernel, fl
   if (kernel) {
     std::vector<float> packed((size_t)l.wcount());
     FM_CUDA(cudaMemcpy(packed.data(), flat + l.w_off, packed.size() * 4, cudaMemcpyDeviceToHost));
-    packed_to_keras(packed.data(), kernel, l.k, l.cin(), l.cout);
+    packed_to_keras(packed.data(), kernel, l.k, l.cin_keras(), l.cout, l.cin());
   }
   if (bias) FM_CUDA(cudaMemcpy(bias, flat + l.b_off, (size_t)l.cout * 4, cudaMemcpyDeviceToHost));
   return FM_OK;
@@ -499,7 +538,8 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
   const int cap = std::max(B, m->cap);
   const int D = m->depth();
   const size_t v0 = (size_t)m->vox(0);
-  FM_TRY(m->x_in.ensure((size_t)cap * v0 * m->spec.in_channels));
+  FM_TRY(m->x_in.ensure((size_t)cap * v0 * m->cin_real));
+  if (m->kcode == 31) FM_TRY(m->x_pad.ensure((size_t)cap * v0 * 16));
   FM_TRY(m->prob.ensure((size_t)cap * v0));
   for (int d = 0; d < D; ++d) {
     const size_t v = (size_t)m->vox(d) * cap;
@@ -561,7 +601,10 @@ static int forward(fm_model* m, int B) {
   for (int d = 0; d < D; ++d) {
     const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
     const Dims5 dd = m->dims(d, la.cout, B);
-    if (d == 0) {
+    if (d == 0 && m->kcode == 31) {
+      FM_TRY(k_pad_cast(ctx, m->x_in.p, m->x_pad.p, dd.voxels(), m->cin_real, 16));
+      FM_TRY(conv_fwd(m, la, m->x_pad.p, nullptr, m->encA[0].p, B));
+    } else if (d == 0) {
       FM_TRY(k_conv3d_simt_fprop(ctx, m->x_in.p, 1, nullptr, la.w_f, m->params + la.b_off, m->encA[0].p,
                                  nullptr, B, dd.X, dd.Y, dd.Z, la.c1, 0, la.cout, la.k, 1, nullptr));
     } else {
@@ -570,13 +613,13 @@ static int forward(fm_model* m, int B) {
     FM_TRY(conv_fwd(m, lb, m->encA[d].p, nullptr, m->encB[d].p, B));
     cur = m->encB[d].p;
     if (d < D - 1) {
-      FM_TRY(k_maxpool3d_fwd(ctx, m->encB[d].p, m->pool[d].p, m->dims(d, lb.cout, B)));
+      FM_TRY(k_maxpool3d_fwd(ctx, m->encB[d].p, m->pool[d].p, m->dims(d, lb.cout, B), m->pz));
       cur = m->pool[d].p;
     }
   }
   for (int d = D - 2; d >= 0; --d) {
     const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
-    FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B)));
+    FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B), m->pz));
     FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
     FM_TRY(conv_fwd(m, db, m->decA[d].p, nullptr, m->decB[d].p, B));
     cur = m->decB[d].p;
@@ -658,14 +701,14 @@ static int backward(fm_model* m, int B) {
     const bool bottom = (d + 1 == D - 1);
     const bf16* act = bottom ? m->encB[D - 1].p : m->decB[d + 1].p;
     bf16* gdst = bottom ? m->gEncB[D - 1].p : m->gDecB[d + 1].p;
-    FM_TRY(k_upsample3d_bwd(ctx, m->gUp[d].p, act, gdst, m->dims(d + 1, da.c1, B), da.c1, 0));
+    FM_TRY(k_upsample3d_bwd(ctx, m->gUp[d].p, act, gdst, m->dims(d + 1, da.c1, B), da.c1, 0, m->pz));
   }
   for (int d = D - 1; d >= 0; --d) {
     const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
     if (d < D - 1) {
       // gradient of encB[d]: skip path + MaxPooling3D backward, masked by its ReLU
       FM_TRY(k_maxpool3d_bwd(ctx, m->encB[d].p, m->gPool[d].p, m->gSkip[d].p, m->gEncB[d].p,
-                             m->dims(d, lb.cout, B), 1));
+                             m->dims(d, lb.cout, B), 1, m->pz));
     }
     FM_TRY(conv_wgrad(m, lb, m->encA[d].p, nullptr, m->gEncB[d].p, B));
     FM_TRY(mark_layer_done(m, lb));
@@ -674,6 +717,9 @@ static int backward(fm_model* m, int B) {
       FM_TRY(conv_wgrad(m, la, m->pool[d - 1].p, nullptr, m->gEncA[d].p, B));
       FM_TRY(mark_layer_done(m, la));
       FM_TRY(conv_dgrad(m, la, 0, m->gEncA[d].p, nullptr, m->gPool[d - 1].p, B));
+    } else if (m->kcode == 31) {
+      FM_TRY(conv_wgrad(m, la, m->x_pad.p, nullptr, m->gEncA[0].p, B));
+      FM_TRY(mark_layer_done(m, la));
     } else {
       const Dims5 dd = m->dims(0, la.cout, B);
       FM_TRY(k_conv3d_simt_wgrad(ctx, m->x_in.p, 1, m->gEncA[0].p, m->grads + la.w_off, B, dd.X, dd.Y, dd.Z,
@@ -708,7 +754,7 @@ extern "C" int fm_predict_device(fm_model* m, uint64_t x_dev, int batch, uint64_
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, false));
   const size_t n = (size_t)batch * m->vox(0);
-  FM_CUDA(cudaMemcpyAsync(m->x_in.p, (const void*)(uintptr_t)x_dev, n * 4, cudaMemcpyDeviceToDevice,
+  FM_CUDA(cudaMemcpyAsync(m->x_in.p, (const void*)(uintptr_t)x_dev, n * m->cin_real * 4, cudaMemcpyDeviceToDevice,
                           m->ctx->stream));
   FM_TRY(forward(m, batch));
   if (y_dev)
@@ -723,7 +769,7 @@ extern "C" int fm_predict(fm_model* m, const float* x, int batch, float* y) {
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, false));
   const size_t n = (size_t)batch * m->vox(0);
-  FM_TRY(upload(m, x, m->x_in.p, n));
+  FM_TRY(upload(m, x, m->x_in.p, n * m->cin_real));
   FM_TRY(forward(m, batch));
   FM_CUDA(cudaMemcpyAsync(y, m->prob.p, n * 4, cudaMemcpyDeviceToHost, m->ctx->stream));
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
@@ -834,23 +880,30 @@ extern "C" int fm_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx
 extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t vol_dims[3],
                                     const int32_t halo_pad[6], const int32_t fit_pad[6],
                                     const double pad_value[2], const int32_t* idx, int64_t n, int batch,
-                                    int shard_rank, int shard_count, double* out, int16_t* out_count) {
+                                    int shard_rank, int shard_count, const float* truth, int prev_truth_index,
+                                    int prev_truth_size, double* out, int16_t* out_count) {
   FM_CHECK(m && vol && vol_dims && halo_pad && fit_pad && pad_value && idx && out && n > 0 && batch > 0,
            FM_EINVAL, "fm_patchwise_predict: bad argument");
   FM_CHECK(shard_count >= 1 && shard_rank >= 0 && shard_rank < shard_count, FM_EINVAL,
            "fm_patchwise_predict: shard %d of %d", shard_rank, shard_count);
   fm_ctx* ctx = m->ctx;
   FM_CUDA(cudaSetDevice(ctx->device));
-  const int32_t patch[3] = {m->spec.X, m->spec.Y, m->spec.Z};
+  const bool is2d = m->kcode == 31;
+  const int nslices = is2d ? m->cin_real - (truth ? prev_truth_size : 0) : m->spec.Z;
+  FM_CHECK(!truth || (is2d && prev_truth_size > 0 && prev_truth_size < m->cin_real), FM_EINVAL,
+           "fm_patchwise_predict: truth conditioning needs a 2D model with in_channels > prev_truth_size");
+  // patch extent in the padded volume and the prediction extent it yields (prediction.py:131-134)
+  const int32_t patch[3] = {m->spec.X, m->spec.Y, nslices};
+  const int32_t pred[3] = {m->spec.X, m->spec.Y, is2d ? 1 : m->spec.Z};
   int32_t out_dims[3];
   for (int a = 0; a < 3; ++a) {
-    FM_CHECK(halo_pad[2 * a] == 0 && halo_pad[2 * a + 1] == 0, FM_EINVAL,
-             "fm_patchwise_predict: 3D models predict the whole patch, halo pad must be 0");
-    out_dims[a] = vol_dims[a] + fit_pad[2 * a] + fit_pad[2 * a + 1];
+    FM_CHECK(halo_pad[2 * a] + halo_pad[2 * a + 1] == patch[a] - pred[a], FM_EINVAL,
+             "fm_patchwise_predict: halo pad on axis %d must total patch - prediction = %d", a, patch[a] - pred[a]);
+    out_dims[a] = vol_dims[a] + fit_pad[2 * a] + fit_pad[2 * a + 1];  // prediction.py:169
   }
   const size_t nv = (size_t)vol_dims[0] * vol_dims[1] * vol_dims[2];
   const size_t nout = (size_t)out_dims[0] * out_dims[1] * out_dims[2];
-  const size_t pv = (size_t)m->vox(0);
+  const size_t pv = (size_t)pred[0] * pred[1] * pred[2];  // predicted voxels per patch
   const int64_t lo = n * shard_rank / shard_count, hi = n * (shard_rank + 1) / shard_count;
   const int64_t nloc = hi - lo;
   batch = (int)std::min<int64_t>(batch, std::max<int64_t>(nloc, 1));
@@ -859,7 +912,7 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
   DevBuf<int32_t>& didx = m->pw_idx;
   DevBuf<double>& dout = m->pw_out;
   DevBuf<int16_t>& dcnt = m->pw_cnt;
-  FM_TRY(dvol.ensure(nv));
+  FM_TRY(dvol.ensure(nv * (truth ? 2 : 1)));
   FM_TRY(dpred.ensure(std::max<size_t>(1, (size_t)nloc) * pv));
   FM_TRY(didx.ensure((size_t)n * 3));
   FM_TRY(dout.ensure(nout));
@@ -867,20 +920,27 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
   // host <-> device through the context's pinned staging buffer (pageable cudaMemcpy runs at a fraction of PCIe)
   void* pin = nullptr;
   const size_t out_bytes = nout * sizeof(double), cnt_bytes = out_count ? nout * sizeof(int16_t) : 0;
-  FM_TRY(fm_ctx_pinned(ctx, std::max(nv * sizeof(float), out_bytes + cnt_bytes), &pin));
+  FM_TRY(fm_ctx_pinned(ctx, std::max(nv * sizeof(float) * (truth ? 2 : 1), out_bytes + cnt_bytes), &pin));
   memcpy(pin, vol, nv * sizeof(float));
-  FM_CUDA(cudaMemcpyAsync(dvol.p, pin, nv * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (truth) memcpy((float*)pin + nv, truth, nv * sizeof(float));
+  FM_CUDA(cudaMemcpyAsync(dvol.p, pin, nv * 4 * (truth ? 2 : 1), cudaMemcpyHostToDevice, ctx->stream));
   FM_CUDA(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
   FM_CUDA(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));
   for (int64_t b0 = lo; b0 < hi; b0 += batch) {
     const int nb = (int)std::min<int64_t>(batch, hi - b0);
+    // 3D: [nb,P0,P1,P2] == the network's [nb,X,Y,Z] input. 2D: [nb,H,W,(slices | truth slices)] channels-last
     FM_TRY(k_gather_patches(ctx, dvol.p, vol_dims, halo_pad, fit_pad, (float)pad_value[0], (float)pad_value[1],
-                            didx.p + b0 * 3, nb, patch, m->x_in.p));
+                            didx.p + b0 * 3, nb, patch, m->x_in.p, is2d ? m->cin_real : 0, 0, 0));
+    if (truth) {
+      const int32_t tpatch[3] = {patch[0], patch[1], prev_truth_size};
+      FM_TRY(k_gather_patches(ctx, dvol.p + nv, vol_dims, halo_pad, fit_pad, 0.f, 0.f, didx.p + b0 * 3, nb, tpatch,
+                              m->x_in.p, m->cin_real, nslices, prev_truth_index));
+    }
     FM_TRY(forward(m, nb));
     FM_CUDA(cudaMemcpyAsync(dpred.p + (size_t)(b0 - lo) * pv, m->prob.p, (size_t)nb * pv * 4,
                             cudaMemcpyDeviceToDevice, ctx->stream));
   }
-  FM_TRY(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, patch, 1, out_dims, dout.p, dcnt.p,
+  FM_TRY(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, pred, 1, out_dims, dout.p, dcnt.p,
                       shard_count == 1 ? 1 : 0));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the H2D staging buffer is reused for the way back
   FM_CUDA(cudaMemcpyAsync(pin, dout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -909,7 +969,7 @@ extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, true));
   const size_t n = (size_t)batch * m->vox(0);
-  FM_TRY(upload(m, x, m->x_in.p, n));
+  FM_TRY(upload(m, x, m->x_in.p, n * m->cin_real));
   FM_TRY(upload(m, t, m->t_in.p, n));
   return train_forward_dev(m, batch);
 }
@@ -978,7 +1038,7 @@ extern "C" int fm_train_step_device(fm_model* m, uint64_t x_dev, uint64_t t_dev,
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, true));
   const size_t n = (size_t)batch * m->vox(0);
-  FM_CUDA(cudaMemcpyAsync(m->x_in.p, (const void*)(uintptr_t)x_dev, n * 4, cudaMemcpyDeviceToDevice,
+  FM_CUDA(cudaMemcpyAsync(m->x_in.p, (const void*)(uintptr_t)x_dev, n * m->cin_real * 4, cudaMemcpyDeviceToDevice,
                           m->ctx->stream));
   FM_CUDA(cudaMemcpyAsync(m->t_in.p, (const void*)(uintptr_t)t_dev, n * 4, cudaMemcpyDeviceToDevice,
                           m->ctx->stream));
@@ -1060,7 +1120,7 @@ extern "C" int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const f
   FM_CUDA(cudaSetDevice(ctx->device));
   OpScratch s(ctx);
   const size_t vox = (size_t)N * X * Y * Z;
-  const int taps = ksize * ksize * ksize, Ct = C1 + C2;
+  const int taps = kext_taps(ksize), Ct = C1 + C2;
   std::vector<float> packed((size_t)Cout * taps * Ct);
   keras_to_packed(w_keras, packed.data(), ksize, Ct, Cout);
   bf16 *dx1 = nullptr, *dx2 = nullptr, *dw = nullptr, *dy = nullptr;

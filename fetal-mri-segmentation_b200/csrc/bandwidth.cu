@@ -56,15 +56,25 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restr
   }
 }
 
+// fp32 [vox][Cin] -> bf16 [vox][Cpad] with zero channel padding (2.5D U-Net input: slices-as-channels)
+__global__ void pad_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t vox, int Cin, int Cpad) {
+  const int64_t total = vox * Cpad;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(g % Cpad);
+    const int64_t v = g / Cpad;
+    out[g] = __float2bfloat16(c < Cin ? __ldg(in + v * Cin + c) : 0.f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // MaxPooling3D((2,2,2)) — Keras call site fetal_net/model/unet3d/unet.py:51 (valid, stride 2)
 // one thread = one pooled voxel x 8 channels (16 B); the two z-children of a window are adjacent
 // in memory so every warp-level request is a run of full 32 B sectors.
 // ---------------------------------------------------------------------------------------------
 __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
-                                     int Y, int Z, int C) {
+                                     int Y, int Z, int C, int pz) {
   const int c8n = C >> 3;
-  const int Xo = X >> 1, Yo = Y >> 1, Zo = Z >> 1;
+  const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
   const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
@@ -84,7 +94,8 @@ __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restric
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dz = 0; dz < 2; ++dz) {
-        const int64_t vi = (((int64_t)n * X + 2 * xo + dx) * Y + 2 * yo + dy) * Z + 2 * zo + dz;
+        if (dz >= pz) continue;
+        const int64_t vi = (((int64_t)n * X + 2 * xo + dx) * Y + 2 * yo + dy) * Z + pz * zo + dz;
         uint4 t = ldg16(x + vi * C + c8 * 8);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
         if (first) {
@@ -108,9 +119,9 @@ __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restric
 // producing conv block: dx = [x>0] * (dskip + [x is the first max of its window] * dy).
 __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                      const bf16* __restrict__ dskip, bf16* __restrict__ dx, int N,
-                                     int X, int Y, int Z, int C, int relu_mask) {
+                                     int X, int Y, int Z, int C, int relu_mask, int pz) {
   const int c8n = C >> 3;
-  const int Xo = X >> 1, Yo = Y >> 1, Zo = Z >> 1;
+  const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
   const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
@@ -127,8 +138,13 @@ __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __r
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
-    vi[k] = (((int64_t)n * X + 2 * xo + ddx) * Y + 2 * yo + ddy) * Z + 2 * zo + ddz;
-    unpack8(ldg16(x + vi[k] * C + c8 * 8), xv[k]);
+    vi[k] = (((int64_t)n * X + 2 * xo + ddx) * Y + 2 * yo + ddy) * Z + pz * zo + ddz;
+    if (ddz < pz) {
+      unpack8(ldg16(x + vi[k] * C + c8 * 8), xv[k]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) xv[k][c] = -INFINITY;  // pz == 1: the z-child does not exist
+    }
   }
   const int64_t vo = (((int64_t)n * Xo + xo) * Yo + yo) * Zo + zo;
   float g8[8];
@@ -148,6 +164,7 @@ __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __r
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
+    if ((k & 1) >= pz) continue;
     float o[8];
     if (dskip != nullptr) {
       unpack8(ldg16(dskip + vi[k] * C + c8 * 8), o);
@@ -168,7 +185,7 @@ __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __r
 // UpSampling3D((2,2,2)) nearest — Keras call site fetal_net/model/unet3d/unet.py:138
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
-                                      int Y, int Z, int C) {
+                                      int Y, int Z, int C, int pz) {
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * X * Y * Z * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,11 +199,12 @@ __global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restri
   const int xx = (int)(r % X);
   const int n = (int)(r / X);
   const uint4 t = ldg16(x + v * C + c8 * 8);
-  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
+  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = pz * Z;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
-    const int64_t vo = (((int64_t)n * X2 + 2 * xx + ddx) * Y2 + 2 * yy + ddy) * Z2 + 2 * z + ddz;
+    if (ddz >= pz) continue;
+    const int64_t vo = (((int64_t)n * X2 + 2 * xx + ddx) * Y2 + 2 * yy + ddy) * Z2 + pz * z + ddz;
     stg16(y + vo * C + c8 * 8, t);
   }
 }
@@ -194,7 +212,7 @@ __global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restri
 // backward: 2^3 sum-pool of dy (fp32 accumulate), optionally masked by ReLU of the coarse activation
 __global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ act,
                                       bf16* __restrict__ dx, int N, int X, int Y, int Z, int C,
-                                      int dyC, int dy_cofs) {
+                                      int dyC, int dy_cofs, int pz) {
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * X * Y * Z * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,14 +225,15 @@ __global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* _
   r /= Y;
   const int xx = (int)(r % X);
   const int n = (int)(r / X);
-  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = 2 * Z;
+  const int X2 = 2 * X, Y2 = 2 * Y, Z2 = pz * Z;
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
-    const int64_t vo = (((int64_t)n * X2 + 2 * xx + ddx) * Y2 + 2 * yy + ddy) * Z2 + 2 * z + ddz;
+    if (ddz >= pz) continue;
+    const int64_t vo = (((int64_t)n * X2 + 2 * xx + ddx) * Y2 + 2 * yy + ddy) * Z2 + pz * z + ddz;
     float f[8];
     unpack8(ldg16(dy + vo * dyC + dy_cofs + c8 * 8), f);
 #pragma unroll
@@ -381,7 +400,7 @@ struct GatherGeom {
 
 __global__ void gather_patches_kernel(const float* __restrict__ vol, GatherGeom gm, float pad0,
                                       float pad1, const int32_t* __restrict__ idx, int64_t n,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, int out_pitch, int out_cofs, int z_shift) {
   const int64_t pv = (int64_t)gm.patch[0] * gm.patch[1] * gm.patch[2];
   const int64_t total = n * pv;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -393,7 +412,7 @@ __global__ void gather_patches_kernel(const float* __restrict__ vol, GatherGeom 
     const int j = (int)(r % gm.patch[1]);
     const int i = (int)(r / gm.patch[1]);
     // coordinate in the fit-padded array -> halo-padded array -> original volume
-    const int c[3] = {idx[pi * 3 + 0] + i, idx[pi * 3 + 1] + j, idx[pi * 3 + 2] + k};
+    const int c[3] = {idx[pi * 3 + 0] + i, idx[pi * 3 + 1] + j, idx[pi * 3 + 2] + k + z_shift};
     float val;
     int h[3], o[3];
     bool in_halo = true, in_vol = true;
@@ -410,7 +429,7 @@ __global__ void gather_patches_kernel(const float* __restrict__ vol, GatherGeom 
       val = pad0;
     else
       val = __ldg(vol + ((int64_t)o[0] * gm.vol[1] + o[1]) * gm.vol[2] + o[2]);
-    out[g] = val;
+    out[((pi * gm.patch[0] + i) * (int64_t)gm.patch[1] + j) * out_pitch + out_cofs + k] = val;
   }
 }
 
@@ -500,42 +519,42 @@ int k_cast_bf16_to_f32(fm_ctx* ctx, const bf16* in, float* out, int64_t n) {
   return FM_OK;
 }
 
-int k_maxpool3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in) {
-  FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % 2 == 0, FM_EINVAL,
+int k_maxpool3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in, int pz) {
+  FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % pz == 0 && (pz == 1 || pz == 2), FM_EINVAL,
            "maxpool3d: need C%%8==0 and even extents (got C=%d %dx%dx%d)", in.C, in.X, in.Y, in.Z);
-  const int64_t total = in.elems() / 64;
+  const int64_t total = in.elems() / (32 * pz);
   ProfScope prof(ctx, "maxpool3d_fwd", 0.0, (double)in.elems() * 2.0 * 1.125);
   maxpool3d_fwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z,
-                                                                     in.C);
+                                                                     in.C, pz);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
 int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dskip, bf16* dx, Dims5 in,
-                    int relu_mask) {
-  FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % 2 == 0, FM_EINVAL,
+                    int relu_mask, int pz) {
+  FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % pz == 0 && (pz == 1 || pz == 2), FM_EINVAL,
            "maxpool3d_bwd: need C%%8==0 and even extents");
-  const int64_t total = in.elems() / 64;
+  const int64_t total = in.elems() / (32 * pz);
   ProfScope prof(ctx, "maxpool3d_bwd", 0.0, (double)in.elems() * 2.0 * (dskip ? 3.125 : 2.125));
   maxpool3d_bwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X,
-                                                                     in.Y, in.Z, in.C, relu_mask);
+                                                                     in.Y, in.Z, in.C, relu_mask, pz);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
-int k_upsample3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in) {
+int k_upsample3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in, int pz) {
   FM_CHECK(in.C % 8 == 0, FM_EINVAL, "upsample3d: need C%%8==0");
   ProfScope prof(ctx, "upsample3d_fwd", 0.0, (double)in.elems() * 2.0 * 9.0);
   upsample3d_fwd_kernel<<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X,
-                                                                               in.Y, in.Z, in.C);
+                                                                               in.Y, in.Z, in.C, pz);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
 int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dims5 coarse, int dy_C,
-                     int dy_cofs) {
+                     int dy_cofs, int pz) {
   FM_CHECK(coarse.C % 8 == 0 && dy_C % 8 == 0 && dy_cofs % 8 == 0, FM_EINVAL,
            "upsample3d_bwd: channel counts must be multiples of 8");
   ProfScope prof(ctx, "upsample3d_bwd", 0.0, (double)coarse.elems() * 2.0 * (act ? 10.0 : 9.0));
   upsample3d_bwd_kernel<<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
-      dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
+      dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs, pz);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -573,9 +592,18 @@ int k_zero(fm_ctx* ctx, void* p, size_t bytes) {
   return FM_OK;
 }
 
+int k_pad_cast(fm_ctx* ctx, const float* in, bf16* out, int64_t vox, int Cin, int Cpad) {
+  ProfScope prof(ctx, "pad_cast", 0.0, (double)vox * (Cin * 4.0 + Cpad * 2.0));
+  pad_cast_kernel<<<grid_for(vox * Cpad, 148 * 32), kThreads, 0, ctx->stream>>>(in, out, vox, Cin, Cpad);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
 int k_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
                      const int32_t halo_pad[6], const int32_t fit_pad[6], float pad0, float pad1,
-                     const int32_t* idx_dev, int64_t n, const int32_t patch[3], float* out) {
+                     const int32_t* idx_dev, int64_t n, const int32_t patch[3], float* out, int out_pitch,
+                     int out_cofs, int z_shift) {
+  if (out_pitch <= 0) out_pitch = patch[2];
   GatherGeom gm;
   for (int a = 0; a < 3; ++a) {
     gm.vol[a] = vol_dims[a];
@@ -588,7 +616,8 @@ int k_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
   const int64_t total = n * (int64_t)patch[0] * patch[1] * patch[2];
   ProfScope prof(ctx, "gather_patches", 0.0, (double)total * 8.0);
   gather_patches_kernel<<<grid_for(total, 148 * 32), kThreads, 0, ctx->stream>>>(vol, gm, pad0, pad1,
-                                                                                idx_dev, n, out);
+                                                                                idx_dev, n, out, out_pitch, out_cofs,
+                                                                                z_shift);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -65,6 +65,12 @@ struct fm_ctx {
 
 int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out);
 
+// Kernel-extent code used by all conv launchers: 3 = 3x3x3, 1 = 1x1x1, 31 = 3x3x1 (Conv2D on a Z = 1 volume:
+// the 2.5D U-Net, fetal_net/model/unet/unet.py:103). Tap index = (kx * kxy + ky) * kz + kzi.
+__host__ __device__ static inline int kext_xy(int kcode) { return kcode == 31 ? 3 : kcode; }
+__host__ __device__ static inline int kext_z(int kcode) { return kcode == 31 ? 1 : kcode; }
+__host__ __device__ static inline int kext_taps(int kcode) { return kext_xy(kcode) * kext_xy(kcode) * kext_z(kcode); }
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -109,14 +115,17 @@ struct Dims5 {
 // bandwidth.cu
 int k_cast_f32_to_bf16(fm_ctx*, const float* in, bf16* out, int64_t n);
 int k_cast_bf16_to_f32(fm_ctx*, const bf16* in, float* out, int64_t n);
-int k_maxpool3d_fwd(fm_ctx*, const bf16* x, bf16* y, Dims5 in);
+// pz = pooling factor along z: 2 (MaxPooling3D / UpSampling3D) or 1 (the 2D layers of the 2.5D U-Net)
+int k_maxpool3d_fwd(fm_ctx*, const bf16* x, bf16* y, Dims5 in, int pz = 2);
 // dx = relu'(x) * ( dskip(optional) + route(dy) ): fused MaxPooling3D backward + skip-gradient add
 int k_maxpool3d_bwd(fm_ctx*, const bf16* x, const bf16* dy, const bf16* dskip, bf16* dx, Dims5 in,
-                    int relu_mask);
-int k_upsample3d_fwd(fm_ctx*, const bf16* x, bf16* y, Dims5 in);
-// dx[v] = (act? act[v]>0 : 1) * sum_{8 children} dy[child]; `in` = coarse dims
+                    int relu_mask, int pz = 2);
+int k_upsample3d_fwd(fm_ctx*, const bf16* x, bf16* y, Dims5 in, int pz = 2);
+// dx[v] = (act? act[v]>0 : 1) * sum_{children} dy[child]; `in` = coarse dims
 int k_upsample3d_bwd(fm_ctx*, const bf16* dy, const bf16* act, bf16* dx, Dims5 coarse,
-                     int dy_C, int dy_cofs);
+                     int dy_C, int dy_cofs, int pz = 2);
+// fp32 [vox][Cin] -> bf16 [vox][Cpad], channels >= Cin zero (first layer of the 2.5D U-Net: 6 -> 16 channels)
+int k_pad_cast(fm_ctx*, const float* in, bf16* out, int64_t vox, int Cin, int Cpad);
 // loss statistics over p,t (fp32): sums[8] (double) = {tp, t, p, tbpb, tb, pb, correct, count}
 int k_dice_sums(fm_ctx*, const float* p, const float* t, int64_t n, double* sums, int accumulate);
 // dL/dz = dL/dp * p (1-p) with global sums (closed form, metrics.py:11-15)
@@ -125,9 +134,12 @@ int k_dice_bwd(fm_ctx*, const float* p, const float* t, const double* sums, int6
 int k_adam(fm_ctx*, float* p, const float* g, float* m, float* v, int64_t n, int iterations,
            float lr);
 int k_zero(fm_ctx*, void* p, size_t bytes);
+// out[(patch voxel (i,j)) * out_pitch + out_cofs + k]: with out_pitch = patch[2], out_cofs = 0 this is the plain
+// [n,P0,P1,P2] gather; the 2.5D path writes the slices and the previous-truth slices as channels of one row
 int k_gather_patches(fm_ctx*, const float* vol, const int32_t vol_dims[3], const int32_t halo_pad[6],
                      const int32_t fit_pad[6], float pad0, float pad1, const int32_t* idx_dev,
-                     int64_t n, const int32_t patch[3], float* out);
+                     int64_t n, const int32_t patch[3], float* out, int out_pitch = 0, int out_cofs = 0,
+                     int z_shift = 0);
 int k_reassemble(fm_ctx*, const float* preds, const int32_t* idx_host, int64_t n_total,
                  int64_t shard_lo, int64_t shard_hi, int64_t pred_base, const int32_t pred_shape[3],
                  int channels, const int32_t out_dims[3], double* out_dev, int16_t* count_dev,

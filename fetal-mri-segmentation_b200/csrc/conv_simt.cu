@@ -38,18 +38,19 @@ __global__ void conv3d_simt_fprop_kernel(const void* __restrict__ x, int x_is_f3
   r /= Y;
   const int xx = (int)(r % X);
   const int n = (int)(r / X);
-  const int pad = K / 2, Ct = C1 + C2, taps = K * K * K;
+  const int Kxy = kext_xy(K), Kz = kext_z(K);
+  const int pad = Kxy / 2, padz = Kz / 2, Ct = C1 + C2, taps = Kxy * Kxy * Kz;
   float acc = bias ? bias[co] : 0.f;
-  for (int kx = 0; kx < K; ++kx) {
+  for (int kx = 0; kx < Kxy; ++kx) {
     const int xi = xx + kx - pad;
     if (xi < 0 || xi >= X) continue;
-    for (int ky = 0; ky < K; ++ky) {
+    for (int ky = 0; ky < Kxy; ++ky) {
       const int yi = yy + ky - pad;
       if (yi < 0 || yi >= Y) continue;
-      for (int kz = 0; kz < K; ++kz) {
-        const int zi = z + kz - pad;
+      for (int kz = 0; kz < Kz; ++kz) {
+        const int zi = z + kz - padz;
         if (zi < 0 || zi >= Z) continue;
-        const int tap = (kx * K + ky) * K + kz;
+        const int tap = (kx * Kxy + ky) * Kz + kz;
         const int64_t vi = (((int64_t)n * X + xi) * Y + yi) * Z + zi;
         const bf16* wr = w + ((int64_t)co * taps + tap) * Ct;
         for (int c = 0; c < C1; ++c) acc += ldx(x, x_is_f32, vi * C1 + c) * __bfloat162float(wr[c]);
@@ -70,7 +71,8 @@ __global__ void conv3d_simt_wgrad_kernel(const void* __restrict__ x, int x_is_f3
                                          const bf16* __restrict__ dy, float* __restrict__ dw, int N,
                                          int X, int Y, int Z, int Cin, int Ct, int cofs, int Cout,
                                          int K, int64_t vox_per_chunk) {
-  const int taps = K * K * K, pad = K / 2;
+  const int Kxy = kext_xy(K), Kz = kext_z(K);
+  const int taps = Kxy * Kxy * Kz, pad = Kxy / 2, padz = Kz / 2;
   const int64_t n_out = (int64_t)Cout * taps * Cin;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t o = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -79,7 +81,7 @@ __global__ void conv3d_simt_wgrad_kernel(const void* __restrict__ x, int x_is_f3
   const int ci = (int)(o % Cin);
   const int tap = (int)((o / Cin) % taps);
   const int co = (int)(o / ((int64_t)Cin * taps));
-  const int kz = tap % K, ky = (tap / K) % K, kx = tap / (K * K);
+  const int kz = tap % Kz, ky = (tap / Kz) % Kxy, kx = tap / (Kz * Kxy);
   const int64_t nvox = (int64_t)N * X * Y * Z;
   const int64_t v0 = (int64_t)blockIdx.y * vox_per_chunk;
   const int64_t v1 = min(nvox, v0 + vox_per_chunk);
@@ -91,7 +93,7 @@ __global__ void conv3d_simt_wgrad_kernel(const void* __restrict__ x, int x_is_f3
     r /= Y;
     const int xx = (int)(r % X);
     const int n = (int)(r / X);
-    const int xi = xx + kx - pad, yi = yy + ky - pad, zi = z + kz - pad;
+    const int xi = xx + kx - pad, yi = yy + ky - pad, zi = z + kz - padz;
     if (xi < 0 || xi >= X || yi < 0 || yi >= Y || zi < 0 || zi >= Z) continue;
     const int64_t vi = (((int64_t)n * X + xi) * Y + yi) * Z + zi;
     acc += __bfloat162float(dy[v * Cout + co]) * ldx(x, x_is_f32, vi * Cin + ci);
@@ -408,7 +410,7 @@ int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2
     return FM_OK;
   }
   const int64_t total = (int64_t)N * X * Y * Z * Cout;
-  ProfScope prof(ctx, "conv3d_simt_fprop", 2.0 * ksize * ksize * ksize * (C1 + C2) * (double)total, 0.0);
+  ProfScope prof(ctx, "conv3d_simt_fprop", 2.0 * kext_taps(ksize) * (C1 + C2) * (double)total, 0.0);
   conv3d_simt_fprop_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(
       x, x_is_f32, x2, w_packed, bias, y, y_f32, N, X, Y, Z, C1, C2, Cout, ksize, relu, mask);
   FM_LAUNCH_OK(ctx);
@@ -418,7 +420,7 @@ int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2
 int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy, float* dw_packed,
                         int N, int X, int Y, int Z, int Cin, int Cin_total, int cin_ofs, int Cout,
                         int ksize) {
-  const int taps = ksize * ksize * ksize;
+  const int taps = kext_taps(ksize);
   const int64_t n_out = (int64_t)Cout * taps * Cin;
   const int64_t nvox = (int64_t)N * X * Y * Z;
   if (x_is_f32 && Cin == 1 && Cin_total == 1 && cin_ofs == 0 && ksize == 3 && (Cout == 16 || Cout == 32)) {

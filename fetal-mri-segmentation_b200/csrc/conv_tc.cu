@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int pad = p.ksize >> 1;
+  const int kxy = kext_xy(p.ksize), kzz = kext_z(p.ksize);
+  const int pad = kxy >> 1, padz = kzz >> 1;
 
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -117,14 +118,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
       m /= p.ty;
       const int ix = m % p.tx;
       const int n = m / p.tx;
-      const int x0 = ix * p.bx - pad, y0 = iy * p.by - pad, z0 = iz * p.bz - pad;
+      const int x0 = ix * p.bx - pad, y0 = iy * p.by - pad, z0 = iz * p.bz - padz;
       for (int s = 0; s < p.nsrc; ++s) {
         const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
         for (int ch = 0; ch < p.nchunks[s]; ++ch) {
           int tap = 0;
-          for (int kx = 0; kx < p.ksize; ++kx)
-            for (int ky = 0; ky < p.ksize; ++ky)
-              for (int kz = 0; kz < p.ksize; ++kz, ++tap) {
+          for (int kx = 0; kx < kxy; ++kx)
+            for (int ky = 0; ky < kxy; ++ky)
+              for (int kz = 0; kz < kzz; ++kz, ++tap) {
                 mbar_wait(empty_bar(stage), ph ^ 1u);
                 mbar_expect_tx_elect(full_bar(stage), tx_bytes);
                 const uint32_t a_dst = smem0 + stage * stage_bytes;
@@ -339,7 +340,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
   const int g_count = min(p.G, p.ngroups - g_first);
   const int mt0 = (int)(((int64_t)p.m_tiles * split) / p.splits);
   const int mt1 = (int)(((int64_t)p.m_tiles * (split + 1)) / p.splits);
-  const int pad = p.ksize >> 1;
+  const int kxy = kext_xy(p.ksize), kzz = kext_z(p.ksize);
+  const int pad = kxy >> 1, padz = kzz >> 1;
   const uint32_t tap_tile_bytes = (uint32_t)kTileM * (uint32_t)p.KC * 2u;
   const uint32_t dy_sub_bytes = (uint32_t)kTileM * (uint32_t)p.NC * 2u;
 
@@ -369,9 +371,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
         mbar_expect_tx_elect(full_bar(stage), (uint32_t)p.g * tap_tile_bytes);
         for (int t = 0; t < p.g; ++t) {
           const int tap = min((g_first + gi) * p.g + t, p.ntaps - 1);  // pad group with a repeat
-          const int dz = tap % p.ksize - pad;
-          const int dy = (tap / p.ksize) % p.ksize - pad;
-          const int dx = tap / (p.ksize * p.ksize) - pad;
+          const int dz = tap % kzz - padz;
+          const int dy = (tap / kzz) % kxy - pad;
+          const int dx = tap / (kzz * kxy) - pad;
           tma_load_5d_elect(smem0 + stage * a_slot + (uint32_t)t * tap_tile_bytes, &p.tmX, full_bar(stage),
                             cc * p.KC, z0 + dz, y0 + dy, x0 + dx, n);
         }
@@ -536,7 +538,7 @@ const int kMaxDynSmem = 227 * 1024;
 }  // namespace
 
 int conv_tc_supported(int C1, int C2, int Cout, int ksize) {
-  if (!(ksize == 1 || ksize == 3)) return 0;
+  if (!(ksize == 1 || ksize == 3 || ksize == 31)) return 0;
   if (!chan_ok(C1)) return 0;
   if (C2 != 0 && !chan_ok(C2)) return 0;
   if (!(Cout == 16 || Cout == 32 || Cout == 64 || (Cout >= 128 && Cout % 128 == 0))) return 0;
@@ -564,7 +566,7 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   p.block_n = std::min(Cout, 128);
   p.n_tiles = Cout / p.block_n;
   p.ksize = ksize;
-  p.ntaps = ksize * ksize * ksize;
+  p.ntaps = kext_taps(ksize);
   p.out_C = out_C;
   p.out_cofs = out_cofs;
   p.relu = relu;
@@ -619,7 +621,7 @@ int k_conv3d_tc_wgrad(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_pack
   p.tz = ceil_div(Z, p.bz);
   p.m_tiles = N * p.tx * p.ty * p.tz;
   p.ksize = ksize;
-  p.ntaps = ksize * ksize * ksize;
+  p.ntaps = kext_taps(ksize);
   p.KC = chunk_of(Cin);
   p.n_cchunks = Cin / p.KC;
   p.g = kTileM / p.KC;

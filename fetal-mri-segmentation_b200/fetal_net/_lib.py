@@ -30,6 +30,11 @@ class UNet3DSpec(ctypes.Structure):
                 ("n_labels", ctypes.c_int32)]
 
 
+class UNet2DSpec(ctypes.Structure):
+    _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("in_channels", ctypes.c_int32),
+                ("depth", ctypes.c_int32), ("n_base_filters", ctypes.c_int32), ("n_labels", ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); exactly the symbols include/fetal_b200.h declares
 SIGNATURES = {
     "fm_ctx_create": (c_int, [c_int, ctypes.POINTER(c_vp)]),
@@ -43,6 +48,7 @@ SIGNATURES = {
     "fm_ctx_profile_count": (c_int, [c_vp]),
     "fm_ctx_profile_get": (c_int, [c_vp, c_int, ctypes.c_char_p, c_dp]),
     "fm_model_create_unet3d": (c_int, [c_vp, ctypes.POINTER(UNet3DSpec), ctypes.POINTER(c_vp)]),
+    "fm_model_create_unet2d": (c_int, [c_vp, ctypes.POINTER(UNet2DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_destroy": (c_int, [c_vp]),
     "fm_model_num_layers": (c_int, [c_vp]),
     "fm_model_layer_info": (c_int, [c_vp, c_int, ctypes.c_char_p, c_i64p]),
@@ -54,7 +60,7 @@ SIGNATURES = {
     "fm_predict": (c_int, [c_vp, c_fp, c_int, c_fp]),
     "fm_patch_plan": (c_int, [c_i32p, c_i32p, c_i32p, c_d, c_i32p, c_i64, c_i64p]),
     "fm_patchwise_predict": (c_int, [c_vp, c_fp, c_i32p, c_i32p, c_i32p, c_dp, c_i32p, c_i64, c_int,
-                                     c_int, c_int, c_dp, c_i16p]),
+                                     c_int, c_int, c_fp, c_int, c_int, c_dp, c_i16p]),
     "fm_reassemble": (c_int, [c_vp, c_fp, c_i32p, c_i64, c_i32p, c_int, c_i32p, c_dp, c_i16p]),
     "fm_gather_patches": (c_int, [c_vp, c_fp, c_i32p, c_i32p, c_i32p, c_dp, c_i32p, c_i64, c_i32p, c_fp]),
     "fm_train_step": (c_int, [c_vp, c_fp, c_fp, c_int, c_f, c_fp]),

@@ -26,17 +26,25 @@ class Model:
     """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
 
     def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
-                 device=None):
+                 device=None, ndim=3):
         lib = _lib.load()
         self._ctx = _lib.get_context(device)
-        in_ch, X, Y, Z = [int(v) for v in input_shape]
-        spec = _lib.UNet3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(n_labels))
+        self.ndim = int(ndim)
         h = _lib.c_vp()
-        _lib.check(lib.fm_model_create_unet3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+        if self.ndim == 3:
+            in_ch, X, Y, Z = [int(v) for v in input_shape]          # channels-first (unet3d/unet.py:9)
+            spec = _lib.UNet3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(n_labels))
+            _lib.check(lib.fm_model_create_unet3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            self.input_shape = (None, in_ch, X, Y, Z)
+            self.output_shape = (None, int(n_labels), X, Y, Z)
+        else:
+            H, W, in_ch = [int(v) for v in input_shape]             # slices-as-channels (unet/unet.py:49-50)
+            spec = _lib.UNet2DSpec(H, W, in_ch, int(depth), int(n_base_filters), int(n_labels))
+            _lib.check(lib.fm_model_create_unet2d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            self.input_shape = (None, H, W, in_ch)
+            self.output_shape = (None, H, W, int(n_labels))
         self._h = h
         self._lib = lib
-        self.input_shape = (None, in_ch, X, Y, Z)
-        self.output_shape = (None, int(n_labels), X, Y, Z)
         self.depth = int(depth)
         self.n_base_filters = int(n_base_filters)
         self.n_labels = int(n_labels)
@@ -47,15 +55,18 @@ class Model:
         if loss_function is not dice_coefficient_loss:
             self.metrics_names.append('dice_coefficient')
         self.stop_training = False
-        self.name = 'unet_model_3d'
+        self.name = 'unet_model_3d' if self.ndim == 3 else 'unet_model_2d'
         # layer table (Keras creation order; Keras would name them conv3d_1..conv3d_N)
         self.layers = []
         for i in range(lib.fm_model_num_layers(h)):
             name = ctypes.create_string_buffer(32)
             info = (ctypes.c_int64 * 5)()
             _lib.check(lib.fm_model_layer_info(h, i, name, info))
-            self.layers.append(dict(index=i, name=name.value.decode(), keras_name="conv3d_%d" % (i + 1),
-                                    cin=int(info[0]), cout=int(info[1]), k=int(info[2])))
+            k = int(info[2]) // 10                                   # 33 / 31 -> 3, 11 -> 1
+            self.layers.append(dict(index=i, name=name.value.decode(),
+                                    keras_name="conv%dd_%d" % (self.ndim, i + 1),
+                                    cin=int(info[0]), cout=int(info[1]), k=k,
+                                    kshape=(k,) * self.ndim + (int(info[0]), int(info[1]))))
 
     def __del__(self):
         try:
@@ -73,7 +84,7 @@ class Model:
         """[kernel_1, bias_1, kernel_2, ...] in Keras layout (k,k,k,Cin,Cout) / (Cout,)."""
         out = []
         for l in self.layers:
-            k = np.empty((l["k"],) * 3 + (l["cin"], l["cout"]), np.float32)
+            k = np.empty(l["kshape"], np.float32)
             b = np.empty((l["cout"],), np.float32)
             _lib.check(self._lib.fm_model_get_weights(self._h, l["index"], _lib.fptr(k), _lib.fptr(b)))
             out += [k, b]
@@ -84,7 +95,7 @@ class Model:
         for l in self.layers:
             k = _lib.f32c(weights[2 * l["index"]])
             b = _lib.f32c(weights[2 * l["index"] + 1])
-            assert k.shape == (l["k"],) * 3 + (l["cin"], l["cout"]), (l["name"], k.shape)
+            assert k.shape == l["kshape"], (l["name"], k.shape)
             assert b.shape == (l["cout"],), (l["name"], b.shape)
             _lib.check(self._lib.fm_model_set_weights(self._h, l["index"], _lib.fptr(k), _lib.fptr(b)))
 
@@ -92,7 +103,7 @@ class Model:
         """Gradients of the last train step (Keras layout) - test hook."""
         out = []
         for l in self.layers:
-            k = np.empty((l["k"],) * 3 + (l["cin"], l["cout"]), np.float32)
+            k = np.empty(l["kshape"], np.float32)
             b = np.empty((l["cout"],), np.float32)
             _lib.check(self._lib.fm_model_get_grads(self._h, l["index"], _lib.fptr(k), _lib.fptr(b)))
             out += [k, b]
@@ -107,9 +118,9 @@ class Model:
         rng = np.random.default_rng(seed)
         ws = []
         for l in self.layers:
-            rf = l["k"] ** 3
+            rf = l["k"] ** self.ndim
             limit = np.sqrt(6.0 / (rf * l["cin"] + rf * l["cout"]))
-            ws.append(rng.uniform(-limit, limit, size=(l["k"],) * 3 + (l["cin"], l["cout"])).astype(np.float32))
+            ws.append(rng.uniform(-limit, limit, size=l["kshape"]).astype(np.float32))
             ws.append(np.zeros((l["cout"],), np.float32))
         self.set_weights(ws)
 
@@ -119,8 +130,7 @@ class Model:
         for l, (k, b) in zip(self.layers, zip(*[iter(self.get_weights())] * 2)):
             arrays[l["keras_name"] + "/kernel:0"] = k
             arrays[l["keras_name"] + "/bias:0"] = b
-        arrays["__config__"] = np.array([self.input_shape[1], self.input_shape[2], self.input_shape[3],
-                                         self.input_shape[4], self.depth, self.n_base_filters, self.n_labels])
+        arrays["__config__"] = np.array(list(self.input_shape[1:]) + [self.depth, self.n_base_filters, self.n_labels])
         with open(path, "wb") as f:   # keep the caller's file name (e.g. '...-epoch01-loss-0.5.h5')
             np.savez(f, **arrays)
 
@@ -139,9 +149,8 @@ class Model:
     # ---- inference -------------------------------------------------------------------------
     def predict(self, x, batch_size=32, verbose=0):
         x = _lib.f32c(x)
-        assert x.ndim == 5 and x.shape[1:] == self.input_shape[1:], \
-            "expected [B,%s], got %s" % (self.input_shape[1:], x.shape)
-        out = np.empty((x.shape[0], self.n_labels) + x.shape[2:], np.float32)
+        assert x.shape[1:] == self.input_shape[1:], "expected [B,%s], got %s" % (self.input_shape[1:], x.shape)
+        out = np.empty((x.shape[0],) + self.output_shape[1:], np.float32)
         for b0 in range(0, x.shape[0], batch_size):
             xb = x[b0:b0 + batch_size]
             yb = out[b0:b0 + batch_size]
@@ -156,7 +165,7 @@ class Model:
     def train_on_batch(self, x, y, **kw):
         self._check_loss()
         x, y = _lib.f32c(x), _lib.f32c(y)
-        assert x.shape[0] == y.shape[0] and x.shape[2:] == y.shape[2:]
+        assert x.shape[1:] == self.input_shape[1:] and y.shape == (x.shape[0],) + self.output_shape[1:], (x.shape, y.shape)
         m = np.zeros(4, np.float32)
         _lib.check(self._lib.fm_train_step(self._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]),
                                            float(self.optimizer.lr), _lib.fptr(m)))
@@ -224,12 +233,12 @@ class Model:
         print_fn("%-10s %-12s %6s %6s %3s %10s" % ("layer", "keras name", "Cin", "Cout", "k", "params"))
         for l in self.layers:
             print_fn("%-10s %-12s %6d %6d %3d %10d" % (l["name"], l["keras_name"], l["cin"], l["cout"], l["k"],
-                                                       l["k"] ** 3 * l["cin"] * l["cout"] + l["cout"]))
+                                                       l["k"] ** self.ndim * l["cin"] * l["cout"] + l["cout"]))
         print_fn("Total params: %d" % self.count_params())
 
     def to_json(self):
         import json
-        return json.dumps(dict(class_name="unet_model_3d", input_shape=self.input_shape[1:], depth=self.depth,
+        return json.dumps(dict(class_name=self.name, input_shape=self.input_shape[1:], depth=self.depth,
                                n_base_filters=self.n_base_filters, n_labels=self.n_labels))
 
 
@@ -250,3 +259,23 @@ def unet_model_3d(input_shape, pool_size=(2, 2, 2), n_labels=1, initial_learning
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
                  device=kargs.get("device"))
+
+
+def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_rate=0.00001, deconvolution=False,
+                  depth=4, n_base_filters=32, include_label_wise_dice_coefficients=False,
+                  batch_normalization=False, activation_name="sigmoid", loss_function=dice_coefficient_loss,
+                  dropout_rate=0, **kargs):
+    """Same signature and defaults as the reference 2D / 2.5D builder (fetal_net/model/unet/unet.py:22-25):
+    `input_shape=(H, W, D)` with the slices (and previous-slice truth) as channels."""
+    if tuple(pool_size) != (2, 2):
+        raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2)" % (pool_size,))
+    if deconvolution or batch_normalization:
+        raise NotImplementedError("deconvolution / batch_normalization are on the §8 'next' list")
+    if activation_name != "sigmoid":
+        raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
+    if dropout_rate:
+        raise NotImplementedError("SpatialDropout2D (dropout_rate > 0) is not built; the shipped config uses 0 "
+                                  "(fetal/config_utils.py:151)")
+    return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
+                 initial_learning_rate=initial_learning_rate, loss_function=loss_function,
+                 device=kargs.get("device"), ndim=2)

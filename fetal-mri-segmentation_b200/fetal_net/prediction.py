@@ -89,8 +89,6 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
     for the caller to reduce — see fetal_net.distributed.sharded_patch_wise_prediction."""
     if permute:
         raise NotImplementedError("permute=True (48-permutation TTA, prediction.py:364-369) is on the §8 'next' list")
-    if truth_data is not None:
-        raise NotImplementedError("truth_data / prev_truth conditioning belongs to the 2.5D path (§8 'next')")
     lib = _lib.load()
     data = np.asarray(data)
     assert data.ndim == 4 and data.shape[0] == 1, "data must be [1,X,Y,Z] (prediction.py:296)"
@@ -107,28 +105,57 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
     # int16 map only travels back when the caller has to divide after a cross-rank reduce
     cnt = np.empty(g["out_dims"], np.int16) if count > 1 else None
 
-    if isinstance(model, Model) and g["is3d"]:
-        assert tuple(g["patch_shape"]) == tuple(model.input_shape[2:]), \
-            "patch_shape %s != model input %s" % (g["patch_shape"], model.input_shape[2:])
+    if isinstance(model, Model):
+        truth = None
+        if g["is3d"]:
+            assert tuple(g["patch_shape"]) == tuple(model.input_shape[2:]), \
+                "patch_shape %s != model input %s" % (g["patch_shape"], model.input_shape[2:])
+            assert truth_data is None, "truth_data conditions the 2.5D model only"
+        else:
+            n_truth = int(prev_truth_size) if truth_data is not None else 0
+            assert tuple(g["patch_shape"][:2]) == tuple(model.input_shape[1:3]) and \
+                g["patch_shape"][2] + n_truth == model.input_shape[3], \
+                "patch_shape %s (+%d truth slices) != model input %s" % (g["patch_shape"], n_truth, model.input_shape[1:])
+            if truth_data is not None:
+                truth = _lib.f32c(np.asarray(truth_data)[0])
+                assert truth.shape == vol.shape
         _lib.check(lib.fm_patchwise_predict(model._h, _lib.fptr(vol), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
                                             _lib.i32ptr(fit), _lib.dptr(padv), _lib.i32ptr(idx), len(idx),
-                                            int(batch_size), rank, count, _lib.dptr(out), _lib.i16ptr(cnt)))
+                                            int(batch_size), rank, count, _lib.fptr(truth),
+                                            int(prev_truth_index or 0), int(prev_truth_size or 0),
+                                            _lib.dptr(out), _lib.i16ptr(cnt)))
     else:
-        if not g["is3d"]:
-            raise NotImplementedError("2D / 2.5D models (unet_model_2d) are on the §8 'next' list")
+        # any other Keras-like model: patches are gathered on the device, the model predicts wherever it
+        # lives, the overlap-add / average runs on the device again
         ctx = _lib.get_context()
         lo, hi = len(idx) * rank // count, len(idx) * (rank + 1) // count
         ps = g["patch_shape"]
         preds = np.empty((hi - lo,) + tuple(g["prediction_shape"]) + (g["channels"],), np.float32)
         patch_i32 = _lib.i32x(ps)
+        truth = None if truth_data is None else _lib.f32c(np.asarray(truth_data)[0])
+        zero_pad = np.zeros(2, np.float64)
         for b0 in range(lo, hi, batch_size):
             bi = np.ascontiguousarray(idx[b0:min(b0 + batch_size, hi)])
             batch = np.empty((len(bi),) + tuple(ps), np.float32)
             _lib.check(lib.fm_gather_patches(ctx.handle, _lib.fptr(vol), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
                                              _lib.i32ptr(fit), _lib.dptr(padv), _lib.i32ptr(bi), len(bi),
                                              _lib.i32ptr(patch_i32), _lib.fptr(batch)))
-            p = predict(model, batch[:, None], permute=False)          # [B,C,x,y,z]
-            preds[b0 - lo:b0 - lo + len(bi)] = np.asarray(p, np.float32).transpose(0, 2, 3, 4, 1)
+            if truth is not None:
+                # prediction.py:106-110: truth slices [z + prev_truth_index, +prev_truth_size) as extra channels
+                ti = bi.copy()
+                ti[:, 2] += int(prev_truth_index)
+                tps = _lib.i32x(list(ps[:2]) + [int(prev_truth_size)])
+                tb = np.empty((len(bi),) + tuple(ps[:2]) + (int(prev_truth_size),), np.float32)
+                _lib.check(lib.fm_gather_patches(ctx.handle, _lib.fptr(truth), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
+                                                 _lib.i32ptr(fit), _lib.dptr(zero_pad), _lib.i32ptr(ti), len(ti),
+                                                 _lib.i32ptr(tps), _lib.fptr(tb)))
+                batch = np.concatenate([batch, tb], axis=-1)
+            if g["is3d"]:
+                p = predict(model, batch[:, None], permute=False)          # [B,C,x,y,z]
+                preds[b0 - lo:b0 - lo + len(bi)] = np.asarray(p, np.float32).transpose(0, 2, 3, 4, 1)
+            else:
+                p = predict(model, batch, permute=False)                   # [B,H,W,C]
+                preds[b0 - lo:b0 - lo + len(bi)] = np.expand_dims(np.asarray(p, np.float32), -2)   # prediction.py:184
         if count == 1:
             _lib.check(lib.fm_reassemble(ctx.handle, _lib.fptr(preds), _lib.i32ptr(idx), len(idx),
                                          _lib.i32ptr(_lib.i32x(g["prediction_shape"])), g["channels"],

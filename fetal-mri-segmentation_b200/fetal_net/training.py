@@ -155,8 +155,9 @@ def load_old_model(model_file, verbose=True, config=None):
     if config is not None:
         loss = getattr(_metrics, config.get('loss', 'dice_coefficient_loss'))
         lr = config.get('initial_learning_rate', lr)
-    m = _model_ns.unet_model_3d(input_shape=tuple(cfg[0:4]), depth=cfg[4], n_base_filters=cfg[5], n_labels=cfg[6],
-                                initial_learning_rate=lr, loss_function=loss)
+    builder = _model_ns.unet_model_3d if len(cfg) == 7 else _model_ns.unet_model_2d   # (C,X,Y,Z) vs (H,W,D)
+    m = builder(input_shape=tuple(cfg[:-3]), depth=cfg[-3], n_base_filters=cfg[-2], n_labels=cfg[-1],
+                initial_learning_rate=lr, loss_function=loss)
     m.load_weights(model_file)
     return m
 

@@ -76,10 +76,26 @@ typedef struct fm_unet3d_spec {
 int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out);
 int fm_model_destroy(fm_model* m);
 
+/* Builder spec of the 2D / "2.5D" U-Net. Replaces the kwargs of unet_model_2d
+ * (fetal_net/model/unet/unet.py:22-25): input_shape=(H,W,in_channels) with the slices (and the previous-slice
+ * truth, fetal_net/generator.py:305-306) as channels; Permute + Conv2D/MaxPooling2D/UpSampling2D stack. */
+typedef struct fm_unet2d_spec {
+  int32_t H, W;           /* each divisible by 2^(depth-1)                          */
+  int32_t in_channels;    /* patch_depth (+ prev_truth_size), 1..16                 */
+  int32_t depth;          /* default 4                                              */
+  int32_t n_base_filters; /* default 32                                             */
+  int32_t n_labels;       /* 1                                                      */
+} fm_unet2d_spec;
+
+/* Replaces: unet_model_2d(...) + model.compile (fetal_net/model/unet/unet.py:49-88). Input [B,H,W,in_channels],
+ * output [B,H,W,n_labels] (the Permute((3,1,2)) / Permute((2,3,1)) pair of the reference is a layout no-op here:
+ * device tensors are channels-last). All entry points below accept either model kind. */
+int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec, fm_model** out);
+
 /* Layer table, Keras creation order (conv3d_1 ... conv3d_15). */
 int fm_model_num_layers(fm_model* m);
-/* info[0]=cin, info[1]=cout, info[2]=kernel extent (3 or 1), info[3]=param offset of kernel,
- * info[4]=param offset of bias (offsets into the flat fp32 parameter buffer). */
+/* info[0]=cin, info[1]=cout, info[2]=kernel extent code (33: 3x3x3, 31: 3x3, 11: 1x1[x1]), info[3]=param offset
+ * of kernel, info[4]=param offset of bias (offsets into the flat fp32 parameter buffer). */
 int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_t info[5]);
 int64_t fm_model_num_params(fm_model* m);
 
@@ -107,23 +123,26 @@ int fm_predict(fm_model* m, const float* x, int batch, float* y);
 int fm_patch_plan(const int32_t padded[3], const int32_t patch[3], const int32_t pred[3],
                   double overlap_factor, int32_t* out_idx, int64_t cap, int64_t* out_n);
 
-/* Replaces the body of patch_wise_prediction for 3D models (fetal_net/prediction.py:161-210):
- * gather patches from the (virtually padded) volume, run the network, overlap-add in float64 in
- * patch order, divide by the int count. `vol` is the UNPADDED float32 volume [X,Y,Z] (host);
- * padding is virtual: `halo_pad` = {before,after} x 3 axes of the first np.pad
- * (prediction.py:138-141, filled with pad_value[0]) and `fit_pad` likewise for pad_for_fit
- * (prediction.py:142-146, filled with pad_value[1]). 3D models predict the whole patch, so
- * halo_pad must be all zero here. `idx` are the n patch corners from fm_patch_plan (coordinates in
- * the padded volume). `out` receives float64 [X+fit, Y+fit, Z+fit, n_labels] (host) - the caller
- * crops pad_for_fit (prediction.py:198-207). `batch` = patches per network launch (reference
- * default 5; the result is batch-invariant).
- * `shard_rank`/`shard_count`: this rank handles patches [rank*n/count, (rank+1)*n/count) and
- * `out` then holds the partial SUM (not divided) when shard_count > 1; use shard 0 of 1 for the
- * single-GPU drop-in. `out_count` (int16, same extent, may be NULL) receives the full count map. */
+/* Replaces the body of patch_wise_prediction (fetal_net/prediction.py:161-210): gather patches from the
+ * (virtually padded) volume, run the network, overlap-add in float64 in patch order, divide by the int count.
+ * `vol` is the UNPADDED float32 volume [X,Y,Z] (host); padding is virtual: `halo_pad` = {before,after} x 3 axes
+ * of the first np.pad (prediction.py:138-141, filled with pad_value[0]) and `fit_pad` likewise for pad_for_fit
+ * (prediction.py:142-146, filled with pad_value[1]). 3D models predict the whole patch (halo_pad all zero);
+ * 2D models take patches (H, W, patch_depth), predict (H, W, 1) and need the z halo (ceil,floor)((patch_depth-1)/2).
+ * `idx` are the n patch corners from fm_patch_plan (coordinates in the padded volume).
+ * `truth` (host float32 [X,Y,Z], may be NULL): previous-slice conditioning of the 2.5D path — the slices
+ * [z + prev_truth_index, +prev_truth_size) of the identically padded (with 0) truth volume are appended as input
+ * channels (prediction.py:106-110,148-156).
+ * `out` receives float64 [X+fit, Y+fit, Z+fit, n_labels] (host) - the caller crops pad_for_fit
+ * (prediction.py:198-207). `batch` = patches per network launch (reference default 5; result is batch-invariant).
+ * `shard_rank`/`shard_count`: this rank handles patches [rank*n/count, (rank+1)*n/count) and `out` then holds
+ * the partial SUM (not divided) when shard_count > 1; use shard 0 of 1 for the single-GPU drop-in.
+ * `out_count` (int16, same extent, may be NULL) receives the full count map. */
 int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t vol_dims[3],
                          const int32_t halo_pad[6], const int32_t fit_pad[6],
                          const double pad_value[2], const int32_t* idx, int64_t n, int batch,
-                         int shard_rank, int shard_count, double* out, int16_t* out_count);
+                         int shard_rank, int shard_count, const float* truth, int prev_truth_index,
+                         int prev_truth_size, double* out, int16_t* out_count);
 
 /* Reassembly alone (test hook for bit-exactness): `preds` float32 [n,P0,P1,P2,C] (host) are
  * overlap-added exactly as fetal_net/prediction.py:188-193,210 does. */

@@ -150,6 +150,25 @@ def keras_adam_step(p, g, m, v, iterations, lr, beta_1=0.9, beta_2=0.999, eps=1e
     p[...] = p - np.float32(lr_t) * m / (np.sqrt(v) + np.float32(eps))
 
 
+def train_step(forward_fn, x, t, w, adam_state, lr, dtype=torch.float32):
+    """Generic fwd + Dice + bwd + Keras-Adam for any of the forward restatements (used for unet2d_forward)."""
+    names = sorted(w.keys())
+    params = {n: torch.tensor(w[n], dtype=dtype, requires_grad=True) for n in names}
+    xt, tt = torch.as_tensor(x).to(dtype), torch.as_tensor(t).to(dtype)
+    p = forward_fn(xt, params)
+    loss = dice_coefficient_loss(tt, p)
+    loss.backward()
+    out = {"loss": float(loss.detach()), "grads": {}, "pred": p.detach().numpy()}
+    it = adam_state.setdefault("iterations", 0)
+    for n in names:
+        g = params[n].grad.detach().to(torch.float32).numpy()
+        out["grads"][n] = g
+        keras_adam_step(w[n], g, adam_state.setdefault("m/" + n, np.zeros_like(w[n])),
+                        adam_state.setdefault("v/" + n, np.zeros_like(w[n])), it, lr)
+    adam_state["iterations"] = it + 1
+    return out
+
+
 def unet3d_train_step(x, t, w, adam_state, lr, depth=4, dtype=torch.float32, quant=None):
     """One fwd + Dice loss + bwd + Keras-Adam update. Mutates w/adam_state. Returns dict of scalars+grads.
     `quant` (e.g. a bf16 round trip) is applied to stored activations/weights in the forward pass; autograd

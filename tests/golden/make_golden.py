@@ -38,6 +38,23 @@ def ramp_model(patch_shape, channels=1):
     return fn, (None, channels) + tuple(patch_shape)
 
 
+def ramp_model_2d(hw, n_in):
+    """2D / 2.5D fake model: predict(batch[B,H,W,n_in]) -> float32 [B,H,W,1]; a fixed-order float32 combination
+    of all input channels (slices and previous-truth slices), position dependent."""
+    h, w = hw
+    g = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    ramp = ((1.0 + (g[0] * 3 + g[1] * 5) % 13).astype(np.float32) / np.float32(16.0))[None, :, :, None]
+
+    def fn(batch):
+        b = np.asarray(batch).astype(np.float32)
+        acc = np.zeros(b.shape[:3] + (1,), np.float32)
+        for c in range(n_in):                                       # fixed summation order
+            acc = (acc + b[..., c:c + 1] * np.float32(0.25 * (c + 1))).astype(np.float32)
+        return (acc * ramp + np.float32(0.125) * ramp).astype(np.float32)
+
+    return fn, (None, h, w, 1)
+
+
 def sha16(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
 
@@ -108,6 +125,31 @@ def main():
         fx["run/%s/batch" % name] = np.int64(bs)
         fx["run/%s/channels" % name] = np.int64(ch)
         fx["run/%s/out" % name] = out                                 # float64 [X,Y,Z,C]
+
+    # ---- (3b) 2D / 2.5D runs (prediction.py:131-141: prediction_shape (H,W,1), z halo (ceil,floor)((D-1)/2)),
+    #           with and without previous-slice truth conditioning (prediction.py:106-110,148-156)
+    run2d = [
+        # name, volume shape, patch (H,W,D), overlap_factor, batch, prev_truth_index, prev_truth_size
+        ("s2d_plain", (1, 24, 20, 9), (16, 16, 5), 0.5, 5, None, None),
+        ("s2d_truth1", (1, 24, 20, 9), (16, 16, 5), 0.5, 4, 1, 1),
+        ("s2d_truth2", (1, 16, 16, 7), (16, 16, 3), 0.0, 3, 0, 2),
+        ("s2d_fit", (1, 12, 20, 6), (16, 16, 5), 0.7, 5, 1, 1),          # x needs pad_for_fit
+    ]
+    for name, vshape, patch, f, bs, pti, pts in run2d:
+        rng = np.random.default_rng(sum(map(ord, name)))
+        vol = rng.standard_normal(vshape).astype(np.float32)
+        truth = (rng.random(vshape) < 0.4).astype(np.float32) if pts else None
+        fn, oshape = ramp_model_2d(patch[:2], patch[2] + (pts or 0))
+        out = pred.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch_shape=patch, overlap_factor=f,
+                                         batch_size=bs, truth_data=truth, prev_truth_index=pti, prev_truth_size=pts)
+        fx["run2d/%s/vol" % name] = vol
+        if truth is not None:
+            fx["run2d/%s/truth" % name] = truth
+        fx["run2d/%s/patch" % name] = np.array(patch, np.int64)
+        fx["run2d/%s/f" % name] = np.float64(f)
+        fx["run2d/%s/batch" % name] = np.int64(bs)
+        fx["run2d/%s/prev" % name] = np.array([-1 if pti is None else pti, 0 if pts is None else pts], np.int64)
+        fx["run2d/%s/out" % name] = out
 
     # ---- (4) get_patch_from_3d_data incl. the out-of-bounds edge-pad branch (patches.py:57-91)
     rng = np.random.default_rng(7)

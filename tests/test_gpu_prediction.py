@@ -9,7 +9,7 @@ import torch
 from oracle import prediction_oracle as po
 from oracle import unet_oracle as uo
 from oracle.ref_harness import FunctionModel
-from tests.golden.make_golden import ramp_model
+from tests.golden.make_golden import ramp_model, ramp_model_2d
 
 pytestmark = pytest.mark.gpu
 
@@ -35,6 +35,25 @@ def test_golden_runs_bit_exact(golden, ctx):
         ref = golden["run/%s/out" % name]
         assert out.dtype == np.float64 and out.shape == ref.shape, name
         assert np.array_equal(out, ref), (name, float(np.abs(out - ref).max()))
+
+
+def test_golden_2d_and_truth_runs_bit_exact(golden, ctx):
+    """2D / 2.5D path of patch_wise_prediction incl. previous-slice truth conditioning (prediction.py:106-110)."""
+    from fetal_net.prediction import patch_wise_prediction
+    names = sorted({k.split("/")[1] for k in golden if k.startswith("run2d/")})
+    for name in names:
+        vol = golden["run2d/%s/vol" % name]
+        patch = tuple(int(v) for v in golden["run2d/%s/patch" % name])
+        pti, pts = [int(v) for v in golden["run2d/%s/prev" % name]]
+        truth = golden.get("run2d/%s/truth" % name)
+        fn, oshape = ramp_model_2d(patch[:2], patch[2] + pts)
+        out = patch_wise_prediction(FunctionModel(fn, oshape), vol, patch_shape=patch,
+                                    overlap_factor=float(golden["run2d/%s/f" % name]),
+                                    batch_size=int(golden["run2d/%s/batch" % name]), truth_data=truth,
+                                    prev_truth_index=pti if truth is not None else None,
+                                    prev_truth_size=pts if truth is not None else None)
+        ref = golden["run2d/%s/out" % name]
+        assert out.shape == ref.shape and np.array_equal(out, ref), (name, float(np.abs(out - ref).max()))
 
 
 def test_cfg1_count_map_bit_exact(golden, ctx):
@@ -128,3 +147,71 @@ def test_sharded_partial_sums_add_up(native):
     cnt = parts[0][1]
     assert all(np.array_equal(cnt, p[1]) for p in parts)
     assert np.array_equal(s / cnt[..., None], full)
+
+
+# ---- native 2D / 2.5D model ----------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def native2d():
+    from fetal_net.model import unet_model_2d
+    layers = uo.unet2d_layers(4, 32, 6)
+    w = uo.glorot_uniform_weights(layers, seed=4, ndim=2)
+    rng = np.random.default_rng(5)
+    for k in w:
+        w[k] = (w[k] * np.sqrt(2.0) * 1.15).astype(np.float32) if k.endswith("/kernel") else \
+            (0.05 * rng.standard_normal(w[k].shape)).astype(np.float32)
+    m = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=32, depth=4)
+    m.set_named_weights(w)
+    return m, w
+
+
+def test_unet2d_forward_matches_oracle(native2d):
+    model, w = native2d
+    assert model.count_params() == 5441569
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 32, 32, 6)).astype(np.float32)
+    p = model.predict(x)
+    assert p.shape == (3, 32, 32, 1)
+    with torch.no_grad():
+        ref = uo.unet2d_forward(torch.as_tensor(x), w).numpy()
+    logit = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    rel = np.linalg.norm(logit(p) - logit(ref)) / np.linalg.norm(logit(ref))
+    assert rel <= 0.03 and np.abs(p - ref).mean() <= 0.006, (rel, np.abs(p - ref).mean())
+    assert np.array_equal(model.predict(x[1:2]), p[1:2])      # batch invariance / determinism
+
+
+def test_unet2d_train_step_matches_oracle(native2d):
+    from fetal_net.model import unet_model_2d
+    _, w0 = native2d
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 32, 32, 6)).astype(np.float32)
+    t = (rng.random((2, 32, 32, 1)) < 0.3).astype(np.float32)
+    model = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=32, depth=4, initial_learning_rate=1e-4)
+    model.set_named_weights(w0)
+    ref = uo.train_step(uo.unet2d_forward, x, t, {k: v.copy() for k, v in w0.items()}, {}, 1e-4)
+    got = model.train_on_batch(x, t)
+    assert got[0] == pytest.approx(ref["loss"], abs=3e-3), (got, ref["loss"])
+    grads = model.get_gradients()
+    bad = []
+    for l, gk in zip(model.layers, grads[0::2]):
+        r = ref["grads"][l["name"] + "/kernel"].astype(np.float64).ravel()
+        g = gk.astype(np.float64).ravel()
+        cos = float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
+        if cos < (0.95 if l["name"] in ("enc0a", "enc0b") else 0.99):
+            bad.append((l["name"], cos))
+    assert not bad, bad
+
+
+def test_native_2d_pipeline_with_truth_equals_own_predict_plus_oracle_reassembly(native2d):
+    """config 4 shape class: 5 slices + 1 previous-truth slice as channels, z-step 1, z halo (2,2)."""
+    from fetal_net.prediction import patch_wise_prediction
+    model, _ = native2d
+    rng = np.random.default_rng(6)
+    vol = rng.standard_normal((1, 48, 32, 10)).astype(np.float32)
+    truth = (rng.random(vol.shape) < 0.4).astype(np.float32)
+    out = patch_wise_prediction(model, vol, patch_shape=(32, 32, 5), overlap_factor=0.5, batch_size=7,
+                                truth_data=truth, prev_truth_index=1, prev_truth_size=1)
+    ref = po.patch_wise_prediction(model, vol, (32, 32, 5), overlap_factor=0.5, batch_size=7, truth_data=truth,
+                                   prev_truth_index=1, prev_truth_size=1)
+    assert out.shape == (48, 32, 10, 1) and out.dtype == np.float64
+    assert np.array_equal(out, ref), float(np.abs(out - ref).max())

@@ -11,7 +11,7 @@ from oracle import prediction_oracle as po
 from oracle import unet_oracle as uo
 from oracle.ref_harness import FunctionModel, reference_available
 
-from tests.golden.make_golden import ramp_model
+from tests.golden.make_golden import ramp_model, ramp_model_2d
 
 
 def sha16(a):
@@ -62,6 +62,23 @@ def test_patchwise_oracle_matches_golden(golden):
         ref = golden["run/%s/out" % name]
         assert out.dtype == np.float64 and out.shape == ref.shape, name
         assert np.array_equal(out, ref), name      # bit-exact
+
+
+def test_patchwise_oracle_2d_and_truth_conditioning_matches_golden(golden):
+    names = sorted({k.split("/")[1] for k in golden if k.startswith("run2d/")})
+    assert len(names) == 4
+    for name in names:
+        vol = golden["run2d/%s/vol" % name]
+        patch = tuple(int(v) for v in golden["run2d/%s/patch" % name])
+        pti, pts = [int(v) for v in golden["run2d/%s/prev" % name]]
+        truth = golden.get("run2d/%s/truth" % name)
+        fn, oshape = ramp_model_2d(patch[:2], patch[2] + pts)
+        out = po.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch,
+                                       overlap_factor=float(golden["run2d/%s/f" % name]),
+                                       batch_size=int(golden["run2d/%s/batch" % name]), truth_data=truth,
+                                       prev_truth_index=pti if truth is not None else None,
+                                       prev_truth_size=pts if truth is not None else None)
+        assert np.array_equal(out, golden["run2d/%s/out" % name]), name
 
 
 def test_extract_patch_matches_golden(golden):
