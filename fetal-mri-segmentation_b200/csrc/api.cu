@@ -173,10 +173,12 @@ struct Layer {
   bf16 *w_mf[2] = {nullptr, nullptr}, *w_md[2] = {nullptr, nullptr};
   bool march_f = false, march_d[2] = {false, false};
   int cin_real = 0;     // true input channels when c1 is zero-padded to 16 (first layer of the 2.5D U-Net)
+  int is_norm = 0;      // InstanceNormalization pseudo-layer of the Isensee net: kernel = gamma, bias = beta (cout each)
+  int stride = 1;       // 2: TF-'SAME' strided conv (Isensee in-convs)
   int cin() const { return c1 + c2; }
   int taps() const { return kext_taps(k); }
   int cin_keras() const { return cin_real ? cin_real : cin(); }
-  int64_t wcount() const { return (int64_t)cout * taps() * cin(); }
+  int64_t wcount() const { return is_norm ? cout : (int64_t)cout * taps() * cin(); }
 };
 
 struct fm_model {
@@ -192,6 +194,12 @@ struct fm_model {
   // activations, allocated for `cap` samples
   int cap = 0;
   bool train_alloc = false;
+  int kind = 0;   // 0: plain U-Net (3D or 2D); 1: Isensee-2017 residual 3D U-Net (forward / inference only)
+  int nseg = 1;   // Isensee: n_segmentation_levels
+  std::vector<DevBuf<bf16>> isIn, isC1, isSum, isUp, isU, isLoc1, isLoc2;
+  std::vector<DevBuf<float>> isSeg;
+  DevBuf<bf16> isRaw;
+  DevBuf<float> isScratch, isAcc;
   int kcode = 3;  // 3: Conv3D 3x3x3 (unet_model_3d); 31: Conv2D 3x3 on a Z = 1 volume (unet_model_2d)
   int pz = 2;     // pooling factor along z
   int cin_real = 1;
@@ -412,6 +420,12 @@ extern "C" int fm_model_destroy(fm_model* m) {
       if (l.w_mf[s]) cudaFree(l.w_mf[s]);
       if (l.w_md[s]) cudaFree(l.w_md[s]);
     }
+  for (auto* v : {&m->isIn, &m->isC1, &m->isSum, &m->isUp, &m->isU, &m->isLoc1, &m->isLoc2})
+    for (auto& b : *v) b.release();
+  for (auto& b : m->isSeg) b.release();
+  m->isRaw.release();
+  m->isScratch.release();
+  m->isAcc.release();
   m->pw_vol.release();
   m->pw_pred.release();
   m->pw_idx.release();
@@ -435,7 +449,7 @@ extern "C" int fm_model_num_layers(fm_model* m) { return m ? (int)m->layers.size
 extern "C" int64_t fm_model_num_params(fm_model* m) {
   if (!m) return -1;
   int64_t n = 0;
-  for (auto& l : m->layers) n += (int64_t)l.cout * l.taps() * l.cin_keras() + l.cout;
+  for (auto& l : m->layers) n += l.is_norm ? 2 * (int64_t)l.cout : (int64_t)l.cout * l.taps() * l.cin_keras() + l.cout;
   return n;
 }
 extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_t info[5]) {
@@ -445,7 +459,7 @@ extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_
   if (info) {
     info[0] = l.cin_keras();
     info[1] = l.cout;
-    info[2] = kext_xy(l.k) * 10 + kext_z(l.k);  // 33: 3x3x3, 31: 3x3(x1), 11: 1x1x1
+    info[2] = l.is_norm ? 0 : kext_xy(l.k) * 10 + kext_z(l.k);  // 33: 3x3x3, 31: 3x3(x1), 11: 1x1x1, 0: norm (gamma, beta)
     info[3] = l.w_off;
     info[4] = l.b_off;
   }
@@ -476,6 +490,12 @@ extern "C" int fm_model_set_weights(fm_model* m, int layer, const float* kernel,
            "fm_model_set_weights: bad argument");
   FM_CUDA(cudaSetDevice(m->ctx->device));
   Layer& l = m->layers[layer];
+  if (l.is_norm) {
+    FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    FM_CUDA(cudaMemcpy(m->params + l.w_off, kernel, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
+    FM_CUDA(cudaMemcpy(m->params + l.b_off, bias, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
+    return FM_OK;
+  }
   std::vector<float> packed((size_t)l.wcount());
   keras_to_packed(kernel, packed.data(), l.k, l.cin_keras(), l.cout, l.cin());
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
@@ -489,7 +509,9 @@ static int get_flat(fm_model* m, const float* flat, int layer, float* kernel, fl
   FM_CUDA(cudaSetDevice(m->ctx->device));
   Layer& l = m->layers[layer];
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
-  if (kernel) {
+  if (kernel && l.is_norm) {
+    FM_CUDA(cudaMemcpy(kernel, flat + l.w_off, (size_t)l.cout * 4, cudaMemcpyDeviceToHost));
+  } else if (kernel) {
     std::vector<float> packed((size_t)l.wcount());
     FM_CUDA(cudaMemcpy(packed.data(), flat + l.w_off, packed.size() * 4, cudaMemcpyDeviceToHost));
     packed_to_keras(packed.data(), kernel, l.k, l.cin_keras(), l.cout, l.cin());
@@ -516,6 +538,7 @@ extern "C" int fm_model_reset_optimizer(fm_model* m) {
 static int refresh_packs(fm_model* m) {
   if (!m->packs_dirty) return FM_OK;
   for (auto& l : m->layers) {
+    if (l.is_norm) continue;
     if (l.k == 1 && l.cout == 1) continue;  // head reads fp32 weights directly
     FM_TRY(k_repack_weights(m->ctx, m->params + l.w_off, l.w_f, l.w_d0, l.c2 ? l.w_d1 : nullptr, l.cout,
                             l.taps(), l.c1, l.c2));
@@ -532,7 +555,13 @@ static int refresh_packs(fm_model* m) {
   return FM_OK;
 }
 
+static int ensure_capacity_isensee(fm_model* m, int B);
+
 static int ensure_capacity(fm_model* m, int B, bool train) {
+  if (m->kind == 1) {
+    FM_CHECK(!train, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
+    return ensure_capacity_isensee(m, B);
+  }
   if (B <= m->cap && (!train || m->train_alloc)) return FM_OK;
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
   const int cap = std::max(B, m->cap);
@@ -592,8 +621,11 @@ static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2,
                              l.cout, l.k, 1, nullptr);
 }
 
+static int forward_isensee(fm_model* m, int B);
+
 // forward pass on x_in (fp32 [B, X, Y, Z], C = 1) -> prob (fp32 [B, X, Y, Z])
 static int forward(fm_model* m, int B) {
+  if (m->kind == 1) return forward_isensee(m, B);
   fm_ctx* ctx = m->ctx;
   const int D = m->depth();
   FM_TRY(refresh_packs(m));
@@ -743,6 +775,224 @@ static void metrics_from_sums(const double s[8], float out[4]) {
 static int upload(fm_model* m, const float* src, float* dst, size_t count) {
   // pageable -> device through the runtime's own staging; callers that care pass pinned memory
   FM_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+  return FM_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Isensee-2017 residual 3D U-Net, forward / inference (fetal_net/model/unet3d/isensee2017.py:39-79):
+// conv block = Conv3D(+bias) -> InstanceNormalization(axis=1) -> LeakyReLU(0.3) (isensee2017.py:12);
+// level: in_conv (stride 2 from level 1, TF 'SAME') -> context module (2 blocks; SpatialDropout3D is
+// identity at inference) -> residual Add; decoder: UpSampling3D -> block -> concat [skip, up] ->
+// localisation module (3^3 block, 1^3 block) -> Conv3D(n_labels, 1) heads summed coarse-to-fine; sigmoid.
+// Layer table in Keras creation order, every conv followed by its norm pseudo-layer (gamma, beta).
+// ---------------------------------------------------------------------------------------------
+extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* spec, fm_model** out) {
+  FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_isensee3d: NULL argument");
+  FM_CHECK(spec->in_channels == 1 && spec->n_labels == 1, FM_EINVAL, "isensee: in_channels and n_labels must be 1");
+  FM_CHECK(spec->depth >= 2 && spec->depth <= 6, FM_EINVAL, "isensee: depth %d unsupported", spec->depth);
+  FM_CHECK(spec->n_base_filters == 16 || spec->n_base_filters == 32, FM_EINVAL, "isensee: n_base_filters 16 or 32");
+  FM_CHECK(spec->n_segmentation_levels >= 1 && spec->n_segmentation_levels <= spec->depth - 1, FM_EINVAL,
+           "isensee: n_segmentation_levels %d out of range", spec->n_segmentation_levels);
+  const int div = 1 << (spec->depth - 1);
+  FM_CHECK(spec->X % div == 0 && spec->Y % div == 0 && spec->Z % div == 0 && spec->X > 0, FM_EINVAL,
+           "isensee: input extent %dx%dx%d must be divisible by 2^(depth-1)=%d", spec->X, spec->Y, spec->Z, div);
+  FM_CUDA(cudaSetDevice(ctx->device));
+  fm_model* m = new fm_model();
+  m->ctx = ctx;
+  m->kind = 1;
+  m->nseg = spec->n_segmentation_levels;
+  m->spec.in_channels = 1;
+  m->spec.X = spec->X;
+  m->spec.Y = spec->Y;
+  m->spec.Z = spec->Z;
+  m->spec.depth = spec->depth;
+  m->spec.n_base_filters = spec->n_base_filters;
+  m->spec.n_labels = 1;
+  const int D = spec->depth, nf = spec->n_base_filters;
+  auto add_conv = [&](const char* fmt, int d, int c1, int c2, int cout, int k, int level, int stride, bool norm) {
+    Layer l;
+    memset(l.name, 0, sizeof(l.name));
+    snprintf(l.name, sizeof(l.name), fmt, d);
+    l.c1 = c1;
+    l.c2 = c2;
+    l.cout = cout;
+    l.k = k;
+    l.level = level;
+    l.stride = stride;
+    l.w_off = m->nparams;
+    m->nparams += l.wcount();
+    l.b_off = m->nparams;
+    m->nparams = (m->nparams + cout + 3) & ~(int64_t)3;
+    m->layers.push_back(l);
+    if (norm) {
+      Layer g;
+      memset(g.name, 0, sizeof(g.name));
+      snprintf(g.name, sizeof(g.name), "%s_norm", l.name);
+      g.is_norm = 1;
+      g.c1 = cout;
+      g.c2 = 0;
+      g.cout = cout;
+      g.k = 1;
+      g.level = level;
+      g.w_off = m->nparams;
+      m->nparams += cout;
+      g.b_off = m->nparams;
+      m->nparams = (m->nparams + cout + 3) & ~(int64_t)3;
+      m->layers.push_back(g);
+    }
+  };
+  int c = 1;
+  for (int l = 0; l < D; ++l) {
+    const int f = nf << l;
+    add_conv("l%d_in", l, c, 0, f, 3, l, l == 0 ? 1 : 2, true);
+    add_conv("l%d_ctx1", l, f, 0, f, 3, l, 1, true);
+    add_conv("l%d_ctx2", l, f, 0, f, 3, l, 1, true);
+    c = f;
+  }
+  for (int l = D - 2; l >= 0; --l) {
+    const int f = nf << l;
+    add_conv("u%d_up", l, c, 0, f, 3, l, 1, true);
+    add_conv("u%d_loc1", l, f, f, f, 3, l, 1, true);  // concat order [skip, up] (isensee2017.py:62)
+    add_conv("u%d_loc2", l, f, 0, f, 1, l, 1, true);
+    c = f;
+    if (l < m->nseg) add_conv("u%d_seg", l, f, 0, 1, 1, l, 1, false);
+  }
+  const size_t pb = (size_t)m->nparams * sizeof(float);
+  FM_CUDA(cudaMalloc((void**)&m->params, pb));
+  FM_CUDA(cudaMemset(m->params, 0, pb));
+  int64_t pack_elems = 0;
+  for (auto& l : m->layers)
+    if (!l.is_norm) pack_elems += (l.wcount() + 63) & ~(int64_t)63;
+  FM_CUDA(cudaMalloc((void**)&m->wpack, (size_t)pack_elems * sizeof(bf16)));
+  FM_CUDA(cudaMemset(m->wpack, 0, (size_t)pack_elems * sizeof(bf16)));
+  bf16* wp = m->wpack;
+  for (auto& l : m->layers) {
+    if (l.is_norm) continue;
+    l.w_f = wp;
+    wp += (l.wcount() + 63) & ~(int64_t)63;
+    if (l.k != 3 || l.c1 < 16 || l.stride != 1) continue;
+    const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
+    const int cs[2] = {l.c1, l.c2};
+    if (use_march() && conv_march_supported(X, Y, Z, l.c1, l.c2, l.cout, l.k)) {
+      l.march_f = true;
+      for (int s = 0; s < (l.c2 ? 2 : 1); ++s)
+        FM_CUDA(cudaMalloc((void**)&l.w_mf[s], (size_t)conv_march_pack_elems(cs[s], l.cout) * sizeof(bf16)));
+    }
+  }
+  m->isIn.resize(D);
+  m->isC1.resize(D);
+  m->isSum.resize(D);
+  m->isUp.resize(D);
+  m->isU.resize(D);
+  m->isLoc1.resize(D);
+  m->isLoc2.resize(D);
+  m->isSeg.resize(D);
+  FM_CUDA(cudaEventCreateWithFlags(&m->ev_tmp, cudaEventDisableTiming));
+  *out = m;
+  return FM_OK;
+}
+
+static int ensure_capacity_isensee(fm_model* m, int B) {
+  if (B <= m->cap) return FM_OK;
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  const int D = m->depth(), nf = m->spec.n_base_filters;
+  const size_t v0 = (size_t)m->vox(0);
+  FM_TRY(m->x_in.ensure((size_t)B * v0));
+  FM_TRY(m->prob.ensure((size_t)B * v0));
+  FM_TRY(m->isAcc.ensure((size_t)B * v0));
+  FM_TRY(m->isRaw.ensure((size_t)B * v0 * nf));
+  FM_TRY(m->isScratch.ensure((size_t)B * (nf << (D - 1)) * 2 * 1026));
+  for (int l = 0; l < D; ++l) {
+    const size_t n = (size_t)B * m->vox(l) * (nf << l);
+    FM_TRY(m->isIn[l].ensure(n));
+    FM_TRY(m->isC1[l].ensure(n));
+    FM_TRY(m->isSum[l].ensure(n));
+    if (l < D - 1) {
+      FM_TRY(m->isUp[l].ensure((size_t)B * m->vox(l) * (nf << (l + 1))));
+      FM_TRY(m->isU[l].ensure(n));
+      FM_TRY(m->isLoc1[l].ensure(n));
+      FM_TRY(m->isLoc2[l].ensure(n));
+      if (l < m->nseg) FM_TRY(m->isSeg[l].ensure((size_t)B * m->vox(l)));
+    }
+  }
+  m->cap = B;
+  return FM_OK;
+}
+
+// one Isensee conv block: Conv3D (+bias) -> raw -> InstanceNorm + LeakyReLU (+ residual add) -> y
+static int isensee_block(fm_model* m, const Layer& l, const Layer& nl, const bf16* x1, const bf16* x2, const bf16* add,
+                         bf16* y, int B) {
+  fm_ctx* ctx = m->ctx;
+  const Dims5 d = m->dims(l.level, l.cout, B);
+  const float* bias = m->params + l.b_off;
+  bf16* raw = m->isRaw.p;
+  if (l.march_f) {
+    FM_TRY(k_conv3d_march(ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, 0,
+                          l.cout, 0));
+  } else if (conv_tc_supported(l.c1, l.c2, l.cout, l.k)) {
+    FM_TRY(k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, l.k, 0,
+                             l.cout, 0, l.stride, d.X * l.stride, d.Y * l.stride, d.Z * l.stride));
+  } else {
+    FM_CHECK(l.stride == 1, FM_EINVAL, "isensee: strided conv %s has no fallback", l.name);
+    FM_TRY(k_conv3d_simt_fprop(ctx, x1, 0, x2, l.w_f, bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, l.k, 0,
+                               nullptr));
+  }
+  return k_instnorm_lrelu(ctx, raw, m->params + nl.w_off, m->params + nl.b_off, add, y, B, m->vox(l.level), l.cout,
+                          m->isScratch.p, m->isScratch.n);
+}
+
+static int forward_isensee(fm_model* m, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int D = m->depth();
+  FM_TRY(refresh_packs(m));
+  auto LI = [&](const char* fmt, int d) {
+    char nm[32];
+    snprintf(nm, sizeof(nm), fmt, d);
+    return layer_index(m, nm);
+  };
+  const bf16* cur = nullptr;
+  for (int l = 0; l < D; ++l) {
+    const int i_in = LI("l%d_in", l), i_c1 = LI("l%d_ctx1", l), i_c2 = LI("l%d_ctx2", l);
+    const Layer &lin = m->layers[i_in], &lc1 = m->layers[i_c1], &lc2 = m->layers[i_c2];
+    if (l == 0) {
+      // Cin = 1: bandwidth kernel, raw output (no activation), then the norm pass
+      const Dims5 d = m->dims(0, lin.cout, B);
+      FM_TRY(k_conv3d_simt_fprop(ctx, m->x_in.p, 1, nullptr, lin.w_f, m->params + lin.b_off, m->isRaw.p, nullptr, B, d.X,
+                                 d.Y, d.Z, 1, 0, lin.cout, 3, 0, nullptr));
+      FM_TRY(k_instnorm_lrelu(ctx, m->isRaw.p, m->params + m->layers[i_in + 1].w_off, m->params + m->layers[i_in + 1].b_off,
+                              nullptr, m->isIn[0].p, B, m->vox(0), lin.cout, m->isScratch.p, m->isScratch.n));
+    } else {
+      FM_TRY(isensee_block(m, lin, m->layers[i_in + 1], cur, nullptr, nullptr, m->isIn[l].p, B));
+    }
+    FM_TRY(isensee_block(m, lc1, m->layers[i_c1 + 1], m->isIn[l].p, nullptr, nullptr, m->isC1[l].p, B));
+    // context output + residual: summation = in_conv + context (isensee2017.py:55)
+    FM_TRY(isensee_block(m, lc2, m->layers[i_c2 + 1], m->isC1[l].p, nullptr, m->isIn[l].p, m->isSum[l].p, B));
+    cur = m->isSum[l].p;
+  }
+  for (int l = D - 2; l >= 0; --l) {
+    const int i_up = LI("u%d_up", l), i_l1 = LI("u%d_loc1", l), i_l2 = LI("u%d_loc2", l);
+    const Layer& lup = m->layers[i_up];
+    FM_TRY(k_upsample3d_fwd(ctx, cur, m->isUp[l].p, m->dims(l + 1, lup.c1, B), 2));
+    FM_TRY(isensee_block(m, lup, m->layers[i_up + 1], m->isUp[l].p, nullptr, nullptr, m->isU[l].p, B));
+    FM_TRY(isensee_block(m, m->layers[i_l1], m->layers[i_l1 + 1], m->isSum[l].p, m->isU[l].p, nullptr, m->isLoc1[l].p, B));
+    FM_TRY(isensee_block(m, m->layers[i_l2], m->layers[i_l2 + 1], m->isLoc1[l].p, nullptr, nullptr, m->isLoc2[l].p, B));
+    cur = m->isLoc2[l].p;
+    if (l < m->nseg) {
+      const Layer& ls = m->layers[LI("u%d_seg", l)];
+      FM_TRY(k_head_fwd(ctx, cur, m->params + ls.w_off, m->params + ls.b_off, m->isSeg[l].p, (int64_t)B * m->vox(l),
+                        ls.c1, 0));
+    }
+  }
+  // deep-supervision sum, coarse to fine (isensee2017.py:68-77), then sigmoid (:79)
+  const float* acc = m->isSeg[m->nseg - 1].p;
+  for (int l = m->nseg - 2; l >= 0; --l) {
+    const Dims5 d = m->dims(l, 1, B);
+    float* dst = (l == 0) ? m->isAcc.p : m->isSeg[l].p;  // in place on the finer map is safe (element-wise)
+    FM_TRY(k_seg_upsample_add(ctx, m->isSeg[l].p, acc, dst, B, d.X, d.Y, d.Z));
+    acc = dst;
+  }
+  FM_TRY(k_sigmoid(ctx, acc, m->prob.p, (int64_t)B * m->vox(0)));
   return FM_OK;
 }
 
@@ -976,6 +1226,7 @@ extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int
 
 extern "C" int fm_train_backward(fm_model* m) {
   FM_CHECK(m, FM_EINVAL, "NULL model");
+  FM_CHECK(m->kind == 0, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
   FM_CHECK(m->fwd_valid, FM_ESTATE, "fm_train_backward called without a preceding fm_train_forward");
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(backward(m, m->last_batch));
@@ -985,6 +1236,7 @@ extern "C" int fm_train_backward(fm_model* m) {
 
 extern "C" int fm_train_apply(fm_model* m, float lr, uint64_t after_stream, float out_metrics[4]) {
   FM_CHECK(m, FM_EINVAL, "NULL model");
+  FM_CHECK(m->kind == 0, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
   fm_ctx* ctx = m->ctx;
   FM_CUDA(cudaSetDevice(ctx->device));
   if (after_stream) {

@@ -249,6 +249,129 @@ __global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* _
   stg16(dx + v * C + c8 * 8, pack8(acc));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNormalization(axis=1) + LeakyReLU(0.3) — keras_contrib layer used by every Isensee conv block
+// (fetal_net/model/unet3d/isensee2017.py:12, unet3d/unet.py:107-111): per (sample, channel) mean / biased
+// variance over the voxels, y = (x - mean) / (sqrt(var) + 1e-3) * gamma + beta   (eps added to the STD).
+// Deterministic two-stage reduction: per-block partial (sum, sum of squares) in fp32 over <= 4096 voxels,
+// combined in fp64 in a fixed order; then one fused normalise + LeakyReLU (+ residual add) pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) instnorm_partial_kernel(const bf16* __restrict__ x, float* __restrict__ part,
+                                                                    int64_t vox_per_sample, int C, int64_t vox_per_block,
+                                                                    int blocks_per_sample) {
+  extern __shared__ float sh[];  // [kThreads][16]
+  const int c8n = C >> 3;
+  const int lanes = kThreads / c8n;
+  const int c8 = threadIdx.x % c8n, l = threadIdx.x / c8n;
+  const int n = blockIdx.y, blk = blockIdx.x;
+  const int64_t v0 = (int64_t)blk * vox_per_block;
+  const int64_t v1 = min(vox_per_sample, v0 + vox_per_block);
+  const bf16* xs = x + (int64_t)n * vox_per_sample * C;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (l < lanes)
+    for (int64_t v = v0 + l; v < v1; v += lanes) {
+      float f[8];
+      unpack8(ldg16(xs + v * C + c8 * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh[threadIdx.x * 16 + i] = s[i];
+    sh[threadIdx.x * 16 + 8 + i] = q[i];
+  }
+  __syncthreads();
+  if (l == 0) {
+    for (int k = 1; k < lanes; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += sh[(k * c8n + c8) * 16 + i];
+        q[i] += sh[(k * c8n + c8) * 16 + 8 + i];
+      }
+    float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + c8 * 8) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[2 * i] = s[i];
+      o[2 * i + 1] = q[i];
+    }
+  }
+}
+
+// scale/shift per (n, c): y = x * scale + shift with scale = gamma / (sqrt(var) + eps), shift = beta - mean * scale
+__global__ void instnorm_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float* __restrict__ ss, int N, int C,
+                                      int blocks_per_sample, double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < blocks_per_sample; ++b) {
+    const float* o = part + (((int64_t)n * blocks_per_sample + b) * C + c) * 2;
+    s += (double)o[0];
+    q += (double)o[1];
+  }
+  const double mean = s * inv_count;
+  const double var = fmax(q * inv_count - mean * mean, 0.0);
+  const double scale = (double)gamma[c] / (sqrt(var) + (double)eps);
+  ss[2 * i] = (float)scale;
+  ss[2 * i + 1] = (float)((double)beta[c] - mean * scale);
+}
+
+__global__ void instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ ss,
+                                      const bf16* __restrict__ add, bf16* __restrict__ y, int64_t vox_per_sample,
+                                      int C, int N, float slope) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)N * vox_per_sample * c8n;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int c8 = (int)(g % c8n);
+  const int64_t v = g / c8n;
+  const int n = (int)(v / vox_per_sample);
+  float f[8], a[8];
+  unpack8(ldg16(x + v * C + c8 * 8), f);
+  const float4* sp = reinterpret_cast<const float4*>(ss + ((int64_t)n * C + c8 * 8) * 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(sp + i);  // (scale, shift) of two channels
+    float u = f[2 * i] * t.x + t.y, w = f[2 * i + 1] * t.z + t.w;
+    f[2 * i] = u > 0.f ? u : slope * u;
+    f[2 * i + 1] = w > 0.f ? w : slope * w;
+  }
+  if (add != nullptr) {
+    unpack8(ldg16(add + v * C + c8 * 8), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += a[i];
+  }
+  stg16(y + v * C + c8 * 8, pack8(f));
+}
+
+// segmentation-head plumbing of the Isensee net (isensee2017.py:68-79): fp32 single-channel maps
+// out[v] = fine[v] + coarse[v >> 1 per axis]   /   p = sigmoid(z)
+__global__ void seg_upsample_add_kernel(const float* __restrict__ fine, const float* __restrict__ coarse,
+                                        float* __restrict__ out, int N, int X, int Y, int Z) {
+  const int64_t total = (int64_t)N * X * Y * Z;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int z = (int)(g % Z);
+  int64_t r = g / Z;
+  const int y = (int)(r % Y);
+  r /= Y;
+  const int x = (int)(r % X);
+  const int n = (int)(r / X);
+  const int64_t vc = (((int64_t)n * (X >> 1) + (x >> 1)) * (Y >> 1) + (y >> 1)) * (Z >> 1) + (z >> 1);
+  out[g] = fine[g] + __ldg(coarse + vc);
+}
+__global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ p, int64_t n) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) p[g] = 1.f / (1.f + __expf(-z[g]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // soft-Dice statistics — fetal_net/metrics.py:11-15 (dice), :18-28 (vod), Keras binary_accuracy
 // deterministic two-stage reduction: per-block partials in double, then one block sums them.
@@ -699,6 +822,42 @@ int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64
 int k_divide_by_count(fm_ctx* ctx, double* out, const int16_t* count, int64_t nvox, int channels) {
   divide_by_count_kernel<<<grid_for(nvox * channels, 148 * 16), kThreads, 0, ctx->stream>>>(
       out, count, nvox, channels);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// x: raw conv output [N][vox][C] bf16 -> y = LeakyReLU(InstanceNorm(x)) (+ add). `scratch` >= N*C*2*(blocks+1) floats.
+int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, const bf16* add, bf16* y,
+                     int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats) {
+  FM_CHECK(C % 8 == 0 && C <= 8 * kThreads, FM_EINVAL, "instnorm: C=%d unsupported", C);
+  int bps = (int)std::min<int64_t>(std::max<int64_t>(1, vox_per_sample / 2048), 1024);
+  const int64_t vpb = ceil_div64(vox_per_sample, bps);
+  bps = (int)ceil_div64(vox_per_sample, vpb);
+  const size_t need = (size_t)N * C * 2 * ((size_t)bps + 1);
+  FM_CHECK(scratch_floats >= need, FM_EINVAL, "instnorm: scratch too small (%zu < %zu floats)", scratch_floats, need);
+  float* part = scratch;
+  float* ss = scratch + (size_t)N * C * 2 * bps;
+  ProfScope prof(ctx, "instnorm_lrelu", 0.0, (double)N * vox_per_sample * C * (add ? 8.0 : 6.0));
+  instnorm_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(x, part, vox_per_sample,
+                                                                                               C, vpb, bps);
+  FM_LAUNCH_OK(ctx);
+  instnorm_final_kernel<<<ceil_div(N * C, 128), 128, 0, ctx->stream>>>(part, gamma, beta, ss, N, C, bps,
+                                                                        1.0 / (double)vox_per_sample, 1e-3f);
+  FM_LAUNCH_OK(ctx);
+  const int64_t total = (int64_t)N * vox_per_sample * (C / 8);
+  instnorm_apply_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, ss, add, y, vox_per_sample, C, N, 0.3f);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_seg_upsample_add(fm_ctx* ctx, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z) {
+  const int64_t total = (int64_t)N * X * Y * Z;
+  seg_upsample_add_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(fine, coarse, out, N, X, Y, Z);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+int k_sigmoid(fm_ctx* ctx, const float* z, float* p, int64_t n) {
+  sigmoid_kernel<<<grid_for(n), kThreads, 0, ctx->stream>>>(z, p, n);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -134,6 +134,11 @@ int k_dice_bwd(fm_ctx*, const float* p, const float* t, const double* sums, int6
 int k_adam(fm_ctx*, float* p, const float* g, float* m, float* v, int64_t n, int iterations,
            float lr);
 int k_zero(fm_ctx*, void* p, size_t bytes);
+// InstanceNormalization(axis=1) + LeakyReLU(0.3) (+ residual add) of a raw conv output (Isensee blocks)
+int k_instnorm_lrelu(fm_ctx*, const bf16* x, const float* gamma, const float* beta, const bf16* add, bf16* y, int N,
+                     int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats);
+int k_seg_upsample_add(fm_ctx*, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z);
+int k_sigmoid(fm_ctx*, const float* z, float* p, int64_t n);
 // out[(patch voxel (i,j)) * out_pitch + out_cofs + k]: with out_pitch = patch[2], out_cofs = 0 this is the plain
 // [n,P0,P1,P2] gather; the 2.5D path writes the slices and the previous-truth slices as channels of one row
 int k_gather_patches(fm_ctx*, const float* vol, const int32_t vol_dims[3], const int32_t halo_pad[6],
@@ -157,7 +162,7 @@ int k_conv3d_simt_wgrad(fm_ctx*, const void* x, int x_is_f32, const bf16* dy, fl
 int k_bias_grad(fm_ctx*, const bf16* dy, float* db, int64_t voxels, int C);
 // 1x1x1 head: z = w.x + b ; p = sigmoid(z) (fp32 out)
 int k_head_fwd(fm_ctx*, const bf16* x, const float* w, const float* b, float* p, int64_t voxels,
-               int C);
+               int C, int apply_sigmoid = 1);
 // head backward: dx[v,c] = dz[v] * w[c] * (x[v,c] > 0); dw[c] = sum_v dz[v] x[v,c]; db = sum dz
 int k_head_bwd(fm_ctx*, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
                float* db, int64_t voxels, int C);
@@ -169,9 +174,12 @@ int k_repack_weights(fm_ctx*, const float* w, bf16* w_f, bf16* w_d0, bf16* w_d1,
 // conv_tc.cu
 struct ConvTcPlan;  // opaque cached TMA descriptors for one conv launch configuration
 int conv_tc_supported(int C1, int C2, int Cout, int ksize);
+// N,X,Y,Z = OUTPUT extent. stride 2 (TF 'SAME', Isensee in-convs) reads an input of extent Xin x Yin x Zin.
+// relu: 0 = none, 1 = ReLU
 int k_conv3d_tc_fprop(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* w_packed,
                       const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z,
-                      int C1, int C2, int Cout, int ksize, int relu, int out_C, int out_cofs);
+                      int C1, int C2, int Cout, int ksize, int relu, int out_C, int out_cofs, int stride = 1,
+                      int Xin = 0, int Yin = 0, int Zin = 0);
 int k_conv3d_tc_wgrad(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y,
                       int Z, int Cin, int Cin_total, int cin_ofs, int Cout, int ksize);
 

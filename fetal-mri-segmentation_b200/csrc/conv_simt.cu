@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restri
                                                             const float* __restrict__ w,
                                                             const float* __restrict__ b,
                                                             float* __restrict__ p, int64_t voxels,
-                                                            int C) {
+                                                            int C, int apply_sigmoid) {
   const int lpv = C >> 3;  // lanes per voxel (power of two <= 32)
   const int sub = threadIdx.x % lpv;
   float wv[8];
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restri
       }
     }
     for (int s = lpv >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (sub == 0 && v < voxels) p[v] = 1.f / (1.f + __expf(-(acc + bb)));
+    if (sub == 0 && v < voxels) p[v] = apply_sigmoid ? 1.f / (1.f + __expf(-(acc + bb))) : acc + bb;
   }
 }
 
@@ -462,14 +462,14 @@ int k_bias_grad(fm_ctx* ctx, const bf16* dy, float* db, int64_t voxels, int C) {
 }
 
 int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float* p, int64_t voxels,
-               int C) {
+               int C, int apply_sigmoid) {
   FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
            "head: channel count %d must be a power of two in [8,256]", C);
   const int lpv = C / 8;
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 32);
   ProfScope prof(ctx, "head_fwd", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 4.0));
-  head_fwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, w, b, p, voxels, C);
+  head_fwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, w, b, p, voxels, C, apply_sigmoid);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -45,6 +45,8 @@ struct alignas(64) FpropParams {
   int out_C, out_cofs;
   int relu;
   int stages;
+  int stride;         // 1, or 2 = strided conv with TF 'SAME' padding (Isensee in-convs, isensee2017.py:51)
+  int pbx, pby, pbz;  // 'before' padding per axis (k/2 for stride 1; TF SAME for stride 2)
   const float* bias;
   bf16* out;
   const bf16* mask;
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
       m /= p.ty;
       const int ix = m % p.tx;
       const int n = m / p.tx;
-      const int x0 = ix * p.bx - pad, y0 = iy * p.by - pad, z0 = iz * p.bz - padz;
+      const int x0 = ix * p.bx * p.stride - p.pbx, y0 = iy * p.by * p.stride - p.pby,
+                z0 = iz * p.bz * p.stride - p.pbz;
       for (int s = 0; s < p.nsrc; ++s) {
         const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
         for (int ch = 0; ch < p.nchunks[s]; ++ch) {
@@ -481,14 +484,16 @@ CUtensorMapSwizzle swizzle_for(int row_bytes) {
 
 // 5-D map over a channels-last activation tensor [N][X][Y][Z][C] (bf16), box (cbox, bz, by, bx, 1)
 int make_act_tmap(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int cbox,
-                  int bz, int by, int bx) {
+                  int bz, int by, int bx, int stride = 1) {
   PFN_encodeTiled enc = get_encode();
   FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2,
                            (cuuint64_t)X * Y * Z * C * 2};
-  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // with a traversal stride the box is given in tensor elements and every stride-th element is loaded
+  const cuuint32_t st = (cuuint32_t)stride;
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bz * st, (cuuint32_t)by * st, (cuuint32_t)bx * st, 1};
+  cuuint32_t estr[5] = {1, st, st, st, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cbox * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -547,7 +552,14 @@ int conv_tc_supported(int C1, int C2, int Cout, int ksize) {
 
 int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w_packed,
                       const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1,
-                      int C2, int Cout, int ksize, int relu, int out_C, int out_cofs) {
+                      int C2, int Cout, int ksize, int relu, int out_C, int out_cofs, int stride, int Xin,
+                      int Yin, int Zin) {
+  FM_CHECK(stride == 1 || (stride == 2 && ksize == 3 && C2 == 0), FM_EINVAL, "conv3d tc: stride %d unsupported", stride);
+  if (stride == 1) {
+    Xin = X;
+    Yin = Y;
+    Zin = Z;
+  }
   FM_CHECK(conv_tc_supported(C1, C2, Cout, ksize), FM_EINVAL,
            "conv3d tc: unsupported channels C1=%d C2=%d Cout=%d k=%d", C1, C2, Cout, ksize);
   FM_CHECK(out_C % 8 == 0 && out_cofs % 8 == 0, FM_EINVAL, "conv3d tc: output channel pitch/offset");
@@ -573,6 +585,14 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   p.bias = bias;
   p.out = y;
   p.mask = mask;
+  p.stride = stride;
+  {
+    // TF 'SAME': pad_total = max((out-1)*stride + k - in, 0), pad_before = pad_total / 2
+    auto pb = [&](int out, int in, int k) { return std::max((out - 1) * stride + k - in, 0) / 2; };
+    p.pbx = pb(X, Xin, kext_xy(ksize));
+    p.pby = pb(Y, Yin, kext_xy(ksize));
+    p.pbz = pb(Z, Zin, kext_z(ksize));
+  }
   const int Ct = C1 + C2;
   const int Cs[2] = {C1, C2};
   const bf16* xs[2] = {x1, x2};
@@ -581,7 +601,7 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
     p.KC[s] = chunk_of(Cs[s]);
     p.nchunks[s] = Cs[s] / p.KC[s];
     p.wcofs[s] = cofs;
-    FM_TRY(make_act_tmap(&p.tmA[s], xs[s], N, X, Y, Z, Cs[s], p.KC[s], p.bz, p.by, p.bx));
+    FM_TRY(make_act_tmap(&p.tmA[s], xs[s], N, Xin, Yin, Zin, Cs[s], p.KC[s], p.bz, p.by, p.bx, stride));
     FM_TRY(make_w_tmap(&p.tmW[s], w_packed, Cout, p.ntaps, Ct, p.KC[s], p.block_n));
     cofs += Cs[s];
   }

@@ -26,12 +26,19 @@ class Model:
     """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
 
     def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
-                 device=None, ndim=3):
+                 device=None, ndim=3, isensee_levels=None):
         lib = _lib.load()
         self._ctx = _lib.get_context(device)
         self.ndim = int(ndim)
         h = _lib.c_vp()
-        if self.ndim == 3:
+        self.trainable = isensee_levels is None
+        if isensee_levels is not None:
+            in_ch, X, Y, Z = [int(v) for v in input_shape]
+            spec = _lib.Isensee3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(isensee_levels), int(n_labels))
+            _lib.check(lib.fm_model_create_isensee3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            self.input_shape = (None, in_ch, X, Y, Z)
+            self.output_shape = (None, int(n_labels), X, Y, Z)
+        elif self.ndim == 3:
             in_ch, X, Y, Z = [int(v) for v in input_shape]          # channels-first (unet3d/unet.py:9)
             spec = _lib.UNet3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(n_labels))
             _lib.check(lib.fm_model_create_unet3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
@@ -55,18 +62,22 @@ class Model:
         if loss_function is not dice_coefficient_loss:
             self.metrics_names.append('dice_coefficient')
         self.stop_training = False
-        self.name = 'unet_model_3d' if self.ndim == 3 else 'unet_model_2d'
+        self.name = 'isensee2017_model_3d' if isensee_levels is not None else \
+            ('unet_model_3d' if self.ndim == 3 else 'unet_model_2d')
         # layer table (Keras creation order; Keras would name them conv3d_1..conv3d_N)
         self.layers = []
         for i in range(lib.fm_model_num_layers(h)):
             name = ctypes.create_string_buffer(32)
             info = (ctypes.c_int64 * 5)()
             _lib.check(lib.fm_model_layer_info(h, i, name, info))
-            k = int(info[2]) // 10                                   # 33 / 31 -> 3, 11 -> 1
-            self.layers.append(dict(index=i, name=name.value.decode(),
-                                    keras_name="conv%dd_%d" % (self.ndim, i + 1),
+            k = int(info[2]) // 10                                   # 33 / 31 -> 3, 11 -> 1, 0 -> norm layer
+            is_norm = int(info[2]) == 0
+            n_same = sum(1 for l in self.layers if l["is_norm"] == is_norm) + 1
+            self.layers.append(dict(index=i, name=name.value.decode(), is_norm=is_norm,
+                                    keras_name=("instance_normalization_%d" if is_norm else "conv%dd_%%d" % self.ndim) % n_same,
                                     cin=int(info[0]), cout=int(info[1]), k=k,
-                                    kshape=(k,) * self.ndim + (int(info[0]), int(info[1]))))
+                                    kshape=(int(info[1]),) if is_norm else
+                                    (k,) * self.ndim + (int(info[0]), int(info[1]))))
 
     def __del__(self):
         try:
@@ -111,13 +122,23 @@ class Model:
 
     def set_named_weights(self, named):
         """`named`: {'<layer>/kernel': ..., '<layer>/bias': ...} keyed by our layer names (enc0a ...)."""
-        self.set_weights([named["%s/%s" % (l["name"], kind)] for l in self.layers for kind in ("kernel", "bias")])
+        ws = []
+        for l in self.layers:
+            if l["is_norm"]:        # '<conv>_norm' pseudo-layer: kernel slot = gamma, bias slot = beta
+                base = l["name"][:-len("_norm")]
+                ws += [named[base + "/gamma"], named[base + "/beta"]]
+            else:
+                ws += [named[l["name"] + "/kernel"], named[l["name"] + "/bias"]]
+        self.set_weights(ws)
 
     def init_glorot_uniform(self, seed=0):
         """Keras default initialisation (glorot_uniform kernels, zero biases)."""
         rng = np.random.default_rng(seed)
         ws = []
         for l in self.layers:
+            if l["is_norm"]:                                        # gamma = 1, beta = 0 (SURVEY.md App. A.6)
+                ws += [np.ones((l["cout"],), np.float32), np.zeros((l["cout"],), np.float32)]
+                continue
             rf = l["k"] ** self.ndim
             limit = np.sqrt(6.0 / (rf * l["cin"] + rf * l["cout"]))
             ws.append(rng.uniform(-limit, limit, size=l["kshape"]).astype(np.float32))
@@ -128,8 +149,8 @@ class Model:
         """HDF5 is absent in this image: weights go to an .npz keyed by Keras layer names."""
         arrays = {}
         for l, (k, b) in zip(self.layers, zip(*[iter(self.get_weights())] * 2)):
-            arrays[l["keras_name"] + "/kernel:0"] = k
-            arrays[l["keras_name"] + "/bias:0"] = b
+            arrays[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")] = k
+            arrays[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")] = b
         arrays["__config__"] = np.array(list(self.input_shape[1:]) + [self.depth, self.n_base_filters, self.n_labels])
         with open(path, "wb") as f:   # keep the caller's file name (e.g. '...-epoch01-loss-0.5.h5')
             np.savez(f, **arrays)
@@ -140,7 +161,8 @@ class Model:
         with np.load(path) as z:
             ws = []
             for l in self.layers:
-                ws += [z[l["keras_name"] + "/kernel:0"], z[l["keras_name"] + "/bias:0"]]
+                ws += [z[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")],
+                       z[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")]]
         self.set_weights(ws)
 
     def reset_optimizer(self):
@@ -159,6 +181,8 @@ class Model:
 
     # ---- training --------------------------------------------------------------------------
     def _check_loss(self):
+        if not self.trainable:
+            raise NotImplementedError("%s: training is on the §8 'next' list (forward / inference is built)" % self.name)
         if self.loss is not dice_coefficient_loss:
             raise NotImplementedError("only dice_coefficient_loss is built on the device path")
 
@@ -172,6 +196,10 @@ class Model:
         return [float(v) for v in m[:len(self.metrics_names)]]
 
     def test_on_batch(self, x, y, **kw):
+        if not self.trainable:                                      # metrics on the host from .predict
+            from .. import metrics as _m
+            p = self.predict(x)
+            return [_m.dice_coefficient_loss(y, p), _m.binary_accuracy(y, p), _m.vod_coefficient(y, p)]
         x, y = _lib.f32c(x), _lib.f32c(y)
         m = np.zeros(4, np.float32)
         _lib.check(self._lib.fm_evaluate(self._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]), _lib.fptr(m)))
@@ -232,7 +260,8 @@ class Model:
     def summary(self, print_fn=print):
         print_fn("%-10s %-12s %6s %6s %3s %10s" % ("layer", "keras name", "Cin", "Cout", "k", "params"))
         for l in self.layers:
-            print_fn("%-10s %-12s %6d %6d %3d %10d" % (l["name"], l["keras_name"], l["cin"], l["cout"], l["k"],
+            print_fn("%-14s %-26s %6d %6d %3d %10d" % (l["name"], l["keras_name"], l["cin"], l["cout"], l["k"],
+                                                       2 * l["cout"] if l["is_norm"] else
                                                        l["k"] ** self.ndim * l["cin"] * l["cout"] + l["cout"]))
         print_fn("Total params: %d" % self.count_params())
 
@@ -279,3 +308,18 @@ def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_ra
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
                  device=kargs.get("device"), ndim=2)
+
+
+def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, depth=5, dropout_rate=0.3,
+                         n_segmentation_levels=1, n_labels=1, optimizer=None, initial_learning_rate=5e-4,
+                         loss_function=dice_coefficient_loss, activation_name="sigmoid", mask_shape=None, **kargs):
+    """Same signature and defaults as the reference builder (fetal_net/model/unet3d/isensee2017.py:15-18).
+    Forward / inference runs on the device (SpatialDropout3D is the identity at inference, so `dropout_rate`
+    has no effect there); training this model family is on the §8 'next' list."""
+    if activation_name != "sigmoid":
+        raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
+    if mask_shape is not None:
+        raise NotImplementedError("mask_shape (closure loss with a second input) is on the §8 'next' list")
+    return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
+                 initial_learning_rate=initial_learning_rate, loss_function=loss_function,
+                 device=kargs.get("device"), ndim=3, isensee_levels=n_segmentation_levels)

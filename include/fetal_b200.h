@@ -92,9 +92,23 @@ typedef struct fm_unet2d_spec {
  * device tensors are channels-last). All entry points below accept either model kind. */
 int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec, fm_model** out);
 
+/* Builder spec of the Isensee-2017 residual 3D U-Net. Replaces the kwargs of isensee2017_model_3d
+ * (fetal_net/model/unet3d/isensee2017.py:15-18). Forward / inference only in this round: fm_predict,
+ * fm_predict_device and fm_patchwise_predict work; the training entry points return FM_EINVAL. The layer table
+ * lists every Conv3D followed by its InstanceNormalization pseudo-layer (kernel = gamma, bias = beta). */
+typedef struct fm_isensee3d_spec {
+  int32_t in_channels;            /* 1                                        */
+  int32_t X, Y, Z;                /* each divisible by 2^(depth-1)            */
+  int32_t depth;                  /* default 5                                */
+  int32_t n_base_filters;         /* default 16                               */
+  int32_t n_segmentation_levels;  /* default 1; BASELINE config 3 uses 3      */
+  int32_t n_labels;               /* 1                                        */
+} fm_isensee3d_spec;
+int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* spec, fm_model** out);
+
 /* Layer table, Keras creation order (conv3d_1 ... conv3d_15). */
 int fm_model_num_layers(fm_model* m);
-/* info[0]=cin, info[1]=cout, info[2]=kernel extent code (33: 3x3x3, 31: 3x3, 11: 1x1[x1]), info[3]=param offset
+/* info[0]=cin, info[1]=cout, info[2]=kernel extent code (33: 3x3x3, 31: 3x3, 11: 1x1[x1], 0: InstanceNormalization gamma/beta), info[3]=param offset
  * of kernel, info[4]=param offset of bias (offsets into the flat fp32 parameter buffer). */
 int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_t info[5]);
 int64_t fm_model_num_params(fm_model* m);

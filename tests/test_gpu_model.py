@@ -211,3 +211,44 @@ def test_bad_shapes_are_rejected():
         unet_model_3d(input_shape=(1, 30, 32, 32), n_base_filters=16)     # not divisible by 2^(depth-1)
     with pytest.raises(_lib.FetalB200Error):
         unet_model_3d(input_shape=(2, 32, 32, 32), n_base_filters=16)     # multi-modality not built
+
+
+# ---- Isensee-2017 residual 3D U-Net (forward / inference) ------------------------------------------
+
+def isensee_weights(layers, seed=0):
+    w = uo.glorot_uniform_weights(layers, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    for name, cin, cout, k in layers:
+        w[name + "/bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        if not name.endswith("_seg"):
+            w[name + "/gamma"] = (1.0 + 0.2 * rng.standard_normal(cout)).astype(np.float32)
+            w[name + "/beta"] = (0.2 * rng.standard_normal(cout)).astype(np.float32)
+        else:
+            w[name + "/kernel"] = (w[name + "/kernel"] * 3.0).astype(np.float32)
+    return w
+
+
+@pytest.mark.parametrize("shape,depth,nseg", [((1, 32, 32, 32), 4, 2), ((1, 64, 64, 32), 5, 3)])
+def test_isensee_forward_matches_oracle(shape, depth, nseg):
+    from fetal_net.model import isensee2017_model_3d
+    layers = uo.isensee3d_layers(depth, 16, nseg)
+    w = isensee_weights(layers, seed=7)
+    model = isensee2017_model_3d(input_shape=shape, n_base_filters=16, depth=depth, n_segmentation_levels=nseg)
+    assert [l["name"] for l in model.layers if not l["is_norm"]] == [n for n, *_ in layers]
+    model.set_named_weights(w)
+    if depth == 5 and nseg == 3:
+        conv_params = sum(l["k"] ** 3 * l["cin"] * l["cout"] + l["cout"] for l in model.layers if not l["is_norm"])
+        assert conv_params == 8263619
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2,) + shape).astype(np.float32)
+    p = model.predict(x)
+    with torch.no_grad():
+        ref = uo.isensee3d_forward(torch.as_tensor(x), w, depth=depth, n_segmentation_levels=nseg).numpy()
+    assert p.shape == ref.shape
+    logit = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    rel = np.linalg.norm(logit(p) - logit(ref)) / np.linalg.norm(logit(ref))
+    # instance normalisation re-scales every block, so bf16 storage error does not shrink with depth: 4 % bound
+    assert rel <= 0.04 and np.abs(p - ref).mean() <= 0.008, (rel, float(np.abs(p - ref).mean()))
+    assert np.array_equal(model.predict(x[1:2]), p[1:2])              # per-sample statistics: batch invariant
+    with pytest.raises(NotImplementedError):
+        model.train_on_batch(x, (x > 0).astype(np.float32))

@@ -130,7 +130,7 @@ def test_reference_api_surface():
     assert list(inspect.signature(ft.train_model).parameters)[:6] == [
         "model", "model_file", "training_generator", "validation_generator", "steps_per_epoch", "validation_steps"]
     with pytest.raises(NotImplementedError):
-        fmod.isensee2017_model_3d(input_shape=(1, 32, 32, 32))
+        fmod.isensee2017_model(input_shape=(32, 32, 5))            # 2D Isensee: on the §8 "next" list
 
 
 def test_host_metrics_known_answers():
