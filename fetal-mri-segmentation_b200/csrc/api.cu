@@ -222,6 +222,9 @@ struct fm_model {
   cudaEvent_t ev_tmp = nullptr;
   int last_batch = 0;
   bool fwd_valid = false;
+  // training passes use the shared-accumulator marching kernel (faster; fp32 summation order not fixed), inference
+  // the bit-reproducible one
+  bool train_pass = false;
 
   int depth() const { return spec.depth; }
   Dims5 dims(int level, int C, int B) const {
@@ -612,8 +615,8 @@ static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2,
   const Dims5 d = m->dims(l.level, l.cout, B);
   const float* bias = m->params + l.b_off;
   if (l.march_f)
-    return k_conv3d_march(ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2,
-                          l.cout, 1, l.cout, 0);
+    return (m->train_pass && l.cout <= 32 ? k_conv3d_march_shared : k_conv3d_march)(
+        ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, 1, l.cout, 0);
   if (conv_tc_supported(l.c1, l.c2, l.cout, l.k))
     return k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout,
                              l.k, 1, l.cout, 0);
@@ -692,8 +695,8 @@ static int conv_dgrad(fm_model* m, const Layer& l, int src, const bf16* dy, cons
   const int cs = src == 0 ? l.c1 : l.c2;
   const bf16* wd = src == 0 ? l.w_d0 : l.w_d1;
   if (l.march_d[src])
-    return k_conv3d_march(ctx, dy, nullptr, l.w_md[src], nullptr, nullptr, dx, mask, B, d.X, d.Y, d.Z, l.cout,
-                          0, cs, 0, cs, 0);
+    return (m->train_pass && cs <= 32 ? k_conv3d_march_shared : k_conv3d_march)(
+        ctx, dy, nullptr, l.w_md[src], nullptr, nullptr, dx, mask, B, d.X, d.Y, d.Z, l.cout, 0, cs, 0, cs, 0);
   if (conv_tc_supported(l.cout, 0, cs, l.k))
     return k_conv3d_tc_fprop(ctx, dy, nullptr, wd, nullptr, dx, mask, B, d.X, d.Y, d.Z, l.cout, 0, cs, l.k,
                              0, cs, 0);
@@ -1207,7 +1210,10 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
 // training
 // ---------------------------------------------------------------------------------------------
 static int train_forward_dev(fm_model* m, int batch) {
-  FM_TRY(forward(m, batch));
+  m->train_pass = true;
+  const int rf = forward(m, batch);
+  m->train_pass = false;
+  FM_TRY(rf);
   FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0));
   m->last_batch = batch;
   m->fwd_valid = true;
@@ -1229,7 +1235,10 @@ extern "C" int fm_train_backward(fm_model* m) {
   FM_CHECK(m->kind == 0, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
   FM_CHECK(m->fwd_valid, FM_ESTATE, "fm_train_backward called without a preceding fm_train_forward");
   FM_CUDA(cudaSetDevice(m->ctx->device));
-  FM_TRY(backward(m, m->last_batch));
+  m->train_pass = true;
+  const int rb = backward(m, m->last_batch);
+  m->train_pass = false;
+  FM_TRY(rb);
   m->fwd_valid = false;
   return FM_OK;
 }
@@ -1307,8 +1316,15 @@ extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int ba
 }
 
 extern "C" int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]) {
-  FM_CHECK(out_metrics, FM_EINVAL, "fm_evaluate: out_metrics is NULL");
-  FM_TRY(fm_train_forward(m, x, t, batch));
+  FM_CHECK(m && x && t && batch > 0 && out_metrics, FM_EINVAL, "fm_evaluate: bad argument");
+  FM_CHECK(m->kind == 0, FM_EINVAL, "fm_evaluate: use fm_predict + host metrics for this model kind");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_TRY(ensure_capacity(m, batch, true));
+  const size_t n = (size_t)batch * m->vox(0);
+  FM_TRY(upload(m, x, m->x_in.p, n * m->cin_real));
+  FM_TRY(upload(m, t, m->t_in.p, n));
+  FM_TRY(forward(m, batch));  // inference kernels: same bits as fm_predict
+  FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)n, m->sums, 0));
   m->fwd_valid = false;
   FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
@@ -1382,7 +1398,7 @@ extern "C" int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const f
   FM_TRY(s.up_bf16(packed.data(), packed.size(), &dw));
   if (bias) FM_TRY(s.up_f32(bias, Cout, &dbias));
   FM_TRY(s.alloc(&dy, vox * Cout));
-  if (impl == 2) {
+  if (impl == 2 || impl == 3) {  // marching kernel: 2 = bit-reproducible, 3 = shared accumulators (training variant)
     FM_CHECK(conv_march_supported(X, Y, Z, C1, C2, Cout, ksize), FM_EINVAL, "march kernel does not cover this shape");
     bf16 *wm1 = nullptr, *wm2 = nullptr;
     FM_TRY(s.alloc(&wm1, (size_t)conv_march_pack_elems(C1, Cout)));
@@ -1391,7 +1407,8 @@ extern "C" int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const f
       FM_TRY(s.alloc(&wm2, (size_t)conv_march_pack_elems(C2, Cout)));
       FM_TRY(k_repack_march(ctx, dw, wm2, Cout, Ct, C1, C2));
     }
-    FM_TRY(k_conv3d_march(ctx, dx1, dx2, wm1, wm2, dbias, dy, nullptr, N, X, Y, Z, C1, C2, Cout, relu, Cout, 0));
+    FM_TRY((impl == 3 && Cout <= 32 ? k_conv3d_march_shared : k_conv3d_march)(ctx, dx1, dx2, wm1, wm2, dbias, dy, nullptr,
+                                                                               N, X, Y, Z, C1, C2, Cout, relu, Cout, 0));
   } else if (impl == 0)
     FM_TRY(k_conv3d_tc_fprop(ctx, dx1, dx2, dw, dbias, dy, nullptr, N, X, Y, Z, C1, C2, Cout, ksize, relu,
                              Cout, 0));
@@ -1419,12 +1436,13 @@ extern "C" int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const 
   FM_TRY(s.up_bf16(dy, vox * Cout, &ddy));
   if (mask) FM_TRY(s.up_bf16(mask, vox * Cin, &dmask));
   FM_TRY(s.alloc(&ddx, vox * Cin));
-  if (impl == 2) {
+  if (impl == 2 || impl == 3) {
     FM_CHECK(conv_march_supported(X, Y, Z, Cout, 0, Cin, ksize), FM_EINVAL, "march kernel does not cover this shape");
     bf16* wm = nullptr;
     FM_TRY(s.alloc(&wm, (size_t)conv_march_pack_elems(Cout, Cin)));
     FM_TRY(k_repack_march(ctx, wd, wm, Cin, Cout, 0, Cout));
-    FM_TRY(k_conv3d_march(ctx, ddy, nullptr, wm, nullptr, nullptr, ddx, dmask, N, X, Y, Z, Cout, 0, Cin, 0, Cin, 0));
+    FM_TRY((impl == 3 && Cin <= 32 ? k_conv3d_march_shared : k_conv3d_march)(ctx, ddy, nullptr, wm, nullptr, nullptr, ddx,
+                                                                             dmask, N, X, Y, Z, Cout, 0, Cin, 0, Cin, 0));
   } else if (impl == 0)
     FM_TRY(k_conv3d_tc_fprop(ctx, ddy, nullptr, wd, nullptr, ddx, dmask, N, X, Y, Z, Cout, 0, Cin, ksize, 0,
                              Cin, 0));

@@ -190,6 +190,10 @@ int k_repack_march(fm_ctx*, const bf16* P, bf16* Wm, int Nrows, int Ktot, int ko
 int k_conv3d_march(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* wm1, const bf16* wm2,
                    const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2,
                    int Cout, int relu, int out_C, int out_cofs);
+// conv_march_shared.cu: same contract, shared accumulators (training passes; not bit-reproducible run to run)
+int k_conv3d_march_shared(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* wm1, const bf16* wm2,
+                          const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2,
+                          int Cout, int relu, int out_C, int out_cofs);
 
 // conv_wgrad_march.cu
 int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize);

@@ -137,6 +137,16 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       ::"r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+      "}"
+      ::"r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
   asm volatile(
       "{\n\t"

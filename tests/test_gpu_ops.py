@@ -43,9 +43,10 @@ MIDS = [c[0] for c in gc.MARCH_CASES]
 MSINGLE = [c for c in gc.MARCH_CASES if c[6] == 0]
 
 
+@pytest.mark.parametrize("impl", [2, 3], ids=["reproducible", "shared-acc"])
 @pytest.mark.parametrize("case", gc.MARCH_CASES, ids=MIDS)
-def test_conv3d_fprop_march(ctx, case):
-    ok, worst = gc.conv_fprop_case(ctx, 2, case)
+def test_conv3d_fprop_march(ctx, case, impl):
+    ok, worst = gc.conv_fprop_case(ctx, impl, case)
     assert ok, "worst error / tolerance = %.3f" % worst
 
 
@@ -54,8 +55,9 @@ def test_conv3d_dgrad_march(ctx, case):
     # dgrad runs the marching kernel with Cout input channels and C1 output channels
     if case[7] > 64 or case[5] > 64:
         pytest.skip("filter bank not resident")
-    ok, worst = gc.conv_dgrad_case(ctx, 2, case)
-    assert ok, "worst error / tolerance = %.3f" % worst
+    for impl in (2, 3):
+        ok, worst = gc.conv_dgrad_case(ctx, impl, case)
+        assert ok, "impl %d: worst error / tolerance = %.3f" % (impl, worst)
 
 
 @pytest.mark.parametrize("case", gc.WGRAD_MARCH_CASES, ids=[c[0] for c in gc.WGRAD_MARCH_CASES])

@@ -38,7 +38,7 @@ def main():
         b = np.zeros(Co, np.float32)
         y = np.empty((vox, Co), np.float32)
         res = {}
-        for impl, tag in ((0, "tap"), (2, "march")):
+        for impl, tag in ((0, "tap"), (2, "march"), (3, "march-shared")):
             ctx.profile(True)
             try:
                 for _ in range(3):
