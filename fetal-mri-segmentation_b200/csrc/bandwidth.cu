@@ -71,8 +71,9 @@ __global__ void pad_cast_kernel(const float* __restrict__ in, bf16* __restrict__
 // one thread = one pooled voxel x 8 channels (16 B); the two z-children of a window are adjacent
 // in memory so every warp-level request is a run of full 32 B sectors.
 // ---------------------------------------------------------------------------------------------
+template <int pz>
 __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
-                                     int Y, int Z, int C, int pz) {
+                                     int Y, int Z, int C) {
   const int c8n = C >> 3;
   const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
   const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
@@ -117,9 +118,10 @@ __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restric
 
 // Backward of MaxPooling3D fused with the skip-connection gradient add and the ReLU mask of the
 // producing conv block: dx = [x>0] * (dskip + [x is the first max of its window] * dy).
+template <int pz>
 __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                      const bf16* __restrict__ dskip, bf16* __restrict__ dx, int N,
-                                     int X, int Y, int Z, int C, int relu_mask, int pz) {
+                                     int X, int Y, int Z, int C, int relu_mask) {
   const int c8n = C >> 3;
   const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
   const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
@@ -184,8 +186,9 @@ __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __r
 // ---------------------------------------------------------------------------------------------
 // UpSampling3D((2,2,2)) nearest — Keras call site fetal_net/model/unet3d/unet.py:138
 // ---------------------------------------------------------------------------------------------
+template <int pz>
 __global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
-                                      int Y, int Z, int C, int pz) {
+                                      int Y, int Z, int C) {
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * X * Y * Z * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,9 +213,10 @@ __global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restri
 }
 
 // backward: 2^3 sum-pool of dy (fp32 accumulate), optionally masked by ReLU of the coarse activation
+template <int pz>
 __global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ act,
                                       bf16* __restrict__ dx, int N, int X, int Y, int Z, int C,
-                                      int dyC, int dy_cofs, int pz) {
+                                      int dyC, int dy_cofs) {
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * X * Y * Z * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,8 +651,10 @@ int k_maxpool3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in, int pz) {
            "maxpool3d: need C%%8==0 and even extents (got C=%d %dx%dx%d)", in.C, in.X, in.Y, in.Z);
   const int64_t total = in.elems() / (32 * pz);
   ProfScope prof(ctx, "maxpool3d_fwd", 0.0, (double)in.elems() * 2.0 * 1.125);
-  maxpool3d_fwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z,
-                                                                     in.C, pz);
+  if (pz == 2)
+    maxpool3d_fwd_kernel<2><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
+  else
+    maxpool3d_fwd_kernel<1><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -658,16 +664,22 @@ int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dski
            "maxpool3d_bwd: need C%%8==0 and even extents");
   const int64_t total = in.elems() / (32 * pz);
   ProfScope prof(ctx, "maxpool3d_bwd", 0.0, (double)in.elems() * 2.0 * (dskip ? 3.125 : 2.125));
-  maxpool3d_bwd_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X,
-                                                                     in.Y, in.Z, in.C, relu_mask, pz);
+  if (pz == 2)
+    maxpool3d_bwd_kernel<2><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
+                                                                          in.C, relu_mask);
+  else
+    maxpool3d_bwd_kernel<1><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
+                                                                          in.C, relu_mask);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
 int k_upsample3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in, int pz) {
   FM_CHECK(in.C % 8 == 0, FM_EINVAL, "upsample3d: need C%%8==0");
   ProfScope prof(ctx, "upsample3d_fwd", 0.0, (double)in.elems() * 2.0 * 9.0);
-  upsample3d_fwd_kernel<<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X,
-                                                                               in.Y, in.Z, in.C, pz);
+  if (pz == 2)
+    upsample3d_fwd_kernel<2><<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
+  else
+    upsample3d_fwd_kernel<1><<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -676,8 +688,12 @@ int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dim
   FM_CHECK(coarse.C % 8 == 0 && dy_C % 8 == 0 && dy_cofs % 8 == 0, FM_EINVAL,
            "upsample3d_bwd: channel counts must be multiples of 8");
   ProfScope prof(ctx, "upsample3d_bwd", 0.0, (double)coarse.elems() * 2.0 * (act ? 10.0 : 9.0));
-  upsample3d_bwd_kernel<<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
-      dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs, pz);
+  if (pz == 2)
+    upsample3d_bwd_kernel<2><<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
+        dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
+  else
+    upsample3d_bwd_kernel<1><<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
+        dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

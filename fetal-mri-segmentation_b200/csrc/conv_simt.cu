@@ -180,74 +180,64 @@ __global__ void __launch_bounds__(kThreads) conv3d_first_kernel(const float* __r
 
 // --------------------------------------------------------------------------------------------
 // first-layer wgrad (Cin = 1): dW[co][tap] = sum_v dY[v][co] * x[v + shift(tap)].
-// A warp owns one (kx, 16-channel slice) class and 32 consecutive voxels per trip; every lane keeps
-// the 9 (ky,kz) x 16 (co) partial sums of its class in registers, the warp butterfly-reduces them once
-// at the end and issues 144 fp32 red.add per warp. dY rows are read as full 32 B sectors.
+// A warp owns one class = (kx, ky, channel slice of CS) and 32 consecutive voxels per trip; every lane keeps the
+// 3 (kz) x CS partial sums of its class in registers - few registers, so 2-3 blocks of 18 warps are resident per
+// SM and the dY / x load latency is hidden by occupancy. Persistent blocks; at the end every warp
+// butterfly-reduces its sums and issues them as fp32 red.add (27 * COUT per block).
 // --------------------------------------------------------------------------------------------
-template <int COUT>
-__global__ void __launch_bounds__(32 * 3 * (COUT / 16) * 2) conv3d_first_wgrad_kernel(
-    const float* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int N, int X,
-    int Y, int Z) {
-  constexpr int NCLS = 3 * (COUT / 16);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = warp % NCLS, vgrp = warp / NCLS;  // 2 voxel groups per block
-  const int kx = cls % 3, chalf = cls / 3;
+template <int COUT, int CS>
+__global__ void __launch_bounds__(32 * 9 * (COUT / CS)) conv3d_first_wgrad_kernel(const float* __restrict__ x,
+                                                                                 const bf16* __restrict__ dy,
+                                                                                 float* __restrict__ dw, int N, int X,
+                                                                                 int Y, int Z) {
+  const int cls = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kx = cls % 3, ky = (cls / 3) % 3, cslice = cls / 9;
   const int64_t nvox = (int64_t)N * X * Y * Z;
-  float acc[9][16];
+  float acc[3][CS];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[t][c] = 0.f;
-  const int64_t stride = (int64_t)gridDim.x * 2 * 32;
-  for (int64_t v = ((int64_t)blockIdx.x * 2 + vgrp) * 32 + lane; v < nvox; v += stride) {
-    const int z = (int)(v % Z);
-    int64_t r = v / Z;
-    const int yy = (int)(r % Y);
-    r /= Y;
-    const int xx = (int)(r % X);
-    const int n = (int)(r / X);
-    const int xi = xx + kx - 1;
-    if (xi < 0 || xi >= X) continue;
-    float g[16];
-    {
-      const uint4* gp = reinterpret_cast<const uint4*>(dy + v * COUT + chalf * 16);
+    for (int c = 0; c < CS; ++c) acc[t][c] = 0.f;
+  // 32-bit index arithmetic: 64-bit div/mod by run-time extents costs ~100 instructions each
+  const uint32_t stride = gridDim.x * 32u, nv32 = (uint32_t)nvox;
+  for (uint32_t v = blockIdx.x * 32u + (uint32_t)lane; v < nv32; v += stride) {
+    const int z = (int)(v % (uint32_t)Z);
+    uint32_t r = v / (uint32_t)Z;
+    const int yy = (int)(r % (uint32_t)Y);
+    r /= (uint32_t)Y;
+    const int xx = (int)(r % (uint32_t)X);
+    const int n = (int)(r / (uint32_t)X);
+    const int xi = xx + kx - 1, yi = yy + ky - 1;
+    if (xi < 0 || xi >= X || yi < 0 || yi >= Y) continue;
+    float g[CS];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint4 t4 = __ldg(gp + h);
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t4);
+    for (int h = 0; h < CS / 8; ++h) {
+      const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(dy + (int64_t)v * COUT + cslice * CS + h * 8));
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(hh[j]);
-          g[8 * h + 2 * j] = f.x;
-          g[8 * h + 2 * j + 1] = f.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(hh[j]);
+        g[8 * h + 2 * j] = f.x;
+        g[8 * h + 2 * j + 1] = f.y;
       }
     }
-    const float* xb = x + ((int64_t)n * X + xi) * Y * Z;
+    const float* xb = x + (((int64_t)n * X + xi) * Y + yi) * Z;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yi = yy + ky - 1;
+    for (int kz = 0; kz < 3; ++kz) {
+      const int zi = z + kz - 1;
+      const float xv = (zi >= 0 && zi < Z) ? __ldg(xb + zi) : 0.f;
 #pragma unroll
-      for (int kz = 0; kz < 3; ++kz) {
-        const int zi = z + kz - 1;
-        float xv = 0.f;
-        if (yi >= 0 && yi < Y && zi >= 0 && zi < Z) xv = __ldg(xb + (int64_t)yi * Z + zi);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) acc[ky * 3 + kz][c] += xv * g[c];
-      }
+      for (int c = 0; c < CS; ++c) acc[kz][c] += xv * g[c];
     }
   }
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < CS; ++c) {
       float a = acc[t][c];
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-      if (lane == ((t * 16 + c) & 31)) {
-        const int co = chalf * 16 + c;
-        atomicAdd(dw + co * 27 + kx * 9 + t, a);  // packed [Cout][27][1]
-      }
+      if (lane == ((t * CS + c) & 31)) atomicAdd(dw + (cslice * CS + c) * 27 + kx * 9 + ky * 3 + t, a);  // [Cout][27][1]
     }
 }
 
@@ -271,6 +261,45 @@ __global__ void bias_grad_kernel(const bf16* __restrict__ dy, float* __restrict_
     for (int k = 1; k < lanes; ++k) acc += sh[k * C + c];
     atomicAdd(db + c, acc);
   }
+}
+
+// Vector form for C = 8*G, G a power of two <= 32: thread i reads 16-byte element i, i+stride, ...
+// of the flat [voxels*G] array; stride is a multiple of G, so a thread's channel group (lane % G)
+// never changes and eight fp32 accumulators suffice. Lanes sharing a group fold by xor-shuffle.
+__global__ void __launch_bounds__(kThreads) bias_grad_vec_kernel(const uint4* __restrict__ dy,
+                                                                 float* __restrict__ db,
+                                                                 int64_t nvec, int G) {
+  __shared__ float sh[256];
+  sh[threadIdx.x] = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  auto add8 = [&](const uint4& t) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] += __uint_as_float(w[j] << 16);
+      acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    }
+  };
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    const uint4 t0 = __ldg(dy + i), t1 = __ldg(dy + i + stride), t2 = __ldg(dy + i + 2 * stride),
+                t3 = __ldg(dy + i + 3 * stride);
+    add8(t0), add8(t1), add8(t2), add8(t3);
+  }
+  for (; i < nvec; i += stride) add8(__ldg(dy + i));
+  for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  if (lane < G)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[lane * 8 + j], acc[j]);
+  __syncthreads();
+  if ((int)threadIdx.x < G * 8) atomicAdd(db + threadIdx.x, sh[threadIdx.x]);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -423,13 +452,14 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
   const int taps = kext_taps(ksize);
   const int64_t n_out = (int64_t)Cout * taps * Cin;
   const int64_t nvox = (int64_t)N * X * Y * Z;
-  if (x_is_f32 && Cin == 1 && Cin_total == 1 && cin_ofs == 0 && ksize == 3 && (Cout == 16 || Cout == 32)) {
+  if (x_is_f32 && Cin == 1 && Cin_total == 1 && cin_ofs == 0 && ksize == 3 && (Cout == 16 || Cout == 32) &&
+      nvox < (int64_t)1 << 31) {
     ProfScope prof(ctx, "conv3d_first_wgrad", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
-    const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 64), (int64_t)ctx->num_sms * 4);
+    const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 32), (int64_t)ctx->num_sms * 3);
     if (Cout == 16)
-      conv3d_first_wgrad_kernel<16><<<grid, 32 * 3 * 1 * 2, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+      conv3d_first_wgrad_kernel<16, 8><<<grid, 32 * 18, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
     else
-      conv3d_first_wgrad_kernel<32><<<grid, 32 * 3 * 2 * 2, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+      conv3d_first_wgrad_kernel<32, 16><<<grid, 32 * 18, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
     FM_LAUNCH_OK(ctx);
     return FM_OK;
   }
@@ -449,6 +479,15 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
 
 int k_bias_grad(fm_ctx* ctx, const bf16* dy, float* db, int64_t voxels, int C) {
   FM_CHECK(C >= 1 && C <= 1024, FM_EINVAL, "bias_grad: C=%d unsupported", C);
+  if (C >= 8 && C <= 256 && (C & (C - 1)) == 0 && ((uintptr_t)dy & 15) == 0) {
+    const int64_t nvec = voxels * (C / 8);
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, nvec / (kThreads * 4)));
+    ProfScope prof(ctx, "bias_grad", 0.0, (double)voxels * C * 2.0);
+    bias_grad_vec_kernel<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dy), db,
+                                                                        nvec, C / 8);
+    FM_LAUNCH_OK(ctx);
+    return FM_OK;
+  }
   const int lanes = std::max(1, kThreads / C);
   const int threads = C * lanes;
   int64_t blocks = std::min<int64_t>((int64_t)ctx->num_sms * 8, std::max<int64_t>(1, voxels / (lanes * 8)));
