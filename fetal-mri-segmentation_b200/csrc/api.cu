@@ -8,6 +8,8 @@
 #include <cmath>
 
 #include "common.cuh"
+#include <chrono>
+#include <thread>
 
 // ---------------------------------------------------------------------------------------------
 // error string (per thread)
@@ -119,6 +121,27 @@ extern "C" int fm_ctx_profile_get(fm_ctx* ctx, int i, char name[48], double out[
   out[1] = ctx->prof[i].flops;
   out[2] = ctx->prof[i].bytes;
   return FM_OK;
+}
+
+// Large host copies into freshly allocated caller memory are page-fault bound (~5 GB/s on one thread);
+// faults on disjoint ranges proceed in parallel, so split the copy over a few short-lived threads.
+static void host_copy(void* dst, const void* src, size_t bytes) {
+  const size_t kMin = (size_t)4 << 20;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t nt = std::min<size_t>({(size_t)8, (size_t)hw, bytes / kMin});
+  if (nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  for (size_t i = 1; i < nt; ++i) {
+    const size_t o = i * chunk;
+    if (o >= bytes) break;
+    th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, bytes - o)); });
+  }
+  memcpy(dst, src, std::min(chunk, bytes));
+  for (auto& t : th) t.join();
 }
 
 int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out) {
@@ -1172,13 +1195,27 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
   FM_TRY(dcnt.ensure(nout));
   // host <-> device through the context's pinned staging buffer (pageable cudaMemcpy runs at a fraction of PCIe)
   void* pin = nullptr;
+  const bool trace = getenv("FETAL_B200_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_start = now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    auto t = now();
+    fprintf(stderr, "[fm_patchwise_predict] %-22s %8.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(t - t_start).count());
+    t_start = t;
+  };
   const size_t out_bytes = nout * sizeof(double), cnt_bytes = out_count ? nout * sizeof(int16_t) : 0;
   FM_TRY(fm_ctx_pinned(ctx, std::max(nv * sizeof(float) * (truth ? 2 : 1), out_bytes + cnt_bytes), &pin));
-  memcpy(pin, vol, nv * sizeof(float));
-  if (truth) memcpy((float*)pin + nv, truth, nv * sizeof(float));
+  lap("workspace");
+  host_copy(pin, vol, nv * sizeof(float));
+  if (truth) host_copy((float*)pin + nv, truth, nv * sizeof(float));
+  lap("stage volume");
   FM_CUDA(cudaMemcpyAsync(dvol.p, pin, nv * 4 * (truth ? 2 : 1), cudaMemcpyHostToDevice, ctx->stream));
   FM_CUDA(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
   FM_CUDA(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));
+  lap("h2d");
   for (int64_t b0 = lo; b0 < hi; b0 += batch) {
     const int nb = (int)std::min<int64_t>(batch, hi - b0);
     // 3D: [nb,P0,P1,P2] == the network's [nb,X,Y,Z] input. 2D: [nb,H,W,(slices | truth slices)] channels-last
@@ -1193,15 +1230,19 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
     FM_CUDA(cudaMemcpyAsync(dpred.p + (size_t)(b0 - lo) * pv, m->prob.p, (size_t)nb * pv * 4,
                             cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  lap("gather + forward");
   FM_TRY(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, pred, 1, out_dims, dout.p, dcnt.p,
                       shard_count == 1 ? 1 : 0));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the H2D staging buffer is reused for the way back
+  lap("reassemble");
   FM_CUDA(cudaMemcpyAsync(pin, dout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_count)
     FM_CUDA(cudaMemcpyAsync((char*)pin + out_bytes, dcnt.p, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));
-  memcpy(out, pin, out_bytes);
-  if (out_count) memcpy(out_count, (char*)pin + out_bytes, cnt_bytes);
+  lap("d2h");
+  host_copy(out, pin, out_bytes);
+  if (out_count) host_copy(out_count, (char*)pin + out_bytes, cnt_bytes);
+  lap("unstage result");
   m->fwd_valid = false;
   return FM_OK;
 }
