@@ -87,12 +87,18 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
     """Drop-in for fetal_net/prediction.py:118-210. `shard=(rank, count)` (extension) makes this call
     process only its contiguous share of the patch list and return (partial float64 sums, int16 counts)
     for the caller to reduce — see fetal_net.distributed.sharded_patch_wise_prediction."""
-    if permute:
-        raise NotImplementedError("permute=True (48-permutation TTA, prediction.py:364-369) is on the §8 'next' list")
     lib = _lib.load()
     data = np.asarray(data)
     assert data.ndim == 4 and data.shape[0] == 1, "data must be [1,X,Y,Z] (prediction.py:296)"
     g = _geometry(model, data, patch_shape, overlap_factor)
+    if permute:
+        # prediction.py:185 routes every batch through predict(..., permute=True): the per-patch average over the
+        # flip/rotation keys. The fused native pipeline has no such hook, so take the generic route with a model
+        # wrapper whose predict() does the averaging — same patches, same order, same reassembly.
+        assert g["is3d"], "permute=True needs [B,C,x,y,z] patches (augment.py:407-434)"
+        assert shard is None, "permute=True is not sharded"
+        return patch_wise_prediction(_PermutingModel(model), data, patch_shape, overlap_factor, batch_size,
+                                     False, truth_data, prev_truth_index, prev_truth_size)
     idx = patch_plan(g["padded"], g["patch_shape"], g["prediction_shape"], overlap_factor)
     vol = _lib.f32c(data[0])                      # Keras casts the float64 feed to float32
     vol_dims = _lib.i32x(vol.shape)
@@ -174,5 +180,137 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
 def predict(model, data, permute=False):
     # prediction.py:354-361
     if permute:
-        raise NotImplementedError("permute=True is on the §8 'next' list")
+        return np.asarray([predict_with_permutations(model, data[i]) for i in range(data.shape[0])])
     return model.predict(data)
+
+
+# ---------------------------------------------------------------------------------------------
+# test-time augmentation wrappers (prediction.py:19-85,364-369; augment.py:380-469). They only
+# re-index the volume on the host; every prediction inside is the device pipeline above.
+# ---------------------------------------------------------------------------------------------
+class _PermutingModel:
+    """Keras-Model duck type whose predict() averages over the permutation keys (prediction.py:356-359)."""
+
+    def __init__(self, model):
+        self._model = model
+        self.output_shape = model.output_shape
+
+    def predict(self, data):
+        return predict(self._model, np.asarray(data), permute=True)
+
+
+def flip_it(data_, axes):
+    # prediction.py:19-22
+    for ax in axes:
+        data_ = np.flip(data_, ax)
+    return data_
+
+
+def generate_permutation_keys():
+    """augment.py:380-396: keys ((rotate_y, rotate_z), flip_x, flip_y, flip_z, transpose) — 3*2*2*2*2 = 48 tuples.
+    Kept as a set like the reference so the float32 mean below adds the terms in the same order."""
+    return set(itertools.product(itertools.combinations_with_replacement(range(2), 2),
+                                 range(2), range(2), range(2), range(2)))
+
+
+def permute_data(data, key):
+    """augment.py:407-434 as it actually behaves: rot90 by rotate_y in the (x,y) plane, then the three flips;
+    rotate_z and transpose are carried in the key but unused (commented out in the reference)."""
+    data = np.copy(data)
+    (rotate_y, _rotate_z), flip_x, flip_y, flip_z, _transpose = key
+    if rotate_y != 0:
+        data = np.rot90(data, rotate_y, axes=(1, 2))
+    if flip_x:
+        data = data[:, ::-1]
+    if flip_y:
+        data = data[:, :, ::-1]
+    if flip_z:
+        data = data[:, :, :, ::-1]
+    return data
+
+
+def reverse_permutation_key(key):
+    # augment.py:467-469
+    return tuple(-r for r in key[0]), key[1], key[2], key[3], key[4]
+
+
+def reverse_permute_data(data, key):
+    # augment.py:448-464: undo in the opposite order with the rotation negated
+    (rotate_y, _rotate_z), flip_x, flip_y, flip_z, _transpose = reverse_permutation_key(key)
+    data = np.copy(data)
+    if flip_z:
+        data = data[:, :, :, ::-1]
+    if flip_y:
+        data = data[:, :, ::-1]
+    if flip_x:
+        data = data[:, ::-1]
+    if rotate_y != 0:
+        data = np.rot90(data, rotate_y, axes=(1, 2))
+    return data
+
+
+def predict_with_permutations(model, data):
+    """prediction.py:364-369: data [C,x,y,z]; mean over all keys of the un-permuted prediction of the permuted
+    patch. All 48 permuted copies go to the device as ONE predict() batch when the patch is square in (x,y)
+    (rot90 keeps the shape); otherwise key by key like the reference."""
+    keys = list(generate_permutation_keys())
+    permuted = [permute_data(data, k) for k in keys]
+    if all(p.shape == permuted[0].shape for p in permuted):
+        outs = np.asarray(model.predict(np.ascontiguousarray(np.stack(permuted))))
+        predictions = [reverse_permute_data(outs[i], k) for i, k in enumerate(keys)]
+    else:
+        predictions = [reverse_permute_data(model.predict(np.ascontiguousarray(p[np.newaxis]))[0], k)
+                       for p, k in zip(permuted, keys)]
+    return np.mean(predictions, axis=0)
+
+
+def predict_flips(data, model, overlap_factor, config):
+    """prediction.py:65-85: the 8 axis-flip subsets in powerset order () (0,) (1,) (2,) (0,1) (0,2) (1,2) (0,1,2);
+    returns the list of un-flipped predictions [X,Y,Z] (the caller takes the median, predict_nifti2.py:86-87)."""
+    patch_shape = list(config["patch_shape"]) + [config["patch_depth"]]
+    axes_sets = itertools.chain.from_iterable(itertools.combinations([0, 1, 2], r) for r in range(4))
+    predictions = []
+    for axes in axes_sets:
+        data_ = flip_it(data, axes)
+        curr = patch_wise_prediction(model=model, data=np.expand_dims(np.squeeze(data_), 0),
+                                     overlap_factor=overlap_factor, patch_shape=patch_shape).squeeze()
+        predictions.append(flip_it(curr, axes).squeeze())
+    return predictions
+
+
+def rescale_intensity_to_image_range(data, in_min, in_max):
+    """What augment.py:123-126 `contrast_augment` asks of skimage.exposure.rescale_intensity(data,
+    in_range=(lo, hi), out_range='image'): clip to [lo, hi], map linearly onto the image's own [min, max]."""
+    data = np.asarray(data)
+    omin, omax = data.min(), data.max()
+    scaled = (np.clip(data, in_min, in_max) - in_min) / (in_max - in_min)
+    return (scaled * (omax - omin) + omin).astype(data.dtype)
+
+
+def predict_augment(data, model, overlap_factor, patch_shape, num_augments=32):
+    """prediction.py:25-62: random contrast window, flips, (x,y) transpose and an in-plane rotation of up to
+    +-30 degrees (scipy.ndimage.rotate, order 2, reshape=False), predict, undo; returns [num_augments,X,Y,Z].
+    Draws from np.random in the reference's order, so a seeded run reproduces the reference's augmentations."""
+    from scipy import ndimage
+    data_max, data_min = data.max(), data.min()
+    data = np.squeeze(data)
+    predictions = []
+    for _ in range(num_augments):
+        val_range = data_max - data_min
+        lo = data_min + 0.10 * np.random.uniform(-1, 1) * val_range
+        hi = data_max + 0.10 * np.random.uniform(-1, 1) * val_range
+        curr = rescale_intensity_to_image_range(data, lo, hi)
+        rotate_factor = np.random.uniform(-30, 30)
+        to_flip = np.arange(0, 3)[np.random.choice([True, False], size=3)]
+        to_transpose = np.random.choice([True, False])
+        curr = flip_it(curr, to_flip)
+        if to_transpose:
+            curr = curr.transpose([1, 0, 2])
+        curr = ndimage.rotate(curr, rotate_factor, order=2, reshape=False)
+        pred = patch_wise_prediction(model=model, data=curr[np.newaxis, ...], overlap_factor=overlap_factor,
+                                     patch_shape=patch_shape).squeeze()
+        pred = ndimage.rotate(pred, -rotate_factor)     # default order 3, reshape=True — as the reference
+        if to_transpose:
+            pred = pred.transpose([1, 0, 2])
+        predictions.append(flip_it(pred, to_flip).squeeze())
+    return np.stack(predictions, axis=0)

@@ -161,6 +161,37 @@ def main():
     for i, c in enumerate(corners):
         fx["patch/out%d" % i] = np.ascontiguousarray(patches.get_patch_from_3d_data(data, (4, 4, 4), np.array(c)))
 
+    # ---- (5) test-time augmentation wrappers (prediction.py:65-85, 364-369, 25-62)
+    rng = np.random.default_rng(11)
+    vol = rng.standard_normal((1, 24, 20, 16)).astype(np.float32)
+    fn, oshape = ramp_model((8, 8, 8), 1)
+    flips = pred.predict_flips(vol, FunctionModel(fn, oshape), 0.5, {"patch_shape": [8, 8], "patch_depth": 8})
+    fx["tta/flips/vol"] = vol
+    fx["tta/flips/out"] = np.stack(flips)                              # [8,X,Y,Z] float64, powerset order
+
+    pdata = rng.standard_normal((1, 8, 8, 6)).astype(np.float32)
+    fn, oshape = ramp_model((8, 8, 6), 2)
+    fx["tta/perm/data"] = pdata
+    fx["tta/perm/out"] = np.asarray(pred.predict_with_permutations(FunctionModel(fn, oshape), pdata))   # [C,x,y,z]
+    vol = rng.standard_normal((1, 20, 12, 9)).astype(np.float32)
+    fx["tta/perm_pw/vol"] = vol
+    fx["tta/perm_pw/out"] = pred.patch_wise_prediction(FunctionModel(fn, oshape), vol, patch_shape=(8, 8, 6),
+                                                       overlap_factor=0.5, batch_size=4, permute=True)
+
+    # predict_augment: skimage is absent, so the reference's contrast_augment (augment.py:123-126) gets the
+    # restated rescale_intensity injected — the RNG draw order, flips, transposes and scipy rotations are the
+    # reference's own code.
+    def rescale(d, lo, hi):
+        d = np.asarray(d)
+        omin, omax = d.min(), d.max()
+        return (((np.clip(d, lo, hi) - lo) / (hi - lo)) * (omax - omin) + omin).astype(d.dtype)
+    pred.contrast_augment = rescale
+    vol = rng.standard_normal((1, 16, 16, 8)).astype(np.float32)
+    fn, oshape = ramp_model((8, 8, 8), 1)
+    np.random.seed(1234)
+    fx["tta/augment/vol"] = vol
+    fx["tta/augment/out"] = pred.predict_augment(vol, FunctionModel(fn, oshape), 0.5, (8, 8, 8), num_augments=1)
+
     np.savez_compressed(os.path.join(OUT, "prediction_golden.npz"), **fx)
     print("wrote", os.path.join(OUT, "prediction_golden.npz"), len(fx), "arrays")
 

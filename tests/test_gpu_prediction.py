@@ -215,3 +215,43 @@ def test_native_2d_pipeline_with_truth_equals_own_predict_plus_oracle_reassembly
                                    prev_truth_index=1, prev_truth_size=1)
     assert out.shape == (48, 32, 10, 1) and out.dtype == np.float64
     assert np.array_equal(out, ref), float(np.abs(out - ref).max())
+
+
+def test_tta_wrappers_match_reference_goldens(golden, ctx):
+    """predict_flips / patch_wise_prediction(permute=True) / predict_augment (prediction.py:25-85,364-369):
+    host re-indexing around the device pipeline; goldens frozen from the reference's own functions."""
+    from fetal_net import prediction as P
+    fn, oshape = ramp_model((8, 8, 8), 1)
+    flips = P.predict_flips(golden["tta/flips/vol"], FunctionModel(fn, oshape), 0.5,
+                            {"patch_shape": [8, 8], "patch_depth": 8})
+    assert len(flips) == 8
+    assert np.array_equal(np.stack(flips), golden["tta/flips/out"])
+
+    fn2, oshape2 = ramp_model((8, 8, 6), 2)
+    out = P.patch_wise_prediction(FunctionModel(fn2, oshape2), golden["tta/perm_pw/vol"], patch_shape=(8, 8, 6),
+                                  overlap_factor=0.5, batch_size=4, permute=True)
+    ref = golden["tta/perm_pw/out"]
+    assert out.shape == ref.shape and out.dtype == np.float64
+    np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-6)    # fp32 mean over 48 keys, then fp64 overlap-add
+
+    np.random.seed(1234)                                           # same draws as make_golden.py
+    aug = P.predict_augment(golden["tta/augment/vol"], FunctionModel(fn, oshape), 0.5, (8, 8, 8), num_augments=1)
+    ref = golden["tta/augment/out"]
+    assert aug.shape == ref.shape
+    np.testing.assert_allclose(aug, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_predict_flips_native_model_consistency(ctx):
+    """Native model through predict_flips: entry () equals the plain call bit-for-bit (inference kernels are
+    reproducible), and every entry is the un-flipped prediction of the flipped volume."""
+    from fetal_net import prediction as P
+    from fetal_net.model import unet_model_3d
+    model = unet_model_3d(input_shape=(1, 16, 16, 16), n_base_filters=16, depth=2)
+    model.init_glorot_uniform(seed=3)
+    vol = np.random.default_rng(5).standard_normal((1, 24, 16, 16)).astype(np.float32)
+    cfg = {"patch_shape": [16, 16], "patch_depth": 16}
+    flips = P.predict_flips(vol, model, 0.5, cfg)
+    plain = P.patch_wise_prediction(model, vol, (16, 16, 16), overlap_factor=0.5).squeeze()
+    assert np.array_equal(flips[0], plain)
+    fl = P.patch_wise_prediction(model, np.flip(vol, 2)[...], (16, 16, 16), overlap_factor=0.5).squeeze()
+    assert np.array_equal(flips[2], np.flip(fl, 1))

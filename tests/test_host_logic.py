@@ -155,3 +155,43 @@ def test_callbacks_order():
     from fetal_net.training import EarlyStopping, ReduceLROnPlateau, get_callbacks
     cbs = get_callbacks("model", early_stopping_patience=3)
     assert isinstance(cbs[2], ReduceLROnPlateau) and isinstance(cbs[3], EarlyStopping)
+
+
+def test_permutation_helpers_match_golden_and_reference(golden):
+    """predict_with_permutations / permute_data / reverse_permute_data (prediction.py:364-369, augment.py:380-469):
+    pure host code around model.predict — checked against the golden frozen from the reference and, where the
+    reference tree exists, against the live functions."""
+    from tests.golden.make_golden import ramp_model
+    from oracle.ref_harness import FunctionModel, reference_available, load_reference_prediction
+    from fetal_net import prediction as P
+    keys = P.generate_permutation_keys()
+    assert len(keys) == 48
+    data = golden["tta/perm/data"]
+    for k in keys:
+        assert np.array_equal(P.reverse_permute_data(P.permute_data(data, k), k), data)
+    fn, oshape = ramp_model((8, 8, 6), 2)
+    out = P.predict_with_permutations(FunctionModel(fn, oshape), data)
+    ref = golden["tta/perm/out"]
+    assert out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, rtol=2e-6, atol=2e-6)
+    batch = np.stack([data, data[:, ::-1]])
+    both = P.predict(FunctionModel(fn, oshape), batch, permute=True)
+    assert both.shape == (2,) + ref.shape
+    np.testing.assert_allclose(both[0], ref, rtol=2e-6, atol=2e-6)
+    if reference_available():
+        rp = load_reference_prediction()
+        assert rp.generate_permutation_keys() == keys
+        for k in list(keys)[:12]:
+            assert np.array_equal(rp.permute_data(data, k), P.permute_data(data, k))
+            assert np.array_equal(rp.reverse_permute_data(data, k), P.reverse_permute_data(data, k))
+        np.testing.assert_allclose(rp.predict_with_permutations(FunctionModel(fn, oshape), data), out,
+                                   rtol=2e-6, atol=2e-6)
+
+
+def test_rescale_intensity_restatement():
+    # skimage.exposure.rescale_intensity(in_range=(lo,hi), out_range='image') semantics used by augment.py:123-126
+    from fetal_net.prediction import rescale_intensity_to_image_range
+    d = np.array([-2.0, -1.0, 0.0, 1.0, 4.0], np.float32)
+    out = rescale_intensity_to_image_range(d, -1.0, 1.0)
+    assert out.dtype == np.float32
+    np.testing.assert_allclose(out, [-2.0, -2.0, 1.0, 4.0, 4.0])
