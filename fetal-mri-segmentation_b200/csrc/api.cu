@@ -223,6 +223,13 @@ struct fm_model {
   std::vector<DevBuf<float>> isSeg;
   DevBuf<bf16> isRaw;
   DevBuf<float> isScratch, isAcc;
+  // Isensee training: per-layer raw conv outputs + (mean, 1/std) for the norm backward, SpatialDropout3D scales per
+  // level, gradient scratch (three per level, the 2f-channel upsample gradient, zero-inserted strided gradients)
+  std::vector<DevBuf<bf16>> isRawL, gIsA, gIsB, gIsC, gIsUp;
+  std::vector<DevBuf<float>> isStatsL, isDropL, gSeg;
+  DevBuf<bf16> gIsRaw, gIsZero;
+  float dropout_rate = 0.f;
+  uint64_t dropout_seed = 0x5EEDull;
   int kcode = 3;  // 3: Conv3D 3x3x3 (unet_model_3d); 31: Conv2D 3x3 on a Z = 1 volume (unet_model_2d)
   int pz = 2;     // pooling factor along z
   int cin_real = 1;
@@ -449,6 +456,12 @@ extern "C" int fm_model_destroy(fm_model* m) {
   for (auto* v : {&m->isIn, &m->isC1, &m->isSum, &m->isUp, &m->isU, &m->isLoc1, &m->isLoc2})
     for (auto& b : *v) b.release();
   for (auto& b : m->isSeg) b.release();
+  for (auto* v : {&m->isRawL, &m->gIsA, &m->gIsB, &m->gIsC, &m->gIsUp})
+    for (auto& b : *v) b.release();
+  for (auto* v : {&m->isStatsL, &m->isDropL, &m->gSeg})
+    for (auto& b : *v) b.release();
+  m->gIsRaw.release();
+  m->gIsZero.release();
   m->isRaw.release();
   m->isScratch.release();
   m->isAcc.release();
@@ -551,6 +564,14 @@ extern "C" int fm_model_get_weights(fm_model* m, int layer, float* kernel, float
 extern "C" int fm_model_get_grads(fm_model* m, int layer, float* kernel, float* bias) {
   return get_flat(m, m ? m->grads : nullptr, layer, kernel, bias);
 }
+extern "C" int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed) {
+  FM_CHECK(m, FM_EINVAL, "NULL model");
+  FM_CHECK(rate >= 0.f && rate < 1.f, FM_EINVAL, "dropout rate %g outside [0,1)", (double)rate);
+  m->dropout_rate = rate;
+  m->dropout_seed = seed;
+  return FM_OK;
+}
+
 extern "C" int fm_model_reset_optimizer(fm_model* m) {
   FM_CHECK(m, FM_EINVAL, "NULL model");
   FM_CUDA(cudaSetDevice(m->ctx->device));
@@ -581,13 +602,10 @@ static int refresh_packs(fm_model* m) {
   return FM_OK;
 }
 
-static int ensure_capacity_isensee(fm_model* m, int B);
+static int ensure_capacity_isensee(fm_model* m, int B, bool train);
 
 static int ensure_capacity(fm_model* m, int B, bool train) {
-  if (m->kind == 1) {
-    FM_CHECK(!train, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
-    return ensure_capacity_isensee(m, B);
-  }
+  if (m->kind == 1) return ensure_capacity_isensee(m, B, train);
   if (B <= m->cap && (!train || m->train_alloc)) return FM_OK;
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
   const int cap = std::max(B, m->cap);
@@ -733,7 +751,10 @@ static int mark_layer_done(fm_model* m, const Layer& l) {
   return FM_OK;
 }
 
+static int backward_isensee(fm_model* m, int B);
+
 static int backward(fm_model* m, int B) {
+  if (m->kind == 1) return backward_isensee(m, B);
   fm_ctx* ctx = m->ctx;
   const int D = m->depth();
   const int64_t n0 = (int64_t)B * m->vox(0);
@@ -885,27 +906,70 @@ extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* s
     if (l < m->nseg) add_conv("u%d_seg", l, f, 0, 1, 1, l, 1, false);
   }
   const size_t pb = (size_t)m->nparams * sizeof(float);
-  FM_CUDA(cudaMalloc((void**)&m->params, pb));
-  FM_CUDA(cudaMemset(m->params, 0, pb));
+  float** bufs[4] = {&m->params, &m->grads, &m->adam_m, &m->adam_v};
+  for (auto b : bufs) {
+    FM_CUDA(cudaMalloc((void**)b, pb));
+    FM_CUDA(cudaMemset(*b, 0, pb));
+  }
+  FM_CUDA(cudaMalloc((void**)&m->sums, 8 * sizeof(double)));
+  FM_CUDA(cudaMemset(m->sums, 0, 8 * sizeof(double)));
   int64_t pack_elems = 0;
   for (auto& l : m->layers)
-    if (!l.is_norm) pack_elems += (l.wcount() + 63) & ~(int64_t)63;
+    if (!l.is_norm) pack_elems += 2 * ((l.wcount() + 63) & ~(int64_t)63);
   FM_CUDA(cudaMalloc((void**)&m->wpack, (size_t)pack_elems * sizeof(bf16)));
   FM_CUDA(cudaMemset(m->wpack, 0, (size_t)pack_elems * sizeof(bf16)));
   bf16* wp = m->wpack;
   for (auto& l : m->layers) {
     if (l.is_norm) continue;
+    const int64_t padded = (l.wcount() + 63) & ~(int64_t)63;
     l.w_f = wp;
-    wp += (l.wcount() + 63) & ~(int64_t)63;
-    if (l.k != 3 || l.c1 < 16 || l.stride != 1) continue;
+    wp += padded;
+    if (l.c1 >= 16) {  // dgrad packs (none for the Cin = 1 first conv)
+      l.w_d0 = wp;
+      l.w_d1 = wp + (int64_t)l.c1 * l.taps() * l.cout;
+    }
+    wp += padded;
+    if (l.k != 3 || l.c1 < 16) continue;
+    // the backward of a stride-2 conv runs as a stride-1 dgrad over the zero-inserted gradient, one level finer
+    const int dl = l.stride == 2 ? l.level - 1 : l.level;
     const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
+    const int Xd = spec->X >> dl, Yd = spec->Y >> dl, Zd = spec->Z >> dl;
     const int cs[2] = {l.c1, l.c2};
-    if (use_march() && conv_march_supported(X, Y, Z, l.c1, l.c2, l.cout, l.k)) {
+    if (l.stride == 1 && use_march() && conv_march_supported(X, Y, Z, l.c1, l.c2, l.cout, l.k)) {
       l.march_f = true;
       for (int s = 0; s < (l.c2 ? 2 : 1); ++s)
         FM_CUDA(cudaMalloc((void**)&l.w_mf[s], (size_t)conv_march_pack_elems(cs[s], l.cout) * sizeof(bf16)));
     }
+    for (int s = 0; s < (l.c2 ? 2 : 1); ++s)
+      if (use_march() && conv_march_supported(Xd, Yd, Zd, l.cout, 0, cs[s], l.k)) {
+        l.march_d[s] = true;
+        FM_CUDA(cudaMalloc((void**)&l.w_md[s], (size_t)conv_march_pack_elems(l.cout, cs[s]) * sizeof(bf16)));
+      }
   }
+  m->layer_done.resize(m->layers.size());
+  for (auto& e : m->layer_done) FM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  {  // gradient buckets as for the plain U-Net: backward runs in reverse creation order
+    const int nl = (int)m->layers.size();
+    const int64_t target = m->nparams / 4 + 1;
+    int hi = nl - 1;
+    int64_t acc = 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      acc += m->layers[i].wcount() + m->layers[i].cout;
+      if (acc >= target || i == 0) {
+        m->buckets.push_back({i, hi});
+        hi = i - 1;
+        acc = 0;
+      }
+    }
+  }
+  m->isRawL.resize(m->layers.size());
+  m->isStatsL.resize(m->layers.size());
+  m->gIsA.resize(D);
+  m->gIsB.resize(D);
+  m->gIsC.resize(D);
+  m->gIsUp.resize(D);
+  m->isDropL.resize(D);
+  m->gSeg.resize(D);
   m->isIn.resize(D);
   m->isC1.resize(D);
   m->isSum.resize(D);
@@ -919,16 +983,39 @@ extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* s
   return FM_OK;
 }
 
-static int ensure_capacity_isensee(fm_model* m, int B) {
-  if (B <= m->cap) return FM_OK;
+static int ensure_capacity_isensee(fm_model* m, int B, bool train) {
+  if (B <= m->cap && (!train || m->train_alloc)) return FM_OK;
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  B = std::max(B, m->cap);
   const int D = m->depth(), nf = m->spec.n_base_filters;
   const size_t v0 = (size_t)m->vox(0);
+  if (train || m->train_alloc) {
+    FM_TRY(m->t_in.ensure((size_t)B * v0));
+    FM_TRY(m->dz.ensure((size_t)B * v0));
+    FM_TRY(m->gIsRaw.ensure((size_t)B * v0 * nf));
+    FM_TRY(m->gIsZero.ensure((size_t)B * v0 * nf * 2));
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+      const Layer& l = m->layers[i];
+      if (l.is_norm || (l.k == 1 && l.cout == 1)) continue;
+      FM_TRY(m->isRawL[i].ensure((size_t)B * m->vox(l.level) * l.cout));
+      FM_TRY(m->isStatsL[i].ensure((size_t)B * l.cout * 2));
+    }
+    for (int l = 0; l < D; ++l) {
+      const size_t n = (size_t)B * m->vox(l) * (nf << l);
+      FM_TRY(m->gIsA[l].ensure(n));
+      FM_TRY(m->gIsB[l].ensure(n));
+      FM_TRY(m->gIsC[l].ensure(n));
+      FM_TRY(m->isDropL[l].ensure((size_t)B * (nf << l)));
+      if (l < D - 1) FM_TRY(m->gIsUp[l].ensure(2 * n));
+      if (l >= 1 && l < m->nseg) FM_TRY(m->gSeg[l].ensure((size_t)B * m->vox(l)));
+    }
+    m->train_alloc = true;
+  }
   FM_TRY(m->x_in.ensure((size_t)B * v0));
   FM_TRY(m->prob.ensure((size_t)B * v0));
   FM_TRY(m->isAcc.ensure((size_t)B * v0));
   FM_TRY(m->isRaw.ensure((size_t)B * v0 * nf));
-  FM_TRY(m->isScratch.ensure((size_t)B * (nf << (D - 1)) * 2 * 1026));
+  FM_TRY(m->isScratch.ensure((size_t)B * (nf << (D - 1)) * 2 * 1028));
   for (int l = 0; l < D; ++l) {
     const size_t n = (size_t)B * m->vox(l) * (nf << l);
     FM_TRY(m->isIn[l].ensure(n));
@@ -946,16 +1033,23 @@ static int ensure_capacity_isensee(fm_model* m, int B) {
   return FM_OK;
 }
 
-// one Isensee conv block: Conv3D (+bias) -> raw -> InstanceNorm + LeakyReLU (+ residual add) -> y
+// one Isensee conv block: Conv3D (+bias) -> raw -> InstanceNorm + LeakyReLU (* dropout scale) (+ residual add) -> y.
+// A training pass keeps the raw conv output and the norm statistics of every block for the backward pass.
 static int isensee_block(fm_model* m, const Layer& l, const Layer& nl, const bf16* x1, const bf16* x2, const bf16* add,
-                         bf16* y, int B) {
+                         bf16* y, int B, const float* chan_scale = nullptr) {
   fm_ctx* ctx = m->ctx;
   const Dims5 d = m->dims(l.level, l.cout, B);
   const float* bias = m->params + l.b_off;
-  bf16* raw = m->isRaw.p;
-  if (l.march_f) {
-    FM_TRY(k_conv3d_march(ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, 0,
-                          l.cout, 0));
+  const int li = (int)(&l - &m->layers[0]);
+  bf16* raw = m->train_pass ? m->isRawL[li].p : m->isRaw.p;
+  float* stats = m->train_pass ? m->isStatsL[li].p : nullptr;
+  if (l.c1 == 1) {
+    // Cin = 1: bandwidth kernel, raw output (no activation)
+    FM_TRY(k_conv3d_simt_fprop(ctx, x1, 1, nullptr, l.w_f, bias, raw, nullptr, B, d.X, d.Y, d.Z, 1, 0, l.cout, 3, 0,
+                               nullptr));
+  } else if (l.march_f) {
+    FM_TRY((m->train_pass && l.cout <= 32 ? k_conv3d_march_shared : k_conv3d_march)(
+        ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, 0, l.cout, 0));
   } else if (conv_tc_supported(l.c1, l.c2, l.cout, l.k)) {
     FM_TRY(k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, l.k, 0,
                              l.cout, 0, l.stride, d.X * l.stride, d.Y * l.stride, d.Z * l.stride));
@@ -965,7 +1059,7 @@ static int isensee_block(fm_model* m, const Layer& l, const Layer& nl, const bf1
                                nullptr));
   }
   return k_instnorm_lrelu(ctx, raw, m->params + nl.w_off, m->params + nl.b_off, add, y, B, m->vox(l.level), l.cout,
-                          m->isScratch.p, m->isScratch.n);
+                          m->isScratch.p, m->isScratch.n, stats, chan_scale);
 }
 
 static int forward_isensee(fm_model* m, int B) {
@@ -981,17 +1075,16 @@ static int forward_isensee(fm_model* m, int B) {
   for (int l = 0; l < D; ++l) {
     const int i_in = LI("l%d_in", l), i_c1 = LI("l%d_ctx1", l), i_c2 = LI("l%d_ctx2", l);
     const Layer &lin = m->layers[i_in], &lc1 = m->layers[i_c1], &lc2 = m->layers[i_c2];
-    if (l == 0) {
-      // Cin = 1: bandwidth kernel, raw output (no activation), then the norm pass
-      const Dims5 d = m->dims(0, lin.cout, B);
-      FM_TRY(k_conv3d_simt_fprop(ctx, m->x_in.p, 1, nullptr, lin.w_f, m->params + lin.b_off, m->isRaw.p, nullptr, B, d.X,
-                                 d.Y, d.Z, 1, 0, lin.cout, 3, 0, nullptr));
-      FM_TRY(k_instnorm_lrelu(ctx, m->isRaw.p, m->params + m->layers[i_in + 1].w_off, m->params + m->layers[i_in + 1].b_off,
-                              nullptr, m->isIn[0].p, B, m->vox(0), lin.cout, m->isScratch.p, m->isScratch.n));
-    } else {
-      FM_TRY(isensee_block(m, lin, m->layers[i_in + 1], cur, nullptr, nullptr, m->isIn[l].p, B));
+    FM_TRY(isensee_block(m, lin, m->layers[i_in + 1], l == 0 ? (const bf16*)m->x_in.p : cur, nullptr, nullptr,
+                         m->isIn[l].p, B));
+    // SpatialDropout3D between the two context convs (isensee2017.py:103-105): training passes only
+    const float* drop = nullptr;
+    if (m->train_pass && m->dropout_rate > 0.f) {
+      FM_TRY(k_dropout_scale(ctx, m->isDropL[l].p, B * lc1.cout, m->dropout_rate,
+                             m->dropout_seed + (uint64_t)m->iterations * 64 + (uint64_t)l));
+      drop = m->isDropL[l].p;
     }
-    FM_TRY(isensee_block(m, lc1, m->layers[i_c1 + 1], m->isIn[l].p, nullptr, nullptr, m->isC1[l].p, B));
+    FM_TRY(isensee_block(m, lc1, m->layers[i_c1 + 1], m->isIn[l].p, nullptr, nullptr, m->isC1[l].p, B, drop));
     // context output + residual: summation = in_conv + context (isensee2017.py:55)
     FM_TRY(isensee_block(m, lc2, m->layers[i_c2 + 1], m->isC1[l].p, nullptr, m->isIn[l].p, m->isSum[l].p, B));
     cur = m->isSum[l].p;
@@ -1019,6 +1112,135 @@ static int forward_isensee(fm_model* m, int B) {
     acc = dst;
   }
   FM_TRY(k_sigmoid(ctx, acc, m->prob.p, (int64_t)B * m->vox(0)));
+  return FM_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Isensee backward. Per block: (InstanceNorm + LeakyReLU [+ dropout]) backward -> gradient of the raw conv output
+// (gIsRaw), bias / weight gradients, dgrad to the block input(s). Fan-outs: in_conv feeds ctx1 and the residual
+// add; summation[l] feeds the next level's stride-2 in_conv and the decoder's concat (or the first upsampling at
+// the bottom); loc2[l] feeds its segmentation head and the next upsampling. The stride-2 convs go backward as
+// stride-1 dgrad / wgrad over the zero-inserted gradient (k_zero_insert), one level finer.
+// Gradients are produced in reverse layer-creation order, so the all-reduce buckets work as for the plain U-Net.
+// ---------------------------------------------------------------------------------------------
+static int is_wgrad(fm_model* m, const Layer& l, int level, const bf16* x1, const bf16* x2, const bf16* dy, int B) {
+  fm_ctx* ctx = m->ctx;
+  const Dims5 d = m->dims(level, l.cout, B);
+  float* dw = m->grads + l.w_off;
+  const bf16* xs[2] = {x1, x2};
+  const int cs[2] = {l.c1, l.c2};
+  int cofs = 0;
+  for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
+    if (use_march() && conv_wgrad_march_supported(d.X, d.Y, d.Z, cs[s], l.cout, l.k))
+      FM_TRY(k_conv3d_wgrad_march(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout));
+    else if (conv_tc_supported(cs[s], 0, l.cout, l.k))
+      FM_TRY(k_conv3d_tc_wgrad(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout, l.k));
+    else
+      FM_TRY(k_conv3d_simt_wgrad(ctx, xs[s], 0, dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout, l.k));
+    cofs += cs[s];
+  }
+  return FM_OK;
+}
+
+static int is_dgrad(fm_model* m, const Layer& l, int level, int src, const bf16* dy, bf16* dx, int B) {
+  fm_ctx* ctx = m->ctx;
+  const Dims5 d = m->dims(level, l.cout, B);
+  const int cs = src == 0 ? l.c1 : l.c2;
+  const bf16* wd = src == 0 ? l.w_d0 : l.w_d1;
+  if (l.march_d[src])
+    return (cs <= 32 ? k_conv3d_march_shared : k_conv3d_march)(ctx, dy, nullptr, l.w_md[src], nullptr, nullptr, dx,
+                                                               nullptr, B, d.X, d.Y, d.Z, l.cout, 0, cs, 0, cs, 0);
+  if (conv_tc_supported(l.cout, 0, cs, l.k))
+    return k_conv3d_tc_fprop(ctx, dy, nullptr, wd, nullptr, dx, nullptr, B, d.X, d.Y, d.Z, l.cout, 0, cs, l.k, 0, cs, 0);
+  return k_conv3d_simt_fprop(ctx, dy, 0, nullptr, wd, nullptr, dx, nullptr, B, d.X, d.Y, d.Z, l.cout, 0, cs, l.k, 0,
+                             nullptr);
+}
+
+// norm + activation backward of block `li` -> m->gIsRaw (gradient of the raw conv output); gamma/beta/bias gradients
+static int is_block_bwd(fm_model* m, int li, const bf16* gy, const bf16* gy2, const float* chan_scale, int B) {
+  const Layer &l = m->layers[li], &nl = m->layers[li + 1];
+  FM_TRY(k_instnorm_lrelu_bwd(m->ctx, m->isRawL[li].p, m->isStatsL[li].p, m->params + nl.w_off, m->params + nl.b_off, gy,
+                              gy2, chan_scale, m->gIsRaw.p, m->grads + nl.w_off, m->grads + nl.b_off, B, m->vox(l.level),
+                              l.cout, m->isScratch.p, m->isScratch.n));
+  FM_TRY(mark_layer_done(m, nl));
+  return k_bias_grad(m->ctx, m->gIsRaw.p, m->grads + l.b_off, (int64_t)B * m->vox(l.level), l.cout);
+}
+
+static int backward_isensee(fm_model* m, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int D = m->depth();
+  const int64_t n0 = (int64_t)B * m->vox(0);
+  auto LI = [&](const char* fmt, int d) {
+    char nm[32];
+    snprintf(nm, sizeof(nm), fmt, d);
+    return layer_index(m, nm);
+  };
+  FM_TRY(k_zero(ctx, m->grads, (size_t)m->nparams * sizeof(float)));
+  // d(loss)/d(summed logits); the deep-supervision sum hands the same gradient, 2^3 sum-pooled, to every head
+  FM_TRY(k_dice_bwd(ctx, m->prob.p, m->t_in.p, m->sums, n0, m->dz.p, 1));
+  std::vector<const float*> gseg(D, nullptr);
+  gseg[0] = m->dz.p;
+  for (int l = 1; l < m->nseg; ++l) {
+    const Dims5 d = m->dims(l, 1, B);
+    FM_TRY(k_sumpool_f32(ctx, gseg[l - 1], m->gSeg[l].p, B, d.X, d.Y, d.Z));
+    gseg[l] = m->gSeg[l].p;
+  }
+  for (int l = 0; l <= D - 2; ++l) {
+    const int i_up = LI("u%d_up", l), i_l1 = LI("u%d_loc1", l), i_l2 = LI("u%d_loc2", l);
+    const Layer &lup = m->layers[i_up], &ll1 = m->layers[i_l1], &ll2 = m->layers[i_l2];
+    // gradient of loc2[l] (gIsA[l]): upsampling path (already stored for l > 0) + segmentation head
+    if (l < m->nseg) {
+      const Layer& ls = m->layers[LI("u%d_seg", l)];
+      FM_TRY(k_head_bwd(ctx, m->isLoc2[l].p, gseg[l], m->params + ls.w_off, m->gIsA[l].p, m->grads + ls.w_off,
+                        m->grads + ls.b_off, (int64_t)B * m->vox(l), ls.c1, l > 0 ? 2 : 1));
+      FM_TRY(mark_layer_done(m, ls));
+    }
+    FM_TRY(is_block_bwd(m, i_l2, m->gIsA[l].p, nullptr, nullptr, B));
+    FM_TRY(is_wgrad(m, ll2, l, m->isLoc1[l].p, nullptr, m->gIsRaw.p, B));
+    FM_TRY(mark_layer_done(m, ll2));
+    FM_TRY(is_dgrad(m, ll2, l, 0, m->gIsRaw.p, m->gIsB[l].p, B));
+    FM_TRY(is_block_bwd(m, i_l1, m->gIsB[l].p, nullptr, nullptr, B));
+    FM_TRY(is_wgrad(m, ll1, l, m->isSum[l].p, m->isU[l].p, m->gIsRaw.p, B));
+    FM_TRY(mark_layer_done(m, ll1));
+    FM_TRY(is_dgrad(m, ll1, l, 0, m->gIsRaw.p, m->gIsC[l].p, B));  // skip part of d(summation[l])
+    FM_TRY(is_dgrad(m, ll1, l, 1, m->gIsRaw.p, m->gIsA[l].p, B));  // d(up block output)
+    FM_TRY(is_block_bwd(m, i_up, m->gIsA[l].p, nullptr, nullptr, B));
+    FM_TRY(is_wgrad(m, lup, l, m->isUp[l].p, nullptr, m->gIsRaw.p, B));
+    FM_TRY(mark_layer_done(m, lup));
+    FM_TRY(is_dgrad(m, lup, l, 0, m->gIsRaw.p, m->gIsUp[l].p, B));
+    bf16* gdst = (l + 1 == D - 1) ? m->gIsC[D - 1].p : m->gIsA[l + 1].p;
+    FM_TRY(k_upsample3d_bwd(ctx, m->gIsUp[l].p, nullptr, gdst, m->dims(l + 1, lup.c1, B), lup.c1, 0, 2));
+  }
+  for (int l = D - 1; l >= 0; --l) {
+    const int i_in = LI("l%d_in", l), i_c1 = LI("l%d_ctx1", l), i_c2 = LI("l%d_ctx2", l);
+    const Layer &lin = m->layers[i_in], &lc1 = m->layers[i_c1], &lc2 = m->layers[i_c2];
+    const bf16* gsum = m->gIsC[l].p;  // complete d(summation[l])
+    FM_TRY(is_block_bwd(m, i_c2, gsum, nullptr, nullptr, B));
+    FM_TRY(is_wgrad(m, lc2, l, m->isC1[l].p, nullptr, m->gIsRaw.p, B));
+    FM_TRY(mark_layer_done(m, lc2));
+    FM_TRY(is_dgrad(m, lc2, l, 0, m->gIsRaw.p, m->gIsA[l].p, B));
+    const float* drop = m->dropout_rate > 0.f ? m->isDropL[l].p : nullptr;
+    FM_TRY(is_block_bwd(m, i_c1, m->gIsA[l].p, nullptr, drop, B));
+    FM_TRY(is_wgrad(m, lc1, l, m->isIn[l].p, nullptr, m->gIsRaw.p, B));
+    FM_TRY(mark_layer_done(m, lc1));
+    FM_TRY(is_dgrad(m, lc1, l, 0, m->gIsRaw.p, m->gIsB[l].p, B));
+    // in_conv output feeds ctx1 and the residual add
+    FM_TRY(is_block_bwd(m, i_in, m->gIsB[l].p, gsum, nullptr, B));
+    if (l == 0) {
+      const Dims5 dd = m->dims(0, lin.cout, B);
+      FM_TRY(k_conv3d_simt_wgrad(ctx, m->x_in.p, 1, m->gIsRaw.p, m->grads + lin.w_off, B, dd.X, dd.Y, dd.Z, 1, 1, 0,
+                                 lin.cout, 3));
+      FM_TRY(mark_layer_done(m, lin));
+    } else {
+      FM_TRY(k_zero_insert(ctx, m->gIsRaw.p, m->gIsZero.p, m->dims(l, lin.cout, B)));
+      FM_TRY(is_wgrad(m, lin, l - 1, m->isSum[l - 1].p, nullptr, m->gIsZero.p, B));
+      FM_TRY(mark_layer_done(m, lin));
+      FM_TRY(is_dgrad(m, lin, l - 1, 0, m->gIsZero.p, m->gIsA[l - 1].p, B));
+      FM_TRY(k_add_bf16(ctx, m->gIsC[l - 1].p, m->gIsA[l - 1].p, m->gIsC[l - 1].p,
+                        (int64_t)B * m->vox(l - 1) * lin.c1));
+    }
+  }
   return FM_OK;
 }
 
@@ -1273,7 +1495,6 @@ extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int
 
 extern "C" int fm_train_backward(fm_model* m) {
   FM_CHECK(m, FM_EINVAL, "NULL model");
-  FM_CHECK(m->kind == 0, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
   FM_CHECK(m->fwd_valid, FM_ESTATE, "fm_train_backward called without a preceding fm_train_forward");
   FM_CUDA(cudaSetDevice(m->ctx->device));
   m->train_pass = true;
@@ -1286,7 +1507,6 @@ extern "C" int fm_train_backward(fm_model* m) {
 
 extern "C" int fm_train_apply(fm_model* m, float lr, uint64_t after_stream, float out_metrics[4]) {
   FM_CHECK(m, FM_EINVAL, "NULL model");
-  FM_CHECK(m->kind == 0, FM_EINVAL, "isensee2017_model_3d: training is not built yet (forward / inference only)");
   fm_ctx* ctx = m->ctx;
   FM_CUDA(cudaSetDevice(ctx->device));
   if (after_stream) {

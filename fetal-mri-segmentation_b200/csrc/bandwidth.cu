@@ -309,8 +309,9 @@ __global__ void __launch_bounds__(kThreads) instnorm_partial_kernel(const bf16* 
 
 // scale/shift per (n, c): y = x * scale + shift with scale = gamma / (sqrt(var) + eps), shift = beta - mean * scale
 __global__ void instnorm_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, float* __restrict__ ss, int N, int C,
-                                      int blocks_per_sample, double inv_count, float eps) {
+                                      const float* __restrict__ beta, float* __restrict__ ss,
+                                      float* __restrict__ stats, int N, int C, int blocks_per_sample,
+                                      double inv_count, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
@@ -325,11 +326,15 @@ __global__ void instnorm_final_kernel(const float* __restrict__ part, const floa
   const double scale = (double)gamma[c] / (sqrt(var) + (double)eps);
   ss[2 * i] = (float)scale;
   ss[2 * i + 1] = (float)((double)beta[c] - mean * scale);
+  if (stats != nullptr) {  // kept for the backward pass: (mean, 1 / (sqrt(var) + eps))
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / (sqrt(var) + (double)eps));
+  }
 }
 
 __global__ void instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ ss,
-                                      const bf16* __restrict__ add, bf16* __restrict__ y, int64_t vox_per_sample,
-                                      int C, int N, float slope) {
+                                      const bf16* __restrict__ add, const float* __restrict__ chan_scale,
+                                      bf16* __restrict__ y, int64_t vox_per_sample, int C, int N, float slope) {
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * vox_per_sample * c8n;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,12 +352,225 @@ __global__ void instnorm_apply_kernel(const bf16* __restrict__ x, const float* _
     f[2 * i] = u > 0.f ? u : slope * u;
     f[2 * i + 1] = w > 0.f ? w : slope * w;
   }
+  if (chan_scale != nullptr) {  // SpatialDropout3D: one keep/scale factor per (sample, channel)
+    const float4* cp = reinterpret_cast<const float4*>(chan_scale + (int64_t)n * C + c8 * 8);
+    const float4 s0 = __ldg(cp), s1 = __ldg(cp + 1);
+    f[0] *= s0.x, f[1] *= s0.y, f[2] *= s0.z, f[3] *= s0.w;
+    f[4] *= s1.x, f[5] *= s1.y, f[6] *= s1.z, f[7] *= s1.w;
+  }
   if (add != nullptr) {
     unpack8(ldg16(add + v * C + c8 * 8), a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] += a[i];
   }
   stg16(y + v * C + c8 * 8, pack8(f));
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm + LeakyReLU backward. With s = sqrt(var) + eps, xh = (x - mean) / s, z = gamma * xh + beta and
+// g = dL/dz = (gy [+ gy2]) * chan_scale * (z > 0 ? 1 : slope):
+//   dgamma = sum g * xh,  dbeta = sum g,
+//   dx = (gamma / s) * (g - mean_v(g) - xh * (s / sigma) * mean_v(g * xh))      (eps sits on the STD, so the
+//   variance term carries s / sigma = 1 + eps / sigma instead of 1)
+// Two passes over (x, gy): per-(sample, block) partial sums of (g, g * xh), fp64 combine, then the apply pass.
+// ---------------------------------------------------------------------------------------------
+struct NormBwdArgs {
+  const bf16* x;          // raw conv output
+  const float* stats;     // [N][C][2] (mean, 1/s)
+  const float* gamma;
+  const float* beta;
+  const bf16* gy;
+  const bf16* gy2;        // optional second gradient (fan-out of the block output)
+  const float* chan_scale;
+  int64_t vox_per_sample;
+  int C;
+  float slope;
+};
+
+__device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, int n, int64_t v, int c8, float g[8], float xh[8]) {
+  float x[8], t[8];
+  unpack8(ldg16(a.x + v * a.C + c8 * 8), x);
+  unpack8(ldg16(a.gy + v * a.C + c8 * 8), g);
+  if (a.gy2 != nullptr) {
+    unpack8(ldg16(a.gy2 + v * a.C + c8 * 8), t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += t[i];
+  }
+  const float4* sp = reinterpret_cast<const float4*>(a.stats + ((int64_t)n * a.C + c8 * 8) * 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 st = __ldg(sp + i);  // (mean, 1/s) of two channels
+    xh[2 * i] = (x[2 * i] - st.x) * st.y;
+    xh[2 * i + 1] = (x[2 * i + 1] - st.z) * st.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = c8 * 8 + i;
+    const float z = __ldg(a.gamma + ch) * xh[i] + __ldg(a.beta + ch);
+    float s = z > 0.f ? 1.f : a.slope;
+    if (a.chan_scale != nullptr) s *= __ldg(a.chan_scale + (int64_t)n * a.C + ch);
+    g[i] *= s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) instnorm_bwd_partial_kernel(NormBwdArgs a, float* __restrict__ part,
+                                                                        int64_t vox_per_block, int blocks_per_sample) {
+  extern __shared__ float sh[];  // [kThreads][16]
+  const int C = a.C, c8n = C >> 3;
+  const int lanes = kThreads / c8n;
+  const int c8 = threadIdx.x % c8n, l = threadIdx.x / c8n;
+  const int n = blockIdx.y, blk = blockIdx.x;
+  const int64_t v0 = (int64_t)n * a.vox_per_sample + (int64_t)blk * vox_per_block;
+  const int64_t v1 = min((int64_t)(n + 1) * a.vox_per_sample, v0 + vox_per_block);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  if (l < lanes)
+    for (int64_t v = v0 + l; v < v1; v += lanes) {
+      float g[8], xh[8];
+      norm_bwd_g(a, n, v, c8, g, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += g[i];
+        s2[i] += g[i] * xh[i];
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh[threadIdx.x * 16 + i] = s1[i];
+    sh[threadIdx.x * 16 + 8 + i] = s2[i];
+  }
+  __syncthreads();
+  if (l == 0) {
+    for (int k = 1; k < lanes; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += sh[(k * c8n + c8) * 16 + i];
+        s2[i] += sh[(k * c8n + c8) * 16 + 8 + i];
+      }
+    float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + c8 * 8) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[2 * i] = s1[i];
+      o[2 * i + 1] = s2[i];
+    }
+  }
+}
+
+// coef[n][c] = (gamma / s, mean(g), (s / sigma) * mean(g * xh)); dgamma / dbeta accumulate over the samples
+__global__ void instnorm_bwd_final_kernel(const float* __restrict__ part, const float* __restrict__ stats,
+                                          const float* __restrict__ gamma, float* __restrict__ coef,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C,
+                                          int blocks_per_sample, double inv_count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i % C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < blocks_per_sample; ++b) {
+    const float* o = part + (((int64_t)n * blocks_per_sample + b) * C + c) * 2;
+    s1 += (double)o[0];
+    s2 += (double)o[1];
+  }
+  const double inv_s = (double)stats[2 * i + 1];
+  const double s = 1.0 / inv_s;
+  const double sigma = fmax(s - (double)eps, 1e-12);
+  coef[4 * i] = (float)((double)gamma[c] * inv_s);
+  coef[4 * i + 1] = (float)(s1 * inv_count);
+  coef[4 * i + 2] = (float)(s / sigma * s2 * inv_count);
+  coef[4 * i + 3] = 0.f;
+  atomicAdd(dgamma + c, (float)s2);
+  atomicAdd(dbeta + c, (float)s1);
+}
+
+__global__ void __launch_bounds__(kThreads) instnorm_bwd_apply_kernel(NormBwdArgs a, const float* __restrict__ coef,
+                                                                      bf16* __restrict__ dx, int N) {
+  const int c8n = a.C >> 3;
+  const int64_t total = (int64_t)N * a.vox_per_sample * c8n;
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= total) return;
+  const int c8 = (int)(gi % c8n);
+  const int64_t v = gi / c8n;
+  const int n = (int)(v / a.vox_per_sample);
+  float g[8], xh[8];
+  norm_bwd_g(a, n, v, c8, g, xh);
+  const float4* cp = reinterpret_cast<const float4*>(coef + ((int64_t)n * a.C + c8 * 8) * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 k = __ldg(cp + i);
+    g[i] = k.x * (g[i] - k.y - xh[i] * k.z);
+  }
+  stg16(dx + v * a.C + c8 * 8, pack8(g));
+}
+
+// transposed-conv helper for the stride-2 in-convs: fine[2v + 1] = coarse[v] per axis, zero elsewhere. A stride-1
+// 'same' dgrad / wgrad over this tensor equals the stride-2 (TF SAME, pad_before = 0) conv's dgrad / wgrad.
+__global__ void zero_insert_kernel(const bf16* __restrict__ coarse, bf16* __restrict__ fine, int N, int X, int Y, int Z,
+                                   int C) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)N * X * Y * Z * 8 * c8n;  // fine voxels x 16-byte groups
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= total) return;
+  const int c8 = (int)(gi % c8n);
+  int64_t v = gi / c8n;
+  const int z = (int)(v % (2 * Z));
+  int64_t r = v / (2 * Z);
+  const int y = (int)(r % (2 * Y));
+  r /= 2 * Y;
+  const int x = (int)(r % (2 * X));
+  const int n = (int)(r / (2 * X));
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if ((x & y & z & 1) != 0) {
+    const int64_t vc = (((int64_t)n * X + (x >> 1)) * Y + (y >> 1)) * Z + (z >> 1);
+    o = ldg16(coarse + vc * C + c8 * 8);
+  }
+  stg16(fine + v * C + c8 * 8, o);
+}
+
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
+                                int64_t n8) {
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n8) return;
+  float fa[8], fb[8];
+  unpack8(ldg16(a + gi * 8), fa);
+  unpack8(ldg16(b + gi * 8), fb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fa[i] += fb[i];
+  stg16(out + gi * 8, pack8(fa));
+}
+
+// gradient of the nearest-neighbour upsampling of a single-channel fp32 map: 2^3 sum-pool
+__global__ void sumpool_f32_kernel(const float* __restrict__ fine, float* __restrict__ coarse, int N, int X, int Y,
+                                   int Z) {  // coarse extents
+  const int64_t total = (int64_t)N * X * Y * Z;
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= total) return;
+  const int z = (int)(gi % Z);
+  int64_t r = gi / Z;
+  const int y = (int)(r % Y);
+  r /= Y;
+  const int x = (int)(r % X);
+  const int n = (int)(r / X);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t vf = (((int64_t)n * 2 * X + 2 * x + (k >> 1)) * 2 * Y + 2 * y + (k & 1)) * 2 * Z + 2 * z;
+    const float2 t = __ldg(reinterpret_cast<const float2*>(fine + vf));
+    acc += t.x + t.y;
+  }
+  coarse[gi] = acc;
+}
+
+// SpatialDropout3D keep mask: scale[n][c] = keep ? 1 / (1 - rate) : 0, from a counter-based hash of (seed, index)
+__global__ void dropout_scale_kernel(float* __restrict__ scale, int n, float rate, uint64_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t h = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);  // splitmix64
+  h = (h ^ (h >> 30)) * 0xBF58476D1CE4E5B9ull;
+  h = (h ^ (h >> 27)) * 0x94D049BB133111EBull;
+  h ^= h >> 31;
+  const float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+  scale[i] = u >= rate ? 1.f / (1.f - rate) : 0.f;
 }
 
 // segmentation-head plumbing of the Isensee net (isensee2017.py:68-79): fp32 single-channel maps
@@ -843,8 +1061,69 @@ int k_divide_by_count(fm_ctx* ctx, double* out, const int16_t* count, int64_t nv
 }
 
 // x: raw conv output [N][vox][C] bf16 -> y = LeakyReLU(InstanceNorm(x)) (+ add). `scratch` >= N*C*2*(blocks+1) floats.
+static int norm_blocks(int64_t vox_per_sample, int64_t* vpb) {
+  int bps = (int)std::min<int64_t>(std::max<int64_t>(1, vox_per_sample / 2048), 1024);
+  *vpb = ceil_div64(vox_per_sample, bps);
+  return (int)ceil_div64(vox_per_sample, *vpb);
+}
+
+// gradient of k_instnorm_lrelu w.r.t. the raw conv output (dx), gamma and beta (accumulated into dgamma / dbeta).
+// `scratch` >= N*C*(2*blocks + 4) floats.
+int k_instnorm_lrelu_bwd(fm_ctx* ctx, const bf16* x, const float* stats, const float* gamma, const float* beta,
+                         const bf16* gy, const bf16* gy2, const float* chan_scale, bf16* dx, float* dgamma,
+                         float* dbeta, int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats) {
+  FM_CHECK(C % 8 == 0 && C <= 8 * kThreads, FM_EINVAL, "instnorm bwd: C=%d unsupported", C);
+  int64_t vpb;
+  const int bps = norm_blocks(vox_per_sample, &vpb);
+  const size_t need = (size_t)N * C * (2 * (size_t)bps + 4);
+  FM_CHECK(scratch_floats >= need, FM_EINVAL, "instnorm bwd: scratch too small (%zu < %zu floats)", scratch_floats, need);
+  float* part = scratch;
+  float* coef = scratch + (size_t)N * C * 2 * bps;
+  NormBwdArgs a{x, stats, gamma, beta, gy, gy2, chan_scale, vox_per_sample, C, 0.3f};
+  ProfScope prof(ctx, "instnorm_lrelu_bwd", 0.0, (double)N * vox_per_sample * C * (gy2 ? 14.0 : 10.0));
+  instnorm_bwd_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(a, part, vpb, bps);
+  FM_LAUNCH_OK(ctx);
+  instnorm_bwd_final_kernel<<<ceil_div(N * C, 128), 128, 0, ctx->stream>>>(part, stats, gamma, coef, dgamma, dbeta, N, C,
+                                                                            bps, 1.0 / (double)vox_per_sample, 1e-3f);
+  FM_LAUNCH_OK(ctx);
+  const int64_t total = (int64_t)N * vox_per_sample * (C / 8);
+  instnorm_bwd_apply_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(a, coef, dx, N);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_zero_insert(fm_ctx* ctx, const bf16* coarse, bf16* fine, Dims5 c) {
+  FM_CHECK(c.C % 8 == 0, FM_EINVAL, "zero_insert: C=%d", c.C);
+  ProfScope prof(ctx, "zero_insert", 0.0, (double)c.elems() * 2.0 * 9.0);
+  zero_insert_kernel<<<grid_for(c.elems()), kThreads, 0, ctx->stream>>>(coarse, fine, c.N, c.X, c.Y, c.Z, c.C);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_add_bf16(fm_ctx* ctx, const bf16* a, const bf16* b, bf16* out, int64_t n) {
+  FM_CHECK(n % 8 == 0, FM_EINVAL, "add_bf16: n %% 8");
+  ProfScope prof(ctx, "add_bf16", 0.0, (double)n * 6.0);
+  add_bf16_kernel<<<grid_for(n / 8), kThreads, 0, ctx->stream>>>(a, b, out, n / 8);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_sumpool_f32(fm_ctx* ctx, const float* fine, float* coarse, int N, int X, int Y, int Z) {
+  ProfScope prof(ctx, "sumpool_f32", 0.0, (double)N * X * Y * Z * 36.0);
+  sumpool_f32_kernel<<<grid_for((int64_t)N * X * Y * Z), kThreads, 0, ctx->stream>>>(fine, coarse, N, X, Y, Z);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_dropout_scale(fm_ctx* ctx, float* scale, int n, float rate, uint64_t seed) {
+  dropout_scale_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(scale, n, rate, seed);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
 int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, const bf16* add, bf16* y,
-                     int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats) {
+                     int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats, float* stats,
+                     const float* chan_scale) {
   FM_CHECK(C % 8 == 0 && C <= 8 * kThreads, FM_EINVAL, "instnorm: C=%d unsupported", C);
   int bps = (int)std::min<int64_t>(std::max<int64_t>(1, vox_per_sample / 2048), 1024);
   const int64_t vpb = ceil_div64(vox_per_sample, bps);
@@ -857,11 +1136,12 @@ int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float
   instnorm_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(x, part, vox_per_sample,
                                                                                                C, vpb, bps);
   FM_LAUNCH_OK(ctx);
-  instnorm_final_kernel<<<ceil_div(N * C, 128), 128, 0, ctx->stream>>>(part, gamma, beta, ss, N, C, bps,
+  instnorm_final_kernel<<<ceil_div(N * C, 128), 128, 0, ctx->stream>>>(part, gamma, beta, ss, stats, N, C, bps,
                                                                         1.0 / (double)vox_per_sample, 1e-3f);
   FM_LAUNCH_OK(ctx);
   const int64_t total = (int64_t)N * vox_per_sample * (C / 8);
-  instnorm_apply_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, ss, add, y, vox_per_sample, C, N, 0.3f);
+  instnorm_apply_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, ss, add, chan_scale, y, vox_per_sample, C, N,
+                                                                        0.3f);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -135,8 +135,18 @@ int k_adam(fm_ctx*, float* p, const float* g, float* m, float* v, int64_t n, int
            float lr);
 int k_zero(fm_ctx*, void* p, size_t bytes);
 // InstanceNormalization(axis=1) + LeakyReLU(0.3) (+ residual add) of a raw conv output (Isensee blocks)
+// `stats` (optional, [N][C][2]) receives (mean, 1/(std+eps)) for the backward pass; `chan_scale` (optional, [N][C])
+// is the SpatialDropout3D keep/scale factor applied after the activation
 int k_instnorm_lrelu(fm_ctx*, const bf16* x, const float* gamma, const float* beta, const bf16* add, bf16* y, int N,
-                     int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats);
+                     int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats, float* stats = nullptr,
+                     const float* chan_scale = nullptr);
+int k_instnorm_lrelu_bwd(fm_ctx*, const bf16* x, const float* stats, const float* gamma, const float* beta,
+                         const bf16* gy, const bf16* gy2, const float* chan_scale, bf16* dx, float* dgamma,
+                         float* dbeta, int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats);
+int k_zero_insert(fm_ctx*, const bf16* coarse, bf16* fine, Dims5 coarse_dims);
+int k_add_bf16(fm_ctx*, const bf16* a, const bf16* b, bf16* out, int64_t n);
+int k_sumpool_f32(fm_ctx*, const float* fine, float* coarse, int N, int X, int Y, int Z);
+int k_dropout_scale(fm_ctx*, float* scale, int n, float rate, uint64_t seed);
 int k_seg_upsample_add(fm_ctx*, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z);
 int k_sigmoid(fm_ctx*, const float* z, float* p, int64_t n);
 // out[(patch voxel (i,j)) * out_pitch + out_cofs + k]: with out_pitch = patch[2], out_cofs = 0 this is the plain
@@ -165,7 +175,7 @@ int k_head_fwd(fm_ctx*, const bf16* x, const float* w, const float* b, float* p,
                int C, int apply_sigmoid = 1);
 // head backward: dx[v,c] = dz[v] * w[c] * (x[v,c] > 0); dw[c] = sum_v dz[v] x[v,c]; db = sum dz
 int k_head_bwd(fm_ctx*, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
-               float* db, int64_t voxels, int C);
+               float* db, int64_t voxels, int C, int mode = 0);
 // weight repack: master fp32 [Cout][taps][Cin] -> bf16 fprop pack (same layout) and bf16 dgrad
 // pack(s) [Cin_s][taps flipped][Cout] per source
 int k_repack_weights(fm_ctx*, const float* w, bf16* w_f, bf16* w_d0, bf16* w_d1, int Cout, int taps,

@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
                                                             bf16* __restrict__ dx,
                                                             float* __restrict__ dw,
                                                             float* __restrict__ db, int64_t voxels,
-                                                            int C) {
+                                                            int C, int mode) {
+  // mode 0: dx = g*w masked by ReLU(x) (plain U-Net head); 1: dx = g*w; 2: dx += g*w (Isensee seg heads)
   const int lpv = C >> 3;
   const int sub = threadIdx.x % lpv;
   float wv[8], gw[8];
@@ -365,10 +366,19 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
       const float2 f = __bfloat1622float2(h[i]);
       gw[2 * i] += g * f.x;
       gw[2 * i + 1] += g * f.y;
-      oh[i] = __floats2bfloat162_rn(f.x > 0.f ? g * wv[2 * i] : 0.f,
-                                    f.y > 0.f ? g * wv[2 * i + 1] : 0.f);
+      oh[i] = __floats2bfloat162_rn(mode != 0 || f.x > 0.f ? g * wv[2 * i] : 0.f,
+                                    mode != 0 || f.y > 0.f ? g * wv[2 * i + 1] : 0.f);
     }
     if (sub == 0) gb += g;
+    if (mode == 2) {
+      const uint4 prev = *reinterpret_cast<const uint4*>(dx + v * C + sub * 8);
+      const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = __bfloat1622float2(ph[i]), b = __bfloat1622float2(oh[i]);
+        oh[i] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+      }
+    }
     *reinterpret_cast<uint4*>(dx + v * C + sub * 8) = o;
   }
   // block reduction: threads with equal `sub` hold partial sums of the same 8 channels
@@ -514,14 +524,14 @@ int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float
 }
 
 int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
-               float* db, int64_t voxels, int C) {
+               float* db, int64_t voxels, int C, int mode) {
   FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
            "head_bwd: channel count %d must be a power of two in [8,256]", C);
   const int lpv = C / 8;
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 8);
   ProfScope prof(ctx, "head_bwd", 4.0 * C * (double)voxels, (double)voxels * (C * 4.0 + 4.0));
-  head_bwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, dz, w, dx, dw, db, voxels, C);
+  head_bwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, dz, w, dx, dw, db, voxels, C, mode);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

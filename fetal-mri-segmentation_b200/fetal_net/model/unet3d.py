@@ -26,16 +26,17 @@ class Model:
     """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
 
     def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
-                 device=None, ndim=3, isensee_levels=None):
+                 device=None, ndim=3, isensee_levels=None, dropout_rate=0.0, dropout_seed=0x5EED):
         lib = _lib.load()
         self._ctx = _lib.get_context(device)
         self.ndim = int(ndim)
         h = _lib.c_vp()
-        self.trainable = isensee_levels is None
+        self.trainable = True
         if isensee_levels is not None:
             in_ch, X, Y, Z = [int(v) for v in input_shape]
             spec = _lib.Isensee3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(isensee_levels), int(n_labels))
             _lib.check(lib.fm_model_create_isensee3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            _lib.check(lib.fm_model_set_dropout(h, float(dropout_rate), int(dropout_seed)))
             self.input_shape = (None, in_ch, X, Y, Z)
             self.output_shape = (None, int(n_labels), X, Y, Z)
         elif self.ndim == 3:
@@ -314,12 +315,13 @@ def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, dept
                          n_segmentation_levels=1, n_labels=1, optimizer=None, initial_learning_rate=5e-4,
                          loss_function=dice_coefficient_loss, activation_name="sigmoid", mask_shape=None, **kargs):
     """Same signature and defaults as the reference builder (fetal_net/model/unet3d/isensee2017.py:15-18).
-    Forward / inference runs on the device (SpatialDropout3D is the identity at inference, so `dropout_rate`
-    has no effect there); training this model family is on the §8 'next' list."""
+    `dropout_rate` drives SpatialDropout3D between the two convs of each context module in training steps
+    (identity at inference); the keep masks come from a counter-based hash (`dropout_seed` kwarg), not TF's RNG."""
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
     if mask_shape is not None:
         raise NotImplementedError("mask_shape (closure loss with a second input) is on the §8 'next' list")
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
-                 device=kargs.get("device"), ndim=3, isensee_levels=n_segmentation_levels)
+                 device=kargs.get("device"), ndim=3, isensee_levels=n_segmentation_levels,
+                 dropout_rate=dropout_rate or 0.0, dropout_seed=kargs.get("dropout_seed", 0x5EED))

@@ -122,6 +122,11 @@ int fm_model_get_weights(fm_model* m, int layer, float* kernel, float* bias);
 int fm_model_get_grads(fm_model* m, int layer, float* kernel, float* bias);
 /* Resets Adam moments and the iteration counter (a fresh model.compile). */
 int fm_model_reset_optimizer(fm_model* m);
+/* Replaces: the `dropout_rate` kwarg of isensee2017_model_3d -> SpatialDropout3D(rate) between the two convs of
+ * every context module (fetal_net/model/unet3d/isensee2017.py:15,51,103-105). Active in training passes only
+ * (fm_train_*), one keep/scale factor per (sample, channel) drawn from a counter-based hash of (seed, step, level);
+ * rate 0 (the default here) switches it off. Plain U-Net models ignore it. */
+int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed);
 
 /* ---- inference ---------------------------------------------------------------------------- */
 

@@ -250,5 +250,75 @@ def test_isensee_forward_matches_oracle(shape, depth, nseg):
     # instance normalisation re-scales every block, so bf16 storage error does not shrink with depth: 4 % bound
     assert rel <= 0.04 and np.abs(p - ref).mean() <= 0.008, (rel, float(np.abs(p - ref).mean()))
     assert np.array_equal(model.predict(x[1:2]), p[1:2])              # per-sample statistics: batch invariant
-    with pytest.raises(NotImplementedError):
-        model.train_on_batch(x, (x > 0).astype(np.float32))
+
+
+def _blob_truth(x):
+    """A smooth-ish binary target correlated with the input (so gradients are not degenerate)."""
+    t = torch.nn.functional.avg_pool3d(torch.as_tensor(x), 5, stride=1, padding=2).numpy()
+    return (t > 0.05).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape,depth,nseg", [((1, 32, 32, 16), 3, 2), ((1, 32, 32, 32), 4, 3)])
+def test_isensee_train_step_matches_oracle(shape, depth, nseg):
+    """fwd + Dice + bwd + Adam of the Isensee net vs torch autograd on the fp32 restatement (dropout off): loss,
+    per-layer gradient direction (kernels, gamma, beta), updated weights, and a falling loss."""
+    from fetal_net.model import isensee2017_model_3d
+    layers = uo.isensee3d_layers(depth, 16, nseg)
+    w = isensee_weights(layers, seed=11)
+    model = isensee2017_model_3d(input_shape=shape, n_base_filters=16, depth=depth, n_segmentation_levels=nseg,
+                                 dropout_rate=0, initial_learning_rate=1e-3)
+    model.set_named_weights(w)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2,) + shape).astype(np.float32)
+    t = _blob_truth(x)
+    wo = {k: v.copy() for k, v in w.items()}
+    ref = uo.train_step(lambda xt, prm: uo.isensee3d_forward(xt, prm, depth=depth, n_segmentation_levels=nseg),
+                        x, t, wo, {}, 1e-3)
+    loss, acc, vod = model.train_on_batch(x, t)
+    assert abs(loss - ref["loss"]) <= 4e-3, (loss, ref["loss"])
+    grads = model.get_gradients()
+    cos = {}
+    for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
+        if l["is_norm"]:
+            base = l["name"][:-len("_norm")]
+            pairs = [(base + "/gamma", gk), (base + "/beta", gb)]
+        else:
+            rk = ref["grads"][l["name"] + "/kernel"]                   # Keras layout, like get_gradients()
+            assert rk.shape == gk.shape, (l["name"], rk.shape, gk.shape)
+            cos[l["name"] + "/kernel"] = float((gk * rk).sum() / (np.linalg.norm(gk) * np.linalg.norm(rk) + 1e-30))
+            if l["name"].endswith("_seg"):
+                pairs = [(l["name"] + "/bias", gb)]
+            else:
+                # a bias in front of an instance norm has an exactly-zero gradient: only rounding noise remains
+                assert np.abs(gb).max() <= 1e-2 * max(np.abs(gk).max(), 1e-12), l["name"]
+                pairs = []
+        for name, g in pairs:
+            r = ref["grads"][name]
+            cos[name] = float((g * r).sum() / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+    worst = min(cos.items(), key=lambda kv: kv[1])
+    assert worst[1] >= 0.97, (worst, sorted(cos.items(), key=lambda kv: kv[1])[:6])
+    assert np.median(list(cos.values())) >= 0.99
+    # a few more steps: the loss falls like the oracle's
+    losses = [loss]
+    for _ in range(5):
+        losses.append(model.train_on_batch(x, t)[0])
+    assert losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_isensee_dropout_training_only():
+    from fetal_net.model import isensee2017_model_3d
+    shape = (1, 32, 32, 16)
+    kw = dict(input_shape=shape, n_base_filters=16, depth=3, n_segmentation_levels=1, initial_learning_rate=1e-3)
+    a = isensee2017_model_3d(dropout_rate=0.0, **kw)
+    b = isensee2017_model_3d(dropout_rate=0.5, **kw)
+    a.init_glorot_uniform(seed=2)
+    b.set_weights(a.get_weights())
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2,) + shape).astype(np.float32)
+    t = _blob_truth(x)
+    assert np.array_equal(a.predict(x), b.predict(x))                 # identity at inference
+    la, lb = a.train_on_batch(x, t)[0], b.train_on_batch(x, t)[0]
+    assert np.isfinite(lb) and la != lb                               # masks change the training forward
+    ga, gb = a.get_gradients(), b.get_gradients()
+    assert all(np.isfinite(g).all() for g in gb)
+    assert any(not np.allclose(p, q) for p, q in zip(ga, gb))
