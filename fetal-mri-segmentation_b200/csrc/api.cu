@@ -47,6 +47,9 @@ extern "C" int fm_ctx_create(int device, fm_ctx** out) {
     return FM_ECUDA;
   }
   FM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  FM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  FM_CUDA(cudaEventCreateWithFlags(&ctx->copy_fence, cudaEventDisableTiming));
+  FM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
   FM_CUDA(cudaMalloc((void**)&ctx->red_scratch, 1024 * 8 * sizeof(double)));
   *out = ctx;
   return FM_OK;
@@ -63,6 +66,9 @@ extern "C" int fm_ctx_destroy(fm_ctx* ctx) {
   }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_fence) cudaEventDestroy(ctx->copy_fence);
+  if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   delete ctx;
   return FM_OK;
 }
@@ -211,6 +217,9 @@ struct fm_model {
   int64_t nparams = 0;
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
   bf16* wpack = nullptr;  // arena for all bf16 packs
+  RepackDesc* repack_tab = nullptr;  // device table for the fused repack launch
+  int repack_n = 0, repack_blocks = 0;
+  double repack_weights = 0.0;
   int iterations = 0;
   bool packs_dirty = true;
 
@@ -447,6 +456,7 @@ extern "C" int fm_model_destroy(fm_model* m) {
   cudaFree(m->adam_m);
   cudaFree(m->adam_v);
   cudaFree(m->wpack);
+  cudaFree(m->repack_tab);
   cudaFree(m->sums);
   for (auto& l : m->layers)
     for (int s = 0; s < 2; ++s) {
@@ -584,6 +594,42 @@ extern "C" int fm_model_reset_optimizer(fm_model* m) {
 
 static int refresh_packs(fm_model* m) {
   if (!m->packs_dirty) return FM_OK;
+  if (!m->repack_tab) {
+    // built on first use: one descriptor per conv layer that keeps bf16 packs, one fused launch from then on
+    std::vector<RepackDesc> tab;
+    int blocks = 0;
+    double weights = 0.0;
+    for (auto& l : m->layers) {
+      if (l.is_norm || (l.k == 1 && l.cout == 1)) continue;  // norm parameters / heads are read as fp32
+      RepackDesc d;
+      d.w_off = l.w_off;
+      d.cout = l.cout;
+      d.taps = l.taps();
+      d.c1 = l.c1;
+      d.c2 = l.c2;
+      d.wf = l.w_f;
+      d.wd0 = l.w_d0;
+      d.wd1 = l.c2 ? l.w_d1 : nullptr;
+      d.mf0 = l.march_f ? l.w_mf[0] : nullptr;
+      d.mf1 = l.march_f && l.c2 ? l.w_mf[1] : nullptr;
+      d.md0 = l.march_d[0] ? l.w_md[0] : nullptr;
+      d.md1 = l.c2 && l.march_d[1] ? l.w_md[1] : nullptr;
+      d.block0 = blocks;
+      blocks += (int)ceil_div64(l.wcount(), 256);
+      weights += (double)l.wcount();
+      tab.push_back(d);
+    }
+    FM_CUDA(cudaMalloc((void**)&m->repack_tab, tab.size() * sizeof(RepackDesc)));
+    FM_CUDA(cudaMemcpy(m->repack_tab, tab.data(), tab.size() * sizeof(RepackDesc), cudaMemcpyHostToDevice));
+    m->repack_n = (int)tab.size();
+    m->repack_blocks = blocks;
+    m->repack_weights = weights;
+  }
+  if (m->repack_n > 0 && !getenv("FETAL_B200_SPLIT_REPACK")) {
+    FM_TRY(k_repack_all(m->ctx, m->params, m->repack_tab, m->repack_n, m->repack_blocks, m->repack_weights));
+    m->packs_dirty = false;
+    return FM_OK;
+  }
   for (auto& l : m->layers) {
     if (l.is_norm) continue;
     if (l.k == 1 && l.cout == 1) continue;  // head reads fp32 weights directly
@@ -1472,11 +1518,26 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
 // ---------------------------------------------------------------------------------------------
 // training
 // ---------------------------------------------------------------------------------------------
-static int train_forward_dev(fm_model* m, int batch) {
+// `t_host` (optional): targets still on the host. They are first needed by the Dice sums at the end of the forward
+// pass, so they are copied on the side stream AFTER the network has been queued — the transfer (and, for pageable
+// memory, the host-side staging) overlaps the forward kernels. The side stream first waits for everything queued on
+// the compute stream before this step, which may still read the previous targets.
+static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullptr) {
+  fm_ctx* ctx = m->ctx;
+  if (t_host) {
+    FM_CUDA(cudaEventRecord(ctx->copy_fence, ctx->stream));
+    FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_fence, 0));
+  }
   m->train_pass = true;
   const int rf = forward(m, batch);
   m->train_pass = false;
   FM_TRY(rf);
+  if (t_host) {
+    FM_CUDA(cudaMemcpyAsync(m->t_in.p, t_host, (size_t)batch * m->vox(0) * sizeof(float), cudaMemcpyHostToDevice,
+                            ctx->copy_stream));
+    FM_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    FM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
+  }
   FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0));
   m->last_batch = batch;
   m->fwd_valid = true;
@@ -1489,8 +1550,7 @@ extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int
   FM_TRY(ensure_capacity(m, batch, true));
   const size_t n = (size_t)batch * m->vox(0);
   FM_TRY(upload(m, x, m->x_in.p, n * m->cin_real));
-  FM_TRY(upload(m, t, m->t_in.p, n));
-  return train_forward_dev(m, batch);
+  return train_forward_dev(m, batch, t);
 }
 
 extern "C" int fm_train_backward(fm_model* m) {

@@ -55,6 +55,9 @@ struct fm_ctx {
   std::vector<ProfRec> prof;
   int sm_major = 0, sm_minor = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
+  // side stream for host->device copies that the head of the compute stream does not need yet (training targets)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_fence = nullptr, copy_done = nullptr;
   int64_t launches = 0;
   // scratch for deterministic two-stage reductions
   double* red_scratch = nullptr;  // [RED_BLOCKS * 8]
@@ -178,6 +181,16 @@ int k_head_bwd(fm_ctx*, const bf16* x, const float* dz, const float* w, bf16* dx
                float* db, int64_t voxels, int C, int mode = 0);
 // weight repack: master fp32 [Cout][taps][Cin] -> bf16 fprop pack (same layout) and bf16 dgrad
 // pack(s) [Cin_s][taps flipped][Cout] per source
+// all layers in ONE launch (after every Adam step): per layer the fprop pack, the dgrad pack(s) and, where the
+// plane-marching kernels run, their packs [chunk][dz][dy][kx = 2,1,0][row][kc] — see k_repack_weights / k_repack_march
+struct RepackDesc {
+  int64_t w_off;   // offset of the master kernel [Cout][taps][C1+C2] in the flat fp32 parameter buffer
+  int cout, taps, c1, c2;
+  bf16 *wf, *wd0, *wd1, *mf0, *mf1, *md0, *md1;  // null = not needed
+  int block0;      // first 256-thread block of this layer in the fused grid
+};
+int k_repack_all(fm_ctx*, const float* params, const RepackDesc* table_dev, int nlayers, int total_blocks,
+                 double total_weights);
 int k_repack_weights(fm_ctx*, const float* w, bf16* w_f, bf16* w_d0, bf16* w_d1, int Cout, int taps,
                      int C1, int C2);
 

@@ -422,6 +422,39 @@ __global__ void repack_weights_kernel(const float* __restrict__ w, bf16* __restr
   }
 }
 
+__device__ __forceinline__ int64_t march_pack_index(int rows, int row, int tap, int k, int Ktot) {
+  // Wm[chunk][dz][dy][kxr][row][kc] with tap = (kx*3 + ky)*3 + kz, kxr = 2 - kx, KC = min(Ktot, 64)
+  const int KC = Ktot < 64 ? Ktot : 64;
+  const int kx = tap / 9, ky = (tap / 3) % 3, kz = tap % 3;
+  const int ch = k / KC, kc = k % KC;
+  return ((((int64_t)(ch * 3 + kz) * 3 + ky) * 3 + (2 - kx)) * rows + row) * KC + kc;
+}
+
+__global__ void __launch_bounds__(kThreads) repack_all_kernel(const float* __restrict__ params,
+                                                              const RepackDesc* __restrict__ tab, int nlayers) {
+  int li = 0;
+  while (li + 1 < nlayers && (int)blockIdx.x >= tab[li + 1].block0) ++li;
+  const RepackDesc d = tab[li];
+  const int Ct = d.c1 + d.c2;
+  const int64_t total = (int64_t)d.cout * d.taps * Ct;
+  const int64_t g = (int64_t)(blockIdx.x - d.block0) * kThreads + threadIdx.x;
+  if (g >= total) return;
+  const int c = (int)(g % Ct);
+  const int tap = (int)((g / Ct) % d.taps);
+  const int co = (int)(g / ((int64_t)Ct * d.taps));
+  const bf16 v = __float2bfloat16(params[d.w_off + g]);
+  if (d.wf) d.wf[g] = v;
+  const int tf = d.taps - 1 - tap;
+  const bool second = c >= d.c1;
+  const int cs = second ? c - d.c1 : c, Cs = second ? d.c2 : d.c1;
+  bf16* wd = second ? d.wd1 : d.wd0;
+  if (wd) wd[((int64_t)cs * d.taps + tf) * d.cout + co] = v;
+  bf16* mf = second ? d.mf1 : d.mf0;
+  if (mf) mf[march_pack_index(d.cout, co, tap, cs, Cs)] = v;
+  bf16* md = second ? d.md1 : d.md0;
+  if (md) md[march_pack_index(Cs, cs, tf, co, d.cout)] = v;
+}
+
 inline int grid_for(int64_t work_items, int cap = 1 << 30) {
   int64_t b = ceil_div64(work_items, kThreads);
   if (b > cap) b = cap;
@@ -532,6 +565,14 @@ int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 8);
   ProfScope prof(ctx, "head_bwd", 4.0 * C * (double)voxels, (double)voxels * (C * 4.0 + 4.0));
   head_bwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, dz, w, dx, dw, db, voxels, C, mode);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_repack_all(fm_ctx* ctx, const float* params, const RepackDesc* table_dev, int nlayers, int total_blocks,
+                 double total_weights) {
+  ProfScope prof(ctx, "repack_all", 0.0, total_weights * 12.0);
+  repack_all_kernel<<<total_blocks, kThreads, 0, ctx->stream>>>(params, table_dev, nlayers);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
