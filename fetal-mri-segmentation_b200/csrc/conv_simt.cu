@@ -180,54 +180,57 @@ __global__ void __launch_bounds__(kThreads) conv3d_first_kernel(const float* __r
 
 // --------------------------------------------------------------------------------------------
 // first-layer wgrad (Cin = 1): dW[co][tap] = sum_v dY[v][co] * x[v + shift(tap)].
-// A warp owns one class = (kx, ky, channel slice of CS) and 32 consecutive voxels per trip; every lane keeps the
-// 3 (kz) x CS partial sums of its class in registers - few registers, so 2-3 blocks of 18 warps are resident per
-// SM and the dY / x load latency is hidden by occupancy. Persistent blocks; at the end every warp
-// butterfly-reduces its sums and issues them as fp32 red.add (27 * COUT per block).
+// A warp owns one class = (kx, ky, 16-channel slice); every lane takes TWO z-adjacent voxels per trip (Z even), so
+// the index arithmetic and the x loads are shared by 96 FMAs and a lane reads 64 contiguous bytes of dY. The
+// 3 (kz) x 16 partial sums of the class stay in registers for the whole (persistent) block; at the end every warp
+// butterfly-reduces them and issues fp32 red.add (27 * COUT per block).
 // --------------------------------------------------------------------------------------------
-template <int COUT, int CS>
-__global__ void __launch_bounds__(32 * 9 * (COUT / CS)) conv3d_first_wgrad_kernel(const float* __restrict__ x,
+template <int COUT>
+__global__ void __launch_bounds__(32 * 9 * (COUT / 16)) conv3d_first_wgrad_kernel(const float* __restrict__ x,
                                                                                  const bf16* __restrict__ dy,
                                                                                  float* __restrict__ dw, int N, int X,
                                                                                  int Y, int Z) {
+  constexpr int CS = 16;
   const int cls = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kx = cls % 3, ky = (cls / 3) % 3, cslice = cls / 9;
-  const int64_t nvox = (int64_t)N * X * Y * Z;
   float acc[3][CS];
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
     for (int c = 0; c < CS; ++c) acc[t][c] = 0.f;
-  // 32-bit index arithmetic: 64-bit div/mod by run-time extents costs ~100 instructions each
-  const uint32_t stride = gridDim.x * 32u, nv32 = (uint32_t)nvox;
-  for (uint32_t v = blockIdx.x * 32u + (uint32_t)lane; v < nv32; v += stride) {
-    const int z = (int)(v % (uint32_t)Z);
-    uint32_t r = v / (uint32_t)Z;
+  // 32-bit index arithmetic (the launcher guarantees < 2^31 voxels): 64-bit div/mod costs ~100 instructions each
+  const uint32_t Zh = (uint32_t)Z >> 1;
+  const uint32_t npairs = (uint32_t)N * X * Y * Zh, stride = gridDim.x * 32u;
+  for (uint32_t p = blockIdx.x * 32u + (uint32_t)lane; p < npairs; p += stride) {
+    const int z = (int)(p % Zh) * 2;
+    uint32_t r = p / Zh;
     const int yy = (int)(r % (uint32_t)Y);
     r /= (uint32_t)Y;
     const int xx = (int)(r % (uint32_t)X);
     const int n = (int)(r / (uint32_t)X);
     const int xi = xx + kx - 1, yi = yy + ky - 1;
     if (xi < 0 || xi >= X || yi < 0 || yi >= Y) continue;
-    float g[CS];
+    const bf16* gp = dy + (int64_t)p * 2 * COUT + cslice * CS;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(gp)), a1 = __ldg(reinterpret_cast<const uint4*>(gp + 8));
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(gp + COUT)),
+                b1 = __ldg(reinterpret_cast<const uint4*>(gp + COUT + 8));
+    const float* xb = x + (((int64_t)n * X + xi) * Y + yi) * Z + z;
+    const float2 xm = __ldg(reinterpret_cast<const float2*>(xb));  // x[z], x[z+1] (z even: 8-byte aligned)
+    const float xl = z > 0 ? __ldg(xb - 1) : 0.f;
+    const float xr = z + 2 < Z ? __ldg(xb + 2) : 0.f;
+    const uint32_t wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const uint32_t wb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int h = 0; h < CS / 8; ++h) {
-      const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(dy + (int64_t)v * COUT + cslice * CS + h * 8));
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(hh[j]);
-        g[8 * h + 2 * j] = f.x;
-        g[8 * h + 2 * j + 1] = f.y;
-      }
-    }
-    const float* xb = x + (((int64_t)n * X + xi) * Y + yi) * Z;
-#pragma unroll
-    for (int kz = 0; kz < 3; ++kz) {
-      const int zi = z + kz - 1;
-      const float xv = (zi >= 0 && zi < Z) ? __ldg(xb + zi) : 0.f;
-#pragma unroll
-      for (int c = 0; c < CS; ++c) acc[kz][c] += xv * g[c];
+    for (int j = 0; j < 8; ++j) {
+      const float ga0 = __uint_as_float(wa[j] << 16), ga1 = __uint_as_float(wa[j] & 0xffff0000u);
+      const float gb0 = __uint_as_float(wb[j] << 16), gb1 = __uint_as_float(wb[j] & 0xffff0000u);
+      // voxel z sees x[z-1], x[z], x[z+1]; voxel z+1 sees x[z], x[z+1], x[z+2]
+      acc[0][2 * j] += xl * ga0 + xm.x * gb0;
+      acc[1][2 * j] += xm.x * ga0 + xm.y * gb0;
+      acc[2][2 * j] += xm.y * ga0 + xr * gb0;
+      acc[0][2 * j + 1] += xl * ga1 + xm.x * gb1;
+      acc[1][2 * j + 1] += xm.x * ga1 + xm.y * gb1;
+      acc[2][2 * j + 1] += xm.y * ga1 + xr * gb1;
     }
   }
 #pragma unroll
@@ -496,13 +499,13 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
   const int64_t n_out = (int64_t)Cout * taps * Cin;
   const int64_t nvox = (int64_t)N * X * Y * Z;
   if (x_is_f32 && Cin == 1 && Cin_total == 1 && cin_ofs == 0 && ksize == 3 && (Cout == 16 || Cout == 32) &&
-      nvox < (int64_t)1 << 31) {
+      nvox < (int64_t)1 << 31 && Z % 2 == 0) {
     ProfScope prof(ctx, "conv3d_first_wgrad", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
-    const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 32), (int64_t)ctx->num_sms * 3);
+    const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 64), (int64_t)ctx->num_sms * (Cout == 16 ? 4 : 2));
     if (Cout == 16)
-      conv3d_first_wgrad_kernel<16, 8><<<grid, 32 * 18, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+      conv3d_first_wgrad_kernel<16><<<grid, 32 * 9, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
     else
-      conv3d_first_wgrad_kernel<32, 16><<<grid, 32 * 18, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+      conv3d_first_wgrad_kernel<32><<<grid, 32 * 18, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
     FM_LAUNCH_OK(ctx);
     return FM_OK;
   }
