@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -67,6 +68,29 @@ struct fm_ctx {
 };
 
 int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out);
+
+// Programmatic dependent launch: the kernel may be scheduled while its stream predecessor drains, runs its
+// prologue (barrier init, TMEM allocation, resident-weight loads), and blocks in `griddepcontrol.wait` (tcp::pdl_wait)
+// before it touches anything the predecessor wrote. FETAL_B200_NO_PDL=1 launches it as a plain kernel.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  static const bool off = [] {
+    const char* e = getenv("FETAL_B200_NO_PDL");
+    return e && e[0] == '1';
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Kernel-extent code used by all conv launchers: 3 = 3x3x3, 1 = 1x1x1, 31 = 3x3x1 (Conv2D on a Z = 1 volume:
 // the 2.5D U-Net, fetal_net/model/unet/unet.py:103). Tap index = (kx * kxy + ky) * kz + kzi.

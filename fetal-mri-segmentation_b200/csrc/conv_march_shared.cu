@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_shared_kernel(const
       for (int t = 0; t < p.nchunks[s] * 9; ++t)
         tma_load_2d_elect(w_base + p.wofs[s] + (uint32_t)t * tile, &p.tmW[s], wfull_bar, 0, t * 3 * p.Cn);
     }
+    // the weights do not depend on the previous kernel in the stream; the activation slabs do
+    pdl_wait();
+    pdl_launch_dependents();
     // every dz slab copy has its own ring of S3 = stages/3 slots, consumed strictly in order by "its" MMA
     // warp (a consumer that skipped slots of a shared ring could not tell mbarrier phases apart)
     const uint32_t S3 = (uint32_t)p.stages / 3u;
@@ -455,7 +458,7 @@ int k_conv3d_march_shared(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf1
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_march_dgrad" : "conv3d_march_fprop",
                  2.0 * 27 * (C1 + C2) * Cout * vox, vox * (C1 + C2 + Cout) * 2.0);
-  conv3d_march_shared_kernel<<<grid, kThreadsM, smem, ctx->stream>>>(p);
+  FM_CUDA(launch_pdl(conv3d_march_shared_kernel, dim3(grid), dim3(kThreadsM), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -274,6 +274,9 @@ __global__ void __launch_bounds__(kThreads) bias_grad_vec_kernel(const uint4* __
                                                                  int64_t nvec, int G) {
   __shared__ float sh[256];
   sh[threadIdx.x] = 0.f;
+  // launched as a programmatic dependent (launch_pdl): sits between two tensor-core kernels of the backward pass
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -529,8 +532,8 @@ int k_bias_grad(fm_ctx* ctx, const bf16* dy, float* db, int64_t voxels, int C) {
     const int64_t nvec = voxels * (C / 8);
     const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, nvec / (kThreads * 4)));
     ProfScope prof(ctx, "bias_grad", 0.0, (double)voxels * C * 2.0);
-    bias_grad_vec_kernel<<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(dy), db,
-                                                                        nvec, C / 8);
+    FM_CUDA(launch_pdl(bias_grad_vec_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->stream,
+                       reinterpret_cast<const uint4*>(dy), db, nvec, C / 8));
     FM_LAUNCH_OK(ctx);
     return FM_OK;
   }

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
 
   if (warp_u == 0) {
     // ===== TMA producer warp (converged; one elected lane issues) =====
+    pdl_wait();  // activations come from the previous kernel in the stream
+    pdl_launch_dependents();
     uint32_t stage = 0, ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -353,6 +355,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
 
   if (warp_u == 0) {
     // ===== TMA producer warp =====
+    pdl_wait();
+    pdl_launch_dependents();
     uint32_t stage = 0, ph = 0, vt = 0;
     for (int mt = mt0; mt < mt1; ++mt, ++vt) {
       int m = mt;
@@ -620,7 +624,7 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_tc_dgrad" : "conv3d_tc_fprop",
                  2.0 * p.ntaps * Ct * Cout * vox, vox * (Ct + Cout) * 2.0);
-  conv3d_tc_fprop_kernel<<<grid, kThreadsTc, smem, ctx->stream>>>(p);
+  FM_CUDA(launch_pdl(conv3d_tc_fprop_kernel, dim3(grid), dim3(kThreadsTc), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -674,7 +678,7 @@ int k_conv3d_tc_wgrad(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_pack
   }
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, "conv3d_tc_wgrad", 2.0 * p.ntaps * Cin * Cout * vox, vox * (Cin + Cout) * 2.0);
-  conv3d_tc_wgrad_kernel<<<items * splits, kThreadsTc, smem, ctx->stream>>>(p);
+  FM_CUDA(launch_pdl(conv3d_tc_wgrad_kernel, dim3(items * splits), dim3(kThreadsTc), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

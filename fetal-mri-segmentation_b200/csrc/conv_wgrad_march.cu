@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
 
   if (warp_u == 0) {
     // ===== TMA producer =====
+    pdl_wait();  // x and dY come from the previous kernels in the stream
+    pdl_launch_dependents();
     const uint32_t x_bytes = (uint32_t)(kBY + 128 / p.kcx - 1) * kBZ * (uint32_t)p.kcx * 2u;  // slab box bytes
     uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
     uint32_t dcount = 0;  // dY tiles issued so far (ring position)
@@ -326,7 +328,7 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   }
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, "conv3d_wgrad_march", 2.0 * 27 * Cin * Cout * vox, vox * (Cin + Cout) * 2.0);
-  conv3d_wgrad_march_kernel<<<pairs * p.ctas_per_pair, kThreadsW, smem, ctx->stream>>>(p);
+  FM_CUDA(launch_pdl(conv3d_wgrad_march_kernel, dim3(pairs * p.ctas_per_pair), dim3(kThreadsW), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
