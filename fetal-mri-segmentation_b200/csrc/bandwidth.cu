@@ -74,6 +74,7 @@ __global__ void pad_cast_kernel(const float* __restrict__ in, bf16* __restrict__
 template <int pz>
 __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
                                      int Y, int Z, int C) {
+  FM_PDL_SYNC();
   const int c8n = C >> 3;
   const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
   const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
@@ -122,6 +123,7 @@ template <int pz>
 __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                      const bf16* __restrict__ dskip, bf16* __restrict__ dx, int N,
                                      int X, int Y, int Z, int C, int relu_mask) {
+  FM_PDL_SYNC();
   const int c8n = C >> 3;
   const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
   const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
@@ -189,6 +191,7 @@ __global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __r
 template <int pz>
 __global__ void upsample3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int X,
                                       int Y, int Z, int C) {
+  FM_PDL_SYNC();
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * X * Y * Z * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +220,7 @@ template <int pz>
 __global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ act,
                                       bf16* __restrict__ dx, int N, int X, int Y, int Z, int C,
                                       int dyC, int dy_cofs) {
+  FM_PDL_SYNC();
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * X * Y * Z * c8n;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -609,6 +613,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __restrict__ p,
                                                                 const float* __restrict__ t,
                                                                 int64_t n, double* __restrict__ part) {
+  FM_PDL_SYNC();
   float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int64_t nv = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
@@ -659,6 +664,7 @@ __global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __r
 
 __global__ void dice_final_kernel(const double* __restrict__ part, int nblocks, double n_elems,
                                   double* __restrict__ sums, int accumulate) {
+  FM_PDL_SYNC();
   const int k = threadIdx.x;
   if (k < 7) {
     double a = 0.0;
@@ -673,6 +679,7 @@ __global__ void dice_final_kernel(const double* __restrict__ part, int nblocks, 
 __global__ void dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
                                 const double* __restrict__ sums, int64_t n, float* __restrict__ dz,
                                 int through_sigmoid) {
+  FM_PDL_SYNC();
   const double I = sums[0], S = sums[1] + sums[2] + 1.0;
   const float a = (float)(-2.0 / S);               // coefficient of t_i
   const float b = (float)((2.0 * I + 1.0) / (S * S));  // constant term
@@ -707,6 +714,7 @@ __global__ void dice_bwd_kernel(const float* __restrict__ p, const float* __rest
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr_t, float b1, float b2,
                             float eps) {
+  FM_PDL_SYNC();
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 4 <= n) {
     float4 pp = *reinterpret_cast<float4*>(p + i);
@@ -870,9 +878,9 @@ int k_maxpool3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in, int pz) {
   const int64_t total = in.elems() / (32 * pz);
   ProfScope prof(ctx, "maxpool3d_fwd", 0.0, (double)in.elems() * 2.0 * 1.125);
   if (pz == 2)
-    maxpool3d_fwd_kernel<2><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
+    FM_CUDA(launch_pdl(maxpool3d_fwd_kernel<2>, dim3(grid_for(total)), dim3(kThreads), 0, ctx->stream, x, y, in.N, in.X, in.Y, in.Z, in.C));
   else
-    maxpool3d_fwd_kernel<1><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
+    FM_CUDA(launch_pdl(maxpool3d_fwd_kernel<1>, dim3(grid_for(total)), dim3(kThreads), 0, ctx->stream, x, y, in.N, in.X, in.Y, in.Z, in.C));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -883,11 +891,11 @@ int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dski
   const int64_t total = in.elems() / (32 * pz);
   ProfScope prof(ctx, "maxpool3d_bwd", 0.0, (double)in.elems() * 2.0 * (dskip ? 3.125 : 2.125));
   if (pz == 2)
-    maxpool3d_bwd_kernel<2><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
-                                                                          in.C, relu_mask);
+    FM_CUDA(launch_pdl(maxpool3d_bwd_kernel<2>, dim3(grid_for(total)), dim3(kThreads), 0, ctx->stream, x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
+                                                                          in.C, relu_mask));
   else
-    maxpool3d_bwd_kernel<1><<<grid_for(total), kThreads, 0, ctx->stream>>>(x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
-                                                                          in.C, relu_mask);
+    FM_CUDA(launch_pdl(maxpool3d_bwd_kernel<1>, dim3(grid_for(total)), dim3(kThreads), 0, ctx->stream, x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
+                                                                          in.C, relu_mask));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -895,9 +903,9 @@ int k_upsample3d_fwd(fm_ctx* ctx, const bf16* x, bf16* y, Dims5 in, int pz) {
   FM_CHECK(in.C % 8 == 0, FM_EINVAL, "upsample3d: need C%%8==0");
   ProfScope prof(ctx, "upsample3d_fwd", 0.0, (double)in.elems() * 2.0 * 9.0);
   if (pz == 2)
-    upsample3d_fwd_kernel<2><<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
+    FM_CUDA(launch_pdl(upsample3d_fwd_kernel<2>, dim3(grid_for(in.elems() / 8)), dim3(kThreads), 0, ctx->stream, x, y, in.N, in.X, in.Y, in.Z, in.C));
   else
-    upsample3d_fwd_kernel<1><<<grid_for(in.elems() / 8), kThreads, 0, ctx->stream>>>(x, y, in.N, in.X, in.Y, in.Z, in.C);
+    FM_CUDA(launch_pdl(upsample3d_fwd_kernel<1>, dim3(grid_for(in.elems() / 8)), dim3(kThreads), 0, ctx->stream, x, y, in.N, in.X, in.Y, in.Z, in.C));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -907,29 +915,29 @@ int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dim
            "upsample3d_bwd: channel counts must be multiples of 8");
   ProfScope prof(ctx, "upsample3d_bwd", 0.0, (double)coarse.elems() * 2.0 * (act ? 10.0 : 9.0));
   if (pz == 2)
-    upsample3d_bwd_kernel<2><<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
-        dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
+    FM_CUDA(launch_pdl(upsample3d_bwd_kernel<2>, dim3(grid_for(coarse.elems() / 8)), dim3(kThreads), 0, ctx->stream, 
+        dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs));
   else
-    upsample3d_bwd_kernel<1><<<grid_for(coarse.elems() / 8), kThreads, 0, ctx->stream>>>(
-        dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs);
+    FM_CUDA(launch_pdl(upsample3d_bwd_kernel<1>, dim3(grid_for(coarse.elems() / 8)), dim3(kThreads), 0, ctx->stream, 
+        dy, act, dx, coarse.N, coarse.X, coarse.Y, coarse.Z, coarse.C, dy_C, dy_cofs));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
 
 int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* sums, int accumulate) {
   ProfScope prof(ctx, "dice_sums", 0.0, (double)n * 8.0);
-  dice_partial_kernel<<<kRedBlocks, kThreads, 0, ctx->stream>>>(p, t, n, ctx->red_scratch);
+  FM_CUDA(launch_pdl(dice_partial_kernel, dim3(kRedBlocks), dim3(kThreads), 0, ctx->stream, p, t, n, ctx->red_scratch));
   FM_LAUNCH_OK(ctx);
-  dice_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->red_scratch, kRedBlocks, (double)n, sums,
-                                              accumulate);
+  FM_CUDA(launch_pdl(dice_final_kernel, dim3(1), dim3(32), 0, ctx->stream, ctx->red_scratch, kRedBlocks, (double)n, sums,
+                                              accumulate));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
 int k_dice_bwd(fm_ctx* ctx, const float* p, const float* t, const double* sums, int64_t n, float* dz,
                int through_sigmoid) {
   ProfScope prof(ctx, "dice_bwd", 0.0, (double)n * 12.0);
-  dice_bwd_kernel<<<grid_for(ceil_div64(n, 4)), kThreads, 0, ctx->stream>>>(p, t, sums, n, dz,
-                                                                           through_sigmoid);
+  FM_CUDA(launch_pdl(dice_bwd_kernel, dim3(grid_for(ceil_div64(n, 4))), dim3(kThreads), 0, ctx->stream, p, t, sums, n, dz,
+                                                                           through_sigmoid));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -939,8 +947,8 @@ int k_adam(fm_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n,
   const double t = (double)iterations + 1.0;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
   ProfScope prof(ctx, "adam", 0.0, (double)n * 28.0);
-  adam_kernel<<<grid_for(ceil_div64(n, 4)), kThreads, 0, ctx->stream>>>(p, g, m, v, n, lr_t, 0.9f,
-                                                                       0.999f, 1e-7f);
+  FM_CUDA(launch_pdl(adam_kernel, dim3(grid_for(ceil_div64(n, 4))), dim3(kThreads), 0, ctx->stream, p, g, m, v, n, lr_t, 0.9f,
+                                                                       0.999f, 1e-7f));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

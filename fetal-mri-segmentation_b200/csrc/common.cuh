@@ -72,6 +72,13 @@ int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out);
 // Programmatic dependent launch: the kernel may be scheduled while its stream predecessor drains, runs its
 // prologue (barrier init, TMEM allocation, resident-weight loads), and blocks in `griddepcontrol.wait` (tcp::pdl_wait)
 // before it touches anything the predecessor wrote. FETAL_B200_NO_PDL=1 launches it as a plain kernel.
+// first statement of a simple kernel launched through launch_pdl: wait for the predecessor, then let the successor in
+#define FM_PDL_SYNC()                                              \
+  do {                                                             \
+    asm volatile("griddepcontrol.wait;" ::: "memory");             \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      Args&&... args) {

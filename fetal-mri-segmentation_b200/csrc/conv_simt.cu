@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kThreads) conv3d_first_kernel(const float* __r
                                                                 const float* __restrict__ bias,
                                                                 bf16* __restrict__ y, int N, int X,
                                                                 int Y, int Z, int relu) {
+  FM_PDL_SYNC();
   __shared__ __align__(16) float ws[27 * COUT];
   __shared__ float bs[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(32 * 9 * (COUT / 16)) conv3d_first_wgrad_kerne
                                                                                  const bf16* __restrict__ dy,
                                                                                  float* __restrict__ dw, int N, int X,
                                                                                  int Y, int Z) {
+  FM_PDL_SYNC();
   constexpr int CS = 16;
   const int cls = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kx = cls % 3, ky = (cls / 3) % 3, cslice = cls / 9;
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restri
                                                             const float* __restrict__ b,
                                                             float* __restrict__ p, int64_t voxels,
                                                             int C, int apply_sigmoid) {
+  FM_PDL_SYNC();
   const int lpv = C >> 3;  // lanes per voxel (power of two <= 32)
   const int sub = threadIdx.x % lpv;
   float wv[8];
@@ -349,6 +352,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
                                                             float* __restrict__ dw,
                                                             float* __restrict__ db, int64_t voxels,
                                                             int C, int mode) {
+  FM_PDL_SYNC();
   // mode 0: dx = g*w masked by ReLU(x) (plain U-Net head); 1: dx = g*w; 2: dx += g*w (Isensee seg heads)
   const int lpv = C >> 3;
   const int sub = threadIdx.x % lpv;
@@ -438,6 +442,7 @@ __device__ __forceinline__ int64_t march_pack_index(int rows, int row, int tap, 
 
 __global__ void __launch_bounds__(kThreads) repack_all_kernel(const float* __restrict__ params,
                                                               const RepackDesc* __restrict__ tab, int nlayers) {
+  FM_PDL_SYNC();
   int li = 0;
   while (li + 1 < nlayers && (int)blockIdx.x >= tab[li + 1].block0) ++li;
   const RepackDesc d = tab[li];
@@ -479,11 +484,11 @@ int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2
     const int grid = grid_for(nvox, ctx->num_sms * 16);
     ProfScope prof(ctx, "conv3d_first", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
     if (Cout == 16)
-      conv3d_first_kernel<16><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, w_packed, bias, y,
-                                                                 N, X, Y, Z, relu);
+      FM_CUDA(launch_pdl(conv3d_first_kernel<16>, dim3(grid), dim3(kThreads), 0, ctx->stream, (const float*)x, w_packed, bias, y,
+                                                                 N, X, Y, Z, relu));
     else
-      conv3d_first_kernel<32><<<grid, kThreads, 0, ctx->stream>>>((const float*)x, w_packed, bias, y,
-                                                                 N, X, Y, Z, relu);
+      FM_CUDA(launch_pdl(conv3d_first_kernel<32>, dim3(grid), dim3(kThreads), 0, ctx->stream, (const float*)x, w_packed, bias, y,
+                                                                 N, X, Y, Z, relu));
     FM_LAUNCH_OK(ctx);
     return FM_OK;
   }
@@ -506,9 +511,9 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
     ProfScope prof(ctx, "conv3d_first_wgrad", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
     const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 64), (int64_t)ctx->num_sms * (Cout == 16 ? 4 : 2));
     if (Cout == 16)
-      conv3d_first_wgrad_kernel<16><<<grid, 32 * 9, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+      FM_CUDA(launch_pdl(conv3d_first_wgrad_kernel<16>, dim3(grid), dim3(32 * 9), 0, ctx->stream, (const float*)x, dy, dw_packed, N, X, Y, Z));
     else
-      conv3d_first_wgrad_kernel<32><<<grid, 32 * 18, 0, ctx->stream>>>((const float*)x, dy, dw_packed, N, X, Y, Z);
+      FM_CUDA(launch_pdl(conv3d_first_wgrad_kernel<32>, dim3(grid), dim3(32 * 18), 0, ctx->stream, (const float*)x, dy, dw_packed, N, X, Y, Z));
     FM_LAUNCH_OK(ctx);
     return FM_OK;
   }
@@ -557,7 +562,7 @@ int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 32);
   ProfScope prof(ctx, "head_fwd", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 4.0));
-  head_fwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, w, b, p, voxels, C, apply_sigmoid);
+  FM_CUDA(launch_pdl(head_fwd_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, w, b, p, voxels, C, apply_sigmoid));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -570,7 +575,7 @@ int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 8);
   ProfScope prof(ctx, "head_bwd", 4.0 * C * (double)voxels, (double)voxels * (C * 4.0 + 4.0));
-  head_bwd_kernel<<<grid, kThreads, 0, ctx->stream>>>(x, dz, w, dx, dw, db, voxels, C, mode);
+  FM_CUDA(launch_pdl(head_bwd_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, dz, w, dx, dw, db, voxels, C, mode));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -578,7 +583,7 @@ int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16
 int k_repack_all(fm_ctx* ctx, const float* params, const RepackDesc* table_dev, int nlayers, int total_blocks,
                  double total_weights) {
   ProfScope prof(ctx, "repack_all", 0.0, total_weights * 12.0);
-  repack_all_kernel<<<total_blocks, kThreads, 0, ctx->stream>>>(params, table_dev, nlayers);
+  FM_CUDA(launch_pdl(repack_all_kernel, dim3(total_blocks), dim3(kThreads), 0, ctx->stream, params, table_dev, nlayers));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
