@@ -614,6 +614,10 @@ static int refresh_packs(fm_model* m) {
       d.mf1 = l.march_f && l.c2 ? l.w_mf[1] : nullptr;
       d.md0 = l.march_d[0] ? l.w_md[0] : nullptr;
       d.md1 = l.c2 && l.march_d[1] ? l.w_md[1] : nullptr;
+      d.kcf0 = conv_march_kc(l.c1, l.c2, l.cout, l.c1);
+      d.kcf1 = l.c2 ? conv_march_kc(l.c1, l.c2, l.cout, l.c2) : 0;
+      d.kcd0 = conv_march_kc(l.cout, 0, l.c1, l.cout);
+      d.kcd1 = l.c2 ? conv_march_kc(l.cout, 0, l.c2, l.cout) : 0;
       d.block0 = blocks;
       blocks += (int)ceil_div64(l.wcount(), 256);
       weights += (double)l.wcount();
@@ -638,9 +642,12 @@ static int refresh_packs(fm_model* m) {
     const int cs[2] = {l.c1, l.c2};
     int kofs = 0;
     for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
-      if (l.march_f) FM_TRY(k_repack_march(m->ctx, l.w_f, l.w_mf[s], l.cout, l.cin(), kofs, cs[s]));
+      if (l.march_f)
+        FM_TRY(k_repack_march(m->ctx, l.w_f, l.w_mf[s], l.cout, l.cin(), kofs, cs[s],
+                              conv_march_kc(l.c1, l.c2, l.cout, cs[s])));
       if (l.march_d[s])
-        FM_TRY(k_repack_march(m->ctx, s == 0 ? l.w_d0 : l.w_d1, l.w_md[s], cs[s], l.cout, 0, l.cout));
+        FM_TRY(k_repack_march(m->ctx, s == 0 ? l.w_d0 : l.w_d1, l.w_md[s], cs[s], l.cout, 0, l.cout,
+                              conv_march_kc(l.cout, 0, cs[s], l.cout)));
       kofs += cs[s];
     }
   }
@@ -1723,10 +1730,10 @@ extern "C" int fm_op_conv3d_fprop(fm_ctx* ctx, int impl, const float* x, const f
     FM_CHECK(conv_march_supported(X, Y, Z, C1, C2, Cout, ksize), FM_EINVAL, "march kernel does not cover this shape");
     bf16 *wm1 = nullptr, *wm2 = nullptr;
     FM_TRY(s.alloc(&wm1, (size_t)conv_march_pack_elems(C1, Cout)));
-    FM_TRY(k_repack_march(ctx, dw, wm1, Cout, Ct, 0, C1));
+    FM_TRY(k_repack_march(ctx, dw, wm1, Cout, Ct, 0, C1, conv_march_kc(C1, C2, Cout, C1)));
     if (C2 > 0) {
       FM_TRY(s.alloc(&wm2, (size_t)conv_march_pack_elems(C2, Cout)));
-      FM_TRY(k_repack_march(ctx, dw, wm2, Cout, Ct, C1, C2));
+      FM_TRY(k_repack_march(ctx, dw, wm2, Cout, Ct, C1, C2, conv_march_kc(C1, C2, Cout, C2)));
     }
     FM_TRY((impl == 3 && Cout <= 32 ? k_conv3d_march_shared : k_conv3d_march)(ctx, dx1, dx2, wm1, wm2, dbias, dy, nullptr,
                                                                                N, X, Y, Z, C1, C2, Cout, relu, Cout, 0));
@@ -1761,7 +1768,7 @@ extern "C" int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const 
     FM_CHECK(conv_march_supported(X, Y, Z, Cout, 0, Cin, ksize), FM_EINVAL, "march kernel does not cover this shape");
     bf16* wm = nullptr;
     FM_TRY(s.alloc(&wm, (size_t)conv_march_pack_elems(Cout, Cin)));
-    FM_TRY(k_repack_march(ctx, wd, wm, Cin, Cout, 0, Cout));
+    FM_TRY(k_repack_march(ctx, wd, wm, Cin, Cout, 0, Cout, conv_march_kc(Cout, 0, Cin, Cout)));
     FM_TRY((impl == 3 && Cin <= 32 ? k_conv3d_march_shared : k_conv3d_march)(ctx, ddy, nullptr, wm, nullptr, nullptr, ddx,
                                                                              dmask, N, X, Y, Z, Cout, 0, Cin, 0, Cin, 0));
   } else if (impl == 0)

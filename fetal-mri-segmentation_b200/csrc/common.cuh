@@ -218,6 +218,7 @@ struct RepackDesc {
   int64_t w_off;   // offset of the master kernel [Cout][taps][C1+C2] in the flat fp32 parameter buffer
   int cout, taps, c1, c2;
   bf16 *wf, *wd0, *wd1, *mf0, *mf1, *md0, *md1;  // null = not needed
+  int kcf0, kcf1, kcd0, kcd1;                    // K-chunk widths of the four marching packs (conv_march_kc)
   int block0;      // first 256-thread block of this layer in the fused grid
 };
 int k_repack_all(fm_ctx*, const float* params, const RepackDesc* table_dev, int nlayers, int total_blocks,
@@ -240,7 +241,10 @@ int k_conv3d_tc_wgrad(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, 
 // conv_march.cu
 int conv_march_supported(int X, int Y, int Z, int C1, int C2, int Cout, int ksize);
 int64_t conv_march_pack_elems(int Cs, int Cout);
-int k_repack_march(fm_ctx*, const bf16* P, bf16* Wm, int Nrows, int Ktot, int kofs, int Cs);
+// K-chunk width of a source with Cs channels in a marching conv (C1 [+ C2] -> Cout): 64 (128-byte slab rows) unless the
+// resident filter bank leaves fewer than two slab slots per dz ring, then 32 (half-size slots, twice as many)
+int conv_march_kc(int C1, int C2, int Cout, int Cs);
+int k_repack_march(fm_ctx*, const bf16* P, bf16* Wm, int Nrows, int Ktot, int kofs, int Cs, int KC);
 int k_conv3d_march(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* wm1, const bf16* wm2,
                    const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2,
                    int Cout, int relu, int out_C, int out_cofs);

@@ -28,7 +28,7 @@ namespace {
 
 constexpr int kThreadsM = 256;  // warp 0 TMA, warps 1-3 MMA issue (one per dz slab copy), warps 4-7 epilogue
 constexpr int kBY = 16, kBZ = 8, kSlabRows = (kBY + 2) * kBZ;  // 144 rows per slab
-constexpr uint32_t kSlot = kSlabRows * 128;                    // 18432 B (1024-aligned)
+constexpr uint32_t kSlot = kSlabRows * 128;                    // 18432 B (1024-aligned): slab slot at KC = 64
 constexpr int kMaxRing = 16;
 
 struct alignas(64) MarchParams {
@@ -47,6 +47,7 @@ struct alignas(64) MarchParams {
   int out_C, out_cofs, relu;
   uint32_t w_bytes;   // bytes the weight TMA loads deliver (mbarrier expect_tx)
   uint32_t w_region;  // shared-memory bytes reserved for them (1024-aligned per source)
+  uint32_t slot;      // bytes per slab slot (1024-aligned)
   int debug;          // FETAL_B200_DEBUG ablation bits: 1 skip slab TMA, 2 skip MMAs, 4 skip epilogue body
   const float* bias;
   bf16* out;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
 
   const uint32_t w_base = smem0;
   const uint32_t a_base = smem0 + p.w_region;
-  const uint32_t bar0 = a_base + (uint32_t)p.stages * kSlot;
+  const uint32_t bar0 = a_base + (uint32_t)p.stages * p.slot;
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * p.stages + b); };
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
                 mbar_expect_tx_elect(full_bar(stage), 0);
               } else {
                 mbar_expect_tx_elect(full_bar(stage), bytes);
-                tma_load_5d_elect(a_base + stage * kSlot, &p.tmA[s], full_bar(stage), ch * p.KC[s], zc + dz, yc, xi, n);
+                tma_load_5d_elect(a_base + stage * p.slot, &p.tmA[s], full_bar(stage), ch * p.KC[s], zc + dz, yc, xi, n);
               }
               if (++sidx[dz] == S3) {
                 sidx[dz] = 0;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_kernel(const __grid
                 const uint32_t stage = (uint32_t)dz * S3 + sidx[dz];
                 mbar_wait(full_bar(stage), sph[dz]);
                 tc_fence_after();
-                uint32_t a_lo = desc_lo(a_base + stage * kSlot, 16u);
+                uint32_t a_lo = desc_lo(a_base + stage * p.slot, 16u);
                 uint32_t b_lo = b_lo0 + (uint32_t)(ch * 9) * btile16;
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) {
@@ -411,9 +412,15 @@ int conv_march_supported(int X, int Y, int Z, int C1, int C2, int Cout, int ksiz
 
 int64_t conv_march_pack_elems(int Cs, int Cout) { return (int64_t)27 * Cs * Cout; }
 
+int conv_march_kc(int C1, int C2, int Cout, int Cs) {
+  const int kc = std::min(Cs, 64);
+  if (kc < 64) return kc;
+  const int full_slots = (kMaxDynSmemM - 2048 - (int)march_w_region(C1, C2, Cout)) / (int)kSlot;
+  return full_slots < 6 ? 32 : 64;
+}
+
 // P: bf16 pack [Nrows][27][Ktot]; writes the march pack of channel range [kofs, kofs+Cs)
-int k_repack_march(fm_ctx* ctx, const bf16* P, bf16* Wm, int Nrows, int Ktot, int kofs, int Cs) {
-  const int KC = std::min(Cs, 64);
+int k_repack_march(fm_ctx* ctx, const bf16* P, bf16* Wm, int Nrows, int Ktot, int kofs, int Cs, int KC) {
   const int64_t total = (int64_t)27 * Cs * Nrows;
   ProfScope prof(ctx, "repack_march", 0.0, (double)total * 4.0);
   repack_march_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, ctx->stream>>>(P, Wm, Nrows, Ktot, kofs, Cs, KC);
@@ -476,7 +483,7 @@ int k_conv3d_march(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1,
   const bf16* wms[2] = {wm1, wm2};
   uint32_t wofs = 0, wbytes = 0;
   for (int s = 0; s < p.nsrc; ++s) {
-    const int KC = std::min(Cs[s], 64);
+    const int KC = conv_march_kc(C1, C2, Cout, Cs[s]);
     p.KC[s] = KC;
     p.nchunks[s] = Cs[s] / KC;
     p.wofs[s] = wofs;
@@ -512,11 +519,14 @@ int k_conv3d_march(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1,
   p.w_bytes = wbytes;
   p.w_region = wofs;
   const uint32_t w_region = wofs;
-  int stages = (kMaxDynSmemM - 2048 - (int)w_region) / (int)kSlot;
+  // slot = one slab at the widest K chunk in use (18 KB at KC = 64, 9 KB when every source runs at KC <= 32)
+  p.slot = (uint32_t)kSlabRows * (uint32_t)std::max(p.KC[0], p.nsrc > 1 ? p.KC[1] : 0) * 2u;
+  p.slot = (p.slot + 1023u) & ~1023u;
+  int stages = (kMaxDynSmemM - 2048 - (int)w_region) / (int)p.slot;
   stages = std::min(stages, 9) / 3 * 3;  // three private rings (one per dz slab copy / MMA warp)
   FM_CHECK(stages >= 3, FM_EINVAL, "conv3d march: filter bank leaves no room for the slab rings");
   p.stages = stages;
-  const size_t smem = (size_t)w_region + (size_t)stages * kSlot + 1024 + 512;
+  const size_t smem = (size_t)w_region + (size_t)stages * p.slot + 1024 + 512;
   FM_CHECK(smem <= (size_t)kMaxDynSmemM, FM_EINVAL, "conv3d march: %zu B of shared memory needed", smem);
   static bool attr_set = false;
   if (!attr_set) {

@@ -432,9 +432,8 @@ __global__ void repack_weights_kernel(const float* __restrict__ w, bf16* __restr
   }
 }
 
-__device__ __forceinline__ int64_t march_pack_index(int rows, int row, int tap, int k, int Ktot) {
-  // Wm[chunk][dz][dy][kxr][row][kc] with tap = (kx*3 + ky)*3 + kz, kxr = 2 - kx, KC = min(Ktot, 64)
-  const int KC = Ktot < 64 ? Ktot : 64;
+__device__ __forceinline__ int64_t march_pack_index(int rows, int row, int tap, int k, int KC) {
+  // Wm[chunk][dz][dy][kxr][row][kc] with tap = (kx*3 + ky)*3 + kz, kxr = 2 - kx
   const int kx = tap / 9, ky = (tap / 3) % 3, kz = tap % 3;
   const int ch = k / KC, kc = k % KC;
   return ((((int64_t)(ch * 3 + kz) * 3 + ky) * 3 + (2 - kx)) * rows + row) * KC + kc;
@@ -461,9 +460,9 @@ __global__ void __launch_bounds__(kThreads) repack_all_kernel(const float* __res
   bf16* wd = second ? d.wd1 : d.wd0;
   if (wd) wd[((int64_t)cs * d.taps + tf) * d.cout + co] = v;
   bf16* mf = second ? d.mf1 : d.mf0;
-  if (mf) mf[march_pack_index(d.cout, co, tap, cs, Cs)] = v;
+  if (mf) mf[march_pack_index(d.cout, co, tap, cs, second ? d.kcf1 : d.kcf0)] = v;
   bf16* md = second ? d.md1 : d.md0;
-  if (md) md[march_pack_index(Cs, cs, tf, co, d.cout)] = v;
+  if (md) md[march_pack_index(Cs, cs, tf, co, second ? d.kcd1 : d.kcd0)] = v;
 }
 
 inline int grid_for(int64_t work_items, int cap = 1 << 30) {
