@@ -662,15 +662,22 @@ __global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __r
   }
 }
 
-__global__ void dice_final_kernel(const double* __restrict__ part, int nblocks, double n_elems,
-                                  double* __restrict__ sums, int accumulate) {
+__global__ void __launch_bounds__(256) dice_final_kernel(const double* __restrict__ part, int nblocks, double n_elems,
+                                                         double* __restrict__ sums, int accumulate) {
   FM_PDL_SYNC();
-  const int k = threadIdx.x;
-  if (k < 7) {
-    double a = 0.0;
-    for (int b = 0; b < nblocks; ++b) a += part[(int64_t)b * 8 + k];
-    sums[k] = accumulate ? sums[k] + a : a;
-  } else if (k == 7) {
+  // 32 strided partial chains per statistic, then a fixed-order fold: deterministic, ~20 dependent adds deep
+  __shared__ double sh[32][8];
+  const int k = threadIdx.x & 7, j = threadIdx.x >> 3;
+  double a = 0.0;
+  if (k < 7)
+    for (int b = j; b < nblocks; b += 32) a += part[(int64_t)b * 8 + k];
+  sh[j][k] = a;
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double s = 0.0;
+    for (int g = 0; g < 32; ++g) s += sh[g][threadIdx.x];
+    sums[threadIdx.x] = accumulate ? sums[threadIdx.x] + s : s;
+  } else if (threadIdx.x == 7) {
     sums[7] = accumulate ? sums[7] + n_elems : n_elems;
   }
 }
@@ -928,7 +935,7 @@ int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* 
   ProfScope prof(ctx, "dice_sums", 0.0, (double)n * 8.0);
   FM_CUDA(launch_pdl(dice_partial_kernel, dim3(kRedBlocks), dim3(kThreads), 0, ctx->stream, p, t, n, ctx->red_scratch));
   FM_LAUNCH_OK(ctx);
-  FM_CUDA(launch_pdl(dice_final_kernel, dim3(1), dim3(32), 0, ctx->stream, ctx->red_scratch, kRedBlocks, (double)n, sums,
+  FM_CUDA(launch_pdl(dice_final_kernel, dim3(1), dim3(256), 0, ctx->stream, ctx->red_scratch, kRedBlocks, (double)n, sums,
                                               accumulate));
   FM_LAUNCH_OK(ctx);
   return FM_OK;

@@ -262,12 +262,23 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_shared_kernel(const
       for (int xo = xa; xo < xb; ++xo) {
         const uint32_t seq = ocount + (uint32_t)(xo - xa);
         const uint32_t rb = seq & ((uint32_t)p.R - 1u);
-        mbar_wait(tfull_bar(rb), (seq >> (31u - (uint32_t)__clz(p.R))) & 1u);
-        tc_fence_after();
         const int64_t v = (((int64_t)n * p.X + xo) * p.Y + y) * p.Z + z;
         const int64_t off = v * p.out_C + p.out_cofs;
+        const int ncg = (dbg & 4) ? 0 : p.Cn / 16;
+        // dgrad: fetch this row's ReLU mask BEFORE waiting for the accumulator, so its latency hides behind the MMAs
+        uint4 mk[8];
+        if (p.mask != nullptr) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off);
+#pragma unroll
+          for (int h = 0; h < 8; ++h)
+            if (h < 2 * ncg) mk[h] = __ldg(mp + h);
+        }
+        mbar_wait(tfull_bar(rb), (seq >> (31u - (uint32_t)__clz(p.R))) & 1u);
+        tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + rb * (uint32_t)p.Cn;
-        for (int c16 = 0; c16 < ((dbg & 4) ? 0 : p.Cn / 16); ++c16) {
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          if (c16 >= ncg) break;
           uint32_t r[16];
           tmem_ld16(taddr + (uint32_t)c16 * 16u, r);
           tmem_ld_wait();
@@ -291,10 +302,9 @@ __global__ void __launch_bounds__(kThreadsM, 1) conv3d_march_shared_kernel(const
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if (p.mask != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off + c16 * 16);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const uint4 mv = __ldg(mp + h);
+              const uint4 mv = mk[2 * c16 + h];
               const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
