@@ -23,6 +23,9 @@ def _worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
+    # bit-reproducible training kernels: per-sample activations are then identical in the 2 x 2 and the 1 x 4 runs and
+    # only the fp32 summation order of the weight gradients differs
+    os.environ["FETAL_B200_DETERMINISTIC"] = "1"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda:%d" % rank))
     from fetal_net.distributed import DataParallelTrainer, sharded_patch_wise_prediction
@@ -55,7 +58,7 @@ def _worker(rank, world, port, out):
             cos.append(float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300)))
         # inference reference with the post-step weights of the DP model (identical on all ranks)
         single = patch_wise_prediction(model, vol, (32, 32, 32), overlap_factor=0.5)
-        out.put(dict(res=res, ref=ref, min_cos=min(cos), infer_equal=bool(np.array_equal(sharded, single)),
+        out.put(dict(res=res, ref=ref, min_cos=min(cos), argmin=int(np.argmin(cos)), cos=[round(v, 5) for v in cos], infer_equal=bool(np.array_equal(sharded, single)),
                      infer_maxdiff=float(np.abs(sharded - single).max())))
     dist.barrier()
     dist.destroy_process_group()
@@ -72,9 +75,9 @@ def test_data_parallel_step_and_sharded_inference():
     r = q.get(timeout=300)
     [p.join(timeout=120) for p in procs]
     # same global Dice loss / metrics as the single-process step on the full batch
-    # (training passes use the shared-accumulator marching kernel: last-bit differences in bf16 activations)
-    assert r["res"][0] == pytest.approx(r["ref"][0], abs=2e-4), r
-    assert r["res"][1] == pytest.approx(r["ref"][1], abs=2e-4), r
-    # summed gradients == full-batch gradients (bf16 activations identical per sample; fp32 red.add order differs)
-    assert r["min_cos"] >= 0.999, r
+    # (FETAL_B200_DETERMINISTIC=1 in the workers: forward activations are bit-identical per sample)
+    assert r["res"][0] == pytest.approx(r["ref"][0], abs=1e-6), r
+    assert r["res"][1] == pytest.approx(r["ref"][1], abs=1e-6), r
+    # summed gradients == full-batch gradients (only the fp32 red.add order differs)
+    assert r["min_cos"] >= 0.9999, r
     assert r["infer_equal"], r
