@@ -51,50 +51,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe). NVML is polled from a thread
+    every few ms (nvidia-smi -lms cannot deliver a sample inside a 50 ms region); the fields are the ones
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` prints."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.thread, self.run = device, [], None, False
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(int(self.device))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.run = True
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll(self):
+        nv = self.nv
+        while self.run:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(mhz), int(rs)))
             except Exception:
                 pass
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+            time.sleep(0.01)
+
+    def stop(self):
+        if self.nv is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable"], samples=0)
+        self.run = False
+        self.thread.join(timeout=1)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({nm for _, rs in self.rows for bit, nm in self.REASONS.items() if rs & bit})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=self.max_mhz, reasons=reasons,
+                    samples=len(sm))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -329,33 +331,52 @@ def run_infer(args):
     for _ in range(max(args.warmup, 3)):
         out = patch_wise_prediction(model, vol, PATCH, overlap_factor=OVERLAP, batch_size=49)
     l0 = ctx.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out = patch_wise_prediction(model, vol, PATCH, overlap_factor=OVERLAP, batch_size=49)
     sec = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    launches = int((ctx.launch_count() - l0) // args.steps)
     nvox = int(np.prod(VOLUME))
+    # device leg: the same call with per-launch CUDA events (gather + network + overlap-add, no host copies)
     ctx.profile(True)
     t1 = time.perf_counter()
     out = patch_wise_prediction(model, vol, PATCH, overlap_factor=OVERLAP, batch_size=49)
     prof_wall = time.perf_counter() - t1
     agg = {}
     for name, kms, fl, by in ctx.profile_records():
-        a = agg.setdefault(name, [0, 0.0])
+        a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
         a[0] += 1
         a[1] += kms
+        a[2] += fl
+        a[3] += by
     ctx.profile(False)
-    breakdown = {k: dict(launches=a[0], ms=a[1]) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
-    breakdown["_sum_kernels_ms"] = sum(a[1] for a in agg.values())
+    dev_ms = sum(a[1] for a in agg.values())
+    breakdown = {k: dict(launches=a[0], ms=a[1], tflops=(a[2] / a[1] / 1e9 if a[2] else None),
+                         gbs=(a[3] / a[1] / 1e6 if a[3] else None))
+                 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+    breakdown["_sum_kernels_ms"] = dev_ms
     breakdown["_wall_ms_profiled_call"] = prof_wall * 1e3
-    line = dict(metric="U-Net infer voxels/sec", value=nvox / sec, unit=UNIT, n_gpus=1, steps=args.steps,
-                warmup=max(args.warmup, 3), ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
+    pk = peaks()
+    top = max(agg.items(), key=lambda kv: kv[1][1])
+    roof = dict(kernel=top[0], bound="tensor", achieved=top[1][2] / top[1][1] / 1e9, peak=pk["tf_sustained"],
+                unit="TFLOP/s", frac=top[1][2] / top[1][1] / 1e9 / pk["tf_sustained"], traffic=None,
+                peak_source=pk["src"] + " (sustained)", launches_per_step=top[1][0], share_of_step=top[1][1] / dev_ms)
+    line = dict(metric="U-Net infer voxels/sec", value=nvox / (dev_ms * 1e-3), unit=UNIT, n_gpus=1, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=dev_ms, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload="patch_wise_prediction 1x256x256x64, patch 64^3, overlap_factor 0.5, 49 patches "
-                                     "(BASELINE configs[0])", patches=49, batch_size=49),
+                                     "(BASELINE configs[0])", patches=49, batch_size=49,
+                            value_is="output voxels / summed kernel time of one call (volume resident in HBM)",
+                            l2="49 patches x 64^3 x up to 96 channels of activations per call >> 126 MB L2"),
+                clocks=clocks,
                 e2e=dict(value=nvox / sec, unit=UNIT, h2d_bytes_per_step=int(vol.nbytes),
-                         d2h_bytes_per_step=int(out.nbytes + nvox * 2)),
-                gpu_launches=int((ctx.launch_count() - l0) // args.steps),
-                conv_tflops=49 * FWD_GF_PER_PATCH / (sec * 1e3), out_mean=float(out.mean()), kernel_breakdown=breakdown)
+                         d2h_bytes_per_step=int(out.nbytes), ms_per_step=sec * 1e3),
+                gpu_launches=launches, roofline=roof,
+                patch_voxels_per_s=49 * int(np.prod(PATCH)) / sec,
+                conv_tflops=49 * FWD_GF_PER_PATCH / dev_ms, out_mean=float(out.mean()), kernel_breakdown=breakdown)
     print(json.dumps(line))
 
 
