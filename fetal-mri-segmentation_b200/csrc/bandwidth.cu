@@ -258,6 +258,45 @@ __global__ void upsample3d_bwd_kernel(const bf16* __restrict__ dy, const bf16* _
 }
 
 
+// Block fold of per-thread (a[8], b[8]) partials over the threads that share a channel group (tid % c8n), c8n a power
+// of two <= 64: xor-shuffles inside a warp, one shared-memory hop across warps, fixed order -> deterministic.
+// Returns true in the c8n threads (tid < c8n) that hold the block totals of channel group `tid`.
+__device__ __forceinline__ bool fold_channel_groups(float a[8], float b[8], float* sh, int c8n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (c8n < 32) {
+    for (int o = c8n; o < 32; o <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        b[i] += __shfl_xor_sync(0xffffffffu, b[i], o);
+      }
+    if (lane < c8n)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sh[(warp * c8n + lane) * 16 + i] = a[i];
+        sh[(warp * c8n + lane) * 16 + 8 + i] = b[i];
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sh[threadIdx.x * 16 + i] = a[i];
+      sh[threadIdx.x * 16 + 8 + i] = b[i];
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= c8n) return false;
+  const int groups = c8n < 32 ? kThreads / 32 : kThreads / c8n;  // rows of sh holding this channel group
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+  for (int k = 0; k < groups; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i] += sh[(k * c8n + threadIdx.x) * 16 + i];
+      b[i] += sh[(k * c8n + threadIdx.x) * 16 + 8 + i];
+    }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // InstanceNormalization(axis=1) + LeakyReLU(0.3) — keras_contrib layer used by every Isensee conv block
 // (fetal_net/model/unet3d/isensee2017.py:12, unet3d/unet.py:107-111): per (sample, channel) mean / biased
@@ -289,20 +328,8 @@ __global__ void __launch_bounds__(kThreads) instnorm_partial_kernel(const bf16* 
         q[i] += f[i] * f[i];
       }
     }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sh[threadIdx.x * 16 + i] = s[i];
-    sh[threadIdx.x * 16 + 8 + i] = q[i];
-  }
-  __syncthreads();
-  if (l == 0) {
-    for (int k = 1; k < lanes; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += sh[(k * c8n + c8) * 16 + i];
-        q[i] += sh[(k * c8n + c8) * 16 + 8 + i];
-      }
-    float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + c8 * 8) * 2;
+  if (fold_channel_groups(s, q, sh, c8n)) {
+    float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + threadIdx.x * 8) * 2;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       o[2 * i] = s[i];
@@ -311,20 +338,27 @@ __global__ void __launch_bounds__(kThreads) instnorm_partial_kernel(const bf16* 
   }
 }
 
-// scale/shift per (n, c): y = x * scale + shift with scale = gamma / (sqrt(var) + eps), shift = beta - mean * scale
+// scale/shift per (n, c): y = x * scale + shift with scale = gamma / (sqrt(var) + eps), shift = beta - mean * scale.
+// One warp per (n, c): lane l folds partials l, l+32, ... in fp64, then a fixed-order butterfly (deterministic).
 __global__ void instnorm_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float* __restrict__ ss,
                                       float* __restrict__ stats, int N, int C, int blocks_per_sample,
                                       double inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < blocks_per_sample; ++b) {
-    const float* o = part + (((int64_t)n * blocks_per_sample + b) * C + c) * 2;
-    s += (double)o[0];
-    q += (double)o[1];
+  for (int b = lane; b < blocks_per_sample; b += 32) {
+    const float2 o = *reinterpret_cast<const float2*>(part + (((int64_t)n * blocks_per_sample + b) * C + c) * 2);
+    s += (double)o.x;
+    q += (double)o.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane != 0) return;
   const double mean = s * inv_count;
   const double var = fmax(q * inv_count - mean * mean, 0.0);
   const double scale = (double)gamma[c] / (sqrt(var) + (double)eps);
@@ -336,38 +370,44 @@ __global__ void instnorm_final_kernel(const float* __restrict__ part, const floa
   }
 }
 
-__global__ void instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ ss,
-                                      const bf16* __restrict__ add, const float* __restrict__ chan_scale,
-                                      bf16* __restrict__ y, int64_t vox_per_sample, int C, int N, float slope) {
+// grid (blocks per sample, N): a thread keeps its 8 channels' (scale, shift[, dropout scale]) in registers and walks
+// the voxels of its block
+__global__ void __launch_bounds__(kThreads) instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ ss,
+                                                                  const bf16* __restrict__ add,
+                                                                  const float* __restrict__ chan_scale,
+                                                                  bf16* __restrict__ y, int64_t vox_per_sample, int C,
+                                                                  int64_t vox_per_block, float slope) {
   const int c8n = C >> 3;
-  const int64_t total = (int64_t)N * vox_per_sample * c8n;
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
-  const int c8 = (int)(g % c8n);
-  const int64_t v = g / c8n;
-  const int n = (int)(v / vox_per_sample);
-  float f[8], a[8];
-  unpack8(ldg16(x + v * C + c8 * 8), f);
+  const int lanes = kThreads / c8n;
+  const int c8 = threadIdx.x % c8n, l = threadIdx.x / c8n;
+  if (l >= lanes) return;
+  const int n = blockIdx.y;
+  float sc[8], sh[8], cs[8];
   const float4* sp = reinterpret_cast<const float4*>(ss + ((int64_t)n * C + c8 * 8) * 2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 t = __ldg(sp + i);  // (scale, shift) of two channels
-    float u = f[2 * i] * t.x + t.y, w = f[2 * i + 1] * t.z + t.w;
-    f[2 * i] = u > 0.f ? u : slope * u;
-    f[2 * i + 1] = w > 0.f ? w : slope * w;
+    sc[2 * i] = t.x, sh[2 * i] = t.y, sc[2 * i + 1] = t.z, sh[2 * i + 1] = t.w;
   }
-  if (chan_scale != nullptr) {  // SpatialDropout3D: one keep/scale factor per (sample, channel)
-    const float4* cp = reinterpret_cast<const float4*>(chan_scale + (int64_t)n * C + c8 * 8);
-    const float4 s0 = __ldg(cp), s1 = __ldg(cp + 1);
-    f[0] *= s0.x, f[1] *= s0.y, f[2] *= s0.z, f[3] *= s0.w;
-    f[4] *= s1.x, f[5] *= s1.y, f[6] *= s1.z, f[7] *= s1.w;
-  }
-  if (add != nullptr) {
-    unpack8(ldg16(add + v * C + c8 * 8), a);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] += a[i];
+  for (int i = 0; i < 8; ++i) cs[i] = chan_scale ? __ldg(chan_scale + (int64_t)n * C + c8 * 8 + i) : 1.f;
+  const int64_t v0 = (int64_t)n * vox_per_sample + (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v1 = min((int64_t)(n + 1) * vox_per_sample, v0 + vox_per_block);
+  for (int64_t v = v0 + l; v < v1; v += lanes) {
+    float f[8], a[8];
+    unpack8(ldg16(x + v * C + c8 * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float u = f[i] * sc[i] + sh[i];
+      f[i] = (u > 0.f ? u : slope * u) * cs[i];
+    }
+    if (add != nullptr) {
+      unpack8(ldg16(add + v * C + c8 * 8), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += a[i];
+    }
+    stg16(y + v * C + c8 * 8, pack8(f));
   }
-  stg16(y + v * C + c8 * 8, pack8(f));
 }
 
 
@@ -392,7 +432,26 @@ struct NormBwdArgs {
   float slope;
 };
 
-__device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, int n, int64_t v, int c8, float g[8], float xh[8]) {
+struct NormConst {
+  float mean[8], inv_s[8], gamma[8], beta[8], cs[8];
+};
+__device__ __forceinline__ void norm_load_const(const NormBwdArgs& a, int n, int c8, NormConst& k) {
+  const float4* sp = reinterpret_cast<const float4*>(a.stats + ((int64_t)n * a.C + c8 * 8) * 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 st = __ldg(sp + i);  // (mean, 1/s) of two channels
+    k.mean[2 * i] = st.x, k.inv_s[2 * i] = st.y, k.mean[2 * i + 1] = st.z, k.inv_s[2 * i + 1] = st.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = c8 * 8 + i;
+    k.gamma[i] = __ldg(a.gamma + ch);
+    k.beta[i] = __ldg(a.beta + ch);
+    k.cs[i] = a.chan_scale ? __ldg(a.chan_scale + (int64_t)n * a.C + ch) : 1.f;
+  }
+}
+__device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, const NormConst& k, int64_t v, int c8, float g[8],
+                                           float xh[8]) {
   float x[8], t[8];
   unpack8(ldg16(a.x + v * a.C + c8 * 8), x);
   unpack8(ldg16(a.gy + v * a.C + c8 * 8), g);
@@ -401,20 +460,11 @@ __device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, int n, int64_t 
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += t[i];
   }
-  const float4* sp = reinterpret_cast<const float4*>(a.stats + ((int64_t)n * a.C + c8 * 8) * 2);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 st = __ldg(sp + i);  // (mean, 1/s) of two channels
-    xh[2 * i] = (x[2 * i] - st.x) * st.y;
-    xh[2 * i + 1] = (x[2 * i + 1] - st.z) * st.w;
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int ch = c8 * 8 + i;
-    const float z = __ldg(a.gamma + ch) * xh[i] + __ldg(a.beta + ch);
-    float s = z > 0.f ? 1.f : a.slope;
-    if (a.chan_scale != nullptr) s *= __ldg(a.chan_scale + (int64_t)n * a.C + ch);
-    g[i] *= s;
+    xh[i] = (x[i] - k.mean[i]) * k.inv_s[i];
+    const float z = k.gamma[i] * xh[i] + k.beta[i];
+    g[i] *= (z > 0.f ? 1.f : a.slope) * k.cs[i];
   }
 }
 
@@ -430,30 +480,21 @@ __global__ void __launch_bounds__(kThreads) instnorm_bwd_partial_kernel(NormBwdA
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  if (l < lanes)
+  if (l < lanes) {
+    NormConst k;
+    norm_load_const(a, n, c8, k);
     for (int64_t v = v0 + l; v < v1; v += lanes) {
       float g[8], xh[8];
-      norm_bwd_g(a, n, v, c8, g, xh);
+      norm_bwd_g(a, k, v, c8, g, xh);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s1[i] += g[i];
         s2[i] += g[i] * xh[i];
       }
     }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sh[threadIdx.x * 16 + i] = s1[i];
-    sh[threadIdx.x * 16 + 8 + i] = s2[i];
   }
-  __syncthreads();
-  if (l == 0) {
-    for (int k = 1; k < lanes; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s1[i] += sh[(k * c8n + c8) * 16 + i];
-        s2[i] += sh[(k * c8n + c8) * 16 + 8 + i];
-      }
-    float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + c8 * 8) * 2;
+  if (fold_channel_groups(s1, s2, sh, c8n)) {
+    float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + threadIdx.x * 8) * 2;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       o[2 * i] = s1[i];
@@ -462,20 +503,27 @@ __global__ void __launch_bounds__(kThreads) instnorm_bwd_partial_kernel(NormBwdA
   }
 }
 
-// coef[n][c] = (gamma / s, mean(g), (s / sigma) * mean(g * xh)); dgamma / dbeta accumulate over the samples
+// coef[n][c] = (gamma / s, mean(g), (s / sigma) * mean(g * xh)); dgamma / dbeta accumulate over the samples.
+// One warp per (n, c), fixed-order fold of the block partials.
 __global__ void instnorm_bwd_final_kernel(const float* __restrict__ part, const float* __restrict__ stats,
                                           const float* __restrict__ gamma, float* __restrict__ coef,
                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C,
                                           int blocks_per_sample, double inv_count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N * C) return;
   const int n = i / C, c = i % C;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < blocks_per_sample; ++b) {
-    const float* o = part + (((int64_t)n * blocks_per_sample + b) * C + c) * 2;
-    s1 += (double)o[0];
-    s2 += (double)o[1];
+  for (int b = lane; b < blocks_per_sample; b += 32) {
+    const float2 o = *reinterpret_cast<const float2*>(part + (((int64_t)n * blocks_per_sample + b) * C + c) * 2);
+    s1 += (double)o.x;
+    s2 += (double)o.y;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane != 0) return;
   const double inv_s = (double)stats[2 * i + 1];
   const double s = 1.0 / inv_s;
   const double sigma = fmax(s - (double)eps, 1e-12);
@@ -487,24 +535,32 @@ __global__ void instnorm_bwd_final_kernel(const float* __restrict__ part, const 
   atomicAdd(dbeta + c, (float)s1);
 }
 
+// grid (blocks per sample, N), like the partial pass
 __global__ void __launch_bounds__(kThreads) instnorm_bwd_apply_kernel(NormBwdArgs a, const float* __restrict__ coef,
-                                                                      bf16* __restrict__ dx, int N) {
+                                                                      bf16* __restrict__ dx, int64_t vox_per_block) {
   const int c8n = a.C >> 3;
-  const int64_t total = (int64_t)N * a.vox_per_sample * c8n;
-  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= total) return;
-  const int c8 = (int)(gi % c8n);
-  const int64_t v = gi / c8n;
-  const int n = (int)(v / a.vox_per_sample);
-  float g[8], xh[8];
-  norm_bwd_g(a, n, v, c8, g, xh);
+  const int lanes = kThreads / c8n;
+  const int c8 = threadIdx.x % c8n, l = threadIdx.x / c8n;
+  if (l >= lanes) return;
+  const int n = blockIdx.y;
+  NormConst k;
+  norm_load_const(a, n, c8, k);
+  float ca[8], cm1[8], cm2[8];
   const float4* cp = reinterpret_cast<const float4*>(coef + ((int64_t)n * a.C + c8 * 8) * 4);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 k = __ldg(cp + i);
-    g[i] = k.x * (g[i] - k.y - xh[i] * k.z);
+    const float4 t = __ldg(cp + i);
+    ca[i] = t.x, cm1[i] = t.y, cm2[i] = t.z;
   }
-  stg16(dx + v * a.C + c8 * 8, pack8(g));
+  const int64_t v0 = (int64_t)n * a.vox_per_sample + (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v1 = min((int64_t)(n + 1) * a.vox_per_sample, v0 + vox_per_block);
+  for (int64_t v = v0 + l; v < v1; v += lanes) {
+    float g[8], xh[8];
+    norm_bwd_g(a, k, v, c8, g, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = ca[i] * (g[i] - cm1[i] - xh[i] * cm2[i]);
+    stg16(dx + v * a.C + c8 * 8, pack8(g));
+  }
 }
 
 // transposed-conv helper for the stride-2 in-convs: fine[2v + 1] = coarse[v] per axis, zero elsewhere. A stride-1
@@ -1077,8 +1133,14 @@ int k_divide_by_count(fm_ctx* ctx, double* out, const int16_t* count, int64_t nv
 
 // x: raw conv output [N][vox][C] bf16 -> y = LeakyReLU(InstanceNorm(x)) (+ add). `scratch` >= N*C*2*(blocks+1) floats.
 static int norm_blocks(int64_t vox_per_sample, int64_t* vpb) {
-  int bps = (int)std::min<int64_t>(std::max<int64_t>(1, vox_per_sample / 2048), 1024);
+  int bps = (int)std::min<int64_t>(std::max<int64_t>(1, vox_per_sample / 512), 1024);
   *vpb = ceil_div64(vox_per_sample, bps);
+  return (int)ceil_div64(vox_per_sample, *vpb);
+}
+// the element-wise passes want many more, smaller blocks: ~4 voxels per thread
+static int norm_apply_blocks(int64_t vox_per_sample, int C, int64_t* vpb) {
+  const int lanes = kThreads / (C / 8);
+  *vpb = (int64_t)lanes * 4;
   return (int)ceil_div64(vox_per_sample, *vpb);
 }
 
@@ -1087,7 +1149,7 @@ static int norm_blocks(int64_t vox_per_sample, int64_t* vpb) {
 int k_instnorm_lrelu_bwd(fm_ctx* ctx, const bf16* x, const float* stats, const float* gamma, const float* beta,
                          const bf16* gy, const bf16* gy2, const float* chan_scale, bf16* dx, float* dgamma,
                          float* dbeta, int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats) {
-  FM_CHECK(C % 8 == 0 && C <= 8 * kThreads, FM_EINVAL, "instnorm bwd: C=%d unsupported", C);
+  FM_CHECK(C >= 8 && C <= 512 && (C & (C - 1)) == 0, FM_EINVAL, "instnorm bwd: C=%d must be a power of two in [8,512]", C);
   int64_t vpb;
   const int bps = norm_blocks(vox_per_sample, &vpb);
   const size_t need = (size_t)N * C * (2 * (size_t)bps + 4);
@@ -1098,11 +1160,13 @@ int k_instnorm_lrelu_bwd(fm_ctx* ctx, const bf16* x, const float* stats, const f
   ProfScope prof(ctx, "instnorm_lrelu_bwd", 0.0, (double)N * vox_per_sample * C * (gy2 ? 14.0 : 10.0));
   instnorm_bwd_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(a, part, vpb, bps);
   FM_LAUNCH_OK(ctx);
-  instnorm_bwd_final_kernel<<<ceil_div(N * C, 128), 128, 0, ctx->stream>>>(part, stats, gamma, coef, dgamma, dbeta, N, C,
-                                                                            bps, 1.0 / (double)vox_per_sample, 1e-3f);
+  instnorm_bwd_final_kernel<<<ceil_div(N * C * 32, 128), 128, 0, ctx->stream>>>(part, stats, gamma, coef, dgamma, dbeta,
+                                                                                 N, C, bps, 1.0 / (double)vox_per_sample,
+                                                                                 1e-3f);
   FM_LAUNCH_OK(ctx);
-  const int64_t total = (int64_t)N * vox_per_sample * (C / 8);
-  instnorm_bwd_apply_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(a, coef, dx, N);
+  int64_t vpa;
+  const int bpa = norm_apply_blocks(vox_per_sample, C, &vpa);
+  instnorm_bwd_apply_kernel<<<dim3(bpa, N), kThreads, 0, ctx->stream>>>(a, coef, dx, vpa);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -1139,10 +1203,9 @@ int k_dropout_scale(fm_ctx* ctx, float* scale, int n, float rate, uint64_t seed)
 int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, const bf16* add, bf16* y,
                      int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats, float* stats,
                      const float* chan_scale) {
-  FM_CHECK(C % 8 == 0 && C <= 8 * kThreads, FM_EINVAL, "instnorm: C=%d unsupported", C);
-  int bps = (int)std::min<int64_t>(std::max<int64_t>(1, vox_per_sample / 2048), 1024);
-  const int64_t vpb = ceil_div64(vox_per_sample, bps);
-  bps = (int)ceil_div64(vox_per_sample, vpb);
+  FM_CHECK(C >= 8 && C <= 512 && (C & (C - 1)) == 0, FM_EINVAL, "instnorm: C=%d must be a power of two in [8,512]", C);
+  int64_t vpb;
+  const int bps = norm_blocks(vox_per_sample, &vpb);
   const size_t need = (size_t)N * C * 2 * ((size_t)bps + 1);
   FM_CHECK(scratch_floats >= need, FM_EINVAL, "instnorm: scratch too small (%zu < %zu floats)", scratch_floats, need);
   float* part = scratch;
@@ -1151,12 +1214,13 @@ int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float
   instnorm_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(x, part, vox_per_sample,
                                                                                                C, vpb, bps);
   FM_LAUNCH_OK(ctx);
-  instnorm_final_kernel<<<ceil_div(N * C, 128), 128, 0, ctx->stream>>>(part, gamma, beta, ss, stats, N, C, bps,
-                                                                        1.0 / (double)vox_per_sample, 1e-3f);
+  instnorm_final_kernel<<<ceil_div(N * C * 32, 128), 128, 0, ctx->stream>>>(part, gamma, beta, ss, stats, N, C, bps,
+                                                                             1.0 / (double)vox_per_sample, 1e-3f);
   FM_LAUNCH_OK(ctx);
-  const int64_t total = (int64_t)N * vox_per_sample * (C / 8);
-  instnorm_apply_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(x, ss, add, chan_scale, y, vox_per_sample, C, N,
-                                                                        0.3f);
+  int64_t vpa;
+  const int bpa = norm_apply_blocks(vox_per_sample, C, &vpa);
+  instnorm_apply_kernel<<<dim3(bpa, N), kThreads, 0, ctx->stream>>>(x, ss, add, chan_scale, y, vox_per_sample, C, vpa,
+                                                                     0.3f);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -45,6 +45,7 @@ struct alignas(64) WgMarchParams {
   int ctas_per_pair;   // grid = n_ci * n_co * ctas_per_pair
   int S3;              // X slab slots per kz ring
   int kcx;             // input channels per CTA / per M block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cin = 16)
+  int kcy;             // output channels per CTA / per N block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cout = 16)
   int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
   float* dw;
 };
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         for (; next_dy <= need; ++next_dy, ++dcount) {
           const uint32_t slot = dcount & (uint32_t)(kDyRing - 1);
           mbar_wait(dyempty_bar(slot), ((dcount >> 3) & 1u) ^ 1u);
-          mbar_expect_tx_elect(dyfull_bar(slot), kDyTile);
-          tma_load_5d_elect(dy_base + slot * kDyTile, &p.tmDY, dyfull_bar(slot), coc * kCC, iz * kBZ, iy * kBY, next_dy, n);
+          mbar_expect_tx_elect(dyfull_bar(slot), (uint32_t)(kBY * kBZ) * (uint32_t)p.kcy * 2u);
+          tma_load_5d_elect(dy_base + slot * kDyTile, &p.tmDY, dyfull_bar(slot), coc * p.kcy, iz * kBZ, iy * kBY, next_dy, n);
         }
 #pragma unroll
         for (int dz = 0; dz < 3; ++dz) {
@@ -150,10 +151,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     // ===== MMA warps: warp w issues the kz = w - 1 slab copy into its own accumulator =====
     const int dz = warp_u - 1;
     const uint32_t d_acc = tmem_base + (uint32_t)(dz * kNcols);
-    const uint32_t idesc1 = make_idesc(128, kCC, 1, 1), idesc2 = make_idesc(128, 2 * kCC, 1, 1),
-                   idesc3 = make_idesc(128, 3 * kCC, 1, 1);
-    const uint32_t hi32 = desc_hi(kSbo, layout_code((int)kRow));            // dY operand: 64-byte rows
-    const uint32_t kstep = (2u * kSbo) >> 4;  // 16 voxels (two 8-row groups) per MMA, in 16-byte units
+    const uint32_t ncy = (uint32_t)p.kcy;
+    const uint32_t idesc1 = make_idesc(128, (int)ncy, 1, 1), idesc2 = make_idesc(128, 2 * (int)ncy, 1, 1),
+                   idesc3 = make_idesc(128, 3 * (int)ncy, 1, 1);
+    const uint32_t b_row = ncy * 2u, b_sbo = 8u * b_row;                     // dY operand: 64- or 32-byte rows
+    const uint32_t hi32 = desc_hi(b_sbo, layout_code((int)b_row));
+    const uint32_t kstep = (2u * b_sbo) >> 4;  // 16 voxels (two 8-row groups) per MMA, in 16-byte units
     const uint32_t a_row = (uint32_t)p.kcx * 2u, a_sbo = 8u * a_row;         // X operand: 64- or 32-byte rows
     const uint32_t a_hi32 = desc_hi(a_sbo, layout_code((int)a_row));
     const uint32_t a_kstep = (2u * a_sbo) >> 4;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         uint32_t a_lo = desc_lo(x_base + stage * kXSlot, a_sbo);          // M blocks (ky) one atom apart
         uint32_t bA = desc_lo(dy_base + rs * kDyTile, kDyTile);           // N blocks (kx) one ring slot apart
         uint32_t bB = desc_lo(dy_base, kDyTile);
-        const uint32_t dA = d_acc + j_lo * kCC, dB = dA + nA * kCC;
+        const uint32_t dA = d_acc + j_lo * ncy, dB = dA + nA * ncy;
 #pragma unroll
         for (int ks = 0; ks < (kBY * kBZ) / 16; ++ks) {
           umma_bf16_lh_elect(dA, a_lo, a_hi32, bA, hi32, idA, 1u);
@@ -219,16 +222,17 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     tc_fence_after();
     const int ky = row / p.kcx, ci = row % p.kcx;
     for (int dz = 0; dz < 3; ++dz) {
-      for (int c16 = 0; c16 < kNcols / 16; ++c16) {
+      for (int c16 = 0; c16 < 3 * p.kcy / 16; ++c16) {
         uint32_t r[16];
         tmem_ld16(lane_base + (uint32_t)(dz * kNcols + c16 * 16), r);
         tmem_ld_wait();
         if (ky < 3) {
-          const int kx = 2 - (c16 >> 1);                 // 32 columns per kx block
+          const int col = c16 * 16;                      // kcy columns per kx block
+          const int kx = 2 - col / p.kcy;
           const int tap = (kx * 3 + ky) * 3 + dz;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = coc * kCC + (c16 & 1) * 16 + j;
+            const int co = coc * p.kcy + col % p.kcy + j;
             atomicAdd(p.dw + ((int64_t)co * 27 + tap) * p.Ct + p.cofs + cic * p.kcx + ci, __uint_as_float(r[j]));
           }
         }
@@ -282,7 +286,7 @@ const int kMaxDynSmemW = 227 * 1024;
 int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize) {
   if (ksize != 3) return 0;
   if (Y % kBY != 0 || Z % kBZ != 0 || X < 2) return 0;
-  if (!(Cin % kCC == 0 || Cin == 16) || Cout % kCC != 0) return 0;
+  if (!(Cin % kCC == 0 || Cin == 16) || !(Cout % kCC == 0 || Cout == 16)) return 0;
   return 1;
 }
 
@@ -300,7 +304,8 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   p.nz = Z / kBZ;
   p.kcx = (Cin % kCC == 0) ? kCC : 16;
   p.n_ci = Cin / p.kcx;
-  p.n_co = Cout / kCC;
+  p.kcy = (Cout % kCC == 0) ? kCC : 16;
+  p.n_co = Cout / p.kcy;
   p.Ct = Cin_total;
   p.cofs = cin_ofs;
   p.dw = dw_packed;
@@ -317,7 +322,7 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
     p.ctas_per_pair = std::min(p.ctas_per_pair, p.items);
   }
   FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));  // halo + discarded M blocks
-  FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, kCC));
+  FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy));
   p.S3 = 4;
   const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)kDyRing * kDyTile + 1024 + 512;
   static bool attr_set = false;

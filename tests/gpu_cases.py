@@ -83,6 +83,8 @@ WGRAD_MARCH_CASES = [
     ("w128_64_x2", 2, 2, 16, 16, 128, 0, 64, 3),         # 8 pairs, two planes
     ("w_cfg_64cube_32_32", 1, 64, 64, 64, 32, 0, 32, 3),
     ("w16_32_32cube", 2, 32, 32, 32, 16, 0, 32, 3),      # enc0b: Cin = 16 (SWIZZLE_32B X operand, 8 M blocks)
+    ("w16_16_32cube", 2, 32, 32, 32, 16, 0, 16, 3),      # Isensee level 0: Cout = 16 (SWIZZLE_32B dY, N = 48)
+    ("w32_16_16x16x24", 1, 16, 16, 24, 32, 0, 16, 3),    # Isensee u0_up: 32 -> 16
 ]
 
 
