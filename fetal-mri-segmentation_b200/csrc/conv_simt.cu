@@ -327,21 +327,29 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restri
   for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + sub * 8 + i);
   const float bb = __ldg(b);
   const int64_t vpb = blockDim.x / lpv;
-  // every thread of the block runs the same trip count (the shuffles below need full warps)
-  for (int64_t base = (int64_t)blockIdx.x * vpb; base < voxels; base += (int64_t)gridDim.x * vpb) {
-    const int64_t v = base + threadIdx.x / lpv;
-    float acc = 0.f;
-    if (v < voxels) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+  // every thread of the block runs the same trip count (the shuffles below need full warps); four voxels per trip
+  // so that four 16-byte loads are in flight per thread
+  constexpr int U = 4;
+  for (int64_t base = (int64_t)blockIdx.x * vpb * U; base < voxels; base += (int64_t)gridDim.x * vpb * U) {
+    uint4 t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * vpb + threadIdx.x / lpv;
+      t[u] = v < voxels ? __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * vpb + threadIdx.x / lpv;
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t[u]);
+      float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 f = __bfloat1622float2(h[i]);
         acc += f.x * wv[2 * i] + f.y * wv[2 * i + 1];
       }
+      for (int s = lpv >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (sub == 0 && v < voxels) p[v] = apply_sigmoid ? 1.f / (1.f + __expf(-(acc + bb))) : acc + bb;
     }
-    for (int s = lpv >> 1; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (sub == 0 && v < voxels) p[v] = apply_sigmoid ? 1.f / (1.f + __expf(-(acc + bb))) : acc + bb;
   }
 }
 
@@ -364,10 +372,19 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
   }
   float gb = 0.f;
   const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / lpv);
-  for (int64_t v = (int64_t)blockIdx.x * (blockDim.x / lpv) + threadIdx.x / lpv; v < voxels;
-       v += vstride) {
-    const float g = __ldg(dz + v);
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8));
+  for (int64_t v0 = (int64_t)blockIdx.x * (blockDim.x / lpv) + threadIdx.x / lpv; v0 < voxels; v0 += 2 * vstride) {
+    // two voxels per trip: both loads are issued before the first is consumed
+    const int64_t v1 = v0 + vstride;
+    const bool has1 = v1 < voxels;
+    const float gg[2] = {__ldg(dz + v0), has1 ? __ldg(dz + v1) : 0.f};
+    const uint4 tt[2] = {__ldg(reinterpret_cast<const uint4*>(x + v0 * C + sub * 8)),
+                         has1 ? __ldg(reinterpret_cast<const uint4*>(x + v1 * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u)};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+    if (u == 1 && !has1) break;
+    const int64_t v = u == 0 ? v0 : v1;
+    const float g = gg[u];
+    const uint4 t = tt[u];
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
     uint4 o;
     __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
@@ -390,6 +407,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
       }
     }
     *reinterpret_cast<uint4*>(dx + v * C + sub * 8) = o;
+    }
   }
   // block reduction: threads with equal `sub` hold partial sums of the same 8 channels
   __shared__ float sh[kThreads][9];
