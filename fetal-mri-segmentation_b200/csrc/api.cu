@@ -1657,7 +1657,6 @@ extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int ba
 
 extern "C" int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]) {
   FM_CHECK(m && x && t && batch > 0 && out_metrics, FM_EINVAL, "fm_evaluate: bad argument");
-  FM_CHECK(m->kind == 0, FM_EINVAL, "fm_evaluate: use fm_predict + host metrics for this model kind");
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, true));
   const size_t n = (size_t)batch * m->vox(0);

@@ -317,6 +317,11 @@ def test_isensee_dropout_training_only():
     x = rng.standard_normal((2,) + shape).astype(np.float32)
     t = _blob_truth(x)
     assert np.array_equal(a.predict(x), b.predict(x))                 # identity at inference
+    # validation metrics (fit_generator's test_on_batch) come from the inference kernels: equal to host metrics of predict
+    from fetal_net import metrics as hm
+    ev = b.test_on_batch(x, t)
+    p = b.predict(x)
+    assert abs(ev[0] - hm.dice_coefficient_loss(t, p)) <= 1e-5 and abs(ev[2] - hm.vod_coefficient(t, p)) <= 1e-5, ev
     la, lb = a.train_on_batch(x, t)[0], b.train_on_batch(x, t)[0]
     assert np.isfinite(lb) and la != lb                               # masks change the training forward
     ga, gb = a.get_gradients(), b.get_gradients()
