@@ -817,16 +817,16 @@ struct GatherGeom {
 __global__ void gather_patches_kernel(const float* __restrict__ vol, GatherGeom gm, float pad0,
                                       float pad1, const int32_t* __restrict__ idx, int64_t n,
                                       float* __restrict__ out, int out_pitch, int out_cofs, int z_shift) {
-  const int64_t pv = (int64_t)gm.patch[0] * gm.patch[1] * gm.patch[2];
-  const int64_t total = n * pv;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-       g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pi = g / pv;
-    int64_t r = g - pi * pv;
-    const int k = (int)(r % gm.patch[2]);
-    r /= gm.patch[2];
-    const int j = (int)(r % gm.patch[1]);
-    const int i = (int)(r / gm.patch[1]);
+  // one patch per blockIdx.y (strided when there are more patches than grid rows); 32-bit arithmetic inside a patch
+  // (64-bit div/mod by run-time extents costs ~100 instructions each)
+  const uint32_t pv = (uint32_t)gm.patch[0] * (uint32_t)gm.patch[1] * (uint32_t)gm.patch[2];
+  for (int64_t pi = blockIdx.y; pi < n; pi += gridDim.y)
+  for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x; r0 < pv; r0 += gridDim.x * blockDim.x) {
+    uint32_t r = r0;
+    const int k = (int)(r % (uint32_t)gm.patch[2]);
+    r /= (uint32_t)gm.patch[2];
+    const int j = (int)(r % (uint32_t)gm.patch[1]);
+    const int i = (int)(r / (uint32_t)gm.patch[1]);
     // coordinate in the fit-padded array -> halo-padded array -> original volume
     const int c[3] = {idx[pi * 3 + 0] + i, idx[pi * 3 + 1] + j, idx[pi * 3 + 2] + k + z_shift};
     float val;
@@ -849,6 +849,49 @@ __global__ void gather_patches_kernel(const float* __restrict__ vol, GatherGeom 
   }
 }
 
+// four z-consecutive patch voxels per thread (patch[2] % 4 == 0): the index arithmetic and the x / y range tests are
+// shared, the store is one 16-byte write when the destination allows it
+__global__ void __launch_bounds__(kThreads) gather_patches4_kernel(const float* __restrict__ vol, GatherGeom gm, float pad0,
+                                                                   float pad1, const int32_t* __restrict__ idx, int64_t n,
+                                                                   float* __restrict__ out, int out_pitch, int out_cofs,
+                                                                   int z_shift, int vec_store) {
+  const uint32_t k4n = (uint32_t)gm.patch[2] >> 2;
+  const uint32_t pv4 = (uint32_t)gm.patch[0] * (uint32_t)gm.patch[1] * k4n;
+  for (int64_t pi = blockIdx.y; pi < n; pi += gridDim.y) {
+    const int c0b = __ldg(idx + pi * 3 + 0), c1b = __ldg(idx + pi * 3 + 1), c2b = __ldg(idx + pi * 3 + 2) + z_shift;
+    for (uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x; r0 < pv4; r0 += gridDim.x * blockDim.x) {
+      uint32_t r = r0;
+      const int k = (int)(r % k4n) * 4;
+      r /= k4n;
+      const int j = (int)(r % (uint32_t)gm.patch[1]);
+      const int i = (int)(r / (uint32_t)gm.patch[1]);
+      const int h0 = c0b + i - gm.fit[0], h1 = c1b + j - gm.fit[1];
+      const int o0 = h0 - gm.halo[0], o1 = h1 - gm.halo[1];
+      const bool halo_xy = h0 >= 0 && h0 < gm.halo_dims[0] && h1 >= 0 && h1 < gm.halo_dims[1];
+      const bool vol_xy = o0 >= 0 && o0 < gm.vol[0] && o1 >= 0 && o1 < gm.vol[1];
+      const float* row = vol + ((int64_t)o0 * gm.vol[1] + o1) * gm.vol[2];
+      float val[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int h2 = c2b + k + e - gm.fit[2], o2 = h2 - gm.halo[2];
+        if (!(halo_xy && h2 >= 0 && h2 < gm.halo_dims[2]))
+          val[e] = pad1;
+        else if (!(vol_xy && o2 >= 0 && o2 < gm.vol[2]))
+          val[e] = pad0;
+        else
+          val[e] = __ldg(row + o2);
+      }
+      float* dst = out + ((pi * gm.patch[0] + i) * (int64_t)gm.patch[1] + j) * out_pitch + out_cofs + k;
+      if (vec_store) {
+        *reinterpret_cast<float4*>(dst) = make_float4(val[0], val[1], val[2], val[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = val[e];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // overlap-add / average reassembly — fetal_net/prediction.py:188-193,210
 // output-stationary: every output voxel walks the (contiguous) range of patches covering it per
@@ -866,17 +909,17 @@ __global__ void reassemble_kernel(const float* __restrict__ preds, ReasmGeom gm,
                                   int starts_pitch, int cover_pitch, int64_t shard_lo,
                                   int64_t shard_hi, int64_t pred_base, double* __restrict__ out,
                                   int16_t* __restrict__ count, int divide) {
-  const int64_t nvox = (int64_t)gm.out[0] * gm.out[1] * gm.out[2];
-  const int64_t total = nvox * gm.channels;
+  // blockIdx.y walks x; 32-bit arithmetic inside one (y, z, channel) plane
   const int64_t pvox = (int64_t)gm.pred[0] * gm.pred[1] * gm.pred[2];
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-       g += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(g % gm.channels);
-    int64_t v = g / gm.channels;
-    const int z = (int)(v % gm.out[2]);
-    int64_t r = v / gm.out[2];
-    const int y = (int)(r % gm.out[1]);
-    const int x = (int)(r / gm.out[1]);
+  const uint32_t plane = (uint32_t)gm.out[1] * (uint32_t)gm.out[2] * (uint32_t)gm.channels;
+  for (int x = blockIdx.y; x < gm.out[0]; x += gridDim.y)
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < plane; q += gridDim.x * blockDim.x) {
+    const int ch = (int)(q % (uint32_t)gm.channels);
+    uint32_t r = q / (uint32_t)gm.channels;
+    const int z = (int)(r % (uint32_t)gm.out[2]);
+    const int y = (int)(r / (uint32_t)gm.out[2]);
+    const int64_t v = (int64_t)x * gm.out[1] * gm.out[2] + r;
+    const int64_t g = (int64_t)x * plane + q;
     const int xlo = cover[(0 * cover_pitch + x) * 2], xhi = cover[(0 * cover_pitch + x) * 2 + 1];
     const int ylo = cover[(1 * cover_pitch + y) * 2], yhi = cover[(1 * cover_pitch + y) * 2 + 1];
     const int zlo = cover[(2 * cover_pitch + z) * 2], zhi = cover[(2 * cover_pitch + z) * 2 + 1];
@@ -901,6 +944,69 @@ __global__ void reassemble_kernel(const float* __restrict__ preds, ReasmGeom gm,
       out[g] = acc / (double)cnt;
     else
       out[g] += acc;
+  }
+}
+
+// single-channel maps with out[2] % 4 == 0: four z-consecutive outputs per thread share the x / y covering sets and
+// the index arithmetic; every output still adds its patches in ascending patch order (ix, iy, iz) in fp64 and
+// divides by its analytic count, so the result is bit-identical to reassemble_kernel
+__global__ void __launch_bounds__(kThreads) reassemble4_kernel(const float* __restrict__ preds, ReasmGeom gm,
+                                                               const int32_t* __restrict__ starts,
+                                                               const int32_t* __restrict__ cover, int starts_pitch,
+                                                               int cover_pitch, int64_t shard_lo, int64_t shard_hi,
+                                                               int64_t pred_base, double* __restrict__ out,
+                                                               int16_t* __restrict__ count, int divide) {
+  const int64_t pvox = (int64_t)gm.pred[0] * gm.pred[1] * gm.pred[2];
+  const uint32_t z4n = (uint32_t)gm.out[2] >> 2;
+  const uint32_t plane4 = (uint32_t)gm.out[1] * z4n;
+  for (int x = blockIdx.y; x < gm.out[0]; x += gridDim.y) {
+    const int2 cx = __ldg(reinterpret_cast<const int2*>(cover + (0 * cover_pitch + x) * 2));
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < plane4; q += gridDim.x * blockDim.x) {
+      const int z = (int)(q % z4n) * 4;
+      const int y = (int)(q / z4n);
+      const int2 cy = __ldg(reinterpret_cast<const int2*>(cover + (1 * cover_pitch + y) * 2));
+      int2 cz[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cz[e] = __ldg(reinterpret_cast<const int2*>(cover + (2 * cover_pitch + z + e) * 2));
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int ix = cx.x; ix < cx.y; ++ix) {
+        const int px = x - __ldg(starts + 0 * starts_pitch + ix);
+        for (int iy = cy.x; iy < cy.y; ++iy) {
+          const int py = y - __ldg(starts + 1 * starts_pitch + iy);
+          const int64_t prow = ((int64_t)px * gm.pred[1] + py) * gm.pred[2];
+          const int64_t pxy = ((int64_t)ix * gm.np[1] + iy) * gm.np[2];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            for (int iz = cz[e].x; iz < cz[e].y; ++iz) {
+              const int64_t patch = pxy + iz;
+              if (patch < shard_lo || patch >= shard_hi) continue;
+              const int pz = z + e - __ldg(starts + 2 * starts_pitch + iz);
+              acc[e] += (double)__ldg(preds + (patch - pred_base) * pvox + prow + pz);
+            }
+        }
+      }
+      const int64_t v = ((int64_t)x * gm.out[1] + y) * gm.out[2] + z;
+      const int nxy = (cx.y - cx.x) * (cy.y - cy.x);
+      double res[4];
+      short cn[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int cnt = nxy * (cz[e].y - cz[e].x);
+        cn[e] = (short)cnt;
+        if (!divide) {
+          res[e] = out[v + e] + acc[e];
+        } else if ((cnt & (cnt - 1)) == 0) {
+          // power-of-two count (the usual case: 1 or 2 covering patches per axis): the quotient is the exact product
+          // with 2^-k, bit-identical to the IEEE division and ~40 instructions cheaper
+          res[e] = acc[e] * __longlong_as_double((long long)(1023 - (31 - __clz(cnt))) << 52);
+        } else {
+          res[e] = acc[e] / (double)cnt;
+        }
+      }
+      reinterpret_cast<double2*>(out + v)[0] = make_double2(res[0], res[1]);
+      reinterpret_cast<double2*>(out + v)[1] = make_double2(res[2], res[3]);
+      if (count != nullptr) *reinterpret_cast<short4*>(count + v) = make_short4(cn[0], cn[1], cn[2], cn[3]);
+    }
   }
 }
 
@@ -1043,9 +1149,18 @@ int k_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
   }
   const int64_t total = n * (int64_t)patch[0] * patch[1] * patch[2];
   ProfScope prof(ctx, "gather_patches", 0.0, (double)total * 8.0);
-  gather_patches_kernel<<<grid_for(total, 148 * 32), kThreads, 0, ctx->stream>>>(vol, gm, pad0, pad1,
-                                                                                idx_dev, n, out, out_pitch, out_cofs,
-                                                                                z_shift);
+  const int64_t pv = (int64_t)patch[0] * patch[1] * patch[2];
+  FM_CHECK(pv < ((int64_t)1 << 31), FM_EINVAL, "gather_patches: patch of %lld voxels", (long long)pv);
+  if (patch[2] % 4 == 0) {
+    const int vec = out_pitch % 4 == 0 && out_cofs % 4 == 0 && ((uintptr_t)out & 15) == 0;
+    const dim3 grid((unsigned)grid_for(pv / 4, 1024), (unsigned)std::min<int64_t>(n, 32768));
+    gather_patches4_kernel<<<grid, kThreads, 0, ctx->stream>>>(vol, gm, pad0, pad1, idx_dev, n, out, out_pitch, out_cofs,
+                                                              z_shift, vec);
+  } else {
+    const dim3 grid((unsigned)grid_for(pv, 1024), (unsigned)std::min<int64_t>(n, 32768));
+    gather_patches_kernel<<<grid, kThreads, 0, ctx->stream>>>(vol, gm, pad0, pad1, idx_dev, n, out, out_pitch, out_cofs,
+                                                             z_shift);
+  }
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -1115,9 +1230,18 @@ int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64
   gm.channels = channels;
   const int64_t total = (int64_t)out_dims[0] * out_dims[1] * out_dims[2] * channels;
   ProfScope prof(ctx, "reassemble", 0.0, (double)(shard_hi - shard_lo) * pred_shape[0] * pred_shape[1] * pred_shape[2] * channels * 4.0 + (double)total * 8.0);
-  reassemble_kernel<<<grid_for(total, 148 * 16), kThreads, 0, ctx->stream>>>(
-      preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo, shard_hi, pred_base, out_dev, count_dev,
-      divide);
+  const int64_t plane = (int64_t)out_dims[1] * out_dims[2] * channels;
+  FM_CHECK(plane < ((int64_t)1 << 31), FM_EINVAL, "reassemble: plane of %lld elements", (long long)plane);
+  if (channels == 1 && out_dims[2] % 4 == 0 && ((uintptr_t)out_dev & 15) == 0 && ((uintptr_t)count_dev & 7) == 0) {
+    const dim3 rgrid((unsigned)grid_for(plane / 4, 256), (unsigned)std::min<int>(out_dims[0], 32768));
+    reassemble4_kernel<<<rgrid, kThreads, 0, ctx->stream>>>(preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo,
+                                                           shard_hi, pred_base, out_dev, count_dev, divide);
+  } else {
+    const dim3 rgrid((unsigned)grid_for(plane, 256), (unsigned)std::min<int>(out_dims[0], 32768));
+    reassemble_kernel<<<rgrid, kThreads, 0, ctx->stream>>>(
+        preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo, shard_hi, pred_base, out_dev, count_dev,
+        divide);
+  }
   FM_LAUNCH_OK(ctx);
   FM_CUDA(cudaFreeAsync(d_starts, ctx->stream));
   FM_CUDA(cudaFreeAsync(d_cover, ctx->stream));
