@@ -248,6 +248,13 @@ struct fm_model {
   std::vector<DevBuf<bf16>> gEncA, gEncB, gPool, gUp, gSkip, gDecA, gDecB;  // gradients
   double* sums = nullptr;  // 8 doubles (device)
   double sums_host[8];
+  // fm_train_step pipelining (pinned host inputs): two device staging buffers filled by the copy stream while the
+  // previous step is still in its backward pass; the call returns once the Dice statistics of ITS forward pass are
+  // on the host, the rest of the step (backward, Adam, repack) keeps running and is ordered before any later call
+  DevBuf<float> stage_x[2], stage_t[2];
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr}, sums_ready = nullptr;
+  double* sums_pin = nullptr;
+  int stage_idx = 0;
 
   // sliding-window workspace (grow-only): volume, corners, per-patch probabilities, fp64 sums, counts
   DevBuf<float> pw_vol, pw_pred;
@@ -501,6 +508,14 @@ extern "C" int fm_model_destroy(fm_model* m) {
                   &m->gPool, &m->gUp, &m->gSkip, &m->gDecA, &m->gDecB})
     for (auto& b : *v) b.release();
   for (auto& e : m->layer_done) cudaEventDestroy(e);
+  for (int b = 0; b < 2; ++b) {
+    m->stage_x[b].release();
+    m->stage_t[b].release();
+    if (m->stage_ready[b]) cudaEventDestroy(m->stage_ready[b]);
+    if (m->stage_free[b]) cudaEventDestroy(m->stage_free[b]);
+  }
+  if (m->sums_ready) cudaEventDestroy(m->sums_ready);
+  if (m->sums_pin) cudaFreeHost(m->sums_pin);
   if (m->ev_tmp) cudaEventDestroy(m->ev_tmp);
   delete m;
   return FM_OK;
@@ -1648,11 +1663,62 @@ extern "C" int fm_train_step_device(fm_model* m, uint64_t x_dev, uint64_t t_dev,
   return fm_train_apply(m, lr, 0, out_metrics);
 }
 
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
                              float out_metrics[4]) {
-  FM_TRY(fm_train_forward(m, x, t, batch));
+  FM_CHECK(m && x && t && batch > 0, FM_EINVAL, "fm_train_step: bad argument");
+  static const bool no_pipe = [] {
+    const char* e = getenv("FETAL_B200_NO_PIPELINE");
+    return e && e[0] == '1';
+  }();
+  if (no_pipe || !out_metrics || !is_pinned_host(x) || !is_pinned_host(t)) {
+    // pageable inputs: the runtime stages them synchronously anyway
+    FM_TRY(fm_train_forward(m, x, t, batch));
+    FM_TRY(fm_train_backward(m));
+    return fm_train_apply(m, lr, 0, out_metrics);
+  }
+  fm_ctx* ctx = m->ctx;
+  FM_CUDA(cudaSetDevice(ctx->device));
+  FM_TRY(ensure_capacity(m, batch, true));
+  if (!m->sums_ready) {
+    for (int b = 0; b < 2; ++b) {
+      FM_CUDA(cudaEventCreateWithFlags(&m->stage_ready[b], cudaEventDisableTiming));
+      FM_CUDA(cudaEventCreateWithFlags(&m->stage_free[b], cudaEventDisableTiming));
+    }
+    FM_CUDA(cudaEventCreateWithFlags(&m->sums_ready, cudaEventDisableTiming));
+    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, 8 * sizeof(double)));
+  }
+  const size_t n = (size_t)batch * m->vox(0), nx = n * m->cin_real;
+  const int b = (m->stage_idx ^= 1);
+  FM_TRY(m->stage_x[b].ensure(nx));
+  FM_TRY(m->stage_t[b].ensure(n));
+  // copy stream: this step's inputs into staging buffer b as soon as the step that last used it has consumed it
+  // (two steps ago) - i.e. concurrently with the previous step's backward pass
+  FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, m->stage_free[b], 0));
+  FM_CUDA(cudaMemcpyAsync(m->stage_x[b].p, x, nx * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+  FM_CUDA(cudaMemcpyAsync(m->stage_t[b].p, t, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+  FM_CUDA(cudaEventRecord(m->stage_ready[b], ctx->copy_stream));
+  // compute stream: staging -> working buffers (device copy), forward, statistics to the host, backward, update
+  FM_CUDA(cudaStreamWaitEvent(ctx->stream, m->stage_ready[b], 0));
+  FM_CUDA(cudaMemcpyAsync(m->x_in.p, m->stage_x[b].p, nx * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(m->t_in.p, m->stage_t[b].p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  FM_CUDA(cudaEventRecord(m->stage_free[b], ctx->stream));
+  FM_TRY(train_forward_dev(m, batch));
+  FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaEventRecord(m->sums_ready, ctx->stream));
   FM_TRY(fm_train_backward(m));
-  return fm_train_apply(m, lr, 0, out_metrics);
+  FM_TRY(fm_train_apply(m, lr, 0, nullptr));
+  FM_CUDA(cudaEventSynchronize(m->sums_ready));  // the inputs were consumed long before: x / t may be reused
+  metrics_from_sums(m->sums_pin, out_metrics);
+  return FM_OK;
 }
 
 extern "C" int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]) {

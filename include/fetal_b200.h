@@ -181,6 +181,11 @@ int fm_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
  * forward, soft-Dice loss (fetal_net/metrics.py:11-15,31-32), backward, Keras-2 Adam.
  * x [B,Cin,X,Y,Z], t [B,n_labels,X,Y,Z] float32 host. out_metrics[4] = loss, binary_accuracy,
  * vod_coefficient, dice_coefficient (the Keras metrics of unet3d/unet.py:81-83). */
+/* Pipelining: when x and t are pinned (page-locked) host buffers, the upload goes through two device staging buffers
+ * on a copy stream and the call returns as soon as the Dice statistics of THIS step's forward pass are on the host;
+ * backward, Adam and the weight repack keep running and are stream-ordered before every later call on the model
+ * (predict, get_weights, the next step), whose upload then overlaps them. x / t may be reused when the call returns.
+ * Pageable buffers (or FETAL_B200_NO_PIPELINE=1) take the fully synchronous route. */
 int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
                   float out_metrics[4]);
 

@@ -183,6 +183,36 @@ def test_trained_network_mask_dice_vs_fp32_oracle():
     assert md >= 0.999, (md, float(np.abs(p - ref).max()))
 
 
+def test_pipelined_train_step_with_pinned_inputs(setup):
+    """fm_train_step with page-locked inputs returns after the forward statistics are on the host and lets the rest of
+    the step overlap the next upload: same losses / weights as the synchronous (pageable) route, and later calls
+    (get_weights, predict) see the finished update."""
+    from fetal_net.model import unet_model_3d
+    _, w = setup
+    rng = np.random.default_rng(21)
+    xs = [rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32) for _ in range(4)]
+    ts = [blob_target(x.shape, rng) for x in xs]
+    losses, weights = [], []
+    for pinned in (False, True):
+        # small learning rate: the training kernels are not bit-reproducible, so two runs drift apart at a rate set
+        # by the step size; at 1e-4 four steps stay within a few 1e-5 of each other
+        model = unet_model_3d(input_shape=(1, 32, 32, 32), n_base_filters=16, depth=4, initial_learning_rate=1e-4)
+        model.set_named_weights(w)
+        ls = []
+        for x, t in zip(xs, ts):
+            if pinned:
+                xp, tp = torch.as_tensor(x).pin_memory(), torch.as_tensor(t).pin_memory()
+                ls.append(model.train_on_batch(xp.numpy(), tp.numpy())[0])
+                xp.zero_()                                            # inputs are free for reuse on return
+            else:
+                ls.append(model.train_on_batch(x, t)[0])
+        losses.append(ls)
+        weights.append(model.get_weights())
+    assert np.allclose(losses[0], losses[1], atol=5e-4), losses
+    for a, b in zip(weights[0], weights[1]):
+        assert np.abs(a - b).max() <= 1.5e-3, float(np.abs(a - b).max())     # <= 4 Adam steps of 1e-4, either sign
+
+
 def test_evaluate_matches_host_metrics(setup):
     import fetal_net.metrics as fm
     model, _ = setup
