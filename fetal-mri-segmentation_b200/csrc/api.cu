@@ -255,6 +255,7 @@ struct fm_model {
   cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr}, sums_ready = nullptr;
   double* sums_pin = nullptr;
   int stage_idx = 0;
+  bool metrics_pending = false;
 
   // sliding-window workspace (grow-only): volume, corners, per-patch probabilities, fp64 sums, counts
   DevBuf<float> pw_vol, pw_pred;
@@ -1578,13 +1579,92 @@ static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullp
   return FM_OK;
 }
 
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static bool pipeline_enabled() {
+  static const bool off = [] {
+    const char* e = getenv("FETAL_B200_NO_PIPELINE");
+    return e && e[0] == '1';
+  }();
+  return !off;
+}
+
+// pinned host inputs -> working buffers through one of two device staging buffers: the H2D copies run on the copy
+// stream as soon as the step that last used that staging buffer has consumed it (two steps ago), i.e. concurrently
+// with whatever the compute stream is still doing for the previous step; the compute stream then takes a device copy
+static int stage_inputs(fm_model* m, const float* x, const float* t, int batch) {
+  fm_ctx* ctx = m->ctx;
+  if (!m->sums_ready) {
+    for (int b = 0; b < 2; ++b) {
+      FM_CUDA(cudaEventCreateWithFlags(&m->stage_ready[b], cudaEventDisableTiming));
+      FM_CUDA(cudaEventCreateWithFlags(&m->stage_free[b], cudaEventDisableTiming));
+    }
+    FM_CUDA(cudaEventCreateWithFlags(&m->sums_ready, cudaEventDisableTiming));
+    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, 8 * sizeof(double)));
+  }
+  const size_t n = (size_t)batch * m->vox(0), nx = n * m->cin_real;
+  const int b = (m->stage_idx ^= 1);
+  FM_TRY(m->stage_x[b].ensure(nx));
+  FM_TRY(m->stage_t[b].ensure(n));
+  FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, m->stage_free[b], 0));
+  FM_CUDA(cudaMemcpyAsync(m->stage_x[b].p, x, nx * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+  FM_CUDA(cudaMemcpyAsync(m->stage_t[b].p, t, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+  FM_CUDA(cudaEventRecord(m->stage_ready[b], ctx->copy_stream));
+  FM_CUDA(cudaStreamWaitEvent(ctx->stream, m->stage_ready[b], 0));
+  FM_CUDA(cudaMemcpyAsync(m->x_in.p, m->stage_x[b].p, nx * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(m->t_in.p, m->stage_t[b].p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  FM_CUDA(cudaEventRecord(m->stage_free[b], ctx->stream));
+  return FM_OK;
+}
+
 extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int batch) {
   FM_CHECK(m && x && t && batch > 0, FM_EINVAL, "fm_train_forward: bad argument");
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, true));
   const size_t n = (size_t)batch * m->vox(0);
+  if (pipeline_enabled() && is_pinned_host(x) && is_pinned_host(t)) {
+    FM_TRY(stage_inputs(m, x, t, batch));
+    return train_forward_dev(m, batch);
+  }
   FM_TRY(upload(m, x, m->x_in.p, n * m->cin_real));
   return train_forward_dev(m, batch, t);
+}
+
+// Data-parallel early return: after the caller's all-reduce of the statistics (queued on the compute stream),
+// fm_train_metrics_async queues their copy to pinned host memory; fm_train_metrics_wait blocks only until that copy
+// has landed - the rest of the step keeps running and is ordered before every later call on the model.
+extern "C" int fm_train_metrics_async(fm_model* m) {
+  FM_CHECK(m && m->fwd_valid, FM_ESTATE, "fm_train_metrics_async needs a preceding fm_train_forward");
+  fm_ctx* ctx = m->ctx;
+  FM_CUDA(cudaSetDevice(ctx->device));
+  if (!m->sums_ready) {
+    for (int b = 0; b < 2; ++b) {
+      FM_CUDA(cudaEventCreateWithFlags(&m->stage_ready[b], cudaEventDisableTiming));
+      FM_CUDA(cudaEventCreateWithFlags(&m->stage_free[b], cudaEventDisableTiming));
+    }
+    FM_CUDA(cudaEventCreateWithFlags(&m->sums_ready, cudaEventDisableTiming));
+    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, 8 * sizeof(double)));
+  }
+  FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaEventRecord(m->sums_ready, ctx->stream));
+  m->metrics_pending = true;
+  return FM_OK;
+}
+extern "C" int fm_train_metrics_wait(fm_model* m, float out_metrics[4]) {
+  FM_CHECK(m && out_metrics, FM_EINVAL, "fm_train_metrics_wait: bad argument");
+  FM_CHECK(m->metrics_pending, FM_ESTATE, "fm_train_metrics_wait without fm_train_metrics_async");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  FM_CUDA(cudaEventSynchronize(m->sums_ready));
+  metrics_from_sums(m->sums_pin, out_metrics);
+  m->metrics_pending = false;
+  return FM_OK;
 }
 
 extern "C" int fm_train_backward(fm_model* m) {
@@ -1663,23 +1743,10 @@ extern "C" int fm_train_step_device(fm_model* m, uint64_t x_dev, uint64_t t_dev,
   return fm_train_apply(m, lr, 0, out_metrics);
 }
 
-static bool is_pinned_host(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeHost;
-}
-
 extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
                              float out_metrics[4]) {
   FM_CHECK(m && x && t && batch > 0, FM_EINVAL, "fm_train_step: bad argument");
-  static const bool no_pipe = [] {
-    const char* e = getenv("FETAL_B200_NO_PIPELINE");
-    return e && e[0] == '1';
-  }();
-  if (no_pipe || !out_metrics || !is_pinned_host(x) || !is_pinned_host(t)) {
+  if (!pipeline_enabled() || !out_metrics || !is_pinned_host(x) || !is_pinned_host(t)) {
     // pageable inputs: the runtime stages them synchronously anyway
     FM_TRY(fm_train_forward(m, x, t, batch));
     FM_TRY(fm_train_backward(m));
@@ -1688,29 +1755,7 @@ extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int ba
   fm_ctx* ctx = m->ctx;
   FM_CUDA(cudaSetDevice(ctx->device));
   FM_TRY(ensure_capacity(m, batch, true));
-  if (!m->sums_ready) {
-    for (int b = 0; b < 2; ++b) {
-      FM_CUDA(cudaEventCreateWithFlags(&m->stage_ready[b], cudaEventDisableTiming));
-      FM_CUDA(cudaEventCreateWithFlags(&m->stage_free[b], cudaEventDisableTiming));
-    }
-    FM_CUDA(cudaEventCreateWithFlags(&m->sums_ready, cudaEventDisableTiming));
-    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, 8 * sizeof(double)));
-  }
-  const size_t n = (size_t)batch * m->vox(0), nx = n * m->cin_real;
-  const int b = (m->stage_idx ^= 1);
-  FM_TRY(m->stage_x[b].ensure(nx));
-  FM_TRY(m->stage_t[b].ensure(n));
-  // copy stream: this step's inputs into staging buffer b as soon as the step that last used it has consumed it
-  // (two steps ago) - i.e. concurrently with the previous step's backward pass
-  FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, m->stage_free[b], 0));
-  FM_CUDA(cudaMemcpyAsync(m->stage_x[b].p, x, nx * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-  FM_CUDA(cudaMemcpyAsync(m->stage_t[b].p, t, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
-  FM_CUDA(cudaEventRecord(m->stage_ready[b], ctx->copy_stream));
-  // compute stream: staging -> working buffers (device copy), forward, statistics to the host, backward, update
-  FM_CUDA(cudaStreamWaitEvent(ctx->stream, m->stage_ready[b], 0));
-  FM_CUDA(cudaMemcpyAsync(m->x_in.p, m->stage_x[b].p, nx * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  FM_CUDA(cudaMemcpyAsync(m->t_in.p, m->stage_t[b].p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  FM_CUDA(cudaEventRecord(m->stage_free[b], ctx->stream));
+  FM_TRY(stage_inputs(m, x, t, batch));
   FM_TRY(train_forward_dev(m, batch));
   FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaEventRecord(m->sums_ready, ctx->stream));

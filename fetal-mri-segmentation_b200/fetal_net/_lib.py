@@ -65,6 +65,8 @@ SIGNATURES = {
     "fm_model_get_grads": (c_int, [c_vp, c_int, c_fp, c_fp]),
     "fm_model_reset_optimizer": (c_int, [c_vp]),
     "fm_model_set_dropout": (c_int, [c_vp, ctypes.c_float, ctypes.c_uint64]),
+    "fm_train_metrics_async": (c_int, [c_vp]),
+    "fm_train_metrics_wait": (c_int, [c_vp, c_fp]),
     "fm_predict": (c_int, [c_vp, c_fp, c_int, c_fp]),
     "fm_patch_plan": (c_int, [c_i32p, c_i32p, c_i32p, c_d, c_i32p, c_i64, c_i64p]),
     "fm_patchwise_predict": (c_int, [c_vp, c_fp, c_i32p, c_i32p, c_i32p, c_dp, c_i32p, c_i64, c_int,

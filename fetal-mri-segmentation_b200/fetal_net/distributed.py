@@ -71,6 +71,7 @@ class DataParallelTrainer:
         _lib.check(lib.fm_train_forward(h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0])))
         with torch.cuda.stream(self.compute_stream):
             dist.all_reduce(self.sums)                                   # 8 doubles: global Dice statistics
+        _lib.check(lib.fm_train_metrics_async(h))                        # global statistics -> pinned host, async
         _lib.check(lib.fm_train_backward(h))
         # buckets complete in order 0,1,2,... (backward runs in reverse layer order)
         with torch.cuda.stream(self.comm_stream if self.overlap else self.compute_stream):
@@ -80,7 +81,10 @@ class DataParallelTrainer:
                 dist.all_reduce(self.grads[off:off + cnt])               # SUM: one global loss scalar
         m = np.zeros(4, np.float32)
         _lib.check(lib.fm_train_apply(h, float(self.model.optimizer.lr),
-                                      self.comm_stream.cuda_stream if self.overlap else 0, _lib.fptr(m)))
+                                      self.comm_stream.cuda_stream if self.overlap else 0, None))
+        # returns once the statistics are on the host; backward / all-reduce / Adam keep running, ordered before any
+        # later call on the model, and the next step's upload (pinned inputs) overlaps them
+        _lib.check(lib.fm_train_metrics_wait(h, _lib.fptr(m)))
         return [float(v) for v in m[:len(self.model.metrics_names)]]
 
 

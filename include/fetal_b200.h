@@ -200,6 +200,15 @@ int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float 
 int fm_train_forward(fm_model* m, const float* x, const float* t, int batch);
 int fm_train_backward(fm_model* m);
 int fm_train_apply(fm_model* m, float lr, uint64_t after_stream, float out_metrics[4]);
+/* Optional early return for the split step (data-parallel trainers): call fm_train_metrics_async after the
+ * all-reduce of the statistics has been queued on the compute stream (it queues their copy to pinned host memory),
+ * run fm_train_backward / the gradient all-reduces / fm_train_apply(..., NULL), and finish with
+ * fm_train_metrics_wait, which blocks only until that copy has landed: backward, Adam and the repack keep running
+ * and are stream-ordered before every later call on the model, so the next step's upload (pinned inputs) overlaps
+ * them. Replaces nothing in the reference (Keras' train_on_batch is synchronous); same numbers as the metrics
+ * argument of fm_train_apply. */
+int fm_train_metrics_async(fm_model* m);
+int fm_train_metrics_wait(fm_model* m, float out_metrics[4]);
 int fm_model_loss_sums(fm_model* m, uint64_t* dev_ptr);               /* 8 x float64, device */
 int fm_model_grad_buffer(fm_model* m, uint64_t* dev_ptr, int64_t* n); /* n x float32, device */
 int fm_model_num_buckets(fm_model* m);
