@@ -18,14 +18,16 @@ from .model.unet3d import Model
 
 
 def get_set_of_patch_indices_full(start, stop, step):
-    # prediction.py:88-95
-    indices = []
-    for start_i, stop_i, step_i in zip(start, stop, step):
-        indices_i = list(range(start_i, stop_i + 1, step_i))
-        if stop_i % step_i > 0:
-            indices_i += [stop_i]
-        indices += [indices_i]
-    return np.array(list(itertools.product(*indices)))
+    """Corner grid of prediction.py:88-95: per axis start, start+step, ... <= stop, plus `stop` itself when it is not a
+    multiple of the step (the reference tests `stop % step`, not `(stop - start) % step`); Cartesian product with the
+    first axis slowest. Host twin of fm_patch_plan."""
+    per_axis = []
+    for lo, hi, stride in zip(start, stop, step):
+        corners = list(range(lo, hi + 1, stride))
+        if hi % stride > 0:
+            corners.append(hi)
+        per_axis.append(corners)
+    return np.array(list(itertools.product(*per_axis)))
 
 
 def patch_plan(padded_shape, patch_shape, prediction_shape, overlap_factor):

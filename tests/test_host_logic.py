@@ -195,3 +195,16 @@ def test_rescale_intensity_restatement():
     out = rescale_intensity_to_image_range(d, -1.0, 1.0)
     assert out.dtype == np.float32
     np.testing.assert_allclose(out, [-2.0, -2.0, 1.0, 4.0, 4.0])
+
+
+def test_host_patch_slicing_matches_reference_goldens(golden):
+    """fetal_net.utils.patches.get_patch_from_3d_data incl. the out-of-bounds edge completion (patches.py:57-91)."""
+    from fetal_net.utils.patches import fix_out_of_bound_patch_attempt, get_patch_from_3d_data
+    data = golden["patch/data"]
+    shape = tuple(int(v) for v in golden["patch/shape"])
+    for i, c in enumerate(golden["patch/corners"]):
+        got = get_patch_from_3d_data(data, shape, c)
+        assert np.array_equal(got, golden["patch/out%d" % i]), (i, c)
+        padded, fixed = fix_out_of_bound_patch_attempt(data, np.asarray(shape), np.asarray(c))
+        sl = tuple(slice(int(f), int(f) + s) for f, s in zip(fixed, shape))
+        assert np.array_equal(padded[(Ellipsis,) + sl], golden["patch/out%d" % i])
