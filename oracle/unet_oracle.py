@@ -233,6 +233,37 @@ def _instance_norm(t, gamma, beta, eps=1e-3):
     return (t - mean) / std * gamma.reshape(shape) + beta.reshape(shape)
 
 
+def instance_norm_lrelu_backward_closed_form(x, gy, gamma, beta, eps=1e-3, slope=0.3, chan_scale=None):
+    """Closed form the CUDA kernels implement (csrc/bandwidth.cu instnorm_bwd_*): gradient of
+    y = LeakyReLU(gamma * (x - mean) / (sqrt(var) + eps) + beta) [* chan_scale] w.r.t. x, gamma, beta, for
+    x, gy of shape [N, C, ...] (statistics per sample and channel over the trailing axes). With s = sigma + eps,
+    xh = (x - mean) / s and g = gy * chan_scale * (z > 0 ? 1 : slope):
+        dgamma = sum g * xh,  dbeta = sum g,
+        dx = (gamma / s) * (g - mean(g) - xh * (s / sigma) * mean(g * xh))
+    (eps sits on the standard deviation, so the variance term carries s / sigma instead of 1).
+    float64 numpy; checked against autograd in tests/test_oracle_pinning.py."""
+    x = np.asarray(x, np.float64)
+    gy = np.asarray(gy, np.float64)
+    axes = tuple(range(2, x.ndim))
+    bshape = (1, -1) + (1,) * (x.ndim - 2)
+    gam = np.asarray(gamma, np.float64).reshape(bshape)
+    bet = np.asarray(beta, np.float64).reshape(bshape)
+    mean = x.mean(axis=axes, keepdims=True)
+    sigma = np.sqrt(x.var(axis=axes, keepdims=True))
+    s = sigma + eps
+    xh = (x - mean) / s
+    z = gam * xh + bet
+    g = gy * np.where(z > 0, 1.0, slope)
+    if chan_scale is not None:
+        g = g * np.asarray(chan_scale, np.float64).reshape(x.shape[:2] + (1,) * (x.ndim - 2))
+    dgamma = (g * xh).sum(axis=(0,) + axes)
+    dbeta = g.sum(axis=(0,) + axes)
+    m1 = g.mean(axis=axes, keepdims=True)
+    m2 = (g * xh).mean(axis=axes, keepdims=True)
+    dx = gam / s * (g - m1 - xh * (s / sigma) * m2)
+    return dx, dgamma, dbeta
+
+
 def isensee3d_forward(x, w, depth=5, n_segmentation_levels=1, return_logits=False):
     dt = x.dtype
 

@@ -148,3 +148,28 @@ def test_param_counts_match_survey():
     assert n(uo.unet3d_layers(4, 32)) == 16315585
     assert n(uo.isensee3d_layers(5, 16, 3)) == 8263619
     assert sum(k ** 2 * ci * co + co for _, ci, co, k in uo.unet2d_layers(4, 32, 6)) == 5441569
+
+
+def test_instance_norm_backward_closed_form_matches_autograd():
+    """The closed form behind the instnorm_bwd_* kernels (eps on the STD, LeakyReLU slope and dropout scale folded in)
+    equals autograd through the oracle's own forward restatement (keras_contrib InstanceNormalization semantics)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import unet_oracle as uo
+    rng = np.random.default_rng(5)
+    N, C = 2, 8
+    x = rng.standard_normal((N, C, 6, 5, 4))
+    x[:, 3] *= 1e-3                                   # a low-variance channel: eps / sigma is not negligible there
+    gy = rng.standard_normal(x.shape)
+    gamma = 1.0 + 0.3 * rng.standard_normal(C)
+    beta = 0.2 * rng.standard_normal(C)
+    cs = (rng.random((N, C)) > 0.3) / 0.7
+    xt = torch.tensor(x, requires_grad=True)
+    gt = torch.tensor(gamma, requires_grad=True)
+    bt = torch.tensor(beta, requires_grad=True)
+    y = F.leaky_relu(uo._instance_norm(xt, gt, bt), 0.3) * torch.tensor(cs).reshape(N, C, 1, 1, 1)
+    y.backward(torch.tensor(gy))
+    dx, dg, db = uo.instance_norm_lrelu_backward_closed_form(x, gy, gamma, beta, chan_scale=cs)
+    np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-9, atol=1e-10)
