@@ -264,6 +264,28 @@ def instance_norm_lrelu_backward_closed_form(x, gy, gamma, beta, eps=1e-3, slope
     return dx, dgamma, dbeta
 
 
+def upsampled_conv_parity_weights(w):
+    """Groundwork for convolving the nearest-upsampled decoder source at COARSE resolution (headroom).
+    For x_up = UpSampling3D(2)(x) and a 3x3x3 'same' conv with torch-layout weights w [Cout, Cin, 3, 3, 3], the output
+    voxel at fine position 2i + p (parity p in {0,1} per axis) only sees coarse voxels i + o with
+        p = 0:  tap 0 -> o = -1,  taps 1, 2 -> o = 0          p = 1:  taps 0, 1 -> o = 0,  tap 2 -> o = +1
+    so per parity class the 27 taps collapse into 2x2x2 summed taps. Returns wc [2,2,2][Cout, Cin, 3, 3, 3] indexed by
+    parity, laid out over coarse offsets o + 1 in {0,1,2} per axis (zeros where a class does not reach).
+    y[..., 2i+p] == conv3d(x, wc[p], padding=1)[..., i] exactly (zero padding agrees at both resolutions)."""
+    w = np.asarray(w)
+    tap_to_offset = {0: (0, 1, 1), 1: (1, 1, 2)}          # parity -> coarse offset index (o + 1) of taps 0, 1, 2
+    wc = np.zeros((2, 2, 2) + w.shape, w.dtype)
+    for px in range(2):
+        for py in range(2):
+            for pz in range(2):
+                for tx in range(3):
+                    for ty in range(3):
+                        for tz in range(3):
+                            ox, oy, oz = tap_to_offset[px][tx], tap_to_offset[py][ty], tap_to_offset[pz][tz]
+                            wc[px, py, pz, :, :, ox, oy, oz] += w[:, :, tx, ty, tz]
+    return wc
+
+
 def isensee3d_forward(x, w, depth=5, n_segmentation_levels=1, return_logits=False):
     dt = x.dtype
 

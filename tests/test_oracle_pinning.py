@@ -173,3 +173,51 @@ def test_instance_norm_backward_closed_form_matches_autograd():
     np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-9, atol=1e-10)
+
+
+def test_strided_conv_backward_as_zero_inserted_stride1_backward():
+    """The identity behind the Isensee stride-2 backward (csrc/api.cu backward_isensee, k_zero_insert): for
+    y = conv3d(pad(x, after=1), w, stride=2) (TF 'SAME', even extents, k = 3), placing dy[v] at the ODD fine position
+    2v + 1 of an otherwise zero tensor dz makes the stride-1 'same' dgrad / wgrad of dz equal the strided conv's own
+    gradients:  dx[u] = sum_t w[t]^T dz[u + 1 - t],   dw[t] = sum_u x[u + t - 1] dz[u]."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 8, 6, 4, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(5, 3, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(F.pad(x, (0, 1, 0, 1, 0, 1)), w, stride=2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dz = torch.zeros(2, 5, 8, 6, 4, dtype=torch.float64)
+    dz[:, :, 1::2, 1::2, 1::2] = dy
+    # stride-1 'same' conv z = conv3d(x, w, padding=1) has dgrad = conv_transpose and wgrad = correlation with x
+    xs = x.detach().clone().requires_grad_(True)
+    ws = w.detach().clone().requires_grad_(True)
+    F.conv3d(xs, ws, padding=1).backward(dz)
+    np.testing.assert_allclose(xs.grad.numpy(), x.grad.numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ws.grad.numpy(), w.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_upsampled_source_conv_equals_parity_class_convs_at_coarse_resolution():
+    """3x3x3 'same' conv over UpSampling3D(2)(x) == eight 2x2x2-support convs over x, one per output parity class
+    (oracle.unet_oracle.upsampled_conv_parity_weights) - 8 x 8 = 64 tap-voxel products per coarse voxel instead of
+    8 x 27 = 216. Exact in float64, borders included."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import unet_oracle as uo
+    torch.manual_seed(1)
+    x = torch.randn(2, 4, 5, 3, 4, dtype=torch.float64)
+    w = torch.randn(6, 4, 3, 3, 3, dtype=torch.float64)
+    up = x.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+    ref = F.conv3d(up, w, padding=1)
+    wc = uo.upsampled_conv_parity_weights(w.numpy())
+    out = torch.zeros_like(ref)
+    nonzero = 0
+    for px in range(2):
+        for py in range(2):
+            for pz in range(2):
+                k = torch.as_tensor(wc[px, py, pz])
+                nonzero += int((k.abs().sum(dim=(0, 1)) > 0).sum())
+                out[:, :, px::2, py::2, pz::2] = F.conv3d(x, k, padding=1)
+    assert nonzero == 64
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-12, atol=1e-12)
