@@ -1,0 +1,66 @@
+"""Optional bridge to the reference's Keras checkpoints (fetal_net/training.py:30-32 ModelCheckpoint `.h5` files,
+fetal/utils.py:42-43 get_last_model_path) — SURVEY.md §8f rank 2.
+
+The build image has neither HDF5 nor Keras, so this module is import-guarded and NOT exercised by the test suite:
+it needs `h5py` (always present where Keras is). Two ways to move weights:
+
+  * in an environment with h5py:   Model.load_weights("fetal_net_model-epoch37-....h5") reads the file directly;
+  * anywhere else:                 run `python tools/export_keras_weights.py model.h5 weights.npz` next to the Keras
+                                   install once, then Model.load_weights("weights.npz") here.
+
+Layout read (Keras 2.x): a weights file has the layer groups at the root, a full `model.save()` file under
+`model_weights/`; the group attribute `layer_names` gives the layer order, each layer group's `weight_names` its
+arrays (`<layer>/kernel:0`, `<layer>/bias:0`; `gamma:0` / `beta:0` for keras_contrib InstanceNormalization).
+Keras numbers auto-named layers per session (`conv3d_7` ...), so layers are matched to ours BY ORDER, not by name:
+convolutions (kernel + bias) and normalisations (gamma + beta) in the order Keras created them, which is the order
+of this package's layer table."""
+import numpy as np
+
+HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
+
+
+def is_hdf5(path):
+    with open(path, "rb") as f:
+        return f.read(8) == HDF5_MAGIC
+
+
+def _as_str(v):
+    return v.decode("utf8") if isinstance(v, bytes) else str(v)
+
+
+def read_keras_h5_weights(path):
+    """-> list of (kind, first, second) in Keras creation order; kind 'conv' (kernel, bias) or 'norm' (gamma, beta).
+    Kernels are returned in Keras layout (k, k[, k], Cin, Cout), exactly what fm_model_set_weights takes."""
+    try:
+        import h5py
+    except ImportError as e:  # pragma: no cover - h5py is absent in the build image
+        raise ImportError("reading a Keras .h5 checkpoint needs h5py; convert it once with "
+                          "tools/export_keras_weights.py where Keras is installed and load the .npz instead") from e
+    out = []
+    with h5py.File(path, "r") as f:
+        g = f["model_weights"] if "model_weights" in f else f
+        for lname in [_as_str(n) for n in g.attrs["layer_names"]]:
+            names = [_as_str(n) for n in g[lname].attrs.get("weight_names", [])]
+            arrays = {n.split("/")[-1].split(":")[0]: np.asarray(g[lname][n]) for n in names}
+            if "kernel" in arrays:
+                bias = arrays.get("bias", np.zeros(arrays["kernel"].shape[-1], np.float32))
+                out.append(("conv", arrays["kernel"].astype(np.float32), bias.astype(np.float32)))
+            elif "gamma" in arrays and "beta" in arrays:
+                out.append(("norm", arrays["gamma"].astype(np.float32), arrays["beta"].astype(np.float32)))
+    return out
+
+
+def to_npz_arrays(entries):
+    """The same weights keyed the way Model.save_weights / load_weights key their .npz (layers renumbered from 1 in
+    creation order: conv3d_1/kernel:0, conv3d_1/bias:0, instance_normalization_1/gamma:0, ...)."""
+    arrays, n_conv, n_norm = {}, 0, 0
+    for kind, a, b in entries:
+        if kind == "conv":
+            n_conv += 1
+            prefix = "conv%dd_%d" % (a.ndim - 2, n_conv)
+            arrays[prefix + "/kernel:0"], arrays[prefix + "/bias:0"] = a, b
+        else:
+            n_norm += 1
+            prefix = "instance_normalization_%d" % n_norm
+            arrays[prefix + "/gamma:0"], arrays[prefix + "/beta:0"] = a, b
+    return arrays

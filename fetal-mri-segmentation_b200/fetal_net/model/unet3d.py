@@ -159,12 +159,23 @@ class Model:
     save = save_weights
 
     def load_weights(self, path):
-        with np.load(path) as z:
-            ws = []
-            for l in self.layers:
-                ws += [z[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")],
-                       z[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")]]
+        """Reads the .npz written by save_weights (whatever the file is called), or - where h5py is installed - a
+        Keras .h5 checkpoint of the reference directly (fetal_net.keras_h5; layers matched by creation order)."""
+        from .. import keras_h5
+        if keras_h5.is_hdf5(path):
+            z = keras_h5.to_npz_arrays(keras_h5.read_keras_h5_weights(path))
+            ws = self._weights_from_mapping(z)
+        else:
+            with np.load(path) as z:
+                ws = self._weights_from_mapping(z)
         self.set_weights(ws)
+
+    def _weights_from_mapping(self, z):
+        ws = []
+        for l in self.layers:
+            ws += [np.asarray(z[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")]),
+                   np.asarray(z[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")])]
+        return ws
 
     def reset_optimizer(self):
         _lib.check(self._lib.fm_model_reset_optimizer(self._h))

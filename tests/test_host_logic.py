@@ -208,3 +208,29 @@ def test_host_patch_slicing_matches_reference_goldens(golden):
         padded, fixed = fix_out_of_bound_patch_attempt(data, np.asarray(shape), np.asarray(c))
         sl = tuple(slice(int(f), int(f) + s) for f, s in zip(fixed, shape))
         assert np.array_equal(padded[(Ellipsis,) + sl], golden["patch/out%d" % i])
+
+
+def test_keras_h5_bridge_host_parts(tmp_path):
+    """fetal_net.keras_h5: file sniffing, creation-order renumbering, and the guarded h5py path
+    (h5py is absent here: the error must say how to convert the checkpoint instead)."""
+    from fetal_net import keras_h5
+    npz = tmp_path / "w.h5"                              # the ModelCheckpoint pattern keeps the .h5 name
+    with open(npz, "wb") as f:
+        np.savez(f, a=np.zeros(3))
+    assert not keras_h5.is_hdf5(str(npz))
+    fake = tmp_path / "keras.h5"
+    fake.write_bytes(keras_h5.HDF5_MAGIC + b"\0" * 64)
+    assert keras_h5.is_hdf5(str(fake))
+    entries = [("conv", np.zeros((3, 3, 3, 1, 16), np.float32), np.zeros(16, np.float32)),
+               ("norm", np.ones(16, np.float32), np.zeros(16, np.float32)),
+               ("conv", np.zeros((3, 3, 3, 16, 16), np.float32), np.zeros(16, np.float32)),
+               ("conv", np.zeros((3, 3, 6, 32), np.float32), np.zeros(32, np.float32))]
+    arrays = keras_h5.to_npz_arrays(entries)
+    assert sorted(arrays) == ["conv2d_3/bias:0", "conv2d_3/kernel:0", "conv3d_1/bias:0", "conv3d_1/kernel:0",
+                              "conv3d_2/bias:0", "conv3d_2/kernel:0", "instance_normalization_1/beta:0",
+                              "instance_normalization_1/gamma:0"]
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="export_keras_weights"):
+            keras_h5.read_keras_h5_weights(str(fake))
