@@ -234,3 +234,34 @@ def test_keras_h5_bridge_host_parts(tmp_path):
     except ImportError:
         with pytest.raises(ImportError, match="export_keras_weights"):
             keras_h5.read_keras_h5_weights(str(fake))
+
+
+def test_checkpoint_npz_roundtrip_logic(tmp_path):
+    """Model.save_weights / load_weights without a device: the .npz is keyed by Keras layer names, kernel layout
+    untouched, file name kept as given (ModelCheckpoint writes '...-epochNN-....h5')."""
+    from fetal_net.model.unet3d import Model
+
+    class Stub:
+        layers = [dict(keras_name="conv3d_1", is_norm=False), dict(keras_name="instance_normalization_1", is_norm=True),
+                  dict(keras_name="conv3d_2", is_norm=False)]
+        input_shape, depth, n_base_filters, n_labels = (None, 1, 8, 8, 8), 2, 16, 1
+        _weights_from_mapping = Model._weights_from_mapping
+
+        def __init__(self):
+            rng = np.random.default_rng(0)
+            self.w = [rng.standard_normal(s).astype(np.float32) for s in
+                      [(3, 3, 3, 1, 16), (16,), (16,), (16,), (3, 3, 3, 16, 1), (1,)]]
+
+        def get_weights(self):
+            return self.w
+
+        def set_weights(self, ws):
+            self.loaded = ws
+
+    a, b = Stub(), Stub()
+    path = str(tmp_path / "fetal_net_model-epoch01-loss-0.500-acc0.900.h5")
+    Model.save_weights(a, path)
+    with np.load(path) as z:
+        assert "conv3d_1/kernel:0" in z.files and "instance_normalization_1/gamma:0" in z.files
+    Model.load_weights(b, path)
+    assert len(b.loaded) == 6 and all(np.array_equal(p, q) for p, q in zip(b.loaded, a.w))
