@@ -63,6 +63,7 @@ class Model:
         if loss_function is not dice_coefficient_loss:
             self.metrics_names.append('dice_coefficient')
         self.stop_training = False
+        self.isensee_levels = isensee_levels
         self.name = 'isensee2017_model_3d' if isensee_levels is not None else \
             ('unet_model_3d' if self.ndim == 3 else 'unet_model_2d')
         # layer table (Keras creation order; Keras would name them conv3d_1..conv3d_N)
@@ -153,6 +154,9 @@ class Model:
             arrays[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")] = k
             arrays[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")] = b
         arrays["__config__"] = np.array(list(self.input_shape[1:]) + [self.depth, self.n_base_filters, self.n_labels])
+        # builder name + its extra arguments, so that load_old_model can rebuild the right family
+        arrays["__builder__"] = np.array(getattr(self, "name", "unet_model_3d"))
+        arrays["__isensee_levels__"] = np.array(int(getattr(self, "isensee_levels", 0) or 0))
         with open(path, "wb") as f:   # keep the caller's file name (e.g. '...-epoch01-loss-0.5.h5')
             np.savez(f, **arrays)
 

@@ -150,14 +150,22 @@ def load_old_model(model_file, verbose=True, config=None):
         print("Loading pre-trained model")
     with np.load(model_file) as z:
         cfg = [int(v) for v in z["__config__"]]
+        builder_name = str(z["__builder__"]) if "__builder__" in z.files else None
+        levels = int(z["__isensee_levels__"]) if "__isensee_levels__" in z.files else 0
     loss = _metrics.dice_coefficient_loss
     lr = 1e-5
     if config is not None:
         loss = getattr(_metrics, config.get('loss', 'dice_coefficient_loss'))
         lr = config.get('initial_learning_rate', lr)
-    builder = _model_ns.unet_model_3d if len(cfg) == 7 else _model_ns.unet_model_2d   # (C,X,Y,Z) vs (H,W,D)
-    m = builder(input_shape=tuple(cfg[:-3]), depth=cfg[-3], n_base_filters=cfg[-2], n_labels=cfg[-1],
-                initial_learning_rate=lr, loss_function=loss)
+    if builder_name is None:                        # archives written before the builder name was stored
+        builder_name = 'unet_model_3d' if len(cfg) == 7 else 'unet_model_2d'   # (C,X,Y,Z) vs (H,W,D)
+    kwargs = dict(input_shape=tuple(cfg[:-3]), depth=cfg[-3], n_base_filters=cfg[-2], n_labels=cfg[-1],
+                  initial_learning_rate=lr, loss_function=loss)
+    if builder_name == 'isensee2017_model_3d':
+        kwargs['n_segmentation_levels'] = levels
+        if config is not None and 'dropout_rate' in config:
+            kwargs['dropout_rate'] = config['dropout_rate']
+    m = getattr(_model_ns, builder_name)(**kwargs)
     m.load_weights(model_file)
     return m
 

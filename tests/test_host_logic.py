@@ -265,3 +265,67 @@ def test_checkpoint_npz_roundtrip_logic(tmp_path):
         assert "conv3d_1/kernel:0" in z.files and "instance_normalization_1/gamma:0" in z.files
     Model.load_weights(b, path)
     assert len(b.loaded) == 6 and all(np.array_equal(p, q) for p, q in zip(b.loaded, a.w))
+
+
+def test_train_model_driver_and_callbacks_on_a_stub(tmp_path):
+    """train_model -> Model.fit_generator -> callbacks (training.py:26-42,89-124) without a device: checkpoint file
+    pattern and save-best-only, CSV log, ReduceLROnPlateau, EarlyStopping, and load_old_model's builder dispatch."""
+    import itertools
+    from fetal_net import training
+    from fetal_net.model.unet3d import Model
+
+    class Opt:
+        lr = 1e-3
+
+    val_losses = [-0.50, -0.60, -0.55, -0.58, -0.57, -0.56, -0.40, -0.40]
+
+    class Stub:
+        metrics_names = ['loss', 'binary_accuracy', 'vod_coefficient']
+        fit_generator = Model.fit_generator
+        save = Model.save_weights
+        _weights_from_mapping = Model._weights_from_mapping
+        layers = [dict(keras_name="conv3d_1", is_norm=False)]
+        input_shape, depth, n_base_filters, n_labels, name, isensee_levels = (None, 1, 8, 8, 8), 2, 16, 1, 'unet_model_3d', None
+
+        def __init__(self):
+            self.optimizer, self.stop_training, self.steps, self.epoch = Opt(), False, 0, 0
+
+        def get_weights(self):
+            return [np.full((3, 3, 3, 1, 16), self.steps, np.float32), np.zeros(16, np.float32)]
+
+        def train_on_batch(self, x, y):
+            self.steps += 1
+            return [-0.3, 0.9, 0.2]
+
+        def test_on_batch(self, x, y):
+            return [val_losses[min(self.epoch, len(val_losses) - 1)], 0.95, 0.3]
+
+    model = Stub()
+
+    def gen():
+        for i in itertools.count():
+            yield np.zeros((2, 1, 8, 8, 8), np.float32), np.zeros((2, 1, 8, 8, 8), np.float32)
+
+    class EpochCounter(training.Callback):
+        def on_epoch_begin(self, epoch, logs=None):
+            model.epoch = epoch
+
+    orig = training.get_callbacks
+    training.get_callbacks = lambda *a, **k: [EpochCounter()] + orig(*a, **dict(k, verbosity=0))
+    try:
+        hist = training.train_model(model, str(tmp_path / "fetal_net_model"), gen(), gen(), steps_per_epoch=3,
+                                    validation_steps=2, initial_learning_rate=1e-3, learning_rate_drop=0.5,
+                                    learning_rate_patience=2, early_stopping_patience=4, n_epochs=20,
+                                    output_folder=str(tmp_path))
+    finally:
+        training.get_callbacks = orig
+    # best val_loss -0.60 at epoch 2; EarlyStopping(patience 4) stops after epoch 6
+    assert len(hist["val_loss"]) == 6 and model.steps == 18
+    files = sorted(os.path.basename(f) for f in os.listdir(tmp_path) if f.endswith(".h5"))
+    assert files == ["fetal_net_model-epoch01-loss-0.500-acc0.950.h5", "fetal_net_model-epoch02-loss-0.600-acc0.950.h5"]
+    assert training.get_last_model_path(str(tmp_path / "fetal_net_model")).endswith("epoch02-loss-0.600-acc0.950.h5")
+    assert model.optimizer.lr == pytest.approx(2.5e-4)              # halved after epochs 4 and 6 (patience 2)
+    rows = open(tmp_path / "training").read().strip().splitlines()
+    assert rows[0].startswith("epoch,") and len(rows) == 7
+    with np.load(tmp_path / files[-1]) as z:
+        assert str(z["__builder__"]) == "unet_model_3d" and [int(v) for v in z["__config__"]] == [1, 8, 8, 8, 2, 16, 1]
