@@ -329,3 +329,44 @@ def test_train_model_driver_and_callbacks_on_a_stub(tmp_path):
     assert rows[0].startswith("epoch,") and len(rows) == 7
     with np.load(tmp_path / files[-1]) as z:
         assert str(z["__builder__"]) == "unet_model_3d" and [int(v) for v in z["__config__"]] == [1, 8, 8, 8, 2, 16, 1]
+
+
+def test_small_host_helpers_on_a_stub():
+    """step_decay / LearningRateScheduler (training.py:22-23,34-37), Model.evaluate (Keras batch-size weighting),
+    Model.summary / to_json - host logic only, no device."""
+    import json
+    from fetal_net import training
+    from fetal_net.model.unet3d import Model
+    assert training.step_decay(0, 1e-3, 0.5, 10) == pytest.approx(1e-3)
+    assert training.step_decay(9, 1e-3, 0.5, 10) == pytest.approx(5e-4)          # floor((1 + 9) / 10) = 1
+    assert training.step_decay(29, 1e-3, 0.5, 10) == pytest.approx(1.25e-4)
+
+    class Opt:
+        lr = 1.0
+
+    class Stub:
+        metrics_names = ['loss', 'binary_accuracy', 'vod_coefficient']
+        optimizer = Opt()
+        ndim, name, depth, n_base_filters, n_labels = 3, 'unet_model_3d', 2, 16, 1
+        input_shape = (None, 1, 8, 8, 8)
+        layers = [dict(name="enc0a", keras_name="conv3d_1", cin=1, cout=16, k=3, is_norm=False),
+                  dict(name="l0_in_norm", keras_name="instance_normalization_1", cin=16, cout=16, k=0, is_norm=True)]
+
+        def test_on_batch(self, x, y):
+            return [float(len(x)), 1.0, 0.5]
+
+        def count_params(self):
+            return 27 * 16 + 16 + 32
+
+    sched = training.LearningRateScheduler(lambda e: 0.1 * (e + 1))
+    sched.set_model(Stub)
+    sched.on_epoch_begin(2)
+    assert Stub.optimizer.lr == pytest.approx(0.3)
+    x = np.zeros((5, 1, 2, 2, 2), np.float32)
+    ev = Model.evaluate(Stub(), x, x, batch_size=2)                  # batches of 2, 2, 1 -> weighted mean of 2, 2, 1
+    assert ev[0] == pytest.approx((2 * 2 + 2 * 2 + 1 * 1) / 5) and ev[1] == pytest.approx(1.0)
+    lines = []
+    Model.summary(Stub(), print_fn=lines.append)
+    assert lines[-1] == "Total params: %d" % (27 * 16 + 16 + 32) and "conv3d_1" in lines[1] and lines[2].split()[-1] == "32"
+    cfg = json.loads(Model.to_json(Stub()))
+    assert cfg["class_name"] == "unet_model_3d" and cfg["input_shape"] == [1, 8, 8, 8]
