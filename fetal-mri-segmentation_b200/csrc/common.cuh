@@ -253,6 +253,20 @@ int k_conv3d_march_shared(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* w
                           const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2,
                           int Cout, int relu, int out_C, int out_cofs);
 
+// conv_march2.cu: second-generation marching kernel (tight issue loops, register-resident bias, one shared
+// accumulator ring). nissue = 1: single issuing warp, bit-reproducible; nissue = 3: one issuing warp per dz slab copy.
+// k_conv3d_march / k_conv3d_march_shared route here unless FETAL_B200_MARCH_V1=1 (A/B against the round-1 kernels).
+int k_conv3d_march2(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* wm1, const bf16* wm2, const float* bias,
+                    bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2, int Cout, int relu,
+                    int out_C, int out_cofs, int nissue);
+static inline bool fm_march_v1() {
+  static const bool v1 = [] {
+    const char* e = getenv("FETAL_B200_MARCH_V1");
+    return e && e[0] == '1';
+  }();
+  return v1;
+}
+
 // conv_wgrad_march.cu
 int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize);
 int k_conv3d_wgrad_march(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,

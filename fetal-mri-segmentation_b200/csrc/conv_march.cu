@@ -441,6 +441,8 @@ int k_repack_march(fm_ctx* ctx, const bf16* P, bf16* Wm, int Nrows, int Ktot, in
 int k_conv3d_march(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1, const bf16* wm2,
                    const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2,
                    int Cout, int relu, int out_C, int out_cofs) {
+  if (!fm_march_v1())
+    return k_conv3d_march2(ctx, x1, x2, wm1, wm2, bias, y, mask, N, X, Y, Z, C1, C2, Cout, relu, out_C, out_cofs, 1);
   FM_CHECK(conv_march_supported(X, Y, Z, C1, C2, Cout, 3), FM_EINVAL,
            "conv3d march: unsupported shape %dx%dx%d C1=%d C2=%d Cout=%d", X, Y, Z, C1, C2, Cout);
   PFN_encodeTiled enc = get_encode_m();

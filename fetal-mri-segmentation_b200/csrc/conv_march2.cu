@@ -1,0 +1,517 @@
+// conv_march2.cu — second-generation plane-marching implicit-GEMM Conv3D 3x3x3 (fprop + dgrad).
+//
+// Same data flow as conv_march.cu / conv_march_shared.cu (a CTA owns a 16(y) x 8(z) column and marches along x; per
+// input plane three z-shifted y-haloed slabs arrive by TMA; the dy tap is an 8-row offset of the A descriptor; the
+// three dx taps are stacked along N into a ring of TMEM accumulator blocks; the filter bank is resident in shared
+// memory), but rebuilt around what the round-1 ncu captures showed (profiles/README.md):
+//
+//   * the MMA-issuing warps were ISSUE bound (231 warp instructions per plane for 6 MMAs: per-plane recomputation
+//     of descriptor constants, un-unrolled k loops, ring bookkeeping). Here Cout is a template parameter, every
+//     per-source constant is hoisted out of the item loop, and a K chunk is issued by a fully unrolled
+//     issue_chunk<NK>() (3 dy x NK MMAs, immediates only), about 70 instructions per plane.
+//   * the epilogue spent a third of its time on the per-plane bias loads (LDG + long scoreboard); bias now lives in
+//     registers for the CTA's lifetime, all TMEM loads of a plane are issued before one wait, and the accumulator
+//     block is handed back (zeroed) before the bf16 conversion and the global stores.
+//   * one accumulator ring shared by all issuing warps (the epilogue hands blocks back zeroed, every MMA
+//     accumulates). NISSUE = 3: one issuing warp per dz slab copy (training passes; the fp32 summation order
+//     follows the interleaving of the three issue streams). NISSUE = 1: a single warp issues every MMA in a fixed
+//     order - bit-reproducible run to run (predict / evaluate / patch_wise_prediction), and with the tight issue
+//     loop one warp keeps the tensor pipe fed.
+//
+// fprop: epilogue = bias + ReLU. dgrad: same kernel on dY with flipped/transposed weights, epilogue = ReLU mask of
+// the producing block. Keras call site: Conv3D in create_convolution_block (fetal_net/model/unet3d/unet.py:102).
+#include <algorithm>
+
+#include "tc_ptx.cuh"
+
+using namespace tcp;
+
+namespace {
+
+constexpr int kThreads2 = 256;  // warp 0 TMA, warps 1-3 MMA issue, warps 4-7 epilogue
+constexpr int kBY = 16, kBZ = 8, kSlabRows = (kBY + 2) * kBZ;  // 144 rows per slab
+constexpr uint32_t kSlotFull = kSlabRows * 128;                // 18432 B (1024-aligned): slab slot at KC = 64
+constexpr int kMaxRing2 = 16;
+
+struct alignas(64) March2Params {
+  CUtensorMap tmA[2];  // activations, box (KC, 8, 18, 1, 1)
+  CUtensorMap tmW[2];  // march-packed weights, 2-D (KC, rows), box (KC, 3*Cn)
+  int nsrc;
+  int nchunks[2];
+  int KC[2];
+  uint32_t wofs[2];  // byte offset of the source's resident weights inside the W region
+  int N, X, Y, Z;
+  int ny, nz, nxc, xchunk, items;
+  int R;       // accumulator ring blocks (power of two)
+  int stages;  // slab slots, a multiple of 3 (one private ring per dz slab copy)
+  int out_C, out_cofs, relu;
+  uint32_t w_bytes;   // bytes the weight TMA loads deliver (mbarrier expect_tx)
+  uint32_t w_region;  // shared-memory bytes reserved for them (1024-aligned per source)
+  uint32_t slot;      // bytes per slab slot (1024-aligned)
+  const float* bias;
+  bf16* out;
+  const bf16* mask;
+};
+
+// 3 dy taps x NK k-steps of one resident K chunk: A = slab (dy = +8 rows = +KC 16-byte units), B = the dx-stacked
+// filter tile of (dz, dy); every MMA accumulates into the ring blocks at `col`.
+template <int NK>
+__device__ __forceinline__ void issue_chunk(uint32_t col, uint32_t a_lo, uint32_t b_lo, uint32_t hi32,
+                                            uint32_t btile16, uint32_t idesc) {
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      umma_bf16_lh_elect(col, a_lo + (uint32_t)(dy * NK * 16 + 2 * k), hi32, b_lo + (uint32_t)dy * btile16 + 2u * (uint32_t)k,
+                         hi32, idesc, 1u);
+  }
+}
+
+__device__ __forceinline__ void issue_chunk_nk(int nk, uint32_t col, uint32_t a_lo, uint32_t b_lo, uint32_t hi32,
+                                               uint32_t btile16, uint32_t idesc) {
+  if (nk == 2)
+    issue_chunk<2>(col, a_lo, b_lo, hi32, btile16, idesc);
+  else if (nk == 4)
+    issue_chunk<4>(col, a_lo, b_lo, hi32, btile16, idesc);
+  else
+    issue_chunk<1>(col, a_lo, b_lo, hi32, btile16, idesc);
+}
+
+template <int NISSUE, int CN>
+__global__ void __launch_bounds__(kThreads2, 1) conv3d_march2_kernel(const __grid_constant__ March2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t w_base = smem0;
+  const uint32_t a_base = smem0 + p.w_region;
+  const uint32_t bar0 = a_base + (uint32_t)p.stages * p.slot;
+  const uint32_t nst = (uint32_t)p.stages;
+  // barrier layout: full[stages] | empty[stages] | tfull[16] | tempty[16] | wfull | tmem slot
+  const uint32_t full0 = bar0, empty0 = bar0 + 8u * nst, tfull0 = bar0 + 16u * nst, tempty0 = tfull0 + 8u * kMaxRing2;
+  const uint32_t wfull_bar = tempty0 + 8u * kMaxRing2;
+  const uint32_t tmem_slot = wfull_bar + 8u;
+
+  constexpr uint32_t Cn = (uint32_t)CN;
+  const uint32_t R = (uint32_t)p.R;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < R * Cn) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) {
+      prefetch_tmap(&p.tmA[s]);
+      prefetch_tmap(&p.tmW[s]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (uint32_t s = 0; s < nst; ++s) {
+        mbar_init(full0 + 8u * s, 1);
+        mbar_init(empty0 + 8u * s, 1);
+      }
+      for (uint32_t b = 0; b < R; ++b) {
+        mbar_init(tfull0 + 8u * b, (uint32_t)NISSUE);  // one tcgen05.commit per MMA-issuing warp
+        mbar_init(tempty0 + 8u * b, 128);
+      }
+      mbar_init(wfull_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) {
+    const int jx = item % p.nxc;
+    int t = item / p.nxc;
+    iz = t % p.nz;
+    t /= p.nz;
+    iy = t % p.ny;
+    n = t / p.ny;
+    xa = jx * p.xchunk;
+    xb = min(p.X, xa + p.xchunk);
+  };
+
+  // make the values the producer / MMA warps compute on provably warp-uniform
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t S3 = nst / 3u;
+
+  if (warp_u == 0) {
+    // ===== producer warp (all lanes converged, one elected lane issues): resident weights once, then one slab per
+    //       (plane, dz, source, chunk); every dz slab copy has its own ring of S3 slots =====
+    mbar_expect_tx_elect(wfull_bar, p.w_bytes);
+    for (int s = 0; s < p.nsrc; ++s) {
+      const uint32_t tile = 3u * Cn * (uint32_t)p.KC[s] * 2u;
+      for (int t = 0; t < p.nchunks[s] * 9; ++t)
+        tma_load_2d_elect(w_base + p.wofs[s] + (uint32_t)t * tile, &p.tmW[s], wfull_bar, 0, t * 3 * CN);
+    }
+    // the weights do not depend on the previous kernel in the stream; the activation slabs do
+    pdl_wait();
+    pdl_launch_dependents();
+    uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
+    const uint32_t bytes0 = (uint32_t)kSlabRows * (uint32_t)p.KC[0] * 2u;
+    const uint32_t bytes1 = (uint32_t)kSlabRows * (uint32_t)p.KC[1] * 2u;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, iy, iz, xa, xb;
+      decode(item, n, iy, iz, xa, xb);
+      const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+      const int yc = iy * kBY - 1, zc = iz * kBZ - 1;
+      for (int xi = x_first; xi <= x_last; ++xi) {
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (s >= p.nsrc) break;
+            const uint32_t bytes = s == 0 ? bytes0 : bytes1;
+            for (int ch = 0; ch < p.nchunks[s]; ++ch) {
+              const uint32_t stage = (uint32_t)dz * S3 + sidx[dz];
+              mbar_wait(empty0 + 8u * stage, sph[dz] ^ 1u);
+              mbar_expect_tx_elect(full0 + 8u * stage, bytes);
+              tma_load_5d_elect(a_base + stage * p.slot, &p.tmA[s], full0 + 8u * stage, ch * p.KC[s], zc + dz, yc, xi, n);
+              if (++sidx[dz] == S3) {
+                sidx[dz] = 0;
+                sph[dz] ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp_u <= 3) {
+    // ===== MMA warps. NISSUE = 3: warp w owns the slab copy dz = w - 1 of every input plane. NISSUE = 1: warp 1
+    //       walks dz = 0, 1, 2 itself (fixed summation order). All MMAs accumulate; the epilogue hands accumulator
+    //       blocks back zeroed. =====
+    const int mw = warp_u - 1;
+    if (mw < NISSUE) {
+      const int dz_lo = (NISSUE == 3) ? mw : 0;
+      const uint32_t ring_mask = R - 1u;
+      const uint32_t ring_shift = 31u - (uint32_t)__clz((int)R);
+      constexpr uint32_t idesc1 = make_idesc(128, CN, 0, 0);
+      constexpr uint32_t idesc2 = make_idesc(128, 2 * CN, 0, 0);
+      constexpr uint32_t idesc3 = make_idesc(128, 3 * CN, 0, 0);
+      // per-source constants (16-byte descriptor units)
+      uint32_t hi32[2], btile16[2], blk16[2], bsrc[2];
+      int nk[2], nch[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
+        hi32[s] = desc_hi(8u * row_bytes, layout_code((int)row_bytes));
+        btile16[s] = (3u * Cn * row_bytes) >> 4;
+        blk16[s] = (Cn * row_bytes) >> 4;
+        bsrc[s] = desc_lo(w_base + p.wofs[s], 16u);
+        nk[s] = p.KC[s] >> 4;
+        nch[s] = s < p.nsrc ? p.nchunks[s] : 0;
+      }
+      const uint32_t a_lo0 = desc_lo(a_base, 16u);
+      const uint32_t slot16 = p.slot >> 4;
+      mbar_wait(wfull_bar, 0);
+      tc_fence_after();
+      uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
+      uint32_t ocount = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int n, iy, iz, xa, xb;
+        decode(item, n, iy, iz, xa, xb);
+        const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
+        for (int xi = x_first; xi <= x_last; ++xi) {
+          const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes fed by plane xi
+          const uint32_t j_lo = (uint32_t)(lo - (xi - 1));
+          const uint32_t nblk = (uint32_t)(hi - lo + 1);
+          const uint32_t seq_lo = ocount + (uint32_t)(lo - xa);
+          const uint32_t rb_lo = seq_lo & ring_mask;
+          // blocks first touched by this plane must have been drained (and zeroed) by the epilogue
+          if (xi == x_first) {
+            for (uint32_t j = 0; j < nblk; ++j) {
+              const uint32_t seq = seq_lo + j;
+              mbar_wait(tempty0 + 8u * (seq & ring_mask), (seq >> ring_shift) & 1u);
+            }
+          } else if (xi + 1 <= xb - 1) {
+            const uint32_t seq = ocount + (uint32_t)(xi + 1 - xa);
+            mbar_wait(tempty0 + 8u * (seq & ring_mask), (seq >> ring_shift) & 1u);
+          }
+          tc_fence_after();
+          // the <= 3 consecutive ring blocks, split only where the ring wraps
+          const uint32_t nA = min(nblk, R - rb_lo), nB = nblk - nA;
+          const uint32_t colA = tmem_base + rb_lo * Cn, colB = tmem_base;
+          const uint32_t idA = nA == 3 ? idesc3 : (nA == 2 ? idesc2 : idesc1);
+          const uint32_t idB = nB == 2 ? idesc2 : idesc1;
+#pragma unroll
+          for (int dzi = 0; dzi < (NISSUE == 3 ? 1 : 3); ++dzi) {
+            const int dz = dz_lo + dzi;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              const uint32_t b_s = bsrc[s] + (uint32_t)(dz * 3) * btile16[s] + j_lo * blk16[s];
+              for (int ch = 0; ch < nch[s]; ++ch) {
+                const uint32_t stage = (uint32_t)dz * S3 + sidx[dzi];
+                mbar_wait(full0 + 8u * stage, sph[dzi]);
+                tc_fence_after();
+                const uint32_t a_lo = a_lo0 + stage * slot16;
+                const uint32_t b_lo = b_s + (uint32_t)(ch * 9) * btile16[s];
+                issue_chunk_nk(nk[s], colA, a_lo, b_lo, hi32[s], btile16[s], idA);
+                if (nB) issue_chunk_nk(nk[s], colB, a_lo, b_lo + nA * blk16[s], hi32[s], btile16[s], idB);
+                umma_commit_elect(empty0 + 8u * stage);
+                if (++sidx[dzi] == S3) {
+                  sidx[dzi] = 0;
+                  sph[dzi] ^= 1u;
+                }
+              }
+            }
+          }
+          // output planes completed by this input plane (each MMA warp contributes one arrival)
+          if (xi - 1 >= xa) umma_commit_elect(tfull0 + 8u * ((ocount + (uint32_t)(xi - 1 - xa)) & ring_mask));
+          if (xi == x_last && xi <= xb - 1) umma_commit_elect(tfull0 + 8u * ((ocount + (uint32_t)(xi - xa)) & ring_mask));
+        }
+        ocount += (uint32_t)(xb - xa);
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, one TMEM lane quarter each; row = (y, z) of the 16 x 8 column =====
+    constexpr int NCG = CN / 16;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int yl = row >> 3, zl = row & 7;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t ring_mask = R - 1u;
+    const uint32_t ring_shift = 31u - (uint32_t)__clz((int)R);
+    // hand every accumulator block to the MMA warps zeroed (TMEM is not initialised by the allocation)
+    for (uint32_t b = 0; b < R; ++b) {
+#pragma unroll
+      for (int c16 = 0; c16 < NCG; ++c16) tmem_st16_zero(lane_base + b * Cn + (uint32_t)(c16 * 16));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8u * b);
+    }
+    // bias stays in registers for the CTA's lifetime
+    float bias_r[CN];
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < CN / 4; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias) + j);
+        bias_r[4 * j] = b4.x;
+        bias_r[4 * j + 1] = b4.y;
+        bias_r[4 * j + 2] = b4.z;
+        bias_r[4 * j + 3] = b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CN; ++j) bias_r[j] = 0.f;
+    }
+    const bool relu = p.relu != 0;
+    const bool has_mask = p.mask != nullptr;
+    uint32_t ocount = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, iy, iz, xa, xb;
+      decode(item, n, iy, iz, xa, xb);
+      const int y = iy * kBY + yl, z = iz * kBZ + zl;
+      const int64_t v0 = (((int64_t)n * p.X + xa) * p.Y + y) * p.Z + z;
+      const int64_t vstep = (int64_t)p.Y * p.Z;
+      for (int xo = xa; xo < xb; ++xo) {
+        const uint32_t seq = ocount + (uint32_t)(xo - xa);
+        const uint32_t rb = seq & ring_mask;
+        const int64_t off = (v0 + (int64_t)(xo - xa) * vstep) * p.out_C + p.out_cofs;
+        // dgrad: fetch this row's ReLU mask BEFORE waiting for the accumulator, so its latency hides behind the MMAs
+        uint4 mk[2 * NCG];
+        if (has_mask) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off);
+#pragma unroll
+          for (int h = 0; h < 2 * NCG; ++h) mk[h] = __ldg(mp + h);
+        }
+        mbar_wait(tfull0 + 8u * rb, (seq >> ring_shift) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = lane_base + rb * Cn;
+        uint32_t r[NCG][16];
+#pragma unroll
+        for (int c16 = 0; c16 < NCG; ++c16) tmem_ld16(taddr + (uint32_t)(c16 * 16), r[c16]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c16 = 0; c16 < NCG; ++c16) tmem_st16_zero(taddr + (uint32_t)(c16 * 16));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8u * rb);  // the block is free (and zero) again; the rest is register work
+#pragma unroll
+        for (int c16 = 0; c16 < NCG; ++c16) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[c16][j]) + bias_r[c16 * 16 + j];
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (has_mask) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 mv = mk[2 * c16 + h];
+              const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 mf = __bfloat1622float2(mh[j]);
+                if (!(mf.x > 0.f)) f[8 * h + 2 * j] = 0.f;
+                if (!(mf.y > 0.f)) f[8 * h + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+          uint4 o[2];
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          uint4* op = reinterpret_cast<uint4*>(p.out + off + c16 * 16);
+          op[0] = o[0];
+          op[1] = o[1];
+        }
+      }
+      ocount += (uint32_t)(xb - xa);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled2 get_encode_m2() {
+  static PFN_encodeTiled2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled2)p;
+  }
+  return fn;
+}
+CUtensorMapSwizzle swz2(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+const int kMaxDynSmem2 = 227 * 1024;
+
+template <int NISSUE, int CN>
+int launch_march2(fm_ctx* ctx, const March2Params& p, size_t smem, int grid) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FM_CUDA(cudaFuncSetAttribute(conv3d_march2_kernel<NISSUE, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxDynSmem2));
+    attr_set = true;
+  }
+  FM_CUDA(launch_pdl(conv3d_march2_kernel<NISSUE, CN>, dim3(grid), dim3(kThreads2), smem, ctx->stream, p));
+  return FM_OK;
+}
+
+}  // namespace
+
+// nissue: 1 = bit-reproducible (single issuing warp), 3 = one issuing warp per dz slab copy (training passes)
+int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1, const bf16* wm2, const float* bias,
+                    bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1, int C2, int Cout, int relu, int out_C,
+                    int out_cofs, int nissue) {
+  FM_CHECK(conv_march_supported(X, Y, Z, C1, C2, Cout, 3), FM_EINVAL,
+           "conv3d march2: unsupported shape %dx%dx%d C1=%d C2=%d Cout=%d", X, Y, Z, C1, C2, Cout);
+  PFN_encodeTiled2 enc = get_encode_m2();
+  FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  March2Params p;
+  memset(&p, 0, sizeof(p));
+  p.nsrc = C2 > 0 ? 2 : 1;
+  p.N = N;
+  p.X = X;
+  p.Y = Y;
+  p.Z = Z;
+  p.ny = Y / kBY;
+  p.nz = Z / kBZ;
+  p.R = std::min(kMaxRing2, 512 / Cout);
+  p.out_C = out_C;
+  p.out_cofs = out_cofs;
+  p.relu = relu;
+  p.bias = bias;
+  p.out = y;
+  p.mask = mask;
+  // x-chunking: trade wave quantisation against the 2 halo planes each chunk re-loads
+  {
+    const int cols = N * p.ny * p.nz;
+    double best = -1.0;
+    int best_nxc = 1;
+    for (int nxc = 1; nxc <= 16; nxc *= 2) {
+      const int xc = ceil_div(X, nxc);
+      if (xc < 4 && nxc > 1) break;
+      const int items = cols * ceil_div(X, xc);
+      const int waves = ceil_div(items, ctx->num_sms);
+      const double eff = (double)items / ((double)waves * ctx->num_sms) * (double)xc / (double)(xc + 1.4);
+      if (eff > best) {
+        best = eff;
+        best_nxc = nxc;
+      }
+    }
+    p.xchunk = ceil_div(X, best_nxc);
+    p.nxc = ceil_div(X, p.xchunk);
+    p.items = cols * p.nxc;
+  }
+  const int Cs[2] = {C1, C2};
+  const bf16* xs[2] = {x1, x2};
+  const bf16* wms[2] = {wm1, wm2};
+  uint32_t wofs = 0, wbytes = 0;
+  p.KC[1] = 16;  // harmless defaults for the unused second source
+  for (int s = 0; s < p.nsrc; ++s) {
+    const int KC = conv_march_kc(C1, C2, Cout, Cs[s]);
+    p.KC[s] = KC;
+    p.nchunks[s] = Cs[s] / KC;
+    p.wofs[s] = wofs;
+    wofs += ((uint32_t)27 * Cs[s] * Cout * 2u + 1023u) & ~1023u;
+    wbytes += (uint32_t)27 * Cs[s] * Cout * 2u;
+    {
+      cuuint64_t dims[5] = {(cuuint64_t)Cs[s], (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
+      cuuint64_t strides[4] = {(cuuint64_t)Cs[s] * 2, (cuuint64_t)Z * Cs[s] * 2, (cuuint64_t)Y * Z * Cs[s] * 2,
+                               (cuuint64_t)X * Y * Z * Cs[s] * 2};
+      cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)kBZ, (cuuint32_t)(kBY + 2), 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = enc(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)xs[s], dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz2(KC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA, "cuTensorMapEncodeTiled(march2 act) failed: %d", (int)r);
+    }
+    {
+      const cuuint64_t rows = (cuuint64_t)p.nchunks[s] * 27 * Cout;
+      cuuint64_t dims[2] = {(cuuint64_t)KC, rows};
+      cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
+      cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(3 * Cout)};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(&p.tmW[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)wms[s], dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz2(KC * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      FM_CHECK(r == CUDA_SUCCESS, FM_ECUDA, "cuTensorMapEncodeTiled(march2 weights) failed: %d", (int)r);
+    }
+  }
+  p.w_bytes = wbytes;
+  p.w_region = wofs;
+  // slot = one slab at the widest K chunk in use (18 KB at KC = 64, 9 KB when every source runs at KC <= 32)
+  p.slot = (uint32_t)kSlabRows * (uint32_t)std::max(p.KC[0], p.nsrc > 1 ? p.KC[1] : 0) * 2u;
+  p.slot = (p.slot + 1023u) & ~1023u;
+  int stages = (kMaxDynSmem2 - 2048 - (int)wofs) / (int)p.slot;
+  stages = std::min(stages, 12) / 3 * 3;  // three private rings (one per dz slab copy)
+  FM_CHECK(stages >= 3, FM_EINVAL, "conv3d march2: filter bank leaves no room for the slab rings");
+  p.stages = stages;
+  const size_t smem = (size_t)wofs + (size_t)stages * p.slot + 1024 + 512;
+  FM_CHECK(smem <= (size_t)kMaxDynSmem2, FM_EINVAL, "conv3d march2: %zu B of shared memory needed", smem);
+  const int grid = std::min(p.items, ctx->num_sms);
+  const double vox = (double)N * X * Y * Z;
+  ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_march_dgrad" : "conv3d_march_fprop",
+                 2.0 * 27 * (C1 + C2) * Cout * vox, vox * (C1 + C2 + Cout) * 2.0);
+  const bool three = nissue == 3 && Cout <= 32;
+  int rc;
+  if (Cout == 16)
+    rc = three ? launch_march2<3, 16>(ctx, p, smem, grid) : launch_march2<1, 16>(ctx, p, smem, grid);
+  else if (Cout == 32)
+    rc = three ? launch_march2<3, 32>(ctx, p, smem, grid) : launch_march2<1, 32>(ctx, p, smem, grid);
+  else
+    rc = launch_march2<1, 64>(ctx, p, smem, grid);
+  FM_TRY(rc);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
