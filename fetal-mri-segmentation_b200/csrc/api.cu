@@ -59,6 +59,9 @@ extern "C" int fm_ctx_destroy(fm_ctx* ctx) {
   if (!ctx) return FM_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  fm_comm_destroy(ctx);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  if (ctx->comm_ev) cudaEventDestroy(ctx->comm_ev);
   if (ctx->red_scratch) cudaFree(ctx->red_scratch);
   for (auto& r : ctx->prof) {
     cudaEventDestroy(r.e0);
@@ -252,6 +255,11 @@ struct fm_model {
   // previous step is still in its backward pass; the call returns once the Dice statistics of ITS forward pass are
   // on the host, the rest of the step (backward, Adam, repack) keeps running and is ordered before any later call
   DevBuf<float> stage_x[2], stage_t[2];
+  // pageable host inputs are first copied (a few host threads) into these pinned ping-pong buffers, so that they take
+  // the same pipelined route; host_stage_done[b] = the H2D copies out of buffer b have completed
+  float* host_stage[2] = {nullptr, nullptr};
+  size_t host_stage_floats[2] = {0, 0};
+  cudaEvent_t host_stage_done[2] = {nullptr, nullptr};
   cudaEvent_t stage_ready[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr}, sums_ready = nullptr;
   double* sums_pin = nullptr;
   int stage_idx = 0;
@@ -517,6 +525,10 @@ extern "C" int fm_model_destroy(fm_model* m) {
   }
   if (m->sums_ready) cudaEventDestroy(m->sums_ready);
   if (m->sums_pin) cudaFreeHost(m->sums_pin);
+  for (int b = 0; b < 2; ++b) {
+    if (m->host_stage[b]) cudaFreeHost(m->host_stage[b]);
+    if (m->host_stage_done[b]) cudaEventDestroy(m->host_stage_done[b]);
+  }
   if (m->ev_tmp) cudaEventDestroy(m->ev_tmp);
   delete m;
   return FM_OK;
@@ -1456,12 +1468,15 @@ extern "C" int fm_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx
   return r;
 }
 
-extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t vol_dims[3],
-                                    const int32_t halo_pad[6], const int32_t fit_pad[6],
-                                    const double pad_value[2], const int32_t* idx, int64_t n, int batch,
-                                    int shard_rank, int shard_count, const float* truth, int prev_truth_index,
-                                    int prev_truth_size, double* out, int16_t* out_count) {
-  FM_CHECK(m && vol && vol_dims && halo_pad && fit_pad && pad_value && idx && out && n > 0 && batch > 0,
+// reduce_root < 0: `out` receives this shard's result (the average for shard 0 of 1, the partial SUM otherwise).
+// reduce_root >= 0: the partial sums are reduced on the ctx communicator to that rank, which divides by the counts and
+// is the only one to copy anything back to the host.
+static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[3], const int32_t halo_pad[6],
+                          const int32_t fit_pad[6], const double pad_value[2], const int32_t* idx, int64_t n, int batch,
+                          int shard_rank, int shard_count, int reduce_root, const float* truth, int prev_truth_index,
+                          int prev_truth_size, double* out, int16_t* out_count) {
+  const bool want_out = reduce_root < 0 || shard_rank == reduce_root;
+  FM_CHECK(m && vol && vol_dims && halo_pad && fit_pad && pad_value && idx && (out || !want_out) && n > 0 && batch > 0,
            FM_EINVAL, "fm_patchwise_predict: bad argument");
   FM_CHECK(shard_count >= 1 && shard_rank >= 0 && shard_rank < shard_count, FM_EINVAL,
            "fm_patchwise_predict: shard %d of %d", shard_rank, shard_count);
@@ -1536,8 +1551,16 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
   lap("gather + forward");
   FM_TRY(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, pred, 1, out_dims, dout.p, dcnt.p,
                       shard_count == 1 ? 1 : 0));
+  if (reduce_root >= 0 && shard_count > 1) {
+    FM_TRY(comm_reduce(ctx, dout.p, nout, 1, reduce_root, ctx->stream));
+    if (want_out) FM_TRY(k_divide_by_count(ctx, dout.p, dcnt.p, (int64_t)nout, 1));
+  }
   FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the H2D staging buffer is reused for the way back
   lap("reassemble");
+  if (!want_out) {
+    m->fwd_valid = false;
+    return FM_OK;
+  }
   FM_CUDA(cudaMemcpyAsync(pin, dout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_count)
     FM_CUDA(cudaMemcpyAsync((char*)pin + out_bytes, dcnt.p, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1548,6 +1571,28 @@ extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t
   lap("unstage result");
   m->fwd_valid = false;
   return FM_OK;
+}
+
+extern "C" int fm_patchwise_predict(fm_model* m, const float* vol, const int32_t vol_dims[3],
+                                    const int32_t halo_pad[6], const int32_t fit_pad[6],
+                                    const double pad_value[2], const int32_t* idx, int64_t n, int batch,
+                                    int shard_rank, int shard_count, const float* truth, int prev_truth_index,
+                                    int prev_truth_size, double* out, int16_t* out_count) {
+  return patchwise_impl(m, vol, vol_dims, halo_pad, fit_pad, pad_value, idx, n, batch, shard_rank, shard_count, -1, truth,
+                        prev_truth_index, prev_truth_size, out, out_count);
+}
+
+extern "C" int fm_patchwise_predict_dp(fm_model* m, const float* vol, const int32_t vol_dims[3],
+                                       const int32_t halo_pad[6], const int32_t fit_pad[6],
+                                       const double pad_value[2], const int32_t* idx, int64_t n, int batch, int root,
+                                       const float* truth, int prev_truth_index, int prev_truth_size, double* out,
+                                       int16_t* out_count) {
+  FM_CHECK(m, FM_EINVAL, "fm_patchwise_predict_dp: NULL model");
+  fm_ctx* ctx = m->ctx;
+  const int ranks = ctx->comm ? ctx->comm_size : 1;
+  FM_CHECK(root >= 0 && root < ranks, FM_EINVAL, "fm_patchwise_predict_dp: root %d of %d ranks", root, ranks);
+  return patchwise_impl(m, vol, vol_dims, halo_pad, fit_pad, pad_value, idx, n, batch, ctx->comm_rank, ranks, root, truth,
+                        prev_truth_index, prev_truth_size, out, out_count);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1601,6 +1646,7 @@ static bool pipeline_enabled() {
 // with whatever the compute stream is still doing for the previous step; the compute stream then takes a device copy
 static int stage_inputs(fm_model* m, const float* x, const float* t, int batch) {
   fm_ctx* ctx = m->ctx;
+  const bool pageable = !is_pinned_host(x) || !is_pinned_host(t);
   if (!m->sums_ready) {
     for (int b = 0; b < 2; ++b) {
       FM_CUDA(cudaEventCreateWithFlags(&m->stage_ready[b], cudaEventDisableTiming));
@@ -1613,10 +1659,31 @@ static int stage_inputs(fm_model* m, const float* x, const float* t, int batch) 
   const int b = (m->stage_idx ^= 1);
   FM_TRY(m->stage_x[b].ensure(nx));
   FM_TRY(m->stage_t[b].ensure(n));
+  if (pageable) {
+    // a caller feeding plain NumPy batches (the reference's generator does): host threads copy them into a pinned
+    // buffer while the GPU still works on the previous step, then the same asynchronous route as pinned inputs
+    if (m->host_stage_floats[b] < nx + n) {
+      if (m->host_stage[b]) {
+        FM_CUDA(cudaEventSynchronize(m->host_stage_done[b]));
+        FM_CUDA(cudaFreeHost(m->host_stage[b]));
+        m->host_stage[b] = nullptr;
+      }
+      FM_CUDA(cudaMallocHost((void**)&m->host_stage[b], (nx + n) * sizeof(float)));
+      m->host_stage_floats[b] = nx + n;
+      if (!m->host_stage_done[b]) FM_CUDA(cudaEventCreateWithFlags(&m->host_stage_done[b], cudaEventDisableTiming));
+    } else {
+      FM_CUDA(cudaEventSynchronize(m->host_stage_done[b]));  // the copies of two steps ago have left the buffer
+    }
+    host_copy(m->host_stage[b], x, nx * sizeof(float));
+    host_copy(m->host_stage[b] + nx, t, n * sizeof(float));
+    x = m->host_stage[b];
+    t = m->host_stage[b] + nx;
+  }
   FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, m->stage_free[b], 0));
   FM_CUDA(cudaMemcpyAsync(m->stage_x[b].p, x, nx * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
   FM_CUDA(cudaMemcpyAsync(m->stage_t[b].p, t, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
   FM_CUDA(cudaEventRecord(m->stage_ready[b], ctx->copy_stream));
+  if (pageable) FM_CUDA(cudaEventRecord(m->host_stage_done[b], ctx->copy_stream));
   FM_CUDA(cudaStreamWaitEvent(ctx->stream, m->stage_ready[b], 0));
   FM_CUDA(cudaMemcpyAsync(m->x_in.p, m->stage_x[b].p, nx * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   FM_CUDA(cudaMemcpyAsync(m->t_in.p, m->stage_t[b].p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1629,7 +1696,7 @@ extern "C" int fm_train_forward(fm_model* m, const float* x, const float* t, int
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_TRY(ensure_capacity(m, batch, true));
   const size_t n = (size_t)batch * m->vox(0);
-  if (pipeline_enabled() && is_pinned_host(x) && is_pinned_host(t)) {
+  if (pipeline_enabled()) {
     FM_TRY(stage_inputs(m, x, t, batch));
     return train_forward_dev(m, batch);
   }
@@ -1746,8 +1813,7 @@ extern "C" int fm_train_step_device(fm_model* m, uint64_t x_dev, uint64_t t_dev,
 extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
                              float out_metrics[4]) {
   FM_CHECK(m && x && t && batch > 0, FM_EINVAL, "fm_train_step: bad argument");
-  if (!pipeline_enabled() || !out_metrics || !is_pinned_host(x) || !is_pinned_host(t)) {
-    // pageable inputs: the runtime stages them synchronously anyway
+  if (!pipeline_enabled() || !out_metrics) {
     FM_TRY(fm_train_forward(m, x, t, batch));
     FM_TRY(fm_train_backward(m));
     return fm_train_apply(m, lr, 0, out_metrics);
@@ -1763,6 +1829,75 @@ extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int ba
   FM_TRY(fm_train_apply(m, lr, 0, nullptr));
   FM_CUDA(cudaEventSynchronize(m->sums_ready));  // the inputs were consumed long before: x / t may be reused
   metrics_from_sums(m->sums_pin, out_metrics);
+  return FM_OK;
+}
+
+extern "C" int fm_train_step_dp(fm_model* m, const float* x, const float* t, int batch, float lr,
+                                float out_metrics[4]) {
+  FM_CHECK(m && x && t && batch > 0 && out_metrics, FM_EINVAL, "fm_train_step_dp: bad argument");
+  fm_ctx* ctx = m->ctx;
+  if (!ctx->comm || ctx->comm_size == 1) return fm_train_step(m, x, t, batch, lr, out_metrics);
+  FM_TRY(fm_train_forward(m, x, t, batch));
+  // 8 float64: the GLOBAL Dice statistics every rank back-propagates (64 bytes; latency only)
+  FM_TRY(comm_allreduce(ctx, m->sums, 8, 1, ctx->stream));
+  FM_TRY(fm_train_metrics_async(m));
+  FM_TRY(fm_train_backward(m));
+  // gradient buckets in completion order (backward runs in reverse creation order): each all-reduce waits only for
+  // the event of the bucket's first layer and overlaps whatever backward still has queued on the compute stream
+  for (size_t b = 0; b < m->buckets.size(); ++b) {
+    const Layer& first = m->layers[m->buckets[b].first];
+    const int last_i = m->buckets[b].second;
+    const int64_t end = last_i + 1 < (int)m->layers.size() ? m->layers[last_i + 1].w_off : m->nparams;
+    FM_CUDA(cudaStreamWaitEvent(ctx->comm_stream, m->layer_done[m->buckets[b].first], 0));
+    FM_TRY(comm_allreduce(ctx, m->grads + first.w_off, (size_t)(end - first.w_off), 0, ctx->comm_stream));
+  }
+  FM_TRY(fm_train_apply(m, lr, (uint64_t)(uintptr_t)ctx->comm_stream, nullptr));
+  return fm_train_metrics_wait(m, out_metrics);
+}
+
+extern "C" int fm_comm_broadcast_params(fm_model* m, int root) {
+  FM_CHECK(m, FM_EINVAL, "fm_comm_broadcast_params: NULL model");
+  fm_ctx* ctx = m->ctx;
+  FM_CUDA(cudaSetDevice(ctx->device));
+  FM_TRY(comm_broadcast(ctx, m->params, (size_t)m->nparams, 0, root, ctx->stream));
+  FM_TRY(comm_broadcast(ctx, m->adam_m, (size_t)m->nparams, 0, root, ctx->stream));
+  FM_TRY(comm_broadcast(ctx, m->adam_v, (size_t)m->nparams, 0, root, ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  m->packs_dirty = true;
+  return FM_OK;
+}
+
+// Adam moments of one layer in Keras layout, and the step counter: what Keras' model.save() keeps besides the weights
+// (the reference resumes with load_old_model(get_last_model_path(...)), fetal/train_fetal.py:25-28)
+extern "C" int fm_model_get_adam_state(fm_model* m, int layer, float* m_kernel, float* m_bias, float* v_kernel,
+                                       float* v_bias) {
+  FM_TRY(get_flat(m, m ? m->adam_m : nullptr, layer, m_kernel, m_bias));
+  return get_flat(m, m ? m->adam_v : nullptr, layer, v_kernel, v_bias);
+}
+static int set_flat(fm_model* m, float* flat, int layer, const float* kernel, const float* bias) {
+  FM_CHECK(m && layer >= 0 && layer < (int)m->layers.size() && kernel && bias, FM_EINVAL, "layer %d out of range", layer);
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  Layer& l = m->layers[layer];
+  FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  if (l.is_norm) {
+    FM_CUDA(cudaMemcpy(flat + l.w_off, kernel, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<float> packed((size_t)l.wcount());
+    keras_to_packed(kernel, packed.data(), l.k, l.cin_keras(), l.cout, l.cin());
+    FM_CUDA(cudaMemcpy(flat + l.w_off, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  }
+  FM_CUDA(cudaMemcpy(flat + l.b_off, bias, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
+  return FM_OK;
+}
+extern "C" int fm_model_set_adam_state(fm_model* m, int layer, const float* m_kernel, const float* m_bias,
+                                       const float* v_kernel, const float* v_bias) {
+  FM_TRY(set_flat(m, m ? m->adam_m : nullptr, layer, m_kernel, m_bias));
+  return set_flat(m, m ? m->adam_v : nullptr, layer, v_kernel, v_bias);
+}
+extern "C" int fm_model_get_iterations(fm_model* m) { return m ? m->iterations : -1; }
+extern "C" int fm_model_set_iterations(fm_model* m, int iterations) {
+  FM_CHECK(m && iterations >= 0, FM_EINVAL, "fm_model_set_iterations: bad argument");
+  m->iterations = iterations;
   return FM_OK;
 }
 

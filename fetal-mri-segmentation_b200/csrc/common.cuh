@@ -65,7 +65,18 @@ struct fm_ctx {
   // pinned staging for host<->device copies
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // data-parallel communicator (comm.cu): ncclComm_t, its side stream (gradient buckets overlap backward) and an event
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  bool comm_enabled = true;  // false: collectives are skipped (bench.py measures the exposed communication time)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev = nullptr;
 };
+
+// comm.cu: in-place SUM collectives on the ctx communicator (no-ops without one); dtype 0 = float32, 1 = float64
+int comm_allreduce(fm_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream);
+int comm_reduce(fm_ctx* ctx, void* buf, size_t count, int dtype, int root, cudaStream_t stream);
+int comm_broadcast(fm_ctx* ctx, void* buf, size_t count, int dtype, int root, cudaStream_t stream);
 
 int fm_ctx_pinned(fm_ctx* ctx, size_t bytes, void** out);
 

@@ -21,6 +21,7 @@ c_fp = ctypes.POINTER(ctypes.c_float)
 c_d = ctypes.c_double
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_i16p = ctypes.POINTER(ctypes.c_int16)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_vp = ctypes.c_void_p
 
 
@@ -85,6 +86,21 @@ SIGNATURES = {
     "fm_train_step_device": (c_int, [c_vp, c_u64, c_u64, c_int, c_f, c_fp]),
     "fm_predict_device": (c_int, [c_vp, c_u64, c_int, c_u64]),
     "fm_evaluate": (c_int, [c_vp, c_fp, c_fp, c_int, c_fp]),
+    "fm_model_get_adam_state": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp, c_fp]),
+    "fm_model_set_adam_state": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp, c_fp]),
+    "fm_model_get_iterations": (c_int, [c_vp]),
+    "fm_model_set_iterations": (c_int, [c_vp, c_int]),
+    "fm_comm_unique_id": (c_int, [c_u8p]),
+    "fm_comm_init": (c_int, [c_vp, c_int, c_int, c_u8p]),
+    "fm_comm_destroy": (c_int, [c_vp]),
+    "fm_comm_info": (c_int, [c_vp, ctypes.POINTER(c_int)]),
+    "fm_comm_enable": (c_int, [c_vp, c_int]),
+    "fm_comm_stream": (c_u64, [c_vp]),
+    "fm_comm_allreduce_bench": (c_int, [c_vp, c_i64, c_int, c_fp]),
+    "fm_comm_broadcast_params": (c_int, [c_vp, c_int]),
+    "fm_train_step_dp": (c_int, [c_vp, c_fp, c_fp, c_int, c_f, c_fp]),
+    "fm_patchwise_predict_dp": (c_int, [c_vp, c_fp, c_i32p, c_i32p, c_i32p, c_dp, c_i32p, c_i64, c_int,
+                                        c_int, c_fp, c_int, c_int, c_dp, c_i16p]),
     "fm_op_conv3d_fprop": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp, c_fp] + [c_int] * 9 + [c_fp]),
     "fm_op_conv3d_dgrad": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "fm_op_conv3d_wgrad": (c_int, [c_vp, c_int, c_fp, c_fp] + [c_int] * 6 + [c_fp, c_fp]),
@@ -192,6 +208,12 @@ class Context:
     def device_info(self):
         out = (c_int * 3)()
         check(load().fm_ctx_device_info(self.handle, out))
+        return tuple(out)
+
+    def comm_info(self):
+        """(rank, ranks, NCCL version code) of the native data-parallel communicator (ranks = 1 without one)."""
+        out = (c_int * 3)()
+        check(load().fm_comm_info(self.handle, out))
         return tuple(out)
 
 

@@ -1,17 +1,21 @@
 """Data-parallel extension of the hot path (the reference is single-process: training.py:115-117).
 
-One process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch) as plumbing:
+One process per GPU. The collectives run on raw NCCL inside libfetalb200 (csrc/comm.cu: fm_comm_init,
+fm_train_step_dp, fm_patchwise_predict_dp) - no device pointer leaves the library. `torch.distributed` (any backend,
+gloo is enough) is only the CONTROL plane: it carries the 128-byte NCCL id from rank 0 to the other ranks.
 
   training   batch sharded over ranks, weights replicated. Soft Dice is a WHOLE-batch statistic
              (metrics.py:11-15 flattens the batch axis), so the forward all-reduces the 8 loss sums and
              every rank back-propagates the global Dice; the gradient of that one global scalar is the
              SUM (not the mean) of the ranks' local gradients. The flat fp32 gradient buffer is
-             all-reduced bucket by bucket on a side stream while the rest of backward still runs
-             (fm_stream_wait_bucket), then every rank applies the identical Adam step.
+             all-reduced bucket by bucket on a side stream while the rest of backward still runs,
+             then every rank applies the identical Adam step.
   inference  the patch list of patch_wise_prediction is split contiguously over ranks; each rank
-             overlap-adds its patches into a private float64 partial sum, one reduce, then sum / count.
-             Counts are analytic (identical on every rank) and never communicated.
+             overlap-adds its patches into a private float64 partial sum on its GPU, one ncclReduce, then
+             sum / count on the root. Counts are analytic (identical on every rank) and never communicated.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -22,86 +26,94 @@ def shard_range(n, rank, count):
     return n * rank // count, n * (rank + 1) // count
 
 
-class _DevPtr:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr=typestr, data=(int(ptr), False), version=2)
-
-
-def _wrap(ptr, n, typestr, device):
-    import torch
-    return torch.as_tensor(_DevPtr(ptr, n, typestr), device="cuda:%d" % device)
+def init_comm(ctx=None, rank=None, world=None):
+    """Creates the native NCCL communicator of `ctx` (idempotent). The id travels through the default
+    torch.distributed process group when one is initialised, otherwise through a TCPStore on
+    MASTER_ADDR:MASTER_PORT+1 (env, as set by torchrun). Returns (rank, world)."""
+    import torch.distributed as dist
+    ctx = ctx or _lib.get_context()
+    lib = _lib.load()
+    r, w, _ = ctx.comm_info()
+    if w > 1:
+        return r, w
+    if dist.is_available() and dist.is_initialized():
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+    else:
+        rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+        world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    if world == 1:
+        return 0, 1
+    uid = np.zeros(128, np.uint8)
+    if rank == 0:
+        _lib.check(lib.fm_comm_unique_id(uid.ctypes.data_as(_lib.c_u8p)))
+    if dist.is_available() and dist.is_initialized():
+        box = [uid.tobytes()]
+        dist.broadcast_object_list(box, src=0)
+        uid = np.frombuffer(box[0], np.uint8).copy()
+    else:
+        store = dist.TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ["MASTER_PORT"]) + 1, world,
+                              is_master=(rank == 0))
+        if rank == 0:
+            store.set("fetal_b200_nccl_uid", uid.tobytes())
+        uid = np.frombuffer(store.get("fetal_b200_nccl_uid"), np.uint8).copy()
+    _lib.check(lib.fm_comm_init(ctx.handle, int(rank), int(world), uid.ctypes.data_as(_lib.c_u8p)))
+    return rank, world
 
 
 class DataParallelTrainer:
-    """Wraps a native Model for multi-GPU training (call after torch.distributed.init_process_group)."""
+    """Wraps a native Model for multi-GPU training: `train_on_batch` on this rank's shard of the global batch."""
 
     def __init__(self, model, overlap=True):
-        import ctypes
-        import torch
-        import torch.distributed as dist
-        self.torch, self.dist = torch, dist
         self.model = model
         self.lib = _lib.load()
+        self.ctx = model._ctx
         self.device = model._ctx.device
-        self.overlap = overlap
-        p, n = _lib.c_u64(0), _lib.c_i64(0)
-        _lib.check(self.lib.fm_model_grad_buffer(model._h, ctypes.byref(p), ctypes.byref(n)))
-        self.grads = _wrap(p.value, n.value, "<f4", self.device)
-        _lib.check(self.lib.fm_model_loss_sums(model._h, ctypes.byref(p)))
-        self.sums = _wrap(p.value, 8, "<f8", self.device)
-        self.buckets = []
-        for b in range(self.lib.fm_model_num_buckets(model._h)):
-            off, cnt = _lib.c_i64(0), _lib.c_i64(0)
-            _lib.check(self.lib.fm_model_bucket_range(model._h, b, ctypes.byref(off), ctypes.byref(cnt)))
-            self.buckets.append((off.value, cnt.value))
-        self.compute_stream = torch.cuda.ExternalStream(model._ctx.stream, device="cuda:%d" % self.device)
-        self.comm_stream = torch.cuda.Stream(device="cuda:%d" % self.device)
+        self.rank, self.world = init_comm(self.ctx)
 
     def broadcast_weights(self, src=0):
-        ws = self.model.get_weights()
-        t = [self.torch.as_tensor(w).cuda(self.device) for w in ws]
-        for x in t:
-            self.dist.broadcast(x, src)
-        self.model.set_weights([x.cpu().numpy() for x in t])
+        """Rank `src`'s weights and Adam state to every replica."""
+        _lib.check(self.lib.fm_comm_broadcast_params(self.model._h, int(src)))
 
     def train_on_batch(self, x, y):
         """x, y: this rank's shard of the global batch. Returns the GLOBAL [loss, acc, vod]."""
-        torch, dist, lib, h = self.torch, self.dist, self.lib, self.model._h
         x, y = _lib.f32c(x), _lib.f32c(y)
-        _lib.check(lib.fm_train_forward(h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0])))
-        with torch.cuda.stream(self.compute_stream):
-            dist.all_reduce(self.sums)                                   # 8 doubles: global Dice statistics
-        _lib.check(lib.fm_train_metrics_async(h))                        # global statistics -> pinned host, async
-        _lib.check(lib.fm_train_backward(h))
-        # buckets complete in order 0,1,2,... (backward runs in reverse layer order)
-        with torch.cuda.stream(self.comm_stream if self.overlap else self.compute_stream):
-            for b, (off, cnt) in enumerate(self.buckets):
-                if self.overlap:
-                    _lib.check(lib.fm_stream_wait_bucket(h, self.comm_stream.cuda_stream, b))
-                dist.all_reduce(self.grads[off:off + cnt])               # SUM: one global loss scalar
         m = np.zeros(4, np.float32)
-        _lib.check(lib.fm_train_apply(h, float(self.model.optimizer.lr),
-                                      self.comm_stream.cuda_stream if self.overlap else 0, None))
-        # returns once the statistics are on the host; backward / all-reduce / Adam keep running, ordered before any
-        # later call on the model, and the next step's upload (pinned inputs) overlaps them
-        _lib.check(lib.fm_train_metrics_wait(h, _lib.fptr(m)))
+        _lib.check(self.lib.fm_train_step_dp(self.model._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]),
+                                             float(self.model.optimizer.lr), _lib.fptr(m)))
         return [float(v) for v in m[:len(self.model.metrics_names)]]
+
+    def allreduce_bench(self, nbytes, iters=20):
+        """(ms per all-reduce, bus GB/s = 2 (n-1)/n * bytes / t) of an in-place fp32 SUM all-reduce of `nbytes`."""
+        ms = np.zeros(1, np.float32)
+        _lib.check(self.lib.fm_comm_allreduce_bench(self.ctx.handle, int(nbytes), int(iters), _lib.fptr(ms)))
+        t = float(ms[0]) * 1e-3
+        return float(ms[0]), 2.0 * (self.world - 1) / self.world * nbytes / t / 1e9
+
+    def set_comm_enabled(self, on):
+        _lib.check(self.lib.fm_comm_enable(self.ctx.handle, 1 if on else 0))
 
 
 def sharded_patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size=5, dst=0):
-    """patch_wise_prediction with the patch list sharded over the ranks of the default process group.
-    Returns the float64 [X,Y,Z,C] volume on rank `dst` (None elsewhere)."""
+    """patch_wise_prediction with the patch list sharded over the ranks. Returns the float64 [X,Y,Z,C] volume on
+    rank `dst` (None elsewhere). Native models reduce the partial sums on the GPUs (fm_patchwise_predict_dp); any
+    other Keras-like model goes through torch.distributed (used by the gloo tests on CPU)."""
+    from .prediction import patch_wise_prediction
+    if hasattr(model, "_h"):
+        rank, count = init_comm(model._ctx)
+        if count == 1:
+            return patch_wise_prediction(model, data, patch_shape, overlap_factor, batch_size)
+        return patch_wise_prediction(model, data, patch_shape, overlap_factor, batch_size, shard=(rank, count),
+                                     reduce_root=dst)
     import torch
     import torch.distributed as dist
-    from .prediction import patch_wise_prediction
     rank, count = dist.get_rank(), dist.get_world_size()
     if count == 1:
         return patch_wise_prediction(model, data, patch_shape, overlap_factor, batch_size)
     part, cnt = patch_wise_prediction(model, data, patch_shape, overlap_factor, batch_size, shard=(rank, count))
-    dev = "cuda:%d" % model._ctx.device if dist.get_backend() == "nccl" else "cpu"
-    t = torch.as_tensor(part).to(dev)
+    t = torch.as_tensor(part)
     dist.reduce(t, dst)                                                  # float64 partial sums
     if rank != dst:
         return None
     assert np.all(cnt > 0), 'Found zeros in count'
-    return t.cpu().numpy() / cnt[..., None]
+    return t.numpy() / cnt[..., None]

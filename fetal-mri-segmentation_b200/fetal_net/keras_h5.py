@@ -12,8 +12,12 @@ Layout read (Keras 2.x): a weights file has the layer groups at the root, a full
 `model_weights/`; the group attribute `layer_names` gives the layer order, each layer group's `weight_names` its
 arrays (`<layer>/kernel:0`, `<layer>/bias:0`; `gamma:0` / `beta:0` for keras_contrib InstanceNormalization).
 Keras numbers auto-named layers per session (`conv3d_7` ...), so layers are matched to ours BY ORDER, not by name:
-convolutions (kernel + bias) and normalisations (gamma + beta) in the order Keras created them, which is the order
-of this package's layer table."""
+convolutions (kernel + bias) and normalisations (gamma + beta) in the order Keras CREATED them, which is the order
+of this package's layer table. The file's `layer_names` attribute is `model.layers`, which Keras sorts by graph depth,
+not by creation (for isensee2017 with n_segmentation_levels >= 2 the coarse Conv3D(n_labels, 1) heads come after
+later-created decoder convs) - so each kind is re-sorted by the numeric suffix of its auto-name (conv3d_7 < conv3d_12),
+which is the true creation order."""
+import re
 import numpy as np
 
 HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
@@ -28,9 +32,24 @@ def _as_str(v):
     return v.decode("utf8") if isinstance(v, bytes) else str(v)
 
 
+def _auto_index(layer_name):
+    """'conv3d_12' -> 12, 'conv3d' (TF-Keras names the first one without a suffix) -> 0."""
+    m = re.search(r"_(\d+)$", layer_name)
+    return int(m.group(1)) if m else 0
+
+
+def creation_order(entries):
+    """Re-sorts (kind, layer_name, first, second) entries so that, within each kind, layers follow the numeric
+    suffix of their Keras auto-name = the order the builder created them in. The relative interleaving of kinds is
+    irrelevant (to_npz_arrays numbers convolutions and normalisations separately)."""
+    convs = sorted((e for e in entries if e[0] == "conv"), key=lambda e: _auto_index(e[1]))
+    norms = sorted((e for e in entries if e[0] == "norm"), key=lambda e: _auto_index(e[1]))
+    return convs + norms
+
+
 def read_keras_h5_weights(path):
-    """-> list of (kind, first, second) in Keras creation order; kind 'conv' (kernel, bias) or 'norm' (gamma, beta).
-    Kernels are returned in Keras layout (k, k[, k], Cin, Cout), exactly what fm_model_set_weights takes."""
+    """-> list of (kind, layer_name, first, second) in Keras CREATION order; kind 'conv' (kernel, bias) or 'norm'
+    (gamma, beta). Kernels are returned in Keras layout (k, k[, k], Cin, Cout), exactly what fm_model_set_weights takes."""
     try:
         import h5py
     except ImportError as e:  # pragma: no cover - h5py is absent in the build image
@@ -44,17 +63,18 @@ def read_keras_h5_weights(path):
             arrays = {n.split("/")[-1].split(":")[0]: np.asarray(g[lname][n]) for n in names}
             if "kernel" in arrays:
                 bias = arrays.get("bias", np.zeros(arrays["kernel"].shape[-1], np.float32))
-                out.append(("conv", arrays["kernel"].astype(np.float32), bias.astype(np.float32)))
+                out.append(("conv", lname, arrays["kernel"].astype(np.float32), bias.astype(np.float32)))
             elif "gamma" in arrays and "beta" in arrays:
-                out.append(("norm", arrays["gamma"].astype(np.float32), arrays["beta"].astype(np.float32)))
-    return out
+                out.append(("norm", lname, arrays["gamma"].astype(np.float32), arrays["beta"].astype(np.float32)))
+    return creation_order(out)
 
 
 def to_npz_arrays(entries):
     """The same weights keyed the way Model.save_weights / load_weights key their .npz (layers renumbered from 1 in
     creation order: conv3d_1/kernel:0, conv3d_1/bias:0, instance_normalization_1/gamma:0, ...)."""
     arrays, n_conv, n_norm = {}, 0, 0
-    for kind, a, b in entries:
+    for e in entries:
+        kind, a, b = e[0], e[-2], e[-1]                     # (kind, a, b) or (kind, layer_name, a, b)
         if kind == "conv":
             n_conv += 1
             prefix = "conv%dd_%d" % (a.ndim - 2, n_conv)

@@ -147,8 +147,7 @@ class Model:
             ws.append(np.zeros((l["cout"],), np.float32))
         self.set_weights(ws)
 
-    def save_weights(self, path):
-        """HDF5 is absent in this image (SURVEY.md §5): weights go to an .npz keyed by Keras layer names."""
+    def _weight_arrays(self):
         arrays = {}
         for l, (k, b) in zip(self.layers, zip(*[iter(self.get_weights())] * 2)):
             arrays[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")] = k
@@ -157,10 +156,64 @@ class Model:
         # builder name + its extra arguments, so that load_old_model can rebuild the right family
         arrays["__builder__"] = np.array(getattr(self, "name", "unet_model_3d"))
         arrays["__isensee_levels__"] = np.array(int(getattr(self, "isensee_levels", 0) or 0))
+        return arrays
+
+    def save_weights(self, path):
+        """HDF5 is absent in this image (SURVEY.md §5): weights go to an .npz keyed by Keras layer names."""
         with open(path, "wb") as f:   # keep the caller's file name (e.g. '...-epoch01-loss-0.5.h5')
+            np.savez(f, **self._weight_arrays())
+
+    def get_optimizer_state(self):
+        """(iterations, lr, [m_kernel, m_bias, v_kernel, v_bias] per layer in Keras layout) - what Keras'
+        model.save() stores besides the weights."""
+        moments = []
+        for l in self.layers:
+            mk, vk = np.empty(l["kshape"], np.float32), np.empty(l["kshape"], np.float32)
+            mb, vb = np.empty((l["cout"],), np.float32), np.empty((l["cout"],), np.float32)
+            _lib.check(self._lib.fm_model_get_adam_state(self._h, l["index"], _lib.fptr(mk), _lib.fptr(mb),
+                                                         _lib.fptr(vk), _lib.fptr(vb)))
+            moments.append((mk, mb, vk, vb))
+        return int(self._lib.fm_model_get_iterations(self._h)), float(self.optimizer.lr), moments
+
+    def set_optimizer_state(self, iterations, lr, moments):
+        assert len(moments) == len(self.layers)
+        for l, (mk, mb, vk, vb) in zip(self.layers, moments):
+            mk, mb, vk, vb = (_lib.f32c(a) for a in (mk, mb, vk, vb))
+            assert mk.shape == l["kshape"] == vk.shape and mb.shape == (l["cout"],) == vb.shape, l["name"]
+            _lib.check(self._lib.fm_model_set_adam_state(self._h, l["index"], _lib.fptr(mk), _lib.fptr(mb),
+                                                         _lib.fptr(vk), _lib.fptr(vb)))
+        _lib.check(self._lib.fm_model_set_iterations(self._h, int(iterations)))
+        self.optimizer.lr = float(lr)
+
+    def save(self, path):
+        """Keras' model.save(): weights AND optimizer state (Adam moments, iteration count, the current - possibly
+        plateau-reduced - learning rate), so that load_old_model(...) + train_model(...) resumes like the reference's
+        load_model() path (fetal/train_fetal.py:25-28, fetal_net/training.py:45-65). save_weights stays weights-only."""
+        arrays = self._weight_arrays()
+        it, lr, moments = self.get_optimizer_state()
+        arrays["__iterations__"] = np.array(it)
+        arrays["__lr__"] = np.array(lr)
+        for l, (mk, mb, vk, vb) in zip(self.layers, moments):
+            arrays["__adam_m__/" + l["keras_name"] + "/kernel"] = mk
+            arrays["__adam_m__/" + l["keras_name"] + "/bias"] = mb
+            arrays["__adam_v__/" + l["keras_name"] + "/kernel"] = vk
+            arrays["__adam_v__/" + l["keras_name"] + "/bias"] = vb
+        with open(path, "wb") as f:
             np.savez(f, **arrays)
 
-    save = save_weights
+    def load_optimizer_state(self, path):
+        """Restores what save() wrote; returns False for a weights-only file (the optimizer then starts fresh)."""
+        from .. import keras_h5
+        if keras_h5.is_hdf5(path):
+            return False
+        with np.load(path) as z:
+            if "__iterations__" not in z.files:
+                return False
+            moments = [tuple(np.asarray(z["__adam_%s__/%s/%s" % (mv, l["keras_name"], kb)])
+                             for mv, kb in (("m", "kernel"), ("m", "bias"), ("v", "kernel"), ("v", "bias")))
+                       for l in self.layers]
+            self.set_optimizer_state(int(z["__iterations__"]), float(z["__lr__"]), moments)
+        return True
 
     def load_weights(self, path):
         """Reads the .npz written by save_weights (whatever the file is called), or - where h5py is installed - a

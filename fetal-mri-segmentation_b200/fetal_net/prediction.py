@@ -85,10 +85,12 @@ def _crop_fit(arr, fit):
 
 def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size=5,
                           permute=False, truth_data=None, prev_truth_index=None, prev_truth_size=None,
-                          shard=None):
+                          shard=None, reduce_root=None):
     """Drop-in for fetal_net/prediction.py:118-210. `shard=(rank, count)` (extension) makes this call
     process only its contiguous share of the patch list and return (partial float64 sums, int16 counts)
-    for the caller to reduce — see fetal_net.distributed.sharded_patch_wise_prediction."""
+    for the caller to reduce; with `reduce_root` (native models, ranks = the library's NCCL communicator) the partial
+    sums are reduced on the GPUs and the call returns the finished volume on that rank and None elsewhere — see
+    fetal_net.distributed.sharded_patch_wise_prediction."""
     lib = _lib.load()
     data = np.asarray(data)
     assert data.ndim == 4 and data.shape[0] == 1, "data must be [1,X,Y,Z] (prediction.py:296)"
@@ -127,6 +129,18 @@ def patch_wise_prediction(model, data, patch_shape, overlap_factor=0, batch_size
             if truth_data is not None:
                 truth = _lib.f32c(np.asarray(truth_data)[0])
                 assert truth.shape == vol.shape
+        if reduce_root is not None and count > 1:
+            is_root = rank == int(reduce_root)
+            _lib.check(lib.fm_patchwise_predict_dp(model._h, _lib.fptr(vol), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
+                                                   _lib.i32ptr(fit), _lib.dptr(padv), _lib.i32ptr(idx), len(idx),
+                                                   int(batch_size), int(reduce_root), _lib.fptr(truth),
+                                                   int(prev_truth_index or 0), int(prev_truth_size or 0),
+                                                   _lib.dptr(out) if is_root else None, None))
+            if not is_root:
+                return None
+            out = _crop_fit(out, g["fit"])
+            assert np.array_equal(out.shape[:-1], data[0].shape), 'prediction shape wrong'
+            return out
         _lib.check(lib.fm_patchwise_predict(model._h, _lib.fptr(vol), _lib.i32ptr(vol_dims), _lib.i32ptr(halo),
                                             _lib.i32ptr(fit), _lib.dptr(padv), _lib.i32ptr(idx), len(idx),
                                             int(batch_size), rank, count, _lib.fptr(truth),
@@ -258,7 +272,10 @@ def predict_with_permutations(model, data):
     keys = list(generate_permutation_keys())
     permuted = [permute_data(data, k) for k in keys]
     if all(p.shape == permuted[0].shape for p in permuted):
-        outs = np.asarray(model.predict(np.ascontiguousarray(np.stack(permuted))))
+        stack = np.ascontiguousarray(np.stack(permuted))
+        # native model: 8 patches per launch, so the activation workspace is sized for 8 (not 32) full patches - the
+        # reference runs one patch at a time and never holds more
+        outs = np.asarray(model.predict(stack, batch_size=8) if isinstance(model, Model) else model.predict(stack))
         predictions = [reverse_permute_data(outs[i], k) for i, k in enumerate(keys)]
     else:
         predictions = [reverse_permute_data(model.predict(np.ascontiguousarray(p[np.newaxis]))[0], k)

@@ -148,6 +148,21 @@ def load_old_model(model_file, verbose=True, config=None):
     the builder arguments, so the model is rebuilt from the stored config (or from `config`)."""
     if verbose:
         print("Loading pre-trained model")
+    from . import keras_h5
+    if keras_h5.is_hdf5(model_file):
+        # a genuine Keras .h5 of the reference: the architecture comes from the config (the reference's manual-build
+        # fallback, training.py:72-84), the weights through the h5py bridge
+        if config is None:
+            raise ValueError("load_old_model(%r): a Keras HDF5 checkpoint needs `config` (model_name, input_shape) to "
+                             "rebuild the architecture" % (model_file,))
+        loss = getattr(_metrics, config.get('loss', 'dice_coefficient_loss'))
+        m = getattr(_model_ns, config['model_name'])(input_shape=config['input_shape'],
+                                                     initial_learning_rate=config.get('initial_learning_rate', 1e-5),
+                                                     loss_function=loss,
+                                                     **({'dropout_rate': config['dropout_rate']}
+                                                        if 'dropout_rate' in config else {}))
+        m.load_weights(model_file)
+        return m
     with np.load(model_file) as z:
         cfg = [int(v) for v in z["__config__"]]
         builder_name = str(z["__builder__"]) if "__builder__" in z.files else None
@@ -167,6 +182,9 @@ def load_old_model(model_file, verbose=True, config=None):
             kwargs['dropout_rate'] = config['dropout_rate']
     m = getattr(_model_ns, builder_name)(**kwargs)
     m.load_weights(model_file)
+    # Keras' load_model also restores the optimizer (Adam moments, iterations, the current learning rate): a resumed
+    # run continues where the checkpoint stopped. Weights-only archives start a fresh optimizer.
+    m.load_optimizer_state(model_file)
     return m
 
 

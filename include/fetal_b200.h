@@ -32,6 +32,7 @@ extern "C" {
 #define FM_ECUDA (-2)    /* CUDA runtime or driver error                */
 #define FM_ENOMEM (-3)   /* device or host allocation failed            */
 #define FM_ESTATE (-4)   /* call order violated (e.g. backward w/o fwd) */
+#define FM_ECOMM (-5)    /* NCCL error / libnccl not loadable           */
 
 typedef struct fm_ctx fm_ctx;
 typedef struct fm_model fm_model;
@@ -122,6 +123,14 @@ int fm_model_get_weights(fm_model* m, int layer, float* kernel, float* bias);
 int fm_model_get_grads(fm_model* m, int layer, float* kernel, float* bias);
 /* Resets Adam moments and the iteration counter (a fresh model.compile). */
 int fm_model_reset_optimizer(fm_model* m);
+/* Optimizer state of one layer, Keras layout like the weights: Adam first / second moments (kernel, bias) and the step
+ * counter. Replaces the optimizer part of Keras' model.save() / load_model() that the reference's resume path relies on
+ * (load_old_model(get_last_model_path(...)), fetal/train_fetal.py:25-28, fetal_net/training.py:45-65). */
+int fm_model_get_adam_state(fm_model* m, int layer, float* m_kernel, float* m_bias, float* v_kernel, float* v_bias);
+int fm_model_set_adam_state(fm_model* m, int layer, const float* m_kernel, const float* m_bias, const float* v_kernel,
+                            const float* v_bias);
+int fm_model_get_iterations(fm_model* m);
+int fm_model_set_iterations(fm_model* m, int iterations);
 /* Replaces: the `dropout_rate` kwarg of isensee2017_model_3d -> SpatialDropout3D(rate) between the two convs of
  * every context module (fetal_net/model/unet3d/isensee2017.py:15,51,103-105). Active in training passes only
  * (fm_train_*), one keep/scale factor per (sample, channel) drawn from a counter-based hash of (seed, step, level);
@@ -185,7 +194,9 @@ int fm_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
  * on a copy stream and the call returns as soon as the Dice statistics of THIS step's forward pass are on the host;
  * backward, Adam and the weight repack keep running and are stream-ordered before every later call on the model
  * (predict, get_weights, the next step), whose upload then overlaps them. x / t may be reused when the call returns.
- * Pageable buffers (or FETAL_B200_NO_PIPELINE=1) take the fully synchronous route. */
+ * Pageable buffers (plain NumPy batches, what the reference's generator yields) are first copied by a few host threads
+ * into pinned ping-pong buffers owned by the model and then take the same route; FETAL_B200_NO_PIPELINE=1 selects the
+ * fully synchronous route. */
 int fm_train_step(fm_model* m, const float* x, const float* t, int batch, float lr,
                   float out_metrics[4]);
 
@@ -221,6 +232,45 @@ int fm_predict_device(fm_model* m, uint64_t x_dev, int batch, uint64_t y_dev);
 
 /* Replaces: model.evaluate / test_on_batch (validation loop of fit_generator). */
 int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]);
+
+/* ---- data parallelism (one process per GPU; NCCL over NVLink 5 / NVSwitch) -----------------------------------
+ * The reference is single-process (fetal_net/training.py:115-117: workers=1, use_multiprocessing=False); these entry
+ * points are the multi-GPU extension of the same two calls (train_on_batch, patch_wise_prediction). libnccl.so.2 is
+ * resolved with dlopen at the first call (FETAL_B200_NCCL_LIB overrides the name). The 128-byte id is created on one
+ * rank and carried to the others by the host program (torch.distributed store, MPI, a file ...). */
+#define FM_COMM_UID_BYTES 128
+int fm_comm_unique_id(uint8_t out[FM_COMM_UID_BYTES]);
+int fm_comm_init(fm_ctx* ctx, int rank, int nranks, const uint8_t uid[FM_COMM_UID_BYTES]);
+int fm_comm_destroy(fm_ctx* ctx);
+/* out[0] = rank, out[1] = ranks (1 without a communicator), out[2] = NCCL version code. */
+int fm_comm_info(fm_ctx* ctx, int out[3]);
+/* on = 0 turns every collective of this ctx into a no-op (bench.py measures the EXPOSED communication time of a
+ * step as the difference; results are then meaningless). */
+int fm_comm_enable(fm_ctx* ctx, int on);
+/* cudaStream_t of the gradient all-reduces (integer handle, for event timing). */
+uint64_t fm_comm_stream(fm_ctx* ctx);
+/* Average duration of `iters` in-place fp32 SUM all-reduces of `bytes` on the communication stream. */
+int fm_comm_allreduce_bench(fm_ctx* ctx, int64_t bytes, int iters, float* ms_per_iter);
+/* Copies rank `root`'s parameters (and Adam state) to every rank: the replicas start identical. */
+int fm_comm_broadcast_params(fm_model* m, int root);
+
+/* Replaces: model.train_on_batch(x, y) on THIS rank's shard of the global batch. Forward; all-reduce of the 8 Dice
+ * sums so that every rank back-propagates the GLOBAL soft Dice (fetal_net/metrics.py:11-15 flattens the batch axis);
+ * backward; SUM all-reduce of the flat fp32 gradient buffer in fm_model_num_buckets() contiguous buckets on the
+ * communication stream, each as soon as its last layer's gradients are final (overlapping the rest of backward);
+ * the identical Keras-Adam step on every rank. out_metrics are the GLOBAL loss / accuracy / VOD / Dice. With pinned
+ * x / t the call returns when the statistics are on the host (like fm_train_step). Without a communicator it is
+ * fm_train_step. */
+int fm_train_step_dp(fm_model* m, const float* x, const float* t, int batch, float lr, float out_metrics[4]);
+
+/* fm_patchwise_predict with the patch list sharded contiguously over the ranks of the ctx communicator: every rank
+ * overlap-adds its patches into a private float64 partial sum on its GPU, one ncclReduce to `root`, which divides by
+ * the (analytic, never communicated) counts and copies the result to `out`; `out` / `out_count` are ignored on the
+ * other ranks (may be NULL). */
+int fm_patchwise_predict_dp(fm_model* m, const float* vol, const int32_t vol_dims[3], const int32_t halo_pad[6],
+                            const int32_t fit_pad[6], const double pad_value[2], const int32_t* idx, int64_t n,
+                            int batch, int root, const float* truth, int prev_truth_index, int prev_truth_size,
+                            double* out, int16_t* out_count);
 
 /* ---- per-op hooks (parity tests call the kernels one at a time through these) --------------
  * All pointers are HOST pointers; tensors are channels-last (NDHWC) fp32 on the host and are

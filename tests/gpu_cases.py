@@ -105,6 +105,21 @@ def conv_fprop_case(ctx, impl, case, seed=0):
     return close_bf16(y, cf_to_cl(ref))
 
 
+def conv_fprop_raw(ctx, impl, case, seed=0):
+    """The raw output of one fprop launch (for run-to-run bit-reproducibility checks)."""
+    name, N, X, Y, Z, C1, C2, Cout, k = case
+    rng = np.random.default_rng(seed)
+    x1 = bf16_round(rng.standard_normal((N, X, Y, Z, C1)))
+    x2 = bf16_round(rng.standard_normal((N, X, Y, Z, C2))) if C2 else None
+    w = bf16_round(rng.standard_normal((k, k, k, C1 + C2, Cout)) / np.sqrt(k ** 3 * (C1 + C2)))
+    b = rng.standard_normal(Cout).astype(np.float32)
+    y = np.empty((N, X, Y, Z, Cout), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_fprop(ctx.handle, impl, _lib.fptr(x1), _lib.fptr(x2), _lib.fptr(w), _lib.fptr(b),
+                                      N, X, Y, Z, C1, C2, Cout, k, 1, _lib.fptr(y)))
+    return y
+
+
 def conv_dgrad_case(ctx, impl, case, seed=1):
     name, N, X, Y, Z, C1, C2, Cout, k = case
     Cin = C1  # single source

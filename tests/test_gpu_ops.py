@@ -1,4 +1,5 @@
 """Per-kernel parity on the GPU, through the C ABI (see tests/gpu_cases.py for the stated tolerance)."""
+import numpy as np
 import pytest
 
 from tests import gpu_cases as gc
@@ -48,6 +49,16 @@ MSINGLE = [c for c in gc.MARCH_CASES if c[6] == 0]
 def test_conv3d_fprop_march(ctx, case, impl):
     ok, worst = gc.conv_fprop_case(ctx, impl, case)
     assert ok, "worst error / tolerance = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", [gc.MARCH_CASES[1], gc.MARCH_CASES[4], gc.MARCH_CASES[7]],
+                         ids=[gc.MARCH_CASES[i][0] for i in (1, 4, 7)])
+def test_conv3d_march_bit_reproducible(ctx, case):
+    """impl 2 is the kernel behind predict / evaluate / patch_wise_prediction: three issuing warps take turns plane by
+    plane under a token, so the fp32 summation order is fixed - the output must be identical run to run."""
+    first = gc.conv_fprop_raw(ctx, 2, case)
+    for _ in range(4):
+        assert np.array_equal(gc.conv_fprop_raw(ctx, 2, case), first)
 
 
 @pytest.mark.parametrize("case", MSINGLE, ids=[c[0] for c in MSINGLE])

@@ -236,6 +236,30 @@ def test_keras_h5_bridge_host_parts(tmp_path):
             keras_h5.read_keras_h5_weights(str(fake))
 
 
+def test_keras_h5_creation_order_for_isensee_heads():
+    """Keras writes `layer_names` in model.layers order (sorted by graph depth): for isensee2017 with 2 segmentation
+    levels the level-1 head Conv3D(n_labels, 1) (created right after u1_loc2) is listed after the later-created level-0
+    decoder convs. The bridge must restore creation order from the auto-name suffixes so kernels line up with our table."""
+    from fetal_net import keras_h5
+    from oracle import unet_oracle as uo
+    layers = uo.isensee3d_layers(3, 16, 2)                   # creation order: (..., u1_loc2, u1_seg, u0_up, ...)
+    names = [n for n, *_ in layers]
+    assert names.index("u1_seg") < names.index("u0_up")
+    entries = []
+    for i, (name, cin, cout, k) in enumerate(layers, start=1):
+        entries.append(("conv", "conv3d_%d" % i, np.full((k, k, k, cin, cout), float(i), np.float32),
+                        np.zeros(cout, np.float32)))
+    # depth-sorted file order: the coarse head moves behind the level-0 decoder convs; 'conv3d_10' < 'conv3d_9' lexically
+    seg = entries.pop(names.index("u1_seg"))
+    entries.insert(len(entries) - 1, seg)
+    shuffled = [e[1] for e in entries]
+    assert shuffled != ["conv3d_%d" % i for i in range(1, len(layers) + 1)]
+    arrays = keras_h5.to_npz_arrays(keras_h5.creation_order(entries))
+    for i, (name, cin, cout, k) in enumerate(layers, start=1):
+        kern = arrays["conv3d_%d/kernel:0" % i]
+        assert kern.shape == (k, k, k, cin, cout) and float(kern.flat[0]) == float(i), (i, name)
+
+
 def test_checkpoint_npz_roundtrip_logic(tmp_path):
     """Model.save_weights / load_weights without a device: the .npz is keyed by Keras layer names, kernel layout
     untouched, file name kept as given (ModelCheckpoint writes '...-epochNN-....h5')."""
@@ -246,11 +270,19 @@ def test_checkpoint_npz_roundtrip_logic(tmp_path):
                   dict(keras_name="conv3d_2", is_norm=False)]
         input_shape, depth, n_base_filters, n_labels = (None, 1, 8, 8, 8), 2, 16, 1
         _weights_from_mapping = Model._weights_from_mapping
+        _weight_arrays = Model._weight_arrays
+        load_optimizer_state = Model.load_optimizer_state
+
+        class optimizer:
+            lr = 3e-4
 
         def __init__(self):
             rng = np.random.default_rng(0)
-            self.w = [rng.standard_normal(s).astype(np.float32) for s in
-                      [(3, 3, 3, 1, 16), (16,), (16,), (16,), (3, 3, 3, 16, 1), (1,)]]
+            shapes = [(3, 3, 3, 1, 16), (16,), (16,), (16,), (3, 3, 3, 16, 1), (1,)]
+            self.w = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+            self.moments = [tuple(rng.standard_normal(s).astype(np.float32) for s in (k, b, k, b))
+                            for k, b in zip(shapes[0::2], shapes[1::2])]
+            self.restored = None
 
         def get_weights(self):
             return self.w
@@ -258,13 +290,33 @@ def test_checkpoint_npz_roundtrip_logic(tmp_path):
         def set_weights(self, ws):
             self.loaded = ws
 
+        def get_optimizer_state(self):
+            return 1234, 2.5e-5, self.moments
+
+        def set_optimizer_state(self, iterations, lr, moments):
+            self.restored = (iterations, lr, moments)
+
     a, b = Stub(), Stub()
     path = str(tmp_path / "fetal_net_model-epoch01-loss-0.500-acc0.900.h5")
     Model.save_weights(a, path)
     with np.load(path) as z:
         assert "conv3d_1/kernel:0" in z.files and "instance_normalization_1/gamma:0" in z.files
+        assert "__iterations__" not in z.files                       # save_weights stays weights-only
     Model.load_weights(b, path)
     assert len(b.loaded) == 6 and all(np.array_equal(p, q) for p, q in zip(b.loaded, a.w))
+    assert Model.load_optimizer_state(b, path) is False and b.restored is None
+    # Keras' model.save(): weights + Adam moments + iteration count + the current (plateau-reduced) learning rate,
+    # which load_old_model restores so a resumed run continues like the reference's load_model path
+    full = str(tmp_path / "fetal_net_model-epoch02-loss-0.600-acc0.910.h5")
+    Model.save(a, full)
+    c = Stub()
+    Model.load_weights(c, full)
+    assert all(np.array_equal(p, q) for p, q in zip(c.loaded, a.w))
+    assert Model.load_optimizer_state(c, full) is True
+    it, lr, moments = c.restored
+    assert it == 1234 and lr == 2.5e-5 and len(moments) == 3
+    for got, ref in zip(moments, a.moments):
+        assert all(np.array_equal(g, r) for g, r in zip(got, ref))
 
 
 def test_train_model_driver_and_callbacks_on_a_stub(tmp_path):
@@ -283,6 +335,7 @@ def test_train_model_driver_and_callbacks_on_a_stub(tmp_path):
         metrics_names = ['loss', 'binary_accuracy', 'vod_coefficient']
         fit_generator = Model.fit_generator
         save = Model.save_weights
+        _weight_arrays = Model._weight_arrays
         _weights_from_mapping = Model._weights_from_mapping
         layers = [dict(keras_name="conv3d_1", is_norm=False)]
         input_shape, depth, n_base_filters, n_labels, name, isensee_levels = (None, 1, 8, 8, 8), 2, 16, 1, 'unet_model_3d', None
