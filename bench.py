@@ -471,18 +471,23 @@ def bench_infer(e, args, steps, warmup):
     l0 = ctx.launch_count()
     sampler = ClockSampler(e.local)
     sampler.start()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        out = call(vol)
-    s_page = (time.perf_counter() - t0) / steps
+
+    def timed_calls(v):
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            r = call(v)
+            ts.append(time.perf_counter() - t0)
+        return r, ts
+    out, t_page = timed_calls(vol)
     clocks = sampler.stop()
     launches = int((ctx.launch_count() - l0) // steps)
     for _ in range(2):
         call(volp)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        call(volp)
-    s_pin = (time.perf_counter() - t0) / steps
+    _, t_pin = timed_calls(volp)
+    # the calls are 10 ms of wall clock each on a shared host: the median over the timed calls is the figure, the mean
+    # (which a single descheduled call can double) is printed beside it
+    s_page, s_pin = float(np.median(t_page)), float(np.median(t_pin))
     nvox = int(np.prod(VOLUME))
     # device leg: the same call with per-launch CUDA events (gather + network + overlap-add, no host copies)
     ctx.profile(True)
@@ -508,9 +513,12 @@ def bench_infer(e, args, steps, warmup):
                             l2="49 patches x 64^3 x up to 96 channels of activations per call >> 126 MB L2"),
                 steps=steps, clocks=clocks,
                 e2e=dict(value=nvox / s_page, unit=UNIT, h2d_bytes_per_step=int(vol.nbytes),
-                         d2h_bytes_per_step=int(out.nbytes), ms_per_step=s_page * 1e3, host_buffers="pageable numpy"),
+                         d2h_bytes_per_step=int(out.nbytes), ms_per_step=s_page * 1e3, host_buffers="pageable numpy",
+                         ms_per_step_mean=float(np.mean(t_page)) * 1e3, ms_per_step_min=float(np.min(t_page)) * 1e3,
+                         statistic="median of %d timed calls" % steps),
                 e2e_pinned=dict(value=nvox / s_pin, unit=UNIT, h2d_bytes_per_step=int(vol.nbytes),
                                 d2h_bytes_per_step=int(out.nbytes), ms_per_step=s_pin * 1e3,
+                                ms_per_step_mean=float(np.mean(t_pin)) * 1e3,
                                 host_buffers="pinned input, pageable output"),
                 gpu_launches=launches, roofline=roofs.get("conv3d_march_fprop"), rooflines=roofs,
                 patch_voxels_per_s=49 * int(np.prod(PATCH)) / s_page,
@@ -539,6 +547,73 @@ def bench_infer_sharded(e, steps):
                 timed="wall clock around the public call incl. H2D of the volume on every rank, the reduce and the D2H "
                       "of the 268 MB float64 result on rank 0; max over ranks",
                 conv_tflops=147 * FWD_GF_PER_PATCH5 / (sec * 1e3), out_mean=float(out.mean()) if out is not None else None)
+
+
+def bench_family(e, kind, steps):
+    """configs[2] (Isensee-2017 residual 3D U-Net, 128x128x64) and configs[3] (2.5D U-Net on 5 slices + previous-truth
+    channel, 256x256): training step and predict through the same entry points, single GPU."""
+    torch, _lib, lib, ctx = e.torch, e._lib, e.lib, e.ctx
+    from fetal_net.model import isensee2017_model_3d, unet_model_2d
+    rng = np.random.default_rng(3)
+    if kind == "isensee":
+        B, shape = 2, (1, 128, 128, 64)
+        model = isensee2017_model_3d(input_shape=shape, n_base_filters=16, depth=5, n_segmentation_levels=3,
+                                     dropout_rate=0.3, initial_learning_rate=5e-4, device=e.local)
+        x = rng.standard_normal((B,) + shape).astype(np.float32)
+        t = (rng.random((B,) + shape) < 0.3).astype(np.float32)
+        fwd_gf, first_gf, units = 173.638, 0.906, B * 128 * 128 * 64
+        name = "isensee2017_model_3d(depth=5,n_base_filters=16,n_segmentation_levels=3,dropout_rate=0.3), batch 2 x " \
+               "1x128x128x64 (BASELINE configs[2])"
+    else:
+        B, shape = 8, (256, 256, 6)
+        model = unet_model_2d(input_shape=shape, n_base_filters=32, depth=4, initial_learning_rate=1e-4, device=e.local)
+        x = rng.standard_normal((B,) + shape).astype(np.float32)
+        x[..., 5] = rng.random((B, 256, 256)) < 0.3
+        t = (rng.random((B, 256, 256, 1)) < 0.3).astype(np.float32)
+        fwd_gf, first_gf, units = 71.504, 2 * 9 * 6 * 32 * 65536 / 1e9, B * 256 * 256
+        name = "unet_model_2d(depth=4,n_base_filters=32) on 5 slices + 1 previous-truth channel, batch 8 x 256x256x6 " \
+               "(BASELINE configs[3])"
+    model.init_glorot_uniform(seed=0)
+    xd, td = torch.as_tensor(x).cuda(), torch.as_tensor(t).cuda()
+    xp, tp = torch.as_tensor(x).pin_memory(), torch.as_tensor(t).pin_memory()
+    m4 = np.zeros(4, np.float32)
+
+    def step():
+        _lib.check(lib.fm_train_step_device(model._h, xd.data_ptr(), td.data_ptr(), B, 1e-4, _lib.fptr(m4)))
+    for _ in range(3):
+        step()
+    sampler = ClockSampler(e.local)
+    sampler.start()
+    ms = timed_device(e, step, steps) / steps
+    clocks = sampler.stop()
+    for _ in range(2):
+        model.train_on_batch(xp.numpy(), tp.numpy())
+    s_e2e = timed_wall(e, lambda: model.train_on_batch(xp.numpy(), tp.numpy()), steps)
+    for _ in range(2):
+        model.predict(xp.numpy())
+    s_pred = timed_wall(e, lambda: model.predict(xp.numpy()), steps)
+    pk = peaks()
+    ctx.profile(True)
+    for _ in range(2):
+        step()
+    agg = aggregate(ctx.profile_records())
+    ctx.profile(False)
+    total_ms = sum(a[1] for a in agg.values())
+    top = max(agg.items(), key=lambda kv: kv[1][1])
+    breakdown = {k: dict(launches=a[0] // 2, ms_per_step=a[1] / 2, share=a[1] / total_ms,
+                         tflops=(a[2] / a[1] / 1e9) if a[1] > 0 and a[2] > 0 else None,
+                         gbs=(a[3] / a[1] / 1e6) if a[1] > 0 and a[3] > 0 else None)
+                 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]}
+    train_gf = B * (3 * fwd_gf - first_gf)
+    return dict(metric="train voxels/sec" if kind == "isensee" else "train pixels/sec", value=units / (ms * 1e-3),
+                unit="voxels/s" if kind == "isensee" else "pixels/s", ms_per_step=ms, config=dict(workload=name, batch=B),
+                clocks=clocks, conv_tflops_whole_step=train_gf / ms,
+                e2e=dict(value=units / s_e2e, ms_per_step=s_e2e * 1e3, host_buffers="pinned",
+                         h2d_bytes_per_step=int(x.nbytes + t.nbytes), d2h_bytes_per_step=64),
+                predict=dict(value=units / s_pred, ms_per_call=s_pred * 1e3, conv_tflops=B * fwd_gf / (s_pred * 1e3),
+                             note="Model.predict with host buffers (H2D + forward + D2H)"),
+                roofline=roofline_of(top[0], top[1], 2, total_ms, pk, clocks, {}), kernel_breakdown=breakdown,
+                loss=float(m4[0]))
 
 
 def run_b200(args):
@@ -581,8 +656,11 @@ def run_b200(args):
                         collective=("libfetalb200 NCCL communicator (fm_train_step_dp), NCCL %s" %
                                     (e.ctx.comm_info()[2],)) if e.world > 1 else None)
             line.update(extra)
+    if args.workload == "all" and e.rank == 0 and e.world == 1 and line is not None:
+        line["families"] = dict(isensee=bench_family(e, "isensee", max(3, args.steps // 4)),
+                                unet2d=bench_family(e, "unet2d", max(3, args.steps // 4)))
     if want_infer and e.rank == 0:
-        inf = bench_infer(e, args, max(3, args.steps // 4), 3)
+        inf = bench_infer(e, args, max(5, args.steps // 2), 3)
         if not args.no_cpu_baseline and e.world == 1:
             inf["cpu_baseline"] = cpu_infer_sample()
         if line is None:

@@ -48,6 +48,7 @@ extern "C" int fm_ctx_create(int device, fm_ctx** out) {
   }
   FM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   FM_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  FM_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
   FM_CUDA(cudaEventCreateWithFlags(&ctx->copy_fence, cudaEventDisableTiming));
   FM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
   FM_CUDA(cudaMalloc((void**)&ctx->red_scratch, 1024 * 8 * sizeof(double)));
@@ -70,6 +71,7 @@ extern "C" int fm_ctx_destroy(fm_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   if (ctx->copy_fence) cudaEventDestroy(ctx->copy_fence);
   if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
   delete ctx;
@@ -270,6 +272,7 @@ struct fm_model {
   DevBuf<int32_t> pw_idx;
   DevBuf<double> pw_out;
   DevBuf<int16_t> pw_cnt;
+  std::vector<cudaEvent_t> pw_events;  // [0] upload, [1] rows ready, [2..] one per finished output slab
 
   // backward bucket events (one per layer, reverse creation order)
   std::vector<cudaEvent_t> layer_done;
@@ -280,6 +283,8 @@ struct fm_model {
   // training passes use the shared-accumulator marching kernel (faster; fp32 summation order not fixed), inference
   // the bit-reproducible one
   bool train_pass = false;
+  // training forward with the targets already in t_in: the head kernel also produces the loss statistics
+  bool targets_ready = false, stats_done = false;
 
   int depth() const { return spec.depth; }
   Dims5 dims(int level, int C, int B) const {
@@ -517,6 +522,8 @@ extern "C" int fm_model_destroy(fm_model* m) {
                   &m->gPool, &m->gUp, &m->gSkip, &m->gDecA, &m->gDecB})
     for (auto& b : *v) b.release();
   for (auto& e : m->layer_done) cudaEventDestroy(e);
+  for (auto& e : m->pw_events)
+    if (e) cudaEventDestroy(e);
   for (int b = 0; b < 2; ++b) {
     m->stage_x[b].release();
     m->stage_t[b].release();
@@ -721,8 +728,7 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
     }
   }
   if (train || m->train_alloc) {
-    FM_TRY(m->t_in.ensure((size_t)cap * v0));
-    FM_TRY(m->dz.ensure((size_t)cap * v0));
+    FM_TRY(m->t_in.ensure((size_t)cap * v0));  // (no dL/dz tensor: the head backward forms the Dice gradient itself)
     for (int d = 0; d < D; ++d) {
       const size_t v = (size_t)m->vox(d) * cap;
       const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
@@ -794,6 +800,13 @@ static int forward(fm_model* m, int B) {
     cur = m->decB[d].p;
   }
   const Layer& lf = m->layers.back();
+  if (m->train_pass && m->targets_ready) {
+    // head + sigmoid + Dice / VOD / accuracy sums in one pass (unet.py:68-69 + metrics.py:11-28)
+    FM_TRY(k_head_fwd_dice(ctx, cur, m->params + lf.w_off, m->params + lf.b_off, m->t_in.p, m->prob.p,
+                           (int64_t)B * m->vox(0), lf.c1, m->sums));
+    m->stats_done = true;
+    return FM_OK;
+  }
   FM_TRY(k_head_fwd(ctx, cur, m->params + lf.w_off, m->params + lf.b_off, m->prob.p,
                     (int64_t)B * m->vox(0), lf.c1));
   return FM_OK;
@@ -807,17 +820,26 @@ static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x
   const bf16* xs[2] = {x1, x2};
   const int cs[2] = {l.c1, l.c2};
   int cofs = 0;
+  bool bias_done = false;
+  static const bool fold_bias = [] {
+    const char* e = getenv("FETAL_B200_SEPARATE_BIAS_GRAD");
+    return !(e && e[0] == '1');
+  }();
   for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
-    if (use_march() && conv_wgrad_march_supported(d.X, d.Y, d.Z, cs[s], l.cout, l.k))
-      FM_TRY(k_conv3d_wgrad_march(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout));
-    else if (conv_tc_supported(cs[s], 0, l.cout, l.k))
+    if (use_march() && conv_wgrad_march_supported(d.X, d.Y, d.Z, cs[s], l.cout, l.k)) {
+      // the marching kernel also sums dY over the voxels (bias gradient) while the tiles sit in shared memory
+      const bool with_bias = fold_bias && !bias_done;
+      FM_TRY(k_conv3d_wgrad_march(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout,
+                                  with_bias ? m->grads + l.b_off : nullptr));
+      bias_done = bias_done || with_bias;
+    } else if (conv_tc_supported(cs[s], 0, l.cout, l.k))
       FM_TRY(k_conv3d_tc_wgrad(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout, l.k));
     else
       FM_TRY(k_conv3d_simt_wgrad(ctx, xs[s], 0, dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout,
                                  l.k));
     cofs += cs[s];
   }
-  FM_TRY(k_bias_grad(ctx, dy, m->grads + l.b_off, d.voxels(), l.cout));
+  if (!bias_done) FM_TRY(k_bias_grad(ctx, dy, m->grads + l.b_off, d.voxels(), l.cout));
   return FM_OK;
 }
 
@@ -852,11 +874,11 @@ static int backward(fm_model* m, int B) {
   const int D = m->depth();
   const int64_t n0 = (int64_t)B * m->vox(0);
   FM_TRY(k_zero(ctx, m->grads, (size_t)m->nparams * sizeof(float)));
-  FM_TRY(k_dice_bwd(ctx, m->prob.p, m->t_in.p, m->sums, n0, m->dz.p, 1));
   const Layer& lf = m->layers.back();
-  // head backward: gradient lands masked by the ReLU of dec0b (or encB[0] when depth == 1)
-  FM_TRY(k_head_bwd(ctx, m->decB[0].p, m->dz.p, m->params + lf.w_off, m->gDecB[0].p, m->grads + lf.w_off,
-                    m->grads + lf.b_off, n0, lf.c1));
+  // head backward with the soft-Dice gradient formed inside (closed form through the sigmoid with the GLOBAL sums):
+  // gradient lands masked by the ReLU of dec0b (or encB[0] when depth == 1)
+  FM_TRY(k_head_bwd(ctx, m->decB[0].p, m->prob.p, m->params + lf.w_off, m->gDecB[0].p, m->grads + lf.w_off,
+                    m->grads + lf.b_off, n0, lf.c1, 0, m->t_in.p, m->sums));
   FM_TRY(mark_layer_done(m, lf));
   for (int d = 0; d <= D - 2; ++d) {
     const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
@@ -1224,6 +1246,8 @@ static int is_wgrad(fm_model* m, const Layer& l, int level, const bf16* x1, cons
   const bf16* xs[2] = {x1, x2};
   const int cs[2] = {l.c1, l.c2};
   int cofs = 0;
+  // no bias gradient here: every Isensee conv feeds an InstanceNormalization, which removes a per-channel constant -
+  // the gradient of such a bias is exactly zero (the heads, which have a live bias, are 1x1x1 kernels handled elsewhere)
   for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
     if (use_march() && conv_wgrad_march_supported(d.X, d.Y, d.Z, cs[s], l.cout, l.k))
       FM_TRY(k_conv3d_wgrad_march(ctx, xs[s], dy, dw, B, d.X, d.Y, d.Z, cs[s], l.cin(), cofs, l.cout));
@@ -1501,6 +1525,31 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
   const int64_t lo = n * shard_rank / shard_count, hi = n * (shard_rank + 1) / shard_count;
   const int64_t nloc = hi - lo;
   batch = (int)std::min<int64_t>(batch, std::max<int64_t>(nloc, 1));
+  // the reassembly plan also validates the corner list (x-major Cartesian product, every voxel covered)
+  ReasmPlan* plan = nullptr;
+  FM_TRY(k_reassemble_prepare(ctx, idx, n, pred, 1, out_dims, &plan));
+  struct PlanGuard {
+    ReasmPlan* p;
+    ~PlanGuard() { k_reassemble_release(p); }
+  } plan_guard{plan};
+  const int32_t* xstarts = nullptr;
+  int ngroups = 0, ppg = 0;
+  k_reassemble_groups(plan, &xstarts, &ngroups, &ppg);
+  // PIPELINE: the patch list is x-major, so output rows below the x corner of the next unprocessed patch are final.
+  // A large caller batch is therefore cut into sub-batches of whole x groups: the volume is uploaded slab by slab on
+  // the copy stream just ahead of the patches that need it, and finished output slabs are overlap-added, copied back
+  // and un-staged while the network still works on later patches. The network is bit-reproducible and batch-invariant,
+  // so the result does not depend on the cut. FETAL_B200_PW_SUB=0 keeps the caller's batch.
+  {
+    static const int sub_env = [] {
+      const char* e = getenv("FETAL_B200_PW_SUB");
+      return e ? atoi(e) : -1;
+    }();
+    if (sub_env > 0)
+      batch = std::min(batch, sub_env);
+    else if (sub_env < 0 && batch > ppg && ngroups >= 3)
+      batch = (int)std::min<int64_t>(batch, (int64_t)ppg * std::max(1, ngroups / 8));
+  }
   FM_TRY(ensure_capacity(m, batch, false));
   DevBuf<float>&dvol = m->pw_vol, &dpred = m->pw_pred;
   DevBuf<int32_t>& didx = m->pw_idx;
@@ -1511,31 +1560,87 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
   FM_TRY(didx.ensure((size_t)n * 3));
   FM_TRY(dout.ensure(nout));
   FM_TRY(dcnt.ensure(nout));
-  // host <-> device through the context's pinned staging buffer (pageable cudaMemcpy runs at a fraction of PCIe)
-  void* pin = nullptr;
   const bool trace = getenv("FETAL_B200_TRACE") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto t_start = now();
   auto lap = [&](const char* what) {
     if (!trace) return;
-    cudaStreamSynchronize(ctx->stream);
     auto t = now();
     fprintf(stderr, "[fm_patchwise_predict] %-22s %8.3f ms\n", what,
             std::chrono::duration<double, std::milli>(t - t_start).count());
     t_start = t;
   };
+  // host <-> device through the context's pinned staging buffer (pageable cudaMemcpy runs at a fraction of PCIe):
+  // [volume | truth | float64 result | int16 counts]
+  const size_t in_bytes = (nv * sizeof(float) * (truth ? 2 : 1) + 4095) & ~(size_t)4095;
   const size_t out_bytes = nout * sizeof(double), cnt_bytes = out_count ? nout * sizeof(int16_t) : 0;
-  FM_TRY(fm_ctx_pinned(ctx, std::max(nv * sizeof(float) * (truth ? 2 : 1), out_bytes + cnt_bytes), &pin));
+  const size_t cnt_off = in_bytes + ((out_bytes + 4095) & ~(size_t)4095);
+  void* pin = nullptr;
+  FM_TRY(fm_ctx_pinned(ctx, cnt_off + cnt_bytes, &pin));
+  char* pin_in = (char*)pin;
+  char* pin_out = (char*)pin + in_bytes;
+  char* pin_cnt = (char*)pin + cnt_off;
+  if ((int)m->pw_events.size() < ngroups + 2) {
+    const size_t old = m->pw_events.size();
+    m->pw_events.resize((size_t)ngroups + 2, nullptr);
+    for (size_t i = old; i < m->pw_events.size(); ++i)
+      FM_CUDA(cudaEventCreateWithFlags(&m->pw_events[i], cudaEventDisableTiming));
+  }
+  cudaEvent_t ev_up = m->pw_events[0], ev_rows = m->pw_events[1];
   lap("workspace");
-  host_copy(pin, vol, nv * sizeof(float));
-  if (truth) host_copy((float*)pin + nv, truth, nv * sizeof(float));
-  lap("stage volume");
-  FM_CUDA(cudaMemcpyAsync(dvol.p, pin, nv * 4 * (truth ? 2 : 1), cudaMemcpyHostToDevice, ctx->stream));
   FM_CUDA(cudaMemcpyAsync(didx.p, idx, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-  FM_CUDA(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));
-  lap("h2d");
+  if (shard_count > 1) FM_CUDA(cudaMemsetAsync(dout.p, 0, nout * 8, ctx->stream));  // partial sums accumulate
+  // the copy stream starts behind everything queued so far (nothing of an earlier call may still read the buffers)
+  FM_CUDA(cudaEventRecord(ctx->copy_fence, ctx->stream));
+  FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_fence, 0));
+  const size_t row_floats = (size_t)vol_dims[1] * vol_dims[2];
+  const int x_off = halo_pad[0] + fit_pad[0];  // padded x = volume x + x_off
+  int rows_up = 0;
+  auto upload_to = [&](int need_rows) -> int {
+    need_rows = std::min(need_rows, (int)vol_dims[0]);
+    if (need_rows <= rows_up) return FM_OK;
+    const size_t off = (size_t)rows_up * row_floats, cnt = (size_t)(need_rows - rows_up) * row_floats;
+    host_copy(pin_in + off * 4, vol + off, cnt * 4);
+    FM_CUDA(cudaMemcpyAsync(dvol.p + off, pin_in + off * 4, cnt * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (truth) {
+      host_copy(pin_in + (nv + off) * 4, truth + off, cnt * 4);
+      FM_CUDA(cudaMemcpyAsync(dvol.p + nv + off, pin_in + (nv + off) * 4, cnt * 4, cudaMemcpyHostToDevice,
+                              ctx->copy_stream));
+    }
+    FM_CUDA(cudaEventRecord(ev_up, ctx->copy_stream));
+    FM_CUDA(cudaStreamWaitEvent(ctx->stream, ev_up, 0));
+    rows_up = need_rows;
+    return FM_OK;
+  };
+  // finished output slabs: (first row, rows, event after their D2H copy)
+  struct Slab {
+    int x0, rows;
+    cudaEvent_t done;
+  };
+  std::vector<Slab> slabs;
+  size_t unstaged = 0;
+  const size_t plane = (size_t)out_dims[1] * out_dims[2];
+  const bool stream_out = want_out && shard_count == 1;  // slab-wise D2H only when no cross-rank reduce follows
+  auto unstage = [&](bool block) {
+    while (unstaged < slabs.size()) {
+      const Slab& sl = slabs[unstaged];
+      if (block) {
+        cudaEventSynchronize(sl.done);
+      } else if (cudaEventQuery(sl.done) != cudaSuccess) {
+        cudaGetLastError();
+        break;
+      }
+      const size_t o = (size_t)sl.x0 * plane, c = (size_t)sl.rows * plane;
+      host_copy(out + o, pin_out + o * 8, c * 8);
+      if (out_count) host_copy(out_count + o, pin_cnt + o * 2, c * 2);
+      ++unstaged;
+    }
+  };
+  int x_done = 0;
   for (int64_t b0 = lo; b0 < hi; b0 += batch) {
     const int nb = (int)std::min<int64_t>(batch, hi - b0);
+    // rows of the volume the patches of this sub-batch read: up to the last patch's corner + its extent
+    FM_TRY(upload_to(idx[(b0 + nb - 1) * 3] - x_off + patch[0]));
     // 3D: [nb,P0,P1,P2] == the network's [nb,X,Y,Z] input. 2D: [nb,H,W,(slices | truth slices)] channels-last
     FM_TRY(k_gather_patches(ctx, dvol.p, vol_dims, halo_pad, fit_pad, (float)pad_value[0], (float)pad_value[1],
                             didx.p + b0 * 3, nb, patch, m->x_in.p, is2d ? m->cin_real : 0, 0, 0));
@@ -1547,29 +1652,48 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
     FM_TRY(forward(m, nb));
     FM_CUDA(cudaMemcpyAsync(dpred.p + (size_t)(b0 - lo) * pv, m->prob.p, (size_t)nb * pv * 4,
                             cudaMemcpyDeviceToDevice, ctx->stream));
+    // output rows below the next unprocessed patch's x corner are final (for this shard)
+    const int x_final = b0 + nb < hi ? std::min<int>(idx[(b0 + nb) * 3], out_dims[0]) : out_dims[0];
+    if (x_final > x_done) {
+      FM_TRY(k_reassemble_rows(ctx, plan, dpred.p, lo, hi, lo, dout.p, dcnt.p, shard_count == 1 ? 1 : 0, x_done, x_final));
+      if (stream_out) {
+        const size_t o = (size_t)x_done * plane, c = (size_t)(x_final - x_done) * plane;
+        FM_CUDA(cudaEventRecord(ev_rows, ctx->stream));
+        FM_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ev_rows, 0));
+        FM_CUDA(cudaMemcpyAsync(pin_out + o * 8, dout.p + o, c * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (out_count)
+          FM_CUDA(cudaMemcpyAsync(pin_cnt + o * 2, dcnt.p + o, c * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        cudaEvent_t done = m->pw_events[2 + slabs.size() % (size_t)ngroups];
+        FM_CUDA(cudaEventRecord(done, ctx->d2h_stream));
+        slabs.push_back(Slab{x_done, x_final - x_done, done});
+      }
+      x_done = x_final;
+    }
+    unstage(false);
   }
-  lap("gather + forward");
-  FM_TRY(k_reassemble(ctx, dpred.p, idx, n, lo, hi, lo, pred, 1, out_dims, dout.p, dcnt.p,
-                      shard_count == 1 ? 1 : 0));
+  lap("enqueue (upload / gather / forward / overlap-add)");
+  if (stream_out) {
+    unstage(true);
+    FM_CUDA(cudaStreamSynchronize(ctx->stream));
+    lap("drain (D2H + unstage)");
+    m->fwd_valid = false;
+    return FM_OK;
+  }
   if (reduce_root >= 0 && shard_count > 1) {
     FM_TRY(comm_reduce(ctx, dout.p, nout, 1, reduce_root, ctx->stream));
     if (want_out) FM_TRY(k_divide_by_count(ctx, dout.p, dcnt.p, (int64_t)nout, 1));
   }
-  FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the H2D staging buffer is reused for the way back
-  lap("reassemble");
-  if (!want_out) {
-    m->fwd_valid = false;
-    return FM_OK;
-  }
-  FM_CUDA(cudaMemcpyAsync(pin, dout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_count)
-    FM_CUDA(cudaMemcpyAsync((char*)pin + out_bytes, dcnt.p, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  lap("reduce");
+  m->fwd_valid = false;
+  if (!want_out) return FM_OK;
+  FM_CUDA(cudaMemcpyAsync(pin_out, dout.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_count) FM_CUDA(cudaMemcpyAsync(pin_cnt, dcnt.p, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));
   lap("d2h");
-  host_copy(out, pin, out_bytes);
-  if (out_count) host_copy(out_count, (char*)pin + out_bytes, cnt_bytes);
+  host_copy(out, pin_out, out_bytes);
+  if (out_count) host_copy(out_count, pin_cnt, cnt_bytes);
   lap("unstage result");
-  m->fwd_valid = false;
   return FM_OK;
 }
 
@@ -1609,8 +1733,11 @@ static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullp
     FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_fence, 0));
   }
   m->train_pass = true;
+  m->targets_ready = t_host == nullptr;  // already uploaded: the head kernel also sums the loss statistics
+  m->stats_done = false;
   const int rf = forward(m, batch);
   m->train_pass = false;
+  m->targets_ready = false;
   FM_TRY(rf);
   if (t_host) {
     FM_CUDA(cudaMemcpyAsync(m->t_in.p, t_host, (size_t)batch * m->vox(0) * sizeof(float), cudaMemcpyHostToDevice,
@@ -1618,7 +1745,8 @@ static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullp
     FM_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     FM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
   }
-  FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0));
+  if (!m->stats_done) FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0));
+  m->stats_done = false;
   m->last_batch = batch;
   m->fwd_valid = true;
   return FM_OK;
@@ -1832,12 +1960,52 @@ extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int ba
   return FM_OK;
 }
 
+// The data-parallel tail of a step whose forward pass has been queued (statistics in m->sums): all-reduce of the Dice
+// sums, backward, bucketed gradient all-reduce overlapped with it, Adam, metrics.
+static int dp_step_after_forward(fm_model* m, float lr, float out_metrics[4]);
+
 extern "C" int fm_train_step_dp(fm_model* m, const float* x, const float* t, int batch, float lr,
                                 float out_metrics[4]) {
   FM_CHECK(m && x && t && batch > 0 && out_metrics, FM_EINVAL, "fm_train_step_dp: bad argument");
   fm_ctx* ctx = m->ctx;
   if (!ctx->comm || ctx->comm_size == 1) return fm_train_step(m, x, t, batch, lr, out_metrics);
   FM_TRY(fm_train_forward(m, x, t, batch));
+  return dp_step_after_forward(m, lr, out_metrics);
+}
+
+extern "C" int fm_train_step_sampled(fm_model* m, fm_volset* s, const int32_t* cases, const int32_t* corners,
+                                     const fm_sample_aug* aug, int batch, int truth_index, int truth_size,
+                                     int prev_truth_index, int prev_truth_size, float lr, float out_metrics[4]) {
+  FM_CHECK(m && s && cases && corners && batch > 0 && out_metrics, FM_EINVAL, "fm_train_step_sampled: bad argument");
+  fm_ctx* ctx = m->ctx;
+  FM_CUDA(cudaSetDevice(ctx->device));
+  const bool is2d = m->kcode == 31;
+  FM_CHECK(m->kind == 0 || !is2d, FM_EINVAL, "fm_train_step_sampled: unsupported model kind");
+  int32_t patch[3];
+  if (is2d) {
+    FM_CHECK(truth_size == 1 && prev_truth_size >= 0 && prev_truth_size < m->cin_real, FM_EINVAL,
+             "fm_train_step_sampled: a 2D model takes truth_size 1 and prev_truth_size < in_channels (%d)", m->cin_real);
+    patch[0] = m->spec.X;
+    patch[1] = m->spec.Y;
+    patch[2] = m->cin_real - prev_truth_size;
+  } else {
+    FM_CHECK(prev_truth_size == 0 && truth_size == m->spec.Z, FM_EINVAL,
+             "fm_train_step_sampled: a 3D model takes truth_size == Z (%d) and no previous-truth channels", m->spec.Z);
+    patch[0] = m->spec.X;
+    patch[1] = m->spec.Y;
+    patch[2] = m->spec.Z;
+  }
+  FM_TRY(ensure_capacity(m, batch, true));
+  FM_TRY(sampler_gather_device(s, cases, corners, aug, batch, patch, truth_index, truth_size, prev_truth_index,
+                               prev_truth_size, m->x_in.p, m->t_in.p));
+  FM_TRY(train_forward_dev(m, batch));
+  if (ctx->comm && ctx->comm_size > 1) return dp_step_after_forward(m, lr, out_metrics);
+  FM_TRY(fm_train_backward(m));
+  return fm_train_apply(m, lr, 0, out_metrics);
+}
+
+static int dp_step_after_forward(fm_model* m, float lr, float out_metrics[4]) {
+  fm_ctx* ctx = m->ctx;
   // 8 float64: the GLOBAL Dice statistics every rank back-propagates (64 bytes; latency only)
   FM_TRY(comm_allreduce(ctx, m->sums, 8, 1, ctx->stream));
   FM_TRY(fm_train_metrics_async(m));
@@ -2053,13 +2221,13 @@ extern "C" int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const f
   FM_TRY(s.alloc(&db, Cout));
   FM_TRY(k_zero(ctx, dw, wn * 4));
   FM_TRY(k_zero(ctx, db, (size_t)Cout * 4));
-  if (impl == 2)
-    FM_TRY(k_conv3d_wgrad_march(ctx, dx, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout));
+  if (impl == 2)  // the marching kernel also produces the bias gradient (column sums of dY)
+    FM_TRY(k_conv3d_wgrad_march(ctx, dx, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, db));
   else if (impl == 0)
     FM_TRY(k_conv3d_tc_wgrad(ctx, dx, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, ksize));
   else
     FM_TRY(k_conv3d_simt_wgrad(ctx, dx, 0, ddy, dw, N, X, Y, Z, Cin, Cin, 0, Cout, ksize));
-  FM_TRY(k_bias_grad(ctx, ddy, db, (int64_t)vox, Cout));
+  if (impl != 2) FM_TRY(k_bias_grad(ctx, ddy, db, (int64_t)vox, Cout));
   std::vector<float> packed(wn);
   FM_CUDA(cudaMemcpyAsync(packed.data(), dw, wn * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (dbias) FM_CUDA(cudaMemcpyAsync(dbias, db, (size_t)Cout * 4, cudaMemcpyDeviceToHost, ctx->stream));

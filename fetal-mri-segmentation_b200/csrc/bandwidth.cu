@@ -908,11 +908,11 @@ __global__ void reassemble_kernel(const float* __restrict__ preds, ReasmGeom gm,
                                   const int32_t* __restrict__ cover,    // [3][max dim][2] lo,hi
                                   int starts_pitch, int cover_pitch, int64_t shard_lo,
                                   int64_t shard_hi, int64_t pred_base, double* __restrict__ out,
-                                  int16_t* __restrict__ count, int divide) {
-  // blockIdx.y walks x; 32-bit arithmetic inside one (y, z, channel) plane
+                                  int16_t* __restrict__ count, int divide, int x_lo, int x_hi) {
+  // blockIdx.y walks x in [x_lo, x_hi); 32-bit arithmetic inside one (y, z, channel) plane
   const int64_t pvox = (int64_t)gm.pred[0] * gm.pred[1] * gm.pred[2];
   const uint32_t plane = (uint32_t)gm.out[1] * (uint32_t)gm.out[2] * (uint32_t)gm.channels;
-  for (int x = blockIdx.y; x < gm.out[0]; x += gridDim.y)
+  for (int x = x_lo + blockIdx.y; x < x_hi; x += gridDim.y)
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < plane; q += gridDim.x * blockDim.x) {
     const int ch = (int)(q % (uint32_t)gm.channels);
     uint32_t r = q / (uint32_t)gm.channels;
@@ -955,11 +955,12 @@ __global__ void __launch_bounds__(kThreads) reassemble4_kernel(const float* __re
                                                                const int32_t* __restrict__ cover, int starts_pitch,
                                                                int cover_pitch, int64_t shard_lo, int64_t shard_hi,
                                                                int64_t pred_base, double* __restrict__ out,
-                                                               int16_t* __restrict__ count, int divide) {
+                                                               int16_t* __restrict__ count, int divide, int x_lo,
+                                                               int x_hi) {
   const int64_t pvox = (int64_t)gm.pred[0] * gm.pred[1] * gm.pred[2];
   const uint32_t z4n = (uint32_t)gm.out[2] >> 2;
   const uint32_t plane4 = (uint32_t)gm.out[1] * z4n;
-  for (int x = blockIdx.y; x < gm.out[0]; x += gridDim.y) {
+  for (int x = x_lo + blockIdx.y; x < x_hi; x += gridDim.y) {
     const int2 cx = __ldg(reinterpret_cast<const int2*>(cover + (0 * cover_pitch + x) * 2));
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < plane4; q += gridDim.x * blockDim.x) {
       const int z = (int)(q % z4n) * 4;
@@ -1102,6 +1103,12 @@ int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* 
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
+// fixed-order fold of `nblocks` x 8 partial statistics in ctx->red_scratch (written by head_fwd_dice_kernel)
+int k_dice_finalize(fm_ctx* ctx, int nblocks, double n_elems, double* sums) {
+  FM_CUDA(launch_pdl(dice_final_kernel, dim3(1), dim3(256), 0, ctx->stream, ctx->red_scratch, nblocks, n_elems, sums, 0));
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
 int k_dice_bwd(fm_ctx* ctx, const float* p, const float* t, const double* sums, int64_t n, float* dz,
                int through_sigmoid) {
   ProfScope prof(ctx, "dice_bwd", 0.0, (double)n * 12.0);
@@ -1167,11 +1174,18 @@ int k_gather_patches(fm_ctx* ctx, const float* vol, const int32_t vol_dims[3],
 
 // Host side of the reassembly: turns the corner list into per-axis start lists + per-coordinate
 // covering ranges (the corners of fm_patch_plan are always a Cartesian product in x-major order;
-// anything else is rejected). `preds` holds patches [pred_base, pred_base + n_local) of the plan.
-int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64_t n_total,
-                 int64_t shard_lo, int64_t shard_hi, int64_t pred_base,
-                 const int32_t pred_shape[3], int channels, const int32_t out_dims[3],
-                 double* out_dev, int16_t* count_dev, int divide) {
+// anything else is rejected). Prepared once per call; the overlap-add itself can then run slab by slab
+// (rows [x_lo, x_hi) of the output) as soon as the patches covering a slab have been predicted.
+struct ReasmPlan {
+  int32_t *d_starts = nullptr, *d_cover = nullptr;
+  int maxnp = 0, maxdim = 0;
+  ReasmGeom gm;
+  std::vector<int32_t> xstarts;  // distinct x corners, ascending
+  int64_t n_total = 0;
+};
+
+int k_reassemble_prepare(fm_ctx* ctx, const int32_t* idx_host, int64_t n_total, const int32_t pred_shape[3],
+                         int channels, const int32_t out_dims[3], ReasmPlan** out_plan) {
   std::vector<int32_t> st[3];
   for (int a = 0; a < 3; ++a) {
     for (int64_t i = 0; i < n_total; ++i) {
@@ -1213,39 +1227,86 @@ int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64
       cover[((size_t)a * maxdim + c) * 2 + 1] = hi;
     }
   }
-  int32_t *d_starts = nullptr, *d_cover = nullptr;
-  FM_CUDA(cudaMallocAsync((void**)&d_starts, starts.size() * 4, ctx->stream));
-  FM_CUDA(cudaMallocAsync((void**)&d_cover, cover.size() * 4, ctx->stream));
-  FM_CUDA(cudaMemcpyAsync(d_starts, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  FM_CUDA(cudaMemcpyAsync(d_cover, cover.data(), cover.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  FM_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope below
-  ReasmGeom gm;
-  for (int a = 0; a < 3; ++a) {
-    gm.out[a] = out_dims[a];
-    gm.pred[a] = pred_shape[a];
+  ReasmPlan* pl = new ReasmPlan();
+  cudaError_t e = cudaMalloc((void**)&pl->d_starts, starts.size() * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->d_cover, cover.size() * 4);
+  // synchronous copies: the host vectors go out of scope below (a few hundred bytes)
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_starts, starts.data(), starts.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_cover, cover.data(), cover.size() * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    fm_set_error("reassemble: %s", cudaGetErrorString(e));
+    k_reassemble_release(pl);
+    return FM_ECUDA;
   }
-  gm.np[0] = (int)np0;
-  gm.np[1] = (int)np1;
-  gm.np[2] = (int)np2;
-  gm.channels = channels;
-  const int64_t total = (int64_t)out_dims[0] * out_dims[1] * out_dims[2] * channels;
-  ProfScope prof(ctx, "reassemble", 0.0, (double)(shard_hi - shard_lo) * pred_shape[0] * pred_shape[1] * pred_shape[2] * channels * 4.0 + (double)total * 8.0);
-  const int64_t plane = (int64_t)out_dims[1] * out_dims[2] * channels;
+  for (int a = 0; a < 3; ++a) {
+    pl->gm.out[a] = out_dims[a];
+    pl->gm.pred[a] = pred_shape[a];
+  }
+  pl->gm.np[0] = (int)np0;
+  pl->gm.np[1] = (int)np1;
+  pl->gm.np[2] = (int)np2;
+  pl->gm.channels = channels;
+  pl->maxnp = maxnp;
+  pl->maxdim = maxdim;
+  pl->xstarts = st[0];
+  pl->n_total = n_total;
+  (void)ctx;
+  *out_plan = pl;
+  return FM_OK;
+}
+
+void k_reassemble_release(ReasmPlan* pl) {
+  if (!pl) return;
+  if (pl->d_starts) cudaFree(pl->d_starts);
+  if (pl->d_cover) cudaFree(pl->d_cover);
+  delete pl;
+}
+
+int k_reassemble_groups(const ReasmPlan* pl, const int32_t** xstarts, int* n_groups, int* patches_per_group) {
+  *xstarts = pl->xstarts.data();
+  *n_groups = pl->gm.np[0];
+  *patches_per_group = pl->gm.np[1] * pl->gm.np[2];
+  return FM_OK;
+}
+
+// overlap-add (+ count, + divide) of the output rows [x_lo, x_hi). `preds` holds patches [pred_base, ...) of the plan.
+int k_reassemble_rows(fm_ctx* ctx, const ReasmPlan* pl, const float* preds, int64_t shard_lo, int64_t shard_hi,
+                      int64_t pred_base, double* out_dev, int16_t* count_dev, int divide, int x_lo, int x_hi) {
+  const ReasmGeom& gm = pl->gm;
+  FM_CHECK(x_lo >= 0 && x_hi <= gm.out[0] && x_lo < x_hi, FM_EINVAL, "reassemble: rows [%d, %d) of %d", x_lo, x_hi, gm.out[0]);
+  const int channels = gm.channels;
+  const double frac = (double)(x_hi - x_lo) / (double)gm.out[0];
+  const int64_t total = (int64_t)gm.out[0] * gm.out[1] * gm.out[2] * channels;
+  ProfScope prof(ctx, "reassemble", 0.0,
+                 frac * ((double)(shard_hi - shard_lo) * gm.pred[0] * gm.pred[1] * gm.pred[2] * channels * 4.0 + (double)total * 8.0));
+  const int64_t plane = (int64_t)gm.out[1] * gm.out[2] * channels;
   FM_CHECK(plane < ((int64_t)1 << 31), FM_EINVAL, "reassemble: plane of %lld elements", (long long)plane);
-  if (channels == 1 && out_dims[2] % 4 == 0 && ((uintptr_t)out_dev & 15) == 0 && ((uintptr_t)count_dev & 7) == 0) {
-    const dim3 rgrid((unsigned)grid_for(plane / 4, 256), (unsigned)std::min<int>(out_dims[0], 32768));
-    reassemble4_kernel<<<rgrid, kThreads, 0, ctx->stream>>>(preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo,
-                                                           shard_hi, pred_base, out_dev, count_dev, divide);
+  const int rows = x_hi - x_lo;
+  if (channels == 1 && gm.out[2] % 4 == 0 && ((uintptr_t)out_dev & 15) == 0 && ((uintptr_t)count_dev & 7) == 0) {
+    const dim3 rgrid((unsigned)grid_for(plane / 4, 256), (unsigned)std::min<int>(rows, 32768));
+    reassemble4_kernel<<<rgrid, kThreads, 0, ctx->stream>>>(preds, gm, pl->d_starts, pl->d_cover, pl->maxnp, pl->maxdim,
+                                                           shard_lo, shard_hi, pred_base, out_dev, count_dev, divide, x_lo,
+                                                           x_hi);
   } else {
-    const dim3 rgrid((unsigned)grid_for(plane, 256), (unsigned)std::min<int>(out_dims[0], 32768));
-    reassemble_kernel<<<rgrid, kThreads, 0, ctx->stream>>>(
-        preds, gm, d_starts, d_cover, maxnp, maxdim, shard_lo, shard_hi, pred_base, out_dev, count_dev,
-        divide);
+    const dim3 rgrid((unsigned)grid_for(plane, 256), (unsigned)std::min<int>(rows, 32768));
+    reassemble_kernel<<<rgrid, kThreads, 0, ctx->stream>>>(preds, gm, pl->d_starts, pl->d_cover, pl->maxnp, pl->maxdim,
+                                                          shard_lo, shard_hi, pred_base, out_dev, count_dev, divide, x_lo,
+                                                          x_hi);
   }
   FM_LAUNCH_OK(ctx);
-  FM_CUDA(cudaFreeAsync(d_starts, ctx->stream));
-  FM_CUDA(cudaFreeAsync(d_cover, ctx->stream));
   return FM_OK;
+}
+
+int k_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx_host, int64_t n_total,
+                 int64_t shard_lo, int64_t shard_hi, int64_t pred_base,
+                 const int32_t pred_shape[3], int channels, const int32_t out_dims[3],
+                 double* out_dev, int16_t* count_dev, int divide) {
+  ReasmPlan* pl = nullptr;
+  FM_TRY(k_reassemble_prepare(ctx, idx_host, n_total, pred_shape, channels, out_dims, &pl));
+  const int rc = k_reassemble_rows(ctx, pl, preds, shard_lo, shard_hi, pred_base, out_dev, count_dev, divide, 0, out_dims[0]);
+  cudaStreamSynchronize(ctx->stream);  // the plan's tables are freed below
+  k_reassemble_release(pl);
+  return rc;
 }
 
 int k_divide_by_count(fm_ctx* ctx, double* out, const int16_t* count, int64_t nvox, int channels) {

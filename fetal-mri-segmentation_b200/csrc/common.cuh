@@ -58,6 +58,9 @@ struct fm_ctx {
   cudaStream_t stream = nullptr;
   // side stream for host->device copies that the head of the compute stream does not need yet (training targets)
   cudaStream_t copy_stream = nullptr;
+  // device->host copies of finished output slabs (patch-wise inference) run on their own stream, so that they never
+  // hold back the next slab's upload
+  cudaStream_t d2h_stream = nullptr;
   cudaEvent_t copy_fence = nullptr, copy_done = nullptr;
   int64_t launches = 0;
   // scratch for deterministic two-stage reductions
@@ -72,6 +75,11 @@ struct fm_ctx {
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t comm_ev = nullptr;
 };
+
+// sampler.cu: cuts a batch of training samples out of device-resident cases into device buffers
+int sampler_gather_device(fm_volset* s, const int32_t* cases, const int32_t* corners, const fm_sample_aug* aug, int batch,
+                          const int32_t patch[3], int truth_index, int truth_size, int prev_truth_index,
+                          int prev_truth_size, float* x_dev, float* y_dev);
 
 // comm.cu: in-place SUM collectives on the ctx communicator (no-ops without one); dtype 0 = float32, 1 = float64
 int comm_allreduce(fm_ctx* ctx, void* buf, size_t count, int dtype, cudaStream_t stream);
@@ -205,6 +213,15 @@ int k_reassemble(fm_ctx*, const float* preds, const int32_t* idx_host, int64_t n
                  int channels, const int32_t out_dims[3], double* out_dev, int16_t* count_dev,
                  int divide);
 int k_divide_by_count(fm_ctx*, double* out, const int16_t* count, int64_t nvox, int channels);
+// the same reassembly prepared once (per-axis start lists / covering ranges on the device) and run slab by slab
+struct ReasmPlan;
+int k_reassemble_prepare(fm_ctx*, const int32_t* idx_host, int64_t n_total, const int32_t pred_shape[3], int channels,
+                         const int32_t out_dims[3], ReasmPlan** out_plan);
+void k_reassemble_release(ReasmPlan* plan);
+// distinct x corners (ascending), their number and the patches per x corner (the list is x-major)
+int k_reassemble_groups(const ReasmPlan* plan, const int32_t** xstarts, int* n_groups, int* patches_per_group);
+int k_reassemble_rows(fm_ctx*, const ReasmPlan* plan, const float* preds, int64_t shard_lo, int64_t shard_hi,
+                      int64_t pred_base, double* out_dev, int16_t* count_dev, int divide, int x_lo, int x_hi);
 
 // conv_simt.cu
 // first layer: fp32 single/multi-channel input (channels-last), small Cin; out bf16 + ReLU
@@ -218,9 +235,14 @@ int k_bias_grad(fm_ctx*, const bf16* dy, float* db, int64_t voxels, int C);
 // 1x1x1 head: z = w.x + b ; p = sigmoid(z) (fp32 out)
 int k_head_fwd(fm_ctx*, const bf16* x, const float* w, const float* b, float* p, int64_t voxels,
                int C, int apply_sigmoid = 1);
-// head backward: dx[v,c] = dz[v] * w[c] * (x[v,c] > 0); dw[c] = sum_v dz[v] x[v,c]; db = sum dz
+// training forward: head + sigmoid + the 8 loss statistics of k_dice_sums in one pass over the activations
+int k_head_fwd_dice(fm_ctx*, const bf16* x, const float* w, const float* b, const float* t, float* p, int64_t voxels,
+                    int C, double* sums);
+int k_dice_finalize(fm_ctx*, int nblocks, double n_elems, double* sums);
+// head backward: dx[v,c] = dz[v] * w[c] * (x[v,c] > 0); dw[c] = sum_v dz[v] x[v,c]; db = sum dz.
+// With `t` and `sums`: `dz` holds the probabilities and dL/dz of the soft-Dice loss is formed inside (fused dice_bwd)
 int k_head_bwd(fm_ctx*, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
-               float* db, int64_t voxels, int C, int mode = 0);
+               float* db, int64_t voxels, int C, int mode = 0, const float* t = nullptr, const double* sums = nullptr);
 // weight repack: master fp32 [Cout][taps][Cin] -> bf16 fprop pack (same layout) and bf16 dgrad
 // pack(s) [Cin_s][taps flipped][Cout] per source
 // all layers in ONE launch (after every Adam step): per layer the fprop pack, the dgrad pack(s) and, where the
@@ -280,5 +302,6 @@ static inline bool fm_march_v1() {
 
 // conv_wgrad_march.cu
 int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize);
+// db (optional): the bias gradient [Cout] = column sums of dY, accumulated (atomics) by the same launch
 int k_conv3d_wgrad_march(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
-                         int Cin, int Cin_total, int cin_ofs, int Cout);
+                         int Cin, int Cin_total, int cin_ofs, int Cout, float* db = nullptr);

@@ -353,15 +353,96 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restri
   }
 }
 
+// Training forward: the 1x1x1 head, the sigmoid AND the partial sums of the soft-Dice / VOD / accuracy statistics in
+// one pass (Conv3D(n_labels, 1) + Activation('sigmoid') of unet3d/unet.py:68-69 + dice_coefficient / vod_coefficient /
+// binary_accuracy of metrics.py:11-28). Per block: 7 double partial sums at part[block * 8 ...], folded in a fixed order
+// by dice_final_kernel (deterministic, no atomics). p is still written: the backward pass needs it.
+__global__ void __launch_bounds__(kThreads) head_fwd_dice_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ b,
+                                                                 const float* __restrict__ t, float* __restrict__ p,
+                                                                 int64_t voxels, int C, double* __restrict__ part) {
+  FM_PDL_SYNC();
+  const int lpv = C >> 3;  // lanes per voxel (power of two <= 32)
+  const int sub = threadIdx.x % lpv;
+  float wv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + sub * 8 + i);
+  const float bb = __ldg(b);
+  const int64_t vpb = blockDim.x / lpv;
+  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  constexpr int U = 4;
+  for (int64_t base = (int64_t)blockIdx.x * vpb * U; base < voxels; base += (int64_t)gridDim.x * vpb * U) {
+    uint4 xv[U];
+    float tv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * vpb + threadIdx.x / lpv;
+      const bool ok = v < voxels;
+      xv[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      tv[u] = ok && sub == 0 ? __ldg(t + v) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = base + u * vpb + threadIdx.x / lpv;
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&xv[u]);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        acc += f.x * wv[2 * i] + f.y * wv[2 * i + 1];
+      }
+      for (int sft = lpv >> 1; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+      if (sub == 0 && v < voxels) {
+        const float pv = 1.f / (1.f + __expf(-(acc + bb)));
+        p[v] = pv;
+        const float tt = tv[u];
+        const float pb = pv > 0.5f ? 1.f : 0.f, tb = tt > 0.5f ? 1.f : 0.f;
+        s[0] += tt * pv;
+        s[1] += tt;
+        s[2] += pv;
+        s[3] += tb * pb;
+        s[4] += tb;
+        s[5] += pb;
+        s[6] += (tt == pb) ? 1.f : 0.f;
+      }
+    }
+  }
+  __shared__ double shd[kThreads / 32][7];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    double wsum = (double)s[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if (lane == 0) shd[warp][k] = wsum;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double a = 0.0;
+    for (int wi = 0; wi < kThreads / 32; ++wi) a += shd[wi][threadIdx.x];
+    part[(int64_t)blockIdx.x * 8 + threadIdx.x] = a;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restrict__ x,
                                                             const float* __restrict__ dz,
                                                             const float* __restrict__ w,
                                                             bf16* __restrict__ dx,
                                                             float* __restrict__ dw,
                                                             float* __restrict__ db, int64_t voxels,
-                                                            int C, int mode) {
+                                                            int C, int mode, const float* __restrict__ pt,
+                                                            const double* __restrict__ sums) {
   FM_PDL_SYNC();
   // mode 0: dx = g*w masked by ReLU(x) (plain U-Net head); 1: dx = g*w; 2: dx += g*w (Isensee seg heads)
+  // `pt` != NULL: `dz` holds the probabilities p, `pt` the targets t and g = dL/dz is formed here - the closed-form
+  // gradient of L = -dice(t, sigmoid(z)) (metrics.py:11-15,31-32, smooth = 1) with the GLOBAL sums - instead of being
+  // read from a dz tensor written by a separate dice_bwd launch
+  float ga = 0.f, gbc = 0.f;
+  if (pt != nullptr) {
+    const double I = sums[0], S = sums[1] + sums[2] + 1.0;
+    ga = (float)(-2.0 / S);
+    gbc = (float)((2.0 * I + 1.0) / (S * S));
+  }
   const int lpv = C >> 3;
   const int sub = threadIdx.x % lpv;
   float wv[8], gw[8];
@@ -376,7 +457,12 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
     // two voxels per trip: both loads are issued before the first is consumed
     const int64_t v1 = v0 + vstride;
     const bool has1 = v1 < voxels;
-    const float gg[2] = {__ldg(dz + v0), has1 ? __ldg(dz + v1) : 0.f};
+    float gg[2] = {__ldg(dz + v0), has1 ? __ldg(dz + v1) : 0.f};
+    if (pt != nullptr) {
+      const float t0 = __ldg(pt + v0), t1 = has1 ? __ldg(pt + v1) : 0.f;
+      gg[0] = (ga * t0 + gbc) * gg[0] * (1.f - gg[0]);
+      gg[1] = (ga * t1 + gbc) * gg[1] * (1.f - gg[1]);
+    }
     const uint4 tt[2] = {__ldg(reinterpret_cast<const uint4*>(x + v0 * C + sub * 8)),
                          has1 ? __ldg(reinterpret_cast<const uint4*>(x + v1 * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u)};
 #pragma unroll
@@ -584,15 +670,34 @@ int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float
   return FM_OK;
 }
 
+// head + sigmoid + Dice / VOD / accuracy partial sums in one pass; `sums` receives the 8 folded statistics
+int k_head_fwd_dice(fm_ctx* ctx, const bf16* x, const float* w, const float* b, const float* t, float* p,
+                    int64_t voxels, int C, double* sums) {
+  FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
+           "head: channel count %d must be a power of two in [8,256]", C);
+  const int lpv = C / 8;
+  const int64_t vpb = kThreads / lpv;
+  const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb * 4), 1024);
+  {
+    ProfScope prof(ctx, "head_fwd_dice", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 8.0));
+    FM_CUDA(launch_pdl(head_fwd_dice_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, C,
+                       ctx->red_scratch));
+    FM_LAUNCH_OK(ctx);
+  }
+  return k_dice_finalize(ctx, grid, (double)voxels, sums);
+}
+
 int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
-               float* db, int64_t voxels, int C, int mode) {
+               float* db, int64_t voxels, int C, int mode, const float* t, const double* sums) {
   FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
            "head_bwd: channel count %d must be a power of two in [8,256]", C);
   const int lpv = C / 8;
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 8);
-  ProfScope prof(ctx, "head_bwd", 4.0 * C * (double)voxels, (double)voxels * (C * 4.0 + 4.0));
-  FM_CUDA(launch_pdl(head_bwd_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, dz, w, dx, dw, db, voxels, C, mode));
+  ProfScope prof(ctx, t ? "head_bwd_dice" : "head_bwd", 4.0 * C * (double)voxels,
+                 (double)voxels * (C * 4.0 + (t ? 8.0 : 4.0)));
+  FM_CUDA(launch_pdl(head_bwd_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, dz, w, dx, dw, db, voxels, C, mode, t,
+                     sums));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

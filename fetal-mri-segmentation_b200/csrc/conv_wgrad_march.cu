@@ -16,6 +16,12 @@
 //     stays resident for the CTA's whole lifetime (persistent CTA over many columns) and is flushed with
 //     fp32 red.add once at the end.
 // One CTA handles one (32 input channels x 32 output channels) pair; pairs are spread over the grid.
+// Round 2: (1) three TMA producer warps (one per kz slab copy; warp 0 also feeds the dY ring) - a single producer
+// walking 4 barrier waits + 4 TMA issues per plane was the pacing role; (2) the dY ring has two MIRROR slots (slots
+// 8, 9 repeat 0, 1, loaded by a second TMA), so the three consecutive N blocks of a plane never wrap and every k-step
+// is ONE MMA (the wrap used to split a quarter of them into an N = 64 and an N = 32 MMA that read A twice); (3) the
+// bias gradient (column sums of dY) is folded in: the four epilogue warps, idle during the march, sum the dY tiles
+// they find in shared memory - the separate bias_grad pass over every dY tensor is gone.
 // TF autodiff gradient of Conv3D in create_convolution_block (fetal_net/model/unet3d/unet.py:102).
 #include <algorithm>
 
@@ -25,7 +31,8 @@ using namespace tcp;
 
 namespace {
 
-constexpr int kThreadsW = 256;  // warp 0 TMA, warps 1-3 MMA issue (kz = 0,1,2), warps 4-7 epilogue
+constexpr int kThreadsW = 320;  // warps 0-2 TMA (kz = 0,1,2; warp 0 also dY), warps 3-5 MMA issue (kz), warps 6-9 epilogue
+constexpr int kProdW = 3, kMma0 = 3, kEpi0W = 6;
 constexpr int kBY = 16, kBZ = 8;
 constexpr int kCC = 32;                                   // channels per operand block (64 B rows, SWIZZLE_64B)
 constexpr uint32_t kRow = kCC * 2;                        // 64 B
@@ -34,6 +41,7 @@ constexpr uint32_t kXSlabRows = (kBY + 3) * kBZ;          // 19 y rows: 16 + hal
 constexpr uint32_t kXSlot = 10240;                        // 9728 B rounded up to 1 KB
 constexpr uint32_t kDyTile = kBY * kBZ * kRow;            // 8192 B
 constexpr int kDyRing = 8;
+constexpr int kDyMirror = 2;                              // slots 8, 9 repeat slots 0, 1
 constexpr int kNcols = 96;                                // (kx, co) columns per accumulator
 
 struct alignas(64) WgMarchParams {
@@ -48,6 +56,7 @@ struct alignas(64) WgMarchParams {
   int kcy;             // output channels per CTA / per N block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cout = 16)
   int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
   float* dw;
+  float* db;           // bias gradient [Cout] (column sums of dY), or NULL
 };
 
 __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const __grid_constant__ WgMarchParams p) {
@@ -57,7 +66,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
 
   const uint32_t x_base = smem0;                                        // 3 * S3 slab slots
   const uint32_t dy_base = x_base + 3u * (uint32_t)p.S3 * kXSlot;        // kDyRing tiles
-  const uint32_t bar0 = dy_base + (uint32_t)kDyRing * kDyTile;
+  const uint32_t bar0 = dy_base + (uint32_t)(kDyRing + kDyMirror) * kDyTile;
   const int nx = 3 * p.S3;
   auto xfull_bar = [&](uint32_t s) { return bar0 + 8u * s; };
   auto xempty_bar = [&](uint32_t s) { return bar0 + 8u * ((uint32_t)nx + s); };
@@ -72,7 +81,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     prefetch_tmap(&p.tmX);
     prefetch_tmap(&p.tmDY);
   }
-  if (warp == 1) {
+  const int pair = blockIdx.x / p.ctas_per_pair;
+  const int rank = blockIdx.x % p.ctas_per_pair;
+  const int cic = pair % p.n_ci, coc = pair / p.n_ci;
+  const bool do_bias = p.db != nullptr && cic == 0;   // one ci chunk per co chunk sums dY
+  if (warp == kMma0) {
     if (lane == 0) {
       for (int s = 0; s < nx; ++s) {
         mbar_init(xfull_bar(s), 1);
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
       }
       for (int s = 0; s < kDyRing; ++s) {
         mbar_init(dyfull_bar(s), 1);
-        mbar_init(dyempty_bar(s), 3);
+        mbar_init(dyempty_bar(s), do_bias ? 7 : 3);  // three MMA warps (+ one arrival per bias-summing warp)
       }
       mbar_init(zero_bar, 128);
       mbar_init(done_bar, 3);
@@ -97,11 +110,6 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 
-  // this CTA's (ci chunk, co chunk) pair and its share of the columns
-  const int pair = blockIdx.x / p.ctas_per_pair;
-  const int rank = blockIdx.x % p.ctas_per_pair;
-  const int cic = pair % p.n_ci, coc = pair / p.n_ci;
-
   auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) {
     const int jx = item % p.nxc;
     int t = item / p.nxc;
@@ -113,47 +121,53 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     xb = min(p.X, xa + p.xchunk);
   };
 
-  if (warp_u == 0) {
-    // ===== TMA producer =====
+  if (warp_u < kProdW) {
+    // ===== TMA producers: warp kz loads the kz-shifted X slab of every plane; warp 0 also the dY tiles =====
+    const int dz = warp_u;
     pdl_wait();  // x and dY come from the previous kernels in the stream
-    pdl_launch_dependents();
+    if (dz == 0) pdl_launch_dependents();
     const uint32_t x_bytes = (uint32_t)(kBY + 128 / p.kcx - 1) * kBZ * (uint32_t)p.kcx * 2u;  // slab box bytes
-    uint32_t sidx[3] = {0u, 0u, 0u}, sph[3] = {0u, 0u, 0u};
+    const uint32_t dy_bytes = (uint32_t)(kBY * kBZ) * (uint32_t)p.kcy * 2u;
+    uint32_t sidx = 0, sph = 0;
     uint32_t dcount = 0;  // dY tiles issued so far (ring position)
+    const uint32_t slot0 = (uint32_t)dz * (uint32_t)p.S3;
     for (int item = rank; item < p.items; item += p.ctas_per_pair) {
       int n, iy, iz, xa, xb;
       decode(item, n, iy, iz, xa, xb);
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       int next_dy = xa;  // next output plane whose dY tile has to be loaded
       for (int xi = x_first; xi <= x_last; ++xi) {
-        const int need = min(xi + 1, xb - 1);  // dY tiles up to this output plane feed input plane xi
-        for (; next_dy <= need; ++next_dy, ++dcount) {
-          const uint32_t slot = dcount & (uint32_t)(kDyRing - 1);
-          mbar_wait(dyempty_bar(slot), ((dcount >> 3) & 1u) ^ 1u);
-          mbar_expect_tx_elect(dyfull_bar(slot), (uint32_t)(kBY * kBZ) * (uint32_t)p.kcy * 2u);
-          tma_load_5d_elect(dy_base + slot * kDyTile, &p.tmDY, dyfull_bar(slot), coc * p.kcy, iz * kBZ, iy * kBY, next_dy, n);
-        }
-#pragma unroll
-        for (int dz = 0; dz < 3; ++dz) {
-          const uint32_t stage = (uint32_t)dz * (uint32_t)p.S3 + sidx[dz];
-          mbar_wait(xempty_bar(stage), sph[dz] ^ 1u);
-          mbar_expect_tx_elect(xfull_bar(stage), x_bytes);
-          tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ + dz - 1,
-                            iy * kBY - 1, xi, n);
-          if (++sidx[dz] == (uint32_t)p.S3) {
-            sidx[dz] = 0;
-            sph[dz] ^= 1u;
+        if (dz == 0) {
+          const int need = min(xi + 1, xb - 1);  // dY tiles up to this output plane feed input plane xi
+          for (; next_dy <= need; ++next_dy, ++dcount) {
+            const uint32_t slot = dcount & (uint32_t)(kDyRing - 1);
+            mbar_wait(dyempty_bar(slot), ((dcount >> 3) & 1u) ^ 1u);
+            const bool mirror = slot < (uint32_t)kDyMirror;
+            mbar_expect_tx_elect(dyfull_bar(slot), mirror ? 2u * dy_bytes : dy_bytes);
+            tma_load_5d_elect(dy_base + slot * kDyTile, &p.tmDY, dyfull_bar(slot), coc * p.kcy, iz * kBZ, iy * kBY, next_dy, n);
+            if (mirror)
+              tma_load_5d_elect(dy_base + (slot + (uint32_t)kDyRing) * kDyTile, &p.tmDY, dyfull_bar(slot), coc * p.kcy,
+                                iz * kBZ, iy * kBY, next_dy, n);
           }
+        }
+        const uint32_t stage = slot0 + sidx;
+        mbar_wait(xempty_bar(stage), sph ^ 1u);
+        mbar_expect_tx_elect(xfull_bar(stage), x_bytes);
+        tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ + dz - 1, iy * kBY - 1, xi, n);
+        if (++sidx == (uint32_t)p.S3) {
+          sidx = 0;
+          sph ^= 1u;
         }
       }
     }
-  } else if (warp_u <= 3) {
-    // ===== MMA warps: warp w issues the kz = w - 1 slab copy into its own accumulator =====
-    const int dz = warp_u - 1;
+  } else if (warp_u < kEpi0W) {
+    // ===== MMA warps: warp kMma0 + kz issues the kz slab copy into its own accumulator =====
+    const int dz = warp_u - kMma0;
     const uint32_t d_acc = tmem_base + (uint32_t)(dz * kNcols);
     const uint32_t ncy = (uint32_t)p.kcy;
     const uint32_t idesc1 = make_idesc(128, (int)ncy, 1, 1), idesc2 = make_idesc(128, 2 * (int)ncy, 1, 1),
                    idesc3 = make_idesc(128, 3 * (int)ncy, 1, 1);
+    (void)idesc2;
     const uint32_t b_row = ncy * 2u, b_sbo = 8u * b_row;                     // dY operand: 64- or 32-byte rows
     const uint32_t hi32 = desc_hi(b_sbo, layout_code((int)b_row));
     const uint32_t kstep = (2u * b_sbo) >> 4;  // 16 voxels (two 8-row groups) per MMA, in 16-byte units
@@ -180,21 +194,17 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         const uint32_t stage = slot0 + sidx;
         mbar_wait(xfull_bar(stage), sph);
         tc_fence_after();
+        // the <= 3 consecutive dY tiles never wrap: slots 8, 9 mirror slots 0, 1
         const uint32_t rs = seq_lo & (uint32_t)(kDyRing - 1);
-        const uint32_t nA = min(nblk, (uint32_t)kDyRing - rs), nB = nblk - nA;
-        const uint32_t idA = nA == 1 ? idesc1 : (nA == 2 ? idesc2 : idesc3);
-        const uint32_t idB = nB == 1 ? idesc1 : idesc2;
+        const uint32_t idA = nblk == 1 ? idesc1 : (nblk == 2 ? idesc2 : idesc3);
         uint32_t a_lo = desc_lo(x_base + stage * kXSlot, a_sbo);          // M blocks (ky) one atom apart
         uint32_t bA = desc_lo(dy_base + rs * kDyTile, kDyTile);           // N blocks (kx) one ring slot apart
-        uint32_t bB = desc_lo(dy_base, kDyTile);
-        const uint32_t dA = d_acc + j_lo * ncy, dB = dA + nA * ncy;
+        const uint32_t dA = d_acc + j_lo * ncy;
 #pragma unroll
         for (int ks = 0; ks < (kBY * kBZ) / 16; ++ks) {
           umma_bf16_lh_elect(dA, a_lo, a_hi32, bA, hi32, idA, 1u);
-          if (nB) umma_bf16_lh_elect(dB, a_lo, a_hi32, bB, hi32, idB, 1u);
           a_lo += a_kstep;
           bA += kstep;
-          bB += kstep;
         }
         umma_commit_elect(xempty_bar(stage));
         if (++sidx == (uint32_t)p.S3) {
@@ -211,13 +221,61 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     umma_commit_elect(done_bar);
   } else {
     // ===== epilogue warps: zero the accumulators, and flush them once at the end =====
-    const int q = warp & 3;
+    const int q = warp & 3;         // TMEM lane quarter of this warp (warp id mod 4)
     const int row = q * 32 + lane;  // (ky, ci) = (row / 32, row % 32); ky == 3 is the discarded block
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int c16 = 0; c16 < 3 * kNcols / 16; ++c16) tmem_st16_zero(lane_base + (uint32_t)c16 * 16u);
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(zero_bar);
+    if (do_bias) {
+      // ===== bias gradient: column sums of the dY tiles as they pass through shared memory. Thread t owns the
+      // 16-byte channel chunk c = t % CH of the rows r0 + k * (128 / CH); TMA wrote the rows swizzled (64-byte rows:
+      // chunk ^= (row >> 1) & 3; 32-byte rows: chunk ^= (row >> 2) & 1). =====
+      const int et = (warp - kEpi0W) * 32 + lane;
+      const int CH = p.kcy / 8, RP = 128 / CH;
+      const int c = et % CH, r0 = et / CH;
+      const uint32_t rowb = (uint32_t)p.kcy * 2u;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      uint32_t dcount = 0;
+      for (int item = rank; item < p.items; item += p.ctas_per_pair) {
+        int n, iy, iz, xa, xb;
+        decode(item, n, iy, iz, xa, xb);
+        for (int xo = xa; xo < xb; ++xo, ++dcount) {
+          const uint32_t slot = dcount & (uint32_t)(kDyRing - 1);
+          mbar_wait(dyfull_bar(slot), (dcount >> 3) & 1u);
+          const uint32_t tile = dy_base + slot * kDyTile;
+          for (int k = 0; k < CH; ++k) {
+            const int r = r0 + k * RP;
+            const int sw = CH == 4 ? ((r >> 1) & 3) : ((r >> 2) & 1);
+            uint32_t v0, v1, v2, v3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                         : "r"(tile + (uint32_t)r * rowb + (uint32_t)((c ^ sw) * 16)));
+            const uint32_t vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[j]));
+              acc[2 * j] += f.x;
+              acc[2 * j + 1] += f.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dyempty_bar(slot));
+        }
+      }
+      // lanes with the same chunk c (lane % CH) fold their sums, then one atomic per channel and warp
+      for (int ofs = CH; ofs < 32; ofs <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], ofs);
+      }
+      if (lane < CH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(p.db + coc * p.kcy + c * 8 + j, acc[j]);
+      }
+    }
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const int ky = row / p.kcx, ci = row % p.kcx;
@@ -242,7 +300,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMma0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -291,7 +349,7 @@ int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize
 }
 
 int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
-                         int Cin, int Cin_total, int cin_ofs, int Cout) {
+                         int Cin, int Cin_total, int cin_ofs, int Cout, float* db) {
   FM_CHECK(conv_wgrad_march_supported(X, Y, Z, Cin, Cout, 3), FM_EINVAL,
            "conv3d wgrad march: unsupported shape %dx%dx%d Cin=%d Cout=%d", X, Y, Z, Cin, Cout);
   WgMarchParams p;
@@ -309,6 +367,7 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   p.Ct = Cin_total;
   p.cofs = cin_ofs;
   p.dw = dw_packed;
+  p.db = db;
   const int pairs = p.n_ci * p.n_co;
   const int cols = N * p.ny * p.nz;
   p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, cols * std::max(1, X / 4)));
@@ -324,7 +383,7 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));  // halo + discarded M blocks
   FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy));
   p.S3 = 4;
-  const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)kDyRing * kDyTile + 1024 + 512;
+  const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)(kDyRing + kDyMirror) * kDyTile + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     FM_CUDA(cudaFuncSetAttribute(conv3d_wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -37,6 +37,12 @@ class Isensee3DSpec(ctypes.Structure):
                 ("n_segmentation_levels", ctypes.c_int32), ("n_labels", ctypes.c_int32)]
 
 
+class SampleAug(ctypes.Structure):
+    """fm_sample_aug: per-sample cheap augmentations of the device sampler."""
+    _fields_ = [("flip", ctypes.c_uint32), ("intensity_scale", ctypes.c_float), ("noise_sigma", ctypes.c_float),
+                ("noise_seed", ctypes.c_uint32)]
+
+
 class UNet2DSpec(ctypes.Structure):
     _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("in_channels", ctypes.c_int32),
                 ("depth", ctypes.c_int32), ("n_base_filters", ctypes.c_int32), ("n_labels", ctypes.c_int32)]
@@ -90,6 +96,13 @@ SIGNATURES = {
     "fm_model_set_adam_state": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp, c_fp]),
     "fm_model_get_iterations": (c_int, [c_vp]),
     "fm_model_set_iterations": (c_int, [c_vp, c_int]),
+    "fm_volset_create": (c_int, [c_vp, c_int, ctypes.POINTER(c_vp)]),
+    "fm_volset_destroy": (c_int, [c_vp]),
+    "fm_volset_set_case": (c_int, [c_vp, c_int, c_fp, c_fp, c_i32p]),
+    "fm_volset_gather": (c_int, [c_vp, c_i32p, c_i32p, ctypes.POINTER(SampleAug), c_int, c_i32p, c_int, c_int, c_int,
+                                 c_int, c_fp, c_fp]),
+    "fm_train_step_sampled": (c_int, [c_vp, c_vp, c_i32p, c_i32p, ctypes.POINTER(SampleAug), c_int, c_int, c_int,
+                                      c_int, c_int, c_f, c_fp]),
     "fm_comm_unique_id": (c_int, [c_u8p]),
     "fm_comm_init": (c_int, [c_vp, c_int, c_int, c_u8p]),
     "fm_comm_destroy": (c_int, [c_vp]),

@@ -333,3 +333,79 @@ def predict_augment(data, model, overlap_factor, patch_shape, num_augments=32):
             pred = pred.transpose([1, 0, 2])
         predictions.append(flip_it(pred, to_flip).squeeze())
     return np.stack(predictions, axis=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the callers of the hot path inside the reference's own prediction module (prediction.py:277-351): host I/O glue
+# (PyTables in, NIfTI out) around predict / patch_wise_prediction. The I/O helpers are the reference's own, reached
+# through the overlay (fetal_net.utils.utils: get_image, pickle_load); they need nibabel / tables like the reference.
+# ---------------------------------------------------------------------------------------------
+def _reference_utils():
+    try:
+        from .utils import utils as ref_utils          # resolves to <FETAL_REFERENCE_ROOT>/fetal_net/utils/utils.py
+    except ImportError as e:
+        raise ImportError("run_validation_case(s) writes NIfTI images with the reference's own helpers "
+                          "(fetal_net/utils/utils.py: get_image, pickle_load): set FETAL_REFERENCE_ROOT to a checkout "
+                          "of the reference (and install nibabel / tables as it requires)") from e
+    return ref_utils
+
+
+def run_validation_case(data_index, output_dir, model, data_file, training_modalities, patch_shape,
+                        overlap_factor=0, permute=False, prev_truth_index=None, prev_truth_size=None,
+                        use_augmentations=False):
+    """prediction.py:277-330 with the same signature: writes data_<modality>.nii.gz, truth.nii.gz and prediction.nii.gz
+    of one case; the prediction itself is predict() (volume == patch) or patch_wise_prediction() on the device."""
+    import os
+    get_image = _reference_utils().get_image
+    if not os.path.exists(output_dir):
+        os.makedirs(output_dir)
+    test_data = np.asarray([data_file.root.data[data_index]])
+    test_truth_data = np.asarray([data_file.root.truth[data_index]]) if prev_truth_index is not None else None
+    for i, modality in enumerate(training_modalities):
+        get_image(test_data[i]).to_filename(os.path.join(output_dir, "data_{0}.nii.gz".format(modality)))
+    get_image(data_file.root.truth[data_index]).to_filename(os.path.join(output_dir, "truth.nii.gz"))
+    if tuple(patch_shape) == tuple(test_data.shape[-3:]):
+        prediction = predict(model, test_data, permute=permute)
+    elif use_augmentations:
+        prediction = predict_augment(data=test_data, model=model, overlap_factor=overlap_factor, patch_shape=patch_shape)
+    else:
+        prediction = patch_wise_prediction(model=model, data=test_data, overlap_factor=overlap_factor,
+                                           patch_shape=patch_shape, truth_data=test_truth_data,
+                                           prev_truth_index=prev_truth_index, prev_truth_size=prev_truth_size)[np.newaxis]
+    prediction = prediction.squeeze()
+    prediction_image = get_image(prediction)
+    if isinstance(prediction_image, list):
+        for i, image in enumerate(prediction_image):
+            filename = os.path.join(output_dir, "prediction_{0}.nii.gz".format(i + 1))
+            image.to_filename(filename)
+    else:
+        filename = os.path.join(output_dir, "prediction.nii.gz")
+        prediction_image.to_filename(filename)
+    return filename
+
+
+def run_validation_cases(validation_keys_file, model_file, training_modalities, hdf5_file, patch_shape,
+                         output_dir=".", overlap_factor=0, permute=False,
+                         prev_truth_index=None, prev_truth_size=None, use_augmentations=False):
+    """prediction.py:333-351 with the same signature (the entry point of fetal/predict.py:5,22-30)."""
+    import os
+    import tables                                        # the reference's data files are PyTables HDF5
+    from .training import get_last_model_path, load_old_model
+    file_names = []
+    validation_indices = _reference_utils().pickle_load(validation_keys_file)
+    model = load_old_model(get_last_model_path(model_file))
+    data_file = tables.open_file(hdf5_file, "r")
+    try:
+        for index in validation_indices:
+            if 'subject_ids' in data_file.root:
+                case_directory = os.path.join(output_dir, data_file.root.subject_ids[index].decode('utf-8'))
+            else:
+                case_directory = os.path.join(output_dir, "validation_case_{}".format(index))
+            file_names.append(
+                run_validation_case(data_index=index, output_dir=case_directory, model=model, data_file=data_file,
+                                    training_modalities=training_modalities, overlap_factor=overlap_factor,
+                                    permute=permute, patch_shape=patch_shape, prev_truth_index=prev_truth_index,
+                                    prev_truth_size=prev_truth_size, use_augmentations=use_augmentations))
+    finally:
+        data_file.close()
+    return file_names

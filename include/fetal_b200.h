@@ -233,6 +233,40 @@ int fm_predict_device(fm_model* m, uint64_t x_dev, int batch, uint64_t y_dev);
 /* Replaces: model.evaluate / test_on_batch (validation loop of fit_generator). */
 int fm_evaluate(fm_model* m, const float* x, const float* t, int batch, float out_metrics[4]);
 
+/* ---- training patches cut on the device ---------------------------------------------------------------------------
+ * Replaces the inner loop of the reference's training generator (fetal_net/generator.py:222-348: add_data ->
+ * extract_patch -> get_patch_from_3d_data, convert_data) for cases that fit in HBM: the data / truth volumes are uploaded
+ * once (float32, the dtype Keras feeds), the host keeps drawing the case order, the random corners and the skip-blank
+ * rejections with the reference's own np.random call sequence (fetal_net/device_sampler.py), and one kernel cuts the
+ * whole batch - data patch, target slice(s) at truth_index, previous-truth slice(s) at prev_truth_index appended as
+ * extra input channels (generator.py:305-306), out-of-range slices edge-replicated (utils/patches.py:75-91) - into the
+ * model's input / target buffers. No host<->device traffic per step besides 32 bytes of arguments per sample. */
+typedef struct fm_volset fm_volset;
+/* Optional per-sample cheap augmentations applied while cutting (not the reference's nilearn / imgaug pipeline):
+ * flip bit 0 / 1 / 2 = x / y / z (data, previous truth and target alike), data *= intensity_scale, data += noise_sigma *
+ * N(0,1) (counter-based hash of noise_seed). A NULL pointer means none. */
+typedef struct fm_sample_aug {
+  uint32_t flip;
+  float intensity_scale;
+  float noise_sigma;
+  uint32_t noise_seed;
+} fm_sample_aug;
+int fm_volset_create(fm_ctx* ctx, int n_cases, fm_volset** out);
+int fm_volset_destroy(fm_volset* s);
+/* data, truth: host float32 [X,Y,Z] of case `index` (data_file.root.data[index] / .truth[index]). */
+int fm_volset_set_case(fm_volset* s, int index, const float* data, const float* truth, const int32_t dims[3]);
+/* Test hook: cuts `batch` samples (case[b], corner[b][3]) into host buffers x_out [B,P0,P1,P2+prev_truth_size] and
+ * y_out [B,P0,P1,truth_size]. */
+int fm_volset_gather(fm_volset* s, const int32_t* cases, const int32_t* corners, const fm_sample_aug* aug, int batch,
+                     const int32_t patch[3], int truth_index, int truth_size, int prev_truth_index, int prev_truth_size,
+                     float* x_out, float* y_out);
+/* Replaces: next(generator) + model.train_on_batch(x, y) for one batch whose samples are cut on the device. The patch
+ * extent follows from the model (3D: (X, Y, Z), truth_size must be Z and prev_truth_size 0; 2D: (H, W, in_channels -
+ * prev_truth_size), truth_size 1). Data-parallel when the ctx has a communicator (like fm_train_step_dp). */
+int fm_train_step_sampled(fm_model* m, fm_volset* s, const int32_t* cases, const int32_t* corners,
+                          const fm_sample_aug* aug, int batch, int truth_index, int truth_size, int prev_truth_index,
+                          int prev_truth_size, float lr, float out_metrics[4]);
+
 /* ---- data parallelism (one process per GPU; NCCL over NVLink 5 / NVSwitch) -----------------------------------
  * The reference is single-process (fetal_net/training.py:115-117: workers=1, use_multiprocessing=False); these entry
  * points are the multi-GPU extension of the same two calls (train_on_batch, patch_wise_prediction). libnccl.so.2 is

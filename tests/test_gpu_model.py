@@ -220,8 +220,10 @@ def test_pipelined_train_step_with_pinned_inputs():
     """fm_train_step with page-locked inputs returns after the forward statistics are on the host and lets the rest of
     the step overlap the next upload: same losses / weights as the synchronous (pageable) route, and later calls
     (get_weights, predict) see the finished update. Runs in a subprocess with FETAL_B200_DETERMINISTIC=1 so that the
-    two routes use bit-reproducible kernels and only the fp32 red.add order of the weight gradients differs: any
-    race in the pipelining would show far above the 1e-4 bound."""
+    two routes use bit-reproducible kernels and only the fp32 red.add order of the weight / bias gradients differs.
+    That order is usually the same from run to run (tools/pipeline_noise.py: six runs agree to 1e-7) but not always,
+    and Adam turns a gradient that is rounding noise around zero into a full +-lr step, so the bound is 1e-3 in the
+    loss; a race in the pipelining (the inputs are zeroed right after every call) would show as O(0.1)."""
     import json
     import subprocess
     import sys
@@ -232,7 +234,7 @@ def test_pipelined_train_step_with_pinned_inputs():
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     a, b = out["losses"]
-    assert np.allclose(a, b, atol=1e-4), out
+    assert np.allclose(a, b, atol=1e-3), out
     assert out["dw"] <= 1.5e-3, out               # <= 4 Adam steps of 1e-4 in either direction
 
 
