@@ -264,6 +264,18 @@ class Model:
                                            float(self.optimizer.lr), _lib.fptr(m)))
         return [float(v) for v in m[:len(self.metrics_names)]]
 
+    def train_on_sampled_batch(self, sampler, cases, corners):
+        """One training step on samples cut on the device by a `fetal_net.device_sampler.DeviceSampler`
+        (next(generator) + train_on_batch of fetal_net/training.py:110-124 with no host batch): fm_train_step_sampled."""
+        self._check_loss()
+        cases, corners = _lib.i32x(cases), _lib.i32x(corners)
+        ti, ts, pi, ps = sampler._args()
+        m = np.zeros(4, np.float32)
+        _lib.check(self._lib.fm_train_step_sampled(self._h, sampler._handle, _lib.i32ptr(cases), _lib.i32ptr(corners),
+                                                   sampler._aug_array(cases.size), int(cases.size), ti, ts, pi, ps,
+                                                   float(self.optimizer.lr), _lib.fptr(m)))
+        return [float(v) for v in m[:len(self.metrics_names)]]
+
     def test_on_batch(self, x, y, **kw):
         if not self.trainable:                                      # metrics on the host from .predict
             from .. import metrics as _m
@@ -299,11 +311,15 @@ class Model:
             for cb in callbacks:
                 cb.on_epoch_begin(epoch)
             tot, n = np.zeros(len(self.metrics_names)), 0
+            on_device = hasattr(generator, "train_on_next_batch")   # DeviceSampler: the batch never visits the host
             for _ in range(int(steps_per_epoch)):
-                x, y = next(generator)[:2]
-                r = self.train_on_batch(x, y)
-                tot += np.asarray(r) * len(x)
-                n += len(x)
+                if on_device:
+                    r, nb = generator.train_on_next_batch(self), generator.batch_size
+                else:
+                    x, y = next(generator)[:2]
+                    r, nb = self.train_on_batch(x, y), len(x)
+                tot += np.asarray(r) * nb
+                n += nb
             logs = {k: float(v) for k, v in zip(self.metrics_names, tot / max(n, 1))}
             if validation_data is not None and validation_steps:
                 vt, vn = np.zeros(len(self.metrics_names)), 0

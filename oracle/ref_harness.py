@@ -59,13 +59,27 @@ _STUBBED = [
 ]
 
 _loaded = None
+_loaded_gen = None
+
+
+def load_reference_generator():
+    """Return the reference `fetal_net.generator` module (cached): data_generator / add_data / extract_patch
+    (generator.py:222-348) run unmodified on NumPy arrays, used to freeze the training-sampler goldens."""
+    global _loaded_gen
+    if _loaded_gen is None:
+        _loaded_gen = _load("fetal_net.generator")
+    return _loaded_gen
 
 
 def load_reference_prediction():
     """Return the reference `fetal_net.prediction` module (cached). Raises if absent."""
     global _loaded
-    if _loaded is not None:
-        return _loaded
+    if _loaded is None:
+        _loaded = _load("fetal_net.prediction")
+    return _loaded
+
+
+def _load(module_name):
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
 
@@ -91,11 +105,10 @@ def load_reference_prediction():
         utils_utils = importlib.import_module("fetal_net.utils.utils")
         if not hasattr(utils_utils, "list_load"):
             utils_utils.list_load = lambda *a, **k: []
-        pred = importlib.import_module("fetal_net.prediction")
+        mod = importlib.import_module(module_name)
         patches = importlib.import_module("fetal_net.utils.patches")
-        pred._ref_patches = patches
-        _loaded = pred
-        return pred
+        mod._ref_patches = patches
+        return mod
     finally:
         # restore interpreter state: the reference modules stay reachable only via `_loaded`
         sys.path[:] = saved_path

@@ -196,5 +196,57 @@ def main():
     print("wrote", os.path.join(OUT, "prediction_golden.npz"), len(fx), "arrays")
 
 
+
+
+def make_sampler_golden():
+    """tests/golden/sampler_golden.npz: batches of the UNMODIFIED reference training generator
+    (fetal_net/generator.py:222-348, augment=None) on small synthetic cases, with the (case, corner) draws recovered
+    from the same seeds. shuffle_index_list=False: random_list_generator re-seeds np.random from the OS every pass
+    (generator.py:202), which no golden can follow."""
+    from oracle.ref_harness import load_reference_generator
+    gen = load_reference_generator()
+
+    class Root:
+        pass
+
+    rng = np.random.default_rng(1234)
+    shapes = [(40, 36, 20), (37, 41, 23), (48, 35, 19)]
+    data = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    truth = []
+    for s in shapes:                                   # blobs with empty borders so that skip_blank rejects some
+        t = np.zeros(s, np.float32)
+        c = [v // 2 for v in s]
+        t[c[0] - 8:c[0] + 9, c[1] - 7:c[1] + 8, c[2] - 4:c[2] + 5] = 1.0
+        truth.append(t)
+    df = Root()
+    df.root = df
+    df.data, df.truth, df.mask = data, truth, None
+    fx = {"n_cases": np.int32(len(shapes))}
+    for i in range(len(shapes)):
+        fx["data_%d" % i], fx["truth_%d" % i] = data[i], truth[i]
+    configs = {
+        # name: (patch_shape, kwargs of data_generator)
+        "u3d": ((16, 16, 8), dict(truth_index=0, truth_size=8, is3d=True, skip_blank=True)),
+        "u25d": ((24, 24, 5), dict(truth_index=2, truth_size=1, prev_truth_index=1, prev_truth_size=1, skip_blank=True)),
+        "u25d_edge": ((24, 24, 5), dict(truth_index=5, truth_size=1, prev_truth_index=-1, prev_truth_size=2,
+                                         skip_blank=False)),
+        "u2d_easy": ((34, 34, 3), dict(truth_index=1, truth_size=1, skip_blank=False, drop_easy_patches=True)),
+    }
+    for name, (patch, kw) in configs.items():
+        np.random.seed(77)
+        g = gen.data_generator(df, [2, 0, 1], batch_size=3, patch_shape=patch, shuffle_index_list=False, augment=None,
+                               categorical=False, **kw)
+        for b in range(3):
+            x, y = next(g)
+            fx["%s_x%d" % (name, b)] = np.asarray(x, np.float32)
+            fx["%s_y%d" % (name, b)] = np.asarray(y, np.float32)
+    np.savez_compressed(os.path.join(OUT, "sampler_golden.npz"), **fx)
+    print("sampler golden:", {k: v.shape for k, v in fx.items() if k.startswith("u") and k.endswith("0")})
+
+
 if __name__ == "__main__":
-    main()
+    if "--sampler" in sys.argv:          # python tests/golden/make_golden.py --sampler : only the sampler fixtures
+        make_sampler_golden()
+    else:
+        main()
+        make_sampler_golden()
