@@ -206,6 +206,12 @@ struct Layer {
   // plane-marching kernel (conv_march.cu): packs per source for fprop / dgrad, null when not applicable
   bf16 *w_mf[2] = {nullptr, nullptr}, *w_md[2] = {nullptr, nullptr};
   bool march_f = false, march_d[2] = {false, false};
+  // decoder conv over [UpSampling3D(coarse), skip] computed at coarse resolution (conv_tc.cu, FpropParams::upmode):
+  // class-combined packs [Cout][64][c1] / [c1][64][Cout] and the fp32 gradient of the 64 class taps
+  bool up_coarse = false;
+  bool up_dgrad = false;  // only the gradient towards the coarse tensor runs at coarse resolution (fprop / wgrad march)
+  bf16 *w_up_f = nullptr, *w_up_d = nullptr;
+  float* dw_up = nullptr;
   int cin_real = 0;     // true input channels when c1 is zero-padded to 16 (first layer of the 2.5D U-Net)
   int is_norm = 0;      // InstanceNormalization pseudo-layer of the Isensee net: kernel = gamma, bias = beta (cout each)
   int stride = 1;       // 2: TF-'SAME' strided conv (Isensee in-convs)
@@ -442,6 +448,27 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_mod
         FM_CUDA(cudaMalloc((void**)&l.w_md[s], (size_t)conv_march_pack_elems(l.cout, cs[s]) * sizeof(bf16)));
       }
   }
+  // decoder convs whose filter bank is too large for the marching kernel run at COARSE resolution on their upsampled
+  // source (dec1a, dec2a of the shipped model); FETAL_B200_NO_UP_COARSE=1 keeps the materialised upsampling
+  for (auto& l : m->layers) {
+    if (strncmp(l.name, "dec", 3) != 0 || l.c2 == 0 || l.k != 3 || m->pz != 2) continue;
+    const char* e = getenv("FETAL_B200_NO_UP_COARSE");
+    if (e && e[0] == '1') continue;
+    const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
+    if (!conv_up_supported(X, Y, Z, l.c1, l.c2, l.cout)) continue;
+    const size_t n = (size_t)l.cout * 64 * l.c1;
+    FM_CUDA(cudaMalloc((void**)&l.w_up_d, n * sizeof(bf16)));
+    if (l.march_f) {
+      // small filter bank (dec0a): forward and weight gradient stay on the marching kernels over the materialised
+      // upsampled tensor; the gradient towards the coarse tensor still drops from 27 fine taps + a sum-pool pass to
+      // 64 class taps per COARSE voxel
+      l.up_dgrad = !(e && e[0] == '2');
+      continue;
+    }
+    l.up_coarse = true;
+    FM_CUDA(cudaMalloc((void**)&l.w_up_f, n * sizeof(bf16)));
+    FM_CUDA(cudaMalloc((void**)&l.dw_up, n * sizeof(float)));
+  }
   FM_CUDA(cudaMalloc((void**)&m->sums, 8 * sizeof(double)));
   FM_CUDA(cudaMemset(m->sums, 0, 8 * sizeof(double)));
   m->encA.resize(D);
@@ -491,11 +518,15 @@ extern "C" int fm_model_destroy(fm_model* m) {
   cudaFree(m->wpack);
   cudaFree(m->repack_tab);
   cudaFree(m->sums);
-  for (auto& l : m->layers)
+  for (auto& l : m->layers) {
     for (int s = 0; s < 2; ++s) {
       if (l.w_mf[s]) cudaFree(l.w_mf[s]);
       if (l.w_md[s]) cudaFree(l.w_md[s]);
     }
+    if (l.w_up_f) cudaFree(l.w_up_f);
+    if (l.w_up_d) cudaFree(l.w_up_d);
+    if (l.dw_up) cudaFree(l.dw_up);
+  }
   for (auto* v : {&m->isIn, &m->isC1, &m->isSum, &m->isUp, &m->isU, &m->isLoc1, &m->isLoc2})
     for (auto& b : *v) b.release();
   for (auto& b : m->isSeg) b.release();
@@ -678,6 +709,8 @@ static int refresh_packs(fm_model* m) {
   }
   if (m->repack_n > 0 && !getenv("FETAL_B200_SPLIT_REPACK")) {
     FM_TRY(k_repack_all(m->ctx, m->params, m->repack_tab, m->repack_n, m->repack_blocks, m->repack_weights));
+    for (auto& l : m->layers)
+      if (l.up_coarse || l.up_dgrad) FM_TRY(k_repack_up(m->ctx, m->params + l.w_off, l.w_up_f, l.w_up_d, l.cout, l.c1, l.cin()));
     m->packs_dirty = false;
     return FM_OK;
   }
@@ -697,6 +730,7 @@ static int refresh_packs(fm_model* m) {
                               conv_march_kc(l.cout, 0, cs[s], l.cout)));
       kofs += cs[s];
     }
+    if (l.up_coarse || l.up_dgrad) FM_TRY(k_repack_up(m->ctx, m->params + l.w_off, l.w_up_f, l.w_up_d, l.cout, l.c1, l.cin()));
   }
   m->packs_dirty = false;
   return FM_OK;
@@ -722,7 +756,7 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
     if (d < D - 1) {
       FM_TRY(m->pool[d].ensure((size_t)m->vox(d + 1) * cap * lb.cout));
       const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
-      FM_TRY(m->up[d].ensure(v * da.c1));
+      if (!da.up_coarse) FM_TRY(m->up[d].ensure(v * da.c1));
       FM_TRY(m->decA[d].ensure(v * da.cout));
       FM_TRY(m->decB[d].ensure(v * db.cout));
     }
@@ -737,7 +771,7 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
       if (d < D - 1) {
         FM_TRY(m->gPool[d].ensure((size_t)m->vox(d + 1) * cap * lb.cout));
         const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
-        FM_TRY(m->gUp[d].ensure(v * da.c1));
+        if (!da.up_coarse && !da.up_dgrad) FM_TRY(m->gUp[d].ensure(v * da.c1));
         FM_TRY(m->gSkip[d].ensure(v * da.c2));
         FM_TRY(m->gDecA[d].ensure(v * da.cout));
         FM_TRY(m->gDecB[d].ensure(v * db.cout));
@@ -794,8 +828,15 @@ static int forward(fm_model* m, int B) {
   }
   for (int d = D - 2; d >= 0; --d) {
     const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
-    FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B), m->pz));
-    FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
+    if (da.up_coarse) {
+      // no upsampled tensor: the conv reads the coarse tensor with class-combined weights (8 taps instead of 27)
+      const Dims5 dd = m->dims(d, da.cout, B);
+      FM_TRY(k_conv3d_up_fprop(ctx, cur, m->encB[d].p, da.w_up_f, da.w_f, m->params + da.b_off, m->decA[d].p, B, dd.X,
+                               dd.Y, dd.Z, da.c1, da.c2, da.cout, 1));
+    } else {
+      FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B), m->pz));
+      FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
+    }
     FM_TRY(conv_fwd(m, db, m->decA[d].p, nullptr, m->decB[d].p, B));
     cur = m->decB[d].p;
   }
@@ -812,8 +853,9 @@ static int forward(fm_model* m, int B) {
   return FM_OK;
 }
 
-// wgrad + bias grad of one conv layer
-static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2, const bf16* dy, int B) {
+// wgrad + bias grad of one conv layer (only_src >= 0: the weight gradient of that source alone, plus the bias)
+static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2, const bf16* dy, int B,
+                      int only_src = -1) {
   fm_ctx* ctx = m->ctx;
   const Dims5 d = m->dims(l.level, l.cout, B);
   float* dw = m->grads + l.w_off;
@@ -826,6 +868,10 @@ static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x
     return !(e && e[0] == '1');
   }();
   for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
+    if (only_src >= 0 && s != only_src) {
+      cofs += cs[s];
+      continue;
+    }
     if (use_march() && conv_wgrad_march_supported(d.X, d.Y, d.Z, cs[s], l.cout, l.k)) {
       // the marching kernel also sums dY over the voxels (bias gradient) while the tiles sit in shared memory
       const bool with_bias = fold_bias && !bias_done;
@@ -841,6 +887,10 @@ static int conv_wgrad(fm_model* m, const Layer& l, const bf16* x1, const bf16* x
   }
   if (!bias_done) FM_TRY(k_bias_grad(ctx, dy, m->grads + l.b_off, d.voxels(), l.cout));
   return FM_OK;
+}
+
+static int conv_wgrad_source(fm_model* m, const Layer& l, int src, const bf16* x, const bf16* dy, int B) {
+  return conv_wgrad(m, l, src == 0 ? x : nullptr, src == 1 ? x : nullptr, dy, B, src);
 }
 
 // dgrad of one source of a conv layer: dx = conv(dy, W flipped^T) [* ReLU mask of `mask`]
@@ -886,15 +936,35 @@ static int backward(fm_model* m, int B) {
     FM_TRY(conv_wgrad(m, db, m->decA[d].p, nullptr, m->gDecB[d].p, B));
     FM_TRY(mark_layer_done(m, db));
     FM_TRY(conv_dgrad(m, db, 0, m->gDecB[d].p, m->decA[d].p, m->gDecA[d].p, B));
-    // dec_a: inputs [up[d], encB[d]]
-    FM_TRY(conv_wgrad(m, da, m->up[d].p, m->encB[d].p, m->gDecA[d].p, B));
-    FM_TRY(mark_layer_done(m, da));
-    FM_TRY(conv_dgrad(m, da, 0, m->gDecA[d].p, nullptr, m->gUp[d].p, B));
-    FM_TRY(conv_dgrad(m, da, 1, m->gDecA[d].p, nullptr, m->gSkip[d].p, B));
-    // through UpSampling3D into the coarser tensor that was upsampled (+ its ReLU mask)
+    // dec_a: inputs [up[d], encB[d]]; the coarser tensor that was upsampled and its ReLU mask
     const bool bottom = (d + 1 == D - 1);
     const bf16* act = bottom ? m->encB[D - 1].p : m->decB[d + 1].p;
     bf16* gdst = bottom ? m->gEncB[D - 1].p : m->gDecB[d + 1].p;
+    if (da.up_coarse) {
+      // weight gradient of the up-source channels from the 64 class taps at coarse resolution, folded onto the 27
+      // taps; the skip channels and the bias through the ordinary kernels; the gradient towards the coarse tensor
+      // straight from dY (no gUp tensor, no sum-pool pass)
+      const Dims5 dd = m->dims(d, da.cout, B);
+      FM_TRY(k_zero(ctx, da.dw_up, (size_t)da.cout * 64 * da.c1 * sizeof(float)));
+      FM_TRY(k_conv3d_up_wgrad(ctx, act, m->gDecA[d].p, da.dw_up, B, dd.X, dd.Y, dd.Z, da.c1, da.cout));
+      FM_TRY(k_fold_up_wgrad(ctx, da.dw_up, m->grads + da.w_off, da.cout, da.c1, da.cin()));
+      FM_TRY(conv_wgrad_source(m, da, 1, m->encB[d].p, m->gDecA[d].p, B));
+      FM_TRY(mark_layer_done(m, da));
+      FM_TRY(k_conv3d_up_dgrad(ctx, m->gDecA[d].p, da.w_up_d, gdst, act, B, dd.X, dd.Y, dd.Z, da.cout, da.c1));
+      FM_TRY(conv_dgrad(m, da, 1, m->gDecA[d].p, nullptr, m->gSkip[d].p, B));
+      continue;
+    }
+    FM_TRY(conv_wgrad(m, da, m->up[d].p, m->encB[d].p, m->gDecA[d].p, B));
+    FM_TRY(mark_layer_done(m, da));
+    if (da.up_dgrad) {
+      const Dims5 dd = m->dims(d, da.cout, B);
+      FM_TRY(k_conv3d_up_dgrad(ctx, m->gDecA[d].p, da.w_up_d, gdst, act, B, dd.X, dd.Y, dd.Z, da.cout, da.c1));
+      FM_TRY(conv_dgrad(m, da, 1, m->gDecA[d].p, nullptr, m->gSkip[d].p, B));
+      continue;
+    }
+    FM_TRY(conv_dgrad(m, da, 0, m->gDecA[d].p, nullptr, m->gUp[d].p, B));
+    FM_TRY(conv_dgrad(m, da, 1, m->gDecA[d].p, nullptr, m->gSkip[d].p, B));
+    // through UpSampling3D into the coarser tensor that was upsampled (+ its ReLU mask)
     FM_TRY(k_upsample3d_bwd(ctx, m->gUp[d].p, act, gdst, m->dims(d + 1, da.c1, B), da.c1, 0, m->pz));
   }
   for (int d = D - 1; d >= 0; --d) {
@@ -2233,6 +2303,72 @@ extern "C" int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const f
   if (dbias) FM_CUDA(cudaMemcpyAsync(dbias, db, (size_t)Cout * 4, cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));
   packed_to_keras(packed.data(), dw_keras, ksize, Cin, Cout);
+  return FM_OK;
+}
+
+// Decoder convolution over concatenate([UpSampling3D(2)(coarse), skip]) computed at coarse resolution (test hooks for
+// k_conv3d_up_*). coarse [N, X/2, Y/2, Z/2, Cc], skip [N, X, Y, Z, Cs], w_keras (3,3,3,Cc+Cs,Cout), y [N, X, Y, Z, Cout].
+extern "C" int fm_op_conv3d_up_fprop(fm_ctx* ctx, const float* coarse, const float* skip, const float* w_keras,
+                                     const float* bias, int N, int X, int Y, int Z, int Cc, int Cs, int Cout, int relu,
+                                     float* y) {
+  FM_CHECK(ctx && coarse && skip && w_keras && y, FM_EINVAL, "fm_op_conv3d_up_fprop: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t vox = (size_t)N * X * Y * Z;
+  const int Ct = Cc + Cs;
+  std::vector<float> packed((size_t)Cout * 27 * Ct);
+  keras_to_packed(w_keras, packed.data(), 3, Ct, Cout);
+  bf16 *dc = nullptr, *dsk = nullptr, *wf = nullptr, *wup = nullptr, *dy = nullptr;
+  float *wm = nullptr, *dbias = nullptr;
+  FM_TRY(s.up_bf16(coarse, vox / 8 * Cc, &dc));
+  FM_TRY(s.up_bf16(skip, vox * Cs, &dsk));
+  FM_TRY(s.up_bf16(packed.data(), packed.size(), &wf));
+  FM_TRY(s.up_f32(packed.data(), packed.size(), &wm));
+  FM_TRY(s.alloc(&wup, (size_t)Cout * 64 * Cc));
+  if (bias) FM_TRY(s.up_f32(bias, Cout, &dbias));
+  FM_TRY(s.alloc(&dy, vox * Cout));
+  FM_TRY(k_repack_up(ctx, wm, wup, nullptr, Cout, Cc, Ct));
+  FM_TRY(k_conv3d_up_fprop(ctx, dc, dsk, wup, wf, dbias, dy, N, X, Y, Z, Cc, Cs, Cout, relu));
+  return s.down_bf16(dy, vox * Cout, y);
+}
+
+// Backward of the same layer towards the coarse tensor: dcoarse [N, X/2, Y/2, Z/2, Cc] (times coarse > 0 when
+// apply_mask) and the weight gradient of the up-source channels dw_up_keras (3,3,3,Cc,Cout).
+extern "C" int fm_op_conv3d_up_bwd(fm_ctx* ctx, const float* coarse, const float* dy, const float* w_keras, int N,
+                                   int X, int Y, int Z, int Cc, int Cs, int Cout, int apply_mask, float* dcoarse,
+                                   float* dw_up_keras) {
+  FM_CHECK(ctx && coarse && dy && w_keras, FM_EINVAL, "fm_op_conv3d_up_bwd: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t vox = (size_t)N * X * Y * Z;
+  const int Ct = Cc + Cs;
+  std::vector<float> packed((size_t)Cout * 27 * Ct);
+  keras_to_packed(w_keras, packed.data(), 3, Ct, Cout);
+  bf16 *dc = nullptr, *ddy = nullptr, *wupd = nullptr, *dgc = nullptr;
+  float *wm = nullptr, *dwu = nullptr, *dw = nullptr;
+  FM_TRY(s.up_bf16(coarse, vox / 8 * Cc, &dc));
+  FM_TRY(s.up_bf16(dy, vox * Cout, &ddy));
+  FM_TRY(s.up_f32(packed.data(), packed.size(), &wm));
+  FM_TRY(s.alloc(&wupd, (size_t)Cout * 64 * Cc));
+  FM_TRY(k_repack_up(ctx, wm, nullptr, wupd, Cout, Cc, Ct));
+  if (dcoarse) {
+    FM_TRY(s.alloc(&dgc, vox / 8 * Cc));
+    FM_TRY(k_conv3d_up_dgrad(ctx, ddy, wupd, dgc, apply_mask ? dc : nullptr, N, X, Y, Z, Cout, Cc));
+    FM_TRY(s.down_bf16(dgc, vox / 8 * Cc, dcoarse));
+  }
+  if (dw_up_keras) {
+    const size_t nu = (size_t)Cout * 64 * Cc, nw = (size_t)Cout * 27 * Cc;
+    FM_TRY(s.alloc(&dwu, nu));
+    FM_TRY(s.alloc(&dw, nw));
+    FM_TRY(k_zero(ctx, dwu, nu * 4));
+    FM_TRY(k_zero(ctx, dw, nw * 4));
+    FM_TRY(k_conv3d_up_wgrad(ctx, dc, ddy, dwu, N, X, Y, Z, Cc, Cout));
+    FM_TRY(k_fold_up_wgrad(ctx, dwu, dw, Cout, Cc, Cc));
+    std::vector<float> host(nw);
+    FM_CUDA(cudaMemcpyAsync(host.data(), dw, nw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FM_CUDA(cudaStreamSynchronize(ctx->stream));
+    packed_to_keras(host.data(), dw_up_keras, 3, Cc, Cout);
+  }
   return FM_OK;
 }
 

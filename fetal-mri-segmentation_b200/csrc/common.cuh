@@ -270,6 +270,19 @@ int k_conv3d_tc_fprop(fm_ctx*, const bf16* x1, const bf16* x2, const bf16* w_pac
                       int Xin = 0, int Yin = 0, int Zin = 0);
 int k_conv3d_tc_wgrad(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y,
                       int Z, int Cin, int Cin_total, int cin_ofs, int Cout, int ksize);
+// Decoder convolution over concatenate([UpSampling3D(2)(coarse), skip]) (unet3d/unet.py:59-62,138) computed WITHOUT
+// the upsampled tensor: per parity class of the fine voxel the 27 taps over the upsampled source collapse into 8 taps over
+// the coarse tensor with summed weights. X, Y, Z = FINE extents; packs from k_repack_up (tap = class * 8 + j).
+int conv_up_supported(int X, int Y, int Z, int Cc, int Cs, int Cout);
+int k_repack_up(fm_ctx*, const float* w_master, bf16* w_up_f, bf16* w_up_d, int Cout, int Cc, int Ct);
+int k_conv3d_up_fprop(fm_ctx*, const bf16* coarse, const bf16* skip, const bf16* w_up, const bf16* w_packed,
+                      const float* bias, bf16* y, int N, int X, int Y, int Z, int Cc, int Cs, int Cout, int relu);
+int k_conv3d_up_dgrad(fm_ctx*, const bf16* dy, const bf16* w_up_d, bf16* dcoarse, const bf16* mask, int N, int X,
+                      int Y, int Z, int Cout, int Cc);
+// dw_up [Cout][64][Cc] fp32, zeroed by the caller; k_fold_up_wgrad adds it onto dW[co][27][Ct] (channels [0, Cc))
+int k_conv3d_up_wgrad(fm_ctx*, const bf16* coarse, const bf16* dy, float* dw_up, int N, int X, int Y, int Z, int Cc,
+                      int Cout);
+int k_fold_up_wgrad(fm_ctx*, const float* dw_up, float* dw_master, int Cout, int Cc, int Ct);
 
 // conv_march.cu
 int conv_march_supported(int X, int Y, int Z, int C1, int C2, int Cout, int ksize);

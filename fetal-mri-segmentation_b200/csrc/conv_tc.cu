@@ -47,6 +47,18 @@ struct alignas(64) FpropParams {
   int stages;
   int stride;         // 1, or 2 = strided conv with TF 'SAME' padding (Isensee in-convs, isensee2017.py:51)
   int pbx, pby, pbz;  // 'before' padding per axis (k/2 for stride 1; TF SAME for stride 2)
+  // Decoder convolutions over concatenate([UpSampling3D(2)(coarse), skip]) WITHOUT the upsampled tensor
+  // (unet3d/unet.py:59-62,138): a fine voxel 2c+p of parity class p only ever sees the 2x2x2 coarse neighbourhood
+  // c + {p-1, p} per axis, so per class the 27 taps over the upsampled source collapse into 8 taps over the coarse
+  // tensor with summed weights W'_p[j] (3.4x fewer MACs on that source).
+  //   upmode 1 (fprop): a tile is 128 coarse positions of ONE class; source 0 = coarse tensor, 8 taps at c0 + j - 1 + p
+  //            (weights [Cout][class*8 + j][Cc]); source 1 = the skip tensor read with traversal stride 2 at
+  //            2*c0 + p + t - 1 for the 27 ordinary taps; the epilogue writes the fine voxels 2c + p.
+  //   upmode 2 (dgrad to the coarse tensor): a tile is 128 coarse positions; the source is dY read with traversal
+  //            stride 2 at 2*(c0 - d) + q, d = j - 1 + q, for the 64 (class q, tap j) pairs (weights transposed).
+  int upmode;
+  int ntaps_s[2];     // taps per source (== ntaps unless upmode)
+  int oX, oY, oZ;     // extents of the OUTPUT tensor (fine grid in upmode 1; == X, Y, Z otherwise)
   const float* bias;
   bf16* out;
   const bf16* mask;
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles;  // m_tiles counts (coarse tile, class) pairs in upmode 1
   const int kxy = kext_xy(p.ksize), kzz = kext_z(p.ksize);
   const int pad = kxy >> 1, padz = kzz >> 1;
 
@@ -116,6 +128,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m = tile / p.n_tiles;
+      int cls = 0;
+      if (p.upmode == 1) {
+        cls = m & 7;
+        m >>= 3;
+      }
       const int iz = m % p.tz;
       m /= p.tz;
       const int iy = m % p.ty;
@@ -124,24 +141,60 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
       const int n = m / p.tx;
       const int x0 = ix * p.bx * p.stride - p.pbx, y0 = iy * p.by * p.stride - p.pby,
                 z0 = iz * p.bz * p.stride - p.pbz;
+      const int px = cls >> 2, py = (cls >> 1) & 1, pz = cls & 1;
       for (int s = 0; s < p.nsrc; ++s) {
         const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
         for (int ch = 0; ch < p.nchunks[s]; ++ch) {
-          int tap = 0;
-          for (int kx = 0; kx < kxy; ++kx)
-            for (int ky = 0; ky < kxy; ++ky)
-              for (int kz = 0; kz < kzz; ++kz, ++tap) {
-                mbar_wait(empty_bar(stage), ph ^ 1u);
-                mbar_expect_tx_elect(full_bar(stage), tx_bytes);
-                const uint32_t a_dst = smem0 + stage * stage_bytes;
-                tma_load_5d_elect(a_dst, &p.tmA[s], full_bar(stage), ch * p.KC[s], z0 + kz, y0 + ky, x0 + kx, n);
-                tma_load_3d_elect(a_dst + kABytes, &p.tmW[s], full_bar(stage), p.wcofs[s] + ch * p.KC[s], tap,
-                                  n_tile * p.block_n);
-                if (++stage == (uint32_t)p.stages) {
-                  stage = 0;
-                  ph ^= 1u;
+          if (p.upmode == 0) {
+            int tap = 0;
+            for (int kx = 0; kx < kxy; ++kx)
+              for (int ky = 0; ky < kxy; ++ky)
+                for (int kz = 0; kz < kzz; ++kz, ++tap) {
+                  mbar_wait(empty_bar(stage), ph ^ 1u);
+                  mbar_expect_tx_elect(full_bar(stage), tx_bytes);
+                  const uint32_t a_dst = smem0 + stage * stage_bytes;
+                  tma_load_5d_elect(a_dst, &p.tmA[s], full_bar(stage), ch * p.KC[s], z0 + kz, y0 + ky, x0 + kx, n);
+                  tma_load_3d_elect(a_dst + kABytes, &p.tmW[s], full_bar(stage), p.wcofs[s] + ch * p.KC[s], tap,
+                                    n_tile * p.block_n);
+                  if (++stage == (uint32_t)p.stages) {
+                    stage = 0;
+                    ph ^= 1u;
+                  }
                 }
+          } else {
+            // x0, y0, z0 are the coarse tile origin here (stride 1, no padding)
+            for (int tap = 0; tap < p.ntaps_s[s]; ++tap) {
+              int ax, ay, az, wtap;
+              if (p.upmode == 1 && s == 0) {        // coarse source, 8 taps of this class
+                ax = x0 + (tap >> 2) - 1 + px;
+                ay = y0 + ((tap >> 1) & 1) - 1 + py;
+                az = z0 + (tap & 1) - 1 + pz;
+                wtap = cls * 8 + tap;
+              } else if (p.upmode == 1) {           // skip source at fine resolution, every second voxel
+                ax = 2 * x0 + px + tap / 9 - 1;
+                ay = 2 * y0 + py + (tap / 3) % 3 - 1;
+                az = 2 * z0 + pz + tap % 3 - 1;
+                wtap = tap;
+              } else {                              // dY at fine resolution: class q = tap / 8, coarse tap j = tap % 8
+                const int q = tap >> 3, j = tap & 7;
+                const int qx = q >> 2, qy = (q >> 1) & 1, qz = q & 1;
+                ax = 2 * (x0 - ((j >> 2) - 1 + qx)) + qx;
+                ay = 2 * (y0 - (((j >> 1) & 1) - 1 + qy)) + qy;
+                az = 2 * (z0 - ((j & 1) - 1 + qz)) + qz;
+                wtap = tap;
               }
+              mbar_wait(empty_bar(stage), ph ^ 1u);
+              mbar_expect_tx_elect(full_bar(stage), tx_bytes);
+              const uint32_t a_dst = smem0 + stage * stage_bytes;
+              tma_load_5d_elect(a_dst, &p.tmA[s], full_bar(stage), ch * p.KC[s], az, ay, ax, n);
+              tma_load_3d_elect(a_dst + kABytes, &p.tmW[s], full_bar(stage), p.wcofs[s] + ch * p.KC[s], wtap,
+                                n_tile * p.block_n);
+              if (++stage == (uint32_t)p.stages) {
+                stage = 0;
+                ph ^= 1u;
+              }
+            }
+          }
         }
       }
     }
@@ -159,7 +212,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
         const uint32_t row_bytes = (uint32_t)p.KC[s] * 2u;
         const uint32_t hi32 = desc_hi(8u * row_bytes, layout_code((int)row_bytes));
         const int nk = p.KC[s] >> 4;
-        const int nst = p.nchunks[s] * p.ntaps;
+        const int nst = p.nchunks[s] * p.ntaps_s[s];
         for (int i = 0; i < nst; ++i) {
           mbar_wait(full_bar(stage), ph);
           tc_fence_after();
@@ -189,15 +242,25 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
       const uint32_t acc = tcount & 1u, acc_ph = (tcount >> 1) & 1u;
       const int n_tile = tile % p.n_tiles;
       int m = tile / p.n_tiles;
+      int cls = 0;
+      if (p.upmode == 1) {
+        cls = m & 7;
+        m >>= 3;
+      }
       const int iz = m % p.tz;
       m /= p.tz;
       const int iy = m % p.ty;
       m /= p.ty;
       const int ix = m % p.tx;
       const int n = m / p.tx;
-      const int x = ix * p.bx + rx, y = iy * p.by + ry, z = iz * p.bz + rz;
+      int x = ix * p.bx + rx, y = iy * p.by + ry, z = iz * p.bz + rz;
       const bool valid = (x < p.X) && (y < p.Y) && (z < p.Z);
-      const int64_t v = (((int64_t)n * p.X + x) * p.Y + y) * p.Z + z;
+      if (p.upmode == 1) {  // row = coarse position c of class p: the fine voxel 2c + p
+        x = 2 * x + (cls >> 2);
+        y = 2 * y + ((cls >> 1) & 1);
+        z = 2 * z + (cls & 1);
+      }
+      const int64_t v = (((int64_t)n * p.oX + x) * p.oY + y) * p.oZ + z;
       const int64_t off = v * p.out_C + p.out_cofs + n_tile * p.block_n;
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -283,6 +346,10 @@ struct alignas(64) WgradParams {
   int ksize, ntaps;
   int Ct, cofs, Cout;  // dW layout [Cout][ntaps][Ct], this source at channel offset cofs
   int stages;
+  // upmode 1: weight gradient of the 64 class-combined taps of a decoder convolution over the COARSE tensor
+  // (see FpropParams::upmode): X = coarse tensor, dY read with traversal stride 2 at 2c + p; a work item carries the
+  // class p and accumulates its 8 taps; dW layout [Cout][64 = class*8 + j][Ct]. N, X, Y, Z are the coarse extents.
+  int upmode;
   float* dw;
 };
 
@@ -333,8 +400,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // work item decode: blockIdx.x = ((split * n_nblocks + nb) * n_cchunks + cc) * n_gsub + gs
+  // work item decode: blockIdx.x = (((split * n_nblocks + nb) * n_cchunks + cc) * n_gsub + gs) [* 8 + class]
   int w = blockIdx.x;
+  int cls = 0;
+  if (p.upmode) {
+    cls = w & 7;
+    w >>= 3;
+  }
+  const int cpx = cls >> 2, cpy = (cls >> 1) & 1, cpz = cls & 1;
   const int gs = w % p.n_gsub;
   w /= p.n_gsub;
   const int cc = w % p.n_cchunks;
@@ -372,15 +445,21 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
       mbar_expect_tx_elect(dyfull_bar(b), dy_bytes);
       for (int j = 0; j < p.NB / p.NC; ++j)
         tma_load_5d_elect(dy0 + b * dy_bytes + (uint32_t)j * dy_sub_bytes, &p.tmDY, dyfull_bar(b),
-                          nb * p.NB + j * p.NC, z0, y0, x0, n);
+                          nb * p.NB + j * p.NC, p.upmode ? 2 * z0 + cpz : z0, p.upmode ? 2 * y0 + cpy : y0,
+                          p.upmode ? 2 * x0 + cpx : x0, n);
       for (int gi = 0; gi < g_count; ++gi) {
         mbar_wait(empty_bar(stage), ph ^ 1u);
         mbar_expect_tx_elect(full_bar(stage), (uint32_t)p.g * tap_tile_bytes);
         for (int t = 0; t < p.g; ++t) {
           const int tap = min((g_first + gi) * p.g + t, p.ntaps - 1);  // pad group with a repeat
-          const int dz = tap % kzz - padz;
-          const int dy = (tap / kzz) % kxy - pad;
-          const int dx = tap / (kzz * kxy) - pad;
+          int dz = tap % kzz - padz;
+          int dy = (tap / kzz) % kxy - pad;
+          int dx = tap / (kzz * kxy) - pad;
+          if (p.upmode) {  // tap = j of this class: coarse offset j - 1 + p per axis
+            dx = (tap >> 2) - 1 + cpx;
+            dy = ((tap >> 1) & 1) - 1 + cpy;
+            dz = (tap & 1) - 1 + cpz;
+          }
           tma_load_5d_elect(smem0 + stage * a_slot + (uint32_t)t * tap_tile_bytes, &p.tmX, full_bar(stage),
                             cc * p.KC, z0 + dz, y0 + dy, x0 + dx, n);
         }
@@ -432,8 +511,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
     tc_fence_after();
     if (mt1 > mt0) {
       for (int gi = 0; gi < g_count; ++gi) {
-        const int tap = (g_first + gi) * p.g + t_in_g;
+        int tap = (g_first + gi) * p.g + t_in_g;
         const bool valid = tap < p.ntaps;
+        int ntaps_out = p.ntaps;
+        if (p.upmode) {
+          tap += cls * 8;
+          ntaps_out = 64;
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * p.NB);
         for (int c16 = 0; c16 < p.NB / 16; ++c16) {
           uint32_t r[16];
@@ -443,7 +527,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_wgrad_kernel(
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int co = nb * p.NB + c16 * 16 + j;
-              atomicAdd(p.dw + ((int64_t)co * p.ntaps + tap) * p.Ct + p.cofs + cc * p.KC + ci,
+              atomicAdd(p.dw + ((int64_t)co * ntaps_out + tap) * p.Ct + p.cofs + cc * p.KC + ci,
                         __uint_as_float(r[j]));
             }
           }
@@ -590,6 +674,11 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   p.out = y;
   p.mask = mask;
   p.stride = stride;
+  p.upmode = 0;
+  p.ntaps_s[0] = p.ntaps_s[1] = p.ntaps;
+  p.oX = X;
+  p.oY = Y;
+  p.oZ = Z;
   {
     // TF 'SAME': pad_total = max((out-1)*stride + k - in, 0), pad_before = pad_total / 2
     auto pb = [&](int out, int in, int k) { return std::max((out - 1) * stride + k - in, 0) / 2; };
@@ -625,6 +714,257 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_tc_dgrad" : "conv3d_tc_fprop",
                  2.0 * p.ntaps * Ct * Cout * vox, vox * (Ct + Cout) * 2.0);
   FM_CUDA(launch_pdl(conv3d_tc_fprop_kernel, dim3(grid), dim3(kThreadsTc), smem, ctx->stream, p));
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder convolutions at coarse resolution (see FpropParams::upmode)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int launch_tc_fprop(fm_ctx* ctx, FpropParams& p, const char* name, double flops, double bytes) {
+  const uint32_t stage_bytes = kABytes + (uint32_t)p.block_n * 128u;
+  int stages = (kMaxDynSmem - 2048) / (int)stage_bytes;
+  stages = std::max(2, std::min(stages, 8));
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FM_CUDA(cudaFuncSetAttribute(conv3d_tc_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.m_tiles * p.n_tiles, ctx->num_sms);
+  ProfScope prof(ctx, name, flops, bytes);
+  FM_CUDA(launch_pdl(conv3d_tc_fprop_kernel, dim3(grid), dim3(kThreadsTc), smem, ctx->stream, p));
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// W'_p[j] = sum of the taps t with floor((p + t - 1) / 2) == j - 1 + p per axis (nearest-neighbour upsampling by 2)
+__device__ __forceinline__ bool tap_in_class(int p, int j, int t) { return ((p + t + 1) >> 1) - 1 == j - 1 + p; }
+
+// master [Cout][27][Ct] fp32 (up source = channels [0, Cc)) -> wf [Cout][64][Cc] and wd [Cc][64][Cout], bf16,
+// tap index = class * 8 + j, class = (px*2 + py)*2 + pz, j = (jx*2 + jy)*2 + jz
+__global__ void __launch_bounds__(256) repack_up_kernel(const float* __restrict__ w, bf16* __restrict__ wf,
+                                                        bf16* __restrict__ wd, int Cout, int Cc, int Ct) {
+  FM_PDL_SYNC();
+  const int64_t total = (int64_t)Cout * 64 * Cc;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int ci = (int)(g % Cc);
+  const int pj = (int)((g / Cc) % 64);
+  const int co = (int)(g / ((int64_t)Cc * 64));
+  const int cls = pj >> 3, j = pj & 7;
+  const int px = cls >> 2, py = (cls >> 1) & 1, pz = cls & 1;
+  const int jx = j >> 2, jy = (j >> 1) & 1, jz = j & 1;
+  float acc = 0.f;
+  for (int tx = 0; tx < 3; ++tx) {
+    if (!tap_in_class(px, jx, tx)) continue;
+    for (int ty = 0; ty < 3; ++ty) {
+      if (!tap_in_class(py, jy, ty)) continue;
+      for (int tz = 0; tz < 3; ++tz) {
+        if (!tap_in_class(pz, jz, tz)) continue;
+        acc += w[((int64_t)co * 27 + (tx * 3 + ty) * 3 + tz) * Ct + ci];
+      }
+    }
+  }
+  const bf16 v = __float2bfloat16(acc);
+  if (wf) wf[g] = v;
+  if (wd) wd[((int64_t)ci * 64 + pj) * Cout + co] = v;
+}
+
+// dW[co][t][ci] += sum over the classes p of dW'_p[j(p, t)][co][ci]: the 64 class-tap gradients folded back onto the
+// 27 taps of the master kernel (every tap belongs to exactly one j per class)
+__global__ void __launch_bounds__(256) fold_up_wgrad_kernel(const float* __restrict__ dwu, float* __restrict__ dw,
+                                                            int Cout, int Cc, int Ct) {
+  FM_PDL_SYNC();
+  const int64_t total = (int64_t)Cout * 27 * Cc;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const int ci = (int)(g % Cc);
+  const int t = (int)((g / Cc) % 27);
+  const int co = (int)(g / ((int64_t)Cc * 27));
+  const int tx = t / 9, ty = (t / 3) % 3, tz = t % 3;
+  float acc = 0.f;
+#pragma unroll
+  for (int cls = 0; cls < 8; ++cls) {
+    const int px = cls >> 2, py = (cls >> 1) & 1, pz = cls & 1;
+    const int jx = ((px + tx + 1) >> 1) - px, jy = ((py + ty + 1) >> 1) - py, jz = ((pz + tz + 1) >> 1) - pz;
+    acc += dwu[((int64_t)co * 64 + cls * 8 + (jx * 2 + jy) * 2 + jz) * Cc + ci];
+  }
+  dw[((int64_t)co * 27 + t) * Ct + ci] += acc;
+}
+
+}  // namespace
+
+int conv_up_supported(int X, int Y, int Z, int Cc, int Cs, int Cout) {
+  if (X % 2 || Y % 2 || Z % 2) return 0;
+  if (!chan_ok(Cc) || !chan_ok(Cs) || !chan_ok(Cout)) return 0;
+  if (!(Cout == 16 || Cout == 32 || Cout == 64 || (Cout >= 128 && Cout % 128 == 0))) return 0;
+  if (!(Cc == 16 || Cc == 32 || Cc == 64 || (Cc >= 128 && Cc % 128 == 0))) return 0;  // N blocks of the dgrad
+  return 1;
+}
+
+int k_repack_up(fm_ctx* ctx, const float* w_master, bf16* w_up_f, bf16* w_up_d, int Cout, int Cc, int Ct) {
+  const int64_t total = (int64_t)Cout * 64 * Cc;
+  ProfScope prof(ctx, "repack_up", 0.0, (double)total * 12.0);
+  FM_CUDA(launch_pdl(repack_up_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, ctx->stream, w_master,
+                     w_up_f, w_up_d, Cout, Cc, Ct));
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_fold_up_wgrad(fm_ctx* ctx, const float* dw_up, float* dw_master, int Cout, int Cc, int Ct) {
+  const int64_t total = (int64_t)Cout * 27 * Cc;
+  ProfScope prof(ctx, "fold_up_wgrad", 0.0, (double)total * 40.0);
+  FM_CUDA(launch_pdl(fold_up_wgrad_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, ctx->stream, dw_up,
+                     dw_master, Cout, Cc, Ct));
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// y[fine] = act(conv3x3x3(concatenate([upsample2(coarse), skip])) + bias), fine extents X, Y, Z
+int k_conv3d_up_fprop(fm_ctx* ctx, const bf16* coarse, const bf16* skip, const bf16* w_up, const bf16* w_packed,
+                      const float* bias, bf16* y, int N, int X, int Y, int Z, int Cc, int Cs, int Cout, int relu) {
+  FM_CHECK(conv_up_supported(X, Y, Z, Cc, Cs, Cout), FM_EINVAL, "conv3d up fprop: unsupported %dx%dx%d Cc=%d Cs=%d Cout=%d",
+           X, Y, Z, Cc, Cs, Cout);
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  const int Xc = X / 2, Yc = Y / 2, Zc = Z / 2;
+  p.nsrc = 2;
+  p.N = N;
+  p.X = Xc;
+  p.Y = Yc;
+  p.Z = Zc;
+  p.oX = X;
+  p.oY = Y;
+  p.oZ = Z;
+  choose_box(Xc, Yc, Zc, &p.bx, &p.by, &p.bz);
+  p.tx = ceil_div(Xc, p.bx);
+  p.ty = ceil_div(Yc, p.by);
+  p.tz = ceil_div(Zc, p.bz);
+  p.m_tiles = N * p.tx * p.ty * p.tz * 8;
+  p.block_n = std::min(Cout, 128);
+  p.n_tiles = Cout / p.block_n;
+  p.ksize = 3;
+  p.ntaps = 27;
+  p.ntaps_s[0] = 8;
+  p.ntaps_s[1] = 27;
+  p.upmode = 1;
+  p.out_C = Cout;
+  p.out_cofs = 0;
+  p.relu = relu;
+  p.bias = bias;
+  p.out = y;
+  p.mask = nullptr;
+  p.stride = 1;
+  p.KC[0] = chunk_of(Cc);
+  p.nchunks[0] = Cc / p.KC[0];
+  p.wcofs[0] = 0;
+  p.KC[1] = chunk_of(Cs);
+  p.nchunks[1] = Cs / p.KC[1];
+  p.wcofs[1] = Cc;
+  FM_TRY(make_act_tmap(&p.tmA[0], coarse, N, Xc, Yc, Zc, Cc, p.KC[0], p.bz, p.by, p.bx));
+  FM_TRY(make_w_tmap(&p.tmW[0], w_up, Cout, 64, Cc, p.KC[0], p.block_n));
+  FM_TRY(make_act_tmap(&p.tmA[1], skip, N, X, Y, Z, Cs, p.KC[1], p.bz, p.by, p.bx, 2));
+  FM_TRY(make_w_tmap(&p.tmW[1], w_packed, Cout, 27, Cc + Cs, p.KC[1], p.block_n));
+  const double vox = (double)N * X * Y * Z;
+  // algorithmic FLOPs of the reference layer (27 taps over every fine voxel); executed: 8 taps on the coarse source
+  return launch_tc_fprop(ctx, p, "conv3d_up_fprop", 2.0 * 27 * (Cc + Cs) * Cout * vox,
+                         vox * ((double)Cc / 8 + Cs + Cout) * 2.0);
+}
+
+// dcoarse = (gradient of the layer above w.r.t. the coarse tensor) [* ReLU mask]: dy fine [N,X,Y,Z,Cout]
+int k_conv3d_up_dgrad(fm_ctx* ctx, const bf16* dy, const bf16* w_up_d, bf16* dcoarse, const bf16* mask, int N, int X,
+                      int Y, int Z, int Cout, int Cc) {
+  FM_CHECK(conv_up_supported(X, Y, Z, Cc, Cout, Cout), FM_EINVAL, "conv3d up dgrad: unsupported %dx%dx%d Cc=%d Cout=%d", X,
+           Y, Z, Cc, Cout);
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  const int Xc = X / 2, Yc = Y / 2, Zc = Z / 2;
+  p.nsrc = 1;
+  p.N = N;
+  p.X = p.oX = Xc;
+  p.Y = p.oY = Yc;
+  p.Z = p.oZ = Zc;
+  choose_box(Xc, Yc, Zc, &p.bx, &p.by, &p.bz);
+  p.tx = ceil_div(Xc, p.bx);
+  p.ty = ceil_div(Yc, p.by);
+  p.tz = ceil_div(Zc, p.bz);
+  p.m_tiles = N * p.tx * p.ty * p.tz;
+  p.block_n = std::min(Cc, 128);
+  p.n_tiles = Cc / p.block_n;
+  p.ksize = 3;
+  p.ntaps = 64;
+  p.ntaps_s[0] = 64;
+  p.upmode = 2;
+  p.out_C = Cc;
+  p.out_cofs = 0;
+  p.relu = 0;
+  p.bias = nullptr;
+  p.out = dcoarse;
+  p.mask = mask;
+  p.stride = 1;
+  p.KC[0] = chunk_of(Cout);
+  p.nchunks[0] = Cout / p.KC[0];
+  p.wcofs[0] = 0;
+  FM_TRY(make_act_tmap(&p.tmA[0], dy, N, X, Y, Z, Cout, p.KC[0], p.bz, p.by, p.bx, 2));
+  FM_TRY(make_w_tmap(&p.tmW[0], w_up_d, Cc, 64, Cout, p.KC[0], p.block_n));
+  const double vox = (double)N * X * Y * Z;
+  // algorithmic: the fine-resolution dgrad towards the upsampled source (27 taps per fine voxel) + its 2^3 sum-pool
+  return launch_tc_fprop(ctx, p, "conv3d_up_dgrad", 2.0 * 27 * Cc * Cout * vox, vox * ((double)Cc / 8 + Cout) * 2.0);
+}
+
+// dw_up [Cout][64][Cc] fp32 (zeroed by the caller) += class-combined weight gradients; fine extents X, Y, Z
+int k_conv3d_up_wgrad(fm_ctx* ctx, const bf16* coarse, const bf16* dy, float* dw_up, int N, int X, int Y, int Z,
+                      int Cc, int Cout) {
+  FM_CHECK(conv_up_supported(X, Y, Z, Cc, Cout, Cout), FM_EINVAL, "conv3d up wgrad: unsupported %dx%dx%d Cc=%d Cout=%d", X,
+           Y, Z, Cc, Cout);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  const int Xc = X / 2, Yc = Y / 2, Zc = Z / 2;
+  p.N = N;
+  p.X = Xc;
+  p.Y = Yc;
+  p.Z = Zc;
+  choose_box(Xc, Yc, Zc, &p.bx, &p.by, &p.bz);
+  p.tx = ceil_div(Xc, p.bx);
+  p.ty = ceil_div(Yc, p.by);
+  p.tz = ceil_div(Zc, p.bz);
+  p.m_tiles = N * p.tx * p.ty * p.tz;
+  p.ksize = 3;
+  p.ntaps = 8;
+  p.upmode = 1;
+  p.KC = chunk_of(Cc);
+  p.n_cchunks = Cc / p.KC;
+  p.g = kTileM / p.KC;
+  p.ngroups = ceil_div(p.ntaps, p.g);
+  p.NB = std::min(Cout, 128);
+  p.NC = std::min(p.NB, 64);
+  p.n_nblocks = Cout / p.NB;
+  p.G = std::min(p.ngroups, 512 / p.NB);
+  p.n_gsub = ceil_div(p.ngroups, p.G);
+  p.Ct = Cc;
+  p.cofs = 0;
+  p.Cout = Cout;
+  p.dw = dw_up;
+  const int items = p.n_gsub * p.n_cchunks * p.n_nblocks * 8;
+  int splits = std::max(1, (2 * ctx->num_sms) / items);
+  splits = std::min(splits, p.m_tiles);
+  p.splits = splits;
+  FM_TRY(make_act_tmap(&p.tmX, coarse, N, Xc, Yc, Zc, Cc, p.KC, p.bz, p.by, p.bx));
+  FM_TRY(make_act_tmap(&p.tmDY, dy, N, X, Y, Z, Cout, p.NC, p.bz, p.by, p.bx, 2));
+  const uint32_t dy_bytes = (uint32_t)kTileM * (uint32_t)p.NB * 2u;
+  int stages = (kMaxDynSmem - 2048 - 2 * (int)dy_bytes) / 32768;
+  stages = std::max(2, std::min(stages, 5));
+  p.stages = stages;
+  const size_t smem = (size_t)stages * 32768 + 2 * dy_bytes + 1024 + 256;
+  FM_CUDA(cudaFuncSetAttribute(conv3d_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  const double vox = (double)N * X * Y * Z;
+  // algorithmic: the fine-resolution weight gradient over the upsampled source (27 taps per fine voxel)
+  ProfScope prof(ctx, "conv3d_up_wgrad", 2.0 * 27 * Cc * Cout * vox, vox * ((double)Cc / 8 + Cout) * 2.0);
+  FM_CUDA(launch_pdl(conv3d_tc_wgrad_kernel, dim3(items * splits), dim3(kThreadsTc), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

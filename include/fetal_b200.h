@@ -320,6 +320,18 @@ int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const float* w_ke
                        float* dx);
 int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const float* dy, int N, int X, int Y,
                        int Z, int Cin, int Cout, float* dw_keras, float* dbias);
+/* Decoder convolution Conv3D(3x3x3, 'same') over concatenate([UpSampling3D(2)(coarse), skip], axis=1)
+ * (fetal_net/model/unet3d/unet.py:59-62,138 with get_up_convolution's UpSampling3D) computed WITHOUT the upsampled
+ * tensor: per parity class of the fine voxel the 27 taps over the upsampled source collapse into 8 taps over the coarse
+ * tensor with summed weights (3.4x fewer MACs on that source). Channels-last float32 in/out, bf16 arithmetic inside.
+ * coarse [N,X/2,Y/2,Z/2,Cc], skip [N,X,Y,Z,Cs], w_keras (3,3,3,Cc+Cs,Cout), y / dy [N,X,Y,Z,Cout]. */
+int fm_op_conv3d_up_fprop(fm_ctx* ctx, const float* coarse, const float* skip, const float* w_keras, const float* bias,
+                          int N, int X, int Y, int Z, int Cc, int Cs, int Cout, int relu, float* y);
+/* Its backward towards the coarse tensor: dcoarse [N,X/2,Y/2,Z/2,Cc] (ReLU-masked by coarse > 0 when apply_mask) and the
+ * weight gradient of the up-source channels dw_up_keras (3,3,3,Cc,Cout); either output may be NULL. */
+int fm_op_conv3d_up_bwd(fm_ctx* ctx, const float* coarse, const float* dy, const float* w_keras, int N, int X, int Y,
+                        int Z, int Cc, int Cs, int Cout, int apply_mask, float* dcoarse, float* dw_up_keras);
+
 int fm_op_maxpool3d(fm_ctx* ctx, const float* x, int N, int X, int Y, int Z, int C, float* y);
 int fm_op_maxpool3d_bwd(fm_ctx* ctx, const float* x, const float* dy, const float* dskip, int N,
                         int X, int Y, int Z, int C, float* dx);

@@ -157,6 +157,64 @@ def conv_wgrad_case(ctx, impl, case, seed=2):
     return e <= 2e-3, e / 2e-3
 
 
+# decoder convolutions at coarse resolution: name, N, X, Y, Z (fine), Cc (coarse / up source), Cs (skip), Cout
+UP_CASES = [
+    ("up_dec2a_16cube", 1, 16, 16, 16, 256, 128, 128),   # dec2a of the depth-4 / 16-filter U-Net (2 N tiles in dgrad)
+    ("up_dec1a_32cube", 1, 32, 32, 32, 128, 64, 64),     # dec1a
+    ("up_dec0a_16cube", 2, 16, 16, 16, 64, 32, 32),      # dec0a channel mix (mixed swizzle widths)
+    ("up_ragged_12x20x8", 2, 12, 20, 8, 64, 64, 64),     # coarse extents 6x10x4: partial boxes / clipping
+    ("up_small_4cube", 3, 4, 4, 4, 32, 16, 16),          # coarse box larger than the tensor
+]
+
+
+def _up_reference(coarse, skip, w, b, dy=None):
+    """torch fp64: conv3d(concatenate([nearest-upsample x2 (coarse), skip])) and its gradients."""
+    ct = cl_to_cf(coarse).double().requires_grad_(True)
+    up = F.interpolate(ct, scale_factor=2, mode="nearest")
+    wt = keras_to_torch_w(w).double().requires_grad_(True)
+    out = F.conv3d(torch.cat([up, cl_to_cf(skip).double()], 1), wt, None if b is None else torch.as_tensor(b).double(),
+                   padding=1)
+    if dy is None:
+        return out
+    out.backward(cl_to_cf(dy).double())
+    return cf_to_cl(ct.grad), wt.grad.permute(2, 3, 4, 1, 0).numpy()
+
+
+def conv_up_fprop_case(ctx, case, seed=7):
+    name, N, X, Y, Z, Cc, Cs, Cout = case
+    rng = np.random.default_rng(seed)
+    coarse = bf16_round(rng.standard_normal((N, X // 2, Y // 2, Z // 2, Cc)))
+    skip = bf16_round(rng.standard_normal((N, X, Y, Z, Cs)))
+    w = bf16_round(rng.standard_normal((3, 3, 3, Cc + Cs, Cout)) / np.sqrt(27 * (Cc + Cs)))
+    b = rng.standard_normal(Cout).astype(np.float32)
+    y = np.empty((N, X, Y, Z, Cout), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_up_fprop(ctx.handle, _lib.fptr(coarse), _lib.fptr(skip), _lib.fptr(w), _lib.fptr(b),
+                                         N, X, Y, Z, Cc, Cs, Cout, 1, _lib.fptr(y)))
+    ref = F.relu(_up_reference(coarse, skip, w, b)).detach()
+    return close_bf16(y, cf_to_cl(ref))
+
+
+def conv_up_bwd_case(ctx, case, seed=8):
+    """Gradient towards the coarse tensor (ReLU-masked) within the bf16 bound, weight gradient of the up-source
+    channels within 2e-3 (fp32 accumulation end to end)."""
+    name, N, X, Y, Z, Cc, Cs, Cout = case
+    rng = np.random.default_rng(seed)
+    coarse = bf16_round(rng.standard_normal((N, X // 2, Y // 2, Z // 2, Cc)))
+    skip = np.zeros((N, X, Y, Z, Cs), np.float32)
+    dy = bf16_round(rng.standard_normal((N, X, Y, Z, Cout)))
+    w = bf16_round(rng.standard_normal((3, 3, 3, Cc + Cs, Cout)) / np.sqrt(27 * Cout))
+    dc = np.empty_like(coarse)
+    dw = np.empty((3, 3, 3, Cc, Cout), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_up_bwd(ctx.handle, _lib.fptr(coarse), _lib.fptr(dy), _lib.fptr(w), N, X, Y, Z, Cc, Cs,
+                                       Cout, 1, _lib.fptr(dc), _lib.fptr(dw)))
+    ref_dc, ref_dw = _up_reference(coarse, skip, w, None, dy)
+    ok, worst = close_bf16(dc, ref_dc * (coarse > 0))
+    e = rel_err(dw, ref_dw[:, :, :, :Cc, :])
+    return ok and e <= 2e-3, max(worst, e / 2e-3)
+
+
 def maxpool_case(ctx, seed=3):
     N, X, Y, Z, C = 2, 8, 12, 16, 32
     rng = np.random.default_rng(seed)

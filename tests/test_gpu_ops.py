@@ -77,6 +77,20 @@ def test_conv3d_wgrad_march(ctx, case):
     assert ok, "rel. error / 2e-3 = %.3f" % worst
 
 
+@pytest.mark.parametrize("case", gc.UP_CASES, ids=[c[0] for c in gc.UP_CASES])
+def test_conv3d_up_fprop(ctx, case):
+    """Decoder conv over concatenate([UpSampling3D(coarse), skip]) computed at coarse resolution == the conv over the
+    materialised upsampled tensor (torch fp64)."""
+    ok, worst = gc.conv_up_fprop_case(ctx, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
+@pytest.mark.parametrize("case", gc.UP_CASES, ids=[c[0] for c in gc.UP_CASES])
+def test_conv3d_up_bwd(ctx, case):
+    ok, worst = gc.conv_up_bwd_case(ctx, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
 def test_maxpool3d_fwd_bwd(ctx):
     ok, worst = gc.maxpool_case(ctx)
     assert ok, worst
