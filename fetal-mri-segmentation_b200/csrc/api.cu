@@ -709,8 +709,25 @@ static int refresh_packs(fm_model* m) {
   }
   if (m->repack_n > 0 && !getenv("FETAL_B200_SPLIT_REPACK")) {
     FM_TRY(k_repack_all(m->ctx, m->params, m->repack_tab, m->repack_n, m->repack_blocks, m->repack_weights));
-    for (auto& l : m->layers)
-      if (l.up_coarse || l.up_dgrad) FM_TRY(k_repack_up(m->ctx, m->params + l.w_off, l.w_up_f, l.w_up_d, l.cout, l.c1, l.cin()));
+    RepackUpTable ut;
+    memset(&ut, 0, sizeof(ut));
+    for (auto& l : m->layers) {
+      if (!(l.up_coarse || l.up_dgrad)) continue;
+      if (ut.n == 8) {
+        FM_TRY(k_repack_up_table(m->ctx, m->params, ut));
+        ut.n = 0;
+      }
+      RepackUpDesc& d = ut.d[ut.n];
+      d.w_off = l.w_off;
+      d.wf = l.w_up_f;
+      d.wd = l.w_up_d;
+      d.cout = l.cout;
+      d.cc = l.c1;
+      d.ct = l.cin();
+      d.block0 = ut.n ? ut.d[ut.n - 1].block0 + (int)ceil_div64((int64_t)ut.d[ut.n - 1].cout * 64 * ut.d[ut.n - 1].cc, 256) : 0;
+      ++ut.n;
+    }
+    FM_TRY(k_repack_up_table(m->ctx, m->params, ut));
     m->packs_dirty = false;
     return FM_OK;
   }
@@ -2303,6 +2320,42 @@ extern "C" int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const f
   if (dbias) FM_CUDA(cudaMemcpyAsync(dbias, db, (size_t)Cout * 4, cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));
   packed_to_keras(packed.data(), dw_keras, ksize, Cin, Cout);
+  return FM_OK;
+}
+
+// First convolution of the network (one fp32 input channel): y = act(conv3x3x3(x) + bias) and / or the weight gradient
+// dw_keras (3,3,3,1,Cout) for a given dy [N,X,Y,Z,Cout] (test hook for conv_first_tc.cu / the SIMT kernels behind it).
+extern "C" int fm_op_conv3d_first(fm_ctx* ctx, const float* x, const float* w_keras, const float* bias, int N, int X,
+                                  int Y, int Z, int Cout, int relu, float* y, const float* dy, float* dw_keras) {
+  FM_CHECK(ctx && x && ((y && w_keras && bias) || (dy && dw_keras)), FM_EINVAL, "fm_op_conv3d_first: NULL argument");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  const size_t vox = (size_t)N * X * Y * Z;
+  float* dx = nullptr;
+  FM_TRY(s.up_f32(x, vox, &dx));
+  if (y) {
+    std::vector<float> packed((size_t)Cout * 27);
+    keras_to_packed(w_keras, packed.data(), 3, 1, Cout);
+    bf16 *wf = nullptr, *out = nullptr;
+    float* dbias = nullptr;
+    FM_TRY(s.up_bf16(packed.data(), packed.size(), &wf));
+    FM_TRY(s.up_f32(bias, Cout, &dbias));
+    FM_TRY(s.alloc(&out, vox * Cout));
+    FM_TRY(k_conv3d_simt_fprop(ctx, dx, 1, nullptr, wf, dbias, out, nullptr, N, X, Y, Z, 1, 0, Cout, 3, relu, nullptr));
+    FM_TRY(s.down_bf16(out, vox * Cout, y));
+  }
+  if (dy && dw_keras) {
+    bf16* ddy = nullptr;
+    float* dw = nullptr;
+    FM_TRY(s.up_bf16(dy, vox * Cout, &ddy));
+    FM_TRY(s.alloc(&dw, (size_t)Cout * 27));
+    FM_TRY(k_zero(ctx, dw, (size_t)Cout * 27 * 4));
+    FM_TRY(k_conv3d_simt_wgrad(ctx, dx, 1, ddy, dw, N, X, Y, Z, 1, 1, 0, Cout, 3));
+    std::vector<float> host((size_t)Cout * 27);
+    FM_CUDA(cudaMemcpyAsync(host.data(), dw, host.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FM_CUDA(cudaStreamSynchronize(ctx->stream));
+    packed_to_keras(host.data(), dw_keras, 3, 1, Cout);
+  }
   return FM_OK;
 }
 

@@ -275,6 +275,17 @@ int k_conv3d_tc_wgrad(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, 
 // the coarse tensor with summed weights. X, Y, Z = FINE extents; packs from k_repack_up (tap = class * 8 + j).
 int conv_up_supported(int X, int Y, int Z, int Cc, int Cs, int Cout);
 int k_repack_up(fm_ctx*, const float* w_master, bf16* w_up_f, bf16* w_up_d, int Cout, int Cc, int Ct);
+// the same for up to 8 layers in one launch (w_off = offset of the layer's master kernel in `params`)
+struct RepackUpDesc {
+  int64_t w_off;
+  bf16 *wf, *wd;
+  int cout, cc, ct, block0;
+};
+struct RepackUpTable {
+  RepackUpDesc d[8];
+  int n;
+};
+int k_repack_up_table(fm_ctx*, const float* params, const RepackUpTable& tab);
 int k_conv3d_up_fprop(fm_ctx*, const bf16* coarse, const bf16* skip, const bf16* w_up, const bf16* w_packed,
                       const float* bias, bf16* y, int N, int X, int Y, int Z, int Cc, int Cs, int Cout, int relu);
 int k_conv3d_up_dgrad(fm_ctx*, const bf16* dy, const bf16* w_up_d, bf16* dcoarse, const bf16* mask, int N, int X,
@@ -283,6 +294,13 @@ int k_conv3d_up_dgrad(fm_ctx*, const bf16* dy, const bf16* w_up_d, bf16* dcoarse
 int k_conv3d_up_wgrad(fm_ctx*, const bf16* coarse, const bf16* dy, float* dw_up, int N, int X, int Y, int Z, int Cc,
                       int Cout);
 int k_fold_up_wgrad(fm_ctx*, const float* dw_up, float* dw_master, int Cout, int Cc, int Ct);
+
+// conv_first_tc.cu: first conv (Cin = 1, fp32 volume) and its weight gradient through an im2col tile + tcgen05;
+// FETAL_B200_SIMT_FIRST=1 keeps the SIMT kernels of conv_simt.cu
+int conv_first_tc_supported(int X, int Y, int Z, int Cout);
+int k_conv3d_first_tc(fm_ctx*, const float* x, const bf16* w_packed, const float* bias, bf16* y, int N, int X, int Y,
+                      int Z, int Cout, int relu);
+int k_conv3d_first_tc_wgrad(fm_ctx*, const float* x, const bf16* dy, float* dw, int N, int X, int Y, int Z, int Cout);
 
 // conv_march.cu
 int conv_march_supported(int X, int Y, int Z, int C1, int C2, int Cout, int ksize);

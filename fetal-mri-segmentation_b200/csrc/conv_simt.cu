@@ -583,6 +583,8 @@ int k_conv3d_simt_fprop(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* x2
                         int C2, int Cout, int ksize, int relu, const bf16* mask) {
   if (x_is_f32 && C1 == 1 && C2 == 0 && ksize == 3 && y != nullptr && y_f32 == nullptr &&
       mask == nullptr && bias != nullptr && (Cout == 16 || Cout == 32)) {
+    if (conv_first_tc_supported(X, Y, Z, Cout))  // im2col tile in shared memory + tcgen05 (conv_first_tc.cu)
+      return k_conv3d_first_tc(ctx, (const float*)x, w_packed, bias, y, N, X, Y, Z, Cout, relu);
     const int64_t nvox = (int64_t)N * X * Y * Z;
     const int grid = grid_for(nvox, ctx->num_sms * 16);
     ProfScope prof(ctx, "conv3d_first", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
@@ -611,6 +613,8 @@ int k_conv3d_simt_wgrad(fm_ctx* ctx, const void* x, int x_is_f32, const bf16* dy
   const int64_t nvox = (int64_t)N * X * Y * Z;
   if (x_is_f32 && Cin == 1 && Cin_total == 1 && cin_ofs == 0 && ksize == 3 && (Cout == 16 || Cout == 32) &&
       nvox < (int64_t)1 << 31 && Z % 2 == 0) {
+    if (conv_first_tc_supported(X, Y, Z, Cout))  // im2col tile in shared memory + tcgen05 (conv_first_tc.cu)
+      return k_conv3d_first_tc_wgrad(ctx, (const float*)x, dy, dw_packed, N, X, Y, Z, Cout);
     ProfScope prof(ctx, "conv3d_first_wgrad", 2.0 * 27 * Cout * (double)nvox, (double)nvox * (4.0 + 2.0 * Cout));
     const int grid = (int)std::min<int64_t>(ceil_div64(nvox, 64), (int64_t)ctx->num_sms * (Cout == 16 ? 4 : 2));
     if (Cout == 16)

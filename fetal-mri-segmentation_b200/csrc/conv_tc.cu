@@ -746,11 +746,15 @@ __device__ __forceinline__ bool tap_in_class(int p, int j, int t) { return ((p +
 
 // master [Cout][27][Ct] fp32 (up source = channels [0, Cc)) -> wf [Cout][64][Cc] and wd [Cc][64][Cout], bf16,
 // tap index = class * 8 + j, class = (px*2 + py)*2 + pz, j = (jx*2 + jy)*2 + jz
-__global__ void __launch_bounds__(256) repack_up_kernel(const float* __restrict__ w, bf16* __restrict__ wf,
-                                                        bf16* __restrict__ wd, int Cout, int Cc, int Ct) {
+__global__ void __launch_bounds__(256) repack_up_kernel(const float* __restrict__ params, const __grid_constant__ RepackUpTable tab) {
   FM_PDL_SYNC();
+  int li = 0;
+  while (li + 1 < tab.n && (int)blockIdx.x >= tab.d[li + 1].block0) ++li;
+  const RepackUpDesc d = tab.d[li];
+  const float* w = params + d.w_off;
+  const int Cout = d.cout, Cc = d.cc, Ct = d.ct;
   const int64_t total = (int64_t)Cout * 64 * Cc;
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t g = (int64_t)(blockIdx.x - d.block0) * blockDim.x + threadIdx.x;
   if (g >= total) return;
   const int ci = (int)(g % Cc);
   const int pj = (int)((g / Cc) % 64);
@@ -770,8 +774,8 @@ __global__ void __launch_bounds__(256) repack_up_kernel(const float* __restrict_
     }
   }
   const bf16 v = __float2bfloat16(acc);
-  if (wf) wf[g] = v;
-  if (wd) wd[((int64_t)ci * 64 + pj) * Cout + co] = v;
+  if (d.wf) d.wf[g] = v;
+  if (d.wd) d.wd[((int64_t)ci * 64 + pj) * Cout + co] = v;
 }
 
 // dW[co][t][ci] += sum over the classes p of dW'_p[j(p, t)][co][ci]: the 64 class-tap gradients folded back onto the
@@ -806,13 +810,30 @@ int conv_up_supported(int X, int Y, int Z, int Cc, int Cs, int Cout) {
   return 1;
 }
 
-int k_repack_up(fm_ctx* ctx, const float* w_master, bf16* w_up_f, bf16* w_up_d, int Cout, int Cc, int Ct) {
-  const int64_t total = (int64_t)Cout * 64 * Cc;
-  ProfScope prof(ctx, "repack_up", 0.0, (double)total * 12.0);
-  FM_CUDA(launch_pdl(repack_up_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, ctx->stream, w_master,
-                     w_up_f, w_up_d, Cout, Cc, Ct));
+int k_repack_up_table(fm_ctx* ctx, const float* params, const RepackUpTable& tab) {
+  if (tab.n == 0) return FM_OK;
+  const RepackUpDesc& last = tab.d[tab.n - 1];
+  const int blocks = last.block0 + (int)ceil_div64((int64_t)last.cout * 64 * last.cc, 256);
+  double total = 0.0;
+  for (int i = 0; i < tab.n; ++i) total += (double)tab.d[i].cout * 64 * tab.d[i].cc;
+  ProfScope prof(ctx, "repack_up", 0.0, total * 12.0);
+  FM_CUDA(launch_pdl(repack_up_kernel, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, params, tab));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
+}
+
+int k_repack_up(fm_ctx* ctx, const float* w_master, bf16* w_up_f, bf16* w_up_d, int Cout, int Cc, int Ct) {
+  RepackUpTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n = 1;
+  tab.d[0].w_off = 0;
+  tab.d[0].wf = w_up_f;
+  tab.d[0].wd = w_up_d;
+  tab.d[0].cout = Cout;
+  tab.d[0].cc = Cc;
+  tab.d[0].ct = Ct;
+  tab.d[0].block0 = 0;
+  return k_repack_up_table(ctx, w_master, tab);
 }
 
 int k_fold_up_wgrad(fm_ctx* ctx, const float* dw_up, float* dw_master, int Cout, int Cc, int Ct) {

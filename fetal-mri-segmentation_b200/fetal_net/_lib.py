@@ -117,6 +117,7 @@ SIGNATURES = {
     "fm_op_conv3d_fprop": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp, c_fp] + [c_int] * 9 + [c_fp]),
     "fm_op_conv3d_dgrad": (c_int, [c_vp, c_int, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp]),
     "fm_op_conv3d_wgrad": (c_int, [c_vp, c_int, c_fp, c_fp] + [c_int] * 6 + [c_fp, c_fp]),
+    "fm_op_conv3d_first": (c_int, [c_vp, c_fp, c_fp, c_fp] + [c_int] * 6 + [c_fp, c_fp, c_fp]),
     "fm_op_conv3d_up_fprop": (c_int, [c_vp, c_fp, c_fp, c_fp, c_fp] + [c_int] * 8 + [c_fp]),
     "fm_op_conv3d_up_bwd": (c_int, [c_vp, c_fp, c_fp, c_fp] + [c_int] * 8 + [c_fp, c_fp]),
     "fm_op_maxpool3d": (c_int, [c_vp, c_fp] + [c_int] * 5 + [c_fp]),

@@ -320,6 +320,11 @@ int fm_op_conv3d_dgrad(fm_ctx* ctx, int impl, const float* dy, const float* w_ke
                        float* dx);
 int fm_op_conv3d_wgrad(fm_ctx* ctx, int impl, const float* x, const float* dy, int N, int X, int Y,
                        int Z, int Cin, int Cout, float* dw_keras, float* dbias);
+/* First Conv3D of the network on the single-channel float32 input x [N,X,Y,Z] (create_convolution_block on the
+ * (1, X, Y, Z) input, unet.py:102): y [N,X,Y,Z,Cout] = act(conv + bias) when y != NULL; the weight gradient
+ * dw_keras (3,3,3,1,Cout) for dy [N,X,Y,Z,Cout] when both are != NULL. */
+int fm_op_conv3d_first(fm_ctx* ctx, const float* x, const float* w_keras, const float* bias, int N, int X, int Y, int Z,
+                       int Cout, int relu, float* y, const float* dy, float* dw_keras);
 /* Decoder convolution Conv3D(3x3x3, 'same') over concatenate([UpSampling3D(2)(coarse), skip], axis=1)
  * (fetal_net/model/unet3d/unet.py:59-62,138 with get_up_convolution's UpSampling3D) computed WITHOUT the upsampled
  * tensor: per parity class of the fine voxel the 27 taps over the upsampled source collapse into 8 taps over the coarse

@@ -215,6 +215,37 @@ def conv_up_bwd_case(ctx, case, seed=8):
     return ok and e <= 2e-3, max(worst, e / 2e-3)
 
 
+FIRST_CASES = [  # name, N, X, Y, Z, Cout : shapes the im2col + tcgen05 first-layer kernels cover (Y % 16 == 0, Z % 8 == 0)
+    ("first16_32cube", 2, 32, 32, 32, 16),
+    ("first32_16x32x8", 3, 5, 32, 8, 32),      # Isensee / 32-filter variants; single z tile, odd x
+    ("first16_64cube", 1, 64, 64, 64, 16),     # the BASELINE patch
+    ("first16_ragged_9x12x6", 2, 9, 12, 6, 16),  # not covered by the tensor-core kernel: SIMT route
+]
+
+
+def conv_first_case(ctx, case, seed=9):
+    """First conv (fp32 single-channel input) forward within the bf16 bound (the tensor-core route rounds the volume to
+    bf16, so the reference does too) and its weight gradient within 2e-3."""
+    name, N, X, Y, Z, Cout = case
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.standard_normal((N, X, Y, Z)))
+    w = bf16_round(rng.standard_normal((3, 3, 3, 1, Cout)) / np.sqrt(27.0))
+    b = rng.standard_normal(Cout).astype(np.float32)
+    dy = bf16_round(rng.standard_normal((N, X, Y, Z, Cout)))
+    y = np.empty((N, X, Y, Z, Cout), np.float32)
+    dw = np.empty((3, 3, 3, 1, Cout), np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_conv3d_first(ctx.handle, _lib.fptr(x), _lib.fptr(w), _lib.fptr(b), N, X, Y, Z, Cout, 1,
+                                      _lib.fptr(y), _lib.fptr(dy), _lib.fptr(dw)))
+    xt = torch.as_tensor(x)[:, None].double()
+    wt = keras_to_torch_w(w).double().requires_grad_(True)
+    out = F.conv3d(xt, wt, torch.as_tensor(b).double(), padding=1)
+    ok, worst = close_bf16(y, cf_to_cl(F.relu(out).detach()))
+    out.backward(cl_to_cf(dy).double())
+    e = rel_err(dw, wt.grad.permute(2, 3, 4, 1, 0).numpy())
+    return ok and e <= 2e-3, max(worst, e / 2e-3)
+
+
 def maxpool_case(ctx, seed=3):
     N, X, Y, Z, C = 2, 8, 12, 16, 32
     rng = np.random.default_rng(seed)

@@ -91,6 +91,12 @@ def test_conv3d_up_bwd(ctx, case):
     assert ok, "worst error / tolerance = %.3f" % worst
 
 
+@pytest.mark.parametrize("case", gc.FIRST_CASES, ids=[c[0] for c in gc.FIRST_CASES])
+def test_conv3d_first_layer(ctx, case):
+    ok, worst = gc.conv_first_case(ctx, case)
+    assert ok, "worst error / tolerance = %.3f" % worst
+
+
 def test_maxpool3d_fwd_bwd(ctx):
     ok, worst = gc.maxpool_case(ctx)
     assert ok, worst
