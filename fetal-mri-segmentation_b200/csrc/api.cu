@@ -697,7 +697,7 @@ static int refresh_packs(fm_model* m) {
       d.kcd0 = conv_march_kc(l.cout, 0, l.c1, l.cout);
       d.kcd1 = l.c2 ? conv_march_kc(l.cout, 0, l.c2, l.cout) : 0;
       d.block0 = blocks;
-      blocks += (int)ceil_div64(l.wcount(), 256);
+      blocks += l.taps() * ceil_div(l.cout, 32) * ceil_div(l.cin(), 32);  // 32 x 32 (co, c) tiles per tap
       weights += (double)l.wcount();
       tab.push_back(d);
     }
@@ -1582,6 +1582,7 @@ extern "C" int fm_reassemble(fm_ctx* ctx, const float* preds, const int32_t* idx
 // reduce_root < 0: `out` receives this shard's result (the average for shard 0 of 1, the partial SUM otherwise).
 // reduce_root >= 0: the partial sums are reduced on the ctx communicator to that rank, which divides by the counts and
 // is the only one to copy anything back to the host.
+static bool is_pinned_host(const void* p);
 static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[3], const int32_t halo_pad[6],
                           const int32_t fit_pad[6], const double pad_value[2], const int32_t* idx, int64_t n, int batch,
                           int shard_rank, int shard_count, int reduce_root, const float* truth, int prev_truth_index,
@@ -1634,8 +1635,27 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
     }();
     if (sub_env > 0)
       batch = std::min(batch, sub_env);
-    else if (sub_env < 0 && batch > ppg && ngroups >= 3)
-      batch = (int)std::min<int64_t>(batch, (int64_t)ppg * std::max(1, ngroups / 8));
+    else if (sub_env < 0 && batch > ppg && ngroups >= 3) {
+      // cut so that a sub-batch fills the SMs in whole waves: the marching kernels run one 16 x 8 column per CTA, a
+      // patch has cpp columns, and q patches (q = SMs / gcd(SMs, cpp); 37 for 64^3 patches on 148 SMs) are a whole
+      // number of waves for them and for the 128-voxel tiles of the deeper levels. The first cut keeps ~3/4 of the
+      // patches (its finished output slabs travel back while the remainder runs); 2D models keep whole x groups.
+      const int64_t cpp = is2d ? 0 : (int64_t)(m->spec.Y / 16) * (m->spec.Z / 8);
+      int64_t q = 0;
+      if (cpp > 0) {
+        int64_t a = ctx->num_sms, b = cpp;
+        while (b) {
+          const int64_t t = a % b;
+          a = b;
+          b = t;
+        }
+        q = ctx->num_sms / a;
+      }
+      if (q > 0 && nloc > q)
+        batch = (int)std::min<int64_t>(batch, q * std::max<int64_t>(1, std::min<int64_t>(2, (nloc * 3 / 4) / q)));
+      else if (q == 0)
+        batch = (int)std::min<int64_t>(batch, (int64_t)ppg * std::max(1, ngroups / 8));
+    }
   }
   FM_TRY(ensure_capacity(m, batch, false));
   DevBuf<float>&dvol = m->pw_vol, &dpred = m->pw_pred;
@@ -1708,6 +1728,13 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
   size_t unstaged = 0;
   const size_t plane = (size_t)out_dims[1] * out_dims[2];
   const bool stream_out = want_out && shard_count == 1;  // slab-wise D2H only when no cross-rank reduce follows
+  // a page-locked result (fm_host_alloc, what fetal_net.prediction hands in) receives the slabs directly: no staging
+  // copy, no first-touch page faults of a fresh 33 MB array
+  const bool out_pinned = want_out && is_pinned_host(out) && (!out_count || is_pinned_host(out_count));
+  if (out_pinned) {
+    pin_out = (char*)out;
+    pin_cnt = (char*)out_count;
+  }
   auto unstage = [&](bool block) {
     while (unstaged < slabs.size()) {
       const Slab& sl = slabs[unstaged];
@@ -1718,8 +1745,10 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
         break;
       }
       const size_t o = (size_t)sl.x0 * plane, c = (size_t)sl.rows * plane;
-      host_copy(out + o, pin_out + o * 8, c * 8);
-      if (out_count) host_copy(out_count + o, pin_cnt + o * 2, c * 2);
+      if (!out_pinned) {
+        host_copy(out + o, pin_out + o * 8, c * 8);
+        if (out_count) host_copy(out_count + o, pin_cnt + o * 2, c * 2);
+      }
       ++unstaged;
     }
   };
@@ -1778,9 +1807,22 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
   if (out_count) FM_CUDA(cudaMemcpyAsync(pin_cnt, dcnt.p, cnt_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaStreamSynchronize(ctx->stream));
   lap("d2h");
-  host_copy(out, pin_out, out_bytes);
-  if (out_count) host_copy(out_count, pin_cnt, cnt_bytes);
+  if (!out_pinned) {
+    host_copy(out, pin_out, out_bytes);
+    if (out_count) host_copy(out_count, pin_cnt, cnt_bytes);
+  }
   lap("unstage result");
+  return FM_OK;
+}
+
+// Page-locked host memory for callers that want results without a staging copy (fetal_net.prediction keeps a pool).
+extern "C" int fm_host_alloc(size_t bytes, void** out) {
+  FM_CHECK(out && bytes > 0, FM_EINVAL, "fm_host_alloc: bad argument");
+  FM_CUDA(cudaMallocHost(out, bytes));
+  return FM_OK;
+}
+extern "C" int fm_host_free(void* p) {
+  if (p) FM_CUDA(cudaFreeHost(p));
   return FM_OK;
 }
 
@@ -1839,6 +1881,7 @@ static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullp
   return FM_OK;
 }
 
+static bool is_pinned_host(const void* p);
 static bool is_pinned_host(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {

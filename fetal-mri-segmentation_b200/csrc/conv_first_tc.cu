@@ -41,27 +41,56 @@ struct alignas(64) FirstParams {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// im2col row of voxel (n, x, y, z): 27 neighbours (zero outside the volume = padding 'same'), bf16, into the
-// 128-byte swizzled row `row` of the tile at `tile` (16-byte chunk index ^= row & 7)
-__device__ __forceinline__ void build_row(const FirstParams& p, uint32_t tile, int row, int n, int x, int y, int z) {
-  float v[32];
+// The builders first stage the tile's input halo - 3 planes x 18 y x 10 z, zero outside the volume (= padding 'same'),
+// rounded to bf16 - in shared memory (5 coalesced loads per thread, issued one tile ahead so their latency hides
+// behind the previous tile's gather), then every thread assembles the im2col row of its voxel from 27 16-bit shared
+// loads: ~100 instructions per voxel instead of the ~320 of gathering from global memory with bounds checks.
+constexpr int kHZ = 12;                          // padded z pitch of the halo (10 used)
+constexpr uint32_t kHaloBytes = 3u * 18u * kHZ * 2u;  // 1296 B
+constexpr int kHaloPerThread = 5;                // 540 halo elements over 128 builder threads
+
+__device__ __forceinline__ void halo_load(const FirstParams& p, int n, int x, int y0, int z0, int tid, float v[kHaloPerThread]) {
 #pragma unroll
-  for (int kx = 0; kx < 3; ++kx) {
-    const int xi = x + kx - 1;
+  for (int k = 0; k < kHaloPerThread; ++k) {
+    const int e = tid + k * 128;
+    const int kx = e / 180, rem = e % 180;
+    const int yy = rem / 10, zz = rem % 10;
+    const int xi = x + kx - 1, yi = y0 + yy - 1, zi = z0 + zz - 1;
+    const bool ok = e < 540 && xi >= 0 && xi < p.X && yi >= 0 && yi < p.Y && zi >= 0 && zi < p.Z;
+    v[k] = ok ? __ldg(p.x + (((int64_t)n * p.X + xi) * p.Y + yi) * p.Z + zi) : 0.f;
+  }
+}
+__device__ __forceinline__ void halo_store(uint32_t halo, int tid, const float v[kHaloPerThread]) {
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yi = y + ky - 1;
-      const bool in_xy = xi >= 0 && xi < p.X && yi >= 0 && yi < p.Y;
-      const float* src = p.x + (((int64_t)n * p.X + xi) * p.Y + yi) * p.Z + z;
-#pragma unroll
-      for (int kz = 0; kz < 3; ++kz) {
-        const int zi = z + kz - 1;
-        v[(kx * 3 + ky) * 3 + kz] = (in_xy && zi >= 0 && zi < p.Z) ? __ldg(src + kz - 1) : 0.f;
-      }
+  for (int k = 0; k < kHaloPerThread; ++k) {
+    const int e = tid + k * 128;
+    if (e < 540) {
+      const int kx = e / 180, rem = e % 180;
+      const int yy = rem / 10, zz = rem % 10;
+      const bf16 h = __float2bfloat16(v[k]);
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(halo + (uint32_t)(((kx * 18 + yy) * kHZ + zz) * 2)),
+                   "h"(*reinterpret_cast<const unsigned short*>(&h))
+                   : "memory");
     }
   }
+}
+// im2col row of the voxel (ry, rz) of the tile from the staged halo into the 128-byte swizzled row `row` of the tile
+// at `tile` (16-byte chunk index ^= row & 7); taps 27..31 zero
+__device__ __forceinline__ void build_row(uint32_t halo, uint32_t tile, int row, int ry, int rz) {
+  uint32_t h[28];
 #pragma unroll
-  for (int t = 27; t < 32; ++t) v[t] = 0.f;
+  for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const uint32_t a = halo + (uint32_t)(((kx * 18 + ry + ky) * kHZ + rz) * 2);
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+        unsigned short u;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(a + 2u * (uint32_t)kz));
+        h[(kx * 3 + ky) * 3 + kz] = u;
+      }
+    }
+  h[27] = 0u;
   const uint32_t rbase = tile + (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
@@ -69,8 +98,8 @@ __device__ __forceinline__ void build_row(const FirstParams& p, uint32_t tile, i
     uint32_t w4[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * c + 2 * j], v[8 * c + 2 * j + 1]);
-      w4[j] = *reinterpret_cast<const uint32_t*>(&h);
+      const int t = 8 * c + 2 * j;
+      w4[j] = t + 1 < 28 ? (h[t] | (h[t + 1] << 16)) : (t < 28 ? h[t] : 0u);
     }
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((uint32_t)c ^ sw) << 4)), "r"(w4[0]),
                  "r"(w4[1]), "r"(w4[2]), "r"(w4[3])
@@ -100,7 +129,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv3d_first_tc_kernel(const __g
   const uint32_t a_base = smem0;
   const uint32_t w_base = a_base + (uint32_t)(kABufs + 1) * kATile;
   const uint32_t dy_tile = 128u * (uint32_t)p.Cout * 2u;
-  const uint32_t bar0 = w_base + (MODE == 0 ? 32u * 128u : (uint32_t)kDyRingF * dy_tile);
+  const uint32_t halo_base = w_base + (MODE == 0 ? 32u * 128u : (uint32_t)kDyRingF * dy_tile);  // two halo buffers
+  const uint32_t bar0 = (halo_base + 2u * kHaloBytes + 15u) & ~15u;
   auto afull = [&](int b) { return bar0 + 8u * (uint32_t)b; };
   auto aempty = [&](int b) { return bar0 + 8u * (uint32_t)(kABufs + b); };
   auto tfull = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kABufs + a); };
@@ -162,13 +192,26 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv3d_first_tc_kernel(const __g
     if (warp_u == 0) pdl_launch_dependents();
     const int row = threadIdx.x;  // 0..127 = y * 8 + z inside the tile
     const int ry = row / kFZ, rz = row % kFZ;
+    float hv[kHaloPerThread];
+    int n, x, y0, z0;
+    if ((int)blockIdx.x < p.tiles) {
+      decode_tile(p, blockIdx.x, n, x, y0, z0);
+      halo_load(p, n, x, y0, z0, row, hv);
+    }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
       const uint32_t b = it % (uint32_t)kABufs, ph = (it / (uint32_t)kABufs) & 1u;
-      int n, x, y0, z0;
-      decode_tile(p, tile, n, x, y0, z0);
+      const uint32_t halo = halo_base + (it & 1u) * kHaloBytes;
+      halo_store(halo, row, hv);
+      // the next tile's halo is already in flight while this one is gathered
+      const int next = tile + gridDim.x;
+      if (next < p.tiles) {
+        decode_tile(p, next, n, x, y0, z0);
+        halo_load(p, n, x, y0, z0, row, hv);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four builder warps: halo complete (two buffers alternate)
       mbar_wait(aempty(b), ph ^ 1u);
-      build_row(p, a_base + b * kATile, row, n, x, y0 + ry, z0 + rz);
+      build_row(halo, a_base + b * kATile, row, ry, rz);
       fence_async_smem();
       mbar_arrive(afull(b));
     }
@@ -315,7 +358,8 @@ PFN_encodeTiledF get_encode_f() {
 }
 
 size_t first_smem(int mode, int Cout) {
-  return (size_t)(kABufs + 1) * kATile + (mode == 0 ? 32u * 128u : (size_t)kDyRingF * 128u * Cout * 2u) + 1024 + 256;
+  return (size_t)(kABufs + 1) * kATile + (mode == 0 ? 32u * 128u : (size_t)kDyRingF * 128u * Cout * 2u) + 2 * kHaloBytes +
+         1024 + 256 + 16;
 }
 
 int fill(FirstParams& p, int N, int X, int Y, int Z, int Cout) {
@@ -359,7 +403,7 @@ int k_conv3d_first_tc(fm_ctx* ctx, const float* x, const bf16* w_packed, const f
     attr_set = true;
   }
   const double nvox = (double)N * X * Y * Z;
-  const int grid = std::min(p.tiles, 2 * ctx->num_sms);
+  const int grid = std::min(p.tiles, 3 * ctx->num_sms);
   ProfScope prof(ctx, "conv3d_first", 2.0 * 27 * Cout * nvox, nvox * (4.0 + 2.0 * Cout));
   FM_CUDA(launch_pdl(conv3d_first_tc_kernel<0>, dim3(grid), dim3(kThreadsF), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);

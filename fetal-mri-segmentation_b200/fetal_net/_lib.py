@@ -74,6 +74,8 @@ SIGNATURES = {
     "fm_model_set_dropout": (c_int, [c_vp, ctypes.c_float, ctypes.c_uint64]),
     "fm_train_metrics_async": (c_int, [c_vp]),
     "fm_train_metrics_wait": (c_int, [c_vp, c_fp]),
+    "fm_host_alloc": (c_int, [ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "fm_host_free": (c_int, [c_vp]),
     "fm_predict": (c_int, [c_vp, c_fp, c_int, c_fp]),
     "fm_patch_plan": (c_int, [c_i32p, c_i32p, c_i32p, c_d, c_i32p, c_i64, c_i64p]),
     "fm_patchwise_predict": (c_int, [c_vp, c_fp, c_i32p, c_i32p, c_i32p, c_dp, c_i32p, c_i64, c_int,
@@ -182,6 +184,53 @@ def f32c(a):
 
 def i32x(vals):
     return np.ascontiguousarray(np.asarray(vals, dtype=np.int32).reshape(-1))
+
+
+class _PinnedBlock:
+    """One page-locked allocation; goes back to the pool when the last NumPy view of it dies."""
+
+    def __init__(self, nbytes):
+        p = c_vp()
+        check(load().fm_host_alloc(nbytes, ctypes.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def release(self):
+        if self.ptr:
+            load().fm_host_free(c_vp(self.ptr))
+            self.ptr = None
+
+
+_pinned_pool = {}       # nbytes -> [free _PinnedBlock]
+_PINNED_POOL_MAX = 4    # free blocks kept per size
+
+
+class _PinnedLease:
+    """Owner object behind a pooled array: returns the block to the pool on garbage collection."""
+
+    def __init__(self, block):
+        self.block = block
+
+    def __del__(self):
+        try:
+            free = _pinned_pool.setdefault(self.block.nbytes, [])
+            if len(free) < _PINNED_POOL_MAX:
+                free.append(self.block)
+            else:
+                self.block.release()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """np.empty(shape, dtype) in page-locked memory from a small pool: what fm_patchwise_predict writes its result
+    into. The array owns its block (through .base) until it and all its views are collected."""
+    dtype = np.dtype(dtype)
+    nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+    free = _pinned_pool.get(nbytes)
+    block = free.pop() if free else _PinnedBlock(nbytes)
+    buf = (ctypes.c_byte * nbytes).from_address(block.ptr)
+    buf._lease = _PinnedLease(block)            # keeps the block out of the pool while any view is alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 _contexts = {}

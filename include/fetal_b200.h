@@ -144,6 +144,12 @@ int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed);
  * With n_labels == 1 the channels-first and channels-last output layouts coincide. */
 int fm_predict(fm_model* m, const float* x, int batch, float* y);
 
+/* Page-locked host memory: a result array allocated here receives the device->host copies of fm_patchwise_predict
+ * directly (no staging copy, no first-touch page faults); fetal_net.prediction keeps a pool of such arrays behind the
+ * NumPy arrays it returns (the reference returns fresh np.zeros arrays, prediction.py:174-175). */
+int fm_host_alloc(size_t bytes, void** out);
+int fm_host_free(void* p);
+
 /* Sliding-window plan. Replaces get_set_of_patch_indices_full + the overlap arithmetic
  * (fetal_net/prediction.py:88-95,135-137,161-163). `padded` is the extent of the padded volume,
  * `pred` the model's prediction extent (== patch for the 3D models). Writes up to `cap` corner
