@@ -382,3 +382,35 @@ def test_isensee_dropout_training_only():
     ga, gb = a.get_gradients(), b.get_gradients()
     assert all(np.isfinite(g).all() for g in gb)
     assert any(not np.allclose(p, q) for p, q in zip(ga, gb))
+
+
+@pytest.mark.parametrize("tag", ["unet3d_d4_nf16", "isensee3d_d3_nf8_seg2", "unet2d_d3_nf16"])
+def test_gpu_matches_keras_fixture(tag):
+    """CUDA path against REAL Keras output (tests/golden/keras_fixture.npz, written by tools/export_keras_fixture.py
+    where Keras/TF exist): same weights, same input -> north_star's bar (logits within the stated bf16 tolerance, soft
+    Dice >= 0.999), and the loss of one train_on_batch within 3e-3. Skips while the fixture is absent."""
+    from oracle import keras_fixture as kf
+    from fetal_net.model import unet_model_3d, unet_model_2d, isensee2017_model_3d
+    z = kf.load()
+    if z is None or tag + "/names" not in z.files:
+        pytest.skip("tests/golden/keras_fixture.npz absent (needs Keras/TF: tools/export_keras_fixture.py)")
+    x, t, ref = z[tag + "/x"], z[tag + "/t"], z[tag + "/predict"]
+    lr = float(z[tag + "/lr"])
+    if tag.startswith("unet3d"):
+        layers = uo.unet3d_layers(4, 16)
+        model = unet_model_3d(input_shape=x.shape[1:], depth=4, n_base_filters=16, initial_learning_rate=lr)
+    elif tag.startswith("isensee"):
+        layers = uo.isensee3d_layers(3, 8, 2)
+        model = isensee2017_model_3d(input_shape=x.shape[1:], depth=3, n_base_filters=8, n_segmentation_levels=2,
+                                     dropout_rate=0.0, initial_learning_rate=lr)
+    else:
+        layers = uo.unet2d_layers(3, 16, 6)
+        model = unet_model_2d(input_shape=x.shape[1:], depth=3, n_base_filters=16, initial_learning_rate=lr)
+    model.set_named_weights(kf.named_weights(z, tag, layers))
+    p = model.predict(x)
+    lg = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    err = np.linalg.norm(lg(p) - lg(ref)) / np.linalg.norm(lg(ref))
+    soft = (2 * (p * ref).sum() + 1) / ((p * p).sum() + (ref * ref).sum() + 1)
+    assert err <= 0.04 and np.abs(p - ref).mean() <= 0.006 and soft >= 0.999, (err, soft)
+    loss = model.train_on_batch(x, t)[0]
+    assert abs(loss - float(z[tag + "/train_metrics"][0])) <= 3e-3

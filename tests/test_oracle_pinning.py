@@ -221,3 +221,63 @@ def test_upsampled_source_conv_equals_parity_class_convs_at_coarse_resolution():
                 out[:, :, px::2, py::2, pz::2] = F.conv3d(x, k, padding=1)
     assert nonzero == 64
     np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-12, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------------------------
+# the pin against REAL Keras: tools/export_keras_fixture.py writes tests/golden/keras_fixture.npz
+# where Keras/TensorFlow exist (not in this image). The reader is exercised on a synthetic file.
+# ----------------------------------------------------------------------------------------------
+KERAS_CASES = {
+    "unet3d_d4_nf16": dict(layers=lambda: uo.unet3d_layers(4, 16), fwd=lambda x, w: uo.unet3d_forward(x, w, depth=4)),
+    "isensee3d_d3_nf8_seg2": dict(layers=lambda: uo.isensee3d_layers(3, 8, 2),
+                                  fwd=lambda x, w: uo.isensee3d_forward(x, w, depth=3, n_segmentation_levels=2)),
+    "unet2d_d3_nf16": dict(layers=lambda: uo.unet2d_layers(3, 16, 6), fwd=lambda x, w: uo.unet2d_forward(x, w, depth=3)),
+}
+
+
+def test_keras_fixture_reader_on_synthetic_file():
+    """Keras-style variable names, numbered from an arbitrary session offset and listed in graph-depth order (the
+    coarse segmentation head AFTER later-created decoder layers), must map back onto the oracle's layer table."""
+    from oracle import keras_fixture as kf
+    layers = uo.isensee3d_layers(3, 8, 2)
+    w = uo.glorot_uniform_weights(layers, seed=3)
+    w.update({k: v + 0.25 for k, v in uo.isensee3d_norm_params(layers).items()})
+    z, names, ci, ni = {}, [], 40, 17
+    for lname, cin, cout, k in layers:
+        ci += 1
+        names += ["conv3d_%d/kernel:0" % ci, "conv3d_%d/bias:0" % ci]
+        z["t/w/conv3d_%d/kernel:0" % ci], z["t/w/conv3d_%d/bias:0" % ci] = w[lname + "/kernel"], w[lname + "/bias"]
+        if not lname.endswith("_seg"):
+            ni += 1
+            names += ["instance_normalization_%d/gamma:0" % ni, "instance_normalization_%d/beta:0" % ni]
+            z["t/w/instance_normalization_%d/gamma:0" % ni] = w[lname + "/gamma"]
+            z["t/w/instance_normalization_%d/beta:0" % ni] = w[lname + "/beta"]
+    rng = np.random.default_rng(0)
+    z["t/names"] = np.array([names[i] for i in rng.permutation(len(names))])
+    got = kf.named_weights(z, "t", layers)
+    assert set(got) == set(w)
+    for k in w:
+        assert np.array_equal(got[k], w[k]), k
+
+
+@pytest.mark.parametrize("tag", sorted(KERAS_CASES))
+def test_oracle_matches_keras_fixture(tag):
+    """The network oracle against real Keras output (predict, loss of one train_on_batch, the Adam-updated weights).
+    Tolerances: both sides are fp32 on a CPU with different summation orders -> 2e-4 on probabilities, 1e-5 on the
+    loss, 2e-6 on the updated weights (one Adam step moves every weight by ~lr)."""
+    from oracle import keras_fixture as kf
+    z = kf.load()
+    if z is None or tag + "/names" not in z.files:
+        pytest.skip("tests/golden/keras_fixture.npz absent (needs Keras/TF: tools/export_keras_fixture.py)")
+    case = KERAS_CASES[tag]
+    layers = case["layers"]()
+    w = kf.named_weights(z, tag, layers)
+    x, t = z[tag + "/x"], z[tag + "/t"]
+    with torch.no_grad():
+        p = case["fwd"](torch.as_tensor(x), w).numpy()
+    assert np.abs(p - z[tag + "/predict"]).max() <= 2e-4
+    res = uo.train_step(case["fwd"], x, t, w, {}, float(z[tag + "/lr"]))
+    assert abs(res["loss"] - float(z[tag + "/train_metrics"][0])) <= 1e-5
+    after = kf.named_weights(z, tag, layers, which="w_after")
+    for k in w:
+        assert np.abs(w[k] - after[k]).max() <= 2e-6, k
