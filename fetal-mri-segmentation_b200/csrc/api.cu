@@ -257,8 +257,23 @@ struct fm_model {
   DevBuf<float> x_in, t_in, prob, dz;
   std::vector<DevBuf<bf16>> encA, encB, pool, up, decA, decB;          // forward
   std::vector<DevBuf<bf16>> gEncA, gEncB, gPool, gUp, gSkip, gDecA, gDecB;  // gradients
-  double* sums = nullptr;  // 8 doubles (device)
-  double sums_host[8];
+  double* sums = nullptr;  // kNumLossSums doubles (device): 7 Dice / VOD / accuracy sums, the count, sum w * bce
+  double sums_host[kNumLossSums];
+  // loss: 0 dice_coefficient_loss, 1 dice_and_xent, 2 dice_and_xent_mask (weight mask = second model input)
+  int loss_kind = 0;
+  float xent_weight = 0.f, xent_inv_sigma = 0.f;
+  DevBuf<float> mask_in;
+  bool mask_valid = false;
+  int mask_batch = 0;
+  XentSpec xent() const {
+    XentSpec xs;
+    if (loss_kind != 0) {
+      xs.weight = xent_weight;
+      xs.inv_sigma = xent_inv_sigma;
+      xs.mask = loss_kind == 2 ? mask_in.p : nullptr;
+    }
+    return xs;
+  }
   // fm_train_step pipelining (pinned host inputs): two device staging buffers filled by the copy stream while the
   // previous step is still in its backward pass; the call returns once the Dice statistics of ITS forward pass are
   // on the host, the rest of the step (backward, Adam, repack) keeps running and is ordered before any later call
@@ -469,8 +484,8 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_mod
     FM_CUDA(cudaMalloc((void**)&l.w_up_f, n * sizeof(bf16)));
     FM_CUDA(cudaMalloc((void**)&l.dw_up, n * sizeof(float)));
   }
-  FM_CUDA(cudaMalloc((void**)&m->sums, 8 * sizeof(double)));
-  FM_CUDA(cudaMemset(m->sums, 0, 8 * sizeof(double)));
+  FM_CUDA(cudaMalloc((void**)&m->sums, kNumLossSums * sizeof(double)));
+  FM_CUDA(cudaMemset(m->sums, 0, kNumLossSums * sizeof(double)));
   m->encA.resize(D);
   m->encB.resize(D);
   m->pool.resize(D);
@@ -545,6 +560,7 @@ extern "C" int fm_model_destroy(fm_model* m) {
   m->pw_out.release();
   m->pw_cnt.release();
   m->x_in.release();
+  m->mask_in.release();
   m->x_pad.release();
   m->t_in.release();
   m->prob.release();
@@ -657,6 +673,33 @@ extern "C" int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed) {
   FM_CHECK(rate >= 0.f && rate < 1.f, FM_EINVAL, "dropout rate %g outside [0,1)", (double)rate);
   m->dropout_rate = rate;
   m->dropout_seed = seed;
+  return FM_OK;
+}
+
+extern "C" int fm_model_set_loss(fm_model* m, int kind, float xent_weight, float dist_sigma) {
+  FM_CHECK(m, FM_EINVAL, "NULL model");
+  FM_CHECK(kind >= 0 && kind <= 2, FM_EINVAL, "fm_model_set_loss: kind %d (0 dice, 1 dice_and_xent, 2 dice_and_xent_mask)", kind);
+  FM_CHECK(kind != 2 || dist_sigma > 0.f, FM_EINVAL, "fm_model_set_loss: dist_sigma must be positive");
+  m->loss_kind = kind;
+  m->xent_weight = kind ? xent_weight : 0.f;
+  m->xent_inv_sigma = kind == 2 ? 1.f / dist_sigma : 0.f;
+  m->mask_valid = false;
+  return FM_OK;
+}
+
+extern "C" int fm_model_set_weight_mask(fm_model* m, const float* mask, int batch) {
+  FM_CHECK(m && mask && batch > 0, FM_EINVAL, "fm_model_set_weight_mask: bad argument");
+  FM_CHECK(m->loss_kind == 2, FM_EINVAL, "fm_model_set_weight_mask: the model's loss takes no weight mask");
+  FM_CUDA(cudaSetDevice(m->ctx->device));
+  const size_t n = (size_t)batch * m->vox(0);
+  if (n > m->mask_in.n) {
+    // the previous step may still read the old buffer
+    FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    FM_TRY(m->mask_in.ensure(n));
+  }
+  FM_CUDA(cudaMemcpyAsync(m->mask_in.p, mask, n * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+  m->mask_valid = true;
+  m->mask_batch = batch;
   return FM_OK;
 }
 
@@ -861,7 +904,7 @@ static int forward(fm_model* m, int B) {
   if (m->train_pass && m->targets_ready) {
     // head + sigmoid + Dice / VOD / accuracy sums in one pass (unet.py:68-69 + metrics.py:11-28)
     FM_TRY(k_head_fwd_dice(ctx, cur, m->params + lf.w_off, m->params + lf.b_off, m->t_in.p, m->prob.p,
-                           (int64_t)B * m->vox(0), lf.c1, m->sums));
+                           (int64_t)B * m->vox(0), lf.c1, m->sums, m->xent()));
     m->stats_done = true;
     return FM_OK;
   }
@@ -945,7 +988,7 @@ static int backward(fm_model* m, int B) {
   // head backward with the soft-Dice gradient formed inside (closed form through the sigmoid with the GLOBAL sums):
   // gradient lands masked by the ReLU of dec0b (or encB[0] when depth == 1)
   FM_TRY(k_head_bwd(ctx, m->decB[0].p, m->prob.p, m->params + lf.w_off, m->gDecB[0].p, m->grads + lf.w_off,
-                    m->grads + lf.b_off, n0, lf.c1, 0, m->t_in.p, m->sums));
+                    m->grads + lf.b_off, n0, lf.c1, 0, m->t_in.p, m->sums, m->xent()));
   FM_TRY(mark_layer_done(m, lf));
   for (int d = 0; d <= D - 2; ++d) {
     const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
@@ -1012,10 +1055,11 @@ static int backward(fm_model* m, int B) {
   return FM_OK;
 }
 
-static void metrics_from_sums(const double s[8], float out[4]) {
+static void metrics_from_sums(const double s[kNumLossSums], float out[4], float xent_weight = 0.f) {
   const double dice = (2.0 * s[0] + 1.0) / (s[1] + s[2] + 1.0);
   const double uni = s[4] + s[5] - s[3];
-  out[0] = (float)(-dice);                       // loss = -dice (metrics.py:31-32)
+  // loss = -dice (metrics.py:31-32) [+ xent_weight * mean(w * bce): dice_and_xent, metrics.py:68-78]
+  out[0] = (float)(-dice + (xent_weight != 0.f && s[7] > 0 ? (double)xent_weight * s[8] / s[7] : 0.0));
   out[1] = (float)(s[7] > 0 ? s[6] / s[7] : 0);  // binary_accuracy
   out[2] = (float)((s[3] + 1.0) / (uni + 1.0));  // vod_coefficient (metrics.py:18-28)
   out[3] = (float)dice;
@@ -1113,8 +1157,8 @@ extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* s
     FM_CUDA(cudaMalloc((void**)b, pb));
     FM_CUDA(cudaMemset(*b, 0, pb));
   }
-  FM_CUDA(cudaMalloc((void**)&m->sums, 8 * sizeof(double)));
-  FM_CUDA(cudaMemset(m->sums, 0, 8 * sizeof(double)));
+  FM_CUDA(cudaMalloc((void**)&m->sums, kNumLossSums * sizeof(double)));
+  FM_CUDA(cudaMemset(m->sums, 0, kNumLossSums * sizeof(double)));
   int64_t pack_elems = 0;
   for (auto& l : m->layers)
     if (!l.is_norm) pack_elems += 2 * ((l.wcount() + 63) & ~(int64_t)63);
@@ -1382,7 +1426,7 @@ static int backward_isensee(fm_model* m, int B) {
   };
   FM_TRY(k_zero(ctx, m->grads, (size_t)m->nparams * sizeof(float)));
   // d(loss)/d(summed logits); the deep-supervision sum hands the same gradient, 2^3 sum-pooled, to every head
-  FM_TRY(k_dice_bwd(ctx, m->prob.p, m->t_in.p, m->sums, n0, m->dz.p, 1));
+  FM_TRY(k_dice_bwd(ctx, m->prob.p, m->t_in.p, m->sums, n0, m->dz.p, 1, m->xent()));
   std::vector<const float*> gseg(D, nullptr);
   gseg[0] = m->dz.p;
   for (int l = 1; l < m->nseg; ++l) {
@@ -1857,6 +1901,8 @@ extern "C" int fm_patchwise_predict_dp(fm_model* m, const float* vol, const int3
 // the compute stream before this step, which may still read the previous targets.
 static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullptr) {
   fm_ctx* ctx = m->ctx;
+  FM_CHECK(m->loss_kind != 2 || (m->mask_valid && m->mask_batch == batch), FM_ESTATE,
+           "dice_and_xent_mask: call fm_model_set_weight_mask with this batch's weight mask before the step");
   if (t_host) {
     FM_CUDA(cudaEventRecord(ctx->copy_fence, ctx->stream));
     FM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_fence, 0));
@@ -1874,7 +1920,8 @@ static int train_forward_dev(fm_model* m, int batch, const float* t_host = nullp
     FM_CUDA(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
     FM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
   }
-  if (!m->stats_done) FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0));
+  if (!m->stats_done)
+    FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)batch * m->vox(0), m->sums, 0, m->xent()));
   m->stats_done = false;
   m->last_batch = batch;
   m->fwd_valid = true;
@@ -1911,7 +1958,7 @@ static int stage_inputs(fm_model* m, const float* x, const float* t, int batch) 
       FM_CUDA(cudaEventCreateWithFlags(&m->stage_free[b], cudaEventDisableTiming));
     }
     FM_CUDA(cudaEventCreateWithFlags(&m->sums_ready, cudaEventDisableTiming));
-    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, 8 * sizeof(double)));
+    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, kNumLossSums * sizeof(double)));
   }
   const size_t n = (size_t)batch * m->vox(0), nx = n * m->cin_real;
   const int b = (m->stage_idx ^= 1);
@@ -1975,9 +2022,9 @@ extern "C" int fm_train_metrics_async(fm_model* m) {
       FM_CUDA(cudaEventCreateWithFlags(&m->stage_free[b], cudaEventDisableTiming));
     }
     FM_CUDA(cudaEventCreateWithFlags(&m->sums_ready, cudaEventDisableTiming));
-    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, 8 * sizeof(double)));
+    FM_CUDA(cudaMallocHost((void**)&m->sums_pin, kNumLossSums * sizeof(double)));
   }
-  FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, kNumLossSums * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaEventRecord(m->sums_ready, ctx->stream));
   m->metrics_pending = true;
   return FM_OK;
@@ -1987,7 +2034,7 @@ extern "C" int fm_train_metrics_wait(fm_model* m, float out_metrics[4]) {
   FM_CHECK(m->metrics_pending, FM_ESTATE, "fm_train_metrics_wait without fm_train_metrics_async");
   FM_CUDA(cudaSetDevice(m->ctx->device));
   FM_CUDA(cudaEventSynchronize(m->sums_ready));
-  metrics_from_sums(m->sums_pin, out_metrics);
+  metrics_from_sums(m->sums_pin, out_metrics, m->loss_kind ? m->xent_weight : 0.f);
   m->metrics_pending = false;
   return FM_OK;
 }
@@ -2017,9 +2064,9 @@ extern "C" int fm_train_apply(fm_model* m, float lr, uint64_t after_stream, floa
   m->packs_dirty = true;
   FM_TRY(refresh_packs(m));
   if (out_metrics) {
-    FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, kNumLossSums * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FM_CUDA(cudaStreamSynchronize(ctx->stream));
-    metrics_from_sums(m->sums_host, out_metrics);
+    metrics_from_sums(m->sums_host, out_metrics, m->loss_kind ? m->xent_weight : 0.f);
   }
   return FM_OK;
 }
@@ -2081,12 +2128,12 @@ extern "C" int fm_train_step(fm_model* m, const float* x, const float* t, int ba
   FM_TRY(ensure_capacity(m, batch, true));
   FM_TRY(stage_inputs(m, x, t, batch));
   FM_TRY(train_forward_dev(m, batch));
-  FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(m->sums_pin, m->sums, kNumLossSums * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   FM_CUDA(cudaEventRecord(m->sums_ready, ctx->stream));
   FM_TRY(fm_train_backward(m));
   FM_TRY(fm_train_apply(m, lr, 0, nullptr));
   FM_CUDA(cudaEventSynchronize(m->sums_ready));  // the inputs were consumed long before: x / t may be reused
-  metrics_from_sums(m->sums_pin, out_metrics);
+  metrics_from_sums(m->sums_pin, out_metrics, m->loss_kind ? m->xent_weight : 0.f);
   return FM_OK;
 }
 
@@ -2137,7 +2184,7 @@ extern "C" int fm_train_step_sampled(fm_model* m, fm_volset* s, const int32_t* c
 static int dp_step_after_forward(fm_model* m, float lr, float out_metrics[4]) {
   fm_ctx* ctx = m->ctx;
   // 8 float64: the GLOBAL Dice statistics every rank back-propagates (64 bytes; latency only)
-  FM_TRY(comm_allreduce(ctx, m->sums, 8, 1, ctx->stream));
+  FM_TRY(comm_allreduce(ctx, m->sums, kNumLossSums, 1, ctx->stream));
   FM_TRY(fm_train_metrics_async(m));
   FM_TRY(fm_train_backward(m));
   // gradient buckets in completion order (backward runs in reverse creation order): each all-reduce waits only for
@@ -2206,12 +2253,14 @@ extern "C" int fm_evaluate(fm_model* m, const float* x, const float* t, int batc
   const size_t n = (size_t)batch * m->vox(0);
   FM_TRY(upload(m, x, m->x_in.p, n * m->cin_real));
   FM_TRY(upload(m, t, m->t_in.p, n));
+  FM_CHECK(m->loss_kind != 2 || (m->mask_valid && m->mask_batch == batch), FM_ESTATE,
+           "dice_and_xent_mask: call fm_model_set_weight_mask with this batch's weight mask before fm_evaluate");
   FM_TRY(forward(m, batch));  // inference kernels: same bits as fm_predict
-  FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)n, m->sums, 0));
+  FM_TRY(k_dice_sums(m->ctx, m->prob.p, m->t_in.p, (int64_t)n, m->sums, 0, m->xent()));
   m->fwd_valid = false;
-  FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  FM_CUDA(cudaMemcpyAsync(m->sums_host, m->sums, kNumLossSums * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
-  metrics_from_sums(m->sums_host, out_metrics);
+  metrics_from_sums(m->sums_host, out_metrics, m->loss_kind ? m->xent_weight : 0.f);
   return FM_OK;
 }
 
@@ -2530,13 +2579,40 @@ extern "C" int fm_op_dice(fm_ctx* ctx, const float* p, const float* t, int64_t n
   double* ds = nullptr;
   FM_TRY(s.up_f32(p, (size_t)n, &dp));
   FM_TRY(s.up_f32(t, (size_t)n, &dt));
-  FM_TRY(s.alloc(&ds, 8));
+  FM_TRY(s.alloc(&ds, kNumLossSums));
   FM_TRY(k_dice_sums(ctx, dp, dt, n, ds, 0));
   FM_CUDA(cudaMemcpyAsync(sums, ds, 64, cudaMemcpyDeviceToHost, ctx->stream));
   if (dloss_dp) {
     FM_TRY(s.alloc(&dg, (size_t)n));
     FM_TRY(k_dice_bwd(ctx, dp, dt, ds, n, dg, 0));
     FM_CUDA(cudaMemcpyAsync(dloss_dp, dg, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  FM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return FM_OK;
+}
+
+extern "C" int fm_op_dice_xent(fm_ctx* ctx, const float* p, const float* t, const float* mask, int64_t n,
+                               float xent_weight, float dist_sigma, double sums[9], float* dloss_dz) {
+  FM_CHECK(ctx && p && t && sums && n > 0, FM_EINVAL, "fm_op_dice_xent: bad argument");
+  FM_CHECK(mask == nullptr || dist_sigma > 0.f, FM_EINVAL, "fm_op_dice_xent: dist_sigma must be positive");
+  FM_CUDA(cudaSetDevice(ctx->device));
+  OpScratch s(ctx);
+  float *dp = nullptr, *dt = nullptr, *dm = nullptr, *dg = nullptr;
+  double* ds = nullptr;
+  FM_TRY(s.up_f32(p, (size_t)n, &dp));
+  FM_TRY(s.up_f32(t, (size_t)n, &dt));
+  if (mask) FM_TRY(s.up_f32(mask, (size_t)n, &dm));
+  XentSpec xs;
+  xs.weight = xent_weight;
+  xs.inv_sigma = mask ? 1.f / dist_sigma : 0.f;
+  xs.mask = dm;
+  FM_TRY(s.alloc(&ds, kNumLossSums));
+  FM_TRY(k_dice_sums(ctx, dp, dt, n, ds, 0, xs));
+  FM_CUDA(cudaMemcpyAsync(sums, ds, kNumLossSums * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dloss_dz) {
+    FM_TRY(s.alloc(&dg, (size_t)n));
+    FM_TRY(k_dice_bwd(ctx, dp, dt, ds, n, dg, 1, xs));
+    FM_CUDA(cudaMemcpyAsync(dloss_dz, dg, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   }
   FM_CUDA(cudaStreamSynchronize(ctx->stream));
   return FM_OK;

@@ -668,9 +668,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __restrict__ p,
                                                                 const float* __restrict__ t,
-                                                                int64_t n, double* __restrict__ part) {
+                                                                int64_t n, double* __restrict__ part, XentSpec xs) {
   FM_PDL_SYNC();
-  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int64_t nv = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __r
       s[4] += tb;
       s[5] += pb;
       s[6] += (ta[k] == pb) ? 1.f : 0.f;
+      if (xs.weight != 0.f) s[7] += xent_voxel_weight(xs, i * 4 + k) * xent_term(ta[k], pa[k]);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -701,17 +702,18 @@ __global__ void __launch_bounds__(kThreads) dice_partial_kernel(const float* __r
       s[4] += tb;
       s[5] += pb;
       s[6] += (t[i] == pb) ? 1.f : 0.f;
+      if (xs.weight != 0.f) s[7] += xent_voxel_weight(xs, i) * xent_term(t[i], p[i]);
     }
   }
-  __shared__ double sh[kThreads / 32][7];
+  __shared__ double sh[kThreads / 32][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
+  for (int k = 0; k < 8; ++k) {
     const double w = warp_sum((double)s[k]);
     if (lane == 0) sh[warp][k] = w;
   }
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 8) {
     double a = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) a += sh[w][threadIdx.x];
     part[(int64_t)blockIdx.x * 8 + threadIdx.x] = a;
@@ -723,17 +725,18 @@ __global__ void __launch_bounds__(256) dice_final_kernel(const double* __restric
   FM_PDL_SYNC();
   // 32 strided partial chains per statistic, then a fixed-order fold: deterministic, ~20 dependent adds deep
   __shared__ double sh[32][8];
+  // partial slot 7 = sum w * binary cross-entropy (zero under the plain Dice loss) -> sums[8]; sums[7] = element count
   const int k = threadIdx.x & 7, j = threadIdx.x >> 3;
   double a = 0.0;
-  if (k < 7)
-    for (int b = j; b < nblocks; b += 32) a += part[(int64_t)b * 8 + k];
+  for (int b = j; b < nblocks; b += 32) a += part[(int64_t)b * 8 + k];
   sh[j][k] = a;
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 8) {
     double s = 0.0;
     for (int g = 0; g < 32; ++g) s += sh[g][threadIdx.x];
-    sums[threadIdx.x] = accumulate ? sums[threadIdx.x] + s : s;
-  } else if (threadIdx.x == 7) {
+    const int dst = threadIdx.x == 7 ? 8 : threadIdx.x;
+    sums[dst] = accumulate ? sums[dst] + s : s;
+  } else if (threadIdx.x == 8) {
     sums[7] = accumulate ? sums[7] + n_elems : n_elems;
   }
 }
@@ -741,11 +744,13 @@ __global__ void __launch_bounds__(256) dice_final_kernel(const double* __restric
 // dL/dz for L = -dice(t, sigmoid(z)): closed form of metrics.py:11-15,31-32 with smooth = 1
 __global__ void dice_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t,
                                 const double* __restrict__ sums, int64_t n, float* __restrict__ dz,
-                                int through_sigmoid) {
+                                int through_sigmoid, XentSpec xs) {
   FM_PDL_SYNC();
   const double I = sums[0], S = sums[1] + sums[2] + 1.0;
   const float a = (float)(-2.0 / S);               // coefficient of t_i
   const float b = (float)((2.0 * I + 1.0) / (S * S));  // constant term
+  // cross-entropy term of dice_and_xent (through the sigmoid only): weight / count * w_i * (p_i - t_i)
+  const float xc = xs.weight != 0.f ? (float)((double)xs.weight / sums[7]) : 0.f;
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 4 <= n) {
     const float4 pp = __ldg(reinterpret_cast<const float4*>(p + i));
@@ -760,12 +765,21 @@ __global__ void dice_bwd_kernel(const float* __restrict__ p, const float* __rest
       o.y *= pp.y * (1.f - pp.y);
       o.z *= pp.z * (1.f - pp.z);
       o.w *= pp.w * (1.f - pp.w);
+      if (xc != 0.f) {
+        o.x += xc * xent_voxel_weight(xs, i) * xent_grad(tt.x, pp.x);
+        o.y += xc * xent_voxel_weight(xs, i + 1) * xent_grad(tt.y, pp.y);
+        o.z += xc * xent_voxel_weight(xs, i + 2) * xent_grad(tt.z, pp.z);
+        o.w += xc * xent_voxel_weight(xs, i + 3) * xent_grad(tt.w, pp.w);
+      }
     }
     *reinterpret_cast<float4*>(dz + i) = o;
   } else {
     for (; i < n; ++i) {
       float o = a * t[i] + b;
-      if (through_sigmoid) o *= p[i] * (1.f - p[i]);
+      if (through_sigmoid) {
+        o *= p[i] * (1.f - p[i]);
+        if (xc != 0.f) o += xc * xent_voxel_weight(xs, i) * xent_grad(t[i], p[i]);
+      }
       dz[i] = o;
     }
   }
@@ -1094,9 +1108,9 @@ int k_upsample3d_bwd(fm_ctx* ctx, const bf16* dy, const bf16* act, bf16* dx, Dim
   return FM_OK;
 }
 
-int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* sums, int accumulate) {
-  ProfScope prof(ctx, "dice_sums", 0.0, (double)n * 8.0);
-  FM_CUDA(launch_pdl(dice_partial_kernel, dim3(kRedBlocks), dim3(kThreads), 0, ctx->stream, p, t, n, ctx->red_scratch));
+int k_dice_sums(fm_ctx* ctx, const float* p, const float* t, int64_t n, double* sums, int accumulate, XentSpec xs) {
+  ProfScope prof(ctx, "dice_sums", 0.0, (double)n * (xs.mask ? 12.0 : 8.0));
+  FM_CUDA(launch_pdl(dice_partial_kernel, dim3(kRedBlocks), dim3(kThreads), 0, ctx->stream, p, t, n, ctx->red_scratch, xs));
   FM_LAUNCH_OK(ctx);
   FM_CUDA(launch_pdl(dice_final_kernel, dim3(1), dim3(256), 0, ctx->stream, ctx->red_scratch, kRedBlocks, (double)n, sums,
                                               accumulate));
@@ -1110,10 +1124,11 @@ int k_dice_finalize(fm_ctx* ctx, int nblocks, double n_elems, double* sums) {
   return FM_OK;
 }
 int k_dice_bwd(fm_ctx* ctx, const float* p, const float* t, const double* sums, int64_t n, float* dz,
-               int through_sigmoid) {
-  ProfScope prof(ctx, "dice_bwd", 0.0, (double)n * 12.0);
+               int through_sigmoid, XentSpec xs) {
+  FM_CHECK(xs.weight == 0.f || through_sigmoid, FM_EINVAL, "dice_bwd: the cross-entropy term is formed through the sigmoid");
+  ProfScope prof(ctx, "dice_bwd", 0.0, (double)n * (xs.mask ? 16.0 : 12.0));
   FM_CUDA(launch_pdl(dice_bwd_kernel, dim3(grid_for(ceil_div64(n, 4))), dim3(kThreads), 0, ctx->stream, p, t, sums, n, dz,
-                                                                           through_sigmoid));
+                                                                           through_sigmoid, xs));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -179,11 +179,36 @@ int k_upsample3d_bwd(fm_ctx*, const bf16* dy, const bf16* act, bf16* dx, Dims5 c
                      int dy_C, int dy_cofs, int pz = 2);
 // fp32 [vox][Cin] -> bf16 [vox][Cpad], channels >= Cin zero (first layer of the 2.5D U-Net: 6 -> 16 channels)
 int k_pad_cast(fm_ctx*, const float* in, bf16* out, int64_t vox, int Cin, int Cpad);
-// loss statistics over p,t (fp32): sums[8] (double) = {tp, t, p, tbpb, tb, pb, correct, count}
-int k_dice_sums(fm_ctx*, const float* p, const float* t, int64_t n, double* sums, int accumulate);
-// dL/dz = dL/dp * p (1-p) with global sums (closed form, metrics.py:11-15)
+// dice_and_xent / dice_and_xent_mask (metrics.py:68-95): loss = -dice + weight * mean(w * binary_crossentropy(t, p)),
+// w = exp(-mask / dist_sigma) per voxel (mask: the second model input of isensee2017.py:85-88) or 1 without a mask.
+// weight == 0 selects the plain soft-Dice loss; the statistics then carry a zero in the cross-entropy slot.
+struct XentSpec {
+  float weight = 0.f;
+  float inv_sigma = 0.f;
+  const float* mask = nullptr;
+};
+constexpr int kNumLossSums = 9;
+#ifdef __CUDACC__
+// Keras K.binary_crossentropy on probabilities (TF backend): p is clipped to [1e-7, 1 - 1e-7] (fp32), turned back into
+// a logit and fed to sigmoid_cross_entropy_with_logits, i.e. -(t log p + (1 - t) log(1 - p)) on the clipped p; its
+// gradient w.r.t. the pre-sigmoid logit is (p - t), and zero where the clip is active.
+__device__ __forceinline__ float xent_term(float t, float p) {
+  const float pc = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
+  return -(t * logf(pc) + (1.f - t) * log1pf(-pc));
+}
+__device__ __forceinline__ float xent_grad(float t, float p) {
+  return (p >= 1e-7f && p <= 1.f - 1e-7f) ? p - t : 0.f;
+}
+__device__ __forceinline__ float xent_voxel_weight(const XentSpec& xs, int64_t i) {
+  return xs.mask != nullptr ? __expf(-__ldg(xs.mask + i) * xs.inv_sigma) : 1.f;
+}
+#endif
+// loss statistics over p,t (fp32): sums[9] (double) = {tp, t, p, tbpb, tb, pb, correct, count, sum w*bce}
+int k_dice_sums(fm_ctx*, const float* p, const float* t, int64_t n, double* sums, int accumulate,
+                XentSpec xs = XentSpec());
+// dL/dz = dL/dp * p (1-p) with global sums (closed form, metrics.py:11-15) [+ weight/count * w * (p - t)]
 int k_dice_bwd(fm_ctx*, const float* p, const float* t, const double* sums, int64_t n, float* dz,
-               int through_sigmoid);
+               int through_sigmoid, XentSpec xs = XentSpec());
 int k_adam(fm_ctx*, float* p, const float* g, float* m, float* v, int64_t n, int iterations,
            float lr);
 int k_zero(fm_ctx*, void* p, size_t bytes);
@@ -237,12 +262,13 @@ int k_head_fwd(fm_ctx*, const bf16* x, const float* w, const float* b, float* p,
                int C, int apply_sigmoid = 1);
 // training forward: head + sigmoid + the 8 loss statistics of k_dice_sums in one pass over the activations
 int k_head_fwd_dice(fm_ctx*, const bf16* x, const float* w, const float* b, const float* t, float* p, int64_t voxels,
-                    int C, double* sums);
+                    int C, double* sums, XentSpec xs = XentSpec());
 int k_dice_finalize(fm_ctx*, int nblocks, double n_elems, double* sums);
 // head backward: dx[v,c] = dz[v] * w[c] * (x[v,c] > 0); dw[c] = sum_v dz[v] x[v,c]; db = sum dz.
 // With `t` and `sums`: `dz` holds the probabilities and dL/dz of the soft-Dice loss is formed inside (fused dice_bwd)
 int k_head_bwd(fm_ctx*, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
-               float* db, int64_t voxels, int C, int mode = 0, const float* t = nullptr, const double* sums = nullptr);
+               float* db, int64_t voxels, int C, int mode = 0, const float* t = nullptr, const double* sums = nullptr,
+               XentSpec xs = XentSpec());
 // weight repack: master fp32 [Cout][taps][Cin] -> bf16 fprop pack (same layout) and bf16 dgrad
 // pack(s) [Cin_s][taps flipped][Cout] per source
 // all layers in ONE launch (after every Adam step): per layer the fprop pack, the dgrad pack(s) and, where the

@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const bf16* __restri
 __global__ void __launch_bounds__(kThreads) head_fwd_dice_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ b,
                                                                  const float* __restrict__ t, float* __restrict__ p,
-                                                                 int64_t voxels, int C, double* __restrict__ part) {
+                                                                 int64_t voxels, int C, double* __restrict__ part,
+                                                                 XentSpec xs) {
   FM_PDL_SYNC();
   const int lpv = C >> 3;  // lanes per voxel (power of two <= 32)
   const int sub = threadIdx.x % lpv;
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_dice_kernel(const bf16* __r
   for (int i = 0; i < 8; ++i) wv[i] = __ldg(w + sub * 8 + i);
   const float bb = __ldg(b);
   const int64_t vpb = blockDim.x / lpv;
-  float s[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   constexpr int U = 4;
   for (int64_t base = (int64_t)blockIdx.x * vpb * U; base < voxels; base += (int64_t)gridDim.x * vpb * U) {
     uint4 xv[U];
@@ -404,20 +405,21 @@ __global__ void __launch_bounds__(kThreads) head_fwd_dice_kernel(const bf16* __r
         s[4] += tb;
         s[5] += pb;
         s[6] += (tt == pb) ? 1.f : 0.f;
+        if (xs.weight != 0.f) s[7] += xent_voxel_weight(xs, v) * xent_term(tt, pv);
       }
     }
   }
-  __shared__ double shd[kThreads / 32][7];
+  __shared__ double shd[kThreads / 32][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
+  for (int k = 0; k < 8; ++k) {
     double wsum = (double)s[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
     if (lane == 0) shd[warp][k] = wsum;
   }
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 8) {
     double a = 0.0;
     for (int wi = 0; wi < kThreads / 32; ++wi) a += shd[wi][threadIdx.x];
     part[(int64_t)blockIdx.x * 8 + threadIdx.x] = a;
@@ -431,17 +433,19 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
                                                             float* __restrict__ dw,
                                                             float* __restrict__ db, int64_t voxels,
                                                             int C, int mode, const float* __restrict__ pt,
-                                                            const double* __restrict__ sums) {
+                                                            const double* __restrict__ sums, XentSpec xs) {
   FM_PDL_SYNC();
   // mode 0: dx = g*w masked by ReLU(x) (plain U-Net head); 1: dx = g*w; 2: dx += g*w (Isensee seg heads)
   // `pt` != NULL: `dz` holds the probabilities p, `pt` the targets t and g = dL/dz is formed here - the closed-form
   // gradient of L = -dice(t, sigmoid(z)) (metrics.py:11-15,31-32, smooth = 1) with the GLOBAL sums - instead of being
   // read from a dz tensor written by a separate dice_bwd launch
-  float ga = 0.f, gbc = 0.f;
+  float ga = 0.f, gbc = 0.f, xc = 0.f;
   if (pt != nullptr) {
     const double I = sums[0], S = sums[1] + sums[2] + 1.0;
     ga = (float)(-2.0 / S);
     gbc = (float)((2.0 * I + 1.0) / (S * S));
+    // dice_and_xent: + weight / count * w_i * (p_i - t_i) (metrics.py:68-78 through the sigmoid)
+    if (xs.weight != 0.f) xc = (float)((double)xs.weight / sums[7]);
   }
   const int lpv = C >> 3;
   const int sub = threadIdx.x % lpv;
@@ -460,8 +464,13 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
     float gg[2] = {__ldg(dz + v0), has1 ? __ldg(dz + v1) : 0.f};
     if (pt != nullptr) {
       const float t0 = __ldg(pt + v0), t1 = has1 ? __ldg(pt + v1) : 0.f;
-      gg[0] = (ga * t0 + gbc) * gg[0] * (1.f - gg[0]);
-      gg[1] = (ga * t1 + gbc) * gg[1] * (1.f - gg[1]);
+      const float p0 = gg[0], p1 = gg[1];
+      gg[0] = (ga * t0 + gbc) * p0 * (1.f - p0);
+      gg[1] = (ga * t1 + gbc) * p1 * (1.f - p1);
+      if (xc != 0.f) {
+        gg[0] += xc * xent_voxel_weight(xs, v0) * xent_grad(t0, p0);
+        if (has1) gg[1] += xc * xent_voxel_weight(xs, v1) * xent_grad(t1, p1);
+      }
     }
     const uint4 tt[2] = {__ldg(reinterpret_cast<const uint4*>(x + v0 * C + sub * 8)),
                          has1 ? __ldg(reinterpret_cast<const uint4*>(x + v1 * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u)};
@@ -708,7 +717,7 @@ int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float
 
 // head + sigmoid + Dice / VOD / accuracy partial sums in one pass; `sums` receives the 8 folded statistics
 int k_head_fwd_dice(fm_ctx* ctx, const bf16* x, const float* w, const float* b, const float* t, float* p,
-                    int64_t voxels, int C, double* sums) {
+                    int64_t voxels, int C, double* sums, XentSpec xs) {
   FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
            "head: channel count %d must be a power of two in [8,256]", C);
   const int lpv = C / 8;
@@ -717,14 +726,14 @@ int k_head_fwd_dice(fm_ctx* ctx, const bf16* x, const float* w, const float* b, 
   {
     ProfScope prof(ctx, "head_fwd_dice", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 8.0));
     FM_CUDA(launch_pdl(head_fwd_dice_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, C,
-                       ctx->red_scratch));
+                       ctx->red_scratch, xs));
     FM_LAUNCH_OK(ctx);
   }
   return k_dice_finalize(ctx, grid, (double)voxels, sums);
 }
 
 int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16* dx, float* dw,
-               float* db, int64_t voxels, int C, int mode, const float* t, const double* sums) {
+               float* db, int64_t voxels, int C, int mode, const float* t, const double* sums, XentSpec xs) {
   FM_CHECK(C >= 8 && C <= 256 && (C & (C - 1)) == 0, FM_EINVAL,
            "head_bwd: channel count %d must be a power of two in [8,256]", C);
   const int lpv = C / 8;
@@ -733,7 +742,7 @@ int k_head_bwd(fm_ctx* ctx, const bf16* x, const float* dz, const float* w, bf16
   ProfScope prof(ctx, t ? "head_bwd_dice" : "head_bwd", 4.0 * C * (double)voxels,
                  (double)voxels * (C * 4.0 + (t ? 8.0 : 4.0)));
   FM_CUDA(launch_pdl(head_bwd_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, dz, w, dx, dw, db, voxels, C, mode, t,
-                     sums));
+                     sums, xs));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

@@ -72,6 +72,8 @@ SIGNATURES = {
     "fm_model_get_grads": (c_int, [c_vp, c_int, c_fp, c_fp]),
     "fm_model_reset_optimizer": (c_int, [c_vp]),
     "fm_model_set_dropout": (c_int, [c_vp, ctypes.c_float, ctypes.c_uint64]),
+    "fm_model_set_loss": (c_int, [c_vp, c_int, ctypes.c_float, ctypes.c_float]),
+    "fm_model_set_weight_mask": (c_int, [c_vp, c_fp, c_int]),
     "fm_train_metrics_async": (c_int, [c_vp]),
     "fm_train_metrics_wait": (c_int, [c_vp, c_fp]),
     "fm_host_alloc": (c_int, [ctypes.c_size_t, ctypes.POINTER(c_vp)]),
@@ -127,6 +129,7 @@ SIGNATURES = {
     "fm_op_upsample3d": (c_int, [c_vp, c_fp] + [c_int] * 5 + [c_fp]),
     "fm_op_upsample3d_bwd": (c_int, [c_vp, c_fp, c_fp] + [c_int] * 5 + [c_fp]),
     "fm_op_dice": (c_int, [c_vp, c_fp, c_fp, c_i64, c_dp, c_fp]),
+    "fm_op_dice_xent": (c_int, [c_vp, c_fp, c_fp, c_fp, c_i64, ctypes.c_float, ctypes.c_float, c_dp, c_fp]),
     "fm_op_adam": (c_int, [c_vp, c_fp, c_fp, c_fp, c_fp, c_i64, c_int, c_f]),
 }
 

@@ -4,8 +4,12 @@
 The callables evaluate on host NumPy arrays (they are identifiers + evaluation helpers); the
 training loss itself is computed on the device by libfetalb200 (fm_train_step) — the builders
 compare `loss_function` by identity with `dice_coefficient_loss`, as the reference does
-(unet3d/unet.py:82-83), and only the soft-Dice loss is built on the device path.
+(unet3d/unet.py:82-83). Built on the device path: `dice_coefficient_loss`, `dice_and_xent` (also as a
+`functools.partial` with `xent_weight`) and `dice_and_xent_mask` (the closure factory that takes the weight-mask
+input, isensee2017.py:85-88); see `device_loss_spec`.
 """
+import functools
+
 import numpy as np
 
 
@@ -63,11 +67,56 @@ def _not_built(name):
     return fn
 
 
+def binary_crossentropy(y_true, y_pred):
+    # Keras K.binary_crossentropy (TF backend) on probabilities: clip to [1e-7, 1 - 1e-7], elementwise
+    t = np.asarray(y_true, dtype=np.float64)
+    p = np.clip(np.asarray(y_pred, dtype=np.float64), 1e-7, 1. - 1e-7)
+    return -(t * np.log(p) + (1. - t) * np.log1p(-p))
+
+
+def weighted_cross_entropy_loss(y_true, y_pred, weight_mask=None):
+    # metrics.py:73-77
+    xent = binary_crossentropy(y_true, y_pred)
+    if weight_mask is not None:
+        xent = np.asarray(weight_mask, dtype=np.float64).reshape(xent.shape) * xent
+    return float(np.mean(xent))
+
+
+def dice_and_xent(y_true, y_pred, xent_weight=1.0, weight_mask=None):
+    # metrics.py:68-70
+    return dice_coefficient_loss(y_true, y_pred) + xent_weight * weighted_cross_entropy_loss(y_true, y_pred, weight_mask)
+
+
+def dice_and_xent_mask(weight_mask, xent_weight=1.0, dist_sigma=3):
+    """metrics.py:89-95: a loss closure over the weight-mask input. With `weight_mask` an array the closure evaluates on
+    the host; the builders call it with the mask INPUT placeholder (isensee2017.py:85-88) - here `None` - and only read
+    its parameters (`device_loss_spec`): on the device the mask arrives per step as the second input."""
+    def _loss(y_true, y_pred):
+        w = None if weight_mask is None else np.exp(-np.asarray(weight_mask, dtype=np.float64) / dist_sigma)
+        return dice_and_xent(y_true, y_pred, xent_weight=xent_weight, weight_mask=w)
+    _loss.xent_weight, _loss.dist_sigma, _loss.is_dice_and_xent_mask = float(xent_weight), float(dist_sigma), True
+    return _loss
+
+
+def device_loss_spec(loss_function, has_mask_input=False):
+    """-> (kind, xent_weight, dist_sigma) for fm_model_set_loss, or None when the loss is not built on the device."""
+    if loss_function is dice_coefficient_loss:
+        return 0, 0.0, 0.0
+    if loss_function is dice_and_xent:
+        return 1, 1.0, 0.0
+    if isinstance(loss_function, functools.partial) and loss_function.func is dice_and_xent and not loss_function.args \
+            and set(loss_function.keywords) <= {"xent_weight"}:
+        return 1, float(loss_function.keywords.get("xent_weight", 1.0)), 0.0
+    if loss_function is dice_and_xent_mask and has_mask_input:
+        return 2, 1.0, 3.0                                   # the factory's defaults, as isensee2017.py:88 calls it
+    if getattr(loss_function, "is_dice_and_xent_mask", False) and has_mask_input:
+        return 2, loss_function.xent_weight, loss_function.dist_sigma
+    return None
+
+
 # names the reference exports (metrics.py:97-100, config_utils.py:73-79)
 dice_coef = dice_coefficient
 dice_coef_loss = dice_coefficient_loss
 binary_crossentropy_loss = _not_built("binary_crossentropy_loss")
 focal_loss = _not_built("focal_loss")
-dice_and_xent = _not_built("dice_and_xent")
-dice_and_xent_mask = _not_built("dice_and_xent_mask")
 double_dice_loss = _not_built("double_dice_loss")

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from .. import _lib
-from ..metrics import dice_coefficient_loss
+from ..metrics import dice_coefficient_loss, device_loss_spec
 
 
 class _Optimizer:
@@ -26,7 +26,7 @@ class Model:
     """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
 
     def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
-                 device=None, ndim=3, isensee_levels=None, dropout_rate=0.0, dropout_seed=0x5EED):
+                 device=None, ndim=3, isensee_levels=None, dropout_rate=0.0, dropout_seed=0x5EED, mask_shape=None):
         lib = _lib.load()
         self._ctx = _lib.get_context(device)
         self.ndim = int(ndim)
@@ -57,7 +57,13 @@ class Model:
         self.n_base_filters = int(n_base_filters)
         self.n_labels = int(n_labels)
         self.optimizer = _Optimizer(initial_learning_rate)
+        # the second (weight mask) input of isensee2017.py:85-88: the loss argument is then the closure FACTORY
+        self.mask_shape = None if mask_shape is None else tuple(int(v) for v in mask_shape)
         self.loss = loss_function
+        self._loss_spec = device_loss_spec(loss_function, has_mask_input=self.mask_shape is not None)
+        if self._loss_spec is not None:
+            _lib.check(lib.fm_model_set_loss(h, int(self._loss_spec[0]), float(self._loss_spec[1]),
+                                             float(self._loss_spec[2])))
         self.metrics = ['binary_accuracy', 'vod_coefficient']
         self.metrics_names = ['loss', 'binary_accuracy', 'vod_coefficient']
         if loss_function is not dice_coefficient_loss:
@@ -239,6 +245,8 @@ class Model:
 
     # ---- inference -------------------------------------------------------------------------
     def predict(self, x, batch_size=32, verbose=0):
+        if self.mask_shape is not None and isinstance(x, (list, tuple)):
+            x = x[0]                                               # the mask input only feeds the loss
         x = _lib.f32c(x)
         assert x.shape[1:] == self.input_shape[1:], "expected [B,%s], got %s" % (self.input_shape[1:], x.shape)
         out = np.empty((x.shape[0],) + self.output_shape[1:], np.float32)
@@ -252,11 +260,25 @@ class Model:
     def _check_loss(self):
         if not self.trainable:
             raise NotImplementedError("%s: training is on the §8 'next' list (forward / inference is built)" % self.name)
-        if self.loss is not dice_coefficient_loss:
-            raise NotImplementedError("only dice_coefficient_loss is built on the device path")
+        if self._loss_spec is None:
+            raise NotImplementedError("loss %r: dice_coefficient_loss, dice_and_xent and dice_and_xent_mask (with "
+                                      "mask_shape) are built on the device path" % (self.loss,))
+
+    def _split_mask(self, x):
+        """`[x, mask]` -> x after handing the weight mask to the device (two-input model, isensee2017.py:85-88)."""
+        if self.mask_shape is None:
+            return x
+        assert isinstance(x, (list, tuple)) and len(x) == 2, "this model takes [x, weight_mask] (mask_shape was given)"
+        x, mask = x
+        mask = _lib.f32c(mask)
+        assert mask.shape[1:] == self.mask_shape and mask.shape[0] == len(x), (mask.shape, self.mask_shape)
+        assert int(np.prod(self.mask_shape)) == int(np.prod(self.output_shape[1:])), "one weight per output voxel"
+        _lib.check(self._lib.fm_model_set_weight_mask(self._h, _lib.fptr(mask), int(mask.shape[0])))
+        return x
 
     def train_on_batch(self, x, y, **kw):
         self._check_loss()
+        x = self._split_mask(x)
         x, y = _lib.f32c(x), _lib.f32c(y)
         assert x.shape[1:] == self.input_shape[1:] and y.shape == (x.shape[0],) + self.output_shape[1:], (x.shape, y.shape)
         m = np.zeros(4, np.float32)
@@ -281,6 +303,8 @@ class Model:
             from .. import metrics as _m
             p = self.predict(x)
             return [_m.dice_coefficient_loss(y, p), _m.binary_accuracy(y, p), _m.vod_coefficient(y, p)]
+        self._check_loss()
+        x = self._split_mask(x)
         x, y = _lib.f32c(x), _lib.f32c(y)
         m = np.zeros(4, np.float32)
         _lib.check(self._lib.fm_evaluate(self._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]), _lib.fptr(m)))
@@ -289,9 +313,11 @@ class Model:
     def evaluate(self, x, y, batch_size=32, verbose=0):
         """Keras semantics: per-batch metrics averaged with batch-size weights."""
         tot, n = np.zeros(len(self.metrics_names)), 0
-        for b0 in range(0, len(x), batch_size):
-            r = self.test_on_batch(x[b0:b0 + batch_size], y[b0:b0 + batch_size])
-            nb = len(x[b0:b0 + batch_size])
+        two = getattr(self, "mask_shape", None) is not None and isinstance(x, (list, tuple))
+        for b0 in range(0, len(y), batch_size):
+            xb = [a[b0:b0 + batch_size] for a in x] if two else x[b0:b0 + batch_size]
+            r = self.test_on_batch(xb, y[b0:b0 + batch_size])
+            nb = len(y[b0:b0 + batch_size])
             tot += np.asarray(r) * nb
             n += nb
         return list(tot / max(n, 1))
@@ -317,7 +343,7 @@ class Model:
                     r, nb = generator.train_on_next_batch(self), generator.batch_size
                 else:
                     x, y = next(generator)[:2]
-                    r, nb = self.train_on_batch(x, y), len(x)
+                    r, nb = self.train_on_batch(x, y), len(y)
                 tot += np.asarray(r) * nb
                 n += nb
             logs = {k: float(v) for k, v in zip(self.metrics_names, tot / max(n, 1))}
@@ -326,8 +352,8 @@ class Model:
                 for _ in range(int(validation_steps)):
                     x, y = next(validation_data)[:2]
                     r = self.test_on_batch(x, y)
-                    vt += np.asarray(r) * len(x)
-                    vn += len(x)
+                    vt += np.asarray(r) * len(y)
+                    vn += len(y)
                 logs.update({"val_" + k: float(v) for k, v in zip(self.metrics_names, vt / max(vn, 1))})
             logs["lr"] = float(self.optimizer.lr)
             for k, v in logs.items():
@@ -403,9 +429,8 @@ def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, dept
     (identity at inference); the keep masks come from a counter-based hash (`dropout_seed` kwarg), not TF's RNG."""
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
-    if mask_shape is not None:
-        raise NotImplementedError("mask_shape (closure loss with a second input) is on the §8 'next' list")
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
                  device=kargs.get("device"), ndim=3, isensee_levels=n_segmentation_levels,
-                 dropout_rate=dropout_rate or 0.0, dropout_seed=kargs.get("dropout_seed", 0x5EED))
+                 dropout_rate=dropout_rate or 0.0, dropout_seed=kargs.get("dropout_seed", 0x5EED),
+                 mask_shape=mask_shape)

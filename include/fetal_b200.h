@@ -136,6 +136,23 @@ int fm_model_set_iterations(fm_model* m, int iterations);
  * (fm_train_*), one keep/scale factor per (sample, channel) drawn from a counter-based hash of (seed, step, level);
  * rate 0 (the default here) switches it off. Plain U-Net models ignore it. */
 int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed);
+/* Replaces: the `loss_function` argument of the builders, looked up by getattr(fetal_net.metrics, config['loss'])
+ * (fetal/train_fetal.py:31, fetal_net/training.py:51-58):
+ *   kind 0  dice_coefficient_loss                       (fetal_net/metrics.py:31-32)                    [default]
+ *   kind 1  dice_and_xent(y_true, y_pred, xent_weight)   = -dice + xent_weight * mean(binary_crossentropy)
+ *                                                        (fetal_net/metrics.py:68-78)
+ *   kind 2  dice_and_xent_mask(weight_mask, xent_weight, dist_sigma): the cross-entropy of every voxel is weighted by
+ *           exp(-weight_mask / dist_sigma) (fetal_net/metrics.py:89-95); the mask is the model's second input
+ *           (`mask_shape`, fetal_net/model/unet3d/isensee2017.py:85-88) and is handed over per step with
+ *           fm_model_set_weight_mask.
+ * The reported loss (out_metrics[0]) becomes the combined one; out_metrics[3] stays the soft Dice coefficient, which
+ * Keras appends to the metrics when the loss is not the Dice loss (unet3d/unet.py:82-83, isensee2017.py:82-83). In a
+ * data-parallel step the cross-entropy sum travels in the same all-reduce as the Dice sums (9 doubles). */
+int fm_model_set_loss(fm_model* m, int kind, float xent_weight, float dist_sigma);
+/* Replaces: the second element of the `[x, mask]` input list a two-input Keras model is trained on
+ * (isensee2017.py:85-88): float32 [batch, X, Y, Z] distances, uploaded for the next training / evaluation call of
+ * that batch size and kept until replaced. FM_EINVAL unless the loss kind is 2. */
+int fm_model_set_weight_mask(fm_model* m, const float* mask, int batch);
 
 /* ---- inference ---------------------------------------------------------------------------- */
 
@@ -351,6 +368,11 @@ int fm_op_upsample3d_bwd(fm_ctx* ctx, const float* dy, const float* act, int N, 
                          int C, float* dx);
 int fm_op_dice(fm_ctx* ctx, const float* p, const float* t, int64_t n, double sums[8],
                float* dloss_dp);
+/* dice_and_xent / dice_and_xent_mask (fetal_net/metrics.py:68-95) on probabilities p: sums[0..7] as fm_op_dice,
+ * sums[8] = sum_i w_i * binary_crossentropy(t_i, p_i), w_i = exp(-mask_i / dist_sigma) (1 when mask == NULL);
+ * dloss_dz (optional) = d(-dice + xent_weight * sums[8] / n) / d(logit) through the sigmoid. */
+int fm_op_dice_xent(fm_ctx* ctx, const float* p, const float* t, const float* mask, int64_t n, float xent_weight,
+                    float dist_sigma, double sums[9], float* dloss_dz);
 int fm_op_adam(fm_ctx* ctx, float* p, const float* g, float* mm, float* vv, int64_t n,
                int iterations, float lr);
 

@@ -130,6 +130,23 @@ def binary_accuracy(t, p):
     return (t == torch.round(p)).to(p.dtype).mean()
 
 
+def binary_crossentropy(t, p, eps=1e-7):
+    """Keras K.binary_crossentropy (TF backend, from_logits=False): p clipped to [eps, 1-eps], turned into a logit and
+    passed to sigmoid_cross_entropy_with_logits == -(t log p + (1-t) log(1-p)) on the clipped p."""
+    pc = p.clamp(eps, 1.0 - eps)
+    return -(t * torch.log(pc) + (1.0 - t) * torch.log1p(-pc))
+
+
+def dice_and_xent(t, p, xent_weight=1.0, weight_mask=None, dist_sigma=None):
+    """metrics.py:68-78 (dice_and_xent + weighted_cross_entropy_loss); with `dist_sigma` the mask is the distance map of
+    dice_and_xent_mask (metrics.py:89-95): weight = exp(-mask / dist_sigma)."""
+    xent = binary_crossentropy(t, p)
+    if weight_mask is not None:
+        w = torch.exp(-weight_mask / dist_sigma) if dist_sigma is not None else weight_mask
+        xent = w.reshape(xent.shape) * xent
+    return dice_coefficient_loss(t, p) + xent_weight * xent.mean()
+
+
 def dice_grad_closed_form(t, p, smooth=1.0):
     """dL/dp for L = -dice: -(2 t S - (2I+smooth)) / S^2, S = sum t + sum p + smooth."""
     I = (t * p).sum()
@@ -150,13 +167,14 @@ def keras_adam_step(p, g, m, v, iterations, lr, beta_1=0.9, beta_2=0.999, eps=1e
     p[...] = p - np.float32(lr_t) * m / (np.sqrt(v) + np.float32(eps))
 
 
-def train_step(forward_fn, x, t, w, adam_state, lr, dtype=torch.float32):
-    """Generic fwd + Dice + bwd + Keras-Adam for any of the forward restatements (used for unet2d_forward)."""
+def train_step(forward_fn, x, t, w, adam_state, lr, dtype=torch.float32, loss_fn=None):
+    """Generic fwd + loss (soft Dice unless `loss_fn(t, p)` is given) + bwd + Keras-Adam for any of the forward
+    restatements."""
     names = sorted(w.keys())
     params = {n: torch.tensor(w[n], dtype=dtype, requires_grad=True) for n in names}
     xt, tt = torch.as_tensor(x).to(dtype), torch.as_tensor(t).to(dtype)
     p = forward_fn(xt, params)
-    loss = dice_coefficient_loss(tt, p)
+    loss = (loss_fn or dice_coefficient_loss)(tt, p)
     loss.backward()
     out = {"loss": float(loss.detach()), "grads": {}, "pred": p.detach().numpy()}
     it = adam_state.setdefault("iterations", 0)

@@ -306,6 +306,41 @@ def dice_case(ctx, seed=5):
     return e1 <= 1e-6 and e2 <= 1e-5, max(e1 / 1e-6, e2 / 1e-5)
 
 
+def dice_xent_case(ctx, with_mask, seed=15):
+    """fm_op_dice_xent (dice_and_xent / dice_and_xent_mask, metrics.py:68-95) against torch autograd in fp64: the ninth
+    statistic (sum w * bce) and d(loss)/d(logit) through the sigmoid. Probabilities include saturated ones (the Keras
+    clip at 1e-7 is active there: zero cross-entropy gradient)."""
+    import torch
+    from oracle import unet_oracle as uo
+    n = 4 * 16 ** 3 + 2
+    rng = np.random.default_rng(seed)
+    z = (4.0 * rng.standard_normal(n)).astype(np.float32)
+    z[:64] = 40.0 * np.sign(z[:64])                        # saturated: p == 1 or ~4e-18 in fp32
+    p = (1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32)
+    t = (rng.random(n) < 0.3).astype(np.float32)
+    mask = (6.0 * rng.random(n)).astype(np.float32) if with_mask else None
+    xw, sigma = 0.7, 3.0
+    sums = np.zeros(9, np.float64)
+    g = np.empty(n, np.float32)
+    lib = _lib.load()
+    _lib.check(lib.fm_op_dice_xent(ctx.handle, _lib.fptr(p), _lib.fptr(t), _lib.fptr(mask) if with_mask else None, n,
+                                   xw, sigma, _lib.dptr(sums), _lib.fptr(g)))
+    # reference: the loss as a function of the logit, with p fixed to the SAME fp32 probabilities the kernel saw
+    pt = torch.tensor(p.astype(np.float64), requires_grad=True)
+    tt = torch.tensor(t.astype(np.float64))
+    mt = torch.tensor(mask.astype(np.float64)) if with_mask else None
+    loss = uo.dice_and_xent(tt, pt, xw, mt, sigma if with_mask else None)
+    loss.backward()
+    gref = (pt.grad * pt.detach() * (1 - pt.detach())).numpy()       # chain through the sigmoid
+    w = np.exp(-mask.astype(np.float64) / sigma) if with_mask else np.ones(n)
+    xent_ref = float((torch.as_tensor(w) * uo.binary_crossentropy(tt, pt.detach())).sum())
+    e1 = abs(sums[8] - xent_ref) / abs(xent_ref)
+    e2 = abs((-(2 * sums[0] + 1) / (sums[1] + sums[2] + 1) + xw * sums[8] / sums[7]) - float(loss)) / abs(float(loss))
+    e3 = rel_err(g, gref)
+    # fp32 log / exp per voxel, fp32 partial sums then fp64: 2e-6 on the sums; 2e-5 on the gradient
+    return e1 <= 2e-6 and e2 <= 2e-6 and e3 <= 2e-5, max(e1 / 2e-6, e2 / 2e-6, e3 / 2e-5)
+
+
 def adam_case(ctx, seed=6):
     from oracle.unet_oracle import keras_adam_step
     n = 100003

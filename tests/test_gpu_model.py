@@ -414,3 +414,89 @@ def test_gpu_matches_keras_fixture(tag):
     assert err <= 0.04 and np.abs(p - ref).mean() <= 0.006 and soft >= 0.999, (err, soft)
     loss = model.train_on_batch(x, t)[0]
     assert abs(loss - float(z[tag + "/train_metrics"][0])) <= 3e-3
+
+
+def _grad_cosines(model, ref_grads):
+    cos = {}
+    grads = model.get_gradients()
+    for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
+        if l["is_norm"]:
+            base = l["name"][:-len("_norm")]
+            pairs = [(base + "/gamma", gk), (base + "/beta", gb)]
+        else:
+            pairs = [(l["name"] + "/kernel", gk)]
+        for name, g in pairs:
+            r = ref_grads[name].astype(np.float64).ravel()
+            g = g.astype(np.float64).ravel()
+            cos[name] = float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
+    return cos
+
+
+def test_unet3d_dice_and_xent_train_step_matches_oracle(setup):
+    """loss_function=dice_and_xent (fetal_net/metrics.py:68-78, config_utils.py:77): the combined loss, the soft Dice
+    metric Keras appends for a non-Dice loss, and the gradients against torch autograd on the fp32 restatement."""
+    import functools
+    from fetal_net import metrics as fmet
+    from fetal_net.model import unet_model_3d
+    _, w0 = setup
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32)
+    t = blob_target(x.shape, rng)
+    for loss_fn, xw in ((fmet.dice_and_xent, 1.0), (functools.partial(fmet.dice_and_xent, xent_weight=0.25), 0.25)):
+        model = unet_model_3d(input_shape=(1, 32, 32, 32), n_base_filters=16, depth=4, initial_learning_rate=1e-4,
+                              loss_function=loss_fn)
+        assert model.metrics_names == ['loss', 'binary_accuracy', 'vod_coefficient', 'dice_coefficient']
+        model.set_named_weights(w0)
+        w = {k: v.copy() for k, v in w0.items()}
+        ref = uo.train_step(lambda xt, prm: uo.unet3d_forward(xt, prm, depth=4), x, t, w, {}, 1e-4,
+                            loss_fn=lambda tt, pp: uo.dice_and_xent(tt, pp, xw))
+        got = model.train_on_batch(x, t)
+        assert len(got) == 4
+        assert got[0] == pytest.approx(ref["loss"], abs=4e-3), (got, ref["loss"])
+        p_ref = ref["pred"]
+        assert got[3] == pytest.approx(fmet.dice_coefficient(t, p_ref), abs=3e-3)
+        # host evaluation helper == oracle loss on the oracle's own prediction
+        assert loss_fn(t, p_ref) == pytest.approx(ref["loss"], abs=1e-5)
+        cos = _grad_cosines(model, ref["grads"])
+        floor = {"enc0a/kernel": 0.95, "enc0b/kernel": 0.97}
+        bad = {k: v for k, v in cos.items() if v < floor.get(k, 0.99)}
+        assert not bad, bad
+        # evaluate() reports the same combined loss on the inference kernels
+        ev = model.test_on_batch(x, t)
+        assert len(ev) == 4 and np.isfinite(ev).all()
+
+
+def test_isensee_dice_and_xent_mask_two_input_model():
+    """isensee2017_model_3d(..., loss_function=dice_and_xent_mask, mask_shape=input_shape) (train_fetal.py:31-39 with
+    config['weight_mask'], isensee2017.py:85-88): the model takes [x, weight_mask]; loss and gradients against torch
+    autograd with weight exp(-mask / 3)."""
+    from fetal_net import metrics as fmet
+    from fetal_net.model import isensee2017_model_3d
+    shape, depth, nseg = (1, 32, 32, 16), 3, 2
+    layers = uo.isensee3d_layers(depth, 16, nseg)
+    w = isensee_weights(layers, seed=13)
+    model = isensee2017_model_3d(input_shape=shape, n_base_filters=16, depth=depth, n_segmentation_levels=nseg,
+                                 dropout_rate=0, initial_learning_rate=1e-3, loss_function=fmet.dice_and_xent_mask,
+                                 mask_shape=shape)
+    model.set_named_weights(w)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2,) + shape).astype(np.float32)
+    t = _blob_truth(x)
+    mask = (8.0 * rng.random((2,) + shape)).astype(np.float32)          # distance-to-border map
+    with pytest.raises(AssertionError):
+        model.train_on_batch(x, t)                                       # the mask input is mandatory
+    wo = {k: v.copy() for k, v in w.items()}
+    mt = torch.as_tensor(mask)
+    ref = uo.train_step(lambda xt, prm: uo.isensee3d_forward(xt, prm, depth=depth, n_segmentation_levels=nseg),
+                        x, t, wo, {}, 1e-3, loss_fn=lambda tt, pp: uo.dice_and_xent(tt, pp, 1.0, mt, 3.0))
+    got = model.train_on_batch([x, mask], t)
+    assert len(got) == 4 and abs(got[0] - ref["loss"]) <= 5e-3, (got, ref["loss"])
+    assert fmet.dice_and_xent_mask(mask)(t, ref["pred"]) == pytest.approx(ref["loss"], abs=1e-5)
+    cos = _grad_cosines(model, ref["grads"])
+    worst = min(cos.items(), key=lambda kv: kv[1])
+    assert worst[1] >= 0.97 and np.median(list(cos.values())) >= 0.99, worst
+    # predict ignores the mask input; a different mask changes the loss
+    assert np.array_equal(model.predict([x, mask]), model.predict(x))
+    ev0 = model.test_on_batch([x, mask], t)
+    ev1 = model.test_on_batch([x, np.zeros_like(mask)], t)
+    assert ev1[0] > ev0[0] + 1e-3                                        # weight 1 everywhere > exp(-mask/3)

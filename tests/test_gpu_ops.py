@@ -112,6 +112,12 @@ def test_dice_sums_and_gradient(ctx):
     assert ok, worst
 
 
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_dice_and_xent_sums_and_gradient(ctx, with_mask):
+    ok, worst = gc.dice_xent_case(ctx, with_mask)
+    assert ok, worst
+
+
 def test_keras_adam(ctx):
     ok, worst = gc.adam_case(ctx)
     assert ok, worst

@@ -423,3 +423,36 @@ def test_small_host_helpers_on_a_stub():
     assert lines[-1] == "Total params: %d" % (27 * 16 + 16 + 32) and "conv3d_1" in lines[1] and lines[2].split()[-1] == "32"
     cfg = json.loads(Model.to_json(Stub()))
     assert cfg["class_name"] == "unet_model_3d" and cfg["input_shape"] == [1, 8, 8, 8]
+
+
+def test_dice_and_xent_host_helpers_and_device_loss_spec():
+    """fetal_net.metrics.dice_and_xent / dice_and_xent_mask (reference metrics.py:68-95): host evaluation against torch's
+    binary_cross_entropy, and the mapping of loss callables to fm_model_set_loss arguments."""
+    import functools
+    import torch
+    import torch.nn.functional as F
+    import fetal_net.metrics as fm
+    from oracle import unet_oracle as uo
+    rng = np.random.default_rng(0)
+    p = rng.random((2, 1, 8, 8, 8)).astype(np.float32)
+    p.ravel()[:3] = [0.0, 1.0, 1e-9]                                 # the Keras clip at 1e-7 is active
+    t = (rng.random(p.shape) < 0.4).astype(np.float32)
+    mask = (5 * rng.random(p.shape)).astype(np.float32)
+    pc = torch.as_tensor(p, dtype=torch.float64).clamp(1e-7, 1 - 1e-7)
+    bce = F.binary_cross_entropy(pc, torch.as_tensor(t, dtype=torch.float64), reduction="none")
+    want = fm.dice_coefficient_loss(t, p) + 0.5 * float(bce.mean())
+    assert fm.dice_and_xent(t, p, xent_weight=0.5) == pytest.approx(want, rel=1e-12)
+    wantm = fm.dice_coefficient_loss(t, p) + float((torch.exp(-torch.as_tensor(mask, dtype=torch.float64) / 3) * bce).mean())
+    assert fm.dice_and_xent_mask(mask)(t, p) == pytest.approx(wantm, rel=1e-12)
+    # the oracle's torch version agrees with the host helper
+    tt, pp = torch.as_tensor(t, dtype=torch.float64), torch.as_tensor(p, dtype=torch.float64)
+    assert float(uo.dice_and_xent(tt, pp, 1.0, torch.as_tensor(mask, dtype=torch.float64), 3.0)) == \
+        pytest.approx(wantm, rel=1e-12)
+    spec = fm.device_loss_spec
+    assert spec(fm.dice_coefficient_loss) == (0, 0.0, 0.0)
+    assert spec(fm.dice_and_xent) == (1, 1.0, 0.0)
+    assert spec(functools.partial(fm.dice_and_xent, xent_weight=0.3)) == (1, 0.3, 0.0)
+    assert spec(fm.dice_and_xent_mask) is None                       # needs the mask input (mask_shape)
+    assert spec(fm.dice_and_xent_mask, has_mask_input=True) == (2, 1.0, 3.0)
+    assert spec(fm.dice_and_xent_mask(None, xent_weight=2.0, dist_sigma=5), has_mask_input=True) == (2, 2.0, 5.0)
+    assert spec(fm.vod_coefficient_loss) is None and spec(fm.focal_loss) is None
