@@ -63,14 +63,29 @@ def peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernels from the committed `ncu --set full` captures (profiles/)."""
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the kernel's launches of one
+    step / one call) from the committed `ncu --set full` capture (profiles/r2_dram_traffic.json, written by
+    tools/summarize_profiles_r2.py from the capture of tools/r2_step13.sh)."""
     out = {}
-    for fn in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
-        path = os.path.join(ROOT, "profiles", fn)
-        if os.path.exists(path):
-            for k, v in json.load(open(path)).items():
-                out.setdefault(k, (v, fn))
+    path = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    if os.path.exists(path):
+        for k, v in json.load(open(path)).items():
+            out[k] = (float(v["avg_bytes_per_launch"]), "r2_dram_traffic.json")
     return out
+
+
+# bench kernel name (ctx.profile) -> key in profiles/r2_dram_traffic.json, per workload
+TRAFFIC_KEYS = {
+    "train": {"conv3d_wgrad_march": "bwd/conv3d_wgrad_march_kernel", "conv3d_march_fprop": "fwd/conv3d_march2_kernel<1, 32>",
+              "conv3d_march_dgrad": "bwd/conv3d_march2_kernel<1, 32>", "maxpool3d_bwd": "bwd/maxpool3d_bwd_kernel<2>",
+              "maxpool3d_fwd": "fwd/maxpool3d_fwd_kernel<2>", "head_fwd_dice": "fwd/head_fwd_dice_kernel",
+              "head_bwd_dice": "bwd/head_bwd_kernel", "upsample3d_fwd": "fwd/upsample3d_fwd_kernel<2>",
+              "adam": "bwd/adam_kernel"},
+    "infer": {"conv3d_march_fprop": "infer/conv3d_march2_kernel<2, 32>", "conv3d_tc_fprop": "infer/conv3d_tc_fprop_kernel",
+              "reassemble": "infer/reassemble4_kernel", "gather_patches": "infer/gather_patches4_kernel",
+              "maxpool3d_fwd": "infer/maxpool3d_fwd_kernel<2>", "upsample3d_fwd": "infer/upsample3d_fwd_kernel<2>",
+              "head_fwd": "infer/head_fwd_kernel"},
+}
 
 
 class ClockSampler:
@@ -275,11 +290,9 @@ def aggregate(recs):
     return agg
 
 
-def roofline_of(name, a, nrep, total_ms, pk, clocks, traffic):
+def roofline_of(name, a, nrep, total_ms, pk, clocks, traffic, workload="train"):
     cnt, kms, fl, by = a
-    tkey = {"conv3d_wgrad_march": "wgrad/conv3d_wgrad_march_kernel", "conv3d_march_fprop": "fprop/conv3d_march2_kernel",
-            "conv3d_march_dgrad": "dgrad/conv3d_march2_kernel", "reassemble": "infer/reassemble4_kernel",
-            "gather_patches": "infer/gather_patches4_kernel"}.get(name)
+    tkey = TRAFFIC_KEYS.get(workload, {}).get(name)
     tr = traffic.get(tkey) if tkey else None
     if fl > 0:
         ach = fl / kms / 1e9        # TFLOP/s: algorithmic flops per launch / avg launch duration
@@ -387,6 +400,8 @@ def bench_train(e, args, patch, fwd_gf, first_gf, steps, warmup, with_profile):
             for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
         top = max(agg.items(), key=lambda kv: kv[1][1])
         rec["roofline"] = roofline_of(top[0], top[1], nprof, total_ms, pk, clocks, traffic)
+        rec["rooflines"] = {k: roofline_of(k, agg[k], nprof, total_ms, pk, clocks, traffic)
+                            for k in TRAFFIC_KEYS["train"] if k in agg}
     rec["_model"], rec["_dp"] = model, dp
     return rec
 
@@ -503,9 +518,10 @@ def bench_infer(e, args, steps, warmup):
                          ((a[3] / a[1] / 1e6) / pk["hbm"] if a[3] > 0 else None))
                  for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])}
     roofs = {}
-    for name in ("conv3d_march_fprop", "conv3d_tc_fprop", "reassemble", "gather_patches"):
+    for name in ("conv3d_march_fprop", "conv3d_tc_fprop", "reassemble", "gather_patches", "maxpool3d_fwd",
+                 "upsample3d_fwd", "head_fwd"):
         if name in agg:
-            roofs[name] = roofline_of(name, agg[name], 1, dev_ms, pk, clocks, traffic)
+            roofs[name] = roofline_of(name, agg[name], 1, dev_ms, pk, clocks, traffic, "infer")
     return dict(metric="U-Net infer voxels/sec", value=nvox / (dev_ms * 1e-3), unit=UNIT, ms_per_step=dev_ms,
                 value_is="output voxels / summed kernel time of one call (volume resident in HBM)",
                 config=dict(workload="patch_wise_prediction 1x256x256x64, patch 64^3, overlap_factor 0.5, 49 patches "
@@ -612,7 +628,7 @@ def bench_family(e, kind, steps):
                          h2d_bytes_per_step=int(x.nbytes + t.nbytes), d2h_bytes_per_step=64),
                 predict=dict(value=units / s_pred, ms_per_call=s_pred * 1e3, conv_tflops=B * fwd_gf / (s_pred * 1e3),
                              note="Model.predict with host buffers (H2D + forward + D2H)"),
-                roofline=roofline_of(top[0], top[1], 2, total_ms, pk, clocks, {}), kernel_breakdown=breakdown,
+                roofline=roofline_of(top[0], top[1], 2, total_ms, pk, clocks, {}, kind), kernel_breakdown=breakdown,
                 loss=float(m4[0]))
 
 
@@ -650,7 +666,7 @@ def run_b200(args):
                         scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                         config=workload_config(e.world), clocks=rec["clocks"], e2e=rec["e2e"],
                         e2e_pageable=rec["e2e_pageable"], gpu_launches=rec["gpu_launches"],
-                        roofline=rec.get("roofline"), cpu_baseline=cpu_base,
+                        roofline=rec.get("roofline"), rooflines=rec.get("rooflines"), cpu_baseline=cpu_base,
                         conv_tflops_whole_step=rec["conv_tflops_whole_step"],
                         kernel_breakdown=rec.get("kernel_breakdown"), loss=rec["loss"],
                         collective=("libfetalb200 NCCL communicator (fm_train_step_dp), NCCL %s" %
