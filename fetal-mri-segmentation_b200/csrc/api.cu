@@ -250,6 +250,9 @@ struct fm_model {
   DevBuf<bf16> gIsRaw, gIsZero;
   float dropout_rate = 0.f;
   uint64_t dropout_seed = 0x5EEDull;
+  // 2D U-Net: SpatialDropout2D keep/scale factors [B][C] after enc<d>a (slot d) and dec<d>a (slot depth + d)
+  std::vector<DevBuf<float>> dropU;
+  bool unet_dropout() const { return kind == 0 && kcode == 31 && dropout_rate > 0.f; }
   int kcode = 3;  // 3: Conv3D 3x3x3 (unet_model_3d); 31: Conv2D 3x3 on a Z = 1 volume (unet_model_2d)
   int pz = 2;     // pooling factor along z
   int cin_real = 1;
@@ -547,7 +550,7 @@ extern "C" int fm_model_destroy(fm_model* m) {
   for (auto& b : m->isSeg) b.release();
   for (auto* v : {&m->isRawL, &m->gIsA, &m->gIsB, &m->gIsC, &m->gIsUp})
     for (auto& b : *v) b.release();
-  for (auto* v : {&m->isStatsL, &m->isDropL, &m->gSeg})
+  for (auto* v : {&m->isStatsL, &m->isDropL, &m->gSeg, &m->dropU})
     for (auto& b : *v) b.release();
   m->gIsRaw.release();
   m->gIsZero.release();
@@ -860,6 +863,18 @@ static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2,
 
 static int forward_isensee(fm_model* m, int B);
 
+// SpatialDropout2D(rate) behind the first conv block of every level of the 2D U-Net (unet/unet.py:60-61,76-77):
+// one keep/scale factor per (sample, channel), drawn per step from the counter-based hash, applied in place. The
+// stored activation is the dropped one, so the next conv's weight gradient and the ReLU mask of the gradient
+// (kept channels are scaled by a positive factor) need no change; the gradient itself is scaled on the way back.
+static int unet_dropout_fwd(fm_model* m, int slot, bf16* act, const Layer& l, int B) {
+  if ((int)m->dropU.size() <= slot) m->dropU.resize(slot + 1);
+  FM_TRY(m->dropU[slot].ensure((size_t)B * l.cout));
+  FM_TRY(k_dropout_scale(m->ctx, m->dropU[slot].p, B * l.cout, m->dropout_rate,
+                         m->dropout_seed + (uint64_t)m->iterations * 64 + (uint64_t)slot));
+  return k_channel_scale(m->ctx, act, m->dropU[slot].p, B, m->vox(l.level), l.cout);
+}
+
 // forward pass on x_in (fp32 [B, X, Y, Z], C = 1) -> prob (fp32 [B, X, Y, Z])
 static int forward(fm_model* m, int B) {
   if (m->kind == 1) return forward_isensee(m, B);
@@ -879,6 +894,7 @@ static int forward(fm_model* m, int B) {
     } else {
       FM_TRY(conv_fwd(m, la, cur, nullptr, m->encA[d].p, B));
     }
+    if (m->train_pass && m->unet_dropout()) FM_TRY(unet_dropout_fwd(m, d, m->encA[d].p, la, B));
     FM_TRY(conv_fwd(m, lb, m->encA[d].p, nullptr, m->encB[d].p, B));
     cur = m->encB[d].p;
     if (d < D - 1) {
@@ -897,6 +913,7 @@ static int forward(fm_model* m, int B) {
       FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B), m->pz));
       FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
     }
+    if (m->train_pass && m->unet_dropout()) FM_TRY(unet_dropout_fwd(m, D + d, m->decA[d].p, da, B));
     FM_TRY(conv_fwd(m, db, m->decA[d].p, nullptr, m->decB[d].p, B));
     cur = m->decB[d].p;
   }
@@ -996,6 +1013,7 @@ static int backward(fm_model* m, int B) {
     FM_TRY(conv_wgrad(m, db, m->decA[d].p, nullptr, m->gDecB[d].p, B));
     FM_TRY(mark_layer_done(m, db));
     FM_TRY(conv_dgrad(m, db, 0, m->gDecB[d].p, m->decA[d].p, m->gDecA[d].p, B));
+    if (m->unet_dropout()) FM_TRY(k_channel_scale(ctx, m->gDecA[d].p, m->dropU[D + d].p, B, m->vox(d), da.cout));
     // dec_a: inputs [up[d], encB[d]]; the coarser tensor that was upsampled and its ReLU mask
     const bool bottom = (d + 1 == D - 1);
     const bf16* act = bottom ? m->encB[D - 1].p : m->decB[d + 1].p;
@@ -1037,6 +1055,7 @@ static int backward(fm_model* m, int B) {
     FM_TRY(conv_wgrad(m, lb, m->encA[d].p, nullptr, m->gEncB[d].p, B));
     FM_TRY(mark_layer_done(m, lb));
     FM_TRY(conv_dgrad(m, lb, 0, m->gEncB[d].p, m->encA[d].p, m->gEncA[d].p, B));
+    if (m->unet_dropout()) FM_TRY(k_channel_scale(ctx, m->gEncA[d].p, m->dropU[d].p, B, m->vox(d), la.cout));
     if (d > 0) {
       FM_TRY(conv_wgrad(m, la, m->pool[d - 1].p, nullptr, m->gEncA[d].p, B));
       FM_TRY(mark_layer_done(m, la));
@@ -1080,22 +1099,49 @@ static int upload(fm_model* m, const float* src, float* dst, size_t count) {
 // localisation module (3^3 block, 1^3 block) -> Conv3D(n_labels, 1) heads summed coarse-to-fine; sigmoid.
 // Layer table in Keras creation order, every conv followed by its norm pseudo-layer (gamma, beta).
 // ---------------------------------------------------------------------------------------------
+struct IsenseeBuild {
+  int X, Y, Z, in_channels, depth, n_base_filters, n_segmentation_levels, kcode;
+};
+static int build_isensee(fm_ctx* ctx, const IsenseeBuild* spec, fm_model** out);
+
 extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* spec, fm_model** out) {
   FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_isensee3d: NULL argument");
   FM_CHECK(spec->in_channels == 1 && spec->n_labels == 1, FM_EINVAL, "isensee: in_channels and n_labels must be 1");
+  IsenseeBuild b{spec->X, spec->Y, spec->Z, 1, spec->depth, spec->n_base_filters, spec->n_segmentation_levels, 3};
+  return build_isensee(ctx, &b, out);
+}
+
+// isensee2017_model (fetal_net/model/unet/isensee.py:14-86): the same graph in 2D on slices-as-channels input -
+// Conv2D 3x3 / 1x1 blocks, strides (2, 2), UpSampling2D, SpatialDropout2D - run on a Z = 1 volume with kernel-extent
+// code 31 and no pooling along z, like the 2D U-Net. The input's `in_channels` slices are zero-padded to 16 channels.
+extern "C" int fm_model_create_isensee2d(fm_ctx* ctx, const fm_isensee2d_spec* spec, fm_model** out) {
+  FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_isensee2d: NULL argument");
+  FM_CHECK(spec->n_labels == 1, FM_EINVAL, "isensee2d: n_labels must be 1");
+  FM_CHECK(spec->in_channels >= 1 && spec->in_channels <= 16, FM_EINVAL, "isensee2d: in_channels %d outside [1,16]",
+           spec->in_channels);
+  IsenseeBuild b{spec->H, spec->W, 1, spec->in_channels, spec->depth, spec->n_base_filters,
+                 spec->n_segmentation_levels, 31};
+  return build_isensee(ctx, &b, out);
+}
+
+static int build_isensee(fm_ctx* ctx, const IsenseeBuild* spec, fm_model** out) {
+  const int kcode = spec->kcode, pz = kcode == 31 ? 1 : 2;
   FM_CHECK(spec->depth >= 2 && spec->depth <= 6, FM_EINVAL, "isensee: depth %d unsupported", spec->depth);
   FM_CHECK(spec->n_base_filters == 16 || spec->n_base_filters == 32, FM_EINVAL, "isensee: n_base_filters 16 or 32");
   FM_CHECK(spec->n_segmentation_levels >= 1 && spec->n_segmentation_levels <= spec->depth - 1, FM_EINVAL,
            "isensee: n_segmentation_levels %d out of range", spec->n_segmentation_levels);
   const int div = 1 << (spec->depth - 1);
-  FM_CHECK(spec->X % div == 0 && spec->Y % div == 0 && spec->Z % div == 0 && spec->X > 0, FM_EINVAL,
+  FM_CHECK(spec->X % div == 0 && spec->Y % div == 0 && (pz == 1 || spec->Z % div == 0) && spec->X > 0, FM_EINVAL,
            "isensee: input extent %dx%dx%d must be divisible by 2^(depth-1)=%d", spec->X, spec->Y, spec->Z, div);
   FM_CUDA(cudaSetDevice(ctx->device));
   fm_model* m = new fm_model();
   m->ctx = ctx;
   m->kind = 1;
+  m->kcode = kcode;
+  m->pz = pz;
+  m->cin_real = spec->in_channels;
   m->nseg = spec->n_segmentation_levels;
-  m->spec.in_channels = 1;
+  m->spec.in_channels = spec->in_channels;
   m->spec.X = spec->X;
   m->spec.Y = spec->Y;
   m->spec.Z = spec->Z;
@@ -1135,18 +1181,20 @@ extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* s
       m->layers.push_back(g);
     }
   };
-  int c = 1;
+  // 2D: the first conv reads a 16-channel zero-padded bf16 copy of the input (tensor-core K granule)
+  int c = kcode == 31 ? 16 : 1;
   for (int l = 0; l < D; ++l) {
     const int f = nf << l;
-    add_conv("l%d_in", l, c, 0, f, 3, l, l == 0 ? 1 : 2, true);
-    add_conv("l%d_ctx1", l, f, 0, f, 3, l, 1, true);
-    add_conv("l%d_ctx2", l, f, 0, f, 3, l, 1, true);
+    add_conv("l%d_in", l, c, 0, f, kcode, l, l == 0 ? 1 : 2, true);
+    if (l == 0 && kcode == 31) m->layers[m->layers.size() - 2].cin_real = spec->in_channels;
+    add_conv("l%d_ctx1", l, f, 0, f, kcode, l, 1, true);
+    add_conv("l%d_ctx2", l, f, 0, f, kcode, l, 1, true);
     c = f;
   }
   for (int l = D - 2; l >= 0; --l) {
     const int f = nf << l;
-    add_conv("u%d_up", l, c, 0, f, 3, l, 1, true);
-    add_conv("u%d_loc1", l, f, f, f, 3, l, 1, true);  // concat order [skip, up] (isensee2017.py:62)
+    add_conv("u%d_up", l, c, 0, f, kcode, l, 1, true);
+    add_conv("u%d_loc1", l, f, f, f, kcode, l, 1, true);  // concat order [skip, up] (isensee2017.py:62)
     add_conv("u%d_loc2", l, f, 0, f, 1, l, 1, true);
     c = f;
     if (l < m->nseg) add_conv("u%d_seg", l, f, 0, 1, 1, l, 1, false);
@@ -1175,7 +1223,7 @@ extern "C" int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* s
       l.w_d1 = wp + (int64_t)l.c1 * l.taps() * l.cout;
     }
     wp += padded;
-    if (l.k != 3 || l.c1 < 16) continue;
+    if (l.k != 3 || l.c1 < 16) continue;  // (the 2D family, k = 31, runs on the per-tap kernels)
     // the backward of a stride-2 conv runs as a stride-1 dgrad over the zero-inserted gradient, one level finer
     const int dl = l.stride == 2 ? l.level - 1 : l.level;
     const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
@@ -1257,7 +1305,8 @@ static int ensure_capacity_isensee(fm_model* m, int B, bool train) {
     }
     m->train_alloc = true;
   }
-  FM_TRY(m->x_in.ensure((size_t)B * v0));
+  FM_TRY(m->x_in.ensure((size_t)B * v0 * m->cin_real));
+  if (m->kcode == 31) FM_TRY(m->x_pad.ensure((size_t)B * v0 * 16));
   FM_TRY(m->prob.ensure((size_t)B * v0));
   FM_TRY(m->isAcc.ensure((size_t)B * v0));
   FM_TRY(m->isRaw.ensure((size_t)B * v0 * nf));
@@ -1298,7 +1347,7 @@ static int isensee_block(fm_model* m, const Layer& l, const Layer& nl, const bf1
         ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, 0, l.cout, 0));
   } else if (conv_tc_supported(l.c1, l.c2, l.cout, l.k)) {
     FM_TRY(k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, l.k, 0,
-                             l.cout, 0, l.stride, d.X * l.stride, d.Y * l.stride, d.Z * l.stride));
+                             l.cout, 0, l.stride, d.X * l.stride, d.Y * l.stride, m->pz == 2 ? d.Z * l.stride : d.Z));
   } else {
     FM_CHECK(l.stride == 1, FM_EINVAL, "isensee: strided conv %s has no fallback", l.name);
     FM_TRY(k_conv3d_simt_fprop(ctx, x1, 0, x2, l.w_f, bias, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, l.k, 0,
@@ -1321,8 +1370,14 @@ static int forward_isensee(fm_model* m, int B) {
   for (int l = 0; l < D; ++l) {
     const int i_in = LI("l%d_in", l), i_c1 = LI("l%d_ctx1", l), i_c2 = LI("l%d_ctx2", l);
     const Layer &lin = m->layers[i_in], &lc1 = m->layers[i_c1], &lc2 = m->layers[i_c2];
-    FM_TRY(isensee_block(m, lin, m->layers[i_in + 1], l == 0 ? (const bf16*)m->x_in.p : cur, nullptr, nullptr,
-                         m->isIn[l].p, B));
+    const bf16* src = cur;
+    if (l == 0 && m->kcode == 31) {
+      FM_TRY(k_pad_cast(ctx, m->x_in.p, m->x_pad.p, (int64_t)B * m->vox(0), m->cin_real, 16));
+      src = m->x_pad.p;
+    } else if (l == 0) {
+      src = (const bf16*)m->x_in.p;  // fp32 single-channel input, read by the Cin = 1 kernel
+    }
+    FM_TRY(isensee_block(m, lin, m->layers[i_in + 1], src, nullptr, nullptr, m->isIn[l].p, B));
     // SpatialDropout3D between the two context convs (isensee2017.py:103-105): training passes only
     const float* drop = nullptr;
     if (m->train_pass && m->dropout_rate > 0.f) {
@@ -1338,7 +1393,7 @@ static int forward_isensee(fm_model* m, int B) {
   for (int l = D - 2; l >= 0; --l) {
     const int i_up = LI("u%d_up", l), i_l1 = LI("u%d_loc1", l), i_l2 = LI("u%d_loc2", l);
     const Layer& lup = m->layers[i_up];
-    FM_TRY(k_upsample3d_fwd(ctx, cur, m->isUp[l].p, m->dims(l + 1, lup.c1, B), 2));
+    FM_TRY(k_upsample3d_fwd(ctx, cur, m->isUp[l].p, m->dims(l + 1, lup.c1, B), m->pz));
     FM_TRY(isensee_block(m, lup, m->layers[i_up + 1], m->isUp[l].p, nullptr, nullptr, m->isU[l].p, B));
     FM_TRY(isensee_block(m, m->layers[i_l1], m->layers[i_l1 + 1], m->isSum[l].p, m->isU[l].p, nullptr, m->isLoc1[l].p, B));
     FM_TRY(isensee_block(m, m->layers[i_l2], m->layers[i_l2 + 1], m->isLoc1[l].p, nullptr, nullptr, m->isLoc2[l].p, B));
@@ -1354,7 +1409,7 @@ static int forward_isensee(fm_model* m, int B) {
   for (int l = m->nseg - 2; l >= 0; --l) {
     const Dims5 d = m->dims(l, 1, B);
     float* dst = (l == 0) ? m->isAcc.p : m->isSeg[l].p;  // in place on the finer map is safe (element-wise)
-    FM_TRY(k_seg_upsample_add(ctx, m->isSeg[l].p, acc, dst, B, d.X, d.Y, d.Z));
+    FM_TRY(k_seg_upsample_add(ctx, m->isSeg[l].p, acc, dst, B, d.X, d.Y, d.Z, m->pz));
     acc = dst;
   }
   FM_TRY(k_sigmoid(ctx, acc, m->prob.p, (int64_t)B * m->vox(0)));
@@ -1412,7 +1467,10 @@ static int is_block_bwd(fm_model* m, int li, const bf16* gy, const bf16* gy2, co
                               gy2, chan_scale, m->gIsRaw.p, m->grads + nl.w_off, m->grads + nl.b_off, B, m->vox(l.level),
                               l.cout, m->isScratch.p, m->isScratch.n));
   FM_TRY(mark_layer_done(m, nl));
-  return k_bias_grad(m->ctx, m->gIsRaw.p, m->grads + l.b_off, (int64_t)B * m->vox(l.level), l.cout);
+  // no bias-gradient pass: the conv bias sits in front of an InstanceNormalization, which removes any per-channel
+  // constant - its gradient is exactly zero (the buffer was zeroed at the start of the backward pass); summing gIsRaw
+  // over the voxels would only return the rounding noise of a sum that vanishes analytically
+  return FM_OK;
 }
 
 static int backward_isensee(fm_model* m, int B) {
@@ -1431,7 +1489,7 @@ static int backward_isensee(fm_model* m, int B) {
   gseg[0] = m->dz.p;
   for (int l = 1; l < m->nseg; ++l) {
     const Dims5 d = m->dims(l, 1, B);
-    FM_TRY(k_sumpool_f32(ctx, gseg[l - 1], m->gSeg[l].p, B, d.X, d.Y, d.Z));
+    FM_TRY(k_sumpool_f32(ctx, gseg[l - 1], m->gSeg[l].p, B, d.X, d.Y, d.Z, m->pz));
     gseg[l] = m->gSeg[l].p;
   }
   for (int l = 0; l <= D - 2; ++l) {
@@ -1458,7 +1516,7 @@ static int backward_isensee(fm_model* m, int B) {
     FM_TRY(mark_layer_done(m, lup));
     FM_TRY(is_dgrad(m, lup, l, 0, m->gIsRaw.p, m->gIsUp[l].p, B));
     bf16* gdst = (l + 1 == D - 1) ? m->gIsC[D - 1].p : m->gIsA[l + 1].p;
-    FM_TRY(k_upsample3d_bwd(ctx, m->gIsUp[l].p, nullptr, gdst, m->dims(l + 1, lup.c1, B), lup.c1, 0, 2));
+    FM_TRY(k_upsample3d_bwd(ctx, m->gIsUp[l].p, nullptr, gdst, m->dims(l + 1, lup.c1, B), lup.c1, 0, m->pz));
   }
   for (int l = D - 1; l >= 0; --l) {
     const int i_in = LI("l%d_in", l), i_c1 = LI("l%d_ctx1", l), i_c2 = LI("l%d_ctx2", l);
@@ -1475,13 +1533,16 @@ static int backward_isensee(fm_model* m, int B) {
     FM_TRY(is_dgrad(m, lc1, l, 0, m->gIsRaw.p, m->gIsB[l].p, B));
     // in_conv output feeds ctx1 and the residual add
     FM_TRY(is_block_bwd(m, i_in, m->gIsB[l].p, gsum, nullptr, B));
-    if (l == 0) {
+    if (l == 0 && m->kcode == 31) {
+      FM_TRY(is_wgrad(m, lin, 0, m->x_pad.p, nullptr, m->gIsRaw.p, B));  // the zero-padded 16-channel input copy
+      FM_TRY(mark_layer_done(m, lin));
+    } else if (l == 0) {
       const Dims5 dd = m->dims(0, lin.cout, B);
       FM_TRY(k_conv3d_simt_wgrad(ctx, m->x_in.p, 1, m->gIsRaw.p, m->grads + lin.w_off, B, dd.X, dd.Y, dd.Z, 1, 1, 0,
                                  lin.cout, 3));
       FM_TRY(mark_layer_done(m, lin));
     } else {
-      FM_TRY(k_zero_insert(ctx, m->gIsRaw.p, m->gIsZero.p, m->dims(l, lin.cout, B)));
+      FM_TRY(k_zero_insert(ctx, m->gIsRaw.p, m->gIsZero.p, m->dims(l, lin.cout, B), m->pz));
       FM_TRY(is_wgrad(m, lin, l - 1, m->isSum[l - 1].p, nullptr, m->gIsZero.p, B));
       FM_TRY(mark_layer_done(m, lin));
       FM_TRY(is_dgrad(m, lin, l - 1, 0, m->gIsZero.p, m->gIsA[l - 1].p, B));

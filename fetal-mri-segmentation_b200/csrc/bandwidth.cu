@@ -565,23 +565,24 @@ __global__ void __launch_bounds__(kThreads) instnorm_bwd_apply_kernel(NormBwdArg
 
 // transposed-conv helper for the stride-2 in-convs: fine[2v + 1] = coarse[v] per axis, zero elsewhere. A stride-1
 // 'same' dgrad / wgrad over this tensor equals the stride-2 (TF SAME, pad_before = 0) conv's dgrad / wgrad.
+// (pz = 1: the 2D family - z is not strided.)
 __global__ void zero_insert_kernel(const bf16* __restrict__ coarse, bf16* __restrict__ fine, int N, int X, int Y, int Z,
-                                   int C) {
+                                   int C, int pz) {
   const int c8n = C >> 3;
-  const int64_t total = (int64_t)N * X * Y * Z * 8 * c8n;  // fine voxels x 16-byte groups
+  const int64_t total = (int64_t)N * X * Y * Z * 4 * pz * c8n;  // fine voxels x 16-byte groups
   const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= total) return;
   const int c8 = (int)(gi % c8n);
   int64_t v = gi / c8n;
-  const int z = (int)(v % (2 * Z));
-  int64_t r = v / (2 * Z);
+  const int z = (int)(v % (pz * Z));
+  int64_t r = v / (pz * Z);
   const int y = (int)(r % (2 * Y));
   r /= 2 * Y;
   const int x = (int)(r % (2 * X));
   const int n = (int)(r / (2 * X));
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if ((x & y & z & 1) != 0) {
-    const int64_t vc = (((int64_t)n * X + (x >> 1)) * Y + (y >> 1)) * Z + (z >> 1);
+  if ((x & y & (pz == 2 ? z : 1) & 1) != 0) {
+    const int64_t vc = (((int64_t)n * X + (x >> 1)) * Y + (y >> 1)) * Z + (pz == 2 ? (z >> 1) : z);
     o = ldg16(coarse + vc * C + c8 * 8);
   }
   stg16(fine + v * C + c8 * 8, o);
@@ -601,7 +602,7 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
 
 // gradient of the nearest-neighbour upsampling of a single-channel fp32 map: 2^3 sum-pool
 __global__ void sumpool_f32_kernel(const float* __restrict__ fine, float* __restrict__ coarse, int N, int X, int Y,
-                                   int Z) {  // coarse extents
+                                   int Z, int pz) {  // coarse extents; pz = 1: 2x2 sum-pool in x, y only
   const int64_t total = (int64_t)N * X * Y * Z;
   const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= total) return;
@@ -614,9 +615,13 @@ __global__ void sumpool_f32_kernel(const float* __restrict__ fine, float* __rest
   float acc = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t vf = (((int64_t)n * 2 * X + 2 * x + (k >> 1)) * 2 * Y + 2 * y + (k & 1)) * 2 * Z + 2 * z;
-    const float2 t = __ldg(reinterpret_cast<const float2*>(fine + vf));
-    acc += t.x + t.y;
+    const int64_t vf = (((int64_t)n * 2 * X + 2 * x + (k >> 1)) * 2 * Y + 2 * y + (k & 1)) * pz * Z + pz * z;
+    if (pz == 2) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(fine + vf));
+      acc += t.x + t.y;
+    } else {
+      acc += __ldg(fine + vf);
+    }
   }
   coarse[gi] = acc;
 }
@@ -636,7 +641,7 @@ __global__ void dropout_scale_kernel(float* __restrict__ scale, int n, float rat
 // segmentation-head plumbing of the Isensee net (isensee2017.py:68-79): fp32 single-channel maps
 // out[v] = fine[v] + coarse[v >> 1 per axis]   /   p = sigmoid(z)
 __global__ void seg_upsample_add_kernel(const float* __restrict__ fine, const float* __restrict__ coarse,
-                                        float* __restrict__ out, int N, int X, int Y, int Z) {
+                                        float* __restrict__ out, int N, int X, int Y, int Z, int pz) {
   const int64_t total = (int64_t)N * X * Y * Z;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= total) return;
@@ -646,7 +651,8 @@ __global__ void seg_upsample_add_kernel(const float* __restrict__ fine, const fl
   r /= Y;
   const int x = (int)(r % X);
   const int n = (int)(r / X);
-  const int64_t vc = (((int64_t)n * (X >> 1) + (x >> 1)) * (Y >> 1) + (y >> 1)) * (Z >> 1) + (z >> 1);
+  const int zc = pz == 2 ? (z >> 1) : z, Zc = pz == 2 ? (Z >> 1) : Z;
+  const int64_t vc = (((int64_t)n * (X >> 1) + (x >> 1)) * (Y >> 1) + (y >> 1)) * Zc + zc;
   out[g] = fine[g] + __ldg(coarse + vc);
 }
 __global__ void sigmoid_kernel(const float* __restrict__ z, float* __restrict__ p, int64_t n) {
@@ -1371,10 +1377,11 @@ int k_instnorm_lrelu_bwd(fm_ctx* ctx, const bf16* x, const float* stats, const f
   return FM_OK;
 }
 
-int k_zero_insert(fm_ctx* ctx, const bf16* coarse, bf16* fine, Dims5 c) {
+int k_zero_insert(fm_ctx* ctx, const bf16* coarse, bf16* fine, Dims5 c, int pz) {
   FM_CHECK(c.C % 8 == 0, FM_EINVAL, "zero_insert: C=%d", c.C);
-  ProfScope prof(ctx, "zero_insert", 0.0, (double)c.elems() * 2.0 * 9.0);
-  zero_insert_kernel<<<grid_for(c.elems()), kThreads, 0, ctx->stream>>>(coarse, fine, c.N, c.X, c.Y, c.Z, c.C);
+  ProfScope prof(ctx, "zero_insert", 0.0, (double)c.elems() * 2.0 * (1.0 + 4.0 * pz));
+  zero_insert_kernel<<<grid_for(c.elems() / 8 * 4 * pz), kThreads, 0, ctx->stream>>>(coarse, fine, c.N, c.X, c.Y, c.Z,
+                                                                                     c.C, pz);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -1387,9 +1394,35 @@ int k_add_bf16(fm_ctx* ctx, const bf16* a, const bf16* b, bf16* out, int64_t n) 
   return FM_OK;
 }
 
-int k_sumpool_f32(fm_ctx* ctx, const float* fine, float* coarse, int N, int X, int Y, int Z) {
-  ProfScope prof(ctx, "sumpool_f32", 0.0, (double)N * X * Y * Z * 36.0);
-  sumpool_f32_kernel<<<grid_for((int64_t)N * X * Y * Z), kThreads, 0, ctx->stream>>>(fine, coarse, N, X, Y, Z);
+int k_sumpool_f32(fm_ctx* ctx, const float* fine, float* coarse, int N, int X, int Y, int Z, int pz) {
+  ProfScope prof(ctx, "sumpool_f32", 0.0, (double)N * X * Y * Z * (4.0 + 16.0 * pz));
+  sumpool_f32_kernel<<<grid_for((int64_t)N * X * Y * Z), kThreads, 0, ctx->stream>>>(fine, coarse, N, X, Y, Z, pz);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// SpatialDropout2D of the 2D U-Net (unet/unet.py:60-61,76-77): x[n][v][c] *= scale[n][c], in place; the same kernel
+// scales the gradient on the way back
+__global__ void channel_scale_kernel(bf16* __restrict__ x, const float* __restrict__ scale, int64_t vox_per_sample,
+                                     int C, int64_t total8) {
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= total8) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(gi % c8n);
+  const int64_t n = gi / c8n / vox_per_sample;
+  float f[8];
+  unpack8(ldg16(x + gi * 8), f);
+  const float* sc = scale + n * C + c8 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] *= __ldg(sc + i);
+  stg16(x + gi * 8, pack8(f));
+}
+
+int k_channel_scale(fm_ctx* ctx, bf16* x, const float* scale, int N, int64_t vox_per_sample, int C) {
+  FM_CHECK(C % 8 == 0, FM_EINVAL, "channel_scale: C=%d must be a multiple of 8", C);
+  const int64_t total8 = (int64_t)N * vox_per_sample * (C / 8);
+  ProfScope prof(ctx, "channel_scale", 0.0, (double)total8 * 32.0);
+  channel_scale_kernel<<<grid_for(total8), kThreads, 0, ctx->stream>>>(x, scale, vox_per_sample, C, total8);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
@@ -1425,9 +1458,10 @@ int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float
   return FM_OK;
 }
 
-int k_seg_upsample_add(fm_ctx* ctx, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z) {
+int k_seg_upsample_add(fm_ctx* ctx, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z,
+                       int pz) {
   const int64_t total = (int64_t)N * X * Y * Z;
-  seg_upsample_add_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(fine, coarse, out, N, X, Y, Z);
+  seg_upsample_add_kernel<<<grid_for(total), kThreads, 0, ctx->stream>>>(fine, coarse, out, N, X, Y, Z, pz);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

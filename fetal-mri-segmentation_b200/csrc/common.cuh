@@ -221,11 +221,14 @@ int k_instnorm_lrelu(fm_ctx*, const bf16* x, const float* gamma, const float* be
 int k_instnorm_lrelu_bwd(fm_ctx*, const bf16* x, const float* stats, const float* gamma, const float* beta,
                          const bf16* gy, const bf16* gy2, const float* chan_scale, bf16* dx, float* dgamma,
                          float* dbeta, int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats);
-int k_zero_insert(fm_ctx*, const bf16* coarse, bf16* fine, Dims5 coarse_dims);
+int k_zero_insert(fm_ctx*, const bf16* coarse, bf16* fine, Dims5 coarse_dims, int pz = 2);
 int k_add_bf16(fm_ctx*, const bf16* a, const bf16* b, bf16* out, int64_t n);
-int k_sumpool_f32(fm_ctx*, const float* fine, float* coarse, int N, int X, int Y, int Z);
+int k_sumpool_f32(fm_ctx*, const float* fine, float* coarse, int N, int X, int Y, int Z, int pz = 2);
 int k_dropout_scale(fm_ctx*, float* scale, int n, float rate, uint64_t seed);
-int k_seg_upsample_add(fm_ctx*, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z);
+// x[n][v][c] *= scale[n][c] in place (SpatialDropout2D of the 2D U-Net, forward and backward)
+int k_channel_scale(fm_ctx*, bf16* x, const float* scale, int N, int64_t vox_per_sample, int C);
+int k_seg_upsample_add(fm_ctx*, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z,
+                       int pz = 2);
 int k_sigmoid(fm_ctx*, const float* z, float* p, int64_t n);
 // out[(patch voxel (i,j)) * out_pitch + out_cofs + k]: with out_pitch = patch[2], out_cofs = 0 this is the plain
 // [n,P0,P1,P2] gather; the 2.5D path writes the slices and the previous-truth slices as channels of one row

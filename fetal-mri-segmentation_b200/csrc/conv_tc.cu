@@ -46,6 +46,7 @@ struct alignas(64) FpropParams {
   int relu;
   int stages;
   int stride;         // 1, or 2 = strided conv with TF 'SAME' padding (Isensee in-convs, isensee2017.py:51)
+  int stride_z;       // = stride, or 1 for the 3x3x1 kernels of the 2D family (strides=(2, 2), unet/isensee.py:49)
   int pbx, pby, pbz;  // 'before' padding per axis (k/2 for stride 1; TF SAME for stride 2)
   // Decoder convolutions over concatenate([UpSampling3D(2)(coarse), skip]) WITHOUT the upsampled tensor
   // (unet3d/unet.py:59-62,138): a fine voxel 2c+p of parity class p only ever sees the 2x2x2 coarse neighbourhood
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv3d_tc_fprop_kernel(
       const int ix = m % p.tx;
       const int n = m / p.tx;
       const int x0 = ix * p.bx * p.stride - p.pbx, y0 = iy * p.by * p.stride - p.pby,
-                z0 = iz * p.bz * p.stride - p.pbz;
+                z0 = iz * p.bz * p.stride_z - p.pbz;
       const int px = cls >> 2, py = (cls >> 1) & 1, pz = cls & 1;
       for (int s = 0; s < p.nsrc; ++s) {
         const uint32_t tx_bytes = (uint32_t)(kTileM + p.block_n) * (uint32_t)p.KC[s] * 2u;
@@ -572,16 +573,16 @@ CUtensorMapSwizzle swizzle_for(int row_bytes) {
 
 // 5-D map over a channels-last activation tensor [N][X][Y][Z][C] (bf16), box (cbox, bz, by, bx, 1)
 int make_act_tmap(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int cbox,
-                  int bz, int by, int bx, int stride = 1) {
+                  int bz, int by, int bx, int stride = 1, int stride_z = 0) {
   PFN_encodeTiled enc = get_encode();
   FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2,
                            (cuuint64_t)X * Y * Z * C * 2};
   // with a traversal stride the box is given in tensor elements and every stride-th element is loaded
-  const cuuint32_t st = (cuuint32_t)stride;
-  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bz * st, (cuuint32_t)by * st, (cuuint32_t)bx * st, 1};
-  cuuint32_t estr[5] = {1, st, st, st, 1};
+  const cuuint32_t st = (cuuint32_t)stride, stz = (cuuint32_t)(stride_z > 0 ? stride_z : stride);
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bz * stz, (cuuint32_t)by * st, (cuuint32_t)bx * st, 1};
+  cuuint32_t estr[5] = {1, stz, st, st, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cbox * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -642,7 +643,9 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
                       const float* bias, bf16* y, const bf16* mask, int N, int X, int Y, int Z, int C1,
                       int C2, int Cout, int ksize, int relu, int out_C, int out_cofs, int stride, int Xin,
                       int Yin, int Zin) {
-  FM_CHECK(stride == 1 || (stride == 2 && ksize == 3 && C2 == 0), FM_EINVAL, "conv3d tc: stride %d unsupported", stride);
+  FM_CHECK(stride == 1 || (stride == 2 && kext_xy(ksize) == 3 && C2 == 0), FM_EINVAL,
+           "conv3d tc: stride %d unsupported", stride);
+  const int stride_z = kext_z(ksize) == 1 ? 1 : stride;
   if (stride == 1) {
     Xin = X;
     Yin = Y;
@@ -674,6 +677,7 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   p.out = y;
   p.mask = mask;
   p.stride = stride;
+  p.stride_z = stride_z;
   p.upmode = 0;
   p.ntaps_s[0] = p.ntaps_s[1] = p.ntaps;
   p.oX = X;
@@ -681,10 +685,10 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   p.oZ = Z;
   {
     // TF 'SAME': pad_total = max((out-1)*stride + k - in, 0), pad_before = pad_total / 2
-    auto pb = [&](int out, int in, int k) { return std::max((out - 1) * stride + k - in, 0) / 2; };
-    p.pbx = pb(X, Xin, kext_xy(ksize));
-    p.pby = pb(Y, Yin, kext_xy(ksize));
-    p.pbz = pb(Z, Zin, kext_z(ksize));
+    auto pb = [&](int out, int in, int k, int st) { return std::max((out - 1) * st + k - in, 0) / 2; };
+    p.pbx = pb(X, Xin, kext_xy(ksize), stride);
+    p.pby = pb(Y, Yin, kext_xy(ksize), stride);
+    p.pbz = pb(Z, Zin, kext_z(ksize), stride_z);
   }
   const int Ct = C1 + C2;
   const int Cs[2] = {C1, C2};
@@ -694,7 +698,7 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
     p.KC[s] = chunk_of(Cs[s]);
     p.nchunks[s] = Cs[s] / p.KC[s];
     p.wcofs[s] = cofs;
-    FM_TRY(make_act_tmap(&p.tmA[s], xs[s], N, Xin, Yin, Zin, Cs[s], p.KC[s], p.bz, p.by, p.bx, stride));
+    FM_TRY(make_act_tmap(&p.tmA[s], xs[s], N, Xin, Yin, Zin, Cs[s], p.KC[s], p.bz, p.by, p.bx, stride, stride_z));
     FM_TRY(make_w_tmap(&p.tmW[s], w_packed, Cout, p.ntaps, Ct, p.KC[s], p.block_n));
     cofs += Cs[s];
   }
@@ -880,6 +884,7 @@ int k_conv3d_up_fprop(fm_ctx* ctx, const bf16* coarse, const bf16* skip, const b
   p.out = y;
   p.mask = nullptr;
   p.stride = 1;
+  p.stride_z = 1;
   p.KC[0] = chunk_of(Cc);
   p.nchunks[0] = Cc / p.KC[0];
   p.wcofs[0] = 0;
@@ -927,6 +932,7 @@ int k_conv3d_up_dgrad(fm_ctx* ctx, const bf16* dy, const bf16* w_up_d, bf16* dco
   p.out = dcoarse;
   p.mask = mask;
   p.stride = 1;
+  p.stride_z = 1;
   p.KC[0] = chunk_of(Cout);
   p.nchunks[0] = Cout / p.KC[0];
   p.wcofs[0] = 0;

@@ -43,6 +43,12 @@ class SampleAug(ctypes.Structure):
                 ("noise_seed", ctypes.c_uint32)]
 
 
+class Isensee2DSpec(ctypes.Structure):
+    _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("in_channels", ctypes.c_int32),
+                ("depth", ctypes.c_int32), ("n_base_filters", ctypes.c_int32),
+                ("n_segmentation_levels", ctypes.c_int32), ("n_labels", ctypes.c_int32)]
+
+
 class UNet2DSpec(ctypes.Structure):
     _fields_ = [("H", ctypes.c_int32), ("W", ctypes.c_int32), ("in_channels", ctypes.c_int32),
                 ("depth", ctypes.c_int32), ("n_base_filters", ctypes.c_int32), ("n_labels", ctypes.c_int32)]
@@ -63,6 +69,7 @@ SIGNATURES = {
     "fm_model_create_unet3d": (c_int, [c_vp, ctypes.POINTER(UNet3DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_create_unet2d": (c_int, [c_vp, ctypes.POINTER(UNet2DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_create_isensee3d": (c_int, [c_vp, ctypes.POINTER(Isensee3DSpec), ctypes.POINTER(c_vp)]),
+    "fm_model_create_isensee2d": (c_int, [c_vp, ctypes.POINTER(Isensee2DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_destroy": (c_int, [c_vp]),
     "fm_model_num_layers": (c_int, [c_vp]),
     "fm_model_layer_info": (c_int, [c_vp, c_int, ctypes.c_char_p, c_i64p]),

@@ -1,5 +1,5 @@
 """Builders exported under the reference's names (fetal_net/model/__init__.py:3-18)."""
-from .unet3d import unet_model_3d, unet_model_2d, isensee2017_model_3d, Model  # noqa: F401
+from .unet3d import unet_model_3d, unet_model_2d, isensee2017_model_3d, isensee2017_model, Model  # noqa: F401
 from .. import reference_overlay_dir as _overlay
 
 # overlay: sub-modules this package does not define (fetal_net.model.fetal_net, .discriminator, .norm ... - Keras
@@ -27,9 +27,7 @@ def _not_built(name, why, ref_module=None):
     return fn
 
 
-_NEXT = "on the §8 'next' list of SURVEY.md — not built yet in the B200 path"
 _OUT = "outside the B200 hot path (SURVEY.md §2: classifier / adversarial models are out of scope)"
-isensee2017_model = _not_built("isensee2017_model", _NEXT)
 fetal_envelope_model = _not_built("fetal_envelope_model", _OUT, "fetal_net")
 fetal_origin_model = _not_built("fetal_origin_model", _OUT, "fetal_net_skip")
 fetal_origin2_model = _not_built("fetal_origin2_model", _OUT, "fetal_net_skip2")

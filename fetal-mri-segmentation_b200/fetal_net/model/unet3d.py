@@ -32,7 +32,14 @@ class Model:
         self.ndim = int(ndim)
         h = _lib.c_vp()
         self.trainable = True
-        if isensee_levels is not None:
+        if isensee_levels is not None and self.ndim == 2:
+            H, W, in_ch = [int(v) for v in input_shape]             # slices-as-channels (unet/isensee.py:38-39)
+            spec = _lib.Isensee2DSpec(H, W, in_ch, int(depth), int(n_base_filters), int(isensee_levels), int(n_labels))
+            _lib.check(lib.fm_model_create_isensee2d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            _lib.check(lib.fm_model_set_dropout(h, float(dropout_rate), int(dropout_seed)))
+            self.input_shape = (None, H, W, in_ch)
+            self.output_shape = (None, H, W, int(n_labels))
+        elif isensee_levels is not None:
             in_ch, X, Y, Z = [int(v) for v in input_shape]
             spec = _lib.Isensee3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(isensee_levels), int(n_labels))
             _lib.check(lib.fm_model_create_isensee3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
@@ -49,6 +56,8 @@ class Model:
             H, W, in_ch = [int(v) for v in input_shape]             # slices-as-channels (unet/unet.py:49-50)
             spec = _lib.UNet2DSpec(H, W, in_ch, int(depth), int(n_base_filters), int(n_labels))
             _lib.check(lib.fm_model_create_unet2d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            if dropout_rate:                                         # SpatialDropout2D (unet/unet.py:60-61,76-77)
+                _lib.check(lib.fm_model_set_dropout(h, float(dropout_rate), int(dropout_seed)))
             self.input_shape = (None, H, W, in_ch)
             self.output_shape = (None, H, W, int(n_labels))
         self._h = h
@@ -70,8 +79,8 @@ class Model:
             self.metrics_names.append('dice_coefficient')
         self.stop_training = False
         self.isensee_levels = isensee_levels
-        self.name = 'isensee2017_model_3d' if isensee_levels is not None else \
-            ('unet_model_3d' if self.ndim == 3 else 'unet_model_2d')
+        self.name = ('isensee2017_model_3d' if self.ndim == 3 else 'isensee2017_model') if isensee_levels is not None \
+            else ('unet_model_3d' if self.ndim == 3 else 'unet_model_2d')
         # layer table (Keras creation order; Keras would name them conv3d_1..conv3d_N)
         self.layers = []
         for i in range(lib.fm_model_num_layers(h)):
@@ -406,19 +415,19 @@ def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_ra
                   batch_normalization=False, activation_name="sigmoid", loss_function=dice_coefficient_loss,
                   dropout_rate=0, **kargs):
     """Same signature and defaults as the reference 2D / 2.5D builder (fetal_net/model/unet/unet.py:22-25):
-    `input_shape=(H, W, D)` with the slices (and previous-slice truth) as channels."""
+    `input_shape=(H, W, D)` with the slices (and previous-slice truth) as channels. `dropout_rate` > 0 puts a
+    SpatialDropout2D behind the first conv block of every level in training steps (unet/unet.py:60-61,76-77; keep
+    masks from the library's counter-based hash, `dropout_seed` kwarg)."""
     if tuple(pool_size) != (2, 2):
         raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2)" % (pool_size,))
     if deconvolution or batch_normalization:
         raise NotImplementedError("deconvolution / batch_normalization are on the §8 'next' list")
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
-    if dropout_rate:
-        raise NotImplementedError("SpatialDropout2D (dropout_rate > 0) is not built; the shipped config uses 0 "
-                                  "(fetal/config_utils.py:151)")
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
-                 device=kargs.get("device"), ndim=2)
+                 device=kargs.get("device"), ndim=2, dropout_rate=dropout_rate or 0.0,
+                 dropout_seed=kargs.get("dropout_seed", 0x5EED))
 
 
 def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, depth=5, dropout_rate=0.3,
@@ -434,3 +443,21 @@ def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, dept
                  device=kargs.get("device"), ndim=3, isensee_levels=n_segmentation_levels,
                  dropout_rate=dropout_rate or 0.0, dropout_seed=kargs.get("dropout_seed", 0x5EED),
                  mask_shape=mask_shape)
+
+
+def isensee2017_model(input_shape=(4, 128, 128, 128), n_base_filters=16, depth=5, dropout_rate=0.3,
+                      n_segmentation_levels=3, n_labels=1, optimizer=None, initial_learning_rate=5e-4,
+                      loss_function=dice_coefficient_loss, activation_name="sigmoid", summation=False, **kargs):
+    """Same signature and defaults as the reference 2D builder (fetal_net/model/unet/isensee.py:14-16):
+    `input_shape=(H, W, D)` with the slices as channels. With `summation=False` (the reference default) only the finest
+    1x1 head reaches the output (isensee.py:81-82) - Keras drops the coarser, unconnected heads from the model, so they
+    hold no weights here either; `summation=True` sums the `n_segmentation_levels` heads coarse to fine through
+    UpSampling2D (isensee.py:69-80)."""
+    if activation_name != "sigmoid":
+        raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
+    if len(input_shape) != 3:
+        raise ValueError("isensee2017_model takes input_shape=(H, W, slices); got %r" % (input_shape,))
+    return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
+                 initial_learning_rate=initial_learning_rate, loss_function=loss_function,
+                 device=kargs.get("device"), ndim=2, isensee_levels=n_segmentation_levels if summation else 1,
+                 dropout_rate=dropout_rate or 0.0, dropout_seed=kargs.get("dropout_seed", 0x5EED))

@@ -176,10 +176,12 @@ def load_old_model(model_file, verbose=True, config=None):
         builder_name = 'unet_model_3d' if len(cfg) == 7 else 'unet_model_2d'   # (C,X,Y,Z) vs (H,W,D)
     kwargs = dict(input_shape=tuple(cfg[:-3]), depth=cfg[-3], n_base_filters=cfg[-2], n_labels=cfg[-1],
                   initial_learning_rate=lr, loss_function=loss)
-    if builder_name == 'isensee2017_model_3d':
+    if builder_name in ('isensee2017_model_3d', 'isensee2017_model'):
         kwargs['n_segmentation_levels'] = levels
-        if config is not None and 'dropout_rate' in config:
-            kwargs['dropout_rate'] = config['dropout_rate']
+        if builder_name == 'isensee2017_model':     # the 2D builder: `levels` heads reach the output only when summed
+            kwargs['summation'] = levels > 1
+    if builder_name != 'unet_model_3d' and config is not None and 'dropout_rate' in config:
+        kwargs['dropout_rate'] = config['dropout_rate']
     m = getattr(_model_ns, builder_name)(**kwargs)
     m.load_weights(model_file)
     # Keras' load_model also restores the optimizer (Adam moments, iterations, the current learning rate): a resumed

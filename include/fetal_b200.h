@@ -94,9 +94,9 @@ typedef struct fm_unet2d_spec {
 int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec, fm_model** out);
 
 /* Builder spec of the Isensee-2017 residual 3D U-Net. Replaces the kwargs of isensee2017_model_3d
- * (fetal_net/model/unet3d/isensee2017.py:15-18). Forward / inference only in this round: fm_predict,
- * fm_predict_device and fm_patchwise_predict work; the training entry points return FM_EINVAL. The layer table
- * lists every Conv3D followed by its InstanceNormalization pseudo-layer (kernel = gamma, bias = beta). */
+ * (fetal_net/model/unet3d/isensee2017.py:15-18). Inference and training (every fm_predict* / fm_patchwise_predict* /
+ * fm_train_* / fm_evaluate entry point). The layer table lists every Conv3D followed by its InstanceNormalization
+ * pseudo-layer (kernel = gamma, bias = beta). */
 typedef struct fm_isensee3d_spec {
   int32_t in_channels;            /* 1                                        */
   int32_t X, Y, Z;                /* each divisible by 2^(depth-1)            */
@@ -106,6 +106,23 @@ typedef struct fm_isensee3d_spec {
   int32_t n_labels;               /* 1                                        */
 } fm_isensee3d_spec;
 int fm_model_create_isensee3d(fm_ctx* ctx, const fm_isensee3d_spec* spec, fm_model** out);
+
+/* Builder spec of the 2D Isensee-2017 net. Replaces the kwargs of isensee2017_model
+ * (fetal_net/model/unet/isensee.py:14-16; config_utils.py:66-69 selects it as model_name for 2D runs):
+ * input_shape=(H,W,in_channels) with the slices as channels, Conv2D 3x3 / 1x1 blocks with InstanceNormalization +
+ * LeakyReLU, strides (2,2) between levels, SpatialDropout2D in the context modules, UpSampling2D, 1x1 heads.
+ * n_segmentation_levels = the number of heads that reach the output: with the reference's default summation=False only
+ * the finest head does (pass 1); with summation=True the coarser heads are upsampled and added (pass the builder's
+ * n_segmentation_levels). Input [B,H,W,in_channels], output [B,H,W,1]. */
+typedef struct fm_isensee2d_spec {
+  int32_t H, W;                   /* each divisible by 2^(depth-1)            */
+  int32_t in_channels;            /* 1..16                                    */
+  int32_t depth;                  /* default 5                                */
+  int32_t n_base_filters;         /* default 16                               */
+  int32_t n_segmentation_levels;  /* heads summed into the output (see above) */
+  int32_t n_labels;               /* 1                                        */
+} fm_isensee2d_spec;
+int fm_model_create_isensee2d(fm_ctx* ctx, const fm_isensee2d_spec* spec, fm_model** out);
 
 /* Layer table, Keras creation order (conv3d_1 ... conv3d_15). */
 int fm_model_num_layers(fm_model* m);

@@ -304,18 +304,26 @@ def upsampled_conv_parity_weights(w):
     return wc
 
 
-def isensee3d_forward(x, w, depth=5, n_segmentation_levels=1, return_logits=False):
+def _isensee_forward(x, w, depth, n_segmentation_levels, return_logits, nd, drop=None):
+    """The Isensee graph on channels-first tensors, 3D (nd = 3) or 2D (nd = 2). `drop`: {level: scale [B,C]} of the
+    SpatialDropout between the two context convs (training with dropout; None = identity)."""
     dt = x.dtype
+    conv = F.conv3d if nd == 3 else F.conv2d
+
+    def up2(t):
+        for ax in range(2, 2 + nd):
+            t = t.repeat_interleave(2, ax)
+        return t
 
     def cb(t, name, stride=1, k=3):
         kk, b = _tw(w, name, dt)
         if k == 3 and stride == 2:
-            t = F.pad(t, (0, 1, 0, 1, 0, 1))       # TF SAME, even input: pad_before 0, pad_after 1 (App. A.3)
-            y = F.conv3d(t, kk, b, stride=2)
+            t = F.pad(t, (0, 1) * nd)              # TF SAME, even input: pad_before 0, pad_after 1 (App. A.3)
+            y = conv(t, kk, b, stride=2)
         elif k == 3:
-            y = F.conv3d(t, kk, b, padding=1)
+            y = conv(t, kk, b, padding=1)
         else:
-            y = F.conv3d(t, kk, b)
+            y = conv(t, kk, b)
         g = torch.as_tensor(w[name + "/gamma"]).to(dt)
         be = torch.as_tensor(w[name + "/beta"]).to(dt)
         return F.leaky_relu(_instance_norm(y, g, be), 0.3)
@@ -324,24 +332,43 @@ def isensee3d_forward(x, w, depth=5, n_segmentation_levels=1, return_logits=Fals
     outs = []
     for l in range(depth):
         inc = cb(cur, "l%d_in" % l, stride=1 if l == 0 else 2)
-        ctx = cb(cb(inc, "l%d_ctx1" % l), "l%d_ctx2" % l)   # dropout: identity at rate 0 / inference
+        c1 = cb(inc, "l%d_ctx1" % l)
+        if drop is not None and l in drop:
+            c1 = c1 * torch.as_tensor(drop[l]).to(dt).reshape(c1.shape[:2] + (1,) * nd)
+        ctx = cb(c1, "l%d_ctx2" % l)                        # dropout: identity at rate 0 / inference
         cur = inc + ctx
         outs.append(cur)
     segs = {}
     for l in range(depth - 2, -1, -1):
-        up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
-        up = cb(up, "u%d_up" % l)
-        cat = torch.cat([outs[l], up], dim=1)           # isensee2017.py:62: [skip, up]
+        up = cb(up2(cur), "u%d_up" % l)
+        cat = torch.cat([outs[l], up], dim=1)           # isensee2017.py:62 / unet/isensee.py:62: [skip, up]
         cur = cb(cb(cat, "u%d_loc1" % l), "u%d_loc2" % l, k=1)
         if l < n_segmentation_levels:
             kk, b = _tw(w, "u%d_seg" % l, dt)
-            segs[l] = F.conv3d(cur, kk, b)
+            segs[l] = conv(cur, kk, b)
     out = None
     for l in reversed(range(n_segmentation_levels)):
         out = segs[l] if out is None else out + segs[l]
         if l > 0:
-            out = out.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+            out = up2(out)
     return out if return_logits else torch.sigmoid(out)
+
+
+def isensee3d_forward(x, w, depth=5, n_segmentation_levels=1, return_logits=False, drop=None):
+    return _isensee_forward(x, w, depth, n_segmentation_levels, return_logits, 3, drop)
+
+
+def isensee2d_layers(depth=5, n_base_filters=16, n_heads=1, in_channels=5, n_labels=1):
+    """isensee2017_model (fetal_net/model/unet/isensee.py:14-86). `n_heads` = heads that reach the output: 1 under the
+    reference default summation=False (only segmentation_layers[0] is connected, isensee.py:81-82; Keras keeps no
+    weights for the unconnected coarser heads), n_segmentation_levels with summation=True."""
+    return isensee3d_layers(depth, n_base_filters, n_heads, in_channels, n_labels)
+
+
+def isensee2d_forward(x, w, depth=5, n_heads=1, return_logits=False, drop=None):
+    """x: [B,H,W,D] (slices-as-channels) -> [B,H,W,1]: Permute((3,1,2)), the 2D graph, Permute((2,3,1))."""
+    out = _isensee_forward(x.permute(0, 3, 1, 2), w, depth, n_heads, return_logits, 2, drop)
+    return out.permute(0, 2, 3, 1)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -352,8 +379,25 @@ def unet2d_layers(depth=4, n_base_filters=32, in_channels=6, n_labels=1):
     return unet3d_layers(depth, n_base_filters, in_channels, n_labels)
 
 
-def unet2d_forward(x, w, depth=4, return_logits=False):
-    """x: [B,H,W,D] (slices-as-channels, Keras input layout) -> [B,H,W,n_labels]."""
+def library_dropout_scales(n, rate, seed):
+    """The library's SpatialDropout keep/scale factors (dropout_scale_kernel, csrc/bandwidth.cu): splitmix64 of
+    (seed, index) -> u in [0,1) from the top 24 bits -> keep ? 1/(1-rate) : 0. Keras draws its masks from TF's RNG,
+    which cannot be reproduced; this restates OUR generator so that a training step WITH dropout can be checked."""
+    i = np.arange(1, n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        h = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * i
+        h = (h ^ (h >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        h = (h ^ (h >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        h ^= h >> np.uint64(31)
+    u = (h >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return np.where(u >= np.float32(rate), np.float32(1.0) / (np.float32(1.0) - np.float32(rate)), np.float32(0.0)) \
+        .astype(np.float32)
+
+
+def unet2d_forward(x, w, depth=4, return_logits=False, drop=None):
+    """x: [B,H,W,D] (slices-as-channels, Keras input layout) -> [B,H,W,n_labels]. `drop` (training with
+    SpatialDropout2D, unet/unet.py:60-61,76-77): {'enc<d>' / 'dec<d>': scale [B,C]} applied behind the first block of
+    the level."""
     dt = x.dtype
     cur = x.permute(0, 3, 1, 2)                      # Permute((3,1,2))
     skips = []
@@ -362,15 +406,20 @@ def unet2d_forward(x, w, depth=4, return_logits=False):
         k, b = _tw(w, name, dt)
         return F.relu(F.conv2d(t, k, b, padding=1))
 
+    def dr(t, key):
+        if drop is None or key not in drop:
+            return t
+        return t * torch.as_tensor(drop[key]).to(dt)[:, :, None, None]
+
     for d in range(depth):
-        cur = cb(cb(cur, "enc%da" % d), "enc%db" % d)
+        cur = cb(dr(cb(cur, "enc%da" % d), "enc%d" % d), "enc%db" % d)
         skips.append(cur)
         if d < depth - 1:
             cur = F.max_pool2d(cur, 2)
     for d in range(depth - 2, -1, -1):
         up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3)
         cur = torch.cat([up, skips[d]], dim=1)
-        cur = cb(cb(cur, "dec%da" % d), "dec%db" % d)
+        cur = cb(dr(cb(cur, "dec%da" % d), "dec%d" % d), "dec%db" % d)
     k, b = _tw(w, "final", dt)
     logits = F.conv2d(cur, k, b)
     out = logits if return_logits else torch.sigmoid(logits)

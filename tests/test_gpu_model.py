@@ -500,3 +500,80 @@ def test_isensee_dice_and_xent_mask_two_input_model():
     ev0 = model.test_on_batch([x, mask], t)
     ev1 = model.test_on_batch([x, np.zeros_like(mask)], t)
     assert ev1[0] > ev0[0] + 1e-3                                        # weight 1 everywhere > exp(-mask/3)
+
+
+# ---- Isensee-2017 in 2D: isensee2017_model (fetal_net/model/unet/isensee.py) -------------------------------------
+
+def _isensee2d_weights(layers, seed):
+    w = uo.glorot_uniform_weights(layers, seed=seed, ndim=2)
+    rng = np.random.default_rng(seed + 1)
+    for name, cin, cout, k in layers:
+        w[name + "/bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        if not name.endswith("_seg"):
+            w[name + "/gamma"] = (1.0 + 0.2 * rng.standard_normal(cout)).astype(np.float32)
+            w[name + "/beta"] = (0.2 * rng.standard_normal(cout)).astype(np.float32)
+        else:
+            w[name + "/kernel"] = (w[name + "/kernel"] * 3.0).astype(np.float32)
+    return w
+
+
+@pytest.mark.parametrize("shape,depth,nseg,summation", [((32, 32, 5), 3, 3, False), ((64, 64, 6), 4, 2, True)])
+def test_isensee2d_forward_and_train_step_match_oracle(shape, depth, nseg, summation):
+    """The 2D Isensee builder (config_utils.py:66-69 model_name 'isensee2017_model'): Conv2D blocks with instance norm,
+    strides (2,2), UpSampling2D; summation=False keeps only the finest head (the reference default), summation=True
+    sums the heads coarse to fine. Forward, loss and gradients against torch autograd on the fp32 restatement."""
+    from fetal_net.model import isensee2017_model
+    heads = nseg if summation else 1
+    layers = uo.isensee2d_layers(depth, 16, heads, shape[2])
+    w = _isensee2d_weights(layers, seed=5)
+    model = isensee2017_model(input_shape=shape, n_base_filters=16, depth=depth, n_segmentation_levels=nseg,
+                              summation=summation, dropout_rate=0, initial_learning_rate=1e-3)
+    assert [l["name"] for l in model.layers if not l["is_norm"]] == [n for n, *_ in layers]
+    assert model.layers[0]["kshape"] == (3, 3, shape[2], 16) and model.output_shape == (None,) + shape[:2] + (1,)
+    assert model.count_params() == sum(v.size for v in w.values())
+    model.set_named_weights(w)
+    back = model.get_weights()
+    assert np.array_equal(back[0], w["l0_in/kernel"])                        # (3,3,Cin,Cout) round trip, Cin padded inside
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2,) + shape).astype(np.float32)
+    t = (torch.nn.functional.avg_pool2d(torch.as_tensor(x[..., shape[2] // 2])[:, None], 5, stride=1, padding=2)
+         .numpy()[:, 0, :, :, None] > 0.05).astype(np.float32)
+    fwd = lambda xt, prm: uo.isensee2d_forward(xt, prm, depth=depth, n_heads=heads)
+    p = model.predict(x)
+    with torch.no_grad():
+        ref = fwd(torch.as_tensor(x), w).numpy()
+    assert p.shape == ref.shape == (2,) + shape[:2] + (1,)
+    logit = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    rel = np.linalg.norm(logit(p) - logit(ref)) / np.linalg.norm(logit(ref))
+    assert rel <= 0.04 and np.abs(p - ref).mean() <= 0.008, (rel, float(np.abs(p - ref).mean()))
+    refstep = uo.train_step(fwd, x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-3)
+    loss = model.train_on_batch(x, t)[0]
+    assert abs(loss - refstep["loss"]) <= 4e-3, (loss, refstep["loss"])
+    cos = _grad_cosines(model, refstep["grads"])
+    worst = min(cos.items(), key=lambda kv: kv[1])
+    assert worst[1] >= 0.97 and np.median(list(cos.values())) >= 0.99, (worst, sorted(cos.items(), key=lambda kv: kv[1])[:5])
+    losses = [loss] + [model.train_on_batch(x, t)[0] for _ in range(5)]
+    assert losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_isensee2d_dropout_and_patchwise():
+    """SpatialDropout2D of the context modules (unet/isensee.py:105): identity at inference, active in training; and
+    the 2.5D sliding window over a volume drives the 2D Isensee model like the 2D U-Net."""
+    from fetal_net.model import isensee2017_model
+    from fetal_net.prediction import patch_wise_prediction
+    from oracle import prediction_oracle as po
+    kw = dict(input_shape=(32, 32, 5), n_base_filters=16, depth=3, initial_learning_rate=1e-3)
+    a = isensee2017_model(dropout_rate=0.0, **kw)
+    b = isensee2017_model(dropout_rate=0.5, **kw)
+    a.init_glorot_uniform(seed=2)
+    b.set_weights(a.get_weights())
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 32, 32, 5)).astype(np.float32)
+    t = (rng.random((2, 32, 32, 1)) < 0.3).astype(np.float32)
+    assert np.array_equal(a.predict(x), b.predict(x))
+    la, lb = a.train_on_batch(x, t)[0], b.train_on_batch(x, t)[0]
+    assert np.isfinite(lb) and la != lb
+    vol = rng.standard_normal((1, 48, 32, 9)).astype(np.float32)
+    out = patch_wise_prediction(a, vol, patch_shape=(32, 32, 5), overlap_factor=0.5, batch_size=4)
+    ref = po.patch_wise_prediction(a, vol, (32, 32, 5), overlap_factor=0.5, batch_size=4)
+    assert out.shape == (48, 32, 9, 1) and np.array_equal(out, ref)

@@ -202,6 +202,44 @@ def test_unet2d_train_step_matches_oracle(native2d):
     assert not bad, bad
 
 
+def test_unet2d_spatial_dropout_train_step_matches_oracle(native2d):
+    """unet_model_2d(dropout_rate=0.25): SpatialDropout2D behind enc<d>a / dec<d>a in training steps
+    (unet/unet.py:60-61,76-77). The keep masks come from the library's counter-based hash, restated in the oracle
+    (library_dropout_scales), so loss and gradients of a step WITH dropout are compared; inference ignores it."""
+    from fetal_net.model import unet_model_2d
+    _, w0 = native2d
+    depth, nf, rate, seed, B = 4, 32, 0.25, 1234, 2
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((B, 32, 32, 6)).astype(np.float32)
+    t = (rng.random((B, 32, 32, 1)) < 0.3).astype(np.float32)
+    model = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=nf, depth=depth, initial_learning_rate=1e-4,
+                          dropout_rate=rate, dropout_seed=seed)
+    plain = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=nf, depth=depth, initial_learning_rate=1e-4)
+    model.set_named_weights(w0)
+    plain.set_named_weights(w0)
+    assert np.array_equal(model.predict(x), plain.predict(x))           # identity at inference
+    drop = {}
+    for d in range(depth):                                              # slot d: enc<d>a (nf * 2^d channels)
+        drop["enc%d" % d] = uo.library_dropout_scales(B * (nf << d), rate, seed + d).reshape(B, -1)
+    for d in range(depth - 1):                                          # slot depth + d: dec<d>a (2 nf * 2^d channels)
+        drop["dec%d" % d] = uo.library_dropout_scales(B * (2 * nf << d), rate, seed + depth + d).reshape(B, -1)
+    assert 0.1 < np.mean([np.mean(v == 0) for v in drop.values()]) < 0.4
+    ref = uo.train_step(lambda xt, prm: uo.unet2d_forward(xt, prm, depth=depth, drop=drop), x, t,
+                        {k: v.copy() for k, v in w0.items()}, {}, 1e-4)
+    got = model.train_on_batch(x, t)
+    assert got[0] == pytest.approx(ref["loss"], abs=3e-3), (got, ref["loss"])
+    assert abs(got[0] - plain.train_on_batch(x, t)[0]) > 1e-4           # the masks did change the forward pass
+    grads = model.get_gradients()
+    bad = []
+    for l, gk in zip(model.layers, grads[0::2]):
+        r = ref["grads"][l["name"] + "/kernel"].astype(np.float64).ravel()
+        g = gk.astype(np.float64).ravel()
+        cos = float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
+        if cos < (0.95 if l["name"] in ("enc0a", "enc0b") else 0.99):
+            bad.append((l["name"], cos))
+    assert not bad, bad
+
+
 def test_native_2d_pipeline_with_truth_equals_own_predict_plus_oracle_reassembly(native2d):
     """config 4 shape class: 5 slices + 1 previous-truth slice as channels, z-step 1, z halo (2,2)."""
     from fetal_net.prediction import patch_wise_prediction

@@ -129,8 +129,11 @@ def test_reference_api_surface():
     assert sig.parameters["loss_function"].default is fm.dice_coefficient_loss
     assert list(inspect.signature(ft.train_model).parameters)[:6] == [
         "model", "model_file", "training_generator", "validation_generator", "steps_per_epoch", "validation_steps"]
-    with pytest.raises(NotImplementedError):
-        fmod.isensee2017_model(input_shape=(32, 32, 5))            # 2D Isensee: on the §8 "next" list
+    sig = inspect.signature(fmod.isensee2017_model)               # unet/isensee.py:14-16
+    assert sig.parameters["n_segmentation_levels"].default == 3 and sig.parameters["summation"].default is False
+    assert sig.parameters["dropout_rate"].default == 0.3 and sig.parameters["initial_learning_rate"].default == 5e-4
+    sig = inspect.signature(fmod.isensee2017_model_3d)            # unet3d/isensee2017.py:15-18
+    assert sig.parameters["mask_shape"].default is None and sig.parameters["n_segmentation_levels"].default == 1
 
 
 def test_host_metrics_known_answers():
