@@ -215,6 +215,7 @@ struct Layer {
   int cin_real = 0;     // true input channels when c1 is zero-padded to 16 (first layer of the 2.5D U-Net)
   int is_norm = 0;      // InstanceNormalization pseudo-layer of the Isensee net: kernel = gamma, bias = beta (cout each)
   int stride = 1;       // 2: TF-'SAME' strided conv (Isensee in-convs)
+  int deconv = 0;       // Deconvolution3D/2D (k = 2 or 21, stride 2): master kernel [class][Cout][Cin] = the Keras layout
   int cin() const { return c1 + c2; }
   int taps() const { return kext_taps(k); }
   int cin_keras() const { return cin_real ? cin_real : cin(); }
@@ -252,6 +253,10 @@ struct fm_model {
   uint64_t dropout_seed = 0x5EEDull;
   // 2D U-Net: SpatialDropout2D keep/scale factors [B][C] after enc<d>a (slot d) and dec<d>a (slot depth + d)
   std::vector<DevBuf<float>> dropU;
+  // deconvolution=True (get_up_convolution, unet3d/unet.py:132-136): the 1x1x1 conv output before the depth-to-space
+  // shuffle, and the shuffled gradient on the way back
+  bool deconvolution = false;
+  DevBuf<bf16> dcZ, dcG;
   bool unet_dropout() const { return kind == 0 && kcode == 31 && dropout_rate > 0.f; }
   int kcode = 3;  // 3: Conv3D 3x3x3 (unet_model_3d); 31: Conv2D 3x3 on a Z = 1 volume (unet_model_2d)
   int pz = 2;     // pooling factor along z
@@ -348,10 +353,18 @@ static bool shared_march(const fm_model* m, int n_channels) {
   return m->train_pass && n_channels <= 32 && !det;
 }
 
-static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_model** out);
+static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int flags, fm_model** out);
 
 extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out) {
+  return fm_model_create_unet3d_ex(ctx, spec, 0, out);
+}
+extern "C" int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec2, fm_model** out) {
+  return fm_model_create_unet2d_ex(ctx, spec2, 0, out);
+}
+
+extern "C" int fm_model_create_unet3d_ex(fm_ctx* ctx, const fm_unet3d_spec* spec, int flags, fm_model** out) {
   FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_unet3d: NULL argument");
+  FM_CHECK((flags & ~FM_UNET_DECONVOLUTION) == 0, FM_EINVAL, "fm_model_create_unet3d_ex: unknown flags 0x%x", flags);
   FM_CHECK(spec->in_channels == 1, FM_EINVAL,
            "in_channels=%d: only the reference's single-modality path (1) is built", spec->in_channels);
   const int div = 1 << (spec->depth > 0 ? spec->depth - 1 : 0);
@@ -359,11 +372,12 @@ extern "C" int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, f
                spec->Z % div == 0,
            FM_EINVAL, "input extent %dx%dx%d must be divisible by 2^(depth-1)=%d (unet3d/unet.py:32-33)",
            spec->X, spec->Y, spec->Z, div);
-  return build_unet(ctx, spec, 3, out);
+  return build_unet(ctx, spec, 3, flags, out);
 }
 
-extern "C" int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec2, fm_model** out) {
+extern "C" int fm_model_create_unet2d_ex(fm_ctx* ctx, const fm_unet2d_spec* spec2, int flags, fm_model** out) {
   FM_CHECK(ctx && spec2 && out, FM_EINVAL, "fm_model_create_unet2d: NULL argument");
+  FM_CHECK((flags & ~FM_UNET_DECONVOLUTION) == 0, FM_EINVAL, "fm_model_create_unet2d_ex: unknown flags 0x%x", flags);
   FM_CHECK(spec2->in_channels >= 1 && spec2->in_channels <= 16, FM_EINVAL,
            "in_channels=%d: the slices-as-channels input supports 1..16 channels", spec2->in_channels);
   const int div = 1 << (spec2->depth > 0 ? spec2->depth - 1 : 0);
@@ -377,10 +391,10 @@ extern "C" int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec2, 
   s.depth = spec2->depth;
   s.n_base_filters = spec2->n_base_filters;
   s.n_labels = spec2->n_labels;
-  return build_unet(ctx, &s, 31, out);
+  return build_unet(ctx, &s, 31, flags, out);
 }
 
-static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_model** out) {
+static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int flags, fm_model** out) {
   FM_CHECK(spec->depth >= 2 && spec->depth <= 6, FM_EINVAL, "depth %d unsupported", spec->depth);
   FM_CHECK(spec->n_labels == 1, FM_EINVAL, "n_labels=%d: only 1 is built", spec->n_labels);
   FM_CHECK(spec->n_base_filters == 16 || spec->n_base_filters == 32, FM_EINVAL,
@@ -392,6 +406,7 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_mod
   m->kcode = kcode;
   m->pz = kcode == 31 ? 1 : 2;
   m->cin_real = spec->in_channels;
+  m->deconvolution = (flags & FM_UNET_DECONVOLUTION) != 0;
   const int D = spec->depth, nf = spec->n_base_filters;
   auto add = [&](const char* fmt, int d, int c1, int c2, int cout, int k, int level) {
     Layer l;
@@ -421,6 +436,12 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_mod
     c = f2;
   }
   for (int d = D - 2; d >= 0; --d) {
+    if (m->deconvolution) {
+      // Deconvolution3D(filters = channels of the coarse tensor, kernel 2, strides 2), created before the block that
+      // consumes it (unet.py:57-59): 8 (4 in 2D) parity-class 1x1x1 matrices, bias, no activation
+      add("up%d", d, c, 0, c, kcode == 31 ? 21 : 2, d + 1);
+      m->layers.back().deconv = 1;
+    }
     add("dec%da", d, c, skipc[d], skipc[d], kcode, d);  // concat order [up, skip] (unet.py:61)
     add("dec%db", d, skipc[d], 0, skipc[d], kcode, d);
     c = skipc[d];
@@ -469,7 +490,7 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, fm_mod
   // decoder convs whose filter bank is too large for the marching kernel run at COARSE resolution on their upsampled
   // source (dec1a, dec2a of the shipped model); FETAL_B200_NO_UP_COARSE=1 keeps the materialised upsampling
   for (auto& l : m->layers) {
-    if (strncmp(l.name, "dec", 3) != 0 || l.c2 == 0 || l.k != 3 || m->pz != 2) continue;
+    if (strncmp(l.name, "dec", 3) != 0 || l.c2 == 0 || l.k != 3 || m->pz != 2 || m->deconvolution) continue;
     const char* e = getenv("FETAL_B200_NO_UP_COARSE");
     if (e && e[0] == '1') continue;
     const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
@@ -563,6 +584,8 @@ extern "C" int fm_model_destroy(fm_model* m) {
   m->pw_out.release();
   m->pw_cnt.release();
   m->x_in.release();
+  m->dcZ.release();
+  m->dcG.release();
   m->mask_in.release();
   m->x_pad.release();
   m->t_in.release();
@@ -643,7 +666,10 @@ extern "C" int fm_model_set_weights(fm_model* m, int layer, const float* kernel,
     return FM_OK;
   }
   std::vector<float> packed((size_t)l.wcount());
-  keras_to_packed(kernel, packed.data(), l.k, l.cin_keras(), l.cout, l.cin());
+  if (l.deconv)  // Keras Conv3DTranspose kernel (2,2,2,Cout,Cin) is already [class][Cout][Cin]
+    memcpy(packed.data(), kernel, packed.size() * sizeof(float));
+  else
+    keras_to_packed(kernel, packed.data(), l.k, l.cin_keras(), l.cout, l.cin());
   FM_CUDA(cudaStreamSynchronize(m->ctx->stream));
   FM_CUDA(cudaMemcpy(m->params + l.w_off, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
   FM_CUDA(cudaMemcpy(m->params + l.b_off, bias, (size_t)l.cout * 4, cudaMemcpyHostToDevice));
@@ -660,7 +686,10 @@ static int get_flat(fm_model* m, const float* flat, int layer, float* kernel, fl
   } else if (kernel) {
     std::vector<float> packed((size_t)l.wcount());
     FM_CUDA(cudaMemcpy(packed.data(), flat + l.w_off, packed.size() * 4, cudaMemcpyDeviceToHost));
-    packed_to_keras(packed.data(), kernel, l.k, l.cin_keras(), l.cout, l.cin());
+    if (l.deconv)
+      memcpy(kernel, packed.data(), packed.size() * sizeof(float));
+    else
+      packed_to_keras(packed.data(), kernel, l.k, l.cin_keras(), l.cout, l.cin());
   }
   if (bias) FM_CUDA(cudaMemcpy(bias, flat + l.b_off, (size_t)l.cout * 4, cudaMemcpyDeviceToHost));
   return FM_OK;
@@ -727,8 +756,9 @@ static int refresh_packs(fm_model* m) {
       if (l.is_norm || (l.k == 1 && l.cout == 1)) continue;  // norm parameters / heads are read as fp32
       RepackDesc d;
       d.w_off = l.w_off;
-      d.cout = l.cout;
-      d.taps = l.taps();
+      // a deconvolution is repacked as the 1x1x1 conv it runs as: [class * Cout + co][1][Cin]
+      d.cout = l.deconv ? l.cout * l.taps() : l.cout;
+      d.taps = l.deconv ? 1 : l.taps();
       d.c1 = l.c1;
       d.c2 = l.c2;
       d.wf = l.w_f;
@@ -743,7 +773,7 @@ static int refresh_packs(fm_model* m) {
       d.kcd0 = conv_march_kc(l.cout, 0, l.c1, l.cout);
       d.kcd1 = l.c2 ? conv_march_kc(l.cout, 0, l.c2, l.cout) : 0;
       d.block0 = blocks;
-      blocks += l.taps() * ceil_div(l.cout, 32) * ceil_div(l.cin(), 32);  // 32 x 32 (co, c) tiles per tap
+      blocks += d.taps * ceil_div(d.cout, 32) * ceil_div(l.cin(), 32);  // 32 x 32 (co, c) tiles per tap
       weights += (double)l.wcount();
       tab.push_back(d);
     }
@@ -780,8 +810,8 @@ static int refresh_packs(fm_model* m) {
   for (auto& l : m->layers) {
     if (l.is_norm) continue;
     if (l.k == 1 && l.cout == 1) continue;  // head reads fp32 weights directly
-    FM_TRY(k_repack_weights(m->ctx, m->params + l.w_off, l.w_f, l.w_d0, l.c2 ? l.w_d1 : nullptr, l.cout,
-                            l.taps(), l.c1, l.c2));
+    FM_TRY(k_repack_weights(m->ctx, m->params + l.w_off, l.w_f, l.w_d0, l.c2 ? l.w_d1 : nullptr,
+                            l.deconv ? l.cout * l.taps() : l.cout, l.deconv ? 1 : l.taps(), l.c1, l.c2));
     const int cs[2] = {l.c1, l.c2};
     int kofs = 0;
     for (int s = 0; s < (l.c2 ? 2 : 1); ++s) {
@@ -820,6 +850,7 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
       FM_TRY(m->pool[d].ensure((size_t)m->vox(d + 1) * cap * lb.cout));
       const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
       if (!da.up_coarse) FM_TRY(m->up[d].ensure(v * da.c1));
+      if (m->deconvolution) FM_TRY(m->dcZ.ensure(v * da.c1));
       FM_TRY(m->decA[d].ensure(v * da.cout));
       FM_TRY(m->decB[d].ensure(v * db.cout));
     }
@@ -835,6 +866,7 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
         FM_TRY(m->gPool[d].ensure((size_t)m->vox(d + 1) * cap * lb.cout));
         const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
         if (!da.up_coarse && !da.up_dgrad) FM_TRY(m->gUp[d].ensure(v * da.c1));
+        if (m->deconvolution) FM_TRY(m->dcG.ensure(v * da.c1));
         FM_TRY(m->gSkip[d].ensure(v * da.c2));
         FM_TRY(m->gDecA[d].ensure(v * da.cout));
         FM_TRY(m->gDecB[d].ensure(v * db.cout));
@@ -909,6 +941,14 @@ static int forward(fm_model* m, int B) {
       const Dims5 dd = m->dims(d, da.cout, B);
       FM_TRY(k_conv3d_up_fprop(ctx, cur, m->encB[d].p, da.w_up_f, da.w_f, m->params + da.b_off, m->decA[d].p, B, dd.X,
                                dd.Y, dd.Z, da.c1, da.c2, da.cout, 1));
+    } else if (m->deconvolution) {
+      // Deconvolution3D: 1x1x1 conv of the coarse tensor to (classes x C) channels, then depth-to-space (+ bias)
+      const Layer& lu = L(m, "up%d", d);
+      const Dims5 dc = m->dims(d + 1, lu.cout, B);
+      FM_TRY(k_conv3d_tc_fprop(ctx, cur, nullptr, lu.w_f, nullptr, m->dcZ.p, nullptr, B, dc.X, dc.Y, dc.Z, lu.c1, 0,
+                               lu.cout * lu.taps(), 1, 0, lu.cout * lu.taps(), 0));
+      FM_TRY(k_depth_to_space(ctx, m->dcZ.p, m->params + lu.b_off, m->up[d].p, dc, m->pz));
+      FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
     } else {
       FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B), m->pz));
       FM_TRY(conv_fwd(m, da, m->up[d].p, m->encB[d].p, m->decA[d].p, B));
@@ -1042,6 +1082,21 @@ static int backward(fm_model* m, int B) {
     }
     FM_TRY(conv_dgrad(m, da, 0, m->gDecA[d].p, nullptr, m->gUp[d].p, B));
     FM_TRY(conv_dgrad(m, da, 1, m->gDecA[d].p, nullptr, m->gSkip[d].p, B));
+    if (m->deconvolution) {
+      // Deconvolution3D backward: bias gradient = column sums of the fine gradient; the shuffled gradient is the dY
+      // of a 1x1x1 conv with (classes x C) outputs: weight gradient against the coarse activation, data gradient
+      // (+ ReLU mask of the coarse block) through the transposed matrix
+      const Layer& lu = L(m, "up%d", d);
+      const Dims5 dc = m->dims(d + 1, lu.cout, B);
+      const int c8 = lu.cout * lu.taps();
+      FM_TRY(k_bias_grad(ctx, m->gUp[d].p, m->grads + lu.b_off, (int64_t)B * m->vox(d), lu.cout));
+      FM_TRY(k_space_to_depth(ctx, m->gUp[d].p, m->dcG.p, dc, m->pz));
+      FM_TRY(k_conv3d_tc_wgrad(ctx, act, m->dcG.p, m->grads + lu.w_off, B, dc.X, dc.Y, dc.Z, lu.c1, lu.c1, 0, c8, 1));
+      FM_TRY(mark_layer_done(m, lu));
+      FM_TRY(k_conv3d_tc_fprop(ctx, m->dcG.p, nullptr, lu.w_d0, nullptr, gdst, act, B, dc.X, dc.Y, dc.Z, c8, 0, lu.c1, 1,
+                               0, lu.c1, 0));
+      continue;
+    }
     // through UpSampling3D into the coarser tensor that was upsampled (+ its ReLU mask)
     FM_TRY(k_upsample3d_bwd(ctx, m->gUp[d].p, act, gdst, m->dims(d + 1, da.c1, B), da.c1, 0, m->pz));
   }

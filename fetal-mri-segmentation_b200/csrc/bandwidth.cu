@@ -1427,6 +1427,58 @@ int k_channel_scale(fm_ctx* ctx, bf16* x, const float* scale, int N, int64_t vox
   return FM_OK;
 }
 
+// Deconvolution (k = 2, s = 2) shuffles: one thread per 16-byte channel group of a FINE voxel.
+template <bool TO_SPACE>
+__global__ void depth_space_kernel(const bf16* __restrict__ src, const float* __restrict__ bias, bf16* __restrict__ dst,
+                                   int N, int X, int Y, int Z, int C, int pz) {  // X, Y, Z = coarse extents
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)N * X * Y * Z * 4 * pz * c8n;
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= total) return;
+  const int c8 = (int)(gi % c8n);
+  int64_t v = gi / c8n;  // fine voxel index
+  const int fz = (int)(v % (pz * Z));
+  int64_t r = v / (pz * Z);
+  const int fy = (int)(r % (2 * Y));
+  r /= 2 * Y;
+  const int fx = (int)(r % (2 * X));
+  const int n = (int)(r / (2 * X));
+  const int a = fx & 1, b = fy & 1, c = pz == 2 ? (fz & 1) : 0;
+  const int cls = (a * 2 + b) * pz + c;
+  const int64_t vc = (((int64_t)n * X + (fx >> 1)) * Y + (fy >> 1)) * Z + (pz == 2 ? (fz >> 1) : fz);
+  const int64_t coarse_ofs = (vc * (4 * pz) + cls) * C + c8 * 8;
+  const int64_t fine_ofs = v * C + c8 * 8;
+  if (TO_SPACE) {
+    float f[8];
+    unpack8(ldg16(src + coarse_ofs), f);
+    if (bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += __ldg(bias + c8 * 8 + i);
+    }
+    stg16(dst + fine_ofs, pack8(f));
+  } else {
+    stg16(dst + coarse_ofs, ldg16(src + fine_ofs));
+  }
+}
+
+int k_depth_to_space(fm_ctx* ctx, const bf16* z8, const float* bias, bf16* fine, Dims5 c, int pz) {
+  FM_CHECK(c.C % 8 == 0, FM_EINVAL, "depth_to_space: C=%d", c.C);
+  const int64_t total = c.elems() / 8 * 4 * pz;
+  ProfScope prof(ctx, "depth_to_space", 0.0, (double)total * 32.0);
+  depth_space_kernel<true><<<grid_for(total), kThreads, 0, ctx->stream>>>(z8, bias, fine, c.N, c.X, c.Y, c.Z, c.C, pz);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_space_to_depth(fm_ctx* ctx, const bf16* fine, bf16* g8, Dims5 c, int pz) {
+  FM_CHECK(c.C % 8 == 0, FM_EINVAL, "space_to_depth: C=%d", c.C);
+  const int64_t total = c.elems() / 8 * 4 * pz;
+  ProfScope prof(ctx, "space_to_depth", 0.0, (double)total * 32.0);
+  depth_space_kernel<false><<<grid_for(total), kThreads, 0, ctx->stream>>>(fine, nullptr, g8, c.N, c.X, c.Y, c.Z, c.C, pz);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
 int k_dropout_scale(fm_ctx* ctx, float* scale, int n, float rate, uint64_t seed) {
   dropout_scale_kernel<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(scale, n, rate, seed);
   FM_LAUNCH_OK(ctx);

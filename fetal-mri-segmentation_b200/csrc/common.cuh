@@ -120,8 +120,10 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 
 // Kernel-extent code used by all conv launchers: 3 = 3x3x3, 1 = 1x1x1, 31 = 3x3x1 (Conv2D on a Z = 1 volume:
 // the 2.5D U-Net, fetal_net/model/unet/unet.py:103). Tap index = (kx * kxy + ky) * kz + kzi.
-__host__ __device__ static inline int kext_xy(int kcode) { return kcode == 31 ? 3 : kcode; }
-__host__ __device__ static inline int kext_z(int kcode) { return kcode == 31 ? 1 : kcode; }
+// 2 = 2x2x2 and 21 = 2x2x1: the stride-2 transposed convolutions (Deconvolution3D / Deconvolution2D,
+// get_up_convolution(deconvolution=True), unet3d/unet.py:132-136) - tap = parity class of the output voxel.
+__host__ __device__ static inline int kext_xy(int kcode) { return kcode == 31 ? 3 : (kcode == 21 ? 2 : kcode); }
+__host__ __device__ static inline int kext_z(int kcode) { return (kcode == 31 || kcode == 21) ? 1 : kcode; }
 __host__ __device__ static inline int kext_taps(int kcode) { return kext_xy(kcode) * kext_xy(kcode) * kext_z(kcode); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -225,6 +227,11 @@ int k_zero_insert(fm_ctx*, const bf16* coarse, bf16* fine, Dims5 coarse_dims, in
 int k_add_bf16(fm_ctx*, const bf16* a, const bf16* b, bf16* out, int64_t n);
 int k_sumpool_f32(fm_ctx*, const float* fine, float* coarse, int N, int X, int Y, int Z, int pz = 2);
 int k_dropout_scale(fm_ctx*, float* scale, int n, float rate, uint64_t seed);
+// Deconvolution3D/2D (kernel 2, stride 2) = a 1x1x1 conv to taps*C channels followed by a depth-to-space shuffle:
+// fine[n][2x+a][2y+b][pz*z+c][co] = z8[n][x][y][z][cls*C + co] + bias[co], cls = (a*2 + b)*pz + c. `coarse` = dims of z8
+// with C = channels per class. The reverse shuffle carries the gradient back.
+int k_depth_to_space(fm_ctx*, const bf16* z8, const float* bias, bf16* fine, Dims5 coarse, int pz);
+int k_space_to_depth(fm_ctx*, const bf16* fine, bf16* g8, Dims5 coarse, int pz);
 // x[n][v][c] *= scale[n][c] in place (SpatialDropout2D of the 2D U-Net, forward and backward)
 int k_channel_scale(fm_ctx*, bf16* x, const float* scale, int N, int64_t vox_per_sample, int C);
 int k_seg_upsample_add(fm_ctx*, const float* fine, const float* coarse, float* out, int N, int X, int Y, int Z,

@@ -68,6 +68,8 @@ SIGNATURES = {
     "fm_ctx_profile_get": (c_int, [c_vp, c_int, ctypes.c_char_p, c_dp]),
     "fm_model_create_unet3d": (c_int, [c_vp, ctypes.POINTER(UNet3DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_create_unet2d": (c_int, [c_vp, ctypes.POINTER(UNet2DSpec), ctypes.POINTER(c_vp)]),
+    "fm_model_create_unet3d_ex": (c_int, [c_vp, ctypes.POINTER(UNet3DSpec), c_int, ctypes.POINTER(c_vp)]),
+    "fm_model_create_unet2d_ex": (c_int, [c_vp, ctypes.POINTER(UNet2DSpec), c_int, ctypes.POINTER(c_vp)]),
     "fm_model_create_isensee3d": (c_int, [c_vp, ctypes.POINTER(Isensee3DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_create_isensee2d": (c_int, [c_vp, ctypes.POINTER(Isensee2DSpec), ctypes.POINTER(c_vp)]),
     "fm_model_destroy": (c_int, [c_vp]),

@@ -43,8 +43,9 @@ def creation_order(entries):
     suffix of their Keras auto-name = the order the builder created them in. The relative interleaving of kinds is
     irrelevant (to_npz_arrays numbers convolutions and normalisations separately)."""
     convs = sorted((e for e in entries if e[0] == "conv"), key=lambda e: _auto_index(e[1]))
+    deconvs = sorted((e for e in entries if e[0] == "deconv"), key=lambda e: _auto_index(e[1]))
     norms = sorted((e for e in entries if e[0] == "norm"), key=lambda e: _auto_index(e[1]))
-    return convs + norms
+    return convs + deconvs + norms
 
 
 def read_keras_h5_weights(path):
@@ -63,7 +64,9 @@ def read_keras_h5_weights(path):
             arrays = {n.split("/")[-1].split(":")[0]: np.asarray(g[lname][n]) for n in names}
             if "kernel" in arrays:
                 bias = arrays.get("bias", np.zeros(arrays["kernel"].shape[-1], np.float32))
-                out.append(("conv", lname, arrays["kernel"].astype(np.float32), bias.astype(np.float32)))
+                # Deconvolution3D/2D layers ("conv3d_transpose_<n>") are numbered on their own by Keras
+                out.append(("deconv" if "transpose" in lname else "conv", lname, arrays["kernel"].astype(np.float32),
+                            bias.astype(np.float32)))
             elif "gamma" in arrays and "beta" in arrays:
                 out.append(("norm", lname, arrays["gamma"].astype(np.float32), arrays["beta"].astype(np.float32)))
     return creation_order(out)
@@ -72,10 +75,14 @@ def read_keras_h5_weights(path):
 def to_npz_arrays(entries):
     """The same weights keyed the way Model.save_weights / load_weights key their .npz (layers renumbered from 1 in
     creation order: conv3d_1/kernel:0, conv3d_1/bias:0, instance_normalization_1/gamma:0, ...)."""
-    arrays, n_conv, n_norm = {}, 0, 0
+    arrays, n_conv, n_norm, n_deconv = {}, 0, 0, 0
     for e in entries:
         kind, a, b = e[0], e[-2], e[-1]                     # (kind, a, b) or (kind, layer_name, a, b)
-        if kind == "conv":
+        if kind == "deconv":
+            n_deconv += 1
+            prefix = "conv%dd_transpose_%d" % (a.ndim - 2, n_deconv)
+            arrays[prefix + "/kernel:0"], arrays[prefix + "/bias:0"] = a, b
+        elif kind == "conv":
             n_conv += 1
             prefix = "conv%dd_%d" % (a.ndim - 2, n_conv)
             arrays[prefix + "/kernel:0"], arrays[prefix + "/bias:0"] = a, b

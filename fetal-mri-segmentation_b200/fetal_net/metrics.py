@@ -68,9 +68,10 @@ def _not_built(name):
 
 
 def binary_crossentropy(y_true, y_pred):
-    # Keras K.binary_crossentropy (TF backend) on probabilities: clip to [1e-7, 1 - 1e-7], elementwise
+    # Keras K.binary_crossentropy (TF backend) on probabilities: clip to [eps, 1 - eps] with both bounds formed in
+    # float32 (1 - eps = 1 - 2^-23), elementwise
     t = np.asarray(y_true, dtype=np.float64)
-    p = np.clip(np.asarray(y_pred, dtype=np.float64), 1e-7, 1. - 1e-7)
+    p = np.clip(np.asarray(y_pred, dtype=np.float64), float(np.float32(1e-7)), float(np.float32(1.) - np.float32(1e-7)))
     return -(t * np.log(p) + (1. - t) * np.log1p(-p))
 
 

@@ -26,7 +26,8 @@ class Model:
     """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
 
     def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
-                 device=None, ndim=3, isensee_levels=None, dropout_rate=0.0, dropout_seed=0x5EED, mask_shape=None):
+                 device=None, ndim=3, isensee_levels=None, dropout_rate=0.0, dropout_seed=0x5EED, mask_shape=None,
+                 deconvolution=False):
         lib = _lib.load()
         self._ctx = _lib.get_context(device)
         self.ndim = int(ndim)
@@ -49,13 +50,15 @@ class Model:
         elif self.ndim == 3:
             in_ch, X, Y, Z = [int(v) for v in input_shape]          # channels-first (unet3d/unet.py:9)
             spec = _lib.UNet3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(n_labels))
-            _lib.check(lib.fm_model_create_unet3d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            _lib.check(lib.fm_model_create_unet3d_ex(self._ctx.handle, ctypes.byref(spec), 1 if deconvolution else 0,
+                                                     ctypes.byref(h)))
             self.input_shape = (None, in_ch, X, Y, Z)
             self.output_shape = (None, int(n_labels), X, Y, Z)
         else:
             H, W, in_ch = [int(v) for v in input_shape]             # slices-as-channels (unet/unet.py:49-50)
             spec = _lib.UNet2DSpec(H, W, in_ch, int(depth), int(n_base_filters), int(n_labels))
-            _lib.check(lib.fm_model_create_unet2d(self._ctx.handle, ctypes.byref(spec), ctypes.byref(h)))
+            _lib.check(lib.fm_model_create_unet2d_ex(self._ctx.handle, ctypes.byref(spec), 1 if deconvolution else 0,
+                                                     ctypes.byref(h)))
             if dropout_rate:                                         # SpatialDropout2D (unet/unet.py:60-61,76-77)
                 _lib.check(lib.fm_model_set_dropout(h, float(dropout_rate), int(dropout_seed)))
             self.input_shape = (None, H, W, in_ch)
@@ -78,6 +81,7 @@ class Model:
         if loss_function is not dice_coefficient_loss:
             self.metrics_names.append('dice_coefficient')
         self.stop_training = False
+        self.deconvolution = bool(deconvolution)
         self.isensee_levels = isensee_levels
         self.name = ('isensee2017_model_3d' if self.ndim == 3 else 'isensee2017_model') if isensee_levels is not None \
             else ('unet_model_3d' if self.ndim == 3 else 'unet_model_2d')
@@ -87,11 +91,13 @@ class Model:
             name = ctypes.create_string_buffer(32)
             info = (ctypes.c_int64 * 5)()
             _lib.check(lib.fm_model_layer_info(h, i, name, info))
-            k = int(info[2]) // 10                                   # 33 / 31 -> 3, 11 -> 1, 0 -> norm layer
+            k = int(info[2]) // 10                                   # 33 / 31 -> 3, 22 / 21 -> 2, 11 -> 1, 0 -> norm
             is_norm = int(info[2]) == 0
-            n_same = sum(1 for l in self.layers if l["is_norm"] == is_norm) + 1
-            self.layers.append(dict(index=i, name=name.value.decode(), is_norm=is_norm,
-                                    keras_name=("instance_normalization_%d" if is_norm else "conv%dd_%%d" % self.ndim) % n_same,
+            is_deconv = k == 2                                       # Keras names them conv3d_transpose_<n>
+            n_same = sum(1 for l in self.layers if (l["is_norm"], l["is_deconv"]) == (is_norm, is_deconv)) + 1
+            self.layers.append(dict(index=i, name=name.value.decode(), is_norm=is_norm, is_deconv=is_deconv,
+                                    keras_name=("instance_normalization_%d" if is_norm else
+                                                ("conv%dd_transpose_%%d" if is_deconv else "conv%dd_%%d") % self.ndim) % n_same,
                                     cin=int(info[0]), cout=int(info[1]), k=k,
                                     kshape=(int(info[1]),) if is_norm else
                                     (k,) * self.ndim + (int(info[0]), int(info[1]))))
@@ -171,6 +177,7 @@ class Model:
         # builder name + its extra arguments, so that load_old_model can rebuild the right family
         arrays["__builder__"] = np.array(getattr(self, "name", "unet_model_3d"))
         arrays["__isensee_levels__"] = np.array(int(getattr(self, "isensee_levels", 0) or 0))
+        arrays["__deconvolution__"] = np.array(int(getattr(self, "deconvolution", False)))
         return arrays
 
     def save_weights(self, path):
@@ -399,15 +406,13 @@ def unet_model_3d(input_shape, pool_size=(2, 2, 2), n_labels=1, initial_learning
     (dropout_rate, mask_shape, old_model_path, ... — train_fetal.py:33-39) are swallowed like there."""
     if tuple(pool_size) != (2, 2, 2):
         raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2,2)" % (pool_size,))
-    if deconvolution:
-        raise NotImplementedError("deconvolution=True (Deconvolution3D) is on the §8 'next' list")
     if batch_normalization:
         raise NotImplementedError("batch_normalization=True is on the §8 'next' list")
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
-                 device=kargs.get("device"))
+                 device=kargs.get("device"), deconvolution=deconvolution)
 
 
 def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_rate=0.00001, deconvolution=False,
@@ -420,14 +425,14 @@ def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_ra
     masks from the library's counter-based hash, `dropout_seed` kwarg)."""
     if tuple(pool_size) != (2, 2):
         raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2)" % (pool_size,))
-    if deconvolution or batch_normalization:
-        raise NotImplementedError("deconvolution / batch_normalization are on the §8 'next' list")
+    if batch_normalization:
+        raise NotImplementedError("batch_normalization=True is on the §8 'next' list")
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
                  device=kargs.get("device"), ndim=2, dropout_rate=dropout_rate or 0.0,
-                 dropout_seed=kargs.get("dropout_seed", 0x5EED))
+                 dropout_seed=kargs.get("dropout_seed", 0x5EED), deconvolution=deconvolution)
 
 
 def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, depth=5, dropout_rate=0.3,

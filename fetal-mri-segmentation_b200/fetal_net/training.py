@@ -167,6 +167,7 @@ def load_old_model(model_file, verbose=True, config=None):
         cfg = [int(v) for v in z["__config__"]]
         builder_name = str(z["__builder__"]) if "__builder__" in z.files else None
         levels = int(z["__isensee_levels__"]) if "__isensee_levels__" in z.files else 0
+        deconv = bool(int(z["__deconvolution__"])) if "__deconvolution__" in z.files else False
     loss = _metrics.dice_coefficient_loss
     lr = 1e-5
     if config is not None:
@@ -176,6 +177,8 @@ def load_old_model(model_file, verbose=True, config=None):
         builder_name = 'unet_model_3d' if len(cfg) == 7 else 'unet_model_2d'   # (C,X,Y,Z) vs (H,W,D)
     kwargs = dict(input_shape=tuple(cfg[:-3]), depth=cfg[-3], n_base_filters=cfg[-2], n_labels=cfg[-1],
                   initial_learning_rate=lr, loss_function=loss)
+    if deconv:
+        kwargs['deconvolution'] = True
     if builder_name in ('isensee2017_model_3d', 'isensee2017_model'):
         kwargs['n_segmentation_levels'] = levels
         if builder_name == 'isensee2017_model':     # the 2D builder: `levels` heads reach the output only when summed

@@ -77,6 +77,16 @@ typedef struct fm_unet3d_spec {
 int fm_model_create_unet3d(fm_ctx* ctx, const fm_unet3d_spec* spec, fm_model** out);
 int fm_model_destroy(fm_model* m);
 
+/* Builder switches of unet_model_3d / unet_model_2d beyond the spec (unet3d/unet.py:17-20, unet/unet.py:22-25).
+ * FM_UNET_DECONVOLUTION: deconvolution=True - get_up_convolution returns Deconvolution3D / Deconvolution2D(filters =
+ * channels of the coarse tensor, kernel_size 2, strides 2) instead of UpSampling (unet3d/unet.py:57-59,132-136). The
+ * layer table then holds an "up<d>" layer in front of every "dec<d>a"; its kernel has the Keras Conv3DTranspose
+ * layout (2,2,2,Cout,Cin). It runs as ONE 1x1x1 tensor-core convolution to (8 x C) channels (4 x C in 2D) - a k = 2,
+ * s = 2 transposed convolution writes every output voxel from exactly one input voxel - plus a depth-to-space
+ * shuffle; backward is the reverse shuffle, a 1x1x1 wgrad and a 1x1x1 dgrad. */
+#define FM_UNET_DECONVOLUTION 1
+int fm_model_create_unet3d_ex(fm_ctx* ctx, const fm_unet3d_spec* spec, int flags, fm_model** out);
+
 /* Builder spec of the 2D / "2.5D" U-Net. Replaces the kwargs of unet_model_2d
  * (fetal_net/model/unet/unet.py:22-25): input_shape=(H,W,in_channels) with the slices (and the previous-slice
  * truth, fetal_net/generator.py:305-306) as channels; Permute + Conv2D/MaxPooling2D/UpSampling2D stack. */
@@ -92,6 +102,7 @@ typedef struct fm_unet2d_spec {
  * output [B,H,W,n_labels] (the Permute((3,1,2)) / Permute((2,3,1)) pair of the reference is a layout no-op here:
  * device tensors are channels-last). All entry points below accept either model kind. */
 int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec, fm_model** out);
+int fm_model_create_unet2d_ex(fm_ctx* ctx, const fm_unet2d_spec* spec, int flags, fm_model** out);
 
 /* Builder spec of the Isensee-2017 residual 3D U-Net. Replaces the kwargs of isensee2017_model_3d
  * (fetal_net/model/unet3d/isensee2017.py:15-18). Inference and training (every fm_predict* / fm_patchwise_predict* /

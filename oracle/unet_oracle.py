@@ -28,8 +28,10 @@ import torch.nn.functional as F
 # layer tables
 # ----------------------------------------------------------------------------------------------
 
-def unet3d_layers(depth=4, n_base_filters=32, in_channels=1, n_labels=1):
-    """[(name, cin, cout, k)] in Keras creation order (unet3d/unet.py:45-68)."""
+def unet3d_layers(depth=4, n_base_filters=32, in_channels=1, n_labels=1, deconvolution=False):
+    """[(name, cin, cout, k)] in Keras creation order (unet3d/unet.py:45-68). deconvolution=True adds the
+    Deconvolution3D(filters = channels of the coarse tensor, kernel 2, strides 2) layers "up<d>" (unet.py:57-59,
+    132-136), created before the block that consumes them; their Keras kernel is (2,2,2,Cout,Cin)."""
     layers = []
     c = in_channels
     skips = []
@@ -42,6 +44,8 @@ def unet3d_layers(depth=4, n_base_filters=32, in_channels=1, n_labels=1):
         c = f2
     for d in range(depth - 2, -1, -1):
         f = skips[d]
+        if deconvolution:
+            layers.append(("up%d" % d, c, c, 2))
         layers.append(("dec%da" % d, c + f, f, 3))
         layers.append(("dec%db" % d, f, f, 3))
         c = f
@@ -92,7 +96,11 @@ def unet3d_forward(x, w, depth=4, return_logits=False, quant=None):
         if d < depth - 1:
             cur = F.max_pool3d(cur, 2)
     for d in range(depth - 2, -1, -1):
-        up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
+        if ("up%d/kernel" % d) in w:                   # Deconvolution3D: Keras kernel (2,2,2,Cout,Cin), bias, no activation
+            kt = torch.as_tensor(w["up%d/kernel" % d]).to(dt).permute(4, 3, 0, 1, 2).contiguous()
+            up = q(F.conv_transpose3d(cur, q(kt), torch.as_tensor(w["up%d/bias" % d]).to(dt), stride=2))
+        else:
+            up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3).repeat_interleave(2, 4)
         cur = torch.cat([up, skips[d]], dim=1)          # unet3d/unet.py:61: [up, skip]
         cur = cb(cur, "dec%da" % d)
         cur = cb(cur, "dec%db" % d)
@@ -130,10 +138,14 @@ def binary_accuracy(t, p):
     return (t == torch.round(p)).to(p.dtype).mean()
 
 
-def binary_crossentropy(t, p, eps=1e-7):
+def binary_crossentropy(t, p):
     """Keras K.binary_crossentropy (TF backend, from_logits=False): p clipped to [eps, 1-eps], turned into a logit and
-    passed to sigmoid_cross_entropy_with_logits == -(t log p + (1-t) log(1-p)) on the clipped p."""
-    pc = p.clamp(eps, 1.0 - eps)
+    passed to sigmoid_cross_entropy_with_logits == -(t log p + (1-t) log(1-p)) on the clipped p. Keras forms eps and
+    1 - eps in the tensor's dtype, float32: the upper bound is float32(1) - float32(1e-7) = 1 - 2^-23 (0.99999988),
+    not 1 - 1e-7 - which caps the per-voxel loss at 15.94, not 16.12."""
+    lo = float(np.float32(1e-7))
+    hi = float(np.float32(1.0) - np.float32(1e-7))
+    pc = p.clamp(lo, hi)
     return -(t * torch.log(pc) + (1.0 - t) * torch.log1p(-pc))
 
 
@@ -375,8 +387,8 @@ def isensee2d_forward(x, w, depth=5, n_heads=1, return_logits=False, drop=None):
 # 2D / 2.5D U-Net (model/unet/unet.py:49-85) — forward only
 # ----------------------------------------------------------------------------------------------
 
-def unet2d_layers(depth=4, n_base_filters=32, in_channels=6, n_labels=1):
-    return unet3d_layers(depth, n_base_filters, in_channels, n_labels)
+def unet2d_layers(depth=4, n_base_filters=32, in_channels=6, n_labels=1, deconvolution=False):
+    return unet3d_layers(depth, n_base_filters, in_channels, n_labels, deconvolution)
 
 
 def library_dropout_scales(n, rate, seed):
@@ -417,7 +429,11 @@ def unet2d_forward(x, w, depth=4, return_logits=False, drop=None):
         if d < depth - 1:
             cur = F.max_pool2d(cur, 2)
     for d in range(depth - 2, -1, -1):
-        up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3)
+        if ("up%d/kernel" % d) in w:                   # Deconvolution2D: Keras kernel (2,2,Cout,Cin)
+            kt = torch.as_tensor(w["up%d/kernel" % d]).to(dt).permute(3, 2, 0, 1).contiguous()
+            up = F.conv_transpose2d(cur, kt, torch.as_tensor(w["up%d/bias" % d]).to(dt), stride=2)
+        else:
+            up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3)
         cur = torch.cat([up, skips[d]], dim=1)
         cur = cb(dr(cb(cur, "dec%da" % d), "dec%d" % d), "dec%db" % d)
     k, b = _tw(w, "final", dt)

@@ -335,7 +335,8 @@ def dice_xent_case(ctx, with_mask, seed=15):
     w = np.exp(-mask.astype(np.float64) / sigma) if with_mask else np.ones(n)
     xent_ref = float((torch.as_tensor(w) * uo.binary_crossentropy(tt, pt.detach())).sum())
     e1 = abs(sums[8] - xent_ref) / abs(xent_ref)
-    e2 = abs((-(2 * sums[0] + 1) / (sums[1] + sums[2] + 1) + xw * sums[8] / sums[7]) - float(loss)) / abs(float(loss))
+    lref = float(loss.detach())
+    e2 = abs((-(2 * sums[0] + 1) / (sums[1] + sums[2] + 1) + xw * sums[8] / sums[7]) - lref) / abs(lref)
     e3 = rel_err(g, gref)
     # fp32 log / exp per voxel, fp32 partial sums then fp64: 2e-6 on the sums; 2e-5 on the gradient
     return e1 <= 2e-6 and e2 <= 2e-6 and e3 <= 2e-5, max(e1 / 2e-6, e2 / 2e-6, e3 / 2e-5)

@@ -577,3 +577,84 @@ def test_isensee2d_dropout_and_patchwise():
     out = patch_wise_prediction(a, vol, patch_shape=(32, 32, 5), overlap_factor=0.5, batch_size=4)
     ref = po.patch_wise_prediction(a, vol, (32, 32, 5), overlap_factor=0.5, batch_size=4)
     assert out.shape == (48, 32, 9, 1) and np.array_equal(out, ref)
+
+
+# ---- deconvolution=True: Deconvolution3D / Deconvolution2D instead of UpSampling (unet3d/unet.py:57-59,132-136) ---------
+
+def _unet_grad_check(model, ref_grads, floor_first=0.95):
+    bad = []
+    grads = model.get_gradients()
+    for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
+        for kind, g in (("kernel", gk), ("bias", gb)):
+            r = ref_grads["%s/%s" % (l["name"], kind)].astype(np.float64).ravel()
+            g = g.astype(np.float64).ravel()
+            cos = float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
+            ratio = float(np.linalg.norm(g) / max(np.linalg.norm(r), 1e-300))
+            floor = floor_first if l["name"] in ("enc0a", "enc0b") else 0.99
+            if not (cos >= floor and 0.9 <= ratio <= 1.1):
+                bad.append((l["name"], kind, round(cos, 4), round(ratio, 4)))
+    return bad
+
+
+def test_unet3d_deconvolution_matches_oracle():
+    from fetal_net.model import unet_model_3d
+    layers = uo.unet3d_layers(4, 16, deconvolution=True)
+    w = decisive_weights(layers, seed=4)
+    for d in range(3):                                            # a linear layer: keep the variance (fan-in = C per class)
+        w["up%d/kernel" % d] = (w["up%d/kernel" % d] * 2.0).astype(np.float32)
+    model = unet_model_3d(input_shape=(1, 32, 32, 32), n_base_filters=16, depth=4, initial_learning_rate=1e-4,
+                          deconvolution=True)
+    assert [l["name"] for l in model.layers] == [n for n, *_ in layers]
+    up2 = [l for l in model.layers if l["name"] == "up2"][0]
+    assert up2["kshape"] == (2, 2, 2, 256, 256) and up2["keras_name"] == "conv3d_transpose_1"
+    assert [l["keras_name"] for l in model.layers if l["name"] in ("dec2a", "final")] == ["conv3d_9", "conv3d_15"]
+    assert model.count_params() == sum(v.size for v in w.values())
+    model.set_named_weights(w)
+    assert np.array_equal(model.get_weights()[2 * up2["index"]], w["up2/kernel"])
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32)
+    t = blob_target(x.shape, rng)
+    with torch.no_grad():
+        ref = uo.unet3d_forward(torch.as_tensor(x), w).numpy()
+    p = model.predict(x)
+    lg = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    err = np.linalg.norm(lg(p) - lg(ref)) / np.linalg.norm(lg(ref))
+    soft = (2 * (p * ref).sum() + 1) / ((p * p).sum() + (ref * ref).sum() + 1)
+    assert err <= 0.03 and np.abs(p - ref).mean() <= 0.006 and soft >= 0.999, (err, soft)
+    refstep = uo.unet3d_train_step(x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-4)
+    got = model.train_on_batch(x, t)
+    assert got[0] == pytest.approx(refstep["loss"], abs=3e-3), (got, refstep["loss"])
+    bad = _unet_grad_check(model, refstep["grads"])
+    assert not bad, bad
+
+
+def test_unet2d_deconvolution_matches_oracle():
+    from fetal_net.model import unet_model_2d
+    depth, nf = 3, 32
+    layers = uo.unet2d_layers(depth, nf, 6, deconvolution=True)
+    w = uo.glorot_uniform_weights(layers, seed=9, ndim=2)
+    rng = np.random.default_rng(10)
+    for k in w:
+        if k.endswith("/kernel"):
+            w[k] = (w[k] * (2.0 if k.startswith("up") else np.sqrt(2.0) * 1.2)).astype(np.float32)
+        else:
+            w[k] = (0.05 * rng.standard_normal(w[k].shape)).astype(np.float32)
+    model = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=nf, depth=depth, initial_learning_rate=1e-4,
+                          deconvolution=True)
+    assert [l["name"] for l in model.layers] == [n for n, *_ in layers]
+    assert [l["kshape"] for l in model.layers if l["name"] == "up0"] == [(2, 2, 64, 64)]
+    model.set_named_weights(w)
+    x = rng.standard_normal((2, 32, 32, 6)).astype(np.float32)
+    t = (rng.random((2, 32, 32, 1)) < 0.3).astype(np.float32)
+    fwd = lambda xt, prm: uo.unet2d_forward(xt, prm, depth=depth)
+    with torch.no_grad():
+        ref = fwd(torch.as_tensor(x), w).numpy()
+    p = model.predict(x)
+    lg = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    err = np.linalg.norm(lg(p) - lg(ref)) / np.linalg.norm(lg(ref))
+    assert err <= 0.03 and np.abs(p - ref).mean() <= 0.006, err
+    refstep = uo.train_step(fwd, x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-4)
+    got = model.train_on_batch(x, t)
+    assert got[0] == pytest.approx(refstep["loss"], abs=3e-3), (got, refstep["loss"])
+    bad = _unet_grad_check(model, refstep["grads"])
+    assert not bad, bad

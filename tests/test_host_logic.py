@@ -441,7 +441,7 @@ def test_dice_and_xent_host_helpers_and_device_loss_spec():
     p.ravel()[:3] = [0.0, 1.0, 1e-9]                                 # the Keras clip at 1e-7 is active
     t = (rng.random(p.shape) < 0.4).astype(np.float32)
     mask = (5 * rng.random(p.shape)).astype(np.float32)
-    pc = torch.as_tensor(p, dtype=torch.float64).clamp(1e-7, 1 - 1e-7)
+    pc = torch.as_tensor(p, dtype=torch.float64).clamp(float(np.float32(1e-7)), float(np.float32(1) - np.float32(1e-7)))
     bce = F.binary_cross_entropy(pc, torch.as_tensor(t, dtype=torch.float64), reduction="none")
     want = fm.dice_coefficient_loss(t, p) + 0.5 * float(bce.mean())
     assert fm.dice_and_xent(t, p, xent_weight=0.5) == pytest.approx(want, rel=1e-12)
