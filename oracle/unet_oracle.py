@@ -406,22 +406,30 @@ def library_dropout_scales(n, rate, seed):
         .astype(np.float32)
 
 
-def unet2d_forward(x, w, depth=4, return_logits=False, drop=None):
+def bf16_round(t):
+    """Storage model of the CUDA path: every stored activation / weight is rounded to bfloat16 on the way forward and
+    the gradient flowing back through the same point is rounded too (the cast is differentiable: autograd casts the
+    incoming gradient to bfloat16 and back) - the CUDA path keeps activations AND their gradients in bf16."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def unet2d_forward(x, w, depth=4, return_logits=False, drop=None, quant=None):
     """x: [B,H,W,D] (slices-as-channels, Keras input layout) -> [B,H,W,n_labels]. `drop` (training with
     SpatialDropout2D, unet/unet.py:60-61,76-77): {'enc<d>' / 'dec<d>': scale [B,C]} applied behind the first block of
     the level."""
     dt = x.dtype
-    cur = x.permute(0, 3, 1, 2)                      # Permute((3,1,2))
+    q = quant if quant is not None else (lambda t: t)
+    cur = q(x.permute(0, 3, 1, 2))                   # Permute((3,1,2))
     skips = []
 
     def cb(t, name):
         k, b = _tw(w, name, dt)
-        return F.relu(F.conv2d(t, k, b, padding=1))
+        return q(F.relu(F.conv2d(t, q(k), b, padding=1)))
 
     def dr(t, key):
         if drop is None or key not in drop:
             return t
-        return t * torch.as_tensor(drop[key]).to(dt)[:, :, None, None]
+        return q(t * torch.as_tensor(drop[key]).to(dt)[:, :, None, None])
 
     for d in range(depth):
         cur = cb(dr(cb(cur, "enc%da" % d), "enc%d" % d), "enc%db" % d)
@@ -431,7 +439,7 @@ def unet2d_forward(x, w, depth=4, return_logits=False, drop=None):
     for d in range(depth - 2, -1, -1):
         if ("up%d/kernel" % d) in w:                   # Deconvolution2D: Keras kernel (2,2,Cout,Cin)
             kt = torch.as_tensor(w["up%d/kernel" % d]).to(dt).permute(3, 2, 0, 1).contiguous()
-            up = F.conv_transpose2d(cur, kt, torch.as_tensor(w["up%d/bias" % d]).to(dt), stride=2)
+            up = q(F.conv_transpose2d(cur, q(kt), torch.as_tensor(w["up%d/bias" % d]).to(dt), stride=2))
         else:
             up = cur.repeat_interleave(2, 2).repeat_interleave(2, 3)
         cur = torch.cat([up, skips[d]], dim=1)

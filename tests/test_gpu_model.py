@@ -581,18 +581,26 @@ def test_isensee2d_dropout_and_patchwise():
 
 # ---- deconvolution=True: Deconvolution3D / Deconvolution2D instead of UpSampling (unet3d/unet.py:57-59,132-136) ---------
 
-def _unet_grad_check(model, ref_grads, floor_first=0.95):
+def _cos(g, r):
+    g, r = g.astype(np.float64).ravel(), r.astype(np.float64).ravel()
+    return float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
+
+
+def _unet_grad_check(model, ref_grads, bf16_grads):
+    """Per-layer gradient direction against the fp32 oracle. The yardstick is the storage format: `bf16_grads` are the
+    gradients of the SAME fp32 oracle with its stored activations / weights rounded to bfloat16; a layer must reach
+    min(0.99, that oracle's own cosine against fp32 - 0.01), and the norm must agree within 10 %."""
     bad = []
     grads = model.get_gradients()
     for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
         for kind, g in (("kernel", gk), ("bias", gb)):
-            r = ref_grads["%s/%s" % (l["name"], kind)].astype(np.float64).ravel()
-            g = g.astype(np.float64).ravel()
-            cos = float(g @ r / max(np.linalg.norm(g) * np.linalg.norm(r), 1e-300))
-            ratio = float(np.linalg.norm(g) / max(np.linalg.norm(r), 1e-300))
-            floor = floor_first if l["name"] in ("enc0a", "enc0b") else 0.99
+            name = "%s/%s" % (l["name"], kind)
+            r = ref_grads[name]
+            cos = _cos(g, r)
+            floor = min(0.99, _cos(bf16_grads[name], r) - 0.01)
+            ratio = float(np.linalg.norm(g.astype(np.float64)) / max(np.linalg.norm(r.astype(np.float64)), 1e-300))
             if not (cos >= floor and 0.9 <= ratio <= 1.1):
-                bad.append((l["name"], kind, round(cos, 4), round(ratio, 4)))
+                bad.append((name, round(cos, 4), round(floor, 4), round(ratio, 4)))
     return bad
 
 
@@ -622,9 +630,10 @@ def test_unet3d_deconvolution_matches_oracle():
     soft = (2 * (p * ref).sum() + 1) / ((p * p).sum() + (ref * ref).sum() + 1)
     assert err <= 0.03 and np.abs(p - ref).mean() <= 0.006 and soft >= 0.999, (err, soft)
     refstep = uo.unet3d_train_step(x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-4)
+    bfstep = uo.unet3d_train_step(x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-4, quant=uo.bf16_round)
     got = model.train_on_batch(x, t)
     assert got[0] == pytest.approx(refstep["loss"], abs=3e-3), (got, refstep["loss"])
-    bad = _unet_grad_check(model, refstep["grads"])
+    bad = _unet_grad_check(model, refstep["grads"], bfstep["grads"])
     assert not bad, bad
 
 
@@ -642,7 +651,7 @@ def test_unet2d_deconvolution_matches_oracle():
     model = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=nf, depth=depth, initial_learning_rate=1e-4,
                           deconvolution=True)
     assert [l["name"] for l in model.layers] == [n for n, *_ in layers]
-    assert [l["kshape"] for l in model.layers if l["name"] == "up0"] == [(2, 2, 64, 64)]
+    assert [l["kshape"] for l in model.layers if l["name"] == "up0"] == [(2, 2, 128, 128)]   # channels of dec1b
     model.set_named_weights(w)
     x = rng.standard_normal((2, 32, 32, 6)).astype(np.float32)
     t = (rng.random((2, 32, 32, 1)) < 0.3).astype(np.float32)
@@ -654,7 +663,9 @@ def test_unet2d_deconvolution_matches_oracle():
     err = np.linalg.norm(lg(p) - lg(ref)) / np.linalg.norm(lg(ref))
     assert err <= 0.03 and np.abs(p - ref).mean() <= 0.006, err
     refstep = uo.train_step(fwd, x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-4)
+    bfstep = uo.train_step(lambda xt, prm: uo.unet2d_forward(xt, prm, depth=depth, quant=uo.bf16_round), x, t,
+                           {k: v.copy() for k, v in w.items()}, {}, 1e-4)
     got = model.train_on_batch(x, t)
     assert got[0] == pytest.approx(refstep["loss"], abs=3e-3), (got, refstep["loss"])
-    bad = _unet_grad_check(model, refstep["grads"])
+    bad = _unet_grad_check(model, refstep["grads"], bfstep["grads"])
     assert not bad, bad
