@@ -213,7 +213,10 @@ struct Layer {
   bf16 *w_up_f = nullptr, *w_up_d = nullptr;
   float* dw_up = nullptr;
   int cin_real = 0;     // true input channels when c1 is zero-padded to 16 (first layer of the 2.5D U-Net)
-  int is_norm = 0;      // InstanceNormalization pseudo-layer of the Isensee net: kernel = gamma, bias = beta (cout each)
+  // 1: normalisation pseudo-layer (InstanceNormalization of the Isensee nets, BatchNormalization of a U-Net built with
+  // batch_normalization=True): kernel = gamma, bias = beta (cout each). 2: the BatchNormalization's non-trainable
+  // moving statistics: kernel = moving_mean, bias = moving_variance (zero gradient; updated by the forward pass)
+  int is_norm = 0;
   int stride = 1;       // 2: TF-'SAME' strided conv (Isensee in-convs)
   int deconv = 0;       // Deconvolution3D/2D (k = 2 or 21, stride 2): master kernel [class][Cout][Cin] = the Keras layout
   int cin() const { return c1 + c2; }
@@ -257,6 +260,13 @@ struct fm_model {
   // shuffle, and the shuffled gradient on the way back
   bool deconvolution = false;
   DevBuf<bf16> dcZ, dcG;
+  // batch_normalization=True (create_convolution_block, unet3d/unet.py:103-104): every conv block is Conv -> BN -> ReLU.
+  // Raw conv outputs + batch statistics per layer (training), one raw scratch (inference), the gradient of a raw output
+  bool batch_norm = false;
+  std::vector<DevBuf<bf16>> bnRawL;
+  std::vector<DevBuf<float>> bnStatsL;
+  DevBuf<bf16> bnRaw, bnGRaw;
+  DevBuf<float> bnScratch;
   bool unet_dropout() const { return kind == 0 && kcode == 31 && dropout_rate > 0.f; }
   int kcode = 3;  // 3: Conv3D 3x3x3 (unet_model_3d); 31: Conv2D 3x3 on a Z = 1 volume (unet_model_2d)
   int pz = 2;     // pooling factor along z
@@ -364,7 +374,8 @@ extern "C" int fm_model_create_unet2d(fm_ctx* ctx, const fm_unet2d_spec* spec2, 
 
 extern "C" int fm_model_create_unet3d_ex(fm_ctx* ctx, const fm_unet3d_spec* spec, int flags, fm_model** out) {
   FM_CHECK(ctx && spec && out, FM_EINVAL, "fm_model_create_unet3d: NULL argument");
-  FM_CHECK((flags & ~FM_UNET_DECONVOLUTION) == 0, FM_EINVAL, "fm_model_create_unet3d_ex: unknown flags 0x%x", flags);
+  FM_CHECK((flags & ~(FM_UNET_DECONVOLUTION | FM_UNET_BATCH_NORMALIZATION)) == 0, FM_EINVAL,
+           "fm_model_create_unet3d_ex: unknown flags 0x%x", flags);
   FM_CHECK(spec->in_channels == 1, FM_EINVAL,
            "in_channels=%d: only the reference's single-modality path (1) is built", spec->in_channels);
   const int div = 1 << (spec->depth > 0 ? spec->depth - 1 : 0);
@@ -377,7 +388,8 @@ extern "C" int fm_model_create_unet3d_ex(fm_ctx* ctx, const fm_unet3d_spec* spec
 
 extern "C" int fm_model_create_unet2d_ex(fm_ctx* ctx, const fm_unet2d_spec* spec2, int flags, fm_model** out) {
   FM_CHECK(ctx && spec2 && out, FM_EINVAL, "fm_model_create_unet2d: NULL argument");
-  FM_CHECK((flags & ~FM_UNET_DECONVOLUTION) == 0, FM_EINVAL, "fm_model_create_unet2d_ex: unknown flags 0x%x", flags);
+  FM_CHECK((flags & ~(FM_UNET_DECONVOLUTION | FM_UNET_BATCH_NORMALIZATION)) == 0, FM_EINVAL,
+           "fm_model_create_unet2d_ex: unknown flags 0x%x", flags);
   FM_CHECK(spec2->in_channels >= 1 && spec2->in_channels <= 16, FM_EINVAL,
            "in_channels=%d: the slices-as-channels input supports 1..16 channels", spec2->in_channels);
   const int div = 1 << (spec2->depth > 0 ? spec2->depth - 1 : 0);
@@ -407,6 +419,7 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int fl
   m->pz = kcode == 31 ? 1 : 2;
   m->cin_real = spec->in_channels;
   m->deconvolution = (flags & FM_UNET_DECONVOLUTION) != 0;
+  m->batch_norm = (flags & FM_UNET_BATCH_NORMALIZATION) != 0;
   const int D = spec->depth, nf = spec->n_base_filters;
   auto add = [&](const char* fmt, int d, int c1, int c2, int cout, int k, int level) {
     Layer l;
@@ -424,6 +437,25 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int fl
     // keep every layer's block 16-byte aligned for the vectorised Adam / allreduce views
     m->nparams = (m->nparams + 3) & ~(int64_t)3;
     m->layers.push_back(l);
+    if (m->batch_norm && (k == 3 || k == 31)) {
+      // BatchNormalization(axis=1) behind the conv of every block: (gamma, beta) and (moving_mean, moving_variance)
+      for (int kind = 1; kind <= 2; ++kind) {
+        Layer g;
+        memset(g.name, 0, sizeof(g.name));
+        snprintf(g.name, sizeof(g.name), kind == 1 ? "%s_norm" : "%s_moving", l.name);
+        g.is_norm = kind;
+        g.c1 = cout;
+        g.c2 = 0;
+        g.cout = cout;
+        g.k = 1;
+        g.level = level;
+        g.w_off = m->nparams;
+        m->nparams += cout;
+        g.b_off = m->nparams;
+        m->nparams = (m->nparams + cout + 3) & ~(int64_t)3;
+        m->layers.push_back(g);
+      }
+    }
   };
   // the 2D model feeds its first conv from a 16-channel zero-padded copy of the input (tensor-core K granule)
   int c = kcode == 31 ? 16 : spec->in_channels;
@@ -473,7 +505,7 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int fl
     wp += padded;
   }
   for (auto& l : m->layers) {
-    if (l.k != 3 || l.c1 < 16) continue;
+    if (l.is_norm || l.k != 3 || l.c1 < 16) continue;
     const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = m->pz == 2 ? spec->Z >> l.level : spec->Z;
     const int cs[2] = {l.c1, l.c2};
     if (use_march() && conv_march_supported(X, Y, Z, l.c1, l.c2, l.cout, l.k)) {
@@ -490,7 +522,9 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int fl
   // decoder convs whose filter bank is too large for the marching kernel run at COARSE resolution on their upsampled
   // source (dec1a, dec2a of the shipped model); FETAL_B200_NO_UP_COARSE=1 keeps the materialised upsampling
   for (auto& l : m->layers) {
-    if (strncmp(l.name, "dec", 3) != 0 || l.c2 == 0 || l.k != 3 || m->pz != 2 || m->deconvolution) continue;
+    if (strncmp(l.name, "dec", 3) != 0 || l.c2 == 0 || l.k != 3 || m->pz != 2 || m->deconvolution || m->batch_norm ||
+        l.is_norm)
+      continue;
     const char* e = getenv("FETAL_B200_NO_UP_COARSE");
     if (e && e[0] == '1') continue;
     const int X = spec->X >> l.level, Y = spec->Y >> l.level, Z = spec->Z >> l.level;
@@ -523,6 +557,8 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int fl
   m->gSkip.resize(D);
   m->gDecA.resize(D);
   m->gDecB.resize(D);
+  m->bnRawL.resize(m->layers.size());
+  m->bnStatsL.resize(m->layers.size());
   m->layer_done.resize(m->layers.size());
   for (auto& e : m->layer_done) FM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   FM_CUDA(cudaEventCreateWithFlags(&m->ev_tmp, cudaEventDisableTiming));
@@ -571,7 +607,7 @@ extern "C" int fm_model_destroy(fm_model* m) {
   for (auto& b : m->isSeg) b.release();
   for (auto* v : {&m->isRawL, &m->gIsA, &m->gIsB, &m->gIsC, &m->gIsUp})
     for (auto& b : *v) b.release();
-  for (auto* v : {&m->isStatsL, &m->isDropL, &m->gSeg, &m->dropU})
+  for (auto* v : {&m->isStatsL, &m->isDropL, &m->gSeg, &m->dropU, &m->bnStatsL})
     for (auto& b : *v) b.release();
   m->gIsRaw.release();
   m->gIsZero.release();
@@ -584,6 +620,10 @@ extern "C" int fm_model_destroy(fm_model* m) {
   m->pw_out.release();
   m->pw_cnt.release();
   m->x_in.release();
+  m->bnRaw.release();
+  m->bnGRaw.release();
+  m->bnScratch.release();
+  for (auto& b : m->bnRawL) b.release();
   m->dcZ.release();
   m->dcG.release();
   m->mask_in.release();
@@ -628,7 +668,8 @@ extern "C" int fm_model_layer_info(fm_model* m, int layer, char name[32], int64_
   if (info) {
     info[0] = l.cin_keras();
     info[1] = l.cout;
-    info[2] = l.is_norm ? 0 : kext_xy(l.k) * 10 + kext_z(l.k);  // 33: 3x3x3, 31: 3x3(x1), 11: 1x1x1, 0: norm (gamma, beta)
+    // 33: 3x3x3, 31: 3x3(x1), 22 / 21: deconvolution, 11: 1x1x1, 0: norm (gamma, beta), -1: BN moving (mean, variance)
+    info[2] = l.is_norm == 2 ? -1 : (l.is_norm ? 0 : kext_xy(l.k) * 10 + kext_z(l.k));
     info[3] = l.w_off;
     info[4] = l.b_off;
   }
@@ -855,6 +896,23 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
       FM_TRY(m->decB[d].ensure(v * db.cout));
     }
   }
+  if (m->batch_norm) {
+    size_t biggest = 0, cmax = 0;
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+      const Layer& l = m->layers[i];
+      if (l.is_norm != 1) continue;
+      const size_t n = (size_t)cap * m->vox(l.level) * l.cout;
+      biggest = std::max(biggest, n);
+      cmax = std::max(cmax, (size_t)l.cout);
+      if (train || m->train_alloc) {
+        FM_TRY(m->bnRawL[i].ensure(n));
+        FM_TRY(m->bnStatsL[i].ensure((size_t)cap * l.cout * 2));
+      }
+    }
+    FM_TRY(m->bnRaw.ensure(biggest));
+    if (train || m->train_alloc) FM_TRY(m->bnGRaw.ensure(biggest));
+    FM_TRY(m->bnScratch.ensure((size_t)cap * cmax * 2 * 1030));
+  }
   if (train || m->train_alloc) {
     FM_TRY(m->t_in.ensure((size_t)cap * v0));  // (no dL/dz tensor: the head backward forms the Dice gradient itself)
     for (int d = 0; d < D; ++d) {
@@ -879,18 +937,83 @@ static int ensure_capacity(fm_model* m, int B, bool train) {
 }
 
 // conv block forward: Conv3D + bias + ReLU (create_convolution_block, unet.py:102-113)
-static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2, bf16* y, int B) {
+static int conv_fwd(fm_model* m, const Layer& l, const bf16* x1, const bf16* x2, bf16* y, int B, int relu = 1) {
   fm_ctx* ctx = m->ctx;
   const Dims5 d = m->dims(l.level, l.cout, B);
   const float* bias = m->params + l.b_off;
   if (l.march_f)
     return (shared_march(m, l.cout) ? k_conv3d_march_shared : k_conv3d_march)(
-        ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, 1, l.cout, 0);
+        ctx, x1, x2, l.w_mf[0], l.w_mf[1], bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout, relu, l.cout, 0);
   if (conv_tc_supported(l.c1, l.c2, l.cout, l.k))
     return k_conv3d_tc_fprop(ctx, x1, x2, l.w_f, bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2, l.cout,
-                             l.k, 1, l.cout, 0);
+                             l.k, relu, l.cout, 0);
   return k_conv3d_simt_fprop(ctx, x1, 0, x2, l.w_f, bias, y, nullptr, B, d.X, d.Y, d.Z, l.c1, l.c2,
-                             l.cout, l.k, 1, nullptr);
+                             l.cout, l.k, relu, nullptr);
+}
+
+// one conv block of a U-Net built with batch_normalization=True: Conv (+bias, no activation) -> raw ->
+// BatchNormalization + ReLU -> y. A training pass keeps the raw output and the batch statistics of every block.
+static int bn_block_fwd(fm_model* m, const Layer& l, const void* x1, int x1_f32, const bf16* x2, bf16* y, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int li = (int)(&l - &m->layers[0]);
+  const Layer &nl = m->layers[li + 1], &ml = m->layers[li + 2];
+  const Dims5 d = m->dims(l.level, l.cout, B);
+  bf16* raw = m->train_pass ? m->bnRawL[li + 1].p : m->bnRaw.p;
+  if (x1_f32)  // the first conv of the 3D model reads the fp32 single-channel input
+    FM_TRY(k_conv3d_simt_fprop(ctx, x1, 1, nullptr, l.w_f, m->params + l.b_off, raw, nullptr, B, d.X, d.Y, d.Z, l.c1, 0,
+                               l.cout, l.k, 0, nullptr));
+  else
+    FM_TRY(conv_fwd(m, l, (const bf16*)x1, x2, raw, B, 0));
+  return k_batchnorm_relu(ctx, raw, m->params + nl.w_off, m->params + nl.b_off, m->params + ml.w_off,
+                          m->params + ml.b_off, y, B, m->vox(l.level), l.cout, m->bnScratch.p, m->bnScratch.n,
+                          m->train_pass ? m->bnStatsL[li + 1].p : nullptr, m->train_pass ? 1 : 0);
+}
+
+static int forward_unet_bn(fm_model* m, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int D = m->depth();
+  FM_TRY(refresh_packs(m));
+  const bf16* cur = nullptr;
+  for (int d = 0; d < D; ++d) {
+    const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
+    if (d == 0 && m->kcode == 31) {
+      FM_TRY(k_pad_cast(ctx, m->x_in.p, m->x_pad.p, (int64_t)B * m->vox(0), m->cin_real, 16));
+      FM_TRY(bn_block_fwd(m, la, m->x_pad.p, 0, nullptr, m->encA[0].p, B));
+    } else if (d == 0) {
+      FM_TRY(bn_block_fwd(m, la, m->x_in.p, 1, nullptr, m->encA[0].p, B));
+    } else {
+      FM_TRY(bn_block_fwd(m, la, cur, 0, nullptr, m->encA[d].p, B));
+    }
+    FM_TRY(bn_block_fwd(m, lb, m->encA[d].p, 0, nullptr, m->encB[d].p, B));
+    cur = m->encB[d].p;
+    if (d < D - 1) {
+      FM_TRY(k_maxpool3d_fwd(ctx, m->encB[d].p, m->pool[d].p, m->dims(d, lb.cout, B), m->pz));
+      cur = m->pool[d].p;
+    }
+  }
+  for (int d = D - 2; d >= 0; --d) {
+    const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
+    if (m->deconvolution) {
+      const Layer& lu = L(m, "up%d", d);
+      const Dims5 dc = m->dims(d + 1, lu.cout, B);
+      FM_TRY(k_conv3d_tc_fprop(ctx, cur, nullptr, lu.w_f, nullptr, m->dcZ.p, nullptr, B, dc.X, dc.Y, dc.Z, lu.c1, 0,
+                               lu.cout * lu.taps(), 1, 0, lu.cout * lu.taps(), 0));
+      FM_TRY(k_depth_to_space(ctx, m->dcZ.p, m->params + lu.b_off, m->up[d].p, dc, m->pz));
+    } else {
+      FM_TRY(k_upsample3d_fwd(ctx, cur, m->up[d].p, m->dims(d + 1, da.c1, B), m->pz));
+    }
+    FM_TRY(bn_block_fwd(m, da, m->up[d].p, 0, m->encB[d].p, m->decA[d].p, B));
+    FM_TRY(bn_block_fwd(m, db, m->decA[d].p, 0, nullptr, m->decB[d].p, B));
+    cur = m->decB[d].p;
+  }
+  const Layer& lf = m->layers.back();
+  if (m->train_pass && m->targets_ready) {
+    FM_TRY(k_head_fwd_dice(ctx, cur, m->params + lf.w_off, m->params + lf.b_off, m->t_in.p, m->prob.p,
+                           (int64_t)B * m->vox(0), lf.c1, m->sums, m->xent()));
+    m->stats_done = true;
+    return FM_OK;
+  }
+  return k_head_fwd(ctx, cur, m->params + lf.w_off, m->params + lf.b_off, m->prob.p, (int64_t)B * m->vox(0), lf.c1);
 }
 
 static int forward_isensee(fm_model* m, int B);
@@ -910,6 +1033,7 @@ static int unet_dropout_fwd(fm_model* m, int slot, bf16* act, const Layer& l, in
 // forward pass on x_in (fp32 [B, X, Y, Z], C = 1) -> prob (fp32 [B, X, Y, Z])
 static int forward(fm_model* m, int B) {
   if (m->kind == 1) return forward_isensee(m, B);
+  if (m->batch_norm) return forward_unet_bn(m, B);
   fm_ctx* ctx = m->ctx;
   const int D = m->depth();
   FM_TRY(refresh_packs(m));
@@ -1035,8 +1159,90 @@ static int mark_layer_done(fm_model* m, const Layer& l) {
 
 static int backward_isensee(fm_model* m, int B);
 
+// BatchNormalization + ReLU backward of block `l` (gy [+ gy2] = gradient of the block's activation) -> m->bnGRaw, the
+// gradient of the raw conv output; gamma / beta gradients. The conv bias in front of the normalisation has an
+// analytically zero gradient (conv_wgrad still sums it: rounding noise, as in Keras).
+static int bn_block_bwd(fm_model* m, const Layer& l, const bf16* gy, const bf16* gy2, int B) {
+  const int li = (int)(&l - &m->layers[0]);
+  const Layer& nl = m->layers[li + 1];
+  FM_TRY(k_batchnorm_relu_bwd(m->ctx, m->bnRawL[li + 1].p, m->bnStatsL[li + 1].p, m->params + nl.w_off,
+                              m->params + nl.b_off, gy, gy2, m->bnGRaw.p, m->grads + nl.w_off, m->grads + nl.b_off, B,
+                              m->vox(l.level), l.cout, m->bnScratch.p, m->bnScratch.n));
+  FM_TRY(mark_layer_done(m, m->layers[li + 2]));
+  return mark_layer_done(m, nl);
+}
+
+// Backward pass of a U-Net built with batch_normalization=True: the ReLU derivative lives in the normalisation
+// backward (it is recomputed from the raw conv output and the batch statistics), so every dgrad / pooling / upsampling
+// gradient runs WITHOUT an activation mask; the decoder's upsampled source is materialised.
+static int backward_unet_bn(fm_model* m, int B) {
+  fm_ctx* ctx = m->ctx;
+  const int D = m->depth();
+  const int64_t n0 = (int64_t)B * m->vox(0);
+  FM_TRY(k_zero(ctx, m->grads, (size_t)m->nparams * sizeof(float)));
+  const Layer& lf = m->layers.back();
+  FM_TRY(k_head_bwd(ctx, m->decB[0].p, m->prob.p, m->params + lf.w_off, m->gDecB[0].p, m->grads + lf.w_off,
+                    m->grads + lf.b_off, n0, lf.c1, 1, m->t_in.p, m->sums, m->xent()));
+  FM_TRY(mark_layer_done(m, lf));
+  for (int d = 0; d <= D - 2; ++d) {
+    const Layer &da = L(m, "dec%da", d), &db = L(m, "dec%db", d);
+    FM_TRY(bn_block_bwd(m, db, m->gDecB[d].p, nullptr, B));
+    FM_TRY(conv_wgrad(m, db, m->decA[d].p, nullptr, m->bnGRaw.p, B));
+    FM_TRY(mark_layer_done(m, db));
+    FM_TRY(conv_dgrad(m, db, 0, m->bnGRaw.p, nullptr, m->gDecA[d].p, B));
+    FM_TRY(bn_block_bwd(m, da, m->gDecA[d].p, nullptr, B));
+    FM_TRY(conv_wgrad(m, da, m->up[d].p, m->encB[d].p, m->bnGRaw.p, B));
+    FM_TRY(mark_layer_done(m, da));
+    FM_TRY(conv_dgrad(m, da, 0, m->bnGRaw.p, nullptr, m->gUp[d].p, B));
+    FM_TRY(conv_dgrad(m, da, 1, m->bnGRaw.p, nullptr, m->gSkip[d].p, B));
+    const bool bottom = (d + 1 == D - 1);
+    const bf16* act = bottom ? m->encB[D - 1].p : m->decB[d + 1].p;
+    bf16* gdst = bottom ? m->gEncB[D - 1].p : m->gDecB[d + 1].p;
+    if (m->deconvolution) {
+      const Layer& lu = L(m, "up%d", d);
+      const Dims5 dc = m->dims(d + 1, lu.cout, B);
+      const int c8 = lu.cout * lu.taps();
+      FM_TRY(k_bias_grad(ctx, m->gUp[d].p, m->grads + lu.b_off, (int64_t)B * m->vox(d), lu.cout));
+      FM_TRY(k_space_to_depth(ctx, m->gUp[d].p, m->dcG.p, dc, m->pz));
+      FM_TRY(k_conv3d_tc_wgrad(ctx, act, m->dcG.p, m->grads + lu.w_off, B, dc.X, dc.Y, dc.Z, lu.c1, lu.c1, 0, c8, 1));
+      FM_TRY(mark_layer_done(m, lu));
+      FM_TRY(k_conv3d_tc_fprop(ctx, m->dcG.p, nullptr, lu.w_d0, nullptr, gdst, nullptr, B, dc.X, dc.Y, dc.Z, c8, 0, lu.c1,
+                               1, 0, lu.c1, 0));
+    } else {
+      FM_TRY(k_upsample3d_bwd(ctx, m->gUp[d].p, nullptr, gdst, m->dims(d + 1, da.c1, B), da.c1, 0, m->pz));
+    }
+  }
+  for (int d = D - 1; d >= 0; --d) {
+    const Layer &la = L(m, "enc%da", d), &lb = L(m, "enc%db", d);
+    if (d < D - 1)  // gradient of encB[d]: skip path + MaxPooling backward (no mask)
+      FM_TRY(k_maxpool3d_bwd(ctx, m->encB[d].p, m->gPool[d].p, m->gSkip[d].p, m->gEncB[d].p, m->dims(d, lb.cout, B), 0,
+                             m->pz));
+    FM_TRY(bn_block_bwd(m, lb, m->gEncB[d].p, nullptr, B));
+    FM_TRY(conv_wgrad(m, lb, m->encA[d].p, nullptr, m->bnGRaw.p, B));
+    FM_TRY(mark_layer_done(m, lb));
+    FM_TRY(conv_dgrad(m, lb, 0, m->bnGRaw.p, nullptr, m->gEncA[d].p, B));
+    FM_TRY(bn_block_bwd(m, la, m->gEncA[d].p, nullptr, B));
+    if (d > 0) {
+      FM_TRY(conv_wgrad(m, la, m->pool[d - 1].p, nullptr, m->bnGRaw.p, B));
+      FM_TRY(mark_layer_done(m, la));
+      FM_TRY(conv_dgrad(m, la, 0, m->bnGRaw.p, nullptr, m->gPool[d - 1].p, B));
+    } else if (m->kcode == 31) {
+      FM_TRY(conv_wgrad(m, la, m->x_pad.p, nullptr, m->bnGRaw.p, B));
+      FM_TRY(mark_layer_done(m, la));
+    } else {
+      const Dims5 dd = m->dims(0, la.cout, B);
+      FM_TRY(k_conv3d_simt_wgrad(ctx, m->x_in.p, 1, m->bnGRaw.p, m->grads + la.w_off, B, dd.X, dd.Y, dd.Z, la.c1, la.c1, 0,
+                                 la.cout, la.k));
+      FM_TRY(k_bias_grad(ctx, m->bnGRaw.p, m->grads + la.b_off, dd.voxels(), la.cout));
+      FM_TRY(mark_layer_done(m, la));
+    }
+  }
+  return FM_OK;
+}
+
 static int backward(fm_model* m, int B) {
   if (m->kind == 1) return backward_isensee(m, B);
+  if (m->batch_norm) return backward_unet_bn(m, B);
   fm_ctx* ctx = m->ctx;
   const int D = m->depth();
   const int64_t n0 = (int64_t)B * m->vox(0);
@@ -2259,6 +2465,9 @@ static int dp_step_after_forward(fm_model* m, float lr, float out_metrics[4]);
 
 extern "C" int fm_train_step_dp(fm_model* m, const float* x, const float* t, int batch, float lr,
                                 float out_metrics[4]) {
+  FM_CHECK(!(m && m->batch_norm), FM_EINVAL,
+           "fm_train_step_dp: batch_normalization=True needs batch statistics over the GLOBAL batch (not built): "
+           "a data-parallel step on local statistics would not equal the single-process reference");
   FM_CHECK(m && x && t && batch > 0 && out_metrics, FM_EINVAL, "fm_train_step_dp: bad argument");
   fm_ctx* ctx = m->ctx;
   if (!ctx->comm || ctx->comm_size == 1) return fm_train_step(m, x, t, batch, lr, out_metrics);

@@ -119,70 +119,85 @@ __global__ void maxpool3d_fwd_kernel(const bf16* __restrict__ x, bf16* __restric
 
 // Backward of MaxPooling3D fused with the skip-connection gradient add and the ReLU mask of the
 // producing conv block: dx = [x>0] * (dskip + [x is the first max of its window] * dy).
+// TWO threads per (pooled voxel, 8 channels): lane pair (l, l^1) = the x-halves ddx = 0 / 1 of the window. Each loads
+// its four children of x and dskip plus dy (9 x 16 B in flight per thread, all issued before the first use), finds its
+// local first maximum and swaps it with the partner by shuffle; the ddx = 0 half wins ties (= first maximum in the
+// window's k order). ~60 registers -> 4 resident blocks per SM instead of 2: the kernel is latency-bound on its loads.
 template <int pz>
-__global__ void maxpool3d_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(kThreads, 4) maxpool3d_bwd_kernel(const bf16* __restrict__ x,
+                                                                    const bf16* __restrict__ dy,
                                      const bf16* __restrict__ dskip, bf16* __restrict__ dx, int N,
                                      int X, int Y, int Z, int C, int relu_mask) {
   FM_PDL_SYNC();
   const int c8n = C >> 3;
   const int Xo = X >> 1, Yo = Y >> 1, Zo = Z / pz;
-  const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n;
+  const int64_t total = (int64_t)N * Xo * Yo * Zo * c8n * 2;
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= total) return;
-  const int c8 = (int)(g % c8n);
-  int64_t v = g / c8n;
+  const bool live = g < total;  // (total is even and blockDim is even: a lane pair is live or dead together)
+  if (!live) g = total - 2 + (threadIdx.x & 1);
+  const int half = (int)(g & 1);
+  int64_t v = g >> 1;
+  const int c8 = (int)(v % c8n);
+  v /= c8n;
   const int zo = (int)(v % Zo);
   v /= Zo;
   const int yo = (int)(v % Yo);
   v /= Yo;
   const int xo = (int)(v % Xo);
   const int n = (int)(v / Xo);
-  float xv[8][8];
-  int64_t vi[8];
+  // element offset of child j (= ddy * 2 + ddz) of this half: base + (ddy * Z + ddz) * C
+  const int64_t base = ((((int64_t)n * X + 2 * xo + half) * Y + 2 * yo) * Z + pz * zo) * C + c8 * 8;
+  const int sy = Z * C;
+#define FM_CHILD_OFS(j) (base + (((j) >> 1) * sy + ((j) & 1) * C))
+  uint4 xr[4], sk[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ddx = k >> 2, ddy = (k >> 1) & 1, ddz = k & 1;
-    vi[k] = (((int64_t)n * X + 2 * xo + ddx) * Y + 2 * yo + ddy) * Z + pz * zo + ddz;
-    if (ddz < pz) {
-      unpack8(ldg16(x + vi[k] * C + c8 * 8), xv[k]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) xv[k][c] = -INFINITY;  // pz == 1: the z-child does not exist
+  for (int j = 0; j < 4; ++j) {
+    if ((j & 1) < pz) {
+      xr[j] = ldg16(x + FM_CHILD_OFS(j));
+      sk[j] = dskip != nullptr ? ldg16(dskip + FM_CHILD_OFS(j)) : make_uint4(0u, 0u, 0u, 0u);
     }
   }
   const int64_t vo = (((int64_t)n * Xo + xo) * Yo + yo) * Zo + zo;
   float g8[8];
   unpack8(ldg16(dy + vo * C + c8 * 8), g8);
+  float best[8];
   int arg[8];
+  unpack8(xr[0], best);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) arg[c] = 0;
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {
+    if ((j & 1) >= pz) continue;  // pz == 1: the z-child does not exist
+    float t[8];
+    unpack8(xr[j], t);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (t[c] > best[c]) {  // strict: the FIRST maximum keeps the gradient
+        best[c] = t[c];
+        arg[c] = j;
+      }
+  }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    float best = xv[0][c];
-    int a = 0;
-#pragma unroll
-    for (int k = 1; k < 8; ++k)
-      if (xv[k][c] > best) {
-        best = xv[k][c];
-        a = k;
-      }
-    arg[c] = a;
+    const float other = __shfl_xor_sync(0xffffffffu, best[c], 1);
+    const bool mine = half == 0 ? best[c] >= other : best[c] > other;
+    if (!mine) arg[c] = -1;
   }
+  if (!live) return;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if ((k & 1) >= pz) continue;
-    float o[8];
-    if (dskip != nullptr) {
-      unpack8(ldg16(dskip + vi[k] * C + c8 * 8), o);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) o[c] = 0.f;
-    }
+  for (int j = 0; j < 4; ++j) {
+    if ((j & 1) >= pz) continue;
+    float o[8], t[8];
+    unpack8(sk[j], o);
+    unpack8(xr[j], t);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      if (arg[c] == k) o[c] += g8[c];
-      if (relu_mask && !(xv[k][c] > 0.f)) o[c] = 0.f;
+      if (arg[c] == j) o[c] += g8[c];
+      if (relu_mask && !(t[c] > 0.f)) o[c] = 0.f;
     }
-    stg16(dx + vi[k] * C + c8 * 8, pack8(o));
+    stg16(dx + FM_CHILD_OFS(j), pack8(o));
   }
+#undef FM_CHILD_OFS
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1078,7 +1093,7 @@ int k_maxpool3d_bwd(fm_ctx* ctx, const bf16* x, const bf16* dy, const bf16* dski
                     int relu_mask, int pz) {
   FM_CHECK(in.C % 8 == 0 && in.X % 2 == 0 && in.Y % 2 == 0 && in.Z % pz == 0 && (pz == 1 || pz == 2), FM_EINVAL,
            "maxpool3d_bwd: need C%%8==0 and even extents");
-  const int64_t total = in.elems() / (32 * pz);
+  const int64_t total = in.elems() / (32 * pz) * 2;  // two threads per (pooled voxel, 8 channels)
   ProfScope prof(ctx, "maxpool3d_bwd", 0.0, (double)in.elems() * 2.0 * (dskip ? 3.125 : 2.125));
   if (pz == 2)
     FM_CUDA(launch_pdl(maxpool3d_bwd_kernel<2>, dim3(grid_for(total)), dim3(kThreads), 0, ctx->stream, x, dy, dskip, dx, in.N, in.X, in.Y, in.Z,
@@ -1506,6 +1521,142 @@ int k_instnorm_lrelu(fm_ctx* ctx, const bf16* x, const float* gamma, const float
   const int bpa = norm_apply_blocks(vox_per_sample, C, &vpa);
   instnorm_apply_kernel<<<dim3(bpa, N), kThreads, 0, ctx->stream>>>(x, ss, add, chan_scale, y, vox_per_sample, C, vpa,
                                                                      0.3f);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNormalization(axis=1) + ReLU — create_convolution_block(batch_normalization=True), unet3d/unet.py:103-104,112.
+// Keras 2.x semantics: training: per-channel mean / BIASED variance over (batch, voxels),
+// y = (x - mean) * rsqrt(var + 1e-3) * gamma + beta; moving_mean / moving_variance <- 0.99 * old + 0.01 * batch value,
+// the variance fed to the moving average carries Keras' sample-size correction n / (n - (1 + eps)); inference: the
+// moving statistics. The per-(sample, block) partial pass, the apply pass and the backward partial / apply passes are
+// the instance-norm kernels above (slope 0 = ReLU); only the folds differ: they run over the samples too, and
+// eps sits under the square root.
+// ---------------------------------------------------------------------------------------------
+// One warp per channel. ss / stats are written for every sample (identical rows) so that the apply kernels are shared.
+__global__ void batchnorm_final_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float* __restrict__ moving_mean,
+                                       float* __restrict__ moving_var, float* __restrict__ ss, float* __restrict__ stats,
+                                       int N, int C, int blocks_per_sample, double count, float eps, float momentum,
+                                       int training) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int b = lane; b < N * blocks_per_sample; b += 32) {  // (n, block) pairs in a fixed order
+      const float2 o = *reinterpret_cast<const float2*>(part + ((int64_t)b * C + c) * 2);
+      s += (double)o.x;
+      q += (double)o.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    mean = s / count;
+    var = fmax(q / count - mean * mean, 0.0);
+  } else {
+    mean = (double)moving_mean[c];
+    var = (double)moving_var[c];
+  }
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double scale = (double)gamma[c] * rstd;
+  for (int n = lane; n < N; n += 32) {
+    ss[((int64_t)n * C + c) * 2] = (float)scale;
+    ss[((int64_t)n * C + c) * 2 + 1] = (float)((double)beta[c] - mean * scale);
+    if (stats != nullptr) {
+      stats[((int64_t)n * C + c) * 2] = (float)mean;
+      stats[((int64_t)n * C + c) * 2 + 1] = (float)rstd;
+    }
+  }
+  if (training && lane == 0 && moving_mean != nullptr) {
+    const double unbiased = var * (count / (count - (1.0 + (double)eps)));
+    moving_mean[c] = (float)((double)moving_mean[c] * momentum + mean * (1.0 - (double)momentum));
+    moving_var[c] = (float)((double)moving_var[c] * momentum + unbiased * (1.0 - (double)momentum));
+  }
+}
+
+// coef[n][c] = (gamma * rstd, mean(g), mean(g * xh)) for every sample; dgamma = sum g * xh, dbeta = sum g (stored).
+__global__ void batchnorm_bwd_final_kernel(const float* __restrict__ part, const float* __restrict__ stats,
+                                           const float* __restrict__ gamma, float* __restrict__ coef,
+                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C,
+                                           int blocks_per_sample, double count) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < N * blocks_per_sample; b += 32) {
+    const float2 o = *reinterpret_cast<const float2*>(part + ((int64_t)b * C + c) * 2);
+    s1 += (double)o.x;
+    s2 += (double)o.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const float a = (float)((double)gamma[c] * (double)stats[2 * c + 1]);  // sample 0's row: all rows are equal
+  for (int n = lane; n < N; n += 32) {
+    float* o = coef + ((int64_t)n * C + c) * 4;
+    o[0] = a;
+    o[1] = (float)(s1 / count);
+    o[2] = (float)(s2 / count);
+    o[3] = 0.f;
+  }
+  if (lane == 0) {
+    dgamma[c] += (float)s2;
+    dbeta[c] += (float)s1;
+  }
+}
+
+int k_batchnorm_relu(fm_ctx* ctx, const bf16* x, const float* gamma, const float* beta, float* moving_mean,
+                     float* moving_var, bf16* y, int N, int64_t vox_per_sample, int C, float* scratch,
+                     size_t scratch_floats, float* stats, int training) {
+  FM_CHECK(C >= 8 && C <= 512 && (C & (C - 1)) == 0, FM_EINVAL, "batchnorm: C=%d must be a power of two in [8,512]", C);
+  int64_t vpb;
+  const int bps = norm_blocks(vox_per_sample, &vpb);
+  const size_t need = (size_t)N * C * 2 * ((size_t)bps + 1);
+  FM_CHECK(scratch_floats >= need, FM_EINVAL, "batchnorm: scratch too small (%zu < %zu floats)", scratch_floats, need);
+  float* part = scratch;
+  float* ss = scratch + (size_t)N * C * 2 * bps;
+  ProfScope prof(ctx, "batchnorm_relu", 0.0, (double)N * vox_per_sample * C * (training ? 6.0 : 4.0));
+  if (training) {
+    instnorm_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(x, part, vox_per_sample,
+                                                                                                 C, vpb, bps);
+    FM_LAUNCH_OK(ctx);
+  }
+  batchnorm_final_kernel<<<ceil_div(C * 32, 128), 128, 0, ctx->stream>>>(part, gamma, beta, moving_mean, moving_var, ss, stats,
+                                                                       N, C, bps, (double)N * (double)vox_per_sample, 1e-3f,
+                                                                       0.99f, training);
+  FM_LAUNCH_OK(ctx);
+  int64_t vpa;
+  const int bpa = norm_apply_blocks(vox_per_sample, C, &vpa);
+  instnorm_apply_kernel<<<dim3(bpa, N), kThreads, 0, ctx->stream>>>(x, ss, nullptr, nullptr, y, vox_per_sample, C, vpa, 0.f);
+  FM_LAUNCH_OK(ctx);
+  return FM_OK;
+}
+
+int k_batchnorm_relu_bwd(fm_ctx* ctx, const bf16* x, const float* stats, const float* gamma, const float* beta,
+                         const bf16* gy, const bf16* gy2, bf16* dx, float* dgamma, float* dbeta, int N,
+                         int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats) {
+  FM_CHECK(C >= 8 && C <= 512 && (C & (C - 1)) == 0, FM_EINVAL, "batchnorm bwd: C=%d must be a power of two in [8,512]", C);
+  int64_t vpb;
+  const int bps = norm_blocks(vox_per_sample, &vpb);
+  const size_t need = (size_t)N * C * (2 * (size_t)bps + 4);
+  FM_CHECK(scratch_floats >= need, FM_EINVAL, "batchnorm bwd: scratch too small (%zu < %zu floats)", scratch_floats, need);
+  float* part = scratch;
+  float* coef = scratch + (size_t)N * C * 2 * bps;
+  NormBwdArgs a{x, stats, gamma, beta, gy, gy2, nullptr, vox_per_sample, C, 0.f};
+  ProfScope prof(ctx, "batchnorm_relu_bwd", 0.0, (double)N * vox_per_sample * C * (gy2 ? 14.0 : 10.0));
+  instnorm_bwd_partial_kernel<<<dim3(bps, N), kThreads, kThreads * 16 * sizeof(float), ctx->stream>>>(a, part, vpb, bps);
+  FM_LAUNCH_OK(ctx);
+  batchnorm_bwd_final_kernel<<<ceil_div(C * 32, 128), 128, 0, ctx->stream>>>(part, stats, gamma, coef, dgamma, dbeta, N, C, bps,
+                                                                           (double)N * (double)vox_per_sample);
+  FM_LAUNCH_OK(ctx);
+  int64_t vpa;
+  const int bpa = norm_apply_blocks(vox_per_sample, C, &vpa);
+  instnorm_bwd_apply_kernel<<<dim3(bpa, N), kThreads, 0, ctx->stream>>>(a, coef, dx, vpa);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }

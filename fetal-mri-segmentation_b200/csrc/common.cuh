@@ -223,6 +223,15 @@ int k_instnorm_lrelu(fm_ctx*, const bf16* x, const float* gamma, const float* be
 int k_instnorm_lrelu_bwd(fm_ctx*, const bf16* x, const float* stats, const float* gamma, const float* beta,
                          const bf16* gy, const bf16* gy2, const float* chan_scale, bf16* dx, float* dgamma,
                          float* dbeta, int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats);
+// BatchNormalization(axis=1) + ReLU of a raw conv output (create_convolution_block(batch_normalization=True)):
+// training = batch statistics (kept in `stats` [N][C][2] = (mean, rsqrt(var + eps)), identical rows) and the moving
+// averages are updated in place; inference = the moving statistics. Scratch as for the instance norm.
+int k_batchnorm_relu(fm_ctx*, const bf16* x, const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                     bf16* y, int N, int64_t vox_per_sample, int C, float* scratch, size_t scratch_floats, float* stats,
+                     int training);
+int k_batchnorm_relu_bwd(fm_ctx*, const bf16* x, const float* stats, const float* gamma, const float* beta, const bf16* gy,
+                         const bf16* gy2, bf16* dx, float* dgamma, float* dbeta, int N, int64_t vox_per_sample, int C,
+                         float* scratch, size_t scratch_floats);
 int k_zero_insert(fm_ctx*, const bf16* coarse, bf16* fine, Dims5 coarse_dims, int pz = 2);
 int k_add_bf16(fm_ctx*, const bf16* a, const bf16* b, bf16* out, int64_t n);
 int k_sumpool_f32(fm_ctx*, const float* fine, float* coarse, int N, int X, int Y, int Z, int pz = 2);

@@ -457,51 +457,54 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restri
   }
   float gb = 0.f;
   const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / lpv);
-  for (int64_t v0 = (int64_t)blockIdx.x * (blockDim.x / lpv) + threadIdx.x / lpv; v0 < voxels; v0 += 2 * vstride) {
-    // two voxels per trip: both loads are issued before the first is consumed
-    const int64_t v1 = v0 + vstride;
-    const bool has1 = v1 < voxels;
-    float gg[2] = {__ldg(dz + v0), has1 ? __ldg(dz + v1) : 0.f};
+  constexpr int U = 4;  // voxels per trip: all loads of a trip are issued before the first is consumed
+  for (int64_t vb = (int64_t)blockIdx.x * (blockDim.x / lpv) + threadIdx.x / lpv; vb < voxels; vb += U * vstride) {
+    float gg[U], tv[U];
+    uint4 tt[U];
+    bool has[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + u * vstride;
+      has[u] = v < voxels;
+      gg[u] = has[u] ? __ldg(dz + v) : 0.f;
+      tv[u] = (pt != nullptr && has[u]) ? __ldg(pt + v) : 0.f;
+      tt[u] = has[u] ? __ldg(reinterpret_cast<const uint4*>(x + v * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
     if (pt != nullptr) {
-      const float t0 = __ldg(pt + v0), t1 = has1 ? __ldg(pt + v1) : 0.f;
-      const float p0 = gg[0], p1 = gg[1];
-      gg[0] = (ga * t0 + gbc) * p0 * (1.f - p0);
-      gg[1] = (ga * t1 + gbc) * p1 * (1.f - p1);
-      if (xc != 0.f) {
-        gg[0] += xc * xent_voxel_weight(xs, v0) * xent_grad(t0, p0);
-        if (has1) gg[1] += xc * xent_voxel_weight(xs, v1) * xent_grad(t1, p1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float p0 = gg[u];
+        gg[u] = (ga * tv[u] + gbc) * p0 * (1.f - p0);
+        if (xc != 0.f && has[u]) gg[u] += xc * xent_voxel_weight(xs, vb + u * vstride) * xent_grad(tv[u], p0);
       }
     }
-    const uint4 tt[2] = {__ldg(reinterpret_cast<const uint4*>(x + v0 * C + sub * 8)),
-                         has1 ? __ldg(reinterpret_cast<const uint4*>(x + v1 * C + sub * 8)) : make_uint4(0u, 0u, 0u, 0u)};
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-    if (u == 1 && !has1) break;
-    const int64_t v = u == 0 ? v0 : v1;
-    const float g = gg[u];
-    const uint4 t = tt[u];
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
-    uint4 o;
-    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      gw[2 * i] += g * f.x;
-      gw[2 * i + 1] += g * f.y;
-      oh[i] = __floats2bfloat162_rn(mode != 0 || f.x > 0.f ? g * wv[2 * i] : 0.f,
-                                    mode != 0 || f.y > 0.f ? g * wv[2 * i + 1] : 0.f);
-    }
-    if (sub == 0) gb += g;
-    if (mode == 2) {
-      const uint4 prev = *reinterpret_cast<const uint4*>(dx + v * C + sub * 8);
-      const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+    for (int u = 0; u < U; ++u) {
+      if (!has[u]) break;
+      const int64_t v = vb + u * vstride;
+      const float g = gg[u];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&tt[u]);
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 a = __bfloat1622float2(ph[i]), b = __bfloat1622float2(oh[i]);
-        oh[i] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+        const float2 f = __bfloat1622float2(h[i]);
+        gw[2 * i] += g * f.x;
+        gw[2 * i + 1] += g * f.y;
+        oh[i] = __floats2bfloat162_rn(mode != 0 || f.x > 0.f ? g * wv[2 * i] : 0.f,
+                                      mode != 0 || f.y > 0.f ? g * wv[2 * i + 1] : 0.f);
       }
-    }
-    *reinterpret_cast<uint4*>(dx + v * C + sub * 8) = o;
+      if (sub == 0) gb += g;
+      if (mode == 2) {
+        const uint4 prev = *reinterpret_cast<const uint4*>(dx + v * C + sub * 8);
+        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __bfloat1622float2(ph[i]), b = __bfloat1622float2(oh[i]);
+          oh[i] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(dx + v * C + sub * 8) = o;
     }
   }
   // block reduction: threads with equal `sub` hold partial sums of the same 8 channels
@@ -722,7 +725,9 @@ int k_head_fwd_dice(fm_ctx* ctx, const bf16* x, const float* w, const float* b, 
            "head: channel count %d must be a power of two in [8,256]", C);
   const int lpv = C / 8;
   const int64_t vpb = kThreads / lpv;
-  const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb * 4), 1024);
+  // one wave of resident blocks (64 registers x 256 threads: 4 blocks per SM): a grid-stride kernel launched with 1024
+  // blocks on 592 slots ran 1.73 waves, the second one three-quarters empty
+  const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb * 4), (int64_t)std::min(1024, 4 * ctx->num_sms));
   {
     ProfScope prof(ctx, "head_fwd_dice", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 8.0));
     FM_CUDA(launch_pdl(head_fwd_dice_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, C,

@@ -45,7 +45,8 @@ def creation_order(entries):
     convs = sorted((e for e in entries if e[0] == "conv"), key=lambda e: _auto_index(e[1]))
     deconvs = sorted((e for e in entries if e[0] == "deconv"), key=lambda e: _auto_index(e[1]))
     norms = sorted((e for e in entries if e[0] == "norm"), key=lambda e: _auto_index(e[1]))
-    return convs + deconvs + norms
+    moving = sorted((e for e in entries if e[0] == "moving"), key=lambda e: _auto_index(e[1]))
+    return convs + deconvs + norms + moving
 
 
 def read_keras_h5_weights(path):
@@ -69,15 +70,24 @@ def read_keras_h5_weights(path):
                             bias.astype(np.float32)))
             elif "gamma" in arrays and "beta" in arrays:
                 out.append(("norm", lname, arrays["gamma"].astype(np.float32), arrays["beta"].astype(np.float32)))
+                if "moving_mean" in arrays:       # BatchNormalization: the non-trainable moving statistics
+                    out.append(("moving", lname, arrays["moving_mean"].astype(np.float32),
+                                arrays["moving_variance"].astype(np.float32)))
     return creation_order(out)
 
 
 def to_npz_arrays(entries):
     """The same weights keyed the way Model.save_weights / load_weights key their .npz (layers renumbered from 1 in
     creation order: conv3d_1/kernel:0, conv3d_1/bias:0, instance_normalization_1/gamma:0, ...)."""
-    arrays, n_conv, n_norm, n_deconv = {}, 0, 0, 0
+    arrays, n_conv, n_norm, n_deconv, n_moving = {}, 0, 0, 0, 0
     for e in entries:
         kind, a, b = e[0], e[-2], e[-1]                     # (kind, a, b) or (kind, layer_name, a, b)
+        stem = re.sub(r"_\d+$", "", e[1]) if len(e) == 4 and kind in ("norm", "moving") else "instance_normalization"
+        if kind == "moving":
+            n_moving += 1
+            prefix = "%s_%d" % (stem, n_moving)
+            arrays[prefix + "/moving_mean:0"], arrays[prefix + "/moving_variance:0"] = a, b
+            continue
         if kind == "deconv":
             n_deconv += 1
             prefix = "conv%dd_transpose_%d" % (a.ndim - 2, n_deconv)
@@ -88,6 +98,6 @@ def to_npz_arrays(entries):
             arrays[prefix + "/kernel:0"], arrays[prefix + "/bias:0"] = a, b
         else:
             n_norm += 1
-            prefix = "instance_normalization_%d" % n_norm
+            prefix = "%s_%d" % (stem, n_norm)
             arrays[prefix + "/gamma:0"], arrays[prefix + "/beta:0"] = a, b
     return arrays

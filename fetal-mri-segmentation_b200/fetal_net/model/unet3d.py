@@ -22,12 +22,17 @@ class _Optimizer:
         self.beta_1, self.beta_2, self.epsilon = 0.9, 0.999, 1e-7
 
 
+def _slot_keys(l):
+    """Suffixes of a layer's two arrays in a checkpoint: kernel/bias, gamma/beta or moving_mean/moving_variance."""
+    return l.get("keys") or (("/gamma:0", "/beta:0") if l["is_norm"] else ("/kernel:0", "/bias:0"))
+
+
 class Model:
     """Keras-Model duck type whose numerics run in libfetalb200 (one fm_model handle)."""
 
     def __init__(self, input_shape, depth, n_base_filters, n_labels, initial_learning_rate, loss_function,
                  device=None, ndim=3, isensee_levels=None, dropout_rate=0.0, dropout_seed=0x5EED, mask_shape=None,
-                 deconvolution=False):
+                 deconvolution=False, batch_normalization=False):
         lib = _lib.load()
         self._ctx = _lib.get_context(device)
         self.ndim = int(ndim)
@@ -50,15 +55,15 @@ class Model:
         elif self.ndim == 3:
             in_ch, X, Y, Z = [int(v) for v in input_shape]          # channels-first (unet3d/unet.py:9)
             spec = _lib.UNet3DSpec(in_ch, X, Y, Z, int(depth), int(n_base_filters), int(n_labels))
-            _lib.check(lib.fm_model_create_unet3d_ex(self._ctx.handle, ctypes.byref(spec), 1 if deconvolution else 0,
-                                                     ctypes.byref(h)))
+            _lib.check(lib.fm_model_create_unet3d_ex(self._ctx.handle, ctypes.byref(spec), (1 if deconvolution else 0) |
+                                                     (2 if batch_normalization else 0), ctypes.byref(h)))
             self.input_shape = (None, in_ch, X, Y, Z)
             self.output_shape = (None, int(n_labels), X, Y, Z)
         else:
             H, W, in_ch = [int(v) for v in input_shape]             # slices-as-channels (unet/unet.py:49-50)
             spec = _lib.UNet2DSpec(H, W, in_ch, int(depth), int(n_base_filters), int(n_labels))
-            _lib.check(lib.fm_model_create_unet2d_ex(self._ctx.handle, ctypes.byref(spec), 1 if deconvolution else 0,
-                                                     ctypes.byref(h)))
+            _lib.check(lib.fm_model_create_unet2d_ex(self._ctx.handle, ctypes.byref(spec), (1 if deconvolution else 0) |
+                                                     (2 if batch_normalization else 0), ctypes.byref(h)))
             if dropout_rate:                                         # SpatialDropout2D (unet/unet.py:60-61,76-77)
                 _lib.check(lib.fm_model_set_dropout(h, float(dropout_rate), int(dropout_seed)))
             self.input_shape = (None, H, W, in_ch)
@@ -82,6 +87,7 @@ class Model:
             self.metrics_names.append('dice_coefficient')
         self.stop_training = False
         self.deconvolution = bool(deconvolution)
+        self.batch_normalization = bool(batch_normalization)
         self.isensee_levels = isensee_levels
         self.name = ('isensee2017_model_3d' if self.ndim == 3 else 'isensee2017_model') if isensee_levels is not None \
             else ('unet_model_3d' if self.ndim == 3 else 'unet_model_2d')
@@ -91,12 +97,19 @@ class Model:
             name = ctypes.create_string_buffer(32)
             info = (ctypes.c_int64 * 5)()
             _lib.check(lib.fm_model_layer_info(h, i, name, info))
-            k = int(info[2]) // 10                                   # 33 / 31 -> 3, 22 / 21 -> 2, 11 -> 1, 0 -> norm
-            is_norm = int(info[2]) == 0
+            code = int(info[2])                                      # 33 / 31, 22 / 21, 11; 0 norm; -1 BN moving statistics
+            k = max(code, 0) // 10                                   # 33 / 31 -> 3, 22 / 21 -> 2, 11 -> 1, norm -> 0
+            is_norm = code <= 0
+            is_moving = code < 0                                     # (moving_mean, moving_variance) of the layer before
             is_deconv = k == 2                                       # Keras names them conv3d_transpose_<n>
-            n_same = sum(1 for l in self.layers if (l["is_norm"], l["is_deconv"]) == (is_norm, is_deconv)) + 1
+            n_same = sum(1 for l in self.layers if (l["is_norm"], l["is_deconv"], l["is_moving"]) ==
+                         (is_norm, is_deconv, is_moving)) + 1
+            norm_name = "batch_normalization_%d" if batch_normalization else "instance_normalization_%d"
             self.layers.append(dict(index=i, name=name.value.decode(), is_norm=is_norm, is_deconv=is_deconv,
-                                    keras_name=("instance_normalization_%d" if is_norm else
+                                    is_moving=is_moving,
+                                    keys=("/moving_mean:0", "/moving_variance:0") if is_moving else
+                                    (("/gamma:0", "/beta:0") if is_norm else ("/kernel:0", "/bias:0")),
+                                    keras_name=(norm_name if is_norm else
                                                 ("conv%dd_transpose_%%d" if is_deconv else "conv%dd_%%d") % self.ndim) % n_same,
                                     cin=int(info[0]), cout=int(info[1]), k=k,
                                     kshape=(int(info[1]),) if is_norm else
@@ -147,7 +160,10 @@ class Model:
         """`named`: {'<layer>/kernel': ..., '<layer>/bias': ...} keyed by our layer names (enc0a ...)."""
         ws = []
         for l in self.layers:
-            if l["is_norm"]:        # '<conv>_norm' pseudo-layer: kernel slot = gamma, bias slot = beta
+            if l.get("is_moving"):  # '<conv>_moving' pseudo-layer of a BatchNormalization
+                base = l["name"][:-len("_moving")]
+                ws += [named[base + "/moving_mean"], named[base + "/moving_variance"]]
+            elif l["is_norm"]:      # '<conv>_norm' pseudo-layer: kernel slot = gamma, bias slot = beta
                 base = l["name"][:-len("_norm")]
                 ws += [named[base + "/gamma"], named[base + "/beta"]]
             else:
@@ -159,6 +175,9 @@ class Model:
         rng = np.random.default_rng(seed)
         ws = []
         for l in self.layers:
+            if l.get("is_moving"):                                  # moving_mean = 0, moving_variance = 1
+                ws += [np.zeros((l["cout"],), np.float32), np.ones((l["cout"],), np.float32)]
+                continue
             if l["is_norm"]:                                        # gamma = 1, beta = 0
                 ws += [np.ones((l["cout"],), np.float32), np.zeros((l["cout"],), np.float32)]
                 continue
@@ -171,13 +190,14 @@ class Model:
     def _weight_arrays(self):
         arrays = {}
         for l, (k, b) in zip(self.layers, zip(*[iter(self.get_weights())] * 2)):
-            arrays[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")] = k
-            arrays[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")] = b
+            arrays[l["keras_name"] + _slot_keys(l)[0]] = k
+            arrays[l["keras_name"] + _slot_keys(l)[1]] = b
         arrays["__config__"] = np.array(list(self.input_shape[1:]) + [self.depth, self.n_base_filters, self.n_labels])
         # builder name + its extra arguments, so that load_old_model can rebuild the right family
         arrays["__builder__"] = np.array(getattr(self, "name", "unet_model_3d"))
         arrays["__isensee_levels__"] = np.array(int(getattr(self, "isensee_levels", 0) or 0))
         arrays["__deconvolution__"] = np.array(int(getattr(self, "deconvolution", False)))
+        arrays["__batch_normalization__"] = np.array(int(getattr(self, "batch_normalization", False)))
         return arrays
 
     def save_weights(self, path):
@@ -252,8 +272,7 @@ class Model:
     def _weights_from_mapping(self, z):
         ws = []
         for l in self.layers:
-            ws += [np.asarray(z[l["keras_name"] + ("/gamma:0" if l["is_norm"] else "/kernel:0")]),
-                   np.asarray(z[l["keras_name"] + ("/beta:0" if l["is_norm"] else "/bias:0")])]
+            ws += [np.asarray(z[l["keras_name"] + _slot_keys(l)[0]]), np.asarray(z[l["keras_name"] + _slot_keys(l)[1]])]
         return ws
 
     def reset_optimizer(self):
@@ -406,13 +425,11 @@ def unet_model_3d(input_shape, pool_size=(2, 2, 2), n_labels=1, initial_learning
     (dropout_rate, mask_shape, old_model_path, ... — train_fetal.py:33-39) are swallowed like there."""
     if tuple(pool_size) != (2, 2, 2):
         raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2,2)" % (pool_size,))
-    if batch_normalization:
-        raise NotImplementedError("batch_normalization=True is on the §8 'next' list")
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
-                 device=kargs.get("device"), deconvolution=deconvolution)
+                 device=kargs.get("device"), deconvolution=deconvolution, batch_normalization=batch_normalization)
 
 
 def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_rate=0.00001, deconvolution=False,
@@ -425,14 +442,15 @@ def unet_model_2d(input_shape, pool_size=(2, 2), n_labels=1, initial_learning_ra
     masks from the library's counter-based hash, `dropout_seed` kwarg)."""
     if tuple(pool_size) != (2, 2):
         raise NotImplementedError("pool_size %r: the B200 path builds the reference default (2,2)" % (pool_size,))
-    if batch_normalization:
-        raise NotImplementedError("batch_normalization=True is on the §8 'next' list")
     if activation_name != "sigmoid":
         raise NotImplementedError("activation_name %r: only 'sigmoid' is built" % activation_name)
+    if batch_normalization and dropout_rate:
+        raise NotImplementedError("batch_normalization=True together with dropout_rate > 0 is not built")
     return Model(input_shape=input_shape, depth=depth, n_base_filters=n_base_filters, n_labels=n_labels,
                  initial_learning_rate=initial_learning_rate, loss_function=loss_function,
                  device=kargs.get("device"), ndim=2, dropout_rate=dropout_rate or 0.0,
-                 dropout_seed=kargs.get("dropout_seed", 0x5EED), deconvolution=deconvolution)
+                 dropout_seed=kargs.get("dropout_seed", 0x5EED), deconvolution=deconvolution,
+                 batch_normalization=batch_normalization)
 
 
 def isensee2017_model_3d(input_shape=(1, 128, 128, 128), n_base_filters=16, depth=5, dropout_rate=0.3,

@@ -168,6 +168,7 @@ def load_old_model(model_file, verbose=True, config=None):
         builder_name = str(z["__builder__"]) if "__builder__" in z.files else None
         levels = int(z["__isensee_levels__"]) if "__isensee_levels__" in z.files else 0
         deconv = bool(int(z["__deconvolution__"])) if "__deconvolution__" in z.files else False
+        bnorm = bool(int(z["__batch_normalization__"])) if "__batch_normalization__" in z.files else False
     loss = _metrics.dice_coefficient_loss
     lr = 1e-5
     if config is not None:
@@ -179,6 +180,8 @@ def load_old_model(model_file, verbose=True, config=None):
                   initial_learning_rate=lr, loss_function=loss)
     if deconv:
         kwargs['deconvolution'] = True
+    if bnorm:
+        kwargs['batch_normalization'] = True
     if builder_name in ('isensee2017_model_3d', 'isensee2017_model'):
         kwargs['n_segmentation_levels'] = levels
         if builder_name == 'isensee2017_model':     # the 2D builder: `levels` heads reach the output only when summed

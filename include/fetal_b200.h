@@ -83,8 +83,15 @@ int fm_model_destroy(fm_model* m);
  * layer table then holds an "up<d>" layer in front of every "dec<d>a"; its kernel has the Keras Conv3DTranspose
  * layout (2,2,2,Cout,Cin). It runs as ONE 1x1x1 tensor-core convolution to (8 x C) channels (4 x C in 2D) - a k = 2,
  * s = 2 transposed convolution writes every output voxel from exactly one input voxel - plus a depth-to-space
- * shuffle; backward is the reverse shuffle, a 1x1x1 wgrad and a 1x1x1 dgrad. */
+ * shuffle; backward is the reverse shuffle, a 1x1x1 wgrad and a 1x1x1 dgrad.
+ * FM_UNET_BATCH_NORMALIZATION: batch_normalization=True - every create_convolution_block is Conv -> BatchNormalization(
+ * axis=1) -> ReLU (unet3d/unet.py:102-113). Keras semantics: batch statistics (biased variance, eps 1e-3 under the root)
+ * in training passes, moving statistics (momentum 0.99, sample-size-corrected variance) at inference. The layer table
+ * lists, behind every block's conv, a "<conv>_norm" pseudo-layer (kernel = gamma, bias = beta) and a "<conv>_moving"
+ * pseudo-layer (kernel = moving_mean, bias = moving_variance; never touched by the optimizer). Single-process training
+ * only: fm_train_step_dp refuses (the statistics would have to span the global batch). */
 #define FM_UNET_DECONVOLUTION 1
+#define FM_UNET_BATCH_NORMALIZATION 2
 int fm_model_create_unet3d_ex(fm_ctx* ctx, const fm_unet3d_spec* spec, int flags, fm_model** out);
 
 /* Builder spec of the 2D / "2.5D" U-Net. Replaces the kwargs of unet_model_2d

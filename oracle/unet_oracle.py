@@ -77,15 +77,55 @@ def _tw(w, name, dtype):
 # plain 3D U-Net
 # ----------------------------------------------------------------------------------------------
 
-def unet3d_forward(x, w, depth=4, return_logits=False, quant=None):
+def _batch_norm(y, w, name, training, bn_updates, eps=1e-3, momentum=0.99):
+    """Keras 2.x BatchNormalization(axis=1) (create_convolution_block(batch_normalization=True), unet3d/unet.py:103-104):
+    training = batch mean / BIASED variance, y = (x - mean) * rsqrt(var + eps) * gamma + beta, and the moving statistics
+    move towards the batch values (the variance with Keras' sample-size correction n / (n - (1 + eps))) - collected in
+    `bn_updates`; inference = the moving statistics."""
+    dims = (0,) + tuple(range(2, y.dim()))
+    shape = (1, -1) + (1,) * (y.dim() - 2)
+    dt = y.dtype
+    gamma, beta = torch.as_tensor(w[name + "/gamma"]).to(dt), torch.as_tensor(w[name + "/beta"]).to(dt)
+    mm, mv = torch.as_tensor(w[name + "/moving_mean"]).to(dt), torch.as_tensor(w[name + "/moving_variance"]).to(dt)
+    if training:
+        mean, var = y.mean(dim=dims), y.var(dim=dims, unbiased=False)
+        if bn_updates is not None:
+            n = float(y.numel() // y.shape[1])
+            bn_updates[name + "/moving_mean"] = (mm.detach() * momentum + mean.detach() * (1 - momentum)).numpy()
+            bn_updates[name + "/moving_variance"] = (mv.detach() * momentum +
+                                                    var.detach() * (n / (n - (1.0 + eps))) * (1 - momentum)).numpy()
+    else:
+        mean, var = mm, mv
+    return (y - mean.reshape(shape)) * torch.rsqrt(var.reshape(shape) + eps) * gamma.reshape(shape) + beta.reshape(shape)
+
+
+def bn_params(layers):
+    """Keras initial values of the BatchNormalization behind every 3x3 conv block: gamma 1, beta 0, moving_mean 0,
+    moving_variance 1."""
+    p = {}
+    for name, cin, cout, k in layers:
+        if k == 3:
+            p[name + "/gamma"] = np.ones((cout,), np.float32)
+            p[name + "/beta"] = np.zeros((cout,), np.float32)
+            p[name + "/moving_mean"] = np.zeros((cout,), np.float32)
+            p[name + "/moving_variance"] = np.ones((cout,), np.float32)
+    return p
+
+
+def unet3d_forward(x, w, depth=4, return_logits=False, quant=None, training=False, bn_updates=None):
     """x: [B,Cin,X,Y,Z] torch tensor. `quant` (optional callable) is applied to every stored
-    activation and to the weights - used to model bf16 storage for tolerance studies."""
+    activation and to the weights - used to model bf16 storage for tolerance studies. Weights holding
+    '<layer>/gamma' switch the block to Conv -> BatchNormalization -> ReLU (`training` selects batch / moving
+    statistics)."""
     dt = x.dtype
     q = quant if quant is not None else (lambda t: t)
 
     def cb(t, name):
         k, b = _tw(w, name, dt)
-        return q(F.relu(F.conv3d(t, q(k), b, padding=1)))
+        y = F.conv3d(t, q(k), b, padding=1)
+        if (name + "/gamma") in w:
+            y = _batch_norm(q(y), w, name, training, bn_updates)
+        return q(F.relu(y))
 
     cur = q(x)
     skips = []
@@ -191,6 +231,9 @@ def train_step(forward_fn, x, t, w, adam_state, lr, dtype=torch.float32, loss_fn
     out = {"loss": float(loss.detach()), "grads": {}, "pred": p.detach().numpy()}
     it = adam_state.setdefault("iterations", 0)
     for n in names:
+        if params[n].grad is None:           # e.g. BatchNormalization moving statistics (the caller applies bn_updates)
+            out["grads"][n] = np.zeros_like(w[n])
+            continue
         g = params[n].grad.detach().to(torch.float32).numpy()
         out["grads"][n] = g
         keras_adam_step(w[n], g, adam_state.setdefault("m/" + n, np.zeros_like(w[n])),
@@ -207,13 +250,18 @@ def unet3d_train_step(x, t, w, adam_state, lr, depth=4, dtype=torch.float32, qua
     params = {n: torch.tensor(w[n], dtype=dtype, requires_grad=True) for n in names}
     xt = torch.as_tensor(x).to(dtype)
     tt = torch.as_tensor(t).to(dtype)
-    p = unet3d_forward(xt, params, depth=depth, quant=quant)
+    bn_updates = {}
+    p = unet3d_forward(xt, params, depth=depth, quant=quant, training=True, bn_updates=bn_updates)
     loss = dice_coefficient_loss(tt, p)
     loss.backward()
     out = {"loss": float(loss.detach()), "binary_accuracy": float(binary_accuracy(tt, p.detach())),
            "vod_coefficient": float(vod_coefficient(tt, p.detach())), "grads": {}, "pred": p.detach().numpy()}
     it = adam_state.setdefault("iterations", 0)
     for n in names:
+        if n in bn_updates:                  # non-trainable moving statistics: no gradient, updated by the forward pass
+            out["grads"][n] = np.zeros_like(w[n])
+            w[n][...] = bn_updates[n].astype(np.float32)
+            continue
         g = params[n].grad.detach().to(torch.float32).numpy()
         out["grads"][n] = g
         m = adam_state.setdefault("m/" + n, np.zeros_like(w[n]))
@@ -413,7 +461,7 @@ def bf16_round(t):
     return t.to(torch.bfloat16).to(t.dtype)
 
 
-def unet2d_forward(x, w, depth=4, return_logits=False, drop=None, quant=None):
+def unet2d_forward(x, w, depth=4, return_logits=False, drop=None, quant=None, training=False, bn_updates=None):
     """x: [B,H,W,D] (slices-as-channels, Keras input layout) -> [B,H,W,n_labels]. `drop` (training with
     SpatialDropout2D, unet/unet.py:60-61,76-77): {'enc<d>' / 'dec<d>': scale [B,C]} applied behind the first block of
     the level."""
@@ -424,7 +472,10 @@ def unet2d_forward(x, w, depth=4, return_logits=False, drop=None, quant=None):
 
     def cb(t, name):
         k, b = _tw(w, name, dt)
-        return q(F.relu(F.conv2d(t, q(k), b, padding=1)))
+        y = F.conv2d(t, q(k), b, padding=1)
+        if (name + "/gamma") in w:
+            y = _batch_norm(q(y), w, name, training, bn_updates)
+        return q(F.relu(y))
 
     def dr(t, key):
         if drop is None or key not in drop:

@@ -669,3 +669,125 @@ def test_unet2d_deconvolution_matches_oracle():
     assert got[0] == pytest.approx(refstep["loss"], abs=3e-3), (got, refstep["loss"])
     bad = _unet_grad_check(model, refstep["grads"], bfstep["grads"])
     assert not bad, bad
+
+
+# ---- batch_normalization=True: Conv -> BatchNormalization(axis=1) -> ReLU blocks (unet3d/unet.py:102-113) ---------------
+
+def _bn_weights(layers, ndim, seed):
+    w = uo.glorot_uniform_weights(layers, seed=seed, ndim=ndim)
+    w.update(uo.bn_params(layers))
+    rng = np.random.default_rng(seed + 1)
+    for name, cin, cout, k in layers:
+        w[name + "/bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        if k == 3:
+            w[name + "/gamma"] = (1.0 + 0.2 * rng.standard_normal(cout)).astype(np.float32)
+            w[name + "/beta"] = (0.2 * rng.standard_normal(cout)).astype(np.float32)
+            w[name + "/moving_mean"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+            w[name + "/moving_variance"] = (0.05 + 0.2 * rng.random(cout)).astype(np.float32)
+    w["final/kernel"] = (w["final/kernel"] * 3.0).astype(np.float32)
+    return w
+
+
+def _bn_grad_check(model, ref_grads, bf_grads):
+    bad = []
+    grads = model.get_gradients()
+    for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
+        if l["is_moving"]:
+            assert not gk.any() and not gb.any(), l["name"]          # non-trainable
+            continue
+        if l["is_norm"]:
+            base = l["name"][:-len("_norm")]
+            pairs = [(base + "/gamma", gk), (base + "/beta", gb)]
+        elif (l["name"] + "/gamma") in ref_grads:                    # conv bias in front of a BN: analytically zero
+            assert np.abs(gb).max() <= 2e-2 * max(np.abs(gk).max(), 1e-12), l["name"]
+            pairs = [(l["name"] + "/kernel", gk)]
+        else:
+            pairs = [(l["name"] + "/kernel", gk), (l["name"] + "/bias", gb)]
+        for name, g in pairs:
+            r = ref_grads[name]
+            cos = _cos(g, r)
+            floor = min(0.99, _cos(bf_grads[name], r) - 0.01)
+            if cos < floor:
+                bad.append((name, round(cos, 4), round(floor, 4)))
+    return bad
+
+
+@pytest.mark.parametrize("deconvolution", [False, True])
+def test_unet3d_batch_normalization_matches_oracle(deconvolution):
+    """unet_model_3d(batch_normalization=True): inference on the moving statistics, a training step on the batch
+    statistics (loss, gradients incl. gamma / beta), the Keras moving-average update, and inference after it."""
+    from fetal_net.model import unet_model_3d
+    depth, nf, shape = 3, 16, (1, 32, 32, 16)
+    layers = uo.unet3d_layers(depth, nf, deconvolution=deconvolution)
+    w = _bn_weights(layers, 3, seed=21)
+    model = unet_model_3d(input_shape=shape, n_base_filters=nf, depth=depth, initial_learning_rate=1e-3,
+                          batch_normalization=True, deconvolution=deconvolution)
+    names = [l["name"] for l in model.layers]
+    assert names[:3] == ["enc0a", "enc0a_norm", "enc0a_moving"] and names[-1] == "final"
+    bnl = [l for l in model.layers if l["name"] == "enc1a_moving"][0]
+    assert bnl["keras_name"] == "batch_normalization_3" and bnl["keys"] == ("/moving_mean:0", "/moving_variance:0")
+    assert model.count_params() == sum(v.size for v in w.values())
+    model.set_named_weights(w)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((4,) + shape).astype(np.float32)
+    t = _blob_truth(x)
+    lg = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+
+    def check_predict(weights):
+        with torch.no_grad():
+            ref = uo.unet3d_forward(torch.as_tensor(x), weights, depth=depth).numpy()
+        p = model.predict(x)
+        rel = np.linalg.norm(lg(p) - lg(ref)) / np.linalg.norm(lg(ref))
+        assert rel <= 0.04 and np.abs(p - ref).mean() <= 0.008, (rel, float(np.abs(p - ref).mean()))
+
+    check_predict(w)                                                   # moving statistics
+    wo = {k: v.copy() for k, v in w.items()}
+    ref = uo.unet3d_train_step(x, t, wo, {}, 1e-3, depth=depth)
+    bf = uo.unet3d_train_step(x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-3, depth=depth, quant=uo.bf16_round)
+    got = model.train_on_batch(x, t)
+    assert abs(got[0] - ref["loss"]) <= 4e-3, (got, ref["loss"])
+    bad = _bn_grad_check(model, ref["grads"], bf["grads"])
+    assert not bad, bad
+    # moving statistics after the step: 0.99 * old + 0.01 * batch value (variance with Keras' sample-size correction)
+    new = dict(zip([l["name"] for l in model.layers], zip(model.get_weights()[0::2], model.get_weights()[1::2])))
+    for name, cin, cout, k in layers:
+        if k != 3:
+            continue
+        mm, mv = new[name + "_moving"]
+        assert np.abs(mm - wo[name + "/moving_mean"]).max() <= 2e-3 * max(1.0, np.abs(wo[name + "/moving_mean"]).max()), name
+        assert np.abs(mv / wo[name + "/moving_variance"] - 1).max() <= 5e-3, name
+        assert np.abs(mm - w[name + "/moving_mean"]).max() > 0          # it did move
+    check_predict(wo)                                                  # inference with the updated weights + statistics
+    losses = [got[0]] + [model.train_on_batch(x, t)[0] for _ in range(5)]
+    assert losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_unet2d_batch_normalization_matches_oracle():
+    from fetal_net.model import unet_model_2d
+    depth, nf = 3, 32
+    layers = uo.unet2d_layers(depth, nf, 6)
+    w = _bn_weights(layers, 2, seed=31)
+    model = unet_model_2d(input_shape=(32, 32, 6), n_base_filters=nf, depth=depth, initial_learning_rate=1e-3,
+                          batch_normalization=True)
+    model.set_named_weights(w)
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((4, 32, 32, 6)).astype(np.float32)
+    t = (rng.random((4, 32, 32, 1)) < 0.3).astype(np.float32)
+    lg = lambda q: np.log(np.clip(q.astype(np.float64), 1e-7, 1 - 1e-7) / np.clip(1 - q.astype(np.float64), 1e-7, 1))
+    with torch.no_grad():
+        ref = uo.unet2d_forward(torch.as_tensor(x), w, depth=depth).numpy()
+    p = model.predict(x)
+    rel = np.linalg.norm(lg(p) - lg(ref)) / np.linalg.norm(lg(ref))
+    assert rel <= 0.04 and np.abs(p - ref).mean() <= 0.008, rel
+    upd = {}
+    fwd = lambda xt, prm: uo.unet2d_forward(xt, prm, depth=depth, training=True, bn_updates=upd)
+    refstep = uo.train_step(fwd, x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-3)
+    bfstep = uo.train_step(lambda xt, prm: uo.unet2d_forward(xt, prm, depth=depth, training=True, quant=uo.bf16_round),
+                           x, t, {k: v.copy() for k, v in w.items()}, {}, 1e-3)
+    got = model.train_on_batch(x, t)
+    assert abs(got[0] - refstep["loss"]) <= 4e-3, (got, refstep["loss"])
+    bad = _bn_grad_check(model, refstep["grads"], bfstep["grads"])
+    assert not bad, bad
+    new = dict(zip([l["name"] for l in model.layers], zip(model.get_weights()[0::2], model.get_weights()[1::2])))
+    for name in ("enc0a", "dec0b"):
+        assert np.abs(new[name + "_moving"][1] / upd[name + "/moving_variance"] - 1).max() <= 5e-3, name
