@@ -531,10 +531,11 @@ static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int fl
     if (!conv_up_supported(X, Y, Z, l.c1, l.c2, l.cout)) continue;
     const size_t n = (size_t)l.cout * 64 * l.c1;
     FM_CUDA(cudaMalloc((void**)&l.w_up_d, n * sizeof(bf16)));
-    if (l.march_f) {
+    const char* all = getenv("FETAL_B200_UP_COARSE_ALL");
+    if (l.march_f && !(all && all[0] == '1')) {
       // small filter bank (dec0a): forward and weight gradient stay on the marching kernels over the materialised
       // upsampled tensor; the gradient towards the coarse tensor still drops from 27 fine taps + a sum-pool pass to
-      // 64 class taps per COARSE voxel
+      // 64 class taps per COARSE voxel. (FETAL_B200_UP_COARSE_ALL=1: all three passes at coarse resolution - A/B.)
       l.up_dgrad = !(e && e[0] == '2');
       continue;
     }
@@ -1964,6 +1965,12 @@ static int patchwise_impl(fm_model* m, const float* vol, const int32_t vol_dims[
   const int nslices = is2d ? m->cin_real - (truth ? prev_truth_size : 0) : m->spec.Z;
   FM_CHECK(!truth || (is2d && prev_truth_size > 0 && prev_truth_size < m->cin_real), FM_EINVAL,
            "fm_patchwise_predict: truth conditioning needs a 2D model with in_channels > prev_truth_size");
+  // The truth slices are gathered with zero fill outside the padded truth volume; the reference edge-replicates there
+  // (get_patch_from_3d_data -> fix_out_of_bound_patch_attempt, mode='edge'). The two agree as long as the slices stay
+  // inside the patch's own z range, whose halo is zero-padded on both sides - anything else is refused, not approximated.
+  FM_CHECK(!truth || (prev_truth_index >= 0 && prev_truth_index + prev_truth_size <= nslices), FM_EINVAL,
+           "fm_patchwise_predict: previous-truth slices [%d, %d) must lie inside the patch depth %d", prev_truth_index,
+           prev_truth_index + prev_truth_size, nslices);
   // patch extent in the padded volume and the prediction extent it yields (prediction.py:131-134)
   const int32_t patch[3] = {m->spec.X, m->spec.Y, nslices};
   const int32_t pred[3] = {m->spec.X, m->spec.Y, is2d ? 1 : m->spec.Z};

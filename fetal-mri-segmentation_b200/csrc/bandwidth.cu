@@ -333,8 +333,25 @@ __global__ void __launch_bounds__(kThreads) instnorm_partial_kernel(const bf16* 
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (l < lanes)
-    for (int64_t v = v0 + l; v < v1; v += lanes) {
+  if (l < lanes) {
+    // four independent 16-byte loads in flight per thread (the pass is latency-bound otherwise: one load per trip)
+    int64_t v = v0 + l;
+    for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
+      uint4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = ldg16(xs + (v + u * (int64_t)lanes) * C + c8 * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(r[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] += f[i] * f[i];
+        }
+      }
+    }
+    for (; v < v1; v += lanes) {
       float f[8];
       unpack8(ldg16(xs + v * C + c8 * 8), f);
 #pragma unroll
@@ -343,6 +360,7 @@ __global__ void __launch_bounds__(kThreads) instnorm_partial_kernel(const bf16* 
         q[i] += f[i] * f[i];
       }
     }
+  }
   if (fold_channel_groups(s, q, sh, c8n)) {
     float* o = part + (((int64_t)n * blocks_per_sample + blk) * C + threadIdx.x * 8) * 2;
 #pragma unroll
@@ -408,13 +426,41 @@ __global__ void __launch_bounds__(kThreads) instnorm_apply_kernel(const bf16* __
   for (int i = 0; i < 8; ++i) cs[i] = chan_scale ? __ldg(chan_scale + (int64_t)n * C + c8 * 8 + i) : 1.f;
   const int64_t v0 = (int64_t)n * vox_per_sample + (int64_t)blockIdx.x * vox_per_block;
   const int64_t v1 = min((int64_t)(n + 1) * vox_per_sample, v0 + vox_per_block);
-  for (int64_t v = v0 + l; v < v1; v += lanes) {
+  // a block covers 4 voxels per thread (norm_apply_blocks): all loads of the thread are issued before the first use
+  uint4 rx[4], ra[4];
+  int64_t vv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    vv[u] = v0 + l + u * (int64_t)lanes;
+    if (vv[u] < v1) {
+      rx[u] = ldg16(x + vv[u] * C + c8 * 8);
+      if (add != nullptr) ra[u] = ldg16(add + vv[u] * C + c8 * 8);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (vv[u] >= v1) continue;
+    float f[8], a[8];
+    unpack8(rx[u], f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = f[i] * sc[i] + sh[i];
+      f[i] = (t > 0.f ? t : slope * t) * cs[i];
+    }
+    if (add != nullptr) {
+      unpack8(ra[u], a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += a[i];
+    }
+    stg16(y + vv[u] * C + c8 * 8, pack8(f));
+  }
+  for (int64_t v = v0 + l + 4 * (int64_t)lanes; v < v1; v += lanes) {  // (blocks larger than 4 voxels per thread)
     float f[8], a[8];
     unpack8(ldg16(x + v * C + c8 * 8), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float u = f[i] * sc[i] + sh[i];
-      f[i] = (u > 0.f ? u : slope * u) * cs[i];
+      const float t = f[i] * sc[i] + sh[i];
+      f[i] = (t > 0.f ? t : slope * t) * cs[i];
     }
     if (add != nullptr) {
       unpack8(ldg16(add + v * C + c8 * 8), a);
@@ -465,13 +511,21 @@ __device__ __forceinline__ void norm_load_const(const NormBwdArgs& a, int n, int
     k.cs[i] = a.chan_scale ? __ldg(a.chan_scale + (int64_t)n * a.C + ch) : 1.f;
   }
 }
-__device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, const NormConst& k, int64_t v, int c8, float g[8],
-                                           float xh[8]) {
+struct NormBwdRaw {
+  uint4 x, gy, gy2;
+};
+__device__ __forceinline__ void norm_bwd_load(const NormBwdArgs& a, int64_t v, int c8, NormBwdRaw& r) {
+  r.x = ldg16(a.x + v * a.C + c8 * 8);
+  r.gy = ldg16(a.gy + v * a.C + c8 * 8);
+  if (a.gy2 != nullptr) r.gy2 = ldg16(a.gy2 + v * a.C + c8 * 8);
+}
+__device__ __forceinline__ void norm_bwd_compute(const NormBwdArgs& a, const NormConst& k, const NormBwdRaw& r, float g[8],
+                                                 float xh[8]) {
   float x[8], t[8];
-  unpack8(ldg16(a.x + v * a.C + c8 * 8), x);
-  unpack8(ldg16(a.gy + v * a.C + c8 * 8), g);
+  unpack8(r.x, x);
+  unpack8(r.gy, g);
   if (a.gy2 != nullptr) {
-    unpack8(ldg16(a.gy2 + v * a.C + c8 * 8), t);
+    unpack8(r.gy2, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += t[i];
   }
@@ -481,6 +535,12 @@ __device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, const NormConst
     const float z = k.gamma[i] * xh[i] + k.beta[i];
     g[i] *= (z > 0.f ? 1.f : a.slope) * k.cs[i];
   }
+}
+__device__ __forceinline__ void norm_bwd_g(const NormBwdArgs& a, const NormConst& k, int64_t v, int c8, float g[8],
+                                           float xh[8]) {
+  NormBwdRaw r;
+  norm_bwd_load(a, v, c8, r);
+  norm_bwd_compute(a, k, r, g, xh);
 }
 
 __global__ void __launch_bounds__(kThreads) instnorm_bwd_partial_kernel(NormBwdArgs a, float* __restrict__ part,
@@ -498,7 +558,26 @@ __global__ void __launch_bounds__(kThreads) instnorm_bwd_partial_kernel(NormBwdA
   if (l < lanes) {
     NormConst k;
     norm_load_const(a, n, c8, k);
-    for (int64_t v = v0 + l; v < v1; v += lanes) {
+    int64_t v = v0 + l;
+    for (; v + (int64_t)lanes < v1; v += 2 * (int64_t)lanes) {  // two voxels per trip: 4-6 loads in flight per thread
+      NormBwdRaw r0, r1;
+      norm_bwd_load(a, v, c8, r0);
+      norm_bwd_load(a, v + lanes, c8, r1);
+      float g[8], xh[8];
+      norm_bwd_compute(a, k, r0, g, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += g[i];
+        s2[i] += g[i] * xh[i];
+      }
+      norm_bwd_compute(a, k, r1, g, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += g[i];
+        s2[i] += g[i] * xh[i];
+      }
+    }
+    for (; v < v1; v += lanes) {
       float g[8], xh[8];
       norm_bwd_g(a, k, v, c8, g, xh);
 #pragma unroll
@@ -569,7 +648,22 @@ __global__ void __launch_bounds__(kThreads) instnorm_bwd_apply_kernel(NormBwdArg
   }
   const int64_t v0 = (int64_t)n * a.vox_per_sample + (int64_t)blockIdx.x * vox_per_block;
   const int64_t v1 = min((int64_t)(n + 1) * a.vox_per_sample, v0 + vox_per_block);
-  for (int64_t v = v0 + l; v < v1; v += lanes) {
+  int64_t v = v0 + l;
+  for (; v + (int64_t)lanes < v1; v += 2 * (int64_t)lanes) {  // two voxels per trip
+    NormBwdRaw r0, r1;
+    norm_bwd_load(a, v, c8, r0);
+    norm_bwd_load(a, v + lanes, c8, r1);
+    float g[8], xh[8];
+    norm_bwd_compute(a, k, r0, g, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = ca[i] * (g[i] - cm1[i] - xh[i] * cm2[i]);
+    stg16(dx + v * a.C + c8 * 8, pack8(g));
+    norm_bwd_compute(a, k, r1, g, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = ca[i] * (g[i] - cm1[i] - xh[i] * cm2[i]);
+    stg16(dx + (v + lanes) * a.C + c8 * 8, pack8(g));
+  }
+  for (; v < v1; v += lanes) {
     float g[8], xh[8];
     norm_bwd_g(a, k, v, c8, g, xh);
 #pragma unroll
