@@ -500,6 +500,14 @@ def bench_infer(e, args, steps, warmup):
     for _ in range(2):
         call(volp)
     _, t_pin = timed_calls(volp)
+    # the same call with the inference passes on the three-issuer conv mode (Model.set_fast_inference: results are no
+    # longer bit-identical run to run; the default above is the reproducible mode)
+    model.set_fast_inference(True)
+    for _ in range(2):
+        out_fast = call(vol)
+    _, t_fast = timed_calls(vol)
+    model.set_fast_inference(False)
+    fast_dev = float(np.abs(out_fast - out).max())
     # the calls are 10 ms of wall clock each on a shared host: the median over the timed calls is the figure, the mean
     # (which a single descheduled call can double) is printed beside it
     s_page, s_pin = float(np.median(t_page)), float(np.median(t_pin))
@@ -536,6 +544,11 @@ def bench_infer(e, args, steps, warmup):
                                 d2h_bytes_per_step=int(out.nbytes), ms_per_step=s_pin * 1e3,
                                 ms_per_step_mean=float(np.mean(t_pin)) * 1e3,
                                 host_buffers="pinned input, pageable output"),
+                e2e_fast_inference=dict(value=nvox / float(np.median(t_fast)), unit=UNIT,
+                                        ms_per_step=float(np.median(t_fast)) * 1e3, host_buffers="pageable numpy",
+                                        max_abs_diff_vs_reproducible=fast_dev,
+                                        note="Model.set_fast_inference(True): three-issuer MMA order, not bit-reproducible "
+                                             "run to run"),
                 gpu_launches=launches, roofline=roofs.get("conv3d_march_fprop"), rooflines=roofs,
                 patch_voxels_per_s=49 * int(np.prod(PATCH)) / s_page,
                 conv_tflops=49 * FWD_GF_PER_PATCH / dev_ms, out_mean=float(out.mean()), kernel_breakdown=breakdown)

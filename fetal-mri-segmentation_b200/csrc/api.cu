@@ -322,6 +322,9 @@ struct fm_model {
   // training passes use the shared-accumulator marching kernel (faster; fp32 summation order not fixed), inference
   // the bit-reproducible one
   bool train_pass = false;
+  // fm_model_set_inference_mode(m, 1): predict / evaluate / patch_wise_prediction also take the three-issuer mode
+  // (about 25 % more conv throughput, results no longer bit-identical from run to run)
+  bool fast_inference = false;
   // training forward with the targets already in t_in: the head kernel also produces the loss statistics
   bool targets_ready = false, stats_done = false;
 
@@ -360,7 +363,7 @@ static bool shared_march(const fm_model* m, int n_channels) {
     const char* e = getenv("FETAL_B200_DETERMINISTIC");
     return e && e[0] == '1';
   }();
-  return m->train_pass && n_channels <= 32 && !det;
+  return (m->train_pass || m->fast_inference) && n_channels <= 32 && !det;
 }
 
 static int build_unet(fm_ctx* ctx, const fm_unet3d_spec* spec, int kcode, int flags, fm_model** out);
@@ -747,6 +750,12 @@ extern "C" int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed) {
   FM_CHECK(rate >= 0.f && rate < 1.f, FM_EINVAL, "dropout rate %g outside [0,1)", (double)rate);
   m->dropout_rate = rate;
   m->dropout_seed = seed;
+  return FM_OK;
+}
+
+extern "C" int fm_model_set_inference_mode(fm_model* m, int fast) {
+  FM_CHECK(m, FM_EINVAL, "NULL model");
+  m->fast_inference = fast != 0;
   return FM_OK;
 }
 

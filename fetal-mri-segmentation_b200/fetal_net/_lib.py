@@ -82,6 +82,7 @@ SIGNATURES = {
     "fm_model_reset_optimizer": (c_int, [c_vp]),
     "fm_model_set_dropout": (c_int, [c_vp, ctypes.c_float, ctypes.c_uint64]),
     "fm_model_set_loss": (c_int, [c_vp, c_int, ctypes.c_float, ctypes.c_float]),
+    "fm_model_set_inference_mode": (c_int, [c_vp, c_int]),
     "fm_model_set_weight_mask": (c_int, [c_vp, c_fp, c_int]),
     "fm_train_metrics_async": (c_int, [c_vp]),
     "fm_train_metrics_wait": (c_int, [c_vp, c_fp]),

@@ -171,6 +171,12 @@ int fm_model_set_iterations(fm_model* m, int iterations);
  * (fm_train_*), one keep/scale factor per (sample, channel) drawn from a counter-based hash of (seed, step, level);
  * rate 0 (the default here) switches it off. Plain U-Net models ignore it. */
 int fm_model_set_dropout(fm_model* m, float rate, uint64_t seed);
+/* No counterpart in the reference (Keras picks its own conv algorithms). fast = 0 (default): predict / evaluate /
+ * patch_wise_prediction issue their tensor-core MMAs in a fixed order - the same input gives the same bits on every
+ * run. fast = 1: inference takes the three-issuer mode of the training passes (about a quarter more conv throughput);
+ * results then differ in the last bf16 bit from run to run, exactly like a training pass. Tolerances against the
+ * oracle are unaffected. FETAL_B200_DETERMINISTIC=1 overrides it. */
+int fm_model_set_inference_mode(fm_model* m, int fast);
 /* Replaces: the `loss_function` argument of the builders, looked up by getattr(fetal_net.metrics, config['loss'])
  * (fetal/train_fetal.py:31, fetal_net/training.py:51-58):
  *   kind 0  dice_coefficient_loss                       (fetal_net/metrics.py:31-32)                    [default]

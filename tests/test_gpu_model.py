@@ -794,3 +794,21 @@ def test_unet2d_batch_normalization_matches_oracle():
     new = dict(zip([l["name"] for l in model.layers], zip(model.get_weights()[0::2], model.get_weights()[1::2])))
     for name in ("enc0a", "dec0b"):
         assert np.abs(new[name + "_moving"][1] / upd[name + "/moving_variance"] - 1).max() <= 5e-3, name
+
+
+def test_fast_inference_mode_stays_within_tolerance(setup):
+    """Model.set_fast_inference (fm_model_set_inference_mode): the three-issuer conv mode in inference differs from
+    the reproducible default only in the accumulation order - last-bit differences of bf16 activations, far inside
+    the stated tolerance against the oracle; switching back restores bit-identical results."""
+    model, w = setup
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 1, 32, 32, 32)).astype(np.float32)
+    p0 = model.predict(x)
+    assert np.array_equal(model.predict(x), p0)
+    model.set_fast_inference(True)
+    p1 = model.predict(x)
+    model.set_fast_inference(False)
+    assert np.array_equal(model.predict(x), p0)
+    with torch.no_grad():
+        ref = uo.unet3d_forward(torch.as_tensor(x), w).numpy()
+    assert np.abs(p1 - p0).max() <= 0.02 and np.abs(p1 - ref).mean() <= 0.006
