@@ -381,3 +381,6 @@ int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize
 // db (optional): the bias gradient [Cout] = column sums of dY, accumulated (atomics) by the same launch
 int k_conv3d_wgrad_march(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
                          int Cin, int Cin_total, int cin_ofs, int Cout, float* db = nullptr);
+// second generation (conv_wgrad_march2.cu): one X slab per plane, the kz shift on z-shifted dY copies (N = 192 + 96)
+int k_conv3d_wgrad_march2(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
+                         int Cin, int Cin_total, int cin_ofs, int Cout, float* db = nullptr);

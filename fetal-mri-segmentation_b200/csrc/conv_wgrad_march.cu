@@ -48,7 +48,8 @@ struct alignas(64) WgMarchParams {
   CUtensorMap tmX;   // box (32, 8, 19, 1, 1)
   CUtensorMap tmDY;  // box (32, 8, 16, 1, 1)
   int N, X, Y, Z;
-  int ny, nz, nxc, xchunk, items;
+  int ny, nz;
+  int T;                 // plane-tiles of the problem: (sample, y tile, z tile) columns x X planes
   int n_ci, n_co;      // 32-channel chunks of Cin (this source) and Cout
   int ctas_per_pair;   // grid = n_ci * n_co * ctas_per_pair
   int S3;              // X slab slots per kz ring
@@ -110,15 +111,22 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 
-  auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) {
-    const int jx = item % p.nxc;
-    int t = item / p.nxc;
-    iz = t % p.nz;
-    t /= p.nz;
-    iy = t % p.ny;
-    n = t / p.ny;
-    xa = jx * p.xchunk;
-    xb = min(p.X, xa + p.xchunk);
+  // Work split: the flat sequence of plane-tiles (column-major: column = (sample, y tile, z tile), then x) is cut into
+  // ctas_per_pair equal contiguous ranges, so every CTA marches over the same number of planes (+-1) whatever the
+  // shape; a range that crosses a column boundary becomes several segments [xa, xb) of consecutive columns.
+  const int t_begin = (int)((int64_t)rank * p.T / p.ctas_per_pair);
+  const int t_end = (int)((int64_t)(rank + 1) * p.T / p.ctas_per_pair);
+  auto next_seg = [&](int& t, int& n, int& iy, int& iz, int& xa, int& xb) -> bool {
+    if (t >= t_end) return false;
+    const int col = t / p.X;
+    xa = t - col * p.X;
+    xb = min(p.X, xa + (t_end - t));
+    iz = col % p.nz;
+    const int r = col / p.nz;
+    iy = r % p.ny;
+    n = r / p.ny;
+    t += xb - xa;
+    return true;
   };
 
   if (warp_u < kProdW) {
@@ -131,9 +139,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     uint32_t sidx = 0, sph = 0;
     uint32_t dcount = 0;  // dY tiles issued so far (ring position)
     const uint32_t slot0 = (uint32_t)dz * (uint32_t)p.S3;
-    for (int item = rank; item < p.items; item += p.ctas_per_pair) {
-      int n, iy, iz, xa, xb;
-      decode(item, n, iy, iz, xa, xb);
+    for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       int next_dy = xa;  // next output plane whose dY tile has to be loaded
       for (int xi = x_first; xi <= x_last; ++xi) {
@@ -178,9 +184,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     tc_fence_after();
     uint32_t sidx = 0, sph = 0, dcount = 0, dwaited = 0;
     const uint32_t slot0 = (uint32_t)dz * (uint32_t)p.S3;
-    for (int item = rank; item < p.items; item += p.ctas_per_pair) {
-      int n, iy, iz, xa, xb;
-      decode(item, n, iy, iz, xa, xb);
+    for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       for (int xi = x_first; xi <= x_last; ++xi) {
         const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes paired with input plane xi
@@ -240,9 +244,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       uint32_t dcount = 0;
-      for (int item = rank; item < p.items; item += p.ctas_per_pair) {
-        int n, iy, iz, xa, xb;
-        decode(item, n, iy, iz, xa, xb);
+      for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
         for (int xo = xa; xo < xb; ++xo, ++dcount) {
           const uint32_t slot = dcount & (uint32_t)(kDyRing - 1);
           mbar_wait(dyfull_bar(slot), (dcount >> 3) & 1u);
@@ -338,6 +340,7 @@ int make_map(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int 
 }
 
 const int kMaxDynSmemW = 227 * 1024;
+const int kDefaultWgradGen = 1;
 
 }  // namespace
 
@@ -350,6 +353,14 @@ int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize
 
 int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
                          int Cin, int Cin_total, int cin_ofs, int Cout, float* db) {
+  {
+    // FETAL_B200_WGRAD_GEN=1|2 selects the kernel generation (A/B measurements); see conv_wgrad_march2.cu
+    static const int gen = [] {
+      const char* e = getenv("FETAL_B200_WGRAD_GEN");
+      return e ? atoi(e) : kDefaultWgradGen;
+    }();
+    if (gen == 2) return k_conv3d_wgrad_march2(ctx, x, dy, dw_packed, N, X, Y, Z, Cin, Cin_total, cin_ofs, Cout, db);
+  }
   FM_CHECK(conv_wgrad_march_supported(X, Y, Z, Cin, Cout, 3), FM_EINVAL,
            "conv3d wgrad march: unsupported shape %dx%dx%d Cin=%d Cout=%d", X, Y, Z, Cin, Cout);
   WgMarchParams p;
@@ -370,16 +381,9 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   p.db = db;
   const int pairs = p.n_ci * p.n_co;
   const int cols = N * p.ny * p.nz;
-  p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, cols * std::max(1, X / 4)));
-  // x-chunking so that every CTA of a pair gets work: items >= ctas_per_pair, chunks of >= 4 planes
-  {
-    int nxc = 1;
-    while (cols * nxc < p.ctas_per_pair * 2 && ceil_div(X, nxc * 2) >= 4) nxc *= 2;
-    p.xchunk = ceil_div(X, nxc);
-    p.nxc = ceil_div(X, p.xchunk);
-    p.items = cols * p.nxc;
-    p.ctas_per_pair = std::min(p.ctas_per_pair, p.items);
-  }
+  p.T = cols * X;
+  // equal contiguous ranges of plane-tiles per CTA (see the kernel), at least 4 planes each
+  p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, p.T / 4));
   FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));  // halo + discarded M blocks
   FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy));
   p.S3 = 4;

@@ -121,3 +121,18 @@ def test_dice_and_xent_sums_and_gradient(ctx, with_mask):
 def test_keras_adam(ctx):
     ok, worst = gc.adam_case(ctx)
     assert ok, worst
+
+
+def test_wgrad_march_second_generation_in_subprocess():
+    """conv_wgrad_march2.cu (one X slab per plane, kz on z-shifted dY copies; FETAL_B200_WGRAD_GEN=2) is kept as a
+    measured alternative to the default kernel: same parity bar, run in a subprocess because the generation is read
+    from the environment once per process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, FETAL_B200_WGRAD_GEN="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ops.py"), "-q", "-m", "gpu",
+                        "-k", "wgrad_march and not second_generation", "-x", "-p", "no:cacheprovider"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
