@@ -44,7 +44,8 @@ struct alignas(64) March2Params {
   int KC[2];
   uint32_t wofs[2];  // byte offset of the source's resident weights inside the W region
   int N, X, Y, Z;
-  int ny, nz, nxc, xchunk, items;
+  int ny, nz;
+  int T;       // plane-tiles of the problem: columns x X planes
   int R;       // accumulator ring blocks (power of two)
   int stages;  // slab slots, a multiple of 3 (one private ring per dz slab copy)
   int out_C, out_cofs, relu;
@@ -150,15 +151,24 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) {
-    const int jx = item % p.nxc;
-    int t = item / p.nxc;
-    iz = t % p.nz;
-    t /= p.nz;
-    iy = t % p.ny;
-    n = t / p.ny;
-    xa = jx * p.xchunk;
-    xb = min(p.X, xa + p.xchunk);
+  // Work split: the flat (column, x) sequence of plane-tiles (column = (sample, y tile, z tile)) is cut into gridDim.x
+  // equal contiguous ranges; `item` = blockIdx.x + k * gridDim.x names the k-th segment of this CTA's range (a range
+  // that crosses a column boundary has several segments [xa, xb) in consecutive columns). Every CTA marches the same
+  // number of planes (+-1) whatever the shape. Returns false past the last segment.
+  const int t_begin = (int)((int64_t)blockIdx.x * p.T / gridDim.x);
+  const int t_end = (int)((int64_t)(blockIdx.x + 1) * p.T / gridDim.x);
+  auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) -> bool {
+    const int k = item / (int)gridDim.x;
+    const int col = t_begin / p.X + k;
+    const int lo = k == 0 ? t_begin : col * p.X;
+    if (lo >= t_end) return false;
+    xa = lo - col * p.X;
+    xb = min(p.X, t_end - col * p.X);
+    iz = col % p.nz;
+    const int r = col / p.nz;
+    iy = r % p.ny;
+    n = r / p.ny;
+    return true;
   };
 
   // make the values the producer / MMA warps compute on provably warp-uniform
@@ -187,9 +197,7 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
     const uint32_t bytes1 = (dbg & 1) ? 0u : (uint32_t)kSlabRows * (uint32_t)p.KC[1] * 2u;
     const int nch0 = p.nchunks[0], nch1 = p.nsrc > 1 ? p.nchunks[1] : 0;
     const int kc0 = p.KC[0], kc1 = p.KC[1];
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      int n, iy, iz, xa, xb;
-      decode(item, n, iy, iz, xa, xb);
+    for (int item = blockIdx.x, n, iy, iz, xa, xb; decode(item, n, iy, iz, xa, xb); item += gridDim.x) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       const int yc = iy * kBY - 1, zc = iz * kBZ - 1 + dz;
       for (int xi = x_first; xi <= x_last; ++xi) {
@@ -261,9 +269,7 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
         turn = (uint32_t)mw;
       }
       uint32_t ocount = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        int n, iy, iz, xa, xb;
-        decode(item, n, iy, iz, xa, xb);
+      for (int item = blockIdx.x, n, iy, iz, xa, xb; decode(item, n, iy, iz, xa, xb); item += gridDim.x) {
         const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
         for (int xi = x_first; xi <= x_last; ++xi) {
           if (PLANE_OWNERS) {
@@ -405,9 +411,8 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
     int64_t it_off = 0;
     const int64_t it_step = (int64_t)p.Y * p.Z * p.out_C;
     auto it_load = [&]() -> bool {
-      if (it_item >= p.items) return false;
       int n, iy, iz, xa, xb;
-      decode(it_item, n, iy, iz, xa, xb);
+      if (!decode(it_item, n, iy, iz, xa, xb)) return false;
       it_xo = xa;
       it_xb = xb;
       const int64_t v0 = (((int64_t)n * p.X + xa) * p.Y + (iy * kBY + yl)) * p.Z + (iz * kBZ + zl);
@@ -587,26 +592,7 @@ int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1
   p.bias = bias;
   p.out = y;
   p.mask = mask;
-  // x-chunking: trade wave quantisation against the 2 halo planes each chunk re-loads
-  {
-    const int cols = N * p.ny * p.nz;
-    double best = -1.0;
-    int best_nxc = 1;
-    for (int nxc = 1; nxc <= 16; nxc *= 2) {
-      const int xc = ceil_div(X, nxc);
-      if (xc < 4 && nxc > 1) break;
-      const int items = cols * ceil_div(X, xc);
-      const int waves = ceil_div(items, ctx->num_sms);
-      const double eff = (double)items / ((double)waves * ctx->num_sms) * (double)xc / (double)(xc + 1.4);
-      if (eff > best) {
-        best = eff;
-        best_nxc = nxc;
-      }
-    }
-    p.xchunk = ceil_div(X, best_nxc);
-    p.nxc = ceil_div(X, p.xchunk);
-    p.items = cols * p.nxc;
-  }
+  p.T = N * p.ny * p.nz * X;
   const int Cs[2] = {C1, C2};
   const bf16* xs[2] = {x1, x2};
   const bf16* wms[2] = {wm1, wm2};
@@ -653,7 +639,7 @@ int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1
   p.stages = stages;
   const size_t smem = (size_t)wofs + (size_t)stages * p.slot + 2048;
   FM_CHECK(smem <= (size_t)kMaxDynSmem2, FM_EINVAL, "conv3d march2: %zu B of shared memory needed", smem);
-  const int grid = std::min(p.items, ctx->num_sms);
+  const int grid = std::max(1, std::min(p.T / 4, ctx->num_sms));  // equal ranges of >= 4 planes (see the kernel)
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_march_dgrad" : "conv3d_march_fprop",
                  2.0 * 27 * (C1 + C2) * Cout * vox, vox * (C1 + C2 + Cout) * 2.0);

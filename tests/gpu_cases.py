@@ -71,6 +71,9 @@ MARCH_CASES = [
     ("m64_16_32cube", 1, 32, 32, 32, 64, 0, 16, 3),     # N = 16 blocks
     ("m_x2", 2, 2, 16, 8, 16, 0, 16, 3),                # only two planes
     ("m_cfg_64cube_32_32", 1, 64, 64, 64, 32, 0, 32, 3),  # dec0b at the real patch size
+    # equal plane ranges per CTA that cross column boundaries: segments of 1-4 planes (7 planes per column, 4 per CTA)
+    ("m_ragged_7x32x16", 2, 7, 32, 16, 32, 0, 32, 3),
+    ("m_ragged_cat_13x32x32", 1, 13, 32, 32, 64, 32, 32, 3),
 ]
 
 
@@ -85,6 +88,8 @@ WGRAD_MARCH_CASES = [
     ("w16_32_32cube", 2, 32, 32, 32, 16, 0, 32, 3),      # enc0b: Cin = 16 (SWIZZLE_32B X operand, 8 M blocks)
     ("w16_16_32cube", 2, 32, 32, 32, 16, 0, 16, 3),      # Isensee level 0: Cout = 16 (SWIZZLE_32B dY, N = 48)
     ("w32_16_16x16x24", 1, 16, 16, 24, 32, 0, 16, 3),    # Isensee u0_up: 32 -> 16
+    ("w_ragged_7x32x16", 2, 7, 32, 16, 32, 0, 32, 3),    # plane ranges crossing column boundaries, 1-plane segments
+    ("w_ragged_13x32x32", 1, 13, 32, 32, 64, 0, 32, 3),
 ]
 
 
