@@ -667,6 +667,10 @@ int k_conv3d_tc_fprop(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* w
   p.tz = ceil_div(Z, p.bz);
   p.m_tiles = N * p.tx * p.ty * p.tz;
   p.block_n = std::min(Cout, 128);
+  // small problems (the 8^3 level: 32 voxel tiles): at the widest N tile fewer than half of the SMs would get a CTA,
+  // and each of those walks its 27 x Cin/64 pipeline stages at L2 latency. Narrower N tiles put 4x the SMs to work
+  // (every N tile re-reads the A tiles from L2 - these layers are latency-bound, not bandwidth-bound).
+  while (p.block_n > 32 && p.m_tiles * (Cout / p.block_n) * 2 <= ctx->num_sms) p.block_n /= 2;
   p.n_tiles = Cout / p.block_n;
   p.ksize = ksize;
   p.ntaps = kext_taps(ksize);
