@@ -432,7 +432,7 @@ def bench_allreduce(e, rec_train, steps):
                 bus_gbs=2.0 * (n - 1) / n * nbytes / (ms * 1e-3) / 1e9, bus_peak_gbs=900.0,
                 frac_of_nvlink=2.0 * (n - 1) / n * nbytes / (ms * 1e-3) / 1e9 / 900.0,
                 step_ms_with_comm=on, step_ms_without_comm=off, exposed_ms=max(on - off, 0.0),
-                note="16.3 MB fp32 in %d buckets + 64 B of Dice sums per step: latency-bound message sizes; "
+                note="16.3 MB fp32 in %d buckets + 72 B of loss sums per step: latency-bound message sizes; "
                      "exposed = step with collectives minus the same step with them switched off (fm_comm_enable)" %
                      int(e.lib.fm_model_num_buckets(model._h)))
 

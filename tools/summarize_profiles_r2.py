@@ -100,8 +100,10 @@ def main():
         if which == "train":
             heads = [i for i, d in enumerate(recs) if d["kernel"].startswith("head_fwd_dice")]
             firsts = [i for i, d in enumerate(recs) if d["kernel"].startswith("conv3d_first_tc_kernel<0>")]
+            adams = [i for i, d in enumerate(recs) if d["kernel"].startswith("adam_kernel")]
             # the first complete step of the capture (the 15-minute budget of the capture may cut the last one short)
-            lo, hi = firsts[0], (firsts[1] if len(firsts) > 1 else len(recs))
+            lo = firsts[0]
+            hi = firsts[1] if len(firsts) > 1 else (adams[0] + 3 if adams and adams[0] > lo else len(recs))
             head = [h for h in heads if h > lo][0]
             for i, d in enumerate(recs[lo:hi], lo):
                 phase = "fwd" if i <= head else "bwd"
