@@ -459,3 +459,26 @@ def test_dice_and_xent_host_helpers_and_device_loss_spec():
     assert spec(fm.dice_and_xent_mask, has_mask_input=True) == (2, 1.0, 3.0)
     assert spec(fm.dice_and_xent_mask(None, xent_weight=2.0, dist_sigma=5), has_mask_input=True) == (2, 2.0, 5.0)
     assert spec(fm.vod_coefficient_loss) is None and spec(fm.focal_loss) is None
+
+
+def test_keras_h5_bridge_orders_transposed_convs_and_batch_norm_statistics():
+    """fetal_net.keras_h5: Deconvolution3D layers ('conv3d_transpose_<n>') and BatchNormalization layers (gamma, beta,
+    moving_mean, moving_variance) of a deconvolution=True / batch_normalization=True reference checkpoint are numbered on
+    their own, in creation order, under the names Model.load_weights looks up."""
+    from fetal_net import keras_h5
+    z = lambda *s: np.zeros(s, np.float32)
+    # graph-depth order as a Keras file would list it: suffixes are the creation order
+    entries = [("conv", "conv3d_12", z(3, 3, 3, 8, 8), z(8)), ("deconv", "conv3d_transpose_4", z(2, 2, 2, 8, 8) + 4, z(8)),
+               ("norm", "batch_normalization_9", z(8) + 9, z(8)), ("moving", "batch_normalization_9", z(8) + 90, z(8)),
+               ("conv", "conv3d_11", z(3, 3, 3, 1, 8), z(8)), ("deconv", "conv3d_transpose_3", z(2, 2, 2, 8, 8) + 3, z(8)),
+               ("norm", "batch_normalization_8", z(8) + 8, z(8)), ("moving", "batch_normalization_8", z(8) + 80, z(8))]
+    arrays = keras_h5.to_npz_arrays(keras_h5.creation_order(entries))
+    assert arrays["conv3d_1/kernel:0"].shape == (3, 3, 3, 1, 8) and arrays["conv3d_2/kernel:0"].shape == (3, 3, 3, 8, 8)
+    assert arrays["conv3d_transpose_1/kernel:0"].flat[0] == 3 and arrays["conv3d_transpose_2/kernel:0"].flat[0] == 4
+    assert arrays["batch_normalization_1/gamma:0"][0] == 8 and arrays["batch_normalization_2/gamma:0"][0] == 9
+    assert arrays["batch_normalization_1/moving_mean:0"][0] == 80
+    assert arrays["batch_normalization_2/moving_mean:0"][0] == 90
+    assert "batch_normalization_2/moving_variance:0" in arrays
+    # instance-norm checkpoints keep their names
+    arrays = keras_h5.to_npz_arrays([("norm", "instance_normalization_5", z(4) + 1, z(4))])
+    assert list(arrays) == ["instance_normalization_1/gamma:0", "instance_normalization_1/beta:0"]
