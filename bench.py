@@ -10,6 +10,9 @@ communicator). Nested records cover the rest of the metric:
 
   infer          configs[0]: patch_wise_prediction of one 1x256x256x64 volume, patch 64^3, overlap_factor 0.5 (49
                  patches): device time, e2e with PAGEABLE and with pinned host buffers, conv / HBM rooflines.
+  train_sampled  (N = 1) the same step fed by the on-device patch sampler (DeviceSampler.train_on_next_batch).
+  families       (N = 1) configs[2] (Isensee-2017, 2 x 128x128x64) and configs[3] (2.5D U-Net, 8 x 256x256x6): step,
+                 e2e, predict, roofline of their dominant kernel.
   train_cfg5     (N > 1) configs[4]'s patch shape: batch 8 x 1x128x128x64 per GPU, same data-parallel step.
   infer_sharded  (N > 1) sharded_patch_wise_prediction of one 1x512x512x128 volume, patch 128x128x64 (147 patches).
   allreduce      (N > 1) gradient all-reduce: bytes, standalone ms and bus GB/s = 2 (n-1)/n * bytes / t, and the
@@ -406,6 +409,33 @@ def bench_train(e, args, patch, fwd_gf, first_gf, steps, warmup, with_profile):
     return rec
 
 
+def bench_train_sampled(e, steps, plain_ms):
+    """fit_generator's inner loop fed by the on-device sampler (fetal_net.device_sampler, the generator.py:243-348
+    counterpart): per step the host draws (case, corner) with the reference generator's RNG call sequence, 32 bytes per
+    sample cross the bus, the patches are cut from the resident volume set straight into the network's input buffers.
+    Wall clock around DeviceSampler.train_on_next_batch at the configs[1] shape, beside the plain device step."""
+    from fetal_net.device_sampler import DeviceSampler
+    from fetal_net.model import unet_model_3d
+    rng = np.random.default_rng(7)
+    shape = (160, 160, 96)
+    data = [rng.standard_normal(shape).astype(np.float32) for _ in range(6)]
+    truth = [(rng.random(shape) < 0.3).astype(np.float32) for _ in range(6)]
+    np.random.seed(1)
+    sampler = DeviceSampler(data, truth, list(range(6)), batch_size=BATCH, patch_shape=PATCH, shuffle_index_list=True,
+                            skip_blank=True, truth_index=0, truth_size=PATCH[2], is3d=True, device=e.local)
+    model = unet_model_3d(input_shape=(1,) + PATCH, n_base_filters=NF, depth=DEPTH, initial_learning_rate=1e-4,
+                          device=e.local)
+    model.init_glorot_uniform(seed=0)
+    for _ in range(3):
+        sampler.train_on_next_batch(model)
+    sec = timed_wall(e, lambda: sampler.train_on_next_batch(model), steps)
+    vox = BATCH * int(np.prod(PATCH))
+    return dict(value=vox / sec, unit=UNIT, ms_per_step=sec * 1e3, fraction_of_device_step_rate=plain_ms / (sec * 1e3),
+                config=dict(workload="DeviceSampler.train_on_next_batch: 6 resident cases of 160x160x96, batch 8 x 64^3 "
+                                     "cut on the device (skip_blank=True, shuffled index list), same model as the "
+                                     "headline step", host_bytes_per_step=32 * BATCH))
+
+
 def bench_allreduce(e, rec_train, steps):
     """Gradient all-reduce: standalone bus bandwidth, and the exposed time per step (collectives on vs off)."""
     dp, model = rec_train["_dp"], rec_train["_model"]
@@ -686,6 +716,7 @@ def run_b200(args):
                                     (e.ctx.comm_info()[2],)) if e.world > 1 else None)
             line.update(extra)
     if args.workload == "all" and e.rank == 0 and e.world == 1 and line is not None:
+        line["train_sampled"] = bench_train_sampled(e, args.steps, line["ms_per_step"])
         line["families"] = dict(isensee=bench_family(e, "isensee", max(3, args.steps // 4)),
                                 unet2d=bench_family(e, "unet2d", max(3, args.steps // 4)))
     if want_infer and e.rank == 0:
