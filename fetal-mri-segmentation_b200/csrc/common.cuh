@@ -129,6 +129,67 @@ __host__ __device__ static inline int kext_taps(int kcode) { return kext_xy(kcod
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ------------------------------------------------------------------------------------------
+// Work split of the plane-marching kernels. A problem is `cols` columns (sample, y tile, z tile) of X planes each; a CTA
+// marches along x inside a column.
+//   mode 0  equal ranges: the flat (column, x) sequence is cut into G contiguous ranges of T / G planes (+-1); a range
+//           that crosses a column boundary has several segments. Perfect balance, but neighbouring columns are walked at
+//           unrelated times, so the y / z halos they share are re-read from DRAM instead of L2.
+//   mode 1  lock-step chunks: every column is cut into nxc chunks of xchunk planes; work unit u = chunk * cols + column,
+//           CTA r takes units r, r + G, ... - a wave of G units covers neighbouring columns at the SAME x range, the
+//           halo re-reads hit L2 (DRAM traffic = algorithmic bytes); nxc is chosen on the host for wave efficiency.
+// `it` counts the CTA's segments / units from 0. Returns false when the CTA is done.
+// ------------------------------------------------------------------------------------------
+struct PlaneSplit {
+  int mode, T, X, cols, nxc, xchunk;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ bool plane_split_next(const PlaneSplit& s, int rank, int G, int it, int& col, int& xa, int& xb) {
+  if (s.mode == 0) {
+    const int t_begin = (int)((int64_t)rank * s.T / G), t_end = (int)((int64_t)(rank + 1) * s.T / G);
+    col = t_begin / s.X + it;
+    const int lo = it == 0 ? t_begin : col * s.X;
+    if (lo >= t_end) return false;
+    xa = lo - col * s.X;
+    xb = min(s.X, t_end - col * s.X);
+    return true;
+  }
+  const int u = rank + it * G;
+  if (u >= s.cols * s.nxc) return false;
+  const int xc = u / s.cols;
+  col = u - xc * s.cols;
+  xa = xc * s.xchunk;
+  xb = min(s.X, xa + s.xchunk);
+  return true;
+}
+#endif
+// host side: fills `s` for `G` CTAs (halo = planes a chunk re-loads, in units of a plane's cost); FETAL_B200_SPLIT=0|1
+static inline void plane_split_setup(PlaneSplit* s, int cols, int X, int G, double halo) {
+  static const int forced = [] {
+    const char* e = getenv("FETAL_B200_SPLIT");
+    return e ? atoi(e) : -1;
+  }();
+  s->mode = forced >= 0 ? forced : 1;
+  s->T = cols * X;
+  s->X = X;
+  s->cols = cols;
+  double best = -1.0;
+  int best_nxc = 1;
+  for (int nxc = 1; nxc <= 32; nxc *= 2) {
+    const int xc = (X + nxc - 1) / nxc;
+    if (xc < 4 && nxc > 1) break;
+    const int units = cols * ((X + xc - 1) / xc);
+    const int waves = (units + G - 1) / G;
+    const double eff = (double)units / ((double)waves * G) * (double)xc / ((double)xc + halo);
+    if (eff > best) {
+      best = eff;
+      best_nxc = nxc;
+    }
+  }
+  s->xchunk = (X + best_nxc - 1) / best_nxc;
+  s->nxc = (X + s->xchunk - 1) / s->xchunk;
+}
+
 // Per-launch profiling hooks: `flops` / `bytes` are the ALGORITHMIC figures of the launch.
 int fm_prof_begin(fm_ctx* ctx, const char* name, double flops, double bytes);
 int fm_prof_end(fm_ctx* ctx);

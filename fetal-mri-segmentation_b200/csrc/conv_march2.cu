@@ -45,7 +45,7 @@ struct alignas(64) March2Params {
   uint32_t wofs[2];  // byte offset of the source's resident weights inside the W region
   int N, X, Y, Z;
   int ny, nz;
-  int T;       // plane-tiles of the problem: columns x X planes
+  PlaneSplit split;  // how the (column, x) plane-tiles are dealt to the CTAs (common.cuh)
   int R;       // accumulator ring blocks (power of two)
   int stages;  // slab slots, a multiple of 3 (one private ring per dz slab copy)
   int out_C, out_cofs, relu;
@@ -151,25 +151,18 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // Work split: the flat (column, x) sequence of plane-tiles (column = (sample, y tile, z tile)) is cut into gridDim.x
-  // equal contiguous ranges; `item` = blockIdx.x + k * gridDim.x names the k-th segment of this CTA's range (a range
-  // that crosses a column boundary has several segments [xa, xb) in consecutive columns). Every CTA marches the same
-  // number of planes (+-1) whatever the shape. Returns false past the last segment.
-  const int t_begin = (int)((int64_t)blockIdx.x * p.T / gridDim.x);
-  const int t_end = (int)((int64_t)(blockIdx.x + 1) * p.T / gridDim.x);
+  // `item` = blockIdx.x + k * gridDim.x names the k-th segment / work unit of this CTA (PlaneSplit in common.cuh).
+  // Returns false past the last one.
   auto decode = [&](int item, int& n, int& iy, int& iz, int& xa, int& xb) -> bool {
-    const int k = item / (int)gridDim.x;
-    const int col = t_begin / p.X + k;
-    const int lo = k == 0 ? t_begin : col * p.X;
-    if (lo >= t_end) return false;
-    xa = lo - col * p.X;
-    xb = min(p.X, t_end - col * p.X);
+    int col;
+    if (!plane_split_next(p.split, (int)blockIdx.x, (int)gridDim.x, item / (int)gridDim.x, col, xa, xb)) return false;
     iz = col % p.nz;
     const int r = col / p.nz;
     iy = r % p.ny;
     n = r / p.ny;
     return true;
   };
+
 
   // make the values the producer / MMA warps compute on provably warp-uniform
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -592,7 +585,6 @@ int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1
   p.bias = bias;
   p.out = y;
   p.mask = mask;
-  p.T = N * p.ny * p.nz * X;
   const int Cs[2] = {C1, C2};
   const bf16* xs[2] = {x1, x2};
   const bf16* wms[2] = {wm1, wm2};
@@ -639,7 +631,9 @@ int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1
   p.stages = stages;
   const size_t smem = (size_t)wofs + (size_t)stages * p.slot + 2048;
   FM_CHECK(smem <= (size_t)kMaxDynSmem2, FM_EINVAL, "conv3d march2: %zu B of shared memory needed", smem);
-  const int grid = std::max(1, std::min(p.T / 4, ctx->num_sms));  // equal ranges of >= 4 planes (see the kernel)
+  int grid = std::max(1, std::min(N * p.ny * p.nz * X / 4, ctx->num_sms));
+  plane_split_setup(&p.split, N * p.ny * p.nz, X, grid, 1.4);
+  if (p.split.mode == 1) grid = std::min(grid, N * p.ny * p.nz * p.split.nxc);
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, mask != nullptr || bias == nullptr ? "conv3d_march_dgrad" : "conv3d_march_fprop",
                  2.0 * 27 * (C1 + C2) * Cout * vox, vox * (C1 + C2 + Cout) * 2.0);

@@ -38,7 +38,7 @@ struct alignas(64) WgMarch2Params {
   CUtensorMap tmDY;  // box (kcy, 8, 16, 1, 1)
   int N, X, Y, Z;
   int ny, nz;
-  int T;                 // plane-tiles of the problem: (sample, y tile, z tile) columns x X planes
+  PlaneSplit split;      // how the (column, x) plane-tiles are dealt to the CTAs of a pair (common.cuh)
   int n_ci, n_co;
   int ctas_per_pair;
   int S;               // X slab slots
@@ -102,21 +102,15 @@ __global__ void __launch_bounds__(kThreadsW2, 1) conv3d_wgrad_march2_kernel(cons
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t R = (uint32_t)p.R;
 
-  // Work split: the flat sequence of plane-tiles (column-major: column = (sample, y tile, z tile), then x) is cut into
-  // ctas_per_pair equal contiguous ranges, so every CTA marches over the same number of planes (+-1) whatever the
-  // shape; a range that crosses a column boundary becomes several segments [xa, xb) of consecutive columns.
-  const int t_begin = (int)((int64_t)rank * p.T / p.ctas_per_pair);
-  const int t_end = (int)((int64_t)(rank + 1) * p.T / p.ctas_per_pair);
-  auto next_seg = [&](int& t, int& n, int& iy, int& iz, int& xa, int& xb) -> bool {
-    if (t >= t_end) return false;
-    const int col = t / p.X;
-    xa = t - col * p.X;
-    xb = min(p.X, xa + (t_end - t));
+  // k-th segment / work unit of this CTA (see PlaneSplit in common.cuh)
+  auto next_seg = [&](int& it, int& n, int& iy, int& iz, int& xa, int& xb) -> bool {
+    int col;
+    if (!plane_split_next(p.split, rank, p.ctas_per_pair, it, col, xa, xb)) return false;
     iz = col % p.nz;
     const int r = col / p.nz;
     iy = r % p.ny;
     n = r / p.ny;
-    t += xb - xa;
+    ++it;
     return true;
   };
 
@@ -126,7 +120,7 @@ __global__ void __launch_bounds__(kThreadsW2, 1) conv3d_wgrad_march2_kernel(cons
     pdl_launch_dependents();
     const uint32_t x_bytes = (uint32_t)(kBY + 128 / p.kcx - 1) * kBZ * (uint32_t)p.kcx * 2u;
     uint32_t sidx = 0, sph = 0;
-    for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
+    for (int it = 0, n, iy, iz, xa, xb; next_seg(it, n, iy, iz, xa, xb);) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       for (int xi = x_first; xi <= x_last; ++xi) {
         mbar_wait(xempty_bar(sidx), sph ^ 1u);
@@ -143,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsW2, 1) conv3d_wgrad_march2_kernel(cons
     pdl_wait();
     const uint32_t dy_bytes = 3u * tile;
     uint32_t dcount = 0;
-    for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
+    for (int it = 0, n, iy, iz, xa, xb; next_seg(it, n, iy, iz, xa, xb);) {
       for (int xo = xa; xo < xb; ++xo, ++dcount) {
         const uint32_t slot = dcount % R;
         mbar_wait(dyempty_bar(slot), ((dcount / R) & 1u) ^ 1u);
@@ -173,7 +167,7 @@ __global__ void __launch_bounds__(kThreadsW2, 1) conv3d_wgrad_march2_kernel(cons
     mbar_wait(zero_bar, 0);
     tc_fence_after();
     uint32_t sidx = 0, sph = 0, dcount = 0, dwaited = 0;
-    for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
+    for (int it = 0, n, iy, iz, xa, xb; next_seg(it, n, iy, iz, xa, xb);) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       for (int xi = x_first; xi <= x_last; ++xi) {
         const int lo = max(xa, xi - 1), hi = min(xb - 1, xi + 1);  // output planes paired with input plane xi
@@ -232,7 +226,7 @@ __global__ void __launch_bounds__(kThreadsW2, 1) conv3d_wgrad_march2_kernel(cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       uint32_t dcount = 0;
-      for (int t = t_begin, n, iy, iz, xa, xb; next_seg(t, n, iy, iz, xa, xb);) {
+      for (int it = 0, n, iy, iz, xa, xb; next_seg(it, n, iy, iz, xa, xb);) {
         for (int xo = xa; xo < xb; ++xo, ++dcount) {
           const uint32_t slot = dcount % R;
           mbar_wait(dyfull_bar(slot), (dcount / R) & 1u);
@@ -351,9 +345,10 @@ int k_conv3d_wgrad_march2(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_
   p.db = db;
   const int pairs = p.n_ci * p.n_co;
   const int cols = N * p.ny * p.nz;
-  p.T = cols * X;
-  // equal contiguous ranges of plane-tiles per CTA (see the kernel), at least 4 planes each
-  p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, p.T / 4));
+  // CTAs per (ci, co) pair: at least 4 planes each; work units dealt as PlaneSplit describes (common.cuh)
+  p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, cols * X / 4));
+  plane_split_setup(&p.split, cols, X, p.ctas_per_pair, 1.0);
+  if (p.split.mode == 1) p.ctas_per_pair = std::min(p.ctas_per_pair, cols * p.split.nxc);
   FM_TRY(make_map2(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));
   FM_TRY(make_map2(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy));
   // shared memory: S slab slots of 10 KB + (R + 2) plane slots of three tiles (24 KB at 32 channels, 12 KB at 16)
