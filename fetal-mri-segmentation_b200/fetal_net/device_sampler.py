@@ -78,6 +78,10 @@ class PatchDraws:
     def _truth_patch(self, case, corner, index, size):
         """get_patch_from_3d_data(truth, patch_shape[:-1] + (size,), corner + (0, 0, index)) by clamped indices."""
         t = self._truth[case]
+        lo = (corner[0], corner[1], corner[2] + index)
+        hi = (lo[0] + self.patch_shape[0], lo[1] + self.patch_shape[1], lo[2] + size)
+        if min(lo) >= 0 and all(h <= n for h, n in zip(hi, t.shape)):
+            return t[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]        # inside the volume: a view, no gather
         ix = np.clip(np.arange(corner[0], corner[0] + self.patch_shape[0]), 0, t.shape[0] - 1)
         iy = np.clip(np.arange(corner[1], corner[1] + self.patch_shape[1]), 0, t.shape[1] - 1)
         iz = np.clip(np.arange(corner[2] + index, corner[2] + index + size), 0, t.shape[2] - 1)
