@@ -2518,8 +2518,16 @@ extern "C" int fm_train_step_sampled(fm_model* m, fm_volset* s, const int32_t* c
                                prev_truth_size, m->x_in.p, m->t_in.p));
   FM_TRY(train_forward_dev(m, batch));
   if (ctx->comm && ctx->comm_size > 1) return dp_step_after_forward(m, lr, out_metrics);
+  if (!pipeline_enabled()) {
+    FM_TRY(fm_train_backward(m));
+    return fm_train_apply(m, lr, 0, out_metrics);
+  }
+  // like fm_train_step: return as soon as the statistics of THIS forward pass are on the host; backward, Adam and the
+  // repack keep running while the caller draws the next batch
+  FM_TRY(fm_train_metrics_async(m));
   FM_TRY(fm_train_backward(m));
-  return fm_train_apply(m, lr, 0, out_metrics);
+  FM_TRY(fm_train_apply(m, lr, 0, nullptr));
+  return fm_train_metrics_wait(m, out_metrics);
 }
 
 static int dp_step_after_forward(fm_model* m, float lr, float out_metrics[4]) {

@@ -64,11 +64,18 @@ __device__ __forceinline__ float gauss(uint32_t seed, uint32_t idx) {
 
 // args per sample: int32 [8] = {case, cx, cy, cz, flip bits (1: x, 2: y, 4: z), noise seed, bits of scale, bits of sigma}
 // x: [B][P0][P1][P2 + prev_size] (data patch | previous-truth slices), y: [B][P0][P1][truth_size]
+// Batches of up to kInlineSamples samples carry their arguments in the kernel parameters (no staging buffer, no
+// synchronisation with the previous step); larger ones read them from `args`.
+constexpr int kInlineSamples = 64;
+struct SampleArgs {
+  int32_t v[kInlineSamples * 8];
+};
 __global__ void __launch_bounds__(kThreadsS) sample_patches_kernel(const fm_volset::DevCase* __restrict__ cases,
-                                                                   const int32_t* __restrict__ args, SampleGeom gm,
+                                                                   const int32_t* __restrict__ args,
+                                                                   const __grid_constant__ SampleArgs inl, SampleGeom gm,
                                                                    float* __restrict__ x, float* __restrict__ y) {
   const int b = blockIdx.y;
-  const int32_t* a = args + b * 8;
+  const int32_t* a = args != nullptr ? args + b * 8 : inl.v + b * 8;
   const fm_volset::DevCase cs = cases[a[0]];
   const int cx = a[1], cy = a[2], cz = a[3], flip = a[4];
   const uint32_t seed = (uint32_t)a[5];
@@ -189,11 +196,16 @@ int sampler_gather_device(fm_volset* s, const int32_t* cases, const int32_t* cor
              "sampler: case %d of sample %d is not loaded", cases[b], b);
   }
   FM_TRY(build_table(s));
-  // per-sample arguments go through a small pinned staging area (async copy, reused next step)
+  // per-sample arguments: inside the kernel parameters for ordinary batches (the call never waits for the previous
+  // step, which is still in its backward pass when the next batch is drawn); through a pinned staging area otherwise
+  SampleArgs inl;
+  const bool inline_args = batch <= kInlineSamples;
   void* pin = nullptr;
-  FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous step's copy out of the staging area has completed
-  FM_TRY(fm_ctx_pinned(ctx, (size_t)batch * 32, &pin));
-  int32_t* h = (int32_t*)pin;
+  if (!inline_args) {
+    FM_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous step's copy out of the staging area has completed
+    FM_TRY(fm_ctx_pinned(ctx, (size_t)batch * 32, &pin));
+  }
+  int32_t* h = inline_args ? inl.v : (int32_t*)pin;
   for (int b = 0; b < batch; ++b) {
     h[b * 8] = cases[b];
     h[b * 8 + 1] = corners[b * 3];
@@ -205,13 +217,15 @@ int sampler_gather_device(fm_volset* s, const int32_t* cases, const int32_t* cor
     memcpy(&h[b * 8 + 6], &scale, 4);
     memcpy(&h[b * 8 + 7], &sigma, 4);
   }
-  if (s->d_args_cap < (size_t)batch * 8) {
-    if (s->d_args) cudaFree(s->d_args);
-    s->d_args = nullptr;
-    FM_CUDA(cudaMalloc((void**)&s->d_args, (size_t)batch * 32));
-    s->d_args_cap = (size_t)batch * 8;
+  if (!inline_args) {
+    if (s->d_args_cap < (size_t)batch * 8) {
+      if (s->d_args) cudaFree(s->d_args);
+      s->d_args = nullptr;
+      FM_CUDA(cudaMalloc((void**)&s->d_args, (size_t)batch * 32));
+      s->d_args_cap = (size_t)batch * 8;
+    }
+    FM_CUDA(cudaMemcpyAsync(s->d_args, h, (size_t)batch * 32, cudaMemcpyHostToDevice, ctx->stream));
   }
-  FM_CUDA(cudaMemcpyAsync(s->d_args, h, (size_t)batch * 32, cudaMemcpyHostToDevice, ctx->stream));
   SampleGeom gm;
   for (int a = 0; a < 3; ++a) gm.patch[a] = patch[a];
   gm.truth_index = truth_index;
@@ -222,7 +236,8 @@ int sampler_gather_device(fm_volset* s, const int32_t* cases, const int32_t* cor
   const int64_t per = (int64_t)patch[0] * patch[1] * (gm.x_pitch + truth_size);
   const dim3 grid((unsigned)std::min<int64_t>(ceil_div64(per, kThreadsS), 4096), (unsigned)batch);
   ProfScope prof(ctx, "sample_patches", 0.0, (double)batch * per * 8.0);
-  sample_patches_kernel<<<grid, kThreadsS, 0, ctx->stream>>>(s->table, s->d_args, gm, x_dev, y_dev);
+  sample_patches_kernel<<<grid, kThreadsS, 0, ctx->stream>>>(s->table, inline_args ? nullptr : s->d_args, inl, gm, x_dev,
+                                                             y_dev);
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
