@@ -2532,6 +2532,8 @@ extern "C" int fm_train_step_sampled(fm_model* m, fm_volset* s, const int32_t* c
 
 static int dp_step_after_forward(fm_model* m, float lr, float out_metrics[4]) {
   fm_ctx* ctx = m->ctx;
+  FM_CHECK(!m->batch_norm, FM_EINVAL,
+           "data-parallel step: batch_normalization=True needs batch statistics over the GLOBAL batch (not built)");
   // 8 float64: the GLOBAL Dice statistics every rank back-propagates (64 bytes; latency only)
   FM_TRY(comm_allreduce(ctx, m->sums, kNumLossSums, 1, ctx->stream));
   FM_TRY(fm_train_metrics_async(m));

@@ -76,7 +76,10 @@ class DataParallelTrainer:
         _lib.check(self.lib.fm_comm_broadcast_params(self.model._h, int(src)))
 
     def train_on_batch(self, x, y):
-        """x, y: this rank's shard of the global batch. Returns the GLOBAL [loss, acc, vod]."""
+        """x, y: this rank's shard of the global batch ([x, weight_mask] for a two-input model). Returns the GLOBAL
+        [loss, acc, vod(, dice)]."""
+        self.model._check_loss()
+        x = self.model._split_mask(x)
         x, y = _lib.f32c(x), _lib.f32c(y)
         m = np.zeros(4, np.float32)
         _lib.check(self.lib.fm_train_step_dp(self.model._h, _lib.fptr(x), _lib.fptr(y), int(x.shape[0]),
