@@ -442,6 +442,7 @@ int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize
 // db (optional): the bias gradient [Cout] = column sums of dY, accumulated (atomics) by the same launch
 int k_conv3d_wgrad_march(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
                          int Cin, int Cin_total, int cin_ofs, int Cout, float* db = nullptr);
-// second generation (conv_wgrad_march2.cu): one X slab per plane, the kz shift on z-shifted dY copies (N = 192 + 96)
-int k_conv3d_wgrad_march2(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
+// alternative (conv_wgrad_march3.cu, FETAL_B200_WGRAD_GEN=3): one z-haloed X slab per plane, the kz tap as a
+// descriptor start offset
+int k_conv3d_wgrad_march3(fm_ctx*, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
                          int Cin, int Cin_total, int cin_ofs, int Cout, float* db = nullptr);

@@ -1,28 +1,16 @@
-// conv_wgrad_march.cu — plane-marching weight gradient of Conv3D 3x3x3 on tcgen05:
+// conv_wgrad_march3.cu — the plane-marching weight gradient (conv_wgrad_march.cu) with ONE X slab per input plane.
 //
-//     dW[kx,ky,kz][ci][co] = sum_v  X[v + (kx-1, ky-1, kz-1)][ci] * dY[v][co]
-//
-// GEMM view per CTA: M = (ky, ci) stacked to 128 rows, N = (kx, co) stacked to 96 columns, K = voxels.
-// Both operands are MN-major (channels are contiguous in memory, voxels are the K axis).
-//   * A CTA owns a 16 (y) x 8 (z) column of the volume and marches along x, exactly like the forward
-//     marching kernel (conv_march.cu): per input plane it loads three z-shifted, y-haloed slabs of X
-//     (19 x 8 rows x 32 channels) and one dY tile per output plane (128 rows x 32 channels).
-//   * the three ky taps are the M-blocks of ONE UMMA A operand: block j starts 8 slab rows (= one swizzle
-//     atom) after block j-1, which is expressed by the descriptor's leading-byte-offset == stride-byte-offset.
-//     (M = 128 holds four 32-channel blocks; the fourth reads one more halo row and is discarded.)
-//   * the three kx taps are the N-blocks of the B operand: the dY tiles of output planes xi-1, xi, xi+1 sit
-//     in consecutive slots of a ring, leading-byte-offset = slot size.
-//   * kz selects the slab copy; each copy has its own MMA-issuing warp and its own TMEM accumulator, which
-//     stays resident for the CTA's whole lifetime (persistent CTA over many columns) and is flushed with
-//     fp32 red.add once at the end.
-// One CTA handles one (32 input channels x 32 output channels) pair; pairs are spread over the grid.
-// Round 2: (1) three TMA producer warps (one per kz slab copy; warp 0 also feeds the dY ring) - a single producer
-// walking 4 barrier waits + 4 TMA issues per plane was the pacing role; (2) the dY ring has two MIRROR slots (slots
-// 8, 9 repeat 0, 1, loaded by a second TMA), so the three consecutive N blocks of a plane never wrap and every k-step
-// is ONE MMA (the wrap used to split a quarter of them into an N = 64 and an N = 32 MMA that read A twice); (3) the
-// bias gradient (column sums of dY) is folded in: the four epilogue warps, idle during the march, sum the dY tiles
-// they find in shared memory - the separate bias_grad pass over every dY tensor is gone.
-// TF autodiff gradient of Conv3D in create_convolution_block (fetal_net/model/unet3d/unet.py:102).
+// The ablation of the first generation (FETAL_B200_WGRAD_DEBUG=2: everything but the MMAs) runs at 0.70 us per plane
+// and CTA against 0.92 us for the whole kernel and 0.61 us of pure tensor-pipe time: the kernel is bound by the
+// L2 -> shared-memory fill of its operands, 39 KB per plane and CTA, of which 29 KB are the THREE z-shifted copies of
+// the same X slab (the kz tap of conv_wgrad_march.cu is a slab copy). Here the slab is loaded once WITH a z halo -
+// box (channels, 10 z, 19 y): y-row r of the slab holds z = z0-1 .. z0+8 - and the kz tap is a START-ADDRESS offset
+// of kz rows (64 B) on the A descriptor; a y-row is 10 rows long, so the ky M-blocks and the 8-voxel K groups sit
+// 640 B apart (LBO = SBO = 10 rows) instead of one 512-byte swizzle atom. That relies on the swizzle being a function of
+// the absolute shared-memory address bits on both sides (TMA write, UMMA read) - the parity tests are the proof.
+// Fill traffic per plane: 12 KB (slab) + 10 KB (dY + mirror) instead of 39 KB.
+// Everything else (dY ring with mirror slots, one accumulator and one issuing warp per kz, bias gradient folded in,
+// work split) is the first generation's.
 #include <algorithm>
 
 #include "tc_ptx.cuh"
@@ -37,14 +25,14 @@ constexpr int kBY = 16, kBZ = 8;
 constexpr int kCC = 32;                                   // channels per operand block (64 B rows, SWIZZLE_64B)
 constexpr uint32_t kRow = kCC * 2;                        // 64 B
 constexpr uint32_t kSbo = 8 * kRow;                       // 512 B: one y row of 8 voxels = one swizzle atom
-constexpr uint32_t kXSlabRows = (kBY + 3) * kBZ;          // 19 y rows: 16 + halo + the discarded 4th block
-constexpr uint32_t kXSlot = 10240;                        // 9728 B rounded up to 1 KB
+constexpr int kXZ = kBZ + 2;                              // rows per y-row of the slab: 8 z + one halo voxel each side
+constexpr uint32_t kXSlot = 12288;                        // 19 y x 10 z rows x 64 B = 12160 B rounded up to 1 KB
 constexpr uint32_t kDyTile = kBY * kBZ * kRow;            // 8192 B
 constexpr int kDyRing = 8;
 constexpr int kDyMirror = 2;                              // slots 8, 9 repeat slots 0, 1
 constexpr int kNcols = 96;                                // (kx, co) columns per accumulator
 
-struct alignas(64) WgMarchParams {
+struct alignas(64) WgMarch3Params {
   CUtensorMap tmX;   // box (32, 8, 19, 1, 1)
   CUtensorMap tmDY;  // box (32, 8, 16, 1, 1)
   int N, X, Y, Z;
@@ -52,7 +40,7 @@ struct alignas(64) WgMarchParams {
   PlaneSplit split;      // how the (column, x) plane-tiles are dealt to the CTAs of a pair (common.cuh)
   int n_ci, n_co;      // 32-channel chunks of Cin (this source) and Cout
   int ctas_per_pair;   // grid = n_ci * n_co * ctas_per_pair
-  int S3;              // X slab slots per kz ring
+  int S3;              // X slab slots (one ring shared by the three kz issuing warps)
   int kcx;             // input channels per CTA / per M block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cin = 16)
   int kcy;             // output channels per CTA / per N block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cout = 16)
   int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
@@ -61,15 +49,15 @@ struct alignas(64) WgMarchParams {
   int debug;           // FETAL_B200_WGRAD_DEBUG ablation bits (timing only): 1 skip the flush atomics, 2 skip the MMAs
 };
 
-__global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const __grid_constant__ WgMarchParams p) {
+__global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march3_kernel(const __grid_constant__ WgMarch3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const uint32_t x_base = smem0;                                        // 3 * S3 slab slots
-  const uint32_t dy_base = x_base + 3u * (uint32_t)p.S3 * kXSlot;        // kDyRing tiles
+  const uint32_t x_base = smem0;                                        // S3 slab slots
+  const uint32_t dy_base = x_base + (uint32_t)p.S3 * kXSlot;             // kDyRing tiles
   const uint32_t bar0 = dy_base + (uint32_t)(kDyRing + kDyMirror) * kDyTile;
-  const int nx = 3 * p.S3;
+  const int nx = p.S3;
   auto xfull_bar = [&](uint32_t s) { return bar0 + 8u * s; };
   auto xempty_bar = [&](uint32_t s) { return bar0 + 8u * ((uint32_t)nx + s); };
   auto dyfull_bar = [&](uint32_t s) { return bar0 + 8u * ((uint32_t)(2 * nx) + s); };
@@ -91,7 +79,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     if (lane == 0) {
       for (int s = 0; s < nx; ++s) {
         mbar_init(xfull_bar(s), 1);
-        mbar_init(xempty_bar(s), 1);
+        mbar_init(xempty_bar(s), 3);   // the three kz issuing warps read the same slab
       }
       for (int s = 0; s < kDyRing; ++s) {
         mbar_init(dyfull_bar(s), 1);
@@ -125,15 +113,16 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
   };
 
   if (warp_u < kProdW) {
-    // ===== TMA producers: warp kz loads the kz-shifted X slab of every plane; warp 0 also the dY tiles =====
-    const int dz = warp_u;
+    // ===== TMA producer: warp 0 loads the z-haloed X slab of every plane and the dY tiles (warps 1, 2 have no role) =====
+    if (warp_u != 0) goto done;
+    const int dz = 0;
     pdl_wait();  // x and dY come from the previous kernels in the stream
-    if (dz == 0) pdl_launch_dependents();
-    const uint32_t x_bytes = (uint32_t)(kBY + 128 / p.kcx - 1) * kBZ * (uint32_t)p.kcx * 2u;  // slab box bytes
+    pdl_launch_dependents();
+    const uint32_t x_bytes = (uint32_t)(kBY + 128 / p.kcx - 1) * kXZ * (uint32_t)p.kcx * 2u;  // slab box bytes
     const uint32_t dy_bytes = (uint32_t)(kBY * kBZ) * (uint32_t)p.kcy * 2u;
     uint32_t sidx = 0, sph = 0;
     uint32_t dcount = 0;  // dY tiles issued so far (ring position)
-    const uint32_t slot0 = (uint32_t)dz * (uint32_t)p.S3;
+    const uint32_t slot0 = 0;
     for (int it = 0, n, iy, iz, xa, xb; next_seg(it, n, iy, iz, xa, xb);) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       int next_dy = xa;  // next output plane whose dY tile has to be loaded
@@ -154,7 +143,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         const uint32_t stage = slot0 + sidx;
         mbar_wait(xempty_bar(stage), sph ^ 1u);
         mbar_expect_tx_elect(xfull_bar(stage), x_bytes);
-        tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ + dz - 1, iy * kBY - 1, xi, n);
+        tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ - 1, iy * kBY - 1, xi, n);
         if (++sidx == (uint32_t)p.S3) {
           sidx = 0;
           sph ^= 1u;
@@ -172,13 +161,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     const uint32_t b_row = ncy * 2u, b_sbo = 8u * b_row;                     // dY operand: 64- or 32-byte rows
     const uint32_t hi32 = desc_hi(b_sbo, layout_code((int)b_row));
     const uint32_t kstep = (2u * b_sbo) >> 4;  // 16 voxels (two 8-row groups) per MMA, in 16-byte units
-    const uint32_t a_row = (uint32_t)p.kcx * 2u, a_sbo = 8u * a_row;         // X operand: 64- or 32-byte rows
+    // X operand: 64- or 32-byte rows; a y-row of the slab is kXZ = 10 rows long, so the 8-voxel K groups and the ky M
+    // blocks are 10 rows apart, and the kz tap is a start offset of kz rows
+    const uint32_t a_row = (uint32_t)p.kcx * 2u, a_sbo = (uint32_t)kXZ * a_row;
     const uint32_t a_hi32 = desc_hi(a_sbo, layout_code((int)a_row));
     const uint32_t a_kstep = (2u * a_sbo) >> 4;
     mbar_wait(zero_bar, 0);                   // accumulators zeroed by the epilogue warps
     tc_fence_after();
     uint32_t sidx = 0, sph = 0, dcount = 0, dwaited = 0;
-    const uint32_t slot0 = (uint32_t)dz * (uint32_t)p.S3;
+    const uint32_t slot0 = 0;
     for (int it = 0, n, iy, iz, xa, xb; next_seg(it, n, iy, iz, xa, xb);) {
       const int x_first = max(xa - 1, 0), x_last = min(xb, p.X - 1);
       for (int xi = x_first; xi <= x_last; ++xi) {
@@ -196,7 +187,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         // the <= 3 consecutive dY tiles never wrap: slots 8, 9 mirror slots 0, 1
         const uint32_t rs = seq_lo & (uint32_t)(kDyRing - 1);
         const uint32_t idA = nblk == 1 ? idesc1 : (nblk == 2 ? idesc2 : idesc3);
-        uint32_t a_lo = desc_lo(x_base + stage * kXSlot, a_sbo);          // M blocks (ky) one atom apart
+        uint32_t a_lo = desc_lo(x_base + stage * kXSlot + (uint32_t)dz * a_row, a_sbo);  // M blocks (ky) one y-row apart
         uint32_t bA = desc_lo(dy_base + rs * kDyTile, kDyTile);           // N blocks (kx) one ring slot apart
         const uint32_t dA = d_acc + j_lo * ncy;
         if (!(p.debug & 2)) {
@@ -299,6 +290,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
     }
   }
 
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == kMma0) {
@@ -311,7 +303,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                     CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_encode_w() {
+PFN_encodeTiled get_encode_w3() {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -323,13 +315,13 @@ PFN_encodeTiled get_encode_w() {
   return fn;
 }
 
-int make_map(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int by, int cbox) {
-  PFN_encodeTiled enc = get_encode_w();
+int make_map3(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int C, int by, int cbox, int bz) {
+  PFN_encodeTiled enc = get_encode_w3();
   FM_CHECK(enc != nullptr, FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)Z * C * 2, (cuuint64_t)Y * Z * C * 2,
                            (cuuint64_t)X * Y * Z * C * 2};
-  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)kBZ, (cuuint32_t)by, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)cbox, (cuuint32_t)bz, (cuuint32_t)by, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
@@ -338,31 +330,15 @@ int make_map(CUtensorMap* tm, const bf16* base, int N, int X, int Y, int Z, int 
   return FM_OK;
 }
 
-const int kMaxDynSmemW = 227 * 1024;
-const int kDefaultWgradGen = 1;
+const int kMaxDynSmemW3 = 227 * 1024;
 
 }  // namespace
 
-int conv_wgrad_march_supported(int X, int Y, int Z, int Cin, int Cout, int ksize) {
-  if (ksize != 3) return 0;
-  if (Y % kBY != 0 || Z % kBZ != 0 || X < 2) return 0;
-  if (!(Cin % kCC == 0 || Cin == 16) || !(Cout % kCC == 0 || Cout == 16)) return 0;
-  return 1;
-}
-
-int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
+int k_conv3d_wgrad_march3(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_packed, int N, int X, int Y, int Z,
                          int Cin, int Cin_total, int cin_ofs, int Cout, float* db) {
-  {
-    // FETAL_B200_WGRAD_GEN=3 selects the single-slab variant (A/B measurements); see conv_wgrad_march3.cu
-    static const int gen = [] {
-      const char* e = getenv("FETAL_B200_WGRAD_GEN");
-      return e ? atoi(e) : kDefaultWgradGen;
-    }();
-    if (gen == 3) return k_conv3d_wgrad_march3(ctx, x, dy, dw_packed, N, X, Y, Z, Cin, Cin_total, cin_ofs, Cout, db);
-  }
   FM_CHECK(conv_wgrad_march_supported(X, Y, Z, Cin, Cout, 3), FM_EINVAL,
            "conv3d wgrad march: unsupported shape %dx%dx%d Cin=%d Cout=%d", X, Y, Z, Cin, Cout);
-  WgMarchParams p;
+  WgMarch3Params p;
   memset(&p, 0, sizeof(p));
   p.N = N;
   p.X = X;
@@ -391,19 +367,19 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   p.ctas_per_pair = std::max(1, std::min(ctx->num_sms / pairs, cols * X / 4));
   plane_split_setup(&p.split, cols, X, p.ctas_per_pair, 1.0);
   if (p.split.mode == 1) p.ctas_per_pair = std::min(p.ctas_per_pair, cols * p.split.nxc);
-  FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));  // halo + discarded M blocks
-  FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy));
-  p.S3 = 4;
-  const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)(kDyRing + kDyMirror) * kDyTile + 1024 + 512;
+  FM_TRY(make_map3(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx, kXZ));  // y halo + discarded M blocks, z halo
+  FM_TRY(make_map3(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy, kBZ));
+  p.S3 = 6;
+  const size_t smem = (size_t)p.S3 * kXSlot + (size_t)(kDyRing + kDyMirror) * kDyTile + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
-    FM_CUDA(cudaFuncSetAttribute(conv3d_wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kMaxDynSmemW));
+    FM_CUDA(cudaFuncSetAttribute(conv3d_wgrad_march3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMaxDynSmemW3));
     attr_set = true;
   }
   const double vox = (double)N * X * Y * Z;
   ProfScope prof(ctx, "conv3d_wgrad_march", 2.0 * 27 * Cin * Cout * vox, vox * (Cin + Cout) * 2.0);
-  FM_CUDA(launch_pdl(conv3d_wgrad_march_kernel, dim3(pairs * p.ctas_per_pair), dim3(kThreadsW), smem, ctx->stream, p));
+  FM_CUDA(launch_pdl(conv3d_wgrad_march3_kernel, dim3(pairs * p.ctas_per_pair), dim3(kThreadsW), smem, ctx->stream, p));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
 }
