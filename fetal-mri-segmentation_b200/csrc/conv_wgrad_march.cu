@@ -58,7 +58,8 @@ struct alignas(64) WgMarchParams {
   int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
   float* dw;
   float* db;           // bias gradient [Cout] (column sums of dY), or NULL
-  int debug;           // FETAL_B200_WGRAD_DEBUG ablation bits (timing only): 1 skip the flush atomics, 2 skip the MMAs
+  int debug;           // FETAL_B200_WGRAD_DEBUG ablation bits (timing only): 1 skip the flush atomics, 2 skip the MMAs,
+                       // 4 skip every plane (launch skeleton)
 };
 
 __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const __grid_constant__ WgMarchParams p) {
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
   // k-th segment / work unit of this CTA (see PlaneSplit in common.cuh)
   auto next_seg = [&](int& it, int& n, int& iy, int& iz, int& xa, int& xb) -> bool {
     int col;
+    if (p.debug & 4) return false;  // ablation: the launch skeleton only (no planes at all)
     if (!plane_split_next(p.split, rank, p.ctas_per_pair, it, col, xa, xb)) return false;
     iz = col % p.nz;
     const int r = col / p.nz;
