@@ -51,7 +51,7 @@ extern "C" int fm_ctx_create(int device, fm_ctx** out) {
   FM_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
   FM_CUDA(cudaEventCreateWithFlags(&ctx->copy_fence, cudaEventDisableTiming));
   FM_CUDA(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
-  FM_CUDA(cudaMalloc((void**)&ctx->red_scratch, 1024 * 8 * sizeof(double)));
+  FM_CUDA(cudaMalloc((void**)&ctx->red_scratch, kRedScratchRows * 8 * sizeof(double)));
   *out = ctx;
   return FM_OK;
 }

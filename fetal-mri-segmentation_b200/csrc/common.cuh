@@ -64,7 +64,7 @@ struct fm_ctx {
   cudaEvent_t copy_fence = nullptr, copy_done = nullptr;
   int64_t launches = 0;
   // scratch for deterministic two-stage reductions
-  double* red_scratch = nullptr;  // [RED_BLOCKS * 8]
+  double* red_scratch = nullptr;  // [kRedScratchRows][8] per-block partial loss statistics
   // pinned staging for host<->device copies
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -251,6 +251,7 @@ struct XentSpec {
   const float* mask = nullptr;
 };
 constexpr int kNumLossSums = 9;
+constexpr int kRedScratchRows = 4096;  // rows of fm_ctx::red_scratch (one per block of the partial-sum kernels)
 #ifdef __CUDACC__
 // Keras K.binary_crossentropy on probabilities (TF backend): p is clipped to [1e-7, 1 - 1e-7] (fp32), turned back into
 // a logit and fed to sigmoid_cross_entropy_with_logits, i.e. -(t log p + (1 - t) log(1 - p)) on the clipped p; its

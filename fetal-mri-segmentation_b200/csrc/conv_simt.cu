@@ -426,6 +426,71 @@ __global__ void __launch_bounds__(kThreads) head_fwd_dice_kernel(const bf16* __r
   }
 }
 
+// Thread-per-voxel form of the two head kernels for C <= 64 (every model of the BASELINE configs): one thread reads
+// its voxel's C channels with C/8 16-byte loads (the sectors a warp's loads share are consumed back to back out of L1),
+// keeps the weights in registers, and - in the training form - updates the loss statistics for its own voxel. The
+// lanes-per-voxel kernels above spend 13.7 warp instructions per voxel (shuffle folds, and the sigmoid / statistics
+// section runs with one active lane in C/8); this one about 3: they were 60 % issue-bound at 3.3-4.3 TB/s.
+template <int C, bool DICE>
+__global__ void __launch_bounds__(kThreads) head_fwd_tpv_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ b, const float* __restrict__ t,
+                                                                float* __restrict__ p, int64_t voxels, int apply_sigmoid,
+                                                                double* __restrict__ part, XentSpec xs) {
+  FM_PDL_SYNC();
+  float wv[C];
+#pragma unroll
+  for (int i = 0; i < C; ++i) wv[i] = __ldg(w + i);
+  const float bb = __ldg(b);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < voxels; v += (int64_t)gridDim.x * blockDim.x) {
+    uint4 r[C / 8];
+    const uint4* src = reinterpret_cast<const uint4*>(x + v * C);
+#pragma unroll
+    for (int j = 0; j < C / 8; ++j) r[j] = __ldg(src + j);
+    const float tt = DICE ? __ldg(t + v) : 0.f;
+    float acc = bb;
+#pragma unroll
+    for (int j = 0; j < C / 8; ++j) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        acc += f.x * wv[j * 8 + 2 * i] + f.y * wv[j * 8 + 2 * i + 1];
+      }
+    }
+    const float pv = (DICE || apply_sigmoid) ? 1.f / (1.f + __expf(-acc)) : acc;
+    p[v] = pv;
+    if (DICE) {
+      const float pb = pv > 0.5f ? 1.f : 0.f, tb = tt > 0.5f ? 1.f : 0.f;
+      s[0] += tt * pv;
+      s[1] += tt;
+      s[2] += pv;
+      s[3] += tb * pb;
+      s[4] += tb;
+      s[5] += pb;
+      s[6] += (tt == pb) ? 1.f : 0.f;
+      if (xs.weight != 0.f) s[7] += xent_voxel_weight(xs, v) * xent_term(tt, pv);
+    }
+  }
+  if (DICE) {
+    __shared__ double shd[kThreads / 32][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double wsum = (double)s[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+      if (lane == 0) shd[warp][k] = wsum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double a = 0.0;
+      for (int wi = 0; wi < kThreads / 32; ++wi) a += shd[wi][threadIdx.x];
+      part[(int64_t)blockIdx.x * 8 + threadIdx.x] = a;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const bf16* __restrict__ x,
                                                             const float* __restrict__ dz,
                                                             const float* __restrict__ w,
@@ -713,6 +778,21 @@ int k_head_fwd(fm_ctx* ctx, const bf16* x, const float* w, const float* b, float
   const int64_t vpb = kThreads / lpv;
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb), (int64_t)ctx->num_sms * 32);
   ProfScope prof(ctx, "head_fwd", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 4.0));
+  if (C <= 64) {  // thread-per-voxel form
+    const int g2 = (int)std::min<int64_t>(ceil_div64(voxels, kThreads), (int64_t)ctx->num_sms * 16);
+    const XentSpec none;
+    if (C == 16)
+      FM_CUDA(launch_pdl(head_fwd_tpv_kernel<16, false>, dim3(g2), dim3(kThreads), 0, ctx->stream, x, w, b,
+                         (const float*)nullptr, p, voxels, apply_sigmoid, (double*)nullptr, none));
+    else if (C == 32)
+      FM_CUDA(launch_pdl(head_fwd_tpv_kernel<32, false>, dim3(g2), dim3(kThreads), 0, ctx->stream, x, w, b,
+                         (const float*)nullptr, p, voxels, apply_sigmoid, (double*)nullptr, none));
+    else
+      FM_CUDA(launch_pdl(head_fwd_tpv_kernel<64, false>, dim3(g2), dim3(kThreads), 0, ctx->stream, x, w, b,
+                         (const float*)nullptr, p, voxels, apply_sigmoid, (double*)nullptr, none));
+    FM_LAUNCH_OK(ctx);
+    return FM_OK;
+  }
   FM_CUDA(launch_pdl(head_fwd_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, w, b, p, voxels, C, apply_sigmoid));
   FM_LAUNCH_OK(ctx);
   return FM_OK;
@@ -728,6 +808,23 @@ int k_head_fwd_dice(fm_ctx* ctx, const bf16* x, const float* w, const float* b, 
   // one wave of resident blocks (64 registers x 256 threads: 4 blocks per SM): a grid-stride kernel launched with 1024
   // blocks on 592 slots ran 1.73 waves, the second one three-quarters empty
   const int grid = (int)std::min<int64_t>(ceil_div64(voxels, vpb * 4), (int64_t)std::min(1024, 4 * ctx->num_sms));
+  if (C <= 64) {  // thread-per-voxel form; one partial row per block of the reduction scratch
+    const int g2 = (int)std::min<int64_t>(ceil_div64(voxels, kThreads), (int64_t)std::min(kRedScratchRows, 16 * ctx->num_sms));
+    {
+      ProfScope prof(ctx, "head_fwd_dice", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 8.0));
+      if (C == 16)
+        FM_CUDA(launch_pdl(head_fwd_tpv_kernel<16, true>, dim3(g2), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, 1,
+                           ctx->red_scratch, xs));
+      else if (C == 32)
+        FM_CUDA(launch_pdl(head_fwd_tpv_kernel<32, true>, dim3(g2), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, 1,
+                           ctx->red_scratch, xs));
+      else
+        FM_CUDA(launch_pdl(head_fwd_tpv_kernel<64, true>, dim3(g2), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, 1,
+                           ctx->red_scratch, xs));
+      FM_LAUNCH_OK(ctx);
+    }
+    return k_dice_finalize(ctx, g2, (double)voxels, sums);
+  }
   {
     ProfScope prof(ctx, "head_fwd_dice", 2.0 * C * (double)voxels, (double)voxels * (C * 2.0 + 8.0));
     FM_CUDA(launch_pdl(head_fwd_dice_kernel, dim3(grid), dim3(kThreads), 0, ctx->stream, x, w, b, t, p, voxels, C,
