@@ -81,13 +81,13 @@ def ncu_traffic():
 TRAFFIC_KEYS = {
     "train": {"conv3d_wgrad_march": "bwd/conv3d_wgrad_march_kernel", "conv3d_march_fprop": "fwd/conv3d_march2_kernel<1, 32>",
               "conv3d_march_dgrad": "bwd/conv3d_march2_kernel<1, 32>", "maxpool3d_bwd": "bwd/maxpool3d_bwd_kernel<2>",
-              "maxpool3d_fwd": "fwd/maxpool3d_fwd_kernel<2>", "head_fwd_dice": "fwd/head_fwd_dice_kernel",
+              "maxpool3d_fwd": "fwd/maxpool3d_fwd_kernel<2>", "head_fwd_dice": "fwd/head_fwd_tpv_kernel<32, 1>",
               "head_bwd_dice": "bwd/head_bwd_kernel", "upsample3d_fwd": "fwd/upsample3d_fwd_kernel<2>",
               "adam": "bwd/adam_kernel"},
     "infer": {"conv3d_march_fprop": "infer/conv3d_march2_kernel<2, 32>", "conv3d_tc_fprop": "infer/conv3d_tc_fprop_kernel",
               "reassemble": "infer/reassemble4_kernel", "gather_patches": "infer/gather_patches4_kernel",
               "maxpool3d_fwd": "infer/maxpool3d_fwd_kernel<2>", "upsample3d_fwd": "infer/upsample3d_fwd_kernel<2>",
-              "head_fwd": "infer/head_fwd_kernel"},
+              "head_fwd": "infer/head_fwd_tpv_kernel<32, 0>"},
 }
 
 

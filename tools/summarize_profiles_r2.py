@@ -98,7 +98,7 @@ def main():
         recs = full(which)
         json.dump(recs, open(os.path.join(DST, "%s_ncu_key_metrics_%s.json" % (TAG, which)), "w"), indent=0)
         if which == "train":
-            heads = [i for i, d in enumerate(recs) if d["kernel"].startswith("head_fwd_dice")]
+            heads = [i for i, d in enumerate(recs) if d["kernel"].startswith("head_fwd")]
             firsts = [i for i, d in enumerate(recs) if d["kernel"].startswith("conv3d_first_tc_kernel<0>")]
             adams = [i for i, d in enumerate(recs) if d["kernel"].startswith("adam_kernel")]
             # the first complete step of the capture (the 15-minute budget of the capture may cut the last one short)
