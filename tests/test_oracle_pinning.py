@@ -281,3 +281,87 @@ def test_oracle_matches_keras_fixture(tag):
     after = kf.named_weights(z, tag, layers, which="w_after")
     for k in w:
         assert np.abs(w[k] - after[k]).max() <= 2e-6, k
+
+
+# ----------------------------------------------------------------------------------------------
+# independent cross-checks of the network oracle's building blocks (explicit NumPy loops, no torch)
+# ----------------------------------------------------------------------------------------------
+def _naive_conv3d_same(x, kern, bias):
+    """Keras Conv3D(padding='same', strides 1) on channels-first x [C,X,Y,Z] with kernel (k0,k1,k2,Cin,Cout):
+    y[co, p] = b[co] + sum_{t, ci} x[ci, p + t - 1] * kern[t0, t1, t2, ci, co] (cross-correlation, zero padding)."""
+    C, X, Y, Z = x.shape
+    k = kern.shape[0]
+    r = k // 2
+    xp = np.zeros((C, X + 2 * r, Y + 2 * r, Z + 2 * r))
+    xp[:, r:r + X, r:r + Y, r:r + Z] = x
+    y = np.zeros((kern.shape[-1], X, Y, Z))
+    for a in range(k):
+        for b in range(k):
+            for c in range(k):
+                y += np.einsum("cxyz,co->oxyz", xp[:, a:a + X, b:b + Y, c:c + Z], kern[a, b, c])
+    return y + bias[:, None, None, None]
+
+
+def test_unet3d_forward_matches_explicit_numpy_on_a_tiny_network():
+    """depth-2 U-Net on a 4x4x2 volume: conv 'same' with the Keras kernel layout, ReLU, 2^3 max-pool, nearest upsampling,
+    concat order [up, skip] (unet3d/unet.py:61), 1x1x1 head + sigmoid - written out with NumPy loops."""
+    layers = uo.unet3d_layers(2, 2)
+    w = uo.glorot_uniform_weights(layers, seed=3)
+    rng = np.random.default_rng(4)
+    for k_ in w:
+        if k_.endswith("/bias"):
+            w[k_] = rng.standard_normal(w[k_].shape).astype(np.float32) * 0.1
+    x = rng.standard_normal((1, 1, 4, 4, 2))
+    relu = lambda a: np.maximum(a, 0)
+    cb = lambda a, name: relu(_naive_conv3d_same(a, w[name + "/kernel"].astype(np.float64), w[name + "/bias"].astype(np.float64)))
+    e0 = cb(cb(x[0], "enc0a"), "enc0b")
+    pooled = e0.reshape(e0.shape[0], 2, 2, 2, 2, 1, 2).max(axis=(2, 4, 6))
+    e1 = cb(cb(pooled, "enc1a"), "enc1b")
+    up = e1.repeat(2, 1).repeat(2, 2).repeat(2, 3)
+    d0 = cb(cb(np.concatenate([up, e0], axis=0), "dec0a"), "dec0b")
+    logits = np.einsum("cxyz,co->oxyz", d0, w["final/kernel"][0, 0, 0].astype(np.float64)) + w["final/bias"].astype(np.float64)[:, None, None, None]
+    want = 1 / (1 + np.exp(-logits))
+    with torch.no_grad():
+        got = uo.unet3d_forward(torch.as_tensor(x), w, depth=2).numpy()[0]
+    assert np.abs(got - want).max() <= 1e-10
+
+
+def test_deconvolution_and_batch_norm_blocks_match_explicit_numpy():
+    """Deconvolution3D(kernel 2, strides 2) with the Keras Conv3DTranspose kernel (2,2,2,Cout,Cin):
+    y[co, 2i+a, 2j+b, 2k+c] = bias[co] + sum_ci x[ci,i,j,k] K[a,b,c,co,ci]; BatchNormalization(axis=1) in training mode:
+    biased batch variance, eps 1e-3 under the root, moving statistics with momentum 0.99 and Keras' sample-size factor."""
+    rng = np.random.default_rng(5)
+    C = 3
+    x = rng.standard_normal((2, C, 2, 3, 2))
+    kern = rng.standard_normal((2, 2, 2, C, C))
+    bias = rng.standard_normal(C)
+    want = np.zeros((2, C, 4, 6, 4))
+    for a in range(2):
+        for b in range(2):
+            for c in range(2):
+                want[:, :, a::2, b::2, c::2] = np.einsum("ncxyz,oc->noxyz", x, kern[a, b, c])
+    want += bias[None, :, None, None, None]
+    layers = [("enc0a", 1, C, 3)]      # (only the 'up0' entries below are read)
+    w = {"up0/kernel": kern, "up0/bias": bias}
+    kt = torch.as_tensor(kern).permute(4, 3, 0, 1, 2).contiguous()
+    got = torch.nn.functional.conv_transpose3d(torch.as_tensor(x), kt, torch.as_tensor(bias), stride=2).numpy()
+    assert np.abs(got - want).max() <= 1e-12 and layers and w             # the permutation unet3d_forward applies
+    # batch norm
+    y = torch.as_tensor(rng.standard_normal((3, 2, 4, 2, 2)) * 2 + 1)
+    wb = {"b/gamma": np.array([1.5, 0.5]), "b/beta": np.array([0.1, -0.2]), "b/moving_mean": np.array([0.3, 0.0]),
+          "b/moving_variance": np.array([2.0, 1.0])}
+    upd = {}
+    out = uo._batch_norm(y, wb, "b", True, upd).numpy()
+    yn = y.numpy()
+    mean = yn.mean(axis=(0, 2, 3, 4))
+    var = yn.var(axis=(0, 2, 3, 4))
+    ref = (yn - mean[None, :, None, None, None]) / np.sqrt(var + 1e-3)[None, :, None, None, None] * \
+        wb["b/gamma"][None, :, None, None, None] + wb["b/beta"][None, :, None, None, None]
+    assert np.abs(out - ref).max() <= 1e-12
+    n = yn.size // 2
+    assert np.allclose(upd["b/moving_mean"], 0.99 * wb["b/moving_mean"] + 0.01 * mean, rtol=0, atol=1e-12)
+    assert np.allclose(upd["b/moving_variance"], 0.99 * wb["b/moving_variance"] + 0.01 * var * n / (n - 1.001), rtol=0, atol=1e-12)
+    inf = uo._batch_norm(y, wb, "b", False, None).numpy()
+    ref_inf = (yn - wb["b/moving_mean"][None, :, None, None, None]) / np.sqrt(wb["b/moving_variance"] + 1e-3)[None, :, None, None, None] * \
+        wb["b/gamma"][None, :, None, None, None] + wb["b/beta"][None, :, None, None, None]
+    assert np.abs(inf - ref_inf).max() <= 1e-12
