@@ -1,4 +1,6 @@
 #!/bin/bash
+# A/B capture of the marching wgrad against the N = 192 + 96 variant (FETAL_B200_WGRAD_GEN=2). That variant was removed
+# after this measurement (profiles/README.md keeps the numbers); GEN=3 now selects the single-slab variant.
 OUT=gpurun_out
 mkdir -p $OUT; rm -f $OUT/s23_*
 for g in 1 2; do
