@@ -421,16 +421,31 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
       return it_load();
     };
     uint32_t r[NCG][16];
-    uint4 mk[2 * NCG];
+    constexpr bool kDeep = CN <= 32;  // Cout = 64 has no registers to spare for a second plane of mask
+    uint4 mk[2 * NCG], mk1[kDeep ? 2 * NCG : 1];
     bool have = it_load();
     int64_t off = it_off;
     uint32_t g = 0;
-    if (have) {
-      if (has_mask) {
-        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off);
+    // dgrad: the ReLU mask of a plane is requested TWO planes ahead of its use (registers mk -> this plane, mk1 -> the
+    // next one, mk2 in flight): one plane period (~0.8 us) did not cover the DRAM latency under load - the masked
+    // 32 -> 32 launch at 64^3 took 141 us against 88 us for the same shape without a mask.
+    if (have && has_mask) {
+      const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off);
 #pragma unroll
-        for (int h = 0; h < 2 * NCG; ++h) mk[h] = __ldg(mp + h);
+      for (int h = 0; h < 2 * NCG; ++h) mk[h] = __ldg(mp + h);
+    }
+    bool have1 = false;
+    int64_t off1 = 0;
+    if constexpr (kDeep) {
+      have1 = have && it_next();
+      off1 = it_off;
+      if (have1 && has_mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off1);
+#pragma unroll
+        for (int h = 0; h < 2 * NCG; ++h) mk1[h] = __ldg(mp + h);
       }
+    }
+    if (have) {
       mbar_wait(tfull0, 0);
       tc_fence_after();
       if (do_tmem) {
@@ -439,14 +454,14 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
       }
     }
     while (have) {
-      const bool have_next = it_next();
-      const int64_t off_next = it_off;
-      // dgrad: the NEXT plane's ReLU mask is requested now, a whole plane ahead of its use
-      uint4 mkn[2 * NCG];
-      if (have_next && has_mask) {
-        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off_next);
+      const bool have_next = kDeep ? have1 : it_next();
+      const bool have2 = kDeep ? (have1 && it_next()) : have_next;  // the plane whose mask is requested now
+      const int64_t off2 = it_off;
+      uint4 mk2[2 * NCG];
+      if (have2 && has_mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off2);
 #pragma unroll
-        for (int h = 0; h < 2 * NCG; ++h) mkn[h] = __ldg(mp + h);
+        for (int h = 0; h < 2 * NCG; ++h) mk2[h] = __ldg(mp + h);
       }
       const uint32_t rb = g & ring_mask;
       const uint32_t taddr = lane_base + rb * Cn;
@@ -505,10 +520,22 @@ __global__ void __launch_bounds__(march2_threads(CN), 1) conv3d_march2_kernel(co
           op[1] = o[c16][1];
         }
       }
-      off = off_next;
+      if constexpr (kDeep) {
+        off = off1;
+        off1 = off2;
 #pragma unroll
-      for (int h = 0; h < 2 * NCG; ++h) mk[h] = mkn[h];
-      have = have_next;
+        for (int h = 0; h < 2 * NCG; ++h) {
+          mk[h] = mk1[h];
+          mk1[h] = mk2[h];
+        }
+        have = have1;
+        have1 = have2;
+      } else {
+        off = off2;
+#pragma unroll
+        for (int h = 0; h < 2 * NCG; ++h) mk[h] = mk2[h];
+        have = have_next;
+      }
       ++g;
     }
   }
