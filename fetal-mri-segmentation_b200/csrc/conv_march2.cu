@@ -653,7 +653,15 @@ int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1
   p.slot = (uint32_t)kSlabRows * (uint32_t)std::max(p.KC[0], p.nsrc > 1 ? p.KC[1] : 0) * 2u;
   p.slot = (p.slot + 1023u) & ~1023u;
   int stages = (kMaxDynSmem2 - 2048 - (int)wofs) / (int)p.slot;
-  stages = std::min(stages, 12) / 3 * 3;  // three private rings (one per dz slab copy)
+  // three private rings (one per dz slab copy), as deep as shared memory allows: the slabs of a plane are requested a
+  // ring-depth ahead of their MMAs, and four planes did not cover the TMA round trip (FETAL_B200_MARCH_STAGES=12 is the
+  // depth of the earlier captures). 36 = what the 1 KB barrier region holds.
+  static const int stage_cap = [] {
+    const char* e = getenv("FETAL_B200_MARCH_STAGES");
+    const int v = e ? atoi(e) : 36;
+    return std::max(3, std::min(v, 36));
+  }();
+  stages = std::min(stages, stage_cap) / 3 * 3;
   FM_CHECK(stages >= 3, FM_EINVAL, "conv3d march2: filter bank leaves no room for the slab rings");
   p.stages = stages;
   const size_t smem = (size_t)wofs + (size_t)stages * p.slot + 2048;

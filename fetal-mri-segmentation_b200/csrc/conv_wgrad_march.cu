@@ -38,7 +38,7 @@ constexpr int kCC = 32;                                   // channels per operan
 constexpr uint32_t kRow = kCC * 2;                        // 64 B
 constexpr uint32_t kSbo = 8 * kRow;                       // 512 B: one y row of 8 voxels = one swizzle atom
 constexpr uint32_t kXSlabRows = (kBY + 3) * kBZ;          // 19 y rows: 16 + halo + the discarded 4th block
-constexpr uint32_t kXSlot = 10240;                        // 9728 B rounded up to 1 KB
+constexpr uint32_t kXSlotBytes = 9728;                    // 19 y rows x 512 B: a multiple of the 512-byte swizzle period
 constexpr uint32_t kDyTile = kBY * kBZ * kRow;            // 8192 B
 constexpr int kDyRing = 8;
 constexpr int kDyMirror = 2;                              // slots 8, 9 repeat slots 0, 1
@@ -53,6 +53,7 @@ struct alignas(64) WgMarchParams {
   int n_ci, n_co;      // 32-channel chunks of Cin (this source) and Cout
   int ctas_per_pair;   // grid = n_ci * n_co * ctas_per_pair
   int S3;              // X slab slots per kz ring
+  uint32_t xslot;      // bytes between slab slots
   int kcx;             // input channels per CTA / per M block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cin = 16)
   int kcy;             // output channels per CTA / per N block: 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B, Cout = 16)
   int Ct, cofs;        // dW layout [Cout][27][Ct], this source at channel offset cofs
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const uint32_t x_base = smem0;                                        // 3 * S3 slab slots
-  const uint32_t dy_base = x_base + 3u * (uint32_t)p.S3 * kXSlot;        // kDyRing tiles
+  const uint32_t dy_base = x_base + 3u * (uint32_t)p.S3 * p.xslot;        // kDyRing tiles
   const uint32_t bar0 = dy_base + (uint32_t)(kDyRing + kDyMirror) * kDyTile;
   const int nx = 3 * p.S3;
   auto xfull_bar = [&](uint32_t s) { return bar0 + 8u * s; };
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         const uint32_t stage = slot0 + sidx;
         mbar_wait(xempty_bar(stage), sph ^ 1u);
         mbar_expect_tx_elect(xfull_bar(stage), x_bytes);
-        tma_load_5d_elect(x_base + stage * kXSlot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ + dz - 1, iy * kBY - 1, xi, n);
+        tma_load_5d_elect(x_base + stage * p.xslot, &p.tmX, xfull_bar(stage), cic * p.kcx, iz * kBZ + dz - 1, iy * kBY - 1, xi, n);
         if (++sidx == (uint32_t)p.S3) {
           sidx = 0;
           sph ^= 1u;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) conv3d_wgrad_march_kernel(const 
         // the <= 3 consecutive dY tiles never wrap: slots 8, 9 mirror slots 0, 1
         const uint32_t rs = seq_lo & (uint32_t)(kDyRing - 1);
         const uint32_t idA = nblk == 1 ? idesc1 : (nblk == 2 ? idesc2 : idesc3);
-        uint32_t a_lo = desc_lo(x_base + stage * kXSlot, a_sbo);          // M blocks (ky) one atom apart
+        uint32_t a_lo = desc_lo(x_base + stage * p.xslot, a_sbo);          // M blocks (ky) one atom apart
         uint32_t bA = desc_lo(dy_base + rs * kDyTile, kDyTile);           // N blocks (kx) one ring slot apart
         const uint32_t dA = d_acc + j_lo * ncy;
         if (!(p.debug & 2)) {
@@ -406,8 +407,16 @@ int k_conv3d_wgrad_march(fm_ctx* ctx, const bf16* x, const bf16* dy, float* dw_p
   if (p.split.mode == 1) p.ctas_per_pair = std::min(p.ctas_per_pair, cols * p.split.nxc);
   FM_TRY(make_map(&p.tmX, x, N, X, Y, Z, Cin, kBY + 128 / p.kcx - 1, p.kcx));  // halo + discarded M blocks
   FM_TRY(make_map(&p.tmDY, dy, N, X, Y, Z, Cout, kBY, p.kcy));
-  p.S3 = 4;
-  const size_t smem = (size_t)3 * p.S3 * kXSlot + (size_t)(kDyRing + kDyMirror) * kDyTile + 1024 + 512;
+  // five slab slots per kz ring, packed at the slab's own 9728 bytes (512-byte aligned: enough for SWIZZLE_64B / 32B,
+  // whose pattern repeats every 512 / 256 bytes of shared-memory address); FETAL_B200_WGRAD_S3=4 is the 1 KB-aligned
+  // four-slot layout of the earlier captures
+  static const int s3_env = [] {
+    const char* e = getenv("FETAL_B200_WGRAD_S3");
+    return e ? atoi(e) : 5;
+  }();
+  p.S3 = s3_env == 4 ? 4 : 5;
+  p.xslot = p.S3 == 4 ? 10240u : kXSlotBytes;
+  const size_t smem = (size_t)3 * p.S3 * p.xslot + (size_t)(kDyRing + kDyMirror) * kDyTile + 1024 + 512;
   static bool attr_set = false;
   if (!attr_set) {
     FM_CUDA(cudaFuncSetAttribute(conv3d_wgrad_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -8,6 +8,8 @@ tail -3 $OUT/s44_ops.log
 ( timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_prediction.py -q -m gpu -x -p no:cacheprovider ) > $OUT/s44_model.log 2>&1
 tail -3 $OUT/s44_model.log
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --workload train > $OUT/s44_bench.json 2> $OUT/s44_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/s44_launches_train.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload train > $OUT/s44_ncu_train.log 2>&1
 python - <<'PY'
 import json
 d=json.loads([l for l in open('gpurun_out/s44_bench.json') if l.startswith('{')][-1])
