@@ -89,8 +89,8 @@ __device__ __forceinline__ void issue_chunk_nk(int nk, uint32_t col, uint32_t a_
 //   2  three warps take whole planes in turn (plane t -> warp t mod 3); a token (mbarrier) passes from the warp that
 //      has issued plane t to the owner of plane t + 1, so the MMAs reach the pipe in the order of mode 0
 //      (bit-reproducible) while barrier waits, descriptor arithmetic and commits of neighbouring planes overlap.
-// (An unordered plane-owner variant with four warps was measured too: no faster than mode 1, and it needs every plane
-// in flight to fit in the slab rings - it is not built.)
+// (Unordered plane-owner variants - mode 2 without the token, three and four warps - were measured twice, with 4-deep and
+// with 6- to 12-deep slab rings: no faster than mode 1 on any layer (profiles/README.md); they are not built.)
 // In mode 2 an accumulator block receives MMAs of three different threads (planes b-1, b, b+1): every plane
 // owner commits to the tfull barrier of each block it fed (tcgen05.commit tracks the executing thread's MMAs only),
 // and the owner of the centre plane stands in for a neighbour plane that does not exist at the volume boundary.
@@ -651,7 +651,9 @@ int k_conv3d_march2(fm_ctx* ctx, const bf16* x1, const bf16* x2, const bf16* wm1
   p.w_region = wofs;
   // slot = one slab at the widest K chunk in use (18 KB at KC = 64, 9 KB when every source runs at KC <= 32)
   p.slot = (uint32_t)kSlabRows * (uint32_t)std::max(p.KC[0], p.nsrc > 1 ? p.KC[1] : 0) * 2u;
-  p.slot = (p.slot + 1023u) & ~1023u;
+  // slots start on a multiple of the swizzle period: 1 KB for 128-byte rows, 512 B (256 B) for 64- (32-) byte rows
+  const uint32_t slot_align = std::max(p.KC[0], p.nsrc > 1 ? p.KC[1] : 0) >= 64 ? 1024u : 512u;
+  p.slot = (p.slot + slot_align - 1u) & ~(slot_align - 1u);
   int stages = (kMaxDynSmem2 - 2048 - (int)wofs) / (int)p.slot;
   // three private rings (one per dz slab copy), as deep as shared memory allows: the slabs of a plane are requested a
   // ring-depth ahead of their MMAs, and four planes did not cover the TMA round trip (FETAL_B200_MARCH_STAGES=12 is the
